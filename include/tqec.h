@@ -1,0 +1,160 @@
+/* libtqec_cuda.so -- C ABI of the B200-native TNMAP / TNMMAP decoding hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes, returns 0 (TQEC_OK) or a negative error code,
+ * and records a message retrievable with tqec_last_error() (thread-local).  The caller owns all host buffers; the
+ * library owns device memory behind opaque handles.  A handle is bound to ONE device and is not re-entrant
+ * (the reference's compiled decoders are not thread-safe either: src/decoding/tndecoder.jl:52); different handles
+ * are independent.  `*_dev` variants take DEVICE pointers and enqueue on the given cudaStream_t (passed as void*)
+ * without synchronising; the plain variants take HOST pointers and return when the results are in host memory.
+ *
+ * Bit-packed layout (all GF(2) data): SHOT-MAJOR, ceil(nbits/64) uint64 words per shot, bit k of word w is bit
+ * 64*w + k -- the `compresscol` layout of the reference's own packed product (src/codes/mod2.jl:58-71).
+ *
+ * Reference interfaces replaced (paths relative to the reference repo, TensorQEC.jl v2.2.1):
+ *   tqec_plan_create        compile(::TNMAP, ::GeneralDecodingProblem)                 src/decoding/tndecoder.jl:46-50
+ *                           compile(::TNMMAP, ::IndependentDepolarizingDecodingProblem) src/decoding/tndecoder.jl:97-146
+ *                           compile(::TNMMAP, ::DetectorErrorModel)                     src/decoding/tndecoder.jl:186-219
+ *                           (the contraction order found by OMEinsum's optimize_code becomes the step order)
+ *   tqec_decode_map         decode(::CompiledTNMAP, ::SimpleSyndrome)                   src/decoding/tndecoder.jl:53-57
+ *   tqec_decode_marginal    update_syndrome! + ct.code(ct.tensors...) + findmax         src/decoding/tndecoder.jl:148-165, 240-253
+ *   tqec_coset_rep          error_pattern + _mixed_integer_programming_for_one_solution src/decoding/tndecoder.jl:167-174, 255-271;
+ *                                                                                       src/decoding/ipdecoder.jl:150-169
+ *   tqec_sample_errors      random_error_pattern                                        src/decoding/error_model.jl:69-71, 97-117;
+ *                                                                                       src/decoding/dem.jl:162-164
+ *   tqec_gf2_apply          syndrome_extraction  (model: bitmul!)                       src/decoding/error_model.jl:131-146; src/codes/mod2.jl:44-57
+ *   tqec_logical_flags      check_logical_error                                         src/decoding/error_model.jl:161-163, 179-181
+ *   tqec_mc_run             multi_round_qec (inner loop + counters)                     src/decoding/threshold.jl:1-19
+ */
+#ifndef TQEC_H
+#define TQEC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TQEC_OK 0
+#define TQEC_ERR_INVALID (-1)     /* bad argument / malformed schedule */
+#define TQEC_ERR_CUDA (-2)        /* CUDA runtime error (message has the CUDA string) */
+#define TQEC_ERR_UNSUPPORTED (-3) /* valid request the library cannot serve (e.g. frontier too wide) */
+#define TQEC_ERR_NOMEM (-4)
+
+#define TQEC_SEMIRING_MAXPLUS 0 /* TNMAP : (max, +) on log-weights, with traceback */
+#define TQEC_SEMIRING_SUMPROD 1 /* TNMMAP: (+, *) on weights, open observable axes  */
+
+#define TQEC_HDR_INTS 16
+/* step header fields (int32 each) */
+enum {
+  TQEC_H_R = 0,       /* number of variables of the absorbed factor                                  */
+  TQEC_H_WIN = 1,     /* state width (bits) before the step                                          */
+  TQEC_H_NOPEN = 2,   /* checks opened by the step: they take slots w_in .. w_in+n_open-1            */
+  TQEC_H_NCLOSE = 3,  /* checks closed by the step                                                   */
+  TQEC_H_WOUT = 4,    /* state width after the step = w_in + n_open - n_close                        */
+  TQEC_H_NK = 5,      /* candidates per output element (power of two)                                */
+  TQEC_H_KB = 6,      /* log2(nk) = back-pointer bits per output element                             */
+  TQEC_H_OFF_T = 7,   /* tables[off + pat*nk + k]  : factor value of candidate k for opened pattern  */
+  TQEC_H_OFF_ML = 8,  /* ints[off + pat]           : in-state mask of the coset representative       */
+  TQEC_H_OFF_MK = 9,  /* ints[off + k]             : in-state mask of kernel candidate k             */
+  TQEC_H_OFF_A0 = 10, /* ints[off + pat]           : variable assignment of the coset representative */
+  TQEC_H_OFF_KER = 11,/* ints[off + k]             : variable assignment of kernel candidate k       */
+  TQEC_H_OFF_VARS = 12,/* ints[off + j]            : id of the factor's j-th variable (output bit)    */
+  TQEC_H_OFF_CLOSE = 13/* ints[off + 2c], [off+2c+1]: (slot, syndrome bit) of closed check c, slots ascending */
+};
+
+typedef struct tqec_plan tqec_plan; /* a compiled schedule resident on one device      */
+typedef struct tqec_gf2 tqec_gf2;   /* a bit-packed GF(2) matrix resident on one device */
+
+typedef struct {
+  int32_t semiring;        /* TQEC_SEMIRING_*                                                     */
+  int32_t n_vars;          /* error variables = bits of a decoded configuration                   */
+  int32_t n_checks;        /* syndrome bits per shot                                              */
+  int32_t n_obs;           /* open observable axes (sum-product only); output has 2^n_obs entries */
+  int32_t n_steps;
+  int32_t w_max;           /* widest state (bits) over all steps                                  */
+  const int32_t *hdr;      /* n_steps * TQEC_HDR_INTS                                             */
+  const int32_t *ints;     /* pooled integer tables                                               */
+  int64_t n_ints;
+  const double *tables;    /* pooled FP64 tables: log-weights (max-plus) or weights (sum-product) */
+  int64_t n_tables;
+  const int32_t *obs_slot; /* n_obs: slot of observable i in the final state                      */
+  int32_t device;          /* CUDA device ordinal                                                 */
+} tqec_plan_desc;
+
+const char *tqec_last_error(void);
+int tqec_version(void);
+int tqec_device_count(int32_t *out);
+
+/* ---- schedule --------------------------------------------------------------------------------------------- */
+int tqec_plan_create(const tqec_plan_desc *desc, tqec_plan **out);
+int tqec_plan_destroy(tqec_plan *plan);
+/* launch geometry and per-shot cost the library derived for the plan */
+enum {
+  TQEC_Q_TEAM_THREADS = 0, TQEC_Q_SHOTS_PER_TEAM = 1, TQEC_Q_SMEM_BYTES = 2, TQEC_Q_GRID = 3,
+  TQEC_Q_TEAMS_PER_SM = 4, TQEC_Q_BP_BYTES_PER_TEAM = 5, TQEC_Q_CANDIDATES_PER_SHOT = 6, TQEC_Q_SM_COUNT = 7,
+  TQEC_Q_LAUNCHES = 8 /* kernels launched through this plan so far */
+};
+int tqec_plan_query(const tqec_plan *plan, int32_t what, int64_t *out);
+
+/* ---- decoding --------------------------------------------------------------------------------------------- */
+/* TNMAP: synd = B * ceil(n_checks/64) words; corr_out = B * ceil(n_vars/64) words (bit v = variable v of the most
+ * probable configuration); logp_out (may be NULL) = B log-weights of that configuration (-inf: infeasible). */
+int tqec_decode_map(tqec_plan *plan, const uint64_t *synd, int64_t n_shots, uint64_t *corr_out, double *logp_out);
+int tqec_decode_map_dev(tqec_plan *plan, const uint64_t *d_synd, int64_t n_shots, uint64_t *d_corr, double *d_logp,
+                        void *stream);
+/* TNMMAP: mar_out = B * 2^n_obs weights, entry index = sum_i obs_i << i (observable 0 fastest = the reference's
+ * column-major `mar`, tndecoder.jl:134); argmax_out (may be NULL) = first maximal entry per shot (findmax). */
+int tqec_decode_marginal(tqec_plan *plan, const uint64_t *synd, int64_t n_shots, double *mar_out,
+                         int32_t *argmax_out);
+int tqec_decode_marginal_dev(tqec_plan *plan, const uint64_t *d_synd, int64_t n_shots, double *d_mar,
+                             int32_t *d_argmax, void *stream);
+
+/* ---- GF(2) ------------------------------------------------------------------------------------------------ */
+/* rows x cols matrix, each row packed into ceil(cols/64) words. */
+int tqec_gf2_create(int32_t rows, int32_t cols, const uint64_t *packed_rows, int32_t device, tqec_gf2 **out);
+int tqec_gf2_destroy(tqec_gf2 *m);
+/* out[shot] = M * in[shot] over GF(2): in = B * ceil(cols/64) words, out = B * ceil(rows/64) words. */
+int tqec_gf2_apply(tqec_gf2 *m, const uint64_t *in, int64_t n_shots, uint64_t *out);
+int tqec_gf2_apply_dev(tqec_gf2 *m, const uint64_t *d_in, int64_t n_shots, uint64_t *d_out, void *stream);
+/* Logical check of e1 against e2 (both B * ceil(cols/64) words; e2 may be NULL = zero): row i of L has class
+ * row_class[i] in {0, 1} (0: X-type logical flip, rows of lz acting on the x block; 1: Z-type, rows of lx acting on
+ * the z block).  flags_out (may be NULL) = B bytes, bit 0 / bit 1 = some class-0 / class-1 row has odd parity on
+ * e1 xor e2.  counts (may be NULL) += {#shots with bit 0, #shots with bit 1, #shots with any, #shots}. */
+int tqec_logical_flags(tqec_gf2 *L, const int32_t *row_class, const uint64_t *e1, const uint64_t *e2,
+                       int64_t n_shots, uint8_t *flags_out, int64_t counts[4]);
+/* TNMMAP error pattern: e = R * synd (any solution of H e = synd), then for every observable row i of L whose
+ * parity on e differs from bit i of sector[shot], e ^= fix[i] (fix = the conjugate logical, packed like e).
+ * R: n_vars x n_checks; L, FIX: n_obs x n_vars. */
+int tqec_coset_rep(tqec_gf2 *R, tqec_gf2 *L, tqec_gf2 *FIX, const uint64_t *synd, const int32_t *sector,
+                   int64_t n_shots, uint64_t *err_out);
+
+/* ---- sampling --------------------------------------------------------------------------------------------- */
+#define TQEC_MODEL_FLIP 0  /* IndependentFlipError: bit i flips iff u < p0[i]            (error_model.jl:69-71)  */
+#define TQEC_MODEL_DEPOL 1 /* IndependentDepolarizingError on n qubits: one u per qubit, Y tested first:
+                              u < py -> Y; u < px+py -> X; u < px+py+pz -> Z (error_model.jl:97-117); output has
+                              2n bits: x errors in bits 0..n-1, z errors in bits n..2n-1 (reduce2general order)    */
+/* u = Philox4x32-10(key = seed, counter = (shot, site)) -> 53-bit uniform; shot = shot_offset + local index, so
+ * the sampled errors do not depend on how shots are split over calls / GPUs. p0,p1,p2 = (p) or (px,py,pz). */
+int tqec_sample_errors(int32_t model, int32_t n_sites, const double *p0, const double *p1, const double *p2,
+                       uint64_t seed, int64_t shot_offset, int64_t n_shots, uint64_t *err_out, int32_t device);
+
+/* ---- fused Monte-Carlo pipeline (sample -> syndrome -> decode -> logical check) ---------------------------- */
+typedef struct {
+  tqec_plan *plan;         /* max-plus plan over n_vars variables                     */
+  tqec_gf2 *H;             /* n_checks x n_vars                                        */
+  tqec_gf2 *L;             /* logical rows x n_vars                                    */
+  const int32_t *row_class;
+  int32_t model;           /* TQEC_MODEL_*                                             */
+  int32_t n_sites;         /* qubits (DEPOL: n_vars = 2 n_sites) or bits (FLIP)        */
+  const double *p0, *p1, *p2;
+  int64_t chunk;           /* shots per internal batch (0 = library default)           */
+} tqec_mc_desc;
+/* counts += {logical X-type failures, logical Z-type failures, any failure, shots} over shots
+ * shot_offset .. shot_offset + n_shots - 1.  elapsed_ms (may be NULL) = device time of the whole pipeline. */
+int tqec_mc_run(const tqec_mc_desc *mc, uint64_t seed, int64_t shot_offset, int64_t n_shots, int64_t counts[4],
+                float *elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TQEC_H */

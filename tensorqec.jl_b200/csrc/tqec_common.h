@@ -1,0 +1,92 @@
+// Internal definitions shared by the translation units of libtqec_cuda.so (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "tqec.h"
+
+namespace tqec {
+
+void set_error(const char *fmt, ...);
+
+#define TQEC_CUDA(call)                                                                      \
+  do {                                                                                       \
+    cudaError_t _e = (call);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      tqec::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return TQEC_ERR_CUDA;                                                                  \
+    }                                                                                        \
+  } while (0)
+
+#define TQEC_REQUIRE(cond, ...)        \
+  do {                                 \
+    if (!(cond)) {                     \
+      tqec::set_error(__VA_ARGS__);    \
+      return TQEC_ERR_INVALID;         \
+    }                                  \
+  } while (0)
+
+static inline int words_for(int nbits) { return nbits <= 0 ? 1 : (nbits + 63) / 64; }
+
+// Device view of a compiled schedule (passed to kernels by value).
+struct PlanDev {
+  const int32_t *hdr;      // n_steps * TQEC_HDR_INTS
+  const int32_t *ints;
+  const double *tables;
+  const int32_t *bp_off;   // n_steps + 1: word offset of each step's back-pointer block inside a team's scratch
+  const int32_t *obs_slot; // n_obs
+  int32_t n_steps, n_vars, n_checks, n_obs;
+  int32_t w_max;           // widest state in bits
+  int32_t sg_log2;         // log2(shots per team)
+  int32_t nsw, ncw;        // syndrome / configuration words per shot
+  int32_t bp_words;        // back-pointer words per team
+};
+
+}  // namespace tqec
+
+struct tqec_plan {
+  tqec::PlanDev dev;
+  int device;
+  int semiring;
+  int team_threads;
+  int shots_per_team;
+  int smem_bytes;
+  int grid_max;          // persistent grid size (teams resident on the whole GPU)
+  int teams_per_sm;
+  int sm_count;
+  double candidates_per_shot;
+  int64_t launches;
+  void *d_hdr, *d_ints, *d_tables, *d_bp_off, *d_obs_slot;
+  uint32_t *d_bp;        // back-pointer scratch: grid_max * bp_words
+  // host staging for the host-pointer entry points
+  void *d_io[4];
+  size_t io_cap[4];
+  cudaStream_t stream;
+};
+
+struct tqec_gf2 {
+  int device;
+  int rows, cols;
+  int rw, cw;            // words per packed output (rows) / input (cols)
+  uint64_t *d_rows;      // rows * cw
+  void *d_io[4];
+  size_t io_cap[4];
+  cudaStream_t stream;
+  int64_t launches;
+};
+
+namespace tqec {
+int ensure_cap(void **ptr, size_t *cap, size_t bytes);
+int launch_decode(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d_corr, double *d_out,
+                  int32_t *d_argmax, cudaStream_t stream);
+int launch_gf2_apply(tqec_gf2 *m, const uint64_t *d_in, int64_t B, uint64_t *d_out, cudaStream_t stream);
+int launch_sample(int model, int n_sites, const double *d_p, uint64_t seed, int64_t shot_offset, int64_t B,
+                  uint64_t *d_err, int words, cudaStream_t stream);
+int launch_flags(tqec_gf2 *L, const int32_t *d_row_class, const uint64_t *d_e1, const uint64_t *d_e2, int64_t B,
+                 uint8_t *d_flags, unsigned long long *d_counts, cudaStream_t stream);
+}  // namespace tqec

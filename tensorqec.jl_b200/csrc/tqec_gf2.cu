@@ -1,0 +1,447 @@
+// Bit-packed GF(2) front / back end of the decoding hot path for sm_100a: Philox error sampling, syndrome
+// extraction (popcount-parity mat-vec), logical-error flags + counters, TNMMAP coset representative, and the fused
+// Monte-Carlo pipeline that chains them around the decoder.  All of it is integer work moving < 100 B per shot;
+// one thread owns one shot and keeps its words in registers, matrix rows are staged in shared memory.
+#include <cstring>
+
+#include "tqec_common.h"
+
+namespace tqec {
+
+static thread_local std::string g_err;
+
+void set_error(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+int ensure_cap(void **ptr, size_t *cap, size_t bytes) {
+  if (*cap >= bytes && *ptr) return TQEC_OK;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr;
+  *cap = 0;
+  size_t want = bytes + bytes / 4 + 256;
+  cudaError_t e = cudaMalloc(ptr, want);
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%zu B) failed: %s", want, cudaGetErrorString(e));
+    return TQEC_ERR_NOMEM;
+  }
+  *cap = want;
+  return TQEC_OK;
+}
+
+// ---- Philox4x32-10 ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+  const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+  c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+}
+
+__device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_t shot, uint32_t site) {
+  uint32_t c0 = (uint32_t)shot, c1 = (uint32_t)(shot >> 32), c2 = site, c3 = 0u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c0, c1, c2, c3, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  const uint64_t bits = (((uint64_t)c0 << 32) | c1) >> 11;
+  return (double)bits * (1.0 / 9007199254740992.0);
+}
+
+// one thread per (shot, output word): sites are visited word by word so that every thread writes whole words
+__global__ void k_sample_errors(int model, int n_sites, const double *__restrict__ p, uint64_t seed, int64_t shot_offset,
+                                int64_t B, uint64_t *__restrict__ err, int words) {
+  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (gid >= B * words) return;
+  const int64_t s = gid / words;
+  const int w = (int)(gid - s * words);
+  const uint64_t shot = (uint64_t)(shot_offset + s);
+  uint64_t out = 0;
+  const int nbits = model == TQEC_MODEL_DEPOL ? 2 * n_sites : n_sites;
+  for (int b = 0; b < 64; ++b) {
+    const int bit = w * 64 + b;
+    if (bit >= nbits) break;
+    if (model == TQEC_MODEL_FLIP) {
+      const double u = philox_uniform(seed, shot, (uint32_t)bit);
+      if (u < p[bit]) out |= 1ull << b;
+    } else {
+      const int q = bit < n_sites ? bit : bit - n_sites;
+      const double u = philox_uniform(seed, shot, (uint32_t)q);
+      const double px = p[q], py = p[n_sites + q], pz = p[2 * n_sites + q];
+      // Y first, then X, then Z (error_model.jl:101-115)
+      const bool isY = u < py;
+      const bool isX = !isY && u < px + py;
+      const bool isZ = !isY && !isX && u < px + py + pz;
+      const bool on = bit < n_sites ? (isX || isY) : (isZ || isY);
+      if (on) out |= 1ull << b;
+    }
+  }
+  err[gid] = out;
+}
+
+int launch_sample(int model, int n_sites, const double *d_p, uint64_t seed, int64_t shot_offset, int64_t B,
+                  uint64_t *d_err, int words, cudaStream_t stream) {
+  if (B <= 0) return TQEC_OK;
+  const int64_t n = B * words;
+  const int threads = 256;
+  k_sample_errors<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>(model, n_sites, d_p, seed, shot_offset, B, d_err, words);
+  TQEC_CUDA(cudaGetLastError());
+  return TQEC_OK;
+}
+
+// ---- packed mat-vec: out[shot] = M in[shot] -------------------------------------------------------------------
+template <int CW>
+__global__ void k_gf2_apply(const uint64_t *__restrict__ rowsM, int rows, int cw_rt, int rw, const uint64_t *__restrict__ in,
+                            int64_t B, uint64_t *__restrict__ out) {
+  extern __shared__ uint64_t sh_rows[];
+  const int cw = CW > 0 ? CW : cw_rt;
+  for (int i = threadIdx.x; i < rows * cw; i += blockDim.x) sh_rows[i] = rowsM[i];
+  __syncthreads();
+  const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (s >= B) return;
+  uint64_t x[CW > 0 ? CW : 1];
+  if (CW > 0) {
+#pragma unroll
+    for (int w = 0; w < CW; ++w) x[w] = in[s * CW + w];
+  }
+  for (int ow = 0; ow < rw; ++ow) {
+    uint64_t o = 0;
+    const int r1 = min(rows, (ow + 1) * 64);
+    for (int r = ow * 64; r < r1; ++r) {
+      uint64_t acc = 0;
+      if (CW > 0) {
+#pragma unroll
+        for (int w = 0; w < CW; ++w) acc ^= sh_rows[r * CW + w] & x[w];
+      } else {
+        for (int w = 0; w < cw; ++w) acc ^= sh_rows[r * cw + w] & in[s * cw + w];
+      }
+      o |= (uint64_t)(__popcll(acc) & 1) << (r & 63);
+    }
+    out[s * rw + ow] = o;
+  }
+}
+
+int launch_gf2_apply(tqec_gf2 *m, const uint64_t *d_in, int64_t B, uint64_t *d_out, cudaStream_t stream) {
+  if (B <= 0) return TQEC_OK;
+  const int threads = 128;
+  const unsigned grid = (unsigned)((B + threads - 1) / threads);
+  const size_t smem = (size_t)m->rows * m->cw * 8;
+  if (smem > 48 * 1024) {
+    set_error("GF(2) matrix of %d x %d does not fit the 48 KiB row cache", m->rows, m->cols);
+    return TQEC_ERR_UNSUPPORTED;
+  }
+  switch (m->cw) {
+    case 1: k_gf2_apply<1><<<grid, threads, smem, stream>>>(m->d_rows, m->rows, m->cw, m->rw, d_in, B, d_out); break;
+    case 2: k_gf2_apply<2><<<grid, threads, smem, stream>>>(m->d_rows, m->rows, m->cw, m->rw, d_in, B, d_out); break;
+    case 3: k_gf2_apply<3><<<grid, threads, smem, stream>>>(m->d_rows, m->rows, m->cw, m->rw, d_in, B, d_out); break;
+    case 4: k_gf2_apply<4><<<grid, threads, smem, stream>>>(m->d_rows, m->rows, m->cw, m->rw, d_in, B, d_out); break;
+    default: k_gf2_apply<0><<<grid, threads, smem, stream>>>(m->d_rows, m->rows, m->cw, m->rw, d_in, B, d_out); break;
+  }
+  TQEC_CUDA(cudaGetLastError());
+  m->launches += 1;
+  return TQEC_OK;
+}
+
+// ---- logical flags + counters ---------------------------------------------------------------------------------
+__global__ void k_logical_flags(const uint64_t *__restrict__ rowsM, const int32_t *__restrict__ row_class, int rows, int cw,
+                                const uint64_t *__restrict__ e1, const uint64_t *__restrict__ e2, int64_t B,
+                                uint8_t *__restrict__ flags, unsigned long long *__restrict__ counts) {
+  extern __shared__ uint64_t sh_rows[];
+  __shared__ unsigned int sh_cnt[3];
+  for (int i = threadIdx.x; i < rows * cw; i += blockDim.x) sh_rows[i] = rowsM[i];
+  if (threadIdx.x < 3) sh_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  unsigned f = 0;
+  if (s < B) {
+    for (int r = 0; r < rows; ++r) {
+      uint64_t acc = 0;
+      for (int w = 0; w < cw; ++w) {
+        const uint64_t d = e1[s * cw + w] ^ (e2 ? e2[s * cw + w] : 0ull);
+        acc ^= sh_rows[r * cw + w] & d;
+      }
+      if (__popcll(acc) & 1) f |= 1u << (row_class[r] & 1);
+    }
+    if (flags) flags[s] = (uint8_t)f;
+  }
+  if (counts) {
+    const unsigned m0 = __ballot_sync(0xffffffffu, f & 1u), m1 = __ballot_sync(0xffffffffu, f & 2u),
+                   ma = __ballot_sync(0xffffffffu, f != 0u);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&sh_cnt[0], __popc(m0));
+      atomicAdd(&sh_cnt[1], __popc(m1));
+      atomicAdd(&sh_cnt[2], __popc(ma));
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 && sh_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)sh_cnt[threadIdx.x]);
+  }
+}
+
+int launch_flags(tqec_gf2 *L, const int32_t *d_row_class, const uint64_t *d_e1, const uint64_t *d_e2, int64_t B,
+                 uint8_t *d_flags, unsigned long long *d_counts, cudaStream_t stream) {
+  if (B <= 0) return TQEC_OK;
+  const int threads = 128;
+  const size_t smem = (size_t)L->rows * L->cw * 8;
+  if (smem > 40 * 1024) {
+    set_error("logical matrix of %d x %d does not fit the row cache", L->rows, L->cols);
+    return TQEC_ERR_UNSUPPORTED;
+  }
+  k_logical_flags<<<(unsigned)((B + threads - 1) / threads), threads, smem, stream>>>(L->d_rows, d_row_class, L->rows, L->cw,
+                                                                                     d_e1, d_e2, B, d_flags, d_counts);
+  TQEC_CUDA(cudaGetLastError());
+  L->launches += 1;
+  return TQEC_OK;
+}
+
+// ---- TNMMAP error pattern: e = R s, then move it into the decoded logical sector --------------------------------
+__global__ void k_coset_fix(const uint64_t *__restrict__ Lrows, const uint64_t *__restrict__ Frows, int n_obs, int cw,
+                            const int32_t *__restrict__ sector, int64_t B, uint64_t *__restrict__ err) {
+  const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (s >= B) return;
+  const int sec = sector[s];
+  for (int i = 0; i < n_obs; ++i) {
+    uint64_t acc = 0;
+    for (int w = 0; w < cw; ++w) acc ^= Lrows[i * cw + w] & err[s * cw + w];
+    if ((__popcll(acc) & 1) != ((sec >> i) & 1))
+      for (int w = 0; w < cw; ++w) err[s * cw + w] ^= Frows[i * cw + w];
+  }
+}
+
+}  // namespace tqec
+
+using namespace tqec;
+
+extern "C" const char *tqec_last_error(void) { return g_err.c_str(); }
+extern "C" int tqec_version(void) { return 100; }
+extern "C" int tqec_device_count(int32_t *out) {
+  TQEC_REQUIRE(out, "tqec_device_count: out is NULL");
+  int n = 0;
+  TQEC_CUDA(cudaGetDeviceCount(&n));
+  *out = n;
+  return TQEC_OK;
+}
+
+extern "C" int tqec_gf2_create(int32_t rows, int32_t cols, const uint64_t *packed_rows, int32_t device, tqec_gf2 **out) {
+  TQEC_REQUIRE(out, "tqec_gf2_create: out is NULL");
+  *out = nullptr;
+  TQEC_REQUIRE(rows >= 0 && cols >= 0 && (rows == 0 || packed_rows), "tqec_gf2_create: bad matrix %d x %d", rows, cols);
+  int ndev = 0;
+  TQEC_CUDA(cudaGetDeviceCount(&ndev));
+  TQEC_REQUIRE(device >= 0 && device < ndev, "tqec_gf2_create: device %d not present (%d visible)", device, ndev);
+  TQEC_CUDA(cudaSetDevice(device));
+  tqec_gf2 *m = new tqec_gf2();
+  std::memset(m, 0, sizeof(*m));
+  m->device = device; m->rows = rows; m->cols = cols; m->rw = words_for(rows); m->cw = words_for(cols);
+  const size_t bytes = (size_t)(rows ? rows : 1) * m->cw * 8;
+  cudaError_t e = cudaMalloc((void **)&m->d_rows, bytes);
+  if (e == cudaSuccess && rows) e = cudaMemcpy(m->d_rows, packed_rows, (size_t)rows * m->cw * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    set_error("tqec_gf2_create: %s", cudaGetErrorString(e));
+    tqec_gf2_destroy(m);
+    return TQEC_ERR_CUDA;
+  }
+  *out = m;
+  return TQEC_OK;
+}
+
+extern "C" int tqec_gf2_destroy(tqec_gf2 *m) {
+  if (!m) return TQEC_OK;
+  cudaSetDevice(m->device);
+  cudaFree(m->d_rows);
+  for (int i = 0; i < 4; ++i) cudaFree(m->d_io[i]);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+  return TQEC_OK;
+}
+
+extern "C" int tqec_gf2_apply_dev(tqec_gf2 *m, const uint64_t *d_in, int64_t B, uint64_t *d_out, void *stream) {
+  TQEC_REQUIRE(m && B >= 0 && (B == 0 || (d_in && d_out)), "tqec_gf2_apply: NULL argument");
+  TQEC_CUDA(cudaSetDevice(m->device));
+  return launch_gf2_apply(m, d_in, B, d_out, (cudaStream_t)stream);
+}
+
+extern "C" int tqec_gf2_apply(tqec_gf2 *m, const uint64_t *in, int64_t B, uint64_t *out) {
+  TQEC_REQUIRE(m && B >= 0 && (B == 0 || (in && out)), "tqec_gf2_apply: NULL argument");
+  if (B == 0) return TQEC_OK;
+  TQEC_CUDA(cudaSetDevice(m->device));
+  const size_t ib = (size_t)B * m->cw * 8, ob = (size_t)B * m->rw * 8;
+  int rc;
+  if ((rc = ensure_cap(&m->d_io[0], &m->io_cap[0], ib))) return rc;
+  if ((rc = ensure_cap(&m->d_io[1], &m->io_cap[1], ob))) return rc;
+  TQEC_CUDA(cudaMemcpyAsync(m->d_io[0], in, ib, cudaMemcpyHostToDevice, m->stream));
+  if ((rc = launch_gf2_apply(m, (const uint64_t *)m->d_io[0], B, (uint64_t *)m->d_io[1], m->stream))) return rc;
+  TQEC_CUDA(cudaMemcpyAsync(out, m->d_io[1], ob, cudaMemcpyDeviceToHost, m->stream));
+  TQEC_CUDA(cudaStreamSynchronize(m->stream));
+  return TQEC_OK;
+}
+
+extern "C" int tqec_logical_flags(tqec_gf2 *L, const int32_t *row_class, const uint64_t *e1, const uint64_t *e2,
+                                  int64_t B, uint8_t *flags_out, int64_t counts[4]) {
+  TQEC_REQUIRE(L && row_class && B >= 0 && (B == 0 || e1), "tqec_logical_flags: NULL argument");
+  if (B == 0) return TQEC_OK;
+  TQEC_CUDA(cudaSetDevice(L->device));
+  const size_t eb = (size_t)B * L->cw * 8;
+  int rc;
+  if ((rc = ensure_cap(&L->d_io[0], &L->io_cap[0], eb))) return rc;
+  if ((rc = ensure_cap(&L->d_io[1], &L->io_cap[1], eb))) return rc;
+  if ((rc = ensure_cap(&L->d_io[2], &L->io_cap[2], (size_t)B))) return rc;
+  if ((rc = ensure_cap(&L->d_io[3], &L->io_cap[3], 64 + (size_t)L->rows * 4))) return rc;
+  unsigned long long *d_counts = (unsigned long long *)L->d_io[3];
+  int32_t *d_cls = (int32_t *)((char *)L->d_io[3] + 64);
+  TQEC_CUDA(cudaMemcpyAsync(L->d_io[0], e1, eb, cudaMemcpyHostToDevice, L->stream));
+  if (e2) TQEC_CUDA(cudaMemcpyAsync(L->d_io[1], e2, eb, cudaMemcpyHostToDevice, L->stream));
+  TQEC_CUDA(cudaMemsetAsync(d_counts, 0, 32, L->stream));
+  TQEC_CUDA(cudaMemcpyAsync(d_cls, row_class, (size_t)L->rows * 4, cudaMemcpyHostToDevice, L->stream));
+  if ((rc = launch_flags(L, d_cls, (const uint64_t *)L->d_io[0], e2 ? (const uint64_t *)L->d_io[1] : nullptr, B,
+                         (uint8_t *)L->d_io[2], counts ? d_counts : nullptr, L->stream))) return rc;
+  if (flags_out) TQEC_CUDA(cudaMemcpyAsync(flags_out, L->d_io[2], (size_t)B, cudaMemcpyDeviceToHost, L->stream));
+  unsigned long long h[4] = {0, 0, 0, 0};
+  if (counts) TQEC_CUDA(cudaMemcpyAsync(h, d_counts, 24, cudaMemcpyDeviceToHost, L->stream));
+  TQEC_CUDA(cudaStreamSynchronize(L->stream));
+  if (counts) {
+    counts[0] += (int64_t)h[0]; counts[1] += (int64_t)h[1]; counts[2] += (int64_t)h[2]; counts[3] += B;
+  }
+  return TQEC_OK;
+}
+
+extern "C" int tqec_coset_rep(tqec_gf2 *R, tqec_gf2 *L, tqec_gf2 *FIX, const uint64_t *synd, const int32_t *sector,
+                              int64_t B, uint64_t *err_out) {
+  TQEC_REQUIRE(R && B >= 0 && (B == 0 || (synd && err_out)), "tqec_coset_rep: NULL argument");
+  TQEC_REQUIRE((L == nullptr) == (FIX == nullptr), "tqec_coset_rep: L and FIX go together");
+  if (L) {
+    TQEC_REQUIRE(L->cols == R->rows && FIX->cols == R->rows && L->rows == FIX->rows && sector,
+                 "tqec_coset_rep: L / FIX must be n_obs x n_vars and sector non-NULL");
+    TQEC_REQUIRE(L->device == R->device && FIX->device == R->device, "tqec_coset_rep: matrices live on different devices");
+  }
+  if (B == 0) return TQEC_OK;
+  TQEC_CUDA(cudaSetDevice(R->device));
+  const size_t ib = (size_t)B * R->cw * 8, ob = (size_t)B * R->rw * 8;
+  int rc;
+  if ((rc = ensure_cap(&R->d_io[0], &R->io_cap[0], ib))) return rc;
+  if ((rc = ensure_cap(&R->d_io[1], &R->io_cap[1], ob))) return rc;
+  TQEC_CUDA(cudaMemcpyAsync(R->d_io[0], synd, ib, cudaMemcpyHostToDevice, R->stream));
+  if ((rc = launch_gf2_apply(R, (const uint64_t *)R->d_io[0], B, (uint64_t *)R->d_io[1], R->stream))) return rc;
+  if (L && L->rows > 0) {
+    if ((rc = ensure_cap(&R->d_io[2], &R->io_cap[2], (size_t)B * 4))) return rc;
+    TQEC_CUDA(cudaMemcpyAsync(R->d_io[2], sector, (size_t)B * 4, cudaMemcpyHostToDevice, R->stream));
+    const int threads = 128;
+    k_coset_fix<<<(unsigned)((B + threads - 1) / threads), threads, 0, R->stream>>>(L->d_rows, FIX->d_rows, L->rows, L->cw,
+                                                                                   (const int32_t *)R->d_io[2], B, (uint64_t *)R->d_io[1]);
+    TQEC_CUDA(cudaGetLastError());
+    R->launches += 1;
+  }
+  TQEC_CUDA(cudaMemcpyAsync(err_out, R->d_io[1], ob, cudaMemcpyDeviceToHost, R->stream));
+  TQEC_CUDA(cudaStreamSynchronize(R->stream));
+  return TQEC_OK;
+}
+
+static int upload_probs(int model, int n_sites, const double *p0, const double *p1, const double *p2, double **d_p,
+                        cudaStream_t stream) {
+  const int np = model == TQEC_MODEL_DEPOL ? 3 : 1;
+  TQEC_CUDA(cudaMalloc((void **)d_p, (size_t)np * (n_sites ? n_sites : 1) * 8));
+  TQEC_CUDA(cudaMemcpyAsync(*d_p, p0, (size_t)n_sites * 8, cudaMemcpyHostToDevice, stream));
+  if (np == 3) {
+    TQEC_CUDA(cudaMemcpyAsync(*d_p + n_sites, p1, (size_t)n_sites * 8, cudaMemcpyHostToDevice, stream));
+    TQEC_CUDA(cudaMemcpyAsync(*d_p + 2 * n_sites, p2, (size_t)n_sites * 8, cudaMemcpyHostToDevice, stream));
+  }
+  return TQEC_OK;
+}
+
+extern "C" int tqec_sample_errors(int32_t model, int32_t n_sites, const double *p0, const double *p1, const double *p2,
+                                  uint64_t seed, int64_t shot_offset, int64_t B, uint64_t *err_out, int32_t device) {
+  TQEC_REQUIRE(model == TQEC_MODEL_FLIP || model == TQEC_MODEL_DEPOL, "tqec_sample_errors: unknown model %d", model);
+  TQEC_REQUIRE(n_sites >= 0 && p0 && (model == TQEC_MODEL_FLIP || (p1 && p2)), "tqec_sample_errors: NULL probability vector");
+  TQEC_REQUIRE(B >= 0 && (B == 0 || err_out), "tqec_sample_errors: NULL output");
+  if (B == 0) return TQEC_OK;
+  int ndev = 0;
+  TQEC_CUDA(cudaGetDeviceCount(&ndev));
+  TQEC_REQUIRE(device >= 0 && device < ndev, "tqec_sample_errors: device %d not present (%d visible)", device, ndev);
+  TQEC_CUDA(cudaSetDevice(device));
+  const int words = words_for(model == TQEC_MODEL_DEPOL ? 2 * n_sites : n_sites);
+  double *d_p = nullptr;
+  uint64_t *d_err = nullptr;
+  int rc = upload_probs(model, n_sites, p0, p1, p2, &d_p, 0);
+  if (!rc && cudaMalloc((void **)&d_err, (size_t)B * words * 8) != cudaSuccess) { set_error("tqec_sample_errors: out of device memory"); rc = TQEC_ERR_NOMEM; }
+  if (!rc) rc = launch_sample(model, n_sites, d_p, seed, shot_offset, B, d_err, words, 0);
+  if (!rc && cudaMemcpy(err_out, d_err, (size_t)B * words * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("tqec_sample_errors: copy back failed: %s", cudaGetErrorString(cudaGetLastError())); rc = TQEC_ERR_CUDA; }
+  cudaFree(d_p);
+  cudaFree(d_err);
+  return rc;
+}
+
+// ---- fused pipeline -------------------------------------------------------------------------------------------
+extern "C" int tqec_mc_run(const tqec_mc_desc *mc, uint64_t seed, int64_t shot_offset, int64_t n_shots, int64_t counts[4],
+                           float *elapsed_ms) {
+  TQEC_REQUIRE(mc && mc->plan && mc->H && mc->L && mc->row_class && counts, "tqec_mc_run: NULL argument");
+  tqec_plan *P = mc->plan;
+  TQEC_REQUIRE(P->semiring == TQEC_SEMIRING_MAXPLUS, "tqec_mc_run: needs a max-plus (TNMAP) plan");
+  const int nbits = mc->model == TQEC_MODEL_DEPOL ? 2 * mc->n_sites : mc->n_sites;
+  TQEC_REQUIRE(mc->model == TQEC_MODEL_FLIP || mc->model == TQEC_MODEL_DEPOL, "tqec_mc_run: unknown model %d", mc->model);
+  TQEC_REQUIRE(nbits == P->dev.n_vars && mc->H->cols == nbits && mc->H->rows == P->dev.n_checks && mc->L->cols == nbits,
+               "tqec_mc_run: shapes disagree (model bits %d, plan vars %d, H %dx%d, L %dx%d)", nbits, P->dev.n_vars,
+               mc->H->rows, mc->H->cols, mc->L->rows, mc->L->cols);
+  TQEC_REQUIRE(mc->H->device == P->device && mc->L->device == P->device, "tqec_mc_run: handles live on different devices");
+  TQEC_REQUIRE(n_shots >= 0, "tqec_mc_run: negative shot count");
+  TQEC_CUDA(cudaSetDevice(P->device));
+  int64_t chunk = mc->chunk > 0 ? mc->chunk : (int64_t)1 << 20;
+  if (chunk > n_shots) chunk = n_shots > 0 ? n_shots : 1;
+  const int ew = P->dev.ncw, sw = P->dev.nsw;
+  cudaStream_t st = P->stream;
+  uint64_t *d_err = nullptr, *d_syn = nullptr, *d_cor = nullptr;
+  double *d_p = nullptr;
+  unsigned long long *d_counts = nullptr;
+  int32_t *d_cls = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = TQEC_OK;
+#define MC_TRY(call)                                                                          \
+  do {                                                                                        \
+    cudaError_t _e = (call);                                                                  \
+    if (_e != cudaSuccess && rc == TQEC_OK) {                                                 \
+      set_error("%s failed: %s", #call, cudaGetErrorString(_e));                              \
+      rc = TQEC_ERR_CUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+  MC_TRY(cudaMalloc((void **)&d_err, (size_t)chunk * ew * 8));
+  MC_TRY(cudaMalloc((void **)&d_syn, (size_t)chunk * sw * 8));
+  MC_TRY(cudaMalloc((void **)&d_cor, (size_t)chunk * ew * 8));
+  MC_TRY(cudaMalloc((void **)&d_counts, 32));
+  MC_TRY(cudaMalloc((void **)&d_cls, (size_t)(mc->L->rows ? mc->L->rows : 1) * 4));
+  MC_TRY(cudaEventCreate(&e0));
+  MC_TRY(cudaEventCreate(&e1));
+  if (rc == TQEC_OK) rc = upload_probs(mc->model, mc->n_sites, mc->p0, mc->p1, mc->p2, &d_p, st);
+  if (rc == TQEC_OK) {
+    MC_TRY(cudaMemsetAsync(d_counts, 0, 32, st));
+    MC_TRY(cudaMemcpyAsync(d_cls, mc->row_class, (size_t)mc->L->rows * 4, cudaMemcpyHostToDevice, st));
+    MC_TRY(cudaEventRecord(e0, st));
+  }
+  for (int64_t done = 0; rc == TQEC_OK && done < n_shots; done += chunk) {
+    const int64_t b = n_shots - done < chunk ? n_shots - done : chunk;
+    rc = launch_sample(mc->model, mc->n_sites, d_p, seed, shot_offset + done, b, d_err, ew, st);
+    if (!rc) rc = launch_gf2_apply(mc->H, d_err, b, d_syn, st);
+    if (!rc) rc = launch_decode(P, d_syn, b, d_cor, nullptr, nullptr, st);
+    if (!rc) rc = launch_flags(mc->L, d_cls, d_err, d_cor, b, nullptr, d_counts, st);
+  }
+  unsigned long long h[4] = {0, 0, 0, 0};
+  if (rc == TQEC_OK) {
+    MC_TRY(cudaEventRecord(e1, st));
+    MC_TRY(cudaMemcpyAsync(h, d_counts, 24, cudaMemcpyDeviceToHost, st));
+    MC_TRY(cudaStreamSynchronize(st));
+    if (rc == TQEC_OK && elapsed_ms) MC_TRY(cudaEventElapsedTime(elapsed_ms, e0, e1));
+  }
+#undef MC_TRY
+  if (rc == TQEC_OK) {
+    counts[0] += (int64_t)h[0]; counts[1] += (int64_t)h[1]; counts[2] += (int64_t)h[2]; counts[3] += n_shots;
+  }
+  cudaFree(d_err); cudaFree(d_syn); cudaFree(d_cor); cudaFree(d_counts); cudaFree(d_cls); cudaFree(d_p);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  return rc;
+}

@@ -1,0 +1,441 @@
+"""The decoder plugin boundary: problems, `TNMAP` / `TNMMAP`, `compile`, `decode`.
+
+Reference: src/decoding/interfaces.jl:6-51 (problem structs), :58-67 (decoder / compiled-decoder abstract types),
+:74-79 (`compile` overloads), :96-105 (`decode` overloads), :116-119 (`DecodingResult`), :124-142 (CSS / classical
+-> general reduction); src/decoding/general_decoding.jl:5-32 (`single_qubit_tensor`, `reduce2general`,
+`extract_decoding`); src/decoding/tndecoder.jl:9-57 (TNMAP), :64-174 (TNMMAP, CSS), :176-271 (TNMMAP, DEM).
+
+`compile` builds the decoder's factor graph exactly as the reference builds its tensor network (same variables, same
+prior tensors, same parity constraints, same open logical axes), lowers it to a frontier schedule
+(schedule.py) and uploads it through `tqec_plan_create`; `decode` marshals bit-packed syndromes through
+`tqec_decode_map` / `tqec_decode_marginal` (+ `tqec_coset_rep`).  `decode` accepts one syndrome or a batch.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any, List, Optional, Sequence
+
+import numpy as np
+
+from . import _cabi, schedule as S
+from .dem import DetectorErrorModel, dem2tanner
+from .error_model import (AbstractErrorModel, CSSErrorPattern, CSSSyndrome, IndependentDepolarizingError,
+                          IndependentFlipError, SimpleSyndrome, iid_error)
+from .mod2 import as_bits, pack_bits, unpack_bits
+from .tanner import AbstractTannerGraph, CSSTannerGraph, SimpleTannerGraph, gf2_right_inverse, logical_operator
+
+
+# ---- problems (interfaces.jl:6-51) ---------------------------------------------------------------------------
+class AbstractDecodingProblem:
+    pass
+
+
+@dataclass
+class SimpleTensorNetwork:
+    """Container of the prior distribution (src/nonclifford/tensornetwork.jl:143-146): `ixs[t]` = 0-based variable
+    labels of tensor t, `tensors[t]` = ndarray with one axis per label (T[i0, i1, ...] = the reference's
+    T[i0+1, i1+1, ...])."""
+    ixs: List[List[int]]
+    tensors: List[np.ndarray]
+
+
+@dataclass
+class ClassicalDecodingProblem(AbstractDecodingProblem):
+    tanner: SimpleTannerGraph
+    pvec: IndependentFlipError
+
+    def __post_init__(self):
+        if not isinstance(self.pvec, IndependentFlipError):
+            self.pvec = IndependentFlipError(self.pvec)
+
+
+@dataclass
+class IndependentDepolarizingDecodingProblem(AbstractDecodingProblem):
+    tanner: CSSTannerGraph
+    pvec: IndependentDepolarizingError
+
+
+@dataclass
+class GeneralDecodingProblem(AbstractDecodingProblem):
+    tanner: SimpleTannerGraph
+    ptn: SimpleTensorNetwork
+
+
+def get_problem(tanner, pvec):
+    if isinstance(tanner, SimpleTannerGraph) and isinstance(pvec, IndependentFlipError):
+        return ClassicalDecodingProblem(tanner, pvec)
+    if isinstance(tanner, CSSTannerGraph) and isinstance(pvec, IndependentDepolarizingError):
+        return IndependentDepolarizingDecodingProblem(tanner, pvec)
+    raise TypeError(f"no decoding problem for ({type(tanner).__name__}, {type(pvec).__name__})")   # MethodError
+
+
+# ---- decoders ---------------------------------------------------------------------------------------------------
+class AbstractDecoder:
+    pass
+
+
+class AbstractClassicalDecoder(AbstractDecoder):
+    pass
+
+
+class AbstractGeneralDecoder(AbstractDecoder):
+    pass
+
+
+class CompiledDecoder:
+    pass
+
+
+@dataclass
+class DecodingResult:
+    """interfaces.jl:116-119, plus what the batched kernels know anyway: `logp` (TNMAP: log-weight of the returned
+    configuration), `marginal` / `sector` (TNMMAP: logical-sector weights and their argmax)."""
+    success_tag: Any
+    error_pattern: Any
+    logp: Optional[np.ndarray] = None
+    marginal: Optional[np.ndarray] = None
+    sector: Optional[np.ndarray] = None
+
+
+@dataclass
+class TNMAP(AbstractGeneralDecoder):
+    """tndecoder.jl:9-11.  `optimizer`: None = built-in frontier ordering; a sequence = absorption order of the
+    prior factors (e.g. the leaf order of a contraction tree found by the caller's TreeSA / GreedyMethod)."""
+    optimizer: Any = None
+    device: int = 0
+
+    def __repr__(self):
+        return "TNMAP"
+
+
+@dataclass
+class NoOptimizer:
+    """tndecoder.jl:64: keep the natural order of the factors."""
+
+    def __repr__(self):
+        return "NoOptimizer"
+
+
+@dataclass
+class TNMMAP(AbstractGeneralDecoder):
+    """tndecoder.jl:77-80.  `factorize` only affects how the reference shapes its DEM network (:195, :199); the
+    frontier lowering always uses the fully factorised (XOR-chain) form, which contracts to the same marginals."""
+    optimizer: Any = None
+    factorize: bool = True
+    device: int = 0
+
+    def __repr__(self):
+        return "TNMMAP"
+
+
+def _order_of(optimizer, n_factors):
+    if optimizer is None:
+        return None
+    if isinstance(optimizer, NoOptimizer):
+        return list(range(n_factors))
+    return [int(i) for i in optimizer]
+
+
+# ---- reductions (general_decoding.jl) ----------------------------------------------------------------------------
+def single_qubit_tensor(px, py, pz) -> np.ndarray:
+    """general_decoding.jl:5: T[x, z] = [1-px-py-pz  pz ; px  py]."""
+    return np.array([[1.0 - px - py - pz, pz], [px, py]])
+
+
+@dataclass
+class CSSToGeneralDecodingProblem:
+    qubit_num: int
+
+
+def reduce2general(tanner: CSSTannerGraph, pvec_or_tn):
+    """general_decoding.jl:20-32: 2n variables (x_i = i, z_i = i + n); checks = X checks on the z block, then Z checks
+    on the x block; priors = one 2x2 tensor per qubit on (i, i+n) or a caller-supplied network."""
+    n = tanner.stgx.nq
+    if isinstance(pvec_or_tn, IndependentDepolarizingError):
+        p = pvec_or_tn
+        tn = SimpleTensorNetwork([[i, i + n] for i in range(n)],
+                                 [single_qubit_tensor(p.px[j], p.py[j], p.pz[j]) for j in range(n)])
+    else:
+        tn = pvec_or_tn
+    sts = [[q + n for q in s] for s in tanner.stgx.s2q] + [list(s) for s in tanner.stgz.s2q]
+    return GeneralDecodingProblem(SimpleTannerGraph(2 * n, sts), tn), CSSToGeneralDecodingProblem(n)
+
+
+def extract_decoding(cgdp: CSSToGeneralDecodingProblem, error_pattern: np.ndarray) -> DecodingResult:
+    n = cgdp.qubit_num
+    e = np.asarray(error_pattern)
+    return DecodingResult(True, CSSErrorPattern(e[..., :n], e[..., n:2 * n]))
+
+
+# ---- TNMAP (tndecoder.jl:16-57) -------------------------------------------------------------------------------------
+class CompiledTNMAP(CompiledDecoder):
+    def __init__(self, sch: S.Schedule, qubit_num: int, device: int):
+        self.schedule = sch
+        self.qubit_num = qubit_num
+        self.plan = _cabi.Plan(sch, device)
+        self.device = device
+
+
+def tnmap_schedule(decoder: TNMAP, problem: GeneralDecodingProblem) -> S.Schedule:
+    """Host-only part of compile(::TNMAP, ::GeneralDecodingProblem): factor graph -> lowered schedule."""
+    t = problem.tanner
+    factors = [S.Factor(tuple(int(v) for v in ix), S.flat_table(tt)) for ix, tt in zip(problem.ptn.ixs, problem.ptn.tensors)]
+    for f in factors:
+        if any(not 0 <= v < t.nq for v in f.vars):
+            raise IndexError("prior tensor label outside 0..nq-1")
+    checks = [S.Check(tuple(c), "syn", s) for s, c in enumerate(t.s2q)]
+    return S.lower(factors, checks, S.MAXPLUS, t.nq, t.ns, 0, order=_order_of(decoder.optimizer, len(factors)))
+
+
+def _compile_tnmap(decoder: TNMAP, problem: GeneralDecodingProblem) -> CompiledTNMAP:
+    return CompiledTNMAP(tnmap_schedule(decoder, problem), problem.tanner.nq, decoder.device)
+
+
+def _syndrome_bits(s, n) -> np.ndarray:
+    b = as_bits(s)
+    b = b[None, :] if b.ndim == 1 else b
+    if b.shape[1] != n:
+        raise ValueError(f"syndrome has {b.shape[1]} bits, the decoder expects {n}")
+    return b
+
+
+def _decode_tnmap(ct: CompiledTNMAP, syndrome: SimpleSyndrome) -> DecodingResult:
+    single = as_bits(syndrome.s).ndim == 1
+    bits = _syndrome_bits(syndrome.s, ct.schedule.n_checks)
+    corr, logp = ct.plan.decode_map(pack_bits(bits))
+    cfg = unpack_bits(corr, ct.qubit_num)
+    ok = np.isfinite(logp)
+    if single:
+        return DecodingResult(bool(ok[0]), cfg[0], logp=logp[0])
+    return DecodingResult(ok, cfg, logp=logp)
+
+
+@dataclass
+class CompiledGeneralDecoder(CompiledDecoder):
+    """interfaces.jl:124-127."""
+    cd: CompiledDecoder
+    reduction: CSSToGeneralDecodingProblem
+
+
+# ---- TNMMAP, CSS (tndecoder.jl:85-174) --------------------------------------------------------------------------------
+class CompiledTNMMAP(CompiledDecoder):
+    def __init__(self, tanner, lx, lz, sch, R, L, FIX, device):
+        self.tanner, self.lx, self.lz = tanner, lx, lz
+        self.schedule = sch
+        self.plan = _cabi.Plan(sch, device)
+        self.R = _cabi.GF2Matrix(R, device)
+        self.L = _cabi.GF2Matrix(L, device)
+        self.FIX = _cabi.GF2Matrix(FIX, device)
+        self.device = device
+
+    def marginal(self, syndrome: CSSSyndrome) -> np.ndarray:
+        """`ct.code(ct.tensors...)` after `update_syndrome!` (tndecoder.jl:148-162): array with 2k axes of size 2,
+        first k = lx-parities of the Z errors, last k = lz-parities of the X errors (batch axis first if batched)."""
+        single = as_bits(syndrome.sx).ndim == 1
+        bits = np.concatenate([_syndrome_bits(syndrome.sx, self.tanner.stgx.ns),
+                               _syndrome_bits(syndrome.sz, self.tanner.stgz.ns)], axis=1)
+        mar, _ = self.plan.decode_marginal(pack_bits(bits))
+        k2 = self.schedule.n_obs
+        out = mar.reshape((mar.shape[0],) + (2,) * k2, order="F") if k2 else mar
+        return out[0] if single else out
+
+
+def tnmmap_css_schedule(decoder: TNMMAP, problem: IndependentDepolarizingDecodingProblem):
+    """Host-only part of the CSS TNMMAP compile -> (lx, lz, schedule, R, L, FIX)."""
+    tanner = problem.tanner
+    n = tanner.stgx.nq
+    nsx, nsz = tanner.stgx.ns, tanner.stgz.ns
+    lx, lz = logical_operator(tanner)
+    k = lx.shape[0]
+    p = problem.pvec
+    factors = [S.Factor((i, i + n), S.flat_table(single_qubit_tensor(p.px[i], p.py[i], p.pz[i]))) for i in range(n)]
+    checks = [S.Check(tuple(q + n for q in c), "syn", i) for i, c in enumerate(tanner.stgx.s2q)]
+    checks += [S.Check(tuple(c), "syn", nsx + i) for i, c in enumerate(tanner.stgz.s2q)]
+    # open axes, in the reference's output order iy (tndecoder.jl:134): lx-parities of Z errors, then lz-parities of X errors
+    checks += [S.Check(tuple(int(q) + n for q in np.flatnonzero(lx[i])), "obs", i) for i in range(k)]
+    checks += [S.Check(tuple(int(q) for q in np.flatnonzero(lz[i])), "obs", k + i) for i in range(k)]
+    sch = S.lower(factors, checks, S.SUMPROD, 2 * n, nsx + nsz, 2 * k, order=_order_of(decoder.optimizer, n))
+    # error_pattern (tndecoder.jl:167-174): any solution of the syndrome equations, moved into the decoded sector
+    Rz, _ = gf2_right_inverse(tanner.stgz.H)            # ex = Rz sz
+    Rx, _ = gf2_right_inverse(tanner.stgx.H)            # ez = Rx sx
+    R = np.zeros((2 * n, nsx + nsz), dtype=np.uint8)
+    R[:n, nsx:] = Rz
+    R[n:, :nsx] = Rx
+    L = np.zeros((2 * k, 2 * n), dtype=np.uint8)
+    FIX = np.zeros((2 * k, 2 * n), dtype=np.uint8)
+    L[:k, n:] = lx                                       # sector bit i     = lx[i] . ez ; repaired by ez += lz[i]
+    FIX[:k, n:] = lz
+    L[k:, :n] = lz                                       # sector bit k + i = lz[i] . ex ; repaired by ex += lx[i]
+    FIX[k:, :n] = lx
+    return lx, lz, sch, R, L, FIX
+
+
+def _compile_tnmmap_css(decoder: TNMMAP, problem: IndependentDepolarizingDecodingProblem) -> CompiledTNMMAP:
+    lx, lz, sch, R, L, FIX = tnmmap_css_schedule(decoder, problem)
+    return CompiledTNMMAP(problem.tanner, lx, lz, sch, R, L, FIX, decoder.device)
+
+
+def _decode_tnmmap_css(ct: CompiledTNMMAP, syndrome: CSSSyndrome) -> DecodingResult:
+    single = as_bits(syndrome.sx).ndim == 1
+    bits = np.concatenate([_syndrome_bits(syndrome.sx, ct.tanner.stgx.ns), _syndrome_bits(syndrome.sz, ct.tanner.stgz.ns)], axis=1)
+    words = pack_bits(bits)
+    mar, pos = ct.plan.decode_marginal(words)
+    n = ct.tanner.stgx.nq
+    e = unpack_bits(_cabi.coset_rep(ct.R, ct.L, ct.FIX, words, pos), 2 * n)
+    ok = mar.max(axis=1) > 0
+    k2 = ct.schedule.n_obs
+    marr = mar.reshape((mar.shape[0],) + (2,) * k2, order="F")
+    if single:
+        return DecodingResult(bool(ok[0]), CSSErrorPattern(e[0, :n], e[0, n:]), marginal=marr[0], sector=int(pos[0]))
+    return DecodingResult(ok, CSSErrorPattern(e[:, :n], e[:, n:]), marginal=marr, sector=pos)
+
+
+# ---- TNMMAP, detector error model (tndecoder.jl:176-271) -----------------------------------------------------------------
+def _gf2_solve(A: np.ndarray, b: np.ndarray):
+    """One solution x of A x = b over GF(2), or None."""
+    A = np.concatenate([as_bits(A).copy(), as_bits(b).reshape(-1, 1)], axis=1)
+    m, n1 = A.shape
+    n = n1 - 1
+    piv = []
+    r = 0
+    for c in range(n):
+        nz = np.flatnonzero(A[r:, c]) if r < m else np.zeros(0, dtype=int)
+        if nz.size == 0:
+            continue
+        p = r + int(nz[0])
+        if p != r:
+            A[[r, p]] = A[[p, r]]
+        for kx in np.flatnonzero(A[:, c]):
+            if kx != r:
+                A[kx] ^= A[r]
+        piv.append(c)
+        r += 1
+        if r == m:
+            break
+    if A[r:, n].any():
+        return None
+    x = np.zeros(n, dtype=np.uint8)
+    for i, c in enumerate(piv):
+        x[c] = A[i, n]
+    return x
+
+
+class CompiledDEMTNMMAP(CompiledDecoder):
+    def __init__(self, tanner, l2q, sch, R, L, FIX, device):
+        self.tanner, self.l2q = tanner, l2q
+        self.schedule = sch
+        self.plan = _cabi.Plan(sch, device)
+        self.R = _cabi.GF2Matrix(R, device)
+        self.L = _cabi.GF2Matrix(L, device)
+        self.FIX = _cabi.GF2Matrix(FIX, device)
+        self.device = device
+
+    def marginal(self, syndrome: SimpleSyndrome) -> np.ndarray:
+        single = as_bits(syndrome.s).ndim == 1
+        mar, _ = self.plan.decode_marginal(pack_bits(_syndrome_bits(syndrome.s, self.tanner.ns)))
+        k = self.schedule.n_obs
+        out = mar.reshape((mar.shape[0],) + (2,) * k, order="F") if k else mar
+        return out[0] if single else out
+
+
+def tnmmap_dem_schedule(decoder: TNMMAP, dem: DetectorErrorModel):
+    """Host-only part of the DEM TNMMAP compile -> (tanner, l2q, schedule, R, L, FIX)."""
+    tanner = dem2tanner(dem)
+    ne, nd = tanner.nq, tanner.ns
+    l2q = [[e for e in range(ne) if l in dem.flipped_detectors[e]] for l in dem.logical_list]
+    factors = [S.Factor((e,), np.array([1.0 - p, p])) for e, p in enumerate(dem.error_rates)]
+    checks = [S.Check(tuple(c), "syn", d) for d, c in enumerate(tanner.s2q)]
+    checks += [S.Check(tuple(c), "obs", l) for l, c in enumerate(l2q)]
+    sch = S.lower(factors, checks, S.SUMPROD, ne, nd, len(l2q), order=_order_of(decoder.optimizer, ne))
+    R, _ = gf2_right_inverse(tanner.H)
+    L = np.zeros((len(l2q), ne), dtype=np.uint8)
+    for l, c in enumerate(l2q):
+        L[l, c] = 1
+    # The reference "repairs" a wrong observable by flipping every mechanism that touches it (tndecoder.jl:257-258,
+    # 266-267), which also changes the detectors.  Here the repair is an undetectable combination of
+    # mechanisms that flips exactly that observable (H f = 0, L f = e_l), when one exists.
+    FIX = np.zeros_like(L)
+    A = np.vstack([tanner.H, L])
+    for l in range(len(l2q)):
+        b = np.zeros(nd + len(l2q), dtype=np.uint8)
+        b[nd + l] = 1
+        f = _gf2_solve(A, b)
+        if f is not None:
+            FIX[l] = f
+    return tanner, l2q, sch, R, L, FIX
+
+
+def _compile_tnmmap_dem(decoder: TNMMAP, dem: DetectorErrorModel) -> CompiledDEMTNMMAP:
+    tanner, l2q, sch, R, L, FIX = tnmmap_dem_schedule(decoder, dem)
+    return CompiledDEMTNMMAP(tanner, l2q, sch, R, L, FIX, decoder.device)
+
+
+def _decode_tnmmap_dem(ct: CompiledDEMTNMMAP, syndrome: SimpleSyndrome) -> DecodingResult:
+    single = as_bits(syndrome.s).ndim == 1
+    words = pack_bits(_syndrome_bits(syndrome.s, ct.tanner.ns))
+    mar, pos = ct.plan.decode_marginal(words)
+    e = unpack_bits(_cabi.coset_rep(ct.R, ct.L, ct.FIX, words, pos), ct.tanner.nq)
+    ok = mar.max(axis=1) > 0
+    k = ct.schedule.n_obs
+    marr = mar.reshape((mar.shape[0],) + (2,) * k, order="F")
+    if single:
+        return DecodingResult(bool(ok[0]), e[0], marginal=marr[0], sector=int(pos[0]))
+    return DecodingResult(ok, e, marginal=marr, sector=pos)
+
+
+# ---- compile / decode dispatch (interfaces.jl:74-105, 129-142) ----------------------------------------------------------
+def compile(decoder: AbstractDecoder, problem, pvec: Optional[AbstractErrorModel] = None):
+    """compile(decoder, problem) | compile(decoder, tanner) | compile(decoder, tanner, pvec) | compile(TNMMAP, dem)."""
+    if isinstance(problem, AbstractTannerGraph):
+        if pvec is None:
+            pvec = iid_error(0.05, problem)                                    # interfaces.jl:74-76
+        problem = get_problem(problem, pvec)                                   # interfaces.jl:77-79
+    elif pvec is not None:
+        raise TypeError("pvec is only meaningful together with a Tanner graph")
+    if isinstance(decoder, TNMAP):
+        if isinstance(problem, GeneralDecodingProblem):
+            return _compile_tnmap(decoder, problem)
+        if isinstance(problem, IndependentDepolarizingDecodingProblem):        # interfaces.jl:129-133
+            gdp, c2g = reduce2general(problem.tanner, problem.pvec)
+            return CompiledGeneralDecoder(_compile_tnmap(decoder, gdp), c2g)
+        if isinstance(problem, ClassicalDecodingProblem):                      # interfaces.jl:139-142
+            t = problem.tanner
+            tn = SimpleTensorNetwork([[i] for i in range(t.nq)], [np.array([1.0 - p, p]) for p in problem.pvec.p])
+            return _compile_tnmap(decoder, GeneralDecodingProblem(t, tn))
+    if isinstance(decoder, TNMMAP):
+        if isinstance(problem, IndependentDepolarizingDecodingProblem):
+            return _compile_tnmmap_css(decoder, problem)
+        if isinstance(problem, DetectorErrorModel):
+            return _compile_tnmmap_dem(decoder, problem)
+    raise TypeError(f"no method compile({type(decoder).__name__}, {type(problem).__name__})")
+
+
+def decode(first, *args):
+    """decode(compiled, syndrome) | decode(decoder, problem|tanner, syndrome[, pvec]) (interfaces.jl:96-105)."""
+    if isinstance(first, AbstractDecoder):
+        if len(args) == 2:
+            prob, syn = args
+            ct = compile(first, prob)
+        elif len(args) == 3:
+            tanner, syn, pvec = args
+            ct = compile(first, tanner, pvec)
+        else:
+            raise TypeError("decode(decoder, problem|tanner, syndrome[, pvec])")
+        return decode(ct, syn)
+    (syn,) = args
+    ct = first
+    if isinstance(ct, CompiledGeneralDecoder):                                  # interfaces.jl:135-137
+        if not isinstance(syn, CSSSyndrome):
+            raise TypeError("a CSS-compiled decoder decodes a CSSSyndrome")
+        sx, sz = as_bits(syn.sx), as_bits(syn.sz)
+        res = decode(ct.cd, SimpleSyndrome(np.concatenate([sx, sz], axis=-1)))
+        out = extract_decoding(ct.reduction, res.error_pattern)
+        out.success_tag, out.logp = res.success_tag, res.logp
+        return out
+    if isinstance(ct, CompiledTNMAP) and isinstance(syn, SimpleSyndrome):
+        return _decode_tnmap(ct, syn)
+    if isinstance(ct, CompiledTNMMAP) and isinstance(syn, CSSSyndrome):
+        return _decode_tnmmap_css(ct, syn)
+    if isinstance(ct, CompiledDEMTNMMAP) and isinstance(syn, SimpleSyndrome):
+        return _decode_tnmmap_dem(ct, syn)
+    raise TypeError(f"no method decode({type(ct).__name__}, {type(syn).__name__})")

@@ -1,0 +1,118 @@
+"""GF(2) host helpers: the `Mod2` scalar of the reference and the bit-packed layouts the C-ABI uses.
+
+Reference: src/codes/mod2.jl:20-41 (Mod2 algebra: + and - are XOR, * is AND), :44-71 (`bitmul!`,
+`compresscol`: 64 rows per UInt64, bit k of word w = row 64*w + k).
+
+Host containers are numpy uint8 vectors / matrices holding 0/1 (the reference's `Vector{Mod2}` is one byte
+per bit as well).  Everything that crosses the C-ABI is bit-packed, SHOT-MAJOR:
+
+    packed[shot, w] (uint64), bit k of word w  <->  bit index 64*w + k          (little-endian bits)
+
+which is `compresscol` applied to the (bits x shots) matrix.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+class Mod2:
+    """GF(2) scalar (src/codes/mod2.jl:20-41).  Kept for API parity; bulk data uses uint8 arrays."""
+
+    __slots__ = ("x",)
+
+    def __init__(self, x):
+        if isinstance(x, Mod2):
+            x = x.x
+        if x not in (0, 1, True, False):
+            raise ValueError(f"Mod2 expects a Bool or 0/1, got {x!r}")  # Bool(x) InexactError in the reference
+        self.x = bool(x)
+
+    def __add__(self, o):
+        return Mod2(self.x ^ Mod2(o).x)
+
+    __sub__ = __add__
+    __radd__ = __add__
+
+    def __neg__(self):
+        return self
+
+    def __mul__(self, o):
+        return Mod2(self.x and Mod2(o).x)
+
+    def __eq__(self, o):
+        return isinstance(o, (Mod2, bool, int)) and self.x == Mod2(o).x
+
+    def __hash__(self):
+        return hash(self.x)
+
+    def __int__(self):
+        return 1 if self.x else 0
+
+    def __bool__(self):
+        return self.x
+
+    def iszero(self):
+        return not self.x
+
+    def __repr__(self):
+        return "1₂" if self.x else "0₂"
+
+
+def as_bits(v) -> np.ndarray:
+    """Anything bit-like (list of 0/1, bools, Mod2) -> uint8 array of 0/1."""
+    if isinstance(v, np.ndarray) and v.dtype != object:
+        a = v.astype(np.uint8, copy=False)
+    else:
+        a = np.array([[int(x) for x in row] if isinstance(row, (list, tuple, np.ndarray)) else int(row) for row in v],
+                     dtype=np.uint8) if len(v) else np.zeros(0, dtype=np.uint8)
+    if a.size and a.max() > 1:
+        raise ValueError("bits must be 0/1")
+    return a
+
+
+def words_for(nbits: int) -> int:
+    return max(1, (nbits + 63) // 64)
+
+
+def pack_bits(bits: np.ndarray) -> np.ndarray:
+    """(B, nbits) uint8 0/1  ->  (B, ceil(nbits/64)) uint64, bit k of word w = bit 64w+k (compresscol layout)."""
+    bits = np.asarray(bits, dtype=np.uint8)
+    if bits.ndim == 1:
+        bits = bits[None, :]
+    B, n = bits.shape
+    W = words_for(n)
+    pad = np.zeros((B, W * 64), dtype=np.uint8)
+    pad[:, :n] = bits
+    by = np.packbits(pad, axis=1, bitorder="little")          # (B, W*8) bytes, little-endian bit order
+    return np.ascontiguousarray(by).view("<u8").reshape(B, W)
+
+
+def unpack_bits(words: np.ndarray, nbits: int) -> np.ndarray:
+    """Inverse of `pack_bits`."""
+    words = np.ascontiguousarray(words, dtype="<u8")
+    if words.ndim == 1:
+        words = words[None, :]
+    B = words.shape[0]
+    by = words.view(np.uint8).reshape(B, -1)
+    return np.unpackbits(by, axis=1, bitorder="little")[:, :nbits].copy()
+
+
+def pack_rows(M: np.ndarray) -> np.ndarray:
+    """Pack each ROW of a 0/1 matrix (rows x nbits) into uint64 words (rows, ceil(nbits/64))."""
+    return pack_bits(np.asarray(M, dtype=np.uint8))
+
+
+def bitmul(A: np.ndarray, B: np.ndarray) -> np.ndarray:
+    """GF(2) matrix product through the packed popcount-parity form of `bitmul!` (mod2.jl:44-57).
+
+    C[i, j] = parity( sum_k popcount(ca[k, i] & cb[k, j]) ), with ca = compresscol(A'), cb = compresscol(B).
+    """
+    A = as_bits(A)
+    B = as_bits(B)
+    ca = pack_rows(A)                 # (m, W): row i of A packed over its columns   == compresscol(A')[:, i]
+    cb = pack_rows(B.T)               # (n, W): column j of B packed over its rows   == compresscol(B)[:, j]
+    x = ca[:, None, :] & cb[None, :, :]
+    # popcount parity of a uint64: fold by XOR
+    for s in (32, 16, 8, 4, 2, 1):
+        x = x ^ (x >> np.uint64(s))
+    return (np.bitwise_xor.reduce(x, axis=2) & np.uint64(1)).astype(np.uint8)

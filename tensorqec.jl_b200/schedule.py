@@ -1,0 +1,405 @@
+"""Lowering of a decoding factor graph to the static kernel schedule executed by `libtqec_cuda.so`.
+
+What is lowered.  The reference builds, per decoder, a tensor network over binary labels
+(src/decoding/tndecoder.jl:33-50 TNMAP; :97-146 TNMMAP/CSS; :186-238 TNMMAP/DEM) made of
+  * prior factors over error variables (`single_qubit_tensor`, general_decoding.jl:5; `[1-p, p]`, tndecoder.jl:202-205),
+  * one parity tensor per check / detector / logical row (`parity_check_matrix`, tndecoder.jl:42-44), whose last
+    label is clamped by the syndrome (evidence, tndecoder.jl:54 / rank-1 vectors, :148-158) or left open
+    (logical sectors, :134),
+and hands it to OMEinsum for a pairwise contraction tree.  A parity tensor is the constraint
+"xor of its labels = 0", i.e. it factorises exactly into a chain of rank-3 XOR tensors with 1-bit partial-parity
+bonds -- the same factorisation the reference itself applies with `factorize=true` (`push_check_node!`,
+tndecoder.jl:221-238).  Contracting that factorised network along a linear (caterpillar) tree that absorbs one
+prior factor at a time gives the FRONTIER RECURRENCE below; its intermediate tensor is indexed by the partial
+parities of the currently open checks (<= d+1 bits for a distance-d rotated surface code, versus 2(d-1) labels
+for any tree over the unfactorised network).
+
+Recurrence (semiring (+)/(x) = max/+ in the log domain for TNMAP, +/* for TNMMAP), for step t absorbing factor f
+with variables v_1..v_r and table T[a], a = sum_j a_j 2^j (first label fastest, column-major like the reference):
+
+    S_t[sigma'] = (+)_a  S_{t-1}[ sigma ]  (x)  T[a]      where sigma is sigma' with
+        - every check c touched by the factor XOR-ed with the parity of the a_j of its variables,
+        - checks whose first variable is in f ("opened") entering with partial parity 0,
+        - checks whose last variable is in f ("closed") required to end at their syndrome bit and dropped,
+        - observable rows (logical sectors) never closed: they index the final tensor.
+
+Candidates are enumerated in ascending a; on exact FP64 ties the smallest a wins (documented tie rule).
+
+Index layout used by the kernels.  The state is a dense array over w bits ("slots"); live checks occupy slots
+0..w_in-1 in a fixed order, checks opened by the step take slots w_in.., closed slots are deleted from the index
+(higher slots shift down).  For an output index the kernel (1) re-inserts the closed bits with the shot's syndrome
+values -> `full`, (2) reads the opened part `pat = full >> w_in`, which pins a coset a0[pat] + ker of admissible
+candidates, (3) gathers S_in[(full ^ M[a]) & inmask] for a in that coset.  All tables are emitted here.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+MAXPLUS = 0
+SUMPROD = 1
+
+HDR_INTS = 16
+(H_R, H_WIN, H_NOPEN, H_NCLOSE, H_WOUT, H_NK, H_KB, H_OFF_T, H_OFF_ML, H_OFF_MK, H_OFF_A0, H_OFF_KER, H_OFF_VARS,
+ H_OFF_CLOSE, H_RSV0, H_RSV1) = range(HDR_INTS)
+
+MAX_FACTOR_RANK = 10
+MAX_SMEM_WIDTH = 13            # 2 * 2^13 * 8 B = 128 KiB of ping-pong state per team
+
+
+@dataclass
+class Factor:
+    vars: Tuple[int, ...]
+    table: np.ndarray            # flat, length 2^r, index a = sum_j a_j << j  (first variable fastest)
+
+
+@dataclass
+class Check:
+    vars: Tuple[int, ...]
+    kind: str                    # "syn" (clamped by syndrome bit `index`) | "obs" (kept open, output axis `index`)
+    index: int
+
+
+@dataclass
+class Step:
+    factor: int
+    vars: Tuple[int, ...]
+    w_in: int
+    w_out: int
+    opened: List[int]
+    closed: List[Tuple[int, int]]            # (slot in the full index, syndrome bit), ascending slot
+    M: np.ndarray                            # (2^r,) masks in the full index space
+    a0: np.ndarray                           # (2^n_open,) representative candidate per opened pattern, -1 = infeasible
+    ker: np.ndarray                          # (nk,) kernel candidates, ascending
+    table: np.ndarray                        # (2^r,) values in the semiring's domain (log for max-plus)
+
+
+@dataclass
+class Schedule:
+    semiring: int
+    n_vars: int
+    n_checks: int
+    n_obs: int
+    steps: List[Step]
+    obs_slot: List[int]
+    order: List[int]
+    factors: List[Factor]
+    checks: List[Check]
+    w_max: int = 0
+    cost: float = 0.0                        # sum_t 2^w_out * nk  = candidate evaluations per shot
+    # flat encoding for the C-ABI
+    hdr: Optional[np.ndarray] = None
+    ints: Optional[np.ndarray] = None
+    tables: Optional[np.ndarray] = None
+
+    def ops_per_shot(self):
+        """Algorithmic FP64 operations per shot: one (x) per candidate and one (+) per candidate beyond the first."""
+        mul = sum((1 << s.w_out) * len(s.ker) for s in self.steps)
+        add = sum((1 << s.w_out) * (len(s.ker) - 1) for s in self.steps)
+        return mul, add
+
+
+# ------------------------------------------------------------------------------------------------------------
+def flat_table(t) -> np.ndarray:
+    """Tensor with one axis per variable (reference layout, column-major) -> flat array indexed by a."""
+    t = np.asarray(t, dtype=np.float64)
+    return t.reshape(-1, order="F").copy()
+
+
+def merge_overlapping(factors: Sequence[Factor], n_vars: int, check_vars) -> List[Factor]:
+    """Make the prior factors a partition of the variables: multiply factors that share a variable into one
+    (exact; the reference contracts the same product), add an all-ones factor for variables no prior mentions
+    (TensorInference's per-variable unity tensor)."""
+    parent = list(range(len(factors)))
+
+    def find(i):
+        while parent[i] != i:
+            parent[i] = parent[parent[i]]
+            i = parent[i]
+        return i
+
+    owner = {}
+    for i, f in enumerate(factors):
+        if len(set(f.vars)) != len(f.vars):
+            raise ValueError(f"factor {i} repeats a variable: {f.vars}")
+        for v in f.vars:
+            if v in owner:
+                parent[find(i)] = find(owner[v])
+            else:
+                owner[v] = i
+    groups = {}
+    for i in range(len(factors)):
+        groups.setdefault(find(i), []).append(i)
+    out = []
+    for root in sorted(groups, key=lambda r: min(groups[r])):
+        members = groups[root]
+        if len(members) == 1:
+            f = factors[members[0]]
+            out.append(Factor(tuple(f.vars), np.asarray(f.table, dtype=np.float64).copy()))
+            continue
+        vs = []
+        for i in members:
+            for v in factors[i].vars:
+                if v not in vs:
+                    vs.append(v)
+        if len(vs) > MAX_FACTOR_RANK:
+            raise ValueError(f"overlapping prior factors merge into rank {len(vs)} > {MAX_FACTOR_RANK}")
+        tab = np.ones(1 << len(vs))
+        a = np.arange(1 << len(vs))
+        for i in members:
+            f = factors[i]
+            idx = np.zeros_like(a)
+            for j, v in enumerate(f.vars):
+                idx |= ((a >> vs.index(v)) & 1) << j
+            tab = tab * np.asarray(f.table)[idx]
+        out.append(Factor(tuple(vs), tab))
+    covered = {v for f in out for v in f.vars}
+    for v in sorted(set(check_vars) - covered):
+        out.append(Factor((v,), np.ones(2)))
+    for f in out:
+        if len(f.vars) > MAX_FACTOR_RANK:
+            raise ValueError(f"prior factor of rank {len(f.vars)} > {MAX_FACTOR_RANK} is not supported")
+        if f.table.shape != (1 << len(f.vars),):
+            raise ValueError("factor table must have 2^rank entries")
+        if (f.table < 0).any() or not np.isfinite(f.table).all():
+            raise ValueError("prior factor entries must be finite and non-negative")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+class _Sim:
+    """Incremental frontier simulation used by the ordering heuristic."""
+
+    def __init__(self, factors, checks):
+        self.factors = factors
+        self.checks = checks
+        self.f_checks = [[] for _ in factors]                     # checks touched by each factor
+        var_owner = {v: i for i, f in enumerate(factors) for v in f.vars}
+        self.c_factors = []
+        for ci, c in enumerate(checks):
+            fs = sorted({var_owner[v] for v in c.vars})
+            self.c_factors.append(fs)
+            for fi in fs:
+                self.f_checks[fi].append(ci)
+        self.var_owner = var_owner
+
+    def step_cost(self, fi, remaining, live):
+        """(w_out, log2 work) of absorbing factor fi given `remaining[c]` = #factors of check c not yet absorbed."""
+        f = self.factors[fi]
+        opened = [c for c in self.f_checks[fi] if c not in live]
+        n_close = sum(1 for c in self.f_checks[fi] if remaining[c] == 1 and self.checks[c].kind == "syn")
+        w_out = len(live) + len(opened) - n_close
+        # rank of the opened part
+        rows = []
+        for v in f.vars:
+            m = 0
+            for k, c in enumerate(opened):
+                if v in self.checks[c].vars:
+                    m |= 1 << k
+            rows.append(m)
+        rank = _gf2_rank(rows)
+        return w_out, w_out + len(f.vars) - rank
+
+
+def _gf2_rank(rows):
+    rows = [r for r in rows if r]
+    rank = 0
+    while rows:
+        p = max(rows)
+        hb = p.bit_length() - 1
+        rows = [r ^ p if (r >> hb) & 1 else r for r in rows if r != p]
+        rows = [r for r in rows if r]
+        rank += 1
+    return rank
+
+
+def _evaluate(order, sim):
+    remaining = [len(fs) for fs in sim.c_factors]
+    live = set()
+    wmax, cost = 0, 0.0
+    for fi in order:
+        w_out, lw = sim.step_cost(fi, remaining, live)
+        for c in sim.f_checks[fi]:
+            live.add(c)
+        for c in sim.f_checks[fi]:
+            remaining[c] -= 1
+            if remaining[c] == 0 and sim.checks[c].kind == "syn":
+                live.discard(c)
+        wmax = max(wmax, w_out, w_out)
+        cost += 2.0 ** lw
+    return wmax, cost
+
+
+def _greedy_order(sim, start):
+    nF = len(sim.factors)
+    remaining = [len(fs) for fs in sim.c_factors]
+    live = set()
+    done = [False] * nF
+    order = []
+    cand = {start}
+    while len(order) < nF:
+        best = None
+        pool = cand if cand else {i for i in range(nF) if not done[i]}
+        for fi in pool:
+            w_out, lw = sim.step_cost(fi, remaining, live)
+            key = (w_out, lw, fi)
+            if best is None or key < best[0]:
+                best = (key, fi)
+        fi = best[1]
+        order.append(fi)
+        done[fi] = True
+        cand.discard(fi)
+        for c in sim.f_checks[fi]:
+            live.add(c)
+        for c in sim.f_checks[fi]:
+            remaining[c] -= 1
+            if remaining[c] == 0 and sim.checks[c].kind == "syn":
+                live.discard(c)
+        # neighbours: factors sharing a live check
+        for c in sim.f_checks[fi]:
+            for fj in sim.c_factors[c]:
+                if not done[fj]:
+                    cand.add(fj)
+    return order
+
+
+def choose_order(factors, checks, max_starts=24):
+    """Pick the absorption order: the best (by candidate evaluations per shot) of the natural order, its reverse,
+    and greedy minimum-frontier sweeps from several starting factors."""
+    sim = _Sim(factors, checks)
+    nF = len(factors)
+    cands = [list(range(nF)), list(range(nF - 1, -1, -1))]
+    deg = sorted(range(nF), key=lambda i: (len(sim.f_checks[i]), i))
+    starts = list(dict.fromkeys(deg[: max_starts // 2] + [0, nF - 1] + list(range(0, nF, max(1, nF // (max_starts // 2))))))
+    for s in starts[:max_starts]:
+        cands.append(_greedy_order(sim, s))
+    scored = [(_evaluate(o, sim), i) for i, o in enumerate(cands)]
+    (wmax, cost), i = min(scored, key=lambda x: (x[0][1], x[0][0], x[1]))
+    return cands[i]
+
+
+# ------------------------------------------------------------------------------------------------------------
+def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_vars: int, n_checks: int,
+          n_obs: int = 0, order: Optional[Sequence[int]] = None, max_width: int = MAX_SMEM_WIDTH) -> Schedule:
+    """Factor graph -> `Schedule` (see module docstring).  `order` optionally fixes the absorption order of the
+    (merged) factors, e.g. the leaf order of a contraction tree chosen by the caller's optimiser."""
+    all_check_vars = {v for c in checks for v in c.vars}
+    factors = merge_overlapping(list(factors), n_vars, all_check_vars)
+    checks = [Check(tuple(dict.fromkeys(c.vars)), c.kind, c.index) for c in checks]
+    for c in checks:
+        if c.kind not in ("syn", "obs"):
+            raise ValueError(f"unknown check kind {c.kind!r}")
+    if order is None:
+        order = choose_order(factors, checks)
+    order = list(order)
+    if sorted(order) != list(range(len(factors))):
+        raise ValueError("order must be a permutation of the (merged) factors")
+    sim = _Sim(factors, checks)
+    remaining = [len(fs) for fs in sim.c_factors]
+
+    live: List[int] = []
+    steps: List[Step] = []
+    # checks with no variable at all: open (and, if clamped, close) at the first step so that a non-zero syndrome
+    # bit on them makes the shot infeasible, as the dense parity tensor would.
+    orphan = [ci for ci, fs in enumerate(sim.c_factors) if not fs]
+    cost = 0.0
+    wmax = 0
+    for t, fi in enumerate(order):
+        f = factors[fi]
+        r = len(f.vars)
+        touched = list(sim.f_checks[fi])
+        if t == 0:
+            touched = touched + orphan
+        w_in = len(live)
+        opened = [c for c in touched if c not in live]
+        full = live + opened
+        pos = {c: k for k, c in enumerate(full)}
+        closing = []
+        for c in touched:
+            if c in orphan:
+                if checks[c].kind == "syn":
+                    closing.append(c)
+                continue
+            remaining[c] -= 1
+            if remaining[c] == 0 and checks[c].kind == "syn":
+                closing.append(c)
+        closed = sorted((pos[c], checks[c].index) for c in closing)
+        m = []
+        for v in f.vars:
+            mv = 0
+            for c in sim.f_checks[fi]:
+                if v in checks[c].vars:
+                    mv |= 1 << pos[c]
+            m.append(mv)
+        A = np.arange(1 << r)
+        M = np.zeros(1 << r, dtype=np.int64)
+        for j in range(r):
+            M ^= np.where((A >> j) & 1, m[j], 0)
+        n_open = len(opened)
+        pat = M >> w_in
+        a0 = np.full(1 << n_open, -1, dtype=np.int64)
+        for a in range((1 << r) - 1, -1, -1):
+            a0[pat[a]] = a                                   # smallest a of each coset
+        ker = np.flatnonzero(pat == 0).astype(np.int64)      # ascending, ker[0] = 0
+        live = [c for c in full if c not in closing]
+        w_out = len(live)
+        if semiring == MAXPLUS:
+            with np.errstate(divide="ignore"):
+                tab = np.log(f.table)
+        else:
+            tab = f.table.copy()
+        steps.append(Step(fi, tuple(f.vars), w_in, w_out, opened, closed, M, a0, ker, tab))
+        cost += float(1 << w_out) * len(ker)
+        wmax = max(wmax, w_in, w_out)                        # the full index is never materialised
+    if wmax > max_width:
+        raise ValueError(f"frontier needs {wmax} bits > {max_width}: the schedule does not fit the on-chip state "
+                         f"(wider plans need the global-memory executor, not built yet)")
+    obs_slot = [-1] * n_obs
+    for k, c in enumerate(live):
+        if checks[c].kind != "obs":
+            raise AssertionError("a clamped check survived the sweep")
+        obs_slot[checks[c].index] = k
+    if any(s < 0 for s in obs_slot) or len(live) != n_obs:
+        raise ValueError("every observable row must be declared exactly once")
+    sch = Schedule(semiring, n_vars, n_checks, n_obs, steps, obs_slot, order, factors, list(checks), wmax, cost)
+    _encode(sch)
+    return sch
+
+
+def _encode(s: Schedule):
+    """Flatten to the arrays `tqec_plan_create` ingests (include/tqec.h, `tqec_plan_desc`)."""
+    hdr = np.zeros((len(s.steps), HDR_INTS), dtype=np.int32)
+    ints: List[int] = []
+    tabs: List[float] = []
+    zero = -np.inf if s.semiring == MAXPLUS else 0.0
+    for t, st in enumerate(s.steps):
+        r = len(st.vars)
+        n_open = len(st.opened)
+        nk = len(st.ker)
+        inmask = (1 << st.w_in) - 1
+        h = hdr[t]
+        h[H_R], h[H_WIN], h[H_NOPEN], h[H_NCLOSE], h[H_WOUT] = r, st.w_in, n_open, len(st.closed), st.w_out
+        h[H_NK], h[H_KB] = nk, nk.bit_length() - 1
+        assert nk & (nk - 1) == 0
+        h[H_OFF_T] = len(tabs)
+        for p in range(1 << n_open):
+            for k in range(nk):
+                tabs.append(float(st.table[st.a0[p] ^ st.ker[k]]) if st.a0[p] >= 0 else zero)
+        h[H_OFF_ML] = len(ints)
+        ints += [int(st.M[st.a0[p]] & inmask) if st.a0[p] >= 0 else 0 for p in range(1 << n_open)]
+        h[H_OFF_MK] = len(ints)
+        ints += [int(st.M[k] & inmask) for k in st.ker]
+        h[H_OFF_A0] = len(ints)
+        ints += [int(st.a0[p]) if st.a0[p] >= 0 else 0 for p in range(1 << n_open)]
+        h[H_OFF_KER] = len(ints)
+        ints += [int(k) for k in st.ker]
+        h[H_OFF_VARS] = len(ints)
+        ints += [int(v) for v in st.vars]
+        h[H_OFF_CLOSE] = len(ints)
+        for slot, bit in st.closed:
+            ints += [int(slot), int(bit)]
+    s.hdr = hdr
+    s.ints = np.asarray(ints if ints else [0], dtype=np.int32)
+    s.tables = np.asarray(tabs if tabs else [0.0], dtype=np.float64)
