@@ -39,6 +39,8 @@ class Network:
     iy: List[int]
     evidence: Dict[int, int] = field(default_factory=dict)
     nvars: int = 0
+    ev_bit: Dict[int, int] = field(default_factory=dict)      # evidence label -> syndrome bit that clamps it
+    syn_leaf: Dict[int, int] = field(default_factory=dict)    # leaf index of a rank-1 syndrome vector -> syndrome bit
 
 
 def general_problem_css(tanner, px, py, pz):
@@ -71,7 +73,7 @@ def tnmap_network(nq, s2q, prior_ixs, priors, syndrome=None) -> Network:
         ixs.append(list(ix))
         tensors.append(np.asarray(t, dtype=np.float64))
     ev = {nq + s: int(0 if syndrome is None else syndrome[s]) for s in range(ns)}
-    return Network(ixs, tensors, [], ev, nvars)
+    return Network(ixs, tensors, [], ev, nvars, {nq + s: s for s in range(ns)})
 
 
 def tnmmap_css_network(tanner, lx, lz, px, py, pz, sx=None, sz=None) -> Network:
@@ -105,11 +107,13 @@ def tnmmap_css_network(tanner, lx, lz, px, py, pz, sx=None, sz=None) -> Network:
         syn[:nsx] = sx
     if sz is not None:
         syn[nsx:] = sz
+    syn_leaf = {}
     for j in range(nsyn):                       # rank-1 syndrome vectors (update_syndrome!, :148-158)
+        syn_leaf[len(ixs)] = j
         ixs.append([2 * n + j])
         tensors.append(np.array([0.0, 1.0]) if syn[j] else np.array([1.0, 0.0]))
     iy = list(range(2 * n + nsyn, nvars))
-    return Network(ixs, tensors, iy, {}, nvars)
+    return Network(ixs, tensors, iy, {}, nvars, {}, syn_leaf)
 
 
 def _push_check_node(ixs, tensors, c, check_label, nvars, factorize):
@@ -146,8 +150,10 @@ def tnmmap_dem_network(error_rates, flipped, n_det, n_obs, syndrome=None, factor
     for e, p in enumerate(error_rates):
         ixs.append([e])
         tensors.append(np.array([1.0 - p, p]))
+    syn_leaf = {}
     for d in range(n_det):
+        syn_leaf[len(ixs)] = d
         ixs.append([ne + d])
         s = 0 if syndrome is None else int(syndrome[d])
         tensors.append(np.array([0.0, 1.0]) if s else np.array([1.0, 0.0]))
-    return Network(ixs, tensors, iy, {}, nvars)
+    return Network(ixs, tensors, iy, {}, nvars, {}, syn_leaf)

@@ -32,7 +32,7 @@ class SimpleTannerGraph(AbstractTannerGraph):
     s2q: List[List[int]]
     H: np.ndarray
 
-    def __init__(self, nq, sts=None, *, H=None):
+    def __init__(self, nq=None, sts=None, *, H=None):
         # SimpleTannerGraph(nq, sts) (ldpc.jl:44-52)  or  SimpleTannerGraph(H) (ldpc.jl:53-58)
         if sts is None and H is None and not isinstance(nq, (int, np.integer)):
             H, nq = nq, None

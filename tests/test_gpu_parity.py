@@ -1,0 +1,296 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle.  Integer / index results are compared bit for bit;
+FP64 marginals within 1e-10 relative (the tolerance BASELINE.json's north_star states); MAP log-weights bit for bit
+(each candidate is one IEEE add and max is exact, so the recurrence is reproducible)."""
+import numpy as np
+import pytest
+
+from oracle import bruteforce, cref, emulator, frontier, gf2, networks, philox
+
+pytestmark = pytest.mark.gpu
+
+MAR_RTOL = 1e-10
+
+
+def _css_case(tq, code, p=0.05, pvec=None):
+    t = tq.CSSTannerGraph(code)
+    em = tq.iid_error(p, t) if pvec is None else pvec
+    return t, em
+
+
+def _syndromes(t, em, seed, B):
+    ex, ez = philox.sample_depolarizing(em.px, em.py, em.pz, seed, 0, B)
+    sx, sz = gf2.css_syndrome(ex, ez, t.stgx.H, t.stgz.H)
+    return ex, ez, sx, sz
+
+
+def test_tnmap_d3_all_syndromes_exhaustive(tq):
+    t, em = _css_case(tq, tq.SurfaceCode(3, 3))
+    ct = tq.compile(tq.TNMAP(), t, em)
+    syn = ((np.arange(256)[:, None] >> np.arange(8)) & 1).astype(np.uint8)
+    res = tq.decode(ct, tq.CSSSyndrome(syn[:, :4], syn[:, 4:]))
+    sch = ct.cd.schedule
+    lp, cfg = frontier.run(sch.factors, sch.checks, sch.order, 0, syn, 18)
+    got = np.concatenate([res.error_pattern.xerror, res.error_pattern.zerror], axis=1)
+    assert np.array_equal(got, cfg)
+    assert np.array_equal(res.logp, lp)
+    # against exhaustive enumeration: the value is the maximum, the pattern is one of the maximisers
+    nq, s2q, pix, pri = networks.general_problem_css(t, em.px, em.py, em.pz)
+    en = bruteforce.Enumeration(nq, s2q, pix, pri)
+    for b in range(256):
+        best, maxs = en.map(syn[b])
+        assert abs(best - lp[b]) <= 1e-12 * abs(best)
+        assert any(np.array_equal(got[b], m) for m in maxs)
+
+
+@pytest.mark.parametrize("d,B", [(5, 4096), (7, 2048), (9, 1024)])
+def test_tnmap_surface_matches_oracle_bit_exact(tq, d, B):
+    t, em = _css_case(tq, tq.SurfaceCode(d, d))
+    ct = tq.compile(tq.TNMAP(), t, em)
+    ex, ez, sx, sz = _syndromes(t, em, 1000 * d, B)
+    res = tq.decode(ct, tq.CSSSyndrome(sx, sz))
+    sch = ct.cd.schedule
+    lp, cfg = cref.FrontierPlan(sch).run(np.concatenate([sx, sz], axis=1))
+    n = d * d
+    assert np.array_equal(res.error_pattern.xerror, cfg[:, :n])
+    assert np.array_equal(res.error_pattern.zerror, cfg[:, n:])
+    assert np.array_equal(res.logp, lp)
+    # the numpy statement of the recurrence agrees with its C port on a subset
+    lp2, cfg2 = frontier.run(sch.factors, sch.checks, sch.order, 0, np.concatenate([sx, sz], axis=1)[:128], 2 * n)
+    assert np.array_equal(lp2, lp[:128]) and np.array_equal(cfg2, cfg[:128])
+    # decoded pattern reproduces the syndrome (the reference's own assertion, test/decoding/tndecoder.jl:57)
+    assert tq.syndrome_extraction(res.error_pattern, t) == tq.CSSSyndrome(sx, sz)
+
+
+def test_tnmap_matches_dense_reference_value(tq):
+    """MAP value equals the dense (reference-style) contraction; the pattern has that weight and the syndrome."""
+    d = 5
+    rng = np.random.default_rng(d)
+    n = d * d
+    em = tq.IndependentDepolarizingError(rng.uniform(0.01, 0.1, n), rng.uniform(0.01, 0.1, n), rng.uniform(0.01, 0.1, n))
+    t = tq.CSSTannerGraph(tq.SurfaceCode(d, d))
+    ct = tq.compile(tq.TNMAP(), t, em)
+    ex, ez, sx, sz = _syndromes(t, em, 11, 256)
+    res = tq.decode(ct, tq.CSSSyndrome(sx, sz))
+    nq, s2q, pix, pri = networks.general_problem_css(t, em.px, em.py, em.pz)
+    dp = cref.DensePlan(networks.tnmap_network(nq, s2q, pix, pri), len(s2q), nq, True)
+    lp, cfg = dp.run(np.concatenate([sx, sz], axis=1))
+    assert np.allclose(res.logp, lp, rtol=1e-12, atol=0)
+    # random per-qubit noise: the maximiser is unique, so the patterns coincide with the reference-style contraction
+    got = np.concatenate([res.error_pattern.xerror, res.error_pattern.zerror], axis=1)
+    assert np.array_equal(got, cfg)
+
+
+@pytest.mark.parametrize("code", ["steane", "color488_5"])
+def test_tnmap_small_codes(tq, code):
+    c = tq.SteaneCode() if code == "steane" else tq.Color488(5)
+    t, em = _css_case(tq, c)
+    ct = tq.compile(tq.TNMAP(), t, em)
+    ex, ez, sx, sz = _syndromes(t, em, 5, 1000)
+    res = tq.decode(ct, tq.CSSSyndrome(sx, sz))
+    sch = ct.cd.schedule
+    lp, cfg = cref.FrontierPlan(sch).run(np.concatenate([sx, sz], axis=1))
+    n = t.stgx.nq
+    assert np.array_equal(np.concatenate([res.error_pattern.xerror, res.error_pattern.zerror], axis=1), cfg)
+    assert np.array_equal(res.logp, lp)
+    assert tq.syndrome_extraction(res.error_pattern, t) == tq.CSSSyndrome(sx, sz)
+
+
+def test_tnmap_single_shot_and_classical(tq):
+    t = tq.CSSTannerGraph(tq.SurfaceCode(3, 3))
+    ct = tq.compile(tq.TNMAP(), t.stgz)                      # classical problem, iid_error(0.05, n) default
+    e = np.array([0, 0, 0, 0, 1, 0, 0, 0, 0], dtype=np.uint8)
+    syn = tq.syndrome_extraction(e, t.stgz)
+    res = tq.decode(ct, syn)
+    assert res.error_pattern.shape == (9,)
+    assert syn == tq.syndrome_extraction(res.error_pattern, t.stgz)
+    res2 = tq.decode(tq.TNMAP(), t.stgz, syn)
+    assert np.array_equal(res2.error_pattern, res.error_pattern)
+
+
+def test_tnmap_correlated_prior(tq):
+    """test/decoding/general_decoding.jl:24-46: a rank-4 prior tensor on (x4, z4, x7, z7) (0-based qubits 3 and 6)."""
+    t = tq.CSSTannerGraph(tq.SurfaceCode(3, 3))
+    n = 9
+    singles = [0, 1, 2, 4, 5, 7, 8]
+    a = np.zeros((2, 2, 2, 2))
+    a[0, 0, 0, 0] = 0.99
+    a[0, 0, 1, 1] = 0.01
+    tn = tq.SimpleTensorNetwork([[i, i + n] for i in singles] + [[3, 3 + n, 6, 6 + n]],
+                                [tq.single_qubit_tensor(0.05, 0.03, 0.01) for _ in singles] + [a])
+    gdp, red = tq.reduce2general(t, tn)
+    ct = tq.compile(tq.TNMAP(), gdp)
+    syn = ((np.arange(256)[:, None] >> np.arange(8)) & 1).astype(np.uint8)
+    res = tq.decode(ct, tq.SimpleSyndrome(syn))
+    nq, s2q = 18, [list(c) for c in gdp.tanner.s2q]
+    en = bruteforce.Enumeration(nq, s2q, tn.ixs, tn.tensors)
+    for b in range(256):
+        best, maxs = en.map(syn[b])
+        if np.isfinite(best):
+            assert res.success_tag[b]
+            assert abs(best - res.logp[b]) <= 1e-12 * abs(best)
+            assert any(np.array_equal(res.error_pattern[b], m) for m in maxs)
+        else:
+            assert not res.success_tag[b]
+
+
+def test_tnmmap_golden_marginal(tq):
+    """test/decoding/tndecoder.jl:101-110: the only numeric contraction golden of the reference."""
+    t = tq.CSSTannerGraph(tq.SurfaceCode(3, 3))
+    p = np.full(9, 0.1)
+    ct = tq.compile(tq.TNMMAP(), t, tq.IndependentDepolarizingError(p, np.zeros(9), np.zeros(9)))
+    mar = ct.marginal(tq.CSSSyndrome(np.zeros(4, dtype=np.uint8), np.zeros(4, dtype=np.uint8)))
+    assert np.allclose(mar, [[0.3972875040000002, 0.004284496000000001], [0.0, 0.0]], atol=1e-10)
+
+
+def test_tnmmap_d3_vs_bruteforce_and_error_pattern(tq):
+    rng = np.random.default_rng(3)
+    t = tq.CSSTannerGraph(tq.SurfaceCode(3, 3))
+    em = tq.IndependentDepolarizingError(rng.uniform(0.01, 0.1, 9), rng.uniform(0.01, 0.1, 9), rng.uniform(0.01, 0.1, 9))
+    ct = tq.compile(tq.TNMMAP(), t, em)
+    syn = ((np.arange(256)[:, None] >> np.arange(8)) & 1).astype(np.uint8)
+    css = tq.CSSSyndrome(syn[:, :4], syn[:, 4:])
+    res = tq.decode(ct, css)
+    lx, lz = tq.logical_operator(t)
+    nq, s2q, pix, pri = networks.general_problem_css(t, em.px, em.py, em.pz)
+    en = bruteforce.Enumeration(nq, s2q, pix, pri)
+    Lg = np.zeros((2, 18), dtype=np.uint8)
+    Lg[0, 9:] = lx[0]
+    Lg[1, :9] = lz[0]
+    for b in range(256):
+        ref = en.marginal(syn[b], Lg)
+        got = res.marginal[b].reshape(-1, order="F")
+        assert np.allclose(got, ref, rtol=MAR_RTOL, atol=0)
+        assert res.sector[b] == int(np.argmax(ref))
+    # error pattern: reproduces the syndrome and lies in the decoded sector (tndecoder.jl:167-174)
+    assert tq.syndrome_extraction(res.error_pattern, t) == css
+    a = (res.error_pattern.zerror @ lx[0]) & 1
+    bb = (res.error_pattern.xerror @ lz[0]) & 1
+    assert np.array_equal(a + 2 * bb, res.sector)
+
+
+@pytest.mark.parametrize("d", [5, 7])
+def test_tnmmap_surface_vs_dense_reference(tq, d):
+    t, em = _css_case(tq, tq.SurfaceCode(d, d), pvec=tq.iid_error(0.04, 0.02, 0.06, d * d))
+    ct = tq.compile(tq.TNMMAP(), t, em)
+    B = 256 if d == 5 else 32
+    ex, ez, sx, sz = _syndromes(t, em, 77, B)
+    mar = ct.marginal(tq.CSSSyndrome(sx, sz)).reshape(B, -1, order="F")
+    lx, lz = tq.logical_operator(t)
+    dp = cref.DensePlan(networks.tnmmap_css_network(t, lx, lz, em.px, em.py, em.pz), 2 * t.stgx.ns, 2 * d * d, False)
+    ref = dp.run(np.concatenate([sx, sz], axis=1))
+    assert np.allclose(mar, ref, rtol=MAR_RTOL, atol=1e-300)
+
+
+def test_gf2_kernels_bit_exact(tq):
+    rng = np.random.default_rng(0)
+    for rows, cols in [(2, 5), (40, 81), (80, 162), (130, 300), (1, 1)]:
+        H = rng.integers(0, 2, size=(rows, cols)).astype(np.uint8)
+        e = rng.integers(0, 2, size=(777, cols)).astype(np.uint8)
+        assert np.array_equal(tq.syndrome_extraction(e, H).s, gf2.syndrome_extraction(e, H))
+    # the reference's known answers (test/codes/ldpc.jl:34-39, test/decoding/error_model.jl:21-27)
+    tg = tq.SimpleTannerGraph(5, [[0, 1, 2, 3], [1, 2, 3, 4]])
+    assert list(tq.syndrome_extraction(np.array([1, 0, 1, 1, 0]), tg).s) == [1, 0]
+    t = tq.CSSTannerGraph(tq.SurfaceCode(3, 3))
+    lx, lz = tq.logical_operator(t)
+    z9 = np.zeros(9, dtype=np.uint8)
+    assert tq.check_logical_error(z9, np.array([1, 1, 1, 0, 0, 0, 0, 0, 0]), lz) is True
+    assert tq.check_logical_error(z9, np.array([1, 1, 0, 1, 1, 0, 0, 0, 0]), lz) is False
+    assert tq.check_logical_error(tq.CSSErrorPattern(z9, z9), tq.CSSErrorPattern(z9, z9), lx, lz) is False
+
+
+def test_sampler_bit_exact_and_offset_invariant(tq):
+    em = tq.iid_error(0.05, 0.06, 0.1, 81)
+    ep = tq.random_error_pattern(em, seed=12345, shots=5000)
+    ox, oz = philox.sample_depolarizing(em.px, em.py, em.pz, 12345, 0, 5000)
+    assert np.array_equal(ep.xerror, ox) and np.array_equal(ep.zerror, oz)
+    ep2 = tq.random_error_pattern(em, seed=12345, shots=1000, shot_offset=4000)
+    assert np.array_equal(ep2.xerror, ox[4000:]) and np.array_equal(ep2.zerror, oz[4000:])
+    # rates (test/decoding/error_model.jl:10-19)
+    assert abs(ep.xerror.mean() - 0.11) < 0.01 and abs(ep.zerror.mean() - 0.16) < 0.01
+    fl = tq.iid_error(0.1, 100)
+    assert np.array_equal(tq.random_error_pattern(fl, seed=(1 << 40) + 5, shots=300), philox.sample_flips(fl.p, (1 << 40) + 5, 0, 300))
+    one = tq.random_error_pattern(fl, seed=3)
+    assert one.shape == (100,)
+
+
+@pytest.mark.parametrize("d,shots", [(3, 20000), (5, 20000)])
+def test_fused_pipeline_counts_bit_exact(tq, d, shots):
+    t, em = _css_case(tq, tq.SurfaceCode(d, d))
+    mc = tq.MonteCarlo(t, tq.TNMAP(), em)
+    counts, ms = mc.run(shots, seed=42, chunk=6000)
+    ex, ez, sx, sz = _syndromes(t, em, 42, shots)
+    sch = mc.compiled.cd.schedule
+    _, cfg = cref.FrontierPlan(sch).run(np.concatenate([sx, sz], axis=1))
+    n = d * d
+    lx, lz = tq.logical_operator(t)
+    fx = gf2.check_logical_error(ex, cfg[:, :n], lz)
+    fz = gf2.check_logical_error(ez, cfg[:, n:], lx)
+    assert list(counts) == [int(fx.sum()), int(fz.sum()), int((fx | fz).sum()), shots]
+    # splitting the run over shot ranges (what the GPU sharding does) gives the same totals
+    c1, _ = mc.run(shots // 2, seed=42)
+    c2, _ = mc.run(shots - shots // 2, seed=42, shot_offset=shots // 2)
+    assert list(c1 + c2) == list(counts)
+    rates = tq.multi_round_qec(t, tq.TNMAP(), em, rounds=shots, seed=42)
+    assert rates == (counts[0] / shots, counts[1] / shots, counts[2] / shots)
+
+
+def test_dem_tnmmap(tq):
+    import os
+    dem = tq.parse_dem_file(os.path.join(os.path.dirname(__file__), "golden", "dem.dem"))
+    ct = tq.compile(tq.TNMMAP(), dem)
+    ep = tq.random_error_pattern(dem, seed=12323, shots=512)
+    syn = tq.syndrome_extraction(ep, ct.tanner)
+    res = tq.decode(ct, syn)
+    # the reference's assertion (test/decoding/tndecoder.jl:112-120)
+    assert syn == tq.syndrome_extraction(res.error_pattern, ct.tanner)
+    # marginals against exhaustive enumeration over the 2^21 mechanism patterns
+    flipped = dem.flipped_detectors
+    nd = dem.n_detectors
+    en = bruteforce.Enumeration(21, ct.tanner.s2q, [[e] for e in range(21)], [np.array([1 - p, p]) for p in dem.error_rates])
+    L = np.zeros((1, 21), dtype=np.uint8)
+    L[0, ct.l2q[0]] = 1
+    for b in range(64):
+        ref = en.marginal(syn.s[b], L)
+        assert np.allclose(res.marginal[b], ref, rtol=MAR_RTOL, atol=0)
+        assert res.sector[b] == int(np.argmax(ref))
+    # dense reference network with and without the rank-3 factorisation (tndecoder.jl:221-238)
+    for fac in (True, False):
+        net = networks.tnmmap_dem_network(dem.error_rates, flipped, nd, 1, factorize=fac)
+        ref = cref.DensePlan(net, nd, 21, False).run(syn.s[:64])
+        assert np.allclose(res.marginal[:64].reshape(64, -1), ref, rtol=MAR_RTOL, atol=0)
+
+
+def test_property_full_size_d9(tq):
+    """BASELINE config 3 shape (d=9, p=0.05) at a size the oracle cannot follow shot by shot: size-independent
+    properties -- every correction reproduces its syndrome, decoding is idempotent on its own output's syndrome,
+    and the fused pipeline's counters equal the counters recomputed from the unfused stages."""
+    d, B = 9, 200_000
+    t, em = _css_case(tq, tq.SurfaceCode(d, d))
+    mc = tq.MonteCarlo(t, tq.TNMAP(), em)
+    counts, _ = mc.run(B, seed=9)
+    ep = tq.random_error_pattern(em, seed=9, shots=B)
+    syn = tq.syndrome_extraction(ep, t)
+    res = tq.decode(mc.compiled, syn)
+    assert tq.syndrome_extraction(res.error_pattern, t) == syn
+    lx, lz = tq.logical_operator(t)
+    fl = tq.check_logical_error(ep, res.error_pattern, lx, lz)
+    assert counts[2] == int(fl.sum()) and counts[3] == B
+    res2 = tq.decode(mc.compiled, tq.syndrome_extraction(res.error_pattern, t))
+    assert np.array_equal(res2.error_pattern.xerror, res.error_pattern.xerror)
+    assert np.array_equal(res2.logp, res.logp)
+    # the MAP weight is at least the weight of the true error
+    T = np.log(np.array([[0.85, 0.05], [0.05, 0.05]]))
+    assert (res.logp >= T[ep.xerror, ep.zerror].sum(axis=1) - 1e-9).all()
+
+
+def test_error_behaviour(tq):
+    t = tq.CSSTannerGraph(tq.SurfaceCode(3, 3))
+    ct = tq.compile(tq.TNMAP(), t)
+    with pytest.raises(ValueError):
+        tq.decode(ct, tq.CSSSyndrome(np.zeros(3, dtype=np.uint8), np.zeros(4, dtype=np.uint8)))
+    with pytest.raises(TypeError):
+        tq.decode(ct, tq.SimpleSyndrome(np.zeros(8, dtype=np.uint8)))
+    with pytest.raises(tq.TqecError):
+        tq.compile(tq.TNMAP(device=99), t)
+    empty = tq.decode(ct, tq.CSSSyndrome(np.zeros((0, 4), dtype=np.uint8), np.zeros((0, 4), dtype=np.uint8)))
+    assert empty.error_pattern.xerror.shape == (0, 9)
