@@ -154,6 +154,12 @@ typedef struct {
 int tqec_mc_run(const tqec_mc_desc *mc, uint64_t seed, int64_t shot_offset, int64_t n_shots, int64_t counts[4],
                 float *elapsed_ms);
 
+/* ---- measurement helper -------------------------------------------------------------------------------------- */
+/* FP64 CUDA-core peak of the device, measured with register-resident chains: DADD instructions/s (T/s), DFMA
+ * TFLOP/s (2 flops each), and the max-plus candidate rate counted as 2 ops (add + compare) in Tops/s.  Roofline
+ * denominator of the decode kernels (MEASURED_PEAKS.json has no FP64 entry). */
+int tqec_fp64_peak(int32_t device, double *dadd_tops, double *dfma_tflops, double *maxplus_tops);
+
 #ifdef __cplusplus
 }
 #endif

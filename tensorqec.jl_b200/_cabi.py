@@ -24,7 +24,7 @@ EXPORTS = [
     "tqec_plan_create", "tqec_plan_destroy", "tqec_plan_query",
     "tqec_decode_map", "tqec_decode_map_dev", "tqec_decode_marginal", "tqec_decode_marginal_dev",
     "tqec_gf2_create", "tqec_gf2_destroy", "tqec_gf2_apply", "tqec_gf2_apply_dev",
-    "tqec_logical_flags", "tqec_coset_rep", "tqec_sample_errors", "tqec_mc_run",
+    "tqec_logical_flags", "tqec_coset_rep", "tqec_sample_errors", "tqec_mc_run", "tqec_fp64_peak",
 ]
 
 
@@ -77,6 +77,7 @@ def lib():
     L.tqec_coset_rep.argtypes = [vp, vp, vp, vp, vp, i64, vp]
     L.tqec_sample_errors.argtypes = [i32, i32, vp, vp, vp, u64, i64, i64, vp, i32]
     L.tqec_mc_run.argtypes = [C.POINTER(McDesc), u64, i64, i64, vp, vp]
+    L.tqec_fp64_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -100,6 +101,14 @@ def require_device(device: int = 0):
         raise TqecError(f"no usable CUDA device: {e} (the decoding path has no CPU fallback)") from None
     if n <= device:
         raise TqecError(f"CUDA device {device} requested but {n} visible (the decoding path has no CPU fallback)")
+
+
+def fp64_peak(device: int = 0):
+    """-> dict(dadd_tops, dfma_tflops, maxplus_tops) measured on `device`."""
+    require_device(device)
+    a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)
+    check(lib().tqec_fp64_peak(device, C.byref(a), C.byref(b), C.byref(c)))
+    return {"dadd_tops": a.value, "dfma_tflops": b.value, "maxplus_tops": c.value}
 
 
 def _ptr(a: np.ndarray):

@@ -445,3 +445,67 @@ extern "C" int tqec_mc_run(const tqec_mc_desc *mc, uint64_t seed, int64_t shot_o
   if (e1) cudaEventDestroy(e1);
   return rc;
 }
+
+// ---- FP64-pipe peak (roofline denominator of the max-plus / sum-product kernels) ------------------------------------
+// MEASURED_PEAKS.json carries HBM and bf16 tensor peaks only; the decode kernels are bound by the FP64 CUDA-core pipe
+// (DADD + DSETP for max-plus, DFMA for sum-product), so the denominator is measured here: register-resident,
+// 8 independent dependency chains per thread, every SM filled.
+template <int MODE>
+__global__ void k_fp64_peak(double *out, int iters, double seed) {
+  double a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = seed + threadIdx.x * 1e-9 + i;
+  const double b = seed * 1e-6 + 1.0000001, c = 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (MODE == 0) a[i] = a[i] + b;                 // DADD
+      else if (MODE == 1) a[i] = fma(a[i], b, c);     // DFMA
+      else a[i] = (a[i] + b > a[(i + 1) & 7]) ? a[i] + b : a[(i + 1) & 7];  // DADD + DSETP + select (max-plus candidate)
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i];
+  if (s == 12345.678) out[0] = s;
+}
+
+extern "C" int tqec_fp64_peak(int32_t device, double *dadd_tops, double *dfma_tflops, double *maxplus_tops) {
+  TQEC_REQUIRE(dadd_tops && dfma_tflops && maxplus_tops, "tqec_fp64_peak: NULL output");
+  int ndev = 0;
+  TQEC_CUDA(cudaGetDeviceCount(&ndev));
+  TQEC_REQUIRE(device >= 0 && device < ndev, "tqec_fp64_peak: device %d not present (%d visible)", device, ndev);
+  TQEC_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  TQEC_CUDA(cudaGetDeviceProperties(&prop, device));
+  double *d_out = nullptr;
+  TQEC_CUDA(cudaMalloc((void **)&d_out, 64));
+  cudaEvent_t e0, e1;
+  TQEC_CUDA(cudaEventCreate(&e0));
+  TQEC_CUDA(cudaEventCreate(&e1));
+  const int threads = 512, blocks = prop.multiProcessorCount * 4, iters = 1 << 14;
+  double res[3] = {0, 0, 0};
+  for (int mode = 0; mode < 3; ++mode) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+      TQEC_CUDA(cudaEventRecord(e0, 0));
+      if (mode == 0) k_fp64_peak<0><<<blocks, threads>>>(d_out, iters, 1.0);
+      else if (mode == 1) k_fp64_peak<1><<<blocks, threads>>>(d_out, iters, 1.0);
+      else k_fp64_peak<2><<<blocks, threads>>>(d_out, iters, 1.0);
+      TQEC_CUDA(cudaEventRecord(e1, 0));
+      TQEC_CUDA(cudaEventSynchronize(e1));
+      float ms = 0;
+      TQEC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      if (rep > 0 && ms < best) best = ms;
+    }
+    const double ops = (double)blocks * threads * iters * 8.0;
+    res[mode] = ops / (best * 1e-3) / 1e12;
+  }
+  *dadd_tops = res[0];
+  *dfma_tflops = 2.0 * res[1];
+  *maxplus_tops = 2.0 * res[2];      // one add + one compare per candidate
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  return TQEC_OK;
+}

@@ -93,6 +93,8 @@ def unpack_bits(words: np.ndarray, nbits: int) -> np.ndarray:
     if words.ndim == 1:
         words = words[None, :]
     B = words.shape[0]
+    if B == 0:
+        return np.zeros((0, nbits), dtype=np.uint8)
     by = words.view(np.uint8).reshape(B, -1)
     return np.unpackbits(by, axis=1, bitorder="little")[:, :nbits].copy()
 
