@@ -31,6 +31,8 @@ void set_error(const char *fmt, ...);
     }                                  \
   } while (0)
 
+#define TQEC_H_FAST 14  // internal: header slot 14 (reserved in the ABI) carries the per-step fast-path flag
+
 static inline int words_for(int nbits) { return nbits <= 0 ? 1 : (nbits + 63) / 64; }
 
 // Device view of a compiled schedule (passed to kernels by value).
@@ -45,6 +47,7 @@ struct PlanDev {
   int32_t sg_log2;         // log2(shots per team)
   int32_t nsw, ncw;        // syndrome / configuration words per shot
   int32_t bp_words;        // back-pointer words per team
+  int32_t n_ints, n_tables; // pool sizes (for the shared-memory copies of warp teams)
 };
 
 }  // namespace tqec
@@ -54,6 +57,8 @@ struct tqec_plan {
   int device;
   int semiring;
   int team_threads;
+  int warp_teams;        // 1: k_frontier_warp (a team is a warp, tables in shared memory); 0: k_frontier_cta
+  int teams_per_cta;
   int shots_per_team;
   int smem_bytes;
   int grid_max;          // persistent grid size (teams resident on the whole GPU)

@@ -1,90 +1,87 @@
 // Frontier-recurrence decoding kernels (TNMAP max-plus with traceback, TNMMAP sum-product) for sm_100a.
 //
-// One TEAM (= one CTA of `team_threads` threads) owns 2^sg_log2 shots at a time and keeps their whole state
-// tensor S[sub][sigma] (FP64, <= 2^(w_max+sg_log2) entries, ping-pong) in shared memory; nothing but the
-// bit-packed syndromes (in), the corrections / marginals (out) and 1..kb back-pointer bits per state entry
-// (L2-resident scratch, max-plus only) ever touches global memory.  The grid is persistent: teams stride over
-// shot groups.  See tensorqec.jl_b200/schedule.py for the recurrence and the table layout, DESIGN.md for the
-// roofline argument (FP64-pipe / issue bound, not HBM bound).
+// A TEAM owns 2^sg_log2 shots at a time and keeps their whole state tensor S[sub][sigma] (FP64, <= 2^(w_max+sg_log2)
+// entries, ping-pong) in shared memory; nothing but the bit-packed syndromes (in), the corrections / marginals (out)
+// and 1..kb back-pointer bits per state entry (L2-resident scratch, max-plus only) ever touches global memory.
+// Two launch shapes share one body:
+//   warp teams (WT = true) : a team is ONE WARP; a CTA holds as many independent warp-teams as shared memory allows
+//                            plus one copy of the schedule tables, so every table read is an LDS and steps are
+//                            separated by __syncwarp only.  Used whenever the state fits 1024 entries per team.
+//   CTA teams  (WT = false): a team is a whole CTA of 32..256 threads, tables stay in global memory (L1/L2), steps are
+//                            separated by __syncthreads.  Used for wide frontiers (w_max > 10) or oversized tables.
+// The grid is persistent: teams stride over shot groups.  See tensorqec.jl_b200/schedule.py for the recurrence and the
+// table layout, DESIGN.md for the roofline argument (FP64-pipe / issue bound, not HBM bound).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "tqec_common.h"
 
 namespace tqec {
 
+template <bool SM> __device__ __forceinline__ int ldi(const int32_t *p) { return SM ? *p : __ldg(p); }
+template <bool SM> __device__ __forceinline__ double ldd(const double *p) { return SM ? *p : __ldg(p); }
+template <bool WT> __device__ __forceinline__ void team_sync() {
+  if (WT) __syncwarp(); else __syncthreads();
+}
+
+// schedule tables as seen by a team (shared-memory copies for warp teams, global memory otherwise)
+struct Tabs {
+  const int32_t *hdr, *ints, *bp_off, *obs_slot;
+  const double *tables;
+};
+
 __device__ __forceinline__ int insert_bit(int x, int slot, int bit) {
   return ((x >> slot) << (slot + 1)) | (bit << slot) | (x & ((1 << slot) - 1));
 }
 
+template <bool SM>
 __device__ __forceinline__ int rebuild_full(int tau, int sub, int n_close, const int32_t *__restrict__ CL,
                                             const uint64_t *__restrict__ sh_syn, int nsw) {
   int full = tau;
   for (int c = 0; c < n_close; ++c) {
-    const int slot = __ldg(CL + 2 * c), bit = __ldg(CL + 2 * c + 1);
+    const int slot = ldi<SM>(CL + 2 * c), bit = ldi<SM>(CL + 2 * c + 1);
     const int sb = (int)((sh_syn[sub * nsw + (bit >> 6)] >> (bit & 63)) & 1ull);
     full = insert_bit(full, slot, sb);
   }
   return full;
 }
 
-template <int SEMI, int NK>
-__device__ __forceinline__ void run_step(const PlanDev &P, const int32_t *__restrict__ h, const double *__restrict__ Sin,
-                                         double *__restrict__ Sout, const uint64_t *__restrict__ sh_syn,
-                                         uint32_t *__restrict__ bpt, int T, int tid) {
-  const int w_in = h[TQEC_H_WIN], n_close = h[TQEC_H_NCLOSE], w_out = h[TQEC_H_WOUT];
-  const int nk = NK > 0 ? NK : h[TQEC_H_NK];
-  const int kb = h[TQEC_H_KB];
-  const double *__restrict__ Tt = P.tables + h[TQEC_H_OFF_T];
-  const int32_t *__restrict__ ML = P.ints + h[TQEC_H_OFF_ML];
-  const int32_t *__restrict__ MK = P.ints + h[TQEC_H_OFF_MK];
-  const int32_t *__restrict__ CL = P.ints + h[TQEC_H_OFF_CLOSE];
+// ---- generic step: any geometry, per-element index arithmetic ------------------------------------------------------
+template <int SEMI, int NK, bool SM>
+__device__ __forceinline__ void run_step(const PlanDev &P, const Tabs &X, const int32_t *__restrict__ h,
+                                         const double *__restrict__ Sin, double *__restrict__ Sout,
+                                         const uint64_t *__restrict__ sh_syn, uint32_t *__restrict__ bpt, int T, int tid) {
+  const int w_in = ldi<SM>(h + TQEC_H_WIN), n_close = ldi<SM>(h + TQEC_H_NCLOSE), w_out = ldi<SM>(h + TQEC_H_WOUT);
+  const int nk = NK > 0 ? NK : ldi<SM>(h + TQEC_H_NK);
+  const int kb = ldi<SM>(h + TQEC_H_KB);
+  const double *__restrict__ Tt = X.tables + ldi<SM>(h + TQEC_H_OFF_T);
+  const int32_t *__restrict__ ML = X.ints + ldi<SM>(h + TQEC_H_OFF_ML);
+  const int32_t *__restrict__ MK = X.ints + ldi<SM>(h + TQEC_H_OFF_MK);
+  const int32_t *__restrict__ CL = X.ints + ldi<SM>(h + TQEC_H_OFF_CLOSE);
   const int n_tot = 1 << (w_out + P.sg_log2);
   const int inmask = (1 << w_in) - 1, outmask = (1 << w_out) - 1;
   const int per_word = kb ? 32 / kb : 1;
-  int mk[NK > 0 ? NK : 1];
-  if (NK > 0) {
-#pragma unroll
-    for (int k = 0; k < NK; ++k) mk[k] = __ldg(MK + k);
-  }
   uint32_t word = 0;
   int jw = 0, wi = 0;
   for (int e = tid; e < n_tot; e += T) {
     const int tau = e & outmask, sub = e >> w_out;
-    const int full = rebuild_full(tau, sub, n_close, CL, sh_syn, P.nsw);
+    const int full = rebuild_full<SM>(tau, sub, n_close, CL, sh_syn, P.nsw);
     const int pat = full >> w_in;
-    const int low = (full & inmask) ^ __ldg(ML + pat);
+    const int low = (full & inmask) ^ ldi<SM>(ML + pat);
     const double *__restrict__ tb = Tt + pat * nk;
     const double *__restrict__ Sb = Sin + (sub << w_in);
-    double best;
+    const double s0 = Sb[low ^ ldi<SM>(MK)], t0 = ldd<SM>(tb);
+    double best = SEMI == TQEC_SEMIRING_MAXPLUS ? s0 + t0 : s0 * t0;
     int bk = 0;
-    if (NK > 0) {
-      double v[NK > 0 ? NK : 1];
 #pragma unroll
-      for (int k = 0; k < NK; ++k) {
-        const double s = Sb[low ^ mk[k]], tv = __ldg(tb + k);
-        v[k] = SEMI == TQEC_SEMIRING_MAXPLUS ? s + tv : s * tv;
-      }
-      best = v[0];
-#pragma unroll
-      for (int k = 1; k < NK; ++k) {
-        if (SEMI == TQEC_SEMIRING_MAXPLUS) {
-          if (v[k] > best) { best = v[k]; bk = k; }
-        } else {
-          best += v[k];
-        }
-      }
-    } else {
-      const double s0 = Sb[low ^ __ldg(MK)], t0 = __ldg(tb);
-      best = SEMI == TQEC_SEMIRING_MAXPLUS ? s0 + t0 : s0 * t0;
-      for (int k = 1; k < nk; ++k) {
-        const double s = Sb[low ^ __ldg(MK + k)], tv = __ldg(tb + k);
-        if (SEMI == TQEC_SEMIRING_MAXPLUS) {
-          const double v = s + tv;
-          if (v > best) { best = v; bk = k; }
-        } else {
-          best += s * tv;
-        }
+    for (int k = 1; k < (NK > 0 ? NK : nk); ++k) {
+      const double s = Sb[low ^ ldi<SM>(MK + k)], tv = ldd<SM>(tb + k);
+      if (SEMI == TQEC_SEMIRING_MAXPLUS) {
+        const double v = s + tv;
+        if (v > best) { best = v; bk = k; }      // strict: the smallest candidate wins exact ties
+      } else {
+        best += s * tv;
       }
     }
     Sout[e] = best;
@@ -99,85 +96,273 @@ __device__ __forceinline__ void run_step(const PlanDev &P, const int32_t *__rest
   if (SEMI == TQEC_SEMIRING_MAXPLUS && kb && jw) bpt[wi * T + tid] = word;
 }
 
-template <int SEMI>
-__global__ void k_frontier(const PlanDev P, const uint64_t *__restrict__ synd, const int64_t B,
-                           uint64_t *__restrict__ corr, double *__restrict__ out, int32_t *__restrict__ argmax_out,
-                           uint32_t *__restrict__ bp_all) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int T = blockDim.x, tid = threadIdx.x;
+// ---- fast step ("state in lane", T = 32) --------------------------------------------------------------------------------
+// One block of U consecutive elements of a thread (j = j0 .. j0+U-1): U*NK gathers, U stores, U*kb back-pointer bits.
+template <int SEMI, int NK, int U>
+__device__ __forceinline__ uint32_t fast_block(const unsigned char *__restrict__ sin_b, unsigned char *__restrict__ so,
+                                               const int (&ck8)[NK], const double (&tv)[NK], int g8, int j0) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int gj8 = __shfl_sync(0xffffffffu, g8, j0 + u);
+    double v[NK];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      const double s = *reinterpret_cast<const double *>(sin_b + (ck8[k] ^ gj8));
+      v[k] = SEMI == TQEC_SEMIRING_MAXPLUS ? s + tv[k] : s * tv[k];
+    }
+    double best;
+    if (SEMI == TQEC_SEMIRING_MAXPLUS) {
+      // the smallest candidate index wins exact ties: the right operand of every comparison must be strictly greater
+      if (NK == 1) {
+        best = v[0];
+      } else if (NK == 2) {
+        const bool p = v[1] > v[0];
+        best = p ? v[1] : v[0];
+        if (p) m |= 1u << u;
+      } else {
+        const bool p01 = v[1] > v[0], p23 = v[3 % NK] > v[2 % NK];
+        const double b01 = p01 ? v[1] : v[0], b23 = p23 ? v[3 % NK] : v[2 % NK];
+        const bool pf = b23 > b01;
+        best = pf ? b23 : b01;
+        const uint32_t bk = pf ? (2u | (uint32_t)p23) : (uint32_t)p01;
+        m |= bk << (2 * u);
+      }
+    } else {
+      best = v[0];
+#pragma unroll
+      for (int k = 1; k < NK; ++k) best += v[k];
+    }
+    *reinterpret_cast<double *>(so + (u << 8)) = best;
+  }
+  return m;
+}
+
+// The element index e = tid + 32*j splits into lane bits and j bits, and so does every quantity derived from it: the
+// re-inserted full index is deposit(tid) | deposit(j << 5) | closed-bit values, the opened pattern and the shot sub-index
+// depend on j only.  Per step each thread folds deposit(tid) into one XOR constant per candidate, lane j holds the
+// j-dependent part (broadcast by one SHFL per element), and factor values / masks sit in registers, so a candidate
+// costs LOP3 + LDS.64 + DADD (+ DSETP + 2 FSEL beyond the first).  The host sets hdr[TQEC_H_FAST] when the split is
+// valid for the chosen geometry.
+template <int SEMI, int NK, bool SM>
+__device__ __forceinline__ void fast_step(const PlanDev &P, const Tabs &X, const int32_t *__restrict__ h,
+                                          const unsigned char *__restrict__ sin_b, unsigned char *__restrict__ sout_b,
+                                          const uint64_t *__restrict__ sh_syn, uint32_t *__restrict__ bpt, int tid) {
+  constexpr int LT = 5, T = 32;
+  constexpr int KB = NK == 1 ? 0 : (NK == 2 ? 1 : 2);
+  const int w_in = ldi<SM>(h + TQEC_H_WIN), n_open = ldi<SM>(h + TQEC_H_NOPEN), n_close = ldi<SM>(h + TQEC_H_NCLOSE);
+  const int w_out = ldi<SM>(h + TQEC_H_WOUT);
+  const double *__restrict__ Tt = X.tables + ldi<SM>(h + TQEC_H_OFF_T);
+  const int32_t *__restrict__ ML = X.ints + ldi<SM>(h + TQEC_H_OFF_ML);
+  const int32_t *__restrict__ MK = X.ints + ldi<SM>(h + TQEC_H_OFF_MK);
+  const int32_t *__restrict__ CL = X.ints + ldi<SM>(h + TQEC_H_OFF_CLOSE);
+  const int lane = tid;
+  const int lgJ = w_out + P.sg_log2 - LT, lg_jj = w_out - LT - n_open;
+  const int inmask = (1 << w_in) - 1, outmask = (1 << w_out) - 1;
+  int pl = tid;                              // deposit(tid)
+  const int ge = lane << LT;                 // first element of this lane's j
+  const int gsub = ge >> w_out;
+  const bool gvalid = lane < (1 << lgJ);
+  int gfull = ge & outmask;                  // deposit(j << 5) | closed-bit values of its shot
+  for (int c = 0; c < n_close; ++c) {
+    const int slot = ldi<SM>(CL + 2 * c), bit = ldi<SM>(CL + 2 * c + 1);
+    pl = insert_bit(pl, slot, 0);
+    const int sb = gvalid ? (int)((sh_syn[gsub * P.nsw + (bit >> 6)] >> (bit & 63)) & 1ull) : 0;
+    gfull = insert_bit(gfull, slot, sb);
+  }
+  const int pl8 = pl << 3;
+  const int g8 = (gfull & inmask) << 3;
+  const int ngrp = 1 << (P.sg_log2 + n_open), njj = 1 << lg_jj;
+  uint32_t word = 0;
+  int pos = 0, wi = 0;
+  unsigned char *__restrict__ so = sout_b + (tid << 3);
+  for (int grp = 0; grp < ngrp; ++grp) {
+    const int pat = grp & ((1 << n_open) - 1), sub = grp >> n_open;
+    const int mlp = ldi<SM>(ML + pat);
+    int ck8[NK];
+    double tv[NK];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      ck8[k] = ((((mlp ^ ldi<SM>(MK + k)) | (sub << w_in)) << 3)) ^ pl8;
+      tv[k] = ldd<SM>(Tt + pat * NK + k);
+    }
+    const int jbase = grp << lg_jj;
+    if (njj >= 4) {
+      for (int jj = 0; jj < njj; jj += 4) {
+        const uint32_t m = fast_block<SEMI, NK, 4>(sin_b, so + ((jbase + jj) << 8), ck8, tv, g8, jbase + jj);
+        if (SEMI == TQEC_SEMIRING_MAXPLUS && KB) {
+          word |= m << pos;
+          pos += 4 * KB;
+          if (pos == 32) { bpt[wi * T + tid] = word; word = 0; pos = 0; ++wi; }
+        }
+      }
+    } else {
+      for (int jj = 0; jj < njj; ++jj) {
+        const uint32_t m = fast_block<SEMI, NK, 1>(sin_b, so + ((jbase + jj) << 8), ck8, tv, g8, jbase + jj);
+        if (SEMI == TQEC_SEMIRING_MAXPLUS && KB) {
+          word |= m << pos;
+          pos += KB;
+          if (pos == 32) { bpt[wi * T + tid] = word; word = 0; pos = 0; ++wi; }
+        }
+      }
+    }
+  }
+  if (SEMI == TQEC_SEMIRING_MAXPLUS && KB && pos) bpt[wi * T + tid] = word;
+}
+
+// ---- one traceback step (shared by both traceback shapes): returns the previous state index, ORs the factor's bits ------
+template <bool SM>
+__device__ __forceinline__ int trace_step(const PlanDev &P, const Tabs &X, const int32_t *__restrict__ h, int tau, int sub,
+                                          int k, const uint64_t *__restrict__ sh_syn, int &a_out) {
+  const int w_in = ldi<SM>(h + TQEC_H_WIN);
+  const int32_t *CL = X.ints + ldi<SM>(h + TQEC_H_OFF_CLOSE);
+  const int full = rebuild_full<SM>(tau, sub, ldi<SM>(h + TQEC_H_NCLOSE), CL, sh_syn, P.nsw);
+  const int pat = full >> w_in;
+  a_out = ldi<SM>(X.ints + ldi<SM>(h + TQEC_H_OFF_A0) + pat) ^ ldi<SM>(X.ints + ldi<SM>(h + TQEC_H_OFF_KER) + k);
+  return (full & ((1 << w_in) - 1)) ^ ldi<SM>(X.ints + ldi<SM>(h + TQEC_H_OFF_ML) + pat) ^
+         ldi<SM>(X.ints + ldi<SM>(h + TQEC_H_OFF_MK) + k);
+}
+
+// ---- the team body ---------------------------------------------------------------------------------------------------
+template <int SEMI, bool WT>
+__device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, double *S0, uint64_t *sh_syn, uint64_t *sh_cfg,
+                                         uint32_t *__restrict__ bp, int T, int LT, int tid, int64_t g_first, int64_t g_stride,
+                                         const uint64_t *__restrict__ synd, int64_t B, uint64_t *__restrict__ corr,
+                                         double *__restrict__ out, int32_t *__restrict__ argmax_out) {
+  constexpr bool SM = WT;
   const int SG = 1 << P.sg_log2;
   const int NS = 1 << (P.w_max + P.sg_log2);
-  double *S0 = reinterpret_cast<double *>(smem_raw);
   double *S1 = S0 + NS;
-  uint64_t *sh_syn = reinterpret_cast<uint64_t *>(S1 + NS);
-  uint64_t *sh_cfg = sh_syn + SG * P.nsw;
-  uint32_t *bp = bp_all + (size_t)blockIdx.x * P.bp_words;
   const int64_t n_groups = (B + SG - 1) >> P.sg_log2;
   const double ONE = SEMI == TQEC_SEMIRING_MAXPLUS ? 0.0 : 1.0;
+  const bool coop_trace = WT && SG < 8 && P.ncw <= 32;
 
-  for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+  for (int64_t g = g_first; g < n_groups; g += g_stride) {
     const int64_t shot0 = g << P.sg_log2;
     for (int i = tid; i < SG * P.nsw; i += T) {
       const int64_t s = shot0 + i / P.nsw;
       sh_syn[i] = s < B ? synd[shot0 * P.nsw + i] : 0ull;
     }
-    if (SEMI == TQEC_SEMIRING_MAXPLUS)
+    if (SEMI == TQEC_SEMIRING_MAXPLUS && !coop_trace)
       for (int i = tid; i < SG * P.ncw; i += T) sh_cfg[i] = 0ull;
     for (int i = tid; i < SG; i += T) S0[i] = ONE;
-    __syncthreads();
+    team_sync<WT>();
 
     double *Sin = S0, *Sout = S1;
     for (int t = 0; t < P.n_steps; ++t) {
-      const int32_t *h = P.hdr + t * TQEC_HDR_INTS;
-      uint32_t *bpt = bp + P.bp_off[t];
-      switch (h[TQEC_H_NK]) {
-        case 1: run_step<SEMI, 1>(P, h, Sin, Sout, sh_syn, bpt, T, tid); break;
-        case 2: run_step<SEMI, 2>(P, h, Sin, Sout, sh_syn, bpt, T, tid); break;
-        case 4: run_step<SEMI, 4>(P, h, Sin, Sout, sh_syn, bpt, T, tid); break;
-        default: run_step<SEMI, 0>(P, h, Sin, Sout, sh_syn, bpt, T, tid); break;
+      const int32_t *h = X.hdr + t * TQEC_HDR_INTS;
+      uint32_t *bpt = bp + ldi<SM>(X.bp_off + t);
+      const int nk = ldi<SM>(h + TQEC_H_NK);
+      if (WT && ldi<SM>(h + TQEC_H_FAST)) {
+        const unsigned char *sb = reinterpret_cast<const unsigned char *>(Sin);
+        unsigned char *ob = reinterpret_cast<unsigned char *>(Sout);
+        if (nk == 2) fast_step<SEMI, 2, SM>(P, X, h, sb, ob, sh_syn, bpt, tid);
+        else if (nk == 1) fast_step<SEMI, 1, SM>(P, X, h, sb, ob, sh_syn, bpt, tid);
+        else fast_step<SEMI, 4, SM>(P, X, h, sb, ob, sh_syn, bpt, tid);
+      } else {
+        switch (nk) {
+          case 1: run_step<SEMI, 1, SM>(P, X, h, Sin, Sout, sh_syn, bpt, T, tid); break;
+          case 2: run_step<SEMI, 2, SM>(P, X, h, Sin, Sout, sh_syn, bpt, T, tid); break;
+          case 4: run_step<SEMI, 4, SM>(P, X, h, Sin, Sout, sh_syn, bpt, T, tid); break;
+          default: run_step<SEMI, 0, SM>(P, X, h, Sin, Sout, sh_syn, bpt, T, tid); break;
+        }
       }
-      __syncthreads();
+      team_sync<WT>();
       double *tmp = Sin; Sin = Sout; Sout = tmp;
     }
 
     if (SEMI == TQEC_SEMIRING_MAXPLUS) {
-      // traceback: one thread per shot walks the back-pointers from the scalar root to the first step
-      for (int sub = tid; sub < SG; sub += T) {
-        int tau = 0;
-        uint64_t *cfg = sh_cfg + sub * P.ncw;
-        for (int t = P.n_steps - 1; t >= 0; --t) {
-          const int32_t *h = P.hdr + t * TQEC_HDR_INTS;
-          const int w_in = h[TQEC_H_WIN], w_out = h[TQEC_H_WOUT], kb = h[TQEC_H_KB], r = h[TQEC_H_R];
-          const int32_t *CL = P.ints + h[TQEC_H_OFF_CLOSE];
-          int k = 0;
-          if (kb) {
-            const int e = (sub << w_out) | tau;
-            const int j = e / T, lane = e - j * T, per_word = 32 / kb;
-            const uint32_t wv = __ldcg(bp + P.bp_off[t] + (j / per_word) * T + lane);
-            k = (wv >> (kb * (j % per_word))) & ((1u << kb) - 1u);
-          }
-          const int full = rebuild_full(tau, sub, h[TQEC_H_NCLOSE], CL, sh_syn, P.nsw);
-          const int pat = full >> w_in;
-          const int a = __ldg(P.ints + h[TQEC_H_OFF_A0] + pat) ^ __ldg(P.ints + h[TQEC_H_OFF_KER] + k);
-          const int32_t *V = P.ints + h[TQEC_H_OFF_VARS];
-          for (int j = 0; j < r; ++j)
-            if ((a >> j) & 1) {
-              const int v = __ldg(V + j);
-              cfg[v >> 6] |= 1ull << (v & 63);
+      if (coop_trace) {
+        // warp-cooperative traceback: the back-pointer words of 8 steps are fetched at once (lane l holds words l and
+        // 32 + l of each step, coalesced), then the chain is resolved from registers with one SHFL per step; lane w
+        // accumulates word w of the configuration.
+        const int lane = tid;
+        for (int sub = 0; sub < SG; ++sub) {
+          int tau = 0;
+          uint64_t myw = 0ull;
+          for (int t0 = P.n_steps - 1; t0 >= 0; t0 -= 8) {
+            uint32_t w0[8], w1[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int t = t0 - u;
+              w0[u] = 0u; w1[u] = 0u;
+              if (t >= 0) {
+                const int o0 = ldi<SM>(X.bp_off + t), nw = ldi<SM>(X.bp_off + t + 1) - o0;
+                if (nw > 0) w0[u] = __ldcg(bp + o0 + lane);
+                if (nw > 32) w1[u] = __ldcg(bp + o0 + 32 + lane);
+              }
             }
-          tau = (full & ((1 << w_in) - 1)) ^ __ldg(P.ints + h[TQEC_H_OFF_ML] + pat) ^ __ldg(P.ints + h[TQEC_H_OFF_MK] + k);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int t = t0 - u;
+              if (t >= 0) {
+                const int32_t *h = X.hdr + t * TQEC_HDR_INTS;
+                const int kb = ldi<SM>(h + TQEC_H_KB), r = ldi<SM>(h + TQEC_H_R);
+                int k = 0;
+                if (kb) {
+                  const int e = (sub << ldi<SM>(h + TQEC_H_WOUT)) | tau;
+                  const int j = e >> 5, ln = e & 31;
+                  int wi, sh;
+                  if (kb == 1) { wi = j >> 5; sh = j & 31; }
+                  else if (kb == 2) { wi = j >> 4; sh = (j & 15) << 1; }
+                  else { const int pw = 32 / kb; wi = j / pw; sh = (j - wi * pw) * kb; }
+                  uint32_t wv;
+                  if (wi < 2) wv = __shfl_sync(0xffffffffu, wi ? w1[u] : w0[u], ln);
+                  else wv = __ldcg(bp + ldi<SM>(X.bp_off + t) + wi * 32 + ln);
+                  k = (wv >> sh) & ((1u << kb) - 1u);
+                }
+                int a;
+                tau = trace_step<SM>(P, X, h, tau, sub, k, sh_syn, a);
+                const int32_t *V = X.ints + ldi<SM>(h + TQEC_H_OFF_VARS);
+                for (int j = 0; j < r; ++j)
+                  if ((a >> j) & 1) {
+                    const int v = ldi<SM>(V + j);
+                    if (lane == (v >> 6)) myw |= 1ull << (v & 63);
+                  }
+              }
+            }
+          }
+          if (shot0 + sub < B) {
+            if (lane < P.ncw) corr[(shot0 + sub) * P.ncw + lane] = myw;
+            if (lane == 0 && out) out[shot0 + sub] = Sin[sub];
+          }
         }
-        if (shot0 + sub < B && out) out[shot0 + sub] = Sin[sub];
+      } else {
+        // one thread per shot walks the back-pointers from the scalar root to the first step
+        for (int sub = tid; sub < SG; sub += T) {
+          int tau = 0;
+          uint64_t *cfg = sh_cfg + sub * P.ncw;
+          for (int t = P.n_steps - 1; t >= 0; --t) {
+            const int32_t *h = X.hdr + t * TQEC_HDR_INTS;
+            const int kb = ldi<SM>(h + TQEC_H_KB), r = ldi<SM>(h + TQEC_H_R);
+            int k = 0;
+            if (kb) {
+              const int e = (sub << ldi<SM>(h + TQEC_H_WOUT)) | tau;
+              const int j = e >> LT, ln = e & (T - 1), per_word = 32 / kb;
+              const uint32_t wv = __ldcg(bp + ldi<SM>(X.bp_off + t) + (j / per_word) * T + ln);
+              k = (wv >> (kb * (j % per_word))) & ((1u << kb) - 1u);
+            }
+            int a;
+            tau = trace_step<SM>(P, X, h, tau, sub, k, sh_syn, a);
+            const int32_t *V = X.ints + ldi<SM>(h + TQEC_H_OFF_VARS);
+            for (int j = 0; j < r; ++j)
+              if ((a >> j) & 1) {
+                const int v = ldi<SM>(V + j);
+                cfg[v >> 6] |= 1ull << (v & 63);
+              }
+          }
+          if (shot0 + sub < B && out) out[shot0 + sub] = Sin[sub];
+        }
+        team_sync<WT>();
+        for (int i = tid; i < SG * P.ncw; i += T)
+          if (shot0 + i / P.ncw < B) corr[shot0 * P.ncw + i] = sh_cfg[i];
       }
-      __syncthreads();
-      for (int i = tid; i < SG * P.ncw; i += T)
-        if (shot0 + i / P.ncw < B) corr[shot0 * P.ncw + i] = sh_cfg[i];
     } else {
       const int NO = 1 << P.n_obs;
       for (int i = tid; i < SG * NO; i += T) {
         const int sub = i >> P.n_obs, idx = i & (NO - 1);
         int src = 0;
-        for (int o = 0; o < P.n_obs; ++o) src |= ((idx >> o) & 1) << __ldg(P.obs_slot + o);
+        for (int o = 0; o < P.n_obs; ++o) src |= ((idx >> o) & 1) << ldi<SM>(X.obs_slot + o);
         if (shot0 + sub < B) out[(shot0 + sub) * NO + idx] = Sin[(sub << P.n_obs) | src];
       }
       if (argmax_out) {
@@ -185,9 +370,9 @@ __global__ void k_frontier(const PlanDev P, const uint64_t *__restrict__ synd, c
           if (shot0 + sub >= B) continue;
           double best = -1.0;
           int bi = 0;
-          for (int idx = 0; idx < NO; ++idx) {
+          for (int idx = 0; idx < NO; ++idx) {             // first maximal entry (findmax)
             int src = 0;
-            for (int o = 0; o < P.n_obs; ++o) src |= ((idx >> o) & 1) << __ldg(P.obs_slot + o);
+            for (int o = 0; o < P.n_obs; ++o) src |= ((idx >> o) & 1) << ldi<SM>(X.obs_slot + o);
             const double v = Sin[(sub << P.n_obs) | src];
             if (v > best) { best = v; bi = idx; }
           }
@@ -195,21 +380,78 @@ __global__ void k_frontier(const PlanDev P, const uint64_t *__restrict__ synd, c
         }
       }
     }
-    __syncthreads();
+    team_sync<WT>();
   }
+}
+
+// per-team shared memory: state ping-pong, syndrome words, configuration words
+__host__ __device__ inline size_t team_smem_bytes(int w_max, int sg, int nsw, int ncw) {
+  return 2 * ((size_t)1 << (w_max + sg)) * sizeof(double) + ((size_t)1 << sg) * (size_t)(nsw + ncw) * sizeof(uint64_t);
+}
+
+// CTA teams: blockDim.x threads form one team, tables in global memory
+template <int SEMI>
+__global__ void k_frontier_cta(const PlanDev P, const uint64_t *__restrict__ synd, const int64_t B,
+                               uint64_t *__restrict__ corr, double *__restrict__ out, int32_t *__restrict__ argmax_out,
+                               uint32_t *__restrict__ bp_all) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int T = blockDim.x, tid = threadIdx.x;
+  const int LT = 31 - __clz(T);
+  const int SG = 1 << P.sg_log2;
+  double *S0 = reinterpret_cast<double *>(smem_raw);
+  uint64_t *sh_syn = reinterpret_cast<uint64_t *>(S0 + ((size_t)2 << (P.w_max + P.sg_log2)));
+  uint64_t *sh_cfg = sh_syn + SG * P.nsw;
+  Tabs X{P.hdr, P.ints, P.bp_off, P.obs_slot, P.tables};
+  team_run<SEMI, false>(P, X, S0, sh_syn, sh_cfg, bp_all + (size_t)blockIdx.x * P.bp_words, T, LT, tid, blockIdx.x,
+                        gridDim.x, synd, B, corr, out, argmax_out);
+}
+
+// warp teams: every warp of the CTA is an independent team; the schedule tables are staged in shared memory once
+template <int SEMI>
+__global__ void k_frontier_warp(const PlanDev P, const uint64_t *__restrict__ synd, const int64_t B,
+                                uint64_t *__restrict__ corr, double *__restrict__ out, int32_t *__restrict__ argmax_out,
+                                uint32_t *__restrict__ bp_all) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int NW = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t per_team = team_smem_bytes(P.w_max, P.sg_log2, P.nsw, P.ncw);
+  // table copies live behind the team regions: tables (8-byte aligned) | hdr | bp_off | obs_slot | ints
+  double *sm_tables = reinterpret_cast<double *>(smem_raw + per_team * NW);
+  int32_t *sm_hdr = reinterpret_cast<int32_t *>(sm_tables + P.n_tables);
+  int32_t *sm_bpoff = sm_hdr + P.n_steps * TQEC_HDR_INTS;
+  int32_t *sm_obs = sm_bpoff + P.n_steps + 1;
+  int32_t *sm_ints = sm_obs + P.n_obs;
+  for (int i = threadIdx.x; i < P.n_tables; i += blockDim.x) sm_tables[i] = P.tables[i];
+  for (int i = threadIdx.x; i < P.n_steps * TQEC_HDR_INTS; i += blockDim.x) sm_hdr[i] = P.hdr[i];
+  for (int i = threadIdx.x; i <= P.n_steps; i += blockDim.x) sm_bpoff[i] = P.bp_off[i];
+  for (int i = threadIdx.x; i < P.n_obs; i += blockDim.x) sm_obs[i] = P.obs_slot[i];
+  for (int i = threadIdx.x; i < P.n_ints; i += blockDim.x) sm_ints[i] = P.ints[i];
+  __syncthreads();
+  const int SG = 1 << P.sg_log2;
+  double *S0 = reinterpret_cast<double *>(smem_raw + per_team * warp);
+  uint64_t *sh_syn = reinterpret_cast<uint64_t *>(S0 + ((size_t)2 << (P.w_max + P.sg_log2)));
+  uint64_t *sh_cfg = sh_syn + SG * P.nsw;
+  Tabs X{sm_hdr, sm_ints, sm_bpoff, sm_obs, sm_tables};
+  const int64_t team = (int64_t)blockIdx.x * NW + warp;
+  team_run<SEMI, true>(P, X, S0, sh_syn, sh_cfg, bp_all + (size_t)team * P.bp_words, 32, 5, lane, team,
+                       (int64_t)gridDim.x * NW, synd, B, corr, out, argmax_out);
 }
 
 int launch_decode(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d_corr, double *d_out,
                   int32_t *d_argmax, cudaStream_t stream) {
   if (B <= 0) return TQEC_OK;
   const int64_t groups = (B + plan->shots_per_team - 1) / plan->shots_per_team;
-  const int grid = (int)(groups < plan->grid_max ? groups : plan->grid_max);
-  if (plan->semiring == TQEC_SEMIRING_MAXPLUS)
-    k_frontier<TQEC_SEMIRING_MAXPLUS><<<grid, plan->team_threads, plan->smem_bytes, stream>>>(
-        plan->dev, d_synd, B, d_corr, d_out, nullptr, plan->d_bp);
-  else
-    k_frontier<TQEC_SEMIRING_SUMPROD><<<grid, plan->team_threads, plan->smem_bytes, stream>>>(
-        plan->dev, d_synd, B, nullptr, d_out, d_argmax, plan->d_bp);
+  const bool mp = plan->semiring == TQEC_SEMIRING_MAXPLUS;
+  if (plan->warp_teams) {
+    const int64_t ctas = (groups + plan->teams_per_cta - 1) / plan->teams_per_cta;
+    const int grid = (int)(ctas < plan->grid_max ? ctas : plan->grid_max);
+    const int threads = 32 * plan->teams_per_cta;
+    if (mp) k_frontier_warp<TQEC_SEMIRING_MAXPLUS><<<grid, threads, plan->smem_bytes, stream>>>(plan->dev, d_synd, B, d_corr, d_out, nullptr, plan->d_bp);
+    else k_frontier_warp<TQEC_SEMIRING_SUMPROD><<<grid, threads, plan->smem_bytes, stream>>>(plan->dev, d_synd, B, nullptr, d_out, d_argmax, plan->d_bp);
+  } else {
+    const int grid = (int)(groups < plan->grid_max ? groups : plan->grid_max);
+    if (mp) k_frontier_cta<TQEC_SEMIRING_MAXPLUS><<<grid, plan->team_threads, plan->smem_bytes, stream>>>(plan->dev, d_synd, B, d_corr, d_out, nullptr, plan->d_bp);
+    else k_frontier_cta<TQEC_SEMIRING_SUMPROD><<<grid, plan->team_threads, plan->smem_bytes, stream>>>(plan->dev, d_synd, B, nullptr, d_out, d_argmax, plan->d_bp);
+  }
   TQEC_CUDA(cudaGetLastError());
   plan->launches += 1;
   return TQEC_OK;
@@ -301,24 +543,38 @@ extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
   int T = 32;
   if (tot_bits > 10) T = 1 << (tot_bits - 5 > 8 ? 8 : tot_bits - 5);
   const int nsw = words_for(d->n_checks), ncw = words_for(d->n_vars);
-  const size_t smem = 2 * ((size_t)1 << tot_bits) * sizeof(double) + ((size_t)1 << sg) * (nsw + ncw) * sizeof(uint64_t);
-  if (smem > (size_t)prop.sharedMemPerBlockOptin) {
+  const size_t per_team = team_smem_bytes(d->w_max, sg, nsw, ncw);
+  const size_t tab_bytes = (size_t)d->n_tables * 8 +
+                           ((size_t)d->n_steps * TQEC_HDR_INTS + d->n_steps + 1 + d->n_obs + (size_t)d->n_ints) * 4 + 8;
+  const size_t budget = (size_t)prop.sharedMemPerBlockOptin;
+  int nw = 0;
+  if (T == 32 && std::getenv("TQEC_NO_WARP_TEAMS") == nullptr && budget > tab_bytes) {
+    nw = (int)((budget - tab_bytes) / per_team);
+    if (nw > 16) nw = 16;
+    if (const char *e = std::getenv("TQEC_TEAMS_PER_CTA")) { const int v = std::atoi(e); if (v >= 1 && v < nw) nw = v; }
+  }
+  p->warp_teams = nw >= 1;
+  p->teams_per_cta = nw >= 1 ? nw : 1;
+  const size_t smem = p->warp_teams ? per_team * nw + tab_bytes : per_team;
+  if (smem > budget) {
     delete p;
-    set_error("schedule needs %zu B of shared memory per team (w_max=%d) > %zu available", smem, d->w_max,
-              (size_t)prop.sharedMemPerBlockOptin);
+    set_error("schedule needs %zu B of shared memory per team (w_max=%d) > %zu available", smem, d->w_max, budget);
     return TQEC_ERR_UNSUPPORTED;
   }
   p->team_threads = T;
   p->shots_per_team = 1 << sg;
   p->smem_bytes = (int)smem;
 
-  const void *kern = d->semiring == TQEC_SEMIRING_MAXPLUS ? (const void *)k_frontier<TQEC_SEMIRING_MAXPLUS>
-                                                          : (const void *)k_frontier<TQEC_SEMIRING_SUMPROD>;
+  const void *kern;
+  if (p->warp_teams) kern = d->semiring == TQEC_SEMIRING_MAXPLUS ? (const void *)k_frontier_warp<TQEC_SEMIRING_MAXPLUS>
+                                                                 : (const void *)k_frontier_warp<TQEC_SEMIRING_SUMPROD>;
+  else kern = d->semiring == TQEC_SEMIRING_MAXPLUS ? (const void *)k_frontier_cta<TQEC_SEMIRING_MAXPLUS>
+                                                   : (const void *)k_frontier_cta<TQEC_SEMIRING_SUMPROD>;
   TQEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  TQEC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
+  TQEC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, p->warp_teams ? 32 * nw : T, smem));
   if (per_sm < 1) per_sm = 1;
-  p->teams_per_sm = per_sm;
+  p->teams_per_sm = per_sm * p->teams_per_cta;
   p->grid_max = per_sm * p->sm_count;
 
   // back-pointer layout per team
@@ -341,13 +597,36 @@ extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
   PlanDev &D = p->dev;
   D.n_steps = d->n_steps; D.n_vars = d->n_vars; D.n_checks = d->n_checks; D.n_obs = d->n_obs;
   D.w_max = d->w_max; D.sg_log2 = sg; D.nsw = nsw; D.ncw = ncw; D.bp_words = bp_off[d->n_steps];
-  rc = upload(&p->d_hdr, d->hdr, (size_t)d->n_steps * TQEC_HDR_INTS);
+  D.n_ints = (int32_t)d->n_ints; D.n_tables = (int32_t)d->n_tables;
+  // per-step fast-path flag (see fast_step): valid iff the element index splits into lane bits and j bits
+  std::vector<int32_t> hdr(d->hdr, d->hdr + (size_t)d->n_steps * TQEC_HDR_INTS);
+  {
+    int LT = 0;
+    while ((1 << LT) < T) ++LT;
+    const bool allow = std::getenv("TQEC_NO_FAST") == nullptr;
+    for (int t = 0; t < d->n_steps; ++t) {
+      int32_t *h = hdr.data() + t * TQEC_HDR_INTS;
+      const int w_in = h[TQEC_H_WIN], n_open = h[TQEC_H_NOPEN], n_close = h[TQEC_H_NCLOSE], w_out = h[TQEC_H_WOUT];
+      const int nk = h[TQEC_H_NK];
+      const int lgJ = w_out + sg - LT;
+      bool ok = allow && p->warp_teams && lgJ >= 0 && lgJ <= 5 && (w_out - LT - n_open) >= 0 && (nk == 1 || nk == 2 || nk == 4);
+      int dep = T - 1;
+      for (int c = 0; c < n_close && ok; ++c) {
+        const int slot = d->ints[h[TQEC_H_OFF_CLOSE] + 2 * c];
+        if (slot >= w_in) ok = false;
+        dep = ((dep >> slot) << (slot + 1)) | (dep & ((1 << slot) - 1));
+      }
+      if (ok && dep >= (1 << w_in)) ok = false;
+      h[TQEC_H_FAST] = ok ? 1 : 0;
+    }
+  }
+  rc = upload(&p->d_hdr, hdr.data(), hdr.size());
   if (!rc) rc = upload(&p->d_ints, d->ints, (size_t)d->n_ints);
   if (!rc) rc = upload(&p->d_tables, d->tables, (size_t)d->n_tables);
   if (!rc) rc = upload(&p->d_bp_off, bp_off.data(), bp_off.size());
   if (!rc) rc = upload(&p->d_obs_slot, d->obs_slot, (size_t)d->n_obs);
   if (!rc) {
-    const size_t bytes = (size_t)p->grid_max * (D.bp_words ? D.bp_words : 1) * sizeof(uint32_t);
+    const size_t bytes = (size_t)p->grid_max * p->teams_per_cta * (D.bp_words ? D.bp_words : 1) * sizeof(uint32_t);
     cudaError_t e = cudaMalloc((void **)&p->d_bp, bytes);
     if (e != cudaSuccess) { set_error("cudaMalloc(%zu B back-pointer scratch): %s", bytes, cudaGetErrorString(e)); rc = TQEC_ERR_NOMEM; }
   }
