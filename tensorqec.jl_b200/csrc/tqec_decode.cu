@@ -97,59 +97,74 @@ __device__ __forceinline__ void run_step(const PlanDev &P, const Tabs &X, const 
 }
 
 // ---- fast step ("state in lane", T = 32) --------------------------------------------------------------------------------
-// One block of U consecutive elements of a thread (j = j0 .. j0+U-1): U*NK gathers, U stores, U*kb back-pointer bits.
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v));
+}
+
+// One block of U consecutive elements of a thread (j = j0 .. j0+U-1, j0 a multiple of U): U*NK gathers (all issued
+// before the first use), U stores, U*kb back-pointer bits.  `gj8` is the j0-dependent byte offset (one broadcast load
+// per block); the other elements differ from it by the constants dl[u] (the deposited low bits of j).  Addresses are
+// ABSOLUTE shared-memory addresses: the state's base is a multiple of its size, so base, lane part, candidate mask and
+// j part combine with XOR only and an address costs one LOP3.
 template <int SEMI, int NK, int U>
-__device__ __forceinline__ uint32_t fast_block(const unsigned char *__restrict__ sin_b, unsigned char *__restrict__ so,
-                                               const int (&ck8)[NK], const double (&tv)[NK], int g8, int j0) {
+__device__ __forceinline__ uint32_t fast_block(uint32_t so, const uint32_t (&ck8)[NK], const double (&tv)[NK],
+                                               const uint32_t (&dl)[8], uint32_t gj8) {
+  double v[U][NK];
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+#pragma unroll
+    for (int k = 0; k < NK; ++k) v[u][k] = lds_f64(u == 0 ? (ck8[k] ^ gj8) : (ck8[k] ^ gj8 ^ dl[u]));
   uint32_t m = 0;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-    const int gj8 = __shfl_sync(0xffffffffu, g8, j0 + u);
-    double v[NK];
 #pragma unroll
-    for (int k = 0; k < NK; ++k) {
-      const double s = *reinterpret_cast<const double *>(sin_b + (ck8[k] ^ gj8));
-      v[k] = SEMI == TQEC_SEMIRING_MAXPLUS ? s + tv[k] : s * tv[k];
-    }
+    for (int k = 0; k < NK; ++k) v[u][k] = SEMI == TQEC_SEMIRING_MAXPLUS ? v[u][k] + tv[k] : v[u][k] * tv[k];
     double best;
     if (SEMI == TQEC_SEMIRING_MAXPLUS) {
       // the smallest candidate index wins exact ties: the right operand of every comparison must be strictly greater
       if (NK == 1) {
-        best = v[0];
+        best = v[u][0];
       } else if (NK == 2) {
-        const bool p = v[1] > v[0];
-        best = p ? v[1] : v[0];
+        const bool p = v[u][1] > v[u][0];
+        best = p ? v[u][1] : v[u][0];
         if (p) m |= 1u << u;
       } else {
-        const bool p01 = v[1] > v[0], p23 = v[3 % NK] > v[2 % NK];
-        const double b01 = p01 ? v[1] : v[0], b23 = p23 ? v[3 % NK] : v[2 % NK];
+        const bool p01 = v[u][1] > v[u][0], p23 = v[u][3 % NK] > v[u][2 % NK];
+        const double b01 = p01 ? v[u][1] : v[u][0], b23 = p23 ? v[u][3 % NK] : v[u][2 % NK];
         const bool pf = b23 > b01;
         best = pf ? b23 : b01;
         const uint32_t bk = pf ? (2u | (uint32_t)p23) : (uint32_t)p01;
         m |= bk << (2 * u);
       }
     } else {
-      best = v[0];
+      best = v[u][0];
 #pragma unroll
-      for (int k = 1; k < NK; ++k) best += v[k];
+      for (int k = 1; k < NK; ++k) best += v[u][k];
     }
-    *reinterpret_cast<double *>(so + (u << 8)) = best;
+    sts_f64(so + (u << 8), best);
   }
   return m;
 }
 
 // The element index e = tid + 32*j splits into lane bits and j bits, and so does every quantity derived from it: the
 // re-inserted full index is deposit(tid) | deposit(j << 5) | closed-bit values, the opened pattern and the shot sub-index
-// depend on j only.  Per step each thread folds deposit(tid) into one XOR constant per candidate, lane j holds the
-// j-dependent part (broadcast by one SHFL per element), and factor values / masks sit in registers, so a candidate
-// costs LOP3 + LDS.64 + DADD (+ DSETP + 2 FSEL beyond the first).  The host sets hdr[TQEC_H_FAST] when the split is
-// valid for the chosen geometry.
+// depend on j only.  Per step each thread folds deposit(tid) and the state's base address into one XOR constant per
+// candidate, the j-dependent part sits in a 32-entry per-team table (one broadcast LDS per block), and factor values /
+// masks sit in registers, so a candidate costs LOP3 + LDS.64 + DADD (+ DSETP + 2 FSEL beyond the first).  The host sets
+// hdr[TQEC_H_FAST] when the split is valid for the chosen geometry.  `sin_abs` / `sout_abs` are absolute shared
+// addresses of the ping-pong states, multiples of the state size; `gtab` is the team's 32-entry table.
 template <int SEMI, int NK, bool SM>
 __device__ __forceinline__ void fast_step(const PlanDev &P, const Tabs &X, const int32_t *__restrict__ h,
-                                          const unsigned char *__restrict__ sin_b, unsigned char *__restrict__ sout_b,
+                                          uint32_t sin_abs, uint32_t sout_abs, uint32_t *__restrict__ gtab,
                                           const uint64_t *__restrict__ sh_syn, uint32_t *__restrict__ bpt, int tid) {
   constexpr int LT = 5, T = 32;
   constexpr int KB = NK == 1 ? 0 : (NK == 2 ? 1 : 2);
+  constexpr int UMAX = NK == 4 ? 4 : 8;
   const int w_in = ldi<SM>(h + TQEC_H_WIN), n_open = ldi<SM>(h + TQEC_H_NOPEN), n_close = ldi<SM>(h + TQEC_H_NCLOSE);
   const int w_out = ldi<SM>(h + TQEC_H_WOUT);
   const double *__restrict__ Tt = X.tables + ldi<SM>(h + TQEC_H_OFF_T);
@@ -159,46 +174,65 @@ __device__ __forceinline__ void fast_step(const PlanDev &P, const Tabs &X, const
   const int lane = tid;
   const int lgJ = w_out + P.sg_log2 - LT, lg_jj = w_out - LT - n_open;
   const int inmask = (1 << w_in) - 1, outmask = (1 << w_out) - 1;
-  int pl = tid;                              // deposit(tid)
-  const int ge = lane << LT;                 // first element of this lane's j
+  int pl = tid;                                          // deposit(tid)
+  int dep1 = 1 << LT, dep2 = 2 << LT, dep4 = 4 << LT;    // deposit of the three low bits of j
+  const int ge = lane << LT;                             // first element of this lane's j
   const int gsub = ge >> w_out;
   const bool gvalid = lane < (1 << lgJ);
-  int gfull = ge & outmask;                  // deposit(j << 5) | closed-bit values of its shot
+  int gfull = ge & outmask;                              // deposit(j << 5) | closed-bit values of its shot
   for (int c = 0; c < n_close; ++c) {
     const int slot = ldi<SM>(CL + 2 * c), bit = ldi<SM>(CL + 2 * c + 1);
     pl = insert_bit(pl, slot, 0);
+    dep1 = insert_bit(dep1, slot, 0);
+    dep2 = insert_bit(dep2, slot, 0);
+    dep4 = insert_bit(dep4, slot, 0);
     const int sb = gvalid ? (int)((sh_syn[gsub * P.nsw + (bit >> 6)] >> (bit & 63)) & 1ull) : 0;
     gfull = insert_bit(gfull, slot, sb);
   }
-  const int pl8 = pl << 3;
-  const int g8 = (gfull & inmask) << 3;
+  gtab[lane] = (uint32_t)((gfull & inmask) << 3);
+  const uint32_t pl8 = (uint32_t)(pl << 3) ^ sin_abs;
+  uint32_t dl[8];
+  dl[0] = 0;
+  dl[1] = (uint32_t)((dep1 & inmask) << 3);
+  dl[2] = (uint32_t)((dep2 & inmask) << 3);
+  dl[4] = (uint32_t)((dep4 & inmask) << 3);
+  dl[3] = dl[1] | dl[2]; dl[5] = dl[1] | dl[4]; dl[6] = dl[2] | dl[4]; dl[7] = dl[3] | dl[4];
   const int ngrp = 1 << (P.sg_log2 + n_open), njj = 1 << lg_jj;
   uint32_t word = 0;
   int pos = 0, wi = 0;
-  unsigned char *__restrict__ so = sout_b + (tid << 3);
+  const uint32_t so = sout_abs + (tid << 3);
+  __syncwarp();
   for (int grp = 0; grp < ngrp; ++grp) {
     const int pat = grp & ((1 << n_open) - 1), sub = grp >> n_open;
     const int mlp = ldi<SM>(ML + pat);
-    int ck8[NK];
+    uint32_t ck8[NK];
     double tv[NK];
 #pragma unroll
     for (int k = 0; k < NK; ++k) {
-      ck8[k] = ((((mlp ^ ldi<SM>(MK + k)) | (sub << w_in)) << 3)) ^ pl8;
+      ck8[k] = (uint32_t)((((mlp ^ ldi<SM>(MK + k)) | (sub << w_in)) << 3)) ^ pl8;
       tv[k] = ldd<SM>(Tt + pat * NK + k);
     }
     const int jbase = grp << lg_jj;
-    if (njj >= 4) {
-      for (int jj = 0; jj < njj; jj += 4) {
-        const uint32_t m = fast_block<SEMI, NK, 4>(sin_b, so + ((jbase + jj) << 8), ck8, tv, g8, jbase + jj);
+    const volatile uint32_t *gt = gtab + jbase;
+    if (njj >= UMAX) {
+      for (int jj = 0; jj < njj; jj += UMAX) {
+        const uint32_t m = fast_block<SEMI, NK, UMAX>(so + ((jbase + jj) << 8), ck8, tv, dl, gt[jj]);
         if (SEMI == TQEC_SEMIRING_MAXPLUS && KB) {
           word |= m << pos;
-          pos += 4 * KB;
+          pos += UMAX * KB;
           if (pos == 32) { bpt[wi * T + tid] = word; word = 0; pos = 0; ++wi; }
         }
       }
+    } else if (UMAX == 8 && njj == 4) {
+      const uint32_t m = fast_block<SEMI, NK, 4>(so + (jbase << 8), ck8, tv, dl, gt[0]);
+      if (SEMI == TQEC_SEMIRING_MAXPLUS && KB) {
+        word |= m << pos;
+        pos += 4 * KB;
+        if (pos == 32) { bpt[wi * T + tid] = word; word = 0; pos = 0; ++wi; }
+      }
     } else {
       for (int jj = 0; jj < njj; ++jj) {
-        const uint32_t m = fast_block<SEMI, NK, 1>(sin_b, so + ((jbase + jj) << 8), ck8, tv, g8, jbase + jj);
+        const uint32_t m = fast_block<SEMI, NK, 1>(so + ((jbase + jj) << 8), ck8, tv, dl, gt[jj]);
         if (SEMI == TQEC_SEMIRING_MAXPLUS && KB) {
           word |= m << pos;
           pos += KB;
@@ -225,13 +259,14 @@ __device__ __forceinline__ int trace_step(const PlanDev &P, const Tabs &X, const
 
 // ---- the team body ---------------------------------------------------------------------------------------------------
 template <int SEMI, bool WT>
-__device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, double *S0, uint64_t *sh_syn, uint64_t *sh_cfg,
+__device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, unsigned char *smem, int s0_off, uint64_t *sh_syn, uint64_t *sh_cfg, uint32_t *gtab,
                                          uint32_t *__restrict__ bp, int T, int LT, int tid, int64_t g_first, int64_t g_stride,
                                          const uint64_t *__restrict__ synd, int64_t B, uint64_t *__restrict__ corr,
                                          double *__restrict__ out, int32_t *__restrict__ argmax_out) {
   constexpr bool SM = WT;
   const int SG = 1 << P.sg_log2;
   const int NS = 1 << (P.w_max + P.sg_log2);
+  double *S0 = reinterpret_cast<double *>(smem + s0_off);
   double *S1 = S0 + NS;
   const int64_t n_groups = (B + SG - 1) >> P.sg_log2;
   const double ONE = SEMI == TQEC_SEMIRING_MAXPLUS ? 0.0 : 1.0;
@@ -249,16 +284,15 @@ __device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, double
     team_sync<WT>();
 
     double *Sin = S0, *Sout = S1;
+    uint32_t sin_abs = (uint32_t)__cvta_generic_to_shared(S0), sout_abs = (uint32_t)__cvta_generic_to_shared(S1);
     for (int t = 0; t < P.n_steps; ++t) {
       const int32_t *h = X.hdr + t * TQEC_HDR_INTS;
       uint32_t *bpt = bp + ldi<SM>(X.bp_off + t);
       const int nk = ldi<SM>(h + TQEC_H_NK);
       if (WT && ldi<SM>(h + TQEC_H_FAST)) {
-        const unsigned char *sb = reinterpret_cast<const unsigned char *>(Sin);
-        unsigned char *ob = reinterpret_cast<unsigned char *>(Sout);
-        if (nk == 2) fast_step<SEMI, 2, SM>(P, X, h, sb, ob, sh_syn, bpt, tid);
-        else if (nk == 1) fast_step<SEMI, 1, SM>(P, X, h, sb, ob, sh_syn, bpt, tid);
-        else fast_step<SEMI, 4, SM>(P, X, h, sb, ob, sh_syn, bpt, tid);
+        if (nk == 2) fast_step<SEMI, 2, SM>(P, X, h, sin_abs, sout_abs, gtab, sh_syn, bpt, tid);
+        else if (nk == 1) fast_step<SEMI, 1, SM>(P, X, h, sin_abs, sout_abs, gtab, sh_syn, bpt, tid);
+        else fast_step<SEMI, 4, SM>(P, X, h, sin_abs, sout_abs, gtab, sh_syn, bpt, tid);
       } else {
         switch (nk) {
           case 1: run_step<SEMI, 1, SM>(P, X, h, Sin, Sout, sh_syn, bpt, T, tid); break;
@@ -269,6 +303,7 @@ __device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, double
       }
       team_sync<WT>();
       double *tmp = Sin; Sin = Sout; Sout = tmp;
+      const uint32_t to = sin_abs; sin_abs = sout_abs; sout_abs = to;
     }
 
     if (SEMI == TQEC_SEMIRING_MAXPLUS) {
@@ -398,11 +433,10 @@ __global__ void k_frontier_cta(const PlanDev P, const uint64_t *__restrict__ syn
   const int T = blockDim.x, tid = threadIdx.x;
   const int LT = 31 - __clz(T);
   const int SG = 1 << P.sg_log2;
-  double *S0 = reinterpret_cast<double *>(smem_raw);
-  uint64_t *sh_syn = reinterpret_cast<uint64_t *>(S0 + ((size_t)2 << (P.w_max + P.sg_log2)));
+  uint64_t *sh_syn = reinterpret_cast<uint64_t *>(smem_raw + ((size_t)16 << (P.w_max + P.sg_log2)));
   uint64_t *sh_cfg = sh_syn + SG * P.nsw;
   Tabs X{P.hdr, P.ints, P.bp_off, P.obs_slot, P.tables};
-  team_run<SEMI, false>(P, X, S0, sh_syn, sh_cfg, bp_all + (size_t)blockIdx.x * P.bp_words, T, LT, tid, blockIdx.x,
+  team_run<SEMI, false>(P, X, smem_raw, 0, sh_syn, sh_cfg, nullptr, bp_all + (size_t)blockIdx.x * P.bp_words, T, LT, tid, blockIdx.x,
                         gridDim.x, synd, B, corr, out, argmax_out);
 }
 
@@ -413,10 +447,16 @@ __global__ void k_frontier_warp(const PlanDev P, const uint64_t *__restrict__ sy
                                 uint32_t *__restrict__ bp_all) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int NW = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t per_team = team_smem_bytes(P.w_max, P.sg_log2, P.nsw, P.ncw);
-  // table copies live behind the team regions: tables (8-byte aligned) | hdr | bp_off | obs_slot | ints
-  double *sm_tables = reinterpret_cast<double *>(smem_raw + per_team * NW);
-  int32_t *sm_hdr = reinterpret_cast<int32_t *>(sm_tables + P.n_tables);
+  const int SG = 1 << P.sg_log2;
+  // layout (offsets chosen by the host, tqec_plan_create): the NW ping-pong states start at an ABSOLUTE shared address
+  // that is a multiple of the state size, so a state base can be XOR-folded into element offsets; the gap in front of
+  // them (the driver reserves the first KiB of the window) and the tail hold the table copies and the per-team words.
+  const size_t state_bytes = (size_t)16 << (P.w_max + P.sg_log2);
+  if (((uint32_t)__cvta_generic_to_shared(smem_raw) + P.off_states) & (uint32_t)(state_bytes / 2 - 1)) __trap();
+  const size_t words_bytes = (size_t)SG * (P.nsw + P.ncw) * sizeof(uint64_t) + 32 * sizeof(uint32_t);
+  unsigned char *words0 = smem_raw + P.off_words;
+  double *sm_tables = reinterpret_cast<double *>(smem_raw + P.off_tables);
+  int32_t *sm_hdr = reinterpret_cast<int32_t *>(smem_raw + P.off_ints);
   int32_t *sm_bpoff = sm_hdr + P.n_steps * TQEC_HDR_INTS;
   int32_t *sm_obs = sm_bpoff + P.n_steps + 1;
   int32_t *sm_ints = sm_obs + P.n_obs;
@@ -426,13 +466,12 @@ __global__ void k_frontier_warp(const PlanDev P, const uint64_t *__restrict__ sy
   for (int i = threadIdx.x; i < P.n_obs; i += blockDim.x) sm_obs[i] = P.obs_slot[i];
   for (int i = threadIdx.x; i < P.n_ints; i += blockDim.x) sm_ints[i] = P.ints[i];
   __syncthreads();
-  const int SG = 1 << P.sg_log2;
-  double *S0 = reinterpret_cast<double *>(smem_raw + per_team * warp);
-  uint64_t *sh_syn = reinterpret_cast<uint64_t *>(S0 + ((size_t)2 << (P.w_max + P.sg_log2)));
+  uint64_t *sh_syn = reinterpret_cast<uint64_t *>(words0 + words_bytes * warp);
   uint64_t *sh_cfg = sh_syn + SG * P.nsw;
+  uint32_t *gtab = reinterpret_cast<uint32_t *>(sh_cfg + SG * P.ncw);
   Tabs X{sm_hdr, sm_ints, sm_bpoff, sm_obs, sm_tables};
   const int64_t team = (int64_t)blockIdx.x * NW + warp;
-  team_run<SEMI, true>(P, X, S0, sh_syn, sh_cfg, bp_all + (size_t)team * P.bp_words, 32, 5, lane, team,
+  team_run<SEMI, true>(P, X, smem_raw, (int)(P.off_states + state_bytes * warp), sh_syn, sh_cfg, gtab, bp_all + (size_t)team * P.bp_words, 32, 5, lane, team,
                        (int64_t)gridDim.x * NW, synd, B, corr, out, argmax_out);
 }
 
@@ -544,18 +583,34 @@ extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
   if (tot_bits > 10) T = 1 << (tot_bits - 5 > 8 ? 8 : tot_bits - 5);
   const int nsw = words_for(d->n_checks), ncw = words_for(d->n_vars);
   const size_t per_team = team_smem_bytes(d->w_max, sg, nsw, ncw);
-  const size_t tab_bytes = (size_t)d->n_tables * 8 +
-                           ((size_t)d->n_steps * TQEC_HDR_INTS + d->n_steps + 1 + d->n_obs + (size_t)d->n_ints) * 4 + 8;
   const size_t budget = (size_t)prop.sharedMemPerBlockOptin;
+  // warp-team layout: [front gap: whatever fits of the three blobs] [states, size-aligned absolute address] [rest]
+  const size_t state_bytes = (size_t)16 << tot_bits, align = state_bytes / 2;
+  const size_t ints_bytes = (((size_t)d->n_steps * TQEC_HDR_INTS + d->n_steps + 1 + d->n_obs + (size_t)d->n_ints) * 4 + 7) & ~(size_t)7;
+  const size_t tables_bytes = (size_t)d->n_tables * 8;
+  const size_t words_team = ((size_t)1 << sg) * (size_t)(nsw + ncw) * 8 + 32 * 4;
+  int reserved = 1024;
+  cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, d->device);
+  const size_t gap = (align - (size_t)reserved % align) % align;
   int nw = 0;
-  if (T == 32 && std::getenv("TQEC_NO_WARP_TEAMS") == nullptr && budget > tab_bytes) {
-    nw = (int)((budget - tab_bytes) / per_team);
-    if (nw > 16) nw = 16;
-    if (const char *e = std::getenv("TQEC_TEAMS_PER_CTA")) { const int v = std::atoi(e); if (v >= 1 && v < nw) nw = v; }
+  size_t off_states = gap, off_ints = 0, off_tables = 0, off_words = 0, smem_warp = 0;
+  if (T == 32 && std::getenv("TQEC_NO_WARP_TEAMS") == nullptr) {
+    int cap = 16;
+    if (const char *e = std::getenv("TQEC_TEAMS_PER_CTA")) { const int v = std::atoi(e); if (v >= 1 && v < cap) cap = v; }
+    for (int cand = cap; cand >= 1 && nw == 0; --cand) {
+      size_t front = 0, tail = gap + state_bytes * cand;
+      const size_t sizes[3] = {ints_bytes, tables_bytes, words_team * cand};
+      size_t offs[3];
+      for (int i = 0; i < 3; ++i) {
+        if (front + sizes[i] <= gap) { offs[i] = front; front += sizes[i]; }
+        else { offs[i] = tail; tail += sizes[i]; }
+      }
+      if (tail <= budget) { nw = cand; off_ints = offs[0]; off_tables = offs[1]; off_words = offs[2]; smem_warp = tail; }
+    }
   }
   p->warp_teams = nw >= 1;
   p->teams_per_cta = nw >= 1 ? nw : 1;
-  const size_t smem = p->warp_teams ? per_team * nw + tab_bytes : per_team;
+  const size_t smem = p->warp_teams ? smem_warp : per_team;
   if (smem > budget) {
     delete p;
     set_error("schedule needs %zu B of shared memory per team (w_max=%d) > %zu available", smem, d->w_max, budget);
@@ -598,6 +653,7 @@ extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
   D.n_steps = d->n_steps; D.n_vars = d->n_vars; D.n_checks = d->n_checks; D.n_obs = d->n_obs;
   D.w_max = d->w_max; D.sg_log2 = sg; D.nsw = nsw; D.ncw = ncw; D.bp_words = bp_off[d->n_steps];
   D.n_ints = (int32_t)d->n_ints; D.n_tables = (int32_t)d->n_tables;
+  D.off_states = (int32_t)off_states; D.off_ints = (int32_t)off_ints; D.off_tables = (int32_t)off_tables; D.off_words = (int32_t)off_words;
   // per-step fast-path flag (see fast_step): valid iff the element index splits into lane bits and j bits
   std::vector<int32_t> hdr(d->hdr, d->hdr + (size_t)d->n_steps * TQEC_HDR_INTS);
   {
