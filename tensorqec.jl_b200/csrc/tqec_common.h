@@ -31,7 +31,8 @@ void set_error(const char *fmt, ...);
     }                                  \
   } while (0)
 
-#define TQEC_H_FAST 14  // internal: header slot 14 (reserved in the ABI) carries the per-step fast-path flag
+#define TQEC_H_FAST 14  // internal (reserved slot of the ABI header): 0 or 1 + offset of the step's fast record in ints
+#define TQEC_H_AM 15    // internal (reserved slot): offset in ints of the traceback (assignment, mask) pairs
 
 static inline int words_for(int nbits) { return nbits <= 0 ? 1 : (nbits + 63) / 64; }
 

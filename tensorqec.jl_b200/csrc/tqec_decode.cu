@@ -35,15 +35,12 @@ __device__ __forceinline__ int insert_bit(int x, int slot, int bit) {
   return ((x >> slot) << (slot + 1)) | (bit << slot) | (x & ((1 << slot) - 1));
 }
 
+// full index of an output index: zeros are inserted at the closed slots (ascending), then the shot's closed-bit values
+// (precomputed once per shot and step in `cb`, already at their final positions) are OR-ed in.
 template <bool SM>
-__device__ __forceinline__ int rebuild_full(int tau, int sub, int n_close, const int32_t *__restrict__ CL,
-                                            const uint64_t *__restrict__ sh_syn, int nsw) {
+__device__ __forceinline__ int deposit0(int tau, int n_close, const int32_t *__restrict__ CL) {
   int full = tau;
-  for (int c = 0; c < n_close; ++c) {
-    const int slot = ldi<SM>(CL + 2 * c), bit = ldi<SM>(CL + 2 * c + 1);
-    const int sb = (int)((sh_syn[sub * nsw + (bit >> 6)] >> (bit & 63)) & 1ull);
-    full = insert_bit(full, slot, sb);
-  }
+  for (int c = 0; c < n_close; ++c) full = insert_bit(full, ldi<SM>(CL + 2 * c), 0);
   return full;
 }
 
@@ -51,7 +48,7 @@ __device__ __forceinline__ int rebuild_full(int tau, int sub, int n_close, const
 template <int SEMI, int NK, bool SM>
 __device__ __forceinline__ void run_step(const PlanDev &P, const Tabs &X, const int32_t *__restrict__ h,
                                          const double *__restrict__ Sin, double *__restrict__ Sout,
-                                         const uint64_t *__restrict__ sh_syn, uint32_t *__restrict__ bpt, int T, int tid) {
+                                         const int32_t *__restrict__ cbt, uint32_t *__restrict__ bpt, int T, int tid) {
   const int w_in = ldi<SM>(h + TQEC_H_WIN), n_close = ldi<SM>(h + TQEC_H_NCLOSE), w_out = ldi<SM>(h + TQEC_H_WOUT);
   const int nk = NK > 0 ? NK : ldi<SM>(h + TQEC_H_NK);
   const int kb = ldi<SM>(h + TQEC_H_KB);
@@ -66,7 +63,7 @@ __device__ __forceinline__ void run_step(const PlanDev &P, const Tabs &X, const 
   int jw = 0, wi = 0;
   for (int e = tid; e < n_tot; e += T) {
     const int tau = e & outmask, sub = e >> w_out;
-    const int full = rebuild_full<SM>(tau, sub, n_close, CL, sh_syn, P.nsw);
+    const int full = deposit0<SM>(tau, n_close, CL) | cbt[sub];
     const int pat = full >> w_in;
     const int low = (full & inmask) ^ ldi<SM>(ML + pat);
     const double *__restrict__ tb = Tt + pat * nk;
@@ -106,6 +103,12 @@ __device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
   asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v));
 }
 
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
 // One block of U consecutive elements of a thread (j = j0 .. j0+U-1, j0 a multiple of U): U*NK gathers (all issued
 // before the first use), U stores, U*kb back-pointer bits.  `gj8` is the j0-dependent byte offset (one broadcast load
 // per block); the other elements differ from it by the constants dl[u] (the deposited low bits of j).  Addresses are
@@ -118,7 +121,7 @@ __device__ __forceinline__ uint32_t fast_block(uint32_t so, const uint32_t (&ck8
 #pragma unroll
   for (int u = 0; u < U; ++u)
 #pragma unroll
-    for (int k = 0; k < NK; ++k) v[u][k] = lds_f64(u == 0 ? (ck8[k] ^ gj8) : (ck8[k] ^ gj8 ^ dl[u]));
+    for (int k = 0; k < NK; ++k) v[u][k] = lds_f64(u == 0 ? (ck8[k] ^ gj8) : xor3(ck8[k], gj8, dl[u]));
   uint32_t m = 0;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
@@ -151,115 +154,93 @@ __device__ __forceinline__ uint32_t fast_block(uint32_t so, const uint32_t (&ck8
   return m;
 }
 
-// The element index e = tid + 32*j splits into lane bits and j bits, and so does every quantity derived from it: the
-// re-inserted full index is deposit(tid) | deposit(j << 5) | closed-bit values, the opened pattern and the shot sub-index
-// depend on j only.  Per step each thread folds deposit(tid) and the state's base address into one XOR constant per
-// candidate, the j-dependent part sits in a 32-entry per-team table (one broadcast LDS per block), and factor values /
-// masks sit in registers, so a candidate costs LOP3 + LDS.64 + DADD (+ DSETP + 2 FSEL beyond the first).  The host sets
-// hdr[TQEC_H_FAST] when the split is valid for the chosen geometry.  `sin_abs` / `sout_abs` are absolute shared
-// addresses of the ping-pong states, multiples of the state size; `gtab` is the team's 32-entry table.
-template <int SEMI, int NK, bool SM>
-__device__ __forceinline__ void fast_step(const PlanDev &P, const Tabs &X, const int32_t *__restrict__ h,
-                                          uint32_t sin_abs, uint32_t sout_abs, uint32_t *__restrict__ gtab,
-                                          const uint64_t *__restrict__ sh_syn, uint32_t *__restrict__ bpt, int tid) {
-  constexpr int LT = 5, T = 32;
+template <int SEMI, int NK, int U>
+__device__ __forceinline__ void fast_blocks(int nblk, const double *__restrict__ rec, uint32_t pl8, uint32_t so,
+                                            const uint32_t (&dl)[8], const volatile uint32_t *__restrict__ gtab,
+                                            uint32_t *__restrict__ bpt, int tid) {
   constexpr int KB = NK == 1 ? 0 : (NK == 2 ? 1 : 2);
-  constexpr int UMAX = NK == 4 ? 4 : 8;
-  const int w_in = ldi<SM>(h + TQEC_H_WIN), n_open = ldi<SM>(h + TQEC_H_NOPEN), n_close = ldi<SM>(h + TQEC_H_NCLOSE);
-  const int w_out = ldi<SM>(h + TQEC_H_WOUT);
-  const double *__restrict__ Tt = X.tables + ldi<SM>(h + TQEC_H_OFF_T);
-  const int32_t *__restrict__ ML = X.ints + ldi<SM>(h + TQEC_H_OFF_ML);
-  const int32_t *__restrict__ MK = X.ints + ldi<SM>(h + TQEC_H_OFF_MK);
-  const int32_t *__restrict__ CL = X.ints + ldi<SM>(h + TQEC_H_OFF_CLOSE);
-  const int lane = tid;
-  const int lgJ = w_out + P.sg_log2 - LT, lg_jj = w_out - LT - n_open;
-  const int inmask = (1 << w_in) - 1, outmask = (1 << w_out) - 1;
-  int pl = tid;                                          // deposit(tid)
-  int dep1 = 1 << LT, dep2 = 2 << LT, dep4 = 4 << LT;    // deposit of the three low bits of j
-  const int ge = lane << LT;                             // first element of this lane's j
-  const int gsub = ge >> w_out;
-  const bool gvalid = lane < (1 << lgJ);
-  int gfull = ge & outmask;                              // deposit(j << 5) | closed-bit values of its shot
-  for (int c = 0; c < n_close; ++c) {
-    const int slot = ldi<SM>(CL + 2 * c), bit = ldi<SM>(CL + 2 * c + 1);
-    pl = insert_bit(pl, slot, 0);
-    dep1 = insert_bit(dep1, slot, 0);
-    dep2 = insert_bit(dep2, slot, 0);
-    dep4 = insert_bit(dep4, slot, 0);
-    const int sb = gvalid ? (int)((sh_syn[gsub * P.nsw + (bit >> 6)] >> (bit & 63)) & 1ull) : 0;
-    gfull = insert_bit(gfull, slot, sb);
-  }
-  gtab[lane] = (uint32_t)((gfull & inmask) << 3);
-  const uint32_t pl8 = (uint32_t)(pl << 3) ^ sin_abs;
-  uint32_t dl[8];
-  dl[0] = 0;
-  dl[1] = (uint32_t)((dep1 & inmask) << 3);
-  dl[2] = (uint32_t)((dep2 & inmask) << 3);
-  dl[4] = (uint32_t)((dep4 & inmask) << 3);
-  dl[3] = dl[1] | dl[2]; dl[5] = dl[1] | dl[4]; dl[6] = dl[2] | dl[4]; dl[7] = dl[3] | dl[4];
-  const int ngrp = 1 << (P.sg_log2 + n_open), njj = 1 << lg_jj;
+  constexpr int RB = NK + (NK + 1) / 2;                 // doubles per block record: NK factor values + packed masks
   uint32_t word = 0;
   int pos = 0, wi = 0;
-  const uint32_t so = sout_abs + (tid << 3);
-  __syncwarp();
-  for (int grp = 0; grp < ngrp; ++grp) {
-    const int pat = grp & ((1 << n_open) - 1), sub = grp >> n_open;
-    const int mlp = ldi<SM>(ML + pat);
+  for (int b = 0; b < nblk; ++b, rec += RB) {
     uint32_t ck8[NK];
     double tv[NK];
 #pragma unroll
-    for (int k = 0; k < NK; ++k) {
-      ck8[k] = (uint32_t)((((mlp ^ ldi<SM>(MK + k)) | (sub << w_in)) << 3)) ^ pl8;
-      tv[k] = ldd<SM>(Tt + pat * NK + k);
+    for (int k = 0; k < NK; ++k) tv[k] = rec[k];
+#pragma unroll
+    for (int k = 0; k < NK; k += 2) {
+      const int2 c2 = *reinterpret_cast<const int2 *>(rec + NK + k / 2);
+      ck8[k] = (uint32_t)c2.x ^ pl8;
+      if (k + 1 < NK) ck8[k + 1] = (uint32_t)c2.y ^ pl8;
     }
-    const int jbase = grp << lg_jj;
-    const volatile uint32_t *gt = gtab + jbase;
-    if (njj >= UMAX) {
-      for (int jj = 0; jj < njj; jj += UMAX) {
-        const uint32_t m = fast_block<SEMI, NK, UMAX>(so + ((jbase + jj) << 8), ck8, tv, dl, gt[jj]);
-        if (SEMI == TQEC_SEMIRING_MAXPLUS && KB) {
-          word |= m << pos;
-          pos += UMAX * KB;
-          if (pos == 32) { bpt[wi * T + tid] = word; word = 0; pos = 0; ++wi; }
-        }
-      }
-    } else if (UMAX == 8 && njj == 4) {
-      const uint32_t m = fast_block<SEMI, NK, 4>(so + (jbase << 8), ck8, tv, dl, gt[0]);
-      if (SEMI == TQEC_SEMIRING_MAXPLUS && KB) {
-        word |= m << pos;
-        pos += 4 * KB;
-        if (pos == 32) { bpt[wi * T + tid] = word; word = 0; pos = 0; ++wi; }
-      }
-    } else {
-      for (int jj = 0; jj < njj; ++jj) {
-        const uint32_t m = fast_block<SEMI, NK, 1>(so + ((jbase + jj) << 8), ck8, tv, dl, gt[jj]);
-        if (SEMI == TQEC_SEMIRING_MAXPLUS && KB) {
-          word |= m << pos;
-          pos += KB;
-          if (pos == 32) { bpt[wi * T + tid] = word; word = 0; pos = 0; ++wi; }
-        }
-      }
+    const uint32_t m = fast_block<SEMI, NK, U>(so + ((b * U) << 8), ck8, tv, dl, gtab[b * U]);
+    if (SEMI == TQEC_SEMIRING_MAXPLUS && KB) {
+      word |= m << pos;
+      pos += U * KB;
+      if (pos == 32) { bpt[wi * 32 + tid] = word; word = 0; pos = 0; ++wi; }
     }
   }
-  if (SEMI == TQEC_SEMIRING_MAXPLUS && KB && pos) bpt[wi * T + tid] = word;
+  if (SEMI == TQEC_SEMIRING_MAXPLUS && KB && pos) bpt[wi * 32 + tid] = word;
 }
 
-// ---- one traceback step (shared by both traceback shapes): returns the previous state index, ORs the factor's bits ------
+// The element index e = tid + 32*j splits into lane bits and j bits, and so does every quantity derived from it: the
+// re-inserted full index is deposit(tid) | deposit(j << 5) | closed-bit values, the opened pattern and the shot sub-index
+// depend on j only.  The host (build_device_tables) precomputes, per step, the deposits of the three low j bits and one
+// record per block of U elements {factor values, XOR constants per candidate}; the device adds the lane part and the
+// state's base address (a multiple of the state size, so XOR is enough) and keeps the j-dependent part in a 32-entry
+// per-team table (one broadcast LDS per block).  A candidate then costs LOP3 + LDS.64 + DADD (+ DSETP + 2 FSEL beyond
+// the first).  `sin_abs` / `sout_abs` are absolute shared addresses of the ping-pong states.
+template <int SEMI, int NK, bool SM>
+__device__ __forceinline__ void fast_step(const PlanDev &P, const Tabs &X, const int32_t *__restrict__ h,
+                                          const int32_t *__restrict__ frec, uint32_t sin_abs, uint32_t sout_abs,
+                                          uint32_t *__restrict__ gtab, const int32_t *__restrict__ cbt,
+                                          uint32_t *__restrict__ bpt, int tid) {
+  const int4 q0 = *reinterpret_cast<const int4 *>(h);            // r, w_in, n_open, n_close
+  const int w_in = q0.y, n_close = q0.w, w_out = ldi<SM>(h + TQEC_H_WOUT);
+  const int32_t *__restrict__ CL = X.ints + ldi<SM>(h + TQEC_H_OFF_CLOSE);
+  const int4 f0 = *reinterpret_cast<const int4 *>(frec);         // dl1, dl2, dl4, nblk
+  const int4 f1 = *reinterpret_cast<const int4 *>(frec + 4);     // U, off_blk
+  const int lane = tid;
+  const int inmask = (1 << w_in) - 1, outmask = (1 << w_out) - 1;
+  int pl = tid;                                                  // deposit(tid)
+  const int ge = lane << 5;                                      // first element of this lane's j
+  int gfull = ge & outmask;                                      // deposit(j << 5)
+  for (int c = 0; c < n_close; ++c) {
+    const int slot = ldi<SM>(CL + 2 * c);
+    pl = insert_bit(pl, slot, 0);
+    gfull = insert_bit(gfull, slot, 0);
+  }
+  const int gsub = (ge >> w_out) & ((1 << P.sg_log2) - 1);
+  gtab[lane] = (uint32_t)(((gfull | cbt[gsub]) & inmask) << 3);
+  const uint32_t pl8 = (uint32_t)(pl << 3) ^ sin_abs;
+  uint32_t dl[8];
+  dl[0] = 0; dl[1] = (uint32_t)f0.x; dl[2] = (uint32_t)f0.y; dl[4] = (uint32_t)f0.z;
+  dl[3] = dl[1] | dl[2]; dl[5] = dl[1] | dl[4]; dl[6] = dl[2] | dl[4]; dl[7] = dl[3] | dl[4];
+  const uint32_t so = sout_abs + (tid << 3);
+  const double *__restrict__ rec = X.tables + f1.y;
+  __syncwarp();
+  if (f1.x == 8) fast_blocks<SEMI, NK, (NK == 4 ? 4 : 8)>(f0.w, rec, pl8, so, dl, gtab, bpt, tid);
+  else if (f1.x == 4) fast_blocks<SEMI, NK, 4>(f0.w, rec, pl8, so, dl, gtab, bpt, tid);
+  else fast_blocks<SEMI, NK, 1>(f0.w, rec, pl8, so, dl, gtab, bpt, tid);
+}
+
+// ---- one traceback step (shared by both traceback shapes): returns the previous state index and the factor's bits ------
 template <bool SM>
-__device__ __forceinline__ int trace_step(const PlanDev &P, const Tabs &X, const int32_t *__restrict__ h, int tau, int sub,
-                                          int k, const uint64_t *__restrict__ sh_syn, int &a_out) {
-  const int w_in = ldi<SM>(h + TQEC_H_WIN);
+__device__ __forceinline__ int trace_step(const Tabs &X, const int32_t *__restrict__ h, int tau, int cbv, int k, int &a_out) {
+  const int4 q0 = *reinterpret_cast<const int4 *>(h);            // r, w_in, n_open, n_close
+  const int w_in = q0.y;
   const int32_t *CL = X.ints + ldi<SM>(h + TQEC_H_OFF_CLOSE);
-  const int full = rebuild_full<SM>(tau, sub, ldi<SM>(h + TQEC_H_NCLOSE), CL, sh_syn, P.nsw);
+  const int full = deposit0<SM>(tau, q0.w, CL) | cbv;
   const int pat = full >> w_in;
-  a_out = ldi<SM>(X.ints + ldi<SM>(h + TQEC_H_OFF_A0) + pat) ^ ldi<SM>(X.ints + ldi<SM>(h + TQEC_H_OFF_KER) + k);
-  return (full & ((1 << w_in) - 1)) ^ ldi<SM>(X.ints + ldi<SM>(h + TQEC_H_OFF_ML) + pat) ^
-         ldi<SM>(X.ints + ldi<SM>(h + TQEC_H_OFF_MK) + k);
+  // (assignment, in-state mask) of candidate k for this opened pattern, precomputed by the host
+  const int2 am = *reinterpret_cast<const int2 *>(X.ints + ldi<SM>(h + TQEC_H_AM) + 2 * (pat * ldi<SM>(h + TQEC_H_NK) + k));
+  a_out = am.x;
+  return (full & ((1 << w_in) - 1)) ^ am.y;
 }
 
 // ---- the team body ---------------------------------------------------------------------------------------------------
 template <int SEMI, bool WT>
-__device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, unsigned char *smem, int s0_off, uint64_t *sh_syn, uint64_t *sh_cfg, uint32_t *gtab,
+__device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, unsigned char *smem, int s0_off, uint64_t *sh_syn, uint64_t *sh_cfg, uint32_t *gtab, int32_t *cb,
                                          uint32_t *__restrict__ bp, int T, int LT, int tid, int64_t g_first, int64_t g_stride,
                                          const uint64_t *__restrict__ synd, int64_t B, uint64_t *__restrict__ corr,
                                          double *__restrict__ out, int32_t *__restrict__ argmax_out) {
@@ -282,6 +263,20 @@ __device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, unsign
       for (int i = tid; i < SG * P.ncw; i += T) sh_cfg[i] = 0ull;
     for (int i = tid; i < SG; i += T) S0[i] = ONE;
     team_sync<WT>();
+    // closed-bit values of every (step, shot): sum_c syndrome_bit(c) << slot(c)
+    for (int i = tid; i < (P.n_steps << P.sg_log2); i += T) {
+      const int t = i >> P.sg_log2, sub = i & (SG - 1);
+      const int32_t *h = X.hdr + t * TQEC_HDR_INTS;
+      const int n_close = ldi<SM>(h + TQEC_H_NCLOSE);
+      const int32_t *CL = X.ints + ldi<SM>(h + TQEC_H_OFF_CLOSE);
+      int v = 0;
+      for (int c = 0; c < n_close; ++c) {
+        const int bit = ldi<SM>(CL + 2 * c + 1);
+        v |= (int)((sh_syn[sub * P.nsw + (bit >> 6)] >> (bit & 63)) & 1ull) << ldi<SM>(CL + 2 * c);
+      }
+      cb[i] = v;
+    }
+    team_sync<WT>();
 
     double *Sin = S0, *Sout = S1;
     uint32_t sin_abs = (uint32_t)__cvta_generic_to_shared(S0), sout_abs = (uint32_t)__cvta_generic_to_shared(S1);
@@ -289,16 +284,19 @@ __device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, unsign
       const int32_t *h = X.hdr + t * TQEC_HDR_INTS;
       uint32_t *bpt = bp + ldi<SM>(X.bp_off + t);
       const int nk = ldi<SM>(h + TQEC_H_NK);
-      if (WT && ldi<SM>(h + TQEC_H_FAST)) {
-        if (nk == 2) fast_step<SEMI, 2, SM>(P, X, h, sin_abs, sout_abs, gtab, sh_syn, bpt, tid);
-        else if (nk == 1) fast_step<SEMI, 1, SM>(P, X, h, sin_abs, sout_abs, gtab, sh_syn, bpt, tid);
-        else fast_step<SEMI, 4, SM>(P, X, h, sin_abs, sout_abs, gtab, sh_syn, bpt, tid);
+      const int fo = WT ? ldi<SM>(h + TQEC_H_FAST) : 0;
+      const int32_t *cbt = cb + (t << P.sg_log2);
+      if (WT && fo) {
+        const int32_t *frec = X.ints + (fo - 1);
+        if (nk == 2) fast_step<SEMI, 2, SM>(P, X, h, frec, sin_abs, sout_abs, gtab, cbt, bpt, tid);
+        else if (nk == 1) fast_step<SEMI, 1, SM>(P, X, h, frec, sin_abs, sout_abs, gtab, cbt, bpt, tid);
+        else fast_step<SEMI, 4, SM>(P, X, h, frec, sin_abs, sout_abs, gtab, cbt, bpt, tid);
       } else {
         switch (nk) {
-          case 1: run_step<SEMI, 1, SM>(P, X, h, Sin, Sout, sh_syn, bpt, T, tid); break;
-          case 2: run_step<SEMI, 2, SM>(P, X, h, Sin, Sout, sh_syn, bpt, T, tid); break;
-          case 4: run_step<SEMI, 4, SM>(P, X, h, Sin, Sout, sh_syn, bpt, T, tid); break;
-          default: run_step<SEMI, 0, SM>(P, X, h, Sin, Sout, sh_syn, bpt, T, tid); break;
+          case 1: run_step<SEMI, 1, SM>(P, X, h, Sin, Sout, cbt, bpt, T, tid); break;
+          case 2: run_step<SEMI, 2, SM>(P, X, h, Sin, Sout, cbt, bpt, T, tid); break;
+          case 4: run_step<SEMI, 4, SM>(P, X, h, Sin, Sout, cbt, bpt, T, tid); break;
+          default: run_step<SEMI, 0, SM>(P, X, h, Sin, Sout, cbt, bpt, T, tid); break;
         }
       }
       team_sync<WT>();
@@ -347,7 +345,7 @@ __device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, unsign
                   k = (wv >> sh) & ((1u << kb) - 1u);
                 }
                 int a;
-                tau = trace_step<SM>(P, X, h, tau, sub, k, sh_syn, a);
+                tau = trace_step<SM>(X, h, tau, cb[(t << P.sg_log2) + sub], k, a);
                 const int32_t *V = X.ints + ldi<SM>(h + TQEC_H_OFF_VARS);
                 for (int j = 0; j < r; ++j)
                   if ((a >> j) & 1) {
@@ -378,7 +376,7 @@ __device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, unsign
               k = (wv >> (kb * (j % per_word))) & ((1u << kb) - 1u);
             }
             int a;
-            tau = trace_step<SM>(P, X, h, tau, sub, k, sh_syn, a);
+            tau = trace_step<SM>(X, h, tau, cb[(t << P.sg_log2) + sub], k, a);
             const int32_t *V = X.ints + ldi<SM>(h + TQEC_H_OFF_VARS);
             for (int j = 0; j < r; ++j)
               if ((a >> j) & 1) {
@@ -419,9 +417,15 @@ __device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, unsign
   }
 }
 
-// per-team shared memory: state ping-pong, syndrome words, configuration words
-__host__ __device__ inline size_t team_smem_bytes(int w_max, int sg, int nsw, int ncw) {
-  return 2 * ((size_t)1 << (w_max + sg)) * sizeof(double) + ((size_t)1 << sg) * (size_t)(nsw + ncw) * sizeof(uint64_t);
+// per-team words: syndrome words, configuration words, the 32-entry j table, closed-bit values per (step, shot)
+__host__ __device__ inline size_t team_words_bytes(int sg, int nsw, int ncw, int n_steps) {
+  const size_t b = ((size_t)1 << sg) * (size_t)(nsw + ncw) * sizeof(uint64_t) + 32 * sizeof(uint32_t) +
+                   ((size_t)n_steps << sg) * sizeof(int32_t);
+  return (b + 15) & ~(size_t)15;
+}
+// per-team shared memory of a CTA team: state ping-pong + words
+__host__ __device__ inline size_t team_smem_bytes(int w_max, int sg, int nsw, int ncw, int n_steps) {
+  return 2 * ((size_t)1 << (w_max + sg)) * sizeof(double) + team_words_bytes(sg, nsw, ncw, n_steps);
 }
 
 // CTA teams: blockDim.x threads form one team, tables in global memory
@@ -435,8 +439,10 @@ __global__ void k_frontier_cta(const PlanDev P, const uint64_t *__restrict__ syn
   const int SG = 1 << P.sg_log2;
   uint64_t *sh_syn = reinterpret_cast<uint64_t *>(smem_raw + ((size_t)16 << (P.w_max + P.sg_log2)));
   uint64_t *sh_cfg = sh_syn + SG * P.nsw;
+  uint32_t *gtab = reinterpret_cast<uint32_t *>(sh_cfg + SG * P.ncw);
+  int32_t *cb = reinterpret_cast<int32_t *>(gtab + 32);
   Tabs X{P.hdr, P.ints, P.bp_off, P.obs_slot, P.tables};
-  team_run<SEMI, false>(P, X, smem_raw, 0, sh_syn, sh_cfg, nullptr, bp_all + (size_t)blockIdx.x * P.bp_words, T, LT, tid, blockIdx.x,
+  team_run<SEMI, false>(P, X, smem_raw, 0, sh_syn, sh_cfg, gtab, cb, bp_all + (size_t)blockIdx.x * P.bp_words, T, LT, tid, blockIdx.x,
                         gridDim.x, synd, B, corr, out, argmax_out);
 }
 
@@ -453,13 +459,13 @@ __global__ void k_frontier_warp(const PlanDev P, const uint64_t *__restrict__ sy
   // them (the driver reserves the first KiB of the window) and the tail hold the table copies and the per-team words.
   const size_t state_bytes = (size_t)16 << (P.w_max + P.sg_log2);
   if (((uint32_t)__cvta_generic_to_shared(smem_raw) + P.off_states) & (uint32_t)(state_bytes / 2 - 1)) __trap();
-  const size_t words_bytes = (size_t)SG * (P.nsw + P.ncw) * sizeof(uint64_t) + 32 * sizeof(uint32_t);
+  const size_t words_bytes = team_words_bytes(P.sg_log2, P.nsw, P.ncw, P.n_steps);
   unsigned char *words0 = smem_raw + P.off_words;
   double *sm_tables = reinterpret_cast<double *>(smem_raw + P.off_tables);
-  int32_t *sm_hdr = reinterpret_cast<int32_t *>(smem_raw + P.off_ints);
-  int32_t *sm_bpoff = sm_hdr + P.n_steps * TQEC_HDR_INTS;
+  int32_t *sm_hdr = reinterpret_cast<int32_t *>(smem_raw + P.off_ints);   // 16-byte aligned; 64 B per step
+  int32_t *sm_ints = sm_hdr + P.n_steps * TQEC_HDR_INTS;                  // stays 16-byte aligned (int4 / int2 loads)
+  int32_t *sm_bpoff = sm_ints + P.n_ints;
   int32_t *sm_obs = sm_bpoff + P.n_steps + 1;
-  int32_t *sm_ints = sm_obs + P.n_obs;
   for (int i = threadIdx.x; i < P.n_tables; i += blockDim.x) sm_tables[i] = P.tables[i];
   for (int i = threadIdx.x; i < P.n_steps * TQEC_HDR_INTS; i += blockDim.x) sm_hdr[i] = P.hdr[i];
   for (int i = threadIdx.x; i <= P.n_steps; i += blockDim.x) sm_bpoff[i] = P.bp_off[i];
@@ -469,9 +475,10 @@ __global__ void k_frontier_warp(const PlanDev P, const uint64_t *__restrict__ sy
   uint64_t *sh_syn = reinterpret_cast<uint64_t *>(words0 + words_bytes * warp);
   uint64_t *sh_cfg = sh_syn + SG * P.nsw;
   uint32_t *gtab = reinterpret_cast<uint32_t *>(sh_cfg + SG * P.ncw);
+  int32_t *cb = reinterpret_cast<int32_t *>(gtab + 32);
   Tabs X{sm_hdr, sm_ints, sm_bpoff, sm_obs, sm_tables};
   const int64_t team = (int64_t)blockIdx.x * NW + warp;
-  team_run<SEMI, true>(P, X, smem_raw, (int)(P.off_states + state_bytes * warp), sh_syn, sh_cfg, gtab, bp_all + (size_t)team * P.bp_words, 32, 5, lane, team,
+  team_run<SEMI, true>(P, X, smem_raw, (int)(P.off_states + state_bytes * warp), sh_syn, sh_cfg, gtab, cb, bp_all + (size_t)team * P.bp_words, 32, 5, lane, team,
                        (int64_t)gridDim.x * NW, synd, B, corr, out, argmax_out);
 }
 
@@ -499,6 +506,73 @@ int launch_decode(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *
 }  // namespace tqec
 
 using namespace tqec;
+
+// Device-side tables derived from the ABI schedule (host, once per plan):
+//   hdr[t][TQEC_H_AM]   -> ints: (assignment, in-state mask) pairs of candidate k for opened pattern p at 2*(p*nk + k),
+//                          i.e. A0[p]^KER[k] and ML[p]^MK[k] -- one 8-byte load per traceback step
+//   hdr[t][TQEC_H_FAST] -> 0, or 1 + offset (16-byte aligned) of the fast-step record {dl1, dl2, dl4, nblk, U, off_blk}:
+//                          dl* = byte offsets of the deposited three low j bits; one record per block of U elements in
+//                          `tables` at off_blk: NK factor values, then the NK XOR constants ((ML^MK | sub << w_in) << 3)
+//                          packed two per double.  A step is fast iff the element index splits into lane bits and j
+//                          bits (see fast_step): 32-thread teams, <= 32 elements per thread, every closed slot below
+//                          w_in, the opened pattern determined by j alone, nk in {1, 2, 4}.
+static void build_device_tables(const tqec_plan_desc *d, int sg, bool want_fast, std::vector<int32_t> &hdr,
+                                std::vector<int32_t> &ints, std::vector<double> &tables) {
+  hdr.assign(d->hdr, d->hdr + (size_t)d->n_steps * TQEC_HDR_INTS);
+  ints.assign(d->ints, d->ints + d->n_ints);
+  tables.assign(d->tables, d->tables + d->n_tables);
+  const int LT = 5, T = 32;
+  auto dep0 = [&](int x, const int32_t *CL, int n_close) {
+    for (int c = 0; c < n_close; ++c) {
+      const int slot = CL[2 * c];
+      x = ((x >> slot) << (slot + 1)) | (x & ((1 << slot) - 1));
+    }
+    return x;
+  };
+  for (int t = 0; t < d->n_steps; ++t) {
+    int32_t *h = hdr.data() + (size_t)t * TQEC_HDR_INTS;
+    const int w_in = h[TQEC_H_WIN], n_open = h[TQEC_H_NOPEN], n_close = h[TQEC_H_NCLOSE], w_out = h[TQEC_H_WOUT];
+    const int nk = h[TQEC_H_NK], np = 1 << n_open;
+    const int32_t *CL = d->ints + h[TQEC_H_OFF_CLOSE];
+    const int32_t *ML = d->ints + h[TQEC_H_OFF_ML], *MK = d->ints + h[TQEC_H_OFF_MK];
+    const int32_t *A0 = d->ints + h[TQEC_H_OFF_A0], *KER = d->ints + h[TQEC_H_OFF_KER];
+    if (ints.size() & 1) ints.push_back(0);
+    h[TQEC_H_AM] = (int32_t)ints.size();
+    for (int pp = 0; pp < np; ++pp)
+      for (int k = 0; k < nk; ++k) { ints.push_back(A0[pp] ^ KER[k]); ints.push_back(ML[pp] ^ MK[k]); }
+    h[TQEC_H_FAST] = 0;
+    const int lgJ = w_out + sg - LT, lg_jj = w_out - LT - n_open;
+    bool ok = want_fast && lgJ >= 0 && lgJ <= 5 && lg_jj >= 0 && (nk == 1 || nk == 2 || nk == 4);
+    for (int c = 0; c < n_close && ok; ++c) if (CL[2 * c] >= w_in) ok = false;
+    if (ok && dep0(T - 1, CL, n_close) >= (1 << w_in)) ok = false;
+    if (!ok) continue;
+    const int inmask = (1 << w_in) - 1;
+    const int J = 1 << lgJ, njj = 1 << lg_jj;
+    const int umax = nk == 4 ? 4 : 8;
+    const int U = njj >= umax ? umax : (njj >= 4 ? 4 : 1);
+    while (ints.size() & 3) ints.push_back(0);
+    h[TQEC_H_FAST] = (int32_t)ints.size() + 1;
+    ints.push_back((dep0(1 << LT, CL, n_close) & inmask) << 3);
+    ints.push_back((dep0(2 << LT, CL, n_close) & inmask) << 3);
+    ints.push_back((dep0(4 << LT, CL, n_close) & inmask) << 3);
+    ints.push_back(J / U);
+    ints.push_back(U == umax ? 8 : U);       // 8 selects the widest block of this candidate count
+    ints.push_back((int32_t)tables.size());
+    ints.push_back(0); ints.push_back(0);
+    const double *Tt = d->tables + h[TQEC_H_OFF_T];
+    for (int b = 0; b < J / U; ++b) {
+      const int grp = (b * U) >> lg_jj, pat = grp & (np - 1), sub = grp >> n_open;
+      for (int k = 0; k < nk; ++k) tables.push_back(Tt[pat * nk + k]);
+      for (int k = 0; k < nk; k += 2) {
+        int32_t c2[2] = {0, 0};
+        for (int q = 0; q < 2 && k + q < nk; ++q) c2[q] = (int32_t)((((uint32_t)(ML[pat] ^ MK[k + q]) | ((uint32_t)sub << w_in)) << 3));
+        double packed;
+        std::memcpy(&packed, c2, sizeof(packed));
+        tables.push_back(packed);
+      }
+    }
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 static int validate_desc(const tqec_plan_desc *d) {
@@ -582,19 +656,26 @@ extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
   int T = 32;
   if (tot_bits > 10) T = 1 << (tot_bits - 5 > 8 ? 8 : tot_bits - 5);
   const int nsw = words_for(d->n_checks), ncw = words_for(d->n_vars);
-  const size_t per_team = team_smem_bytes(d->w_max, sg, nsw, ncw);
+  const bool want_warp = T == 32 && std::getenv("TQEC_NO_WARP_TEAMS") == nullptr;
+
+  // device tables: the ABI pools plus, per step, the traceback (assignment, mask) pairs and the fast-step records
+  std::vector<int32_t> hdr, ints;
+  std::vector<double> tables;
+  build_device_tables(d, sg, want_warp && std::getenv("TQEC_NO_FAST") == nullptr, hdr, ints, tables);
+
+  const size_t per_team = team_smem_bytes(d->w_max, sg, nsw, ncw, d->n_steps);
   const size_t budget = (size_t)prop.sharedMemPerBlockOptin;
   // warp-team layout: [front gap: whatever fits of the three blobs] [states, size-aligned absolute address] [rest]
   const size_t state_bytes = (size_t)16 << tot_bits, align = state_bytes / 2;
-  const size_t ints_bytes = (((size_t)d->n_steps * TQEC_HDR_INTS + d->n_steps + 1 + d->n_obs + (size_t)d->n_ints) * 4 + 7) & ~(size_t)7;
-  const size_t tables_bytes = (size_t)d->n_tables * 8;
-  const size_t words_team = ((size_t)1 << sg) * (size_t)(nsw + ncw) * 8 + 32 * 4;
+  const size_t ints_bytes = ((hdr.size() + d->n_steps + 1 + d->n_obs + ints.size()) * 4 + 15) & ~(size_t)15;
+  const size_t tables_bytes = (tables.size() * 8 + 15) & ~(size_t)15;
+  const size_t words_team = team_words_bytes(sg, nsw, ncw, d->n_steps);
   int reserved = 1024;
   cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, d->device);
   const size_t gap = (align - (size_t)reserved % align) % align;
   int nw = 0;
   size_t off_states = gap, off_ints = 0, off_tables = 0, off_words = 0, smem_warp = 0;
-  if (T == 32 && std::getenv("TQEC_NO_WARP_TEAMS") == nullptr) {
+  if (want_warp) {
     int cap = 16;
     if (const char *e = std::getenv("TQEC_TEAMS_PER_CTA")) { const int v = std::atoi(e); if (v >= 1 && v < cap) cap = v; }
     for (int cand = cap; cand >= 1 && nw == 0; --cand) {
@@ -652,33 +733,11 @@ extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
   PlanDev &D = p->dev;
   D.n_steps = d->n_steps; D.n_vars = d->n_vars; D.n_checks = d->n_checks; D.n_obs = d->n_obs;
   D.w_max = d->w_max; D.sg_log2 = sg; D.nsw = nsw; D.ncw = ncw; D.bp_words = bp_off[d->n_steps];
-  D.n_ints = (int32_t)d->n_ints; D.n_tables = (int32_t)d->n_tables;
+  D.n_ints = (int32_t)ints.size(); D.n_tables = (int32_t)tables.size();
   D.off_states = (int32_t)off_states; D.off_ints = (int32_t)off_ints; D.off_tables = (int32_t)off_tables; D.off_words = (int32_t)off_words;
-  // per-step fast-path flag (see fast_step): valid iff the element index splits into lane bits and j bits
-  std::vector<int32_t> hdr(d->hdr, d->hdr + (size_t)d->n_steps * TQEC_HDR_INTS);
-  {
-    int LT = 0;
-    while ((1 << LT) < T) ++LT;
-    const bool allow = std::getenv("TQEC_NO_FAST") == nullptr;
-    for (int t = 0; t < d->n_steps; ++t) {
-      int32_t *h = hdr.data() + t * TQEC_HDR_INTS;
-      const int w_in = h[TQEC_H_WIN], n_open = h[TQEC_H_NOPEN], n_close = h[TQEC_H_NCLOSE], w_out = h[TQEC_H_WOUT];
-      const int nk = h[TQEC_H_NK];
-      const int lgJ = w_out + sg - LT;
-      bool ok = allow && p->warp_teams && lgJ >= 0 && lgJ <= 5 && (w_out - LT - n_open) >= 0 && (nk == 1 || nk == 2 || nk == 4);
-      int dep = T - 1;
-      for (int c = 0; c < n_close && ok; ++c) {
-        const int slot = d->ints[h[TQEC_H_OFF_CLOSE] + 2 * c];
-        if (slot >= w_in) ok = false;
-        dep = ((dep >> slot) << (slot + 1)) | (dep & ((1 << slot) - 1));
-      }
-      if (ok && dep >= (1 << w_in)) ok = false;
-      h[TQEC_H_FAST] = ok ? 1 : 0;
-    }
-  }
   rc = upload(&p->d_hdr, hdr.data(), hdr.size());
-  if (!rc) rc = upload(&p->d_ints, d->ints, (size_t)d->n_ints);
-  if (!rc) rc = upload(&p->d_tables, d->tables, (size_t)d->n_tables);
+  if (!rc) rc = upload(&p->d_ints, ints.data(), ints.size());
+  if (!rc) rc = upload(&p->d_tables, tables.data(), tables.size());
   if (!rc) rc = upload(&p->d_bp_off, bp_off.data(), bp_off.size());
   if (!rc) rc = upload(&p->d_obs_slot, d->obs_slot, (size_t)d->n_obs);
   if (!rc) {
