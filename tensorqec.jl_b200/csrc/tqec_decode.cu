@@ -239,157 +239,191 @@ __device__ __forceinline__ int trace_step(const Tabs &X, const int32_t *__restri
 }
 
 // ---- the team body ---------------------------------------------------------------------------------------------------
+// forward sweep over all steps for the SG shots whose syndrome words sit in sh_syn; returns the final state
 template <int SEMI, bool WT>
-__device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, unsigned char *smem, int s0_off, uint64_t *sh_syn, uint64_t *sh_cfg, uint32_t *gtab, int32_t *cb,
-                                         uint32_t *__restrict__ bp, int T, int LT, int tid, int64_t g_first, int64_t g_stride,
+__device__ __forceinline__ double *forward_pass(const PlanDev &P, const Tabs &X, double *S0, const uint64_t *sh_syn,
+                                                uint32_t *gtab, int32_t *cb, uint32_t *__restrict__ bp, int T, int tid) {
+  constexpr bool SM = WT;
+  const int SG = 1 << P.sg_log2;
+  const int NS = 1 << (P.w_max + P.sg_log2);
+  double *S1 = S0 + NS;
+  const double ONE = SEMI == TQEC_SEMIRING_MAXPLUS ? 0.0 : 1.0;
+  for (int i = tid; i < SG; i += T) S0[i] = ONE;
+  // closed-bit values of every (step, shot): sum_c syndrome_bit(c) << slot(c)
+  for (int i = tid; i < (P.n_steps << P.sg_log2); i += T) {
+    const int t = i >> P.sg_log2, sub = i & (SG - 1);
+    const int32_t *h = X.hdr + t * TQEC_HDR_INTS;
+    const int n_close = ldi<SM>(h + TQEC_H_NCLOSE);
+    const int32_t *CL = X.ints + ldi<SM>(h + TQEC_H_OFF_CLOSE);
+    int v = 0;
+    for (int c = 0; c < n_close; ++c) {
+      const int bit = ldi<SM>(CL + 2 * c + 1);
+      v |= (int)((sh_syn[sub * P.nsw + (bit >> 6)] >> (bit & 63)) & 1ull) << ldi<SM>(CL + 2 * c);
+    }
+    cb[i] = v;
+  }
+  team_sync<WT>();
+
+  double *Sin = S0, *Sout = S1;
+  uint32_t sin_abs = (uint32_t)__cvta_generic_to_shared(S0), sout_abs = (uint32_t)__cvta_generic_to_shared(S1);
+  for (int t = 0; t < P.n_steps; ++t) {
+    const int32_t *h = X.hdr + t * TQEC_HDR_INTS;
+    uint32_t *bpt = bp + ldi<SM>(X.bp_off + t);
+    const int nk = ldi<SM>(h + TQEC_H_NK);
+    const int fo = WT ? ldi<SM>(h + TQEC_H_FAST) : 0;
+    const int32_t *cbt = cb + (t << P.sg_log2);
+    if (WT && fo) {
+      const int32_t *frec = X.ints + (fo - 1);
+      if (nk == 2) fast_step<SEMI, 2, SM>(P, X, h, frec, sin_abs, sout_abs, gtab, cbt, bpt, tid);
+      else if (nk == 1) fast_step<SEMI, 1, SM>(P, X, h, frec, sin_abs, sout_abs, gtab, cbt, bpt, tid);
+      else fast_step<SEMI, 4, SM>(P, X, h, frec, sin_abs, sout_abs, gtab, cbt, bpt, tid);
+    } else {
+      switch (nk) {
+        case 1: run_step<SEMI, 1, SM>(P, X, h, Sin, Sout, cbt, bpt, T, tid); break;
+        case 2: run_step<SEMI, 2, SM>(P, X, h, Sin, Sout, cbt, bpt, T, tid); break;
+        case 4: run_step<SEMI, 4, SM>(P, X, h, Sin, Sout, cbt, bpt, T, tid); break;
+        default: run_step<SEMI, 0, SM>(P, X, h, Sin, Sout, cbt, bpt, T, tid); break;
+      }
+    }
+    team_sync<WT>();
+    double *tmp = Sin; Sin = Sout; Sout = tmp;
+    const uint32_t to = sin_abs; sin_abs = sout_abs; sout_abs = to;
+  }
+  return Sin;
+}
+
+// back-pointer of output element e of a step: word index / shift inside the team's per-step block
+__device__ __forceinline__ void bp_locate(int e, int LT, int T, int kb, int &word, int &sh) {
+  const int j = e >> LT, ln = e & (T - 1);
+  int wi;
+  if (kb == 1) { wi = j >> 5; sh = j & 31; }
+  else if (kb == 2) { wi = j >> 4; sh = (j & 15) << 1; }
+  else { const int pw = 32 / kb; wi = j / pw; sh = (j - wi * pw) * kb; }
+  word = wi * T + ln;
+}
+
+template <int SEMI, bool WT>
+__device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, unsigned char *smem, int s0_off, uint64_t *sh_syn,
+                                         uint64_t *sh_cfg, uint32_t *gtab, int32_t *cb, uint32_t *__restrict__ bp, int T,
+                                         int LT, int tid, int64_t g_first, int64_t g_stride,
                                          const uint64_t *__restrict__ synd, int64_t B, uint64_t *__restrict__ corr,
                                          double *__restrict__ out, int32_t *__restrict__ argmax_out) {
   constexpr bool SM = WT;
   const int SG = 1 << P.sg_log2;
-  const int NS = 1 << (P.w_max + P.sg_log2);
   double *S0 = reinterpret_cast<double *>(smem + s0_off);
-  double *S1 = S0 + NS;
-  const int64_t n_groups = (B + SG - 1) >> P.sg_log2;
-  const double ONE = SEMI == TQEC_SEMIRING_MAXPLUS ? 0.0 : 1.0;
-  const bool coop_trace = WT && SG < 8 && P.ncw <= 32;
 
+  if (SEMI == TQEC_SEMIRING_MAXPLUS && WT && P.defer) {
+    // Deferred traceback (warp teams): the team runs the forward sweeps of 32 consecutive shots one pass after the other
+    // (each pass packs SG shots), keeping every pass's back-pointers in its own slice of the scratch; then lane q walks
+    // the back-pointers of shot q, so the serial traceback costs one warp-instruction stream per 32 shots, not per shot.
+    // Lane q keeps its shot's syndrome and configuration words in registers (nsw, ncw <= 4).
+    const int NF = 32 >> P.sg_log2;
+    const int64_t n_super = (B + 31) >> 5;
+    for (int64_t g = g_first; g < n_super; g += g_stride) {
+      const int64_t shot0 = g << 5, myshot = shot0 + tid;
+      uint64_t syn[4] = {0ull, 0ull, 0ull, 0ull};
+      if (myshot < B)
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+          if (w < P.nsw) syn[w] = synd[myshot * P.nsw + w];
+      for (int f = 0; f < NF; ++f) {
+        if (shot0 + (f << P.sg_log2) >= B) break;
+        if ((tid >> P.sg_log2) == f) {
+          const int sub = tid & (SG - 1);
+#pragma unroll
+          for (int w = 0; w < 4; ++w)
+            if (w < P.nsw) sh_syn[sub * P.nsw + w] = syn[w];
+        }
+        __syncwarp();
+        const double *Sfin = forward_pass<SEMI, WT>(P, X, S0, sh_syn, gtab, cb, bp + (size_t)f * P.bp_words, T, tid);
+        if (out && tid < SG && shot0 + (f << P.sg_log2) + tid < B) out[shot0 + (f << P.sg_log2) + tid] = Sfin[tid];
+        __syncwarp();
+      }
+      // lane q: traceback of shot q
+      const int f = tid >> P.sg_log2, sub = tid & (SG - 1);
+      const uint32_t *bpq = bp + (size_t)f * P.bp_words;
+      uint64_t cfg[4] = {0ull, 0ull, 0ull, 0ull};
+      int tau = 0;
+      for (int t = P.n_steps - 1; t >= 0; --t) {
+        const int32_t *h = X.hdr + t * TQEC_HDR_INTS;
+        const int4 q0 = *reinterpret_cast<const int4 *>(h);          // r, w_in, n_open, n_close
+        const int4 q1 = *reinterpret_cast<const int4 *>(h + 4);      // w_out, nk, kb, off_T
+        const int4 q3 = *reinterpret_cast<const int4 *>(h + 12);     // off_vars, off_close, fast, am
+        const int kb = q1.z;
+        int k = 0;
+        if (kb) {
+          int word, sh;
+          bp_locate((sub << q1.x) | tau, 5, 32, kb, word, sh);
+          k = (__ldcg(bpq + ldi<SM>(X.bp_off + t) + word) >> sh) & ((1u << kb) - 1u);
+        }
+        const int32_t *CL = X.ints + q3.y;
+        int full = tau;
+        for (int c = 0; c < q0.w; ++c) {
+          const int slot = ldi<SM>(CL + 2 * c), bit = ldi<SM>(CL + 2 * c + 1), w = bit >> 6;
+          const uint64_t sw = w == 0 ? syn[0] : (w == 1 ? syn[1] : (w == 2 ? syn[2] : syn[3]));
+          full = insert_bit(full, slot, (int)((sw >> (bit & 63)) & 1ull));
+        }
+        const int pat = full >> q0.y;
+        const int2 am = *reinterpret_cast<const int2 *>(X.ints + q3.w + 2 * (pat * q1.y + k));
+        const int32_t *V = X.ints + q3.x;
+        for (int j = 0; j < q0.x; ++j) {
+          const int v = ldi<SM>(V + j);
+          const uint64_t bitv = (uint64_t)((am.x >> j) & 1) << (v & 63);
+          const int w = v >> 6;
+          cfg[0] |= w == 0 ? bitv : 0ull; cfg[1] |= w == 1 ? bitv : 0ull;
+          cfg[2] |= w == 2 ? bitv : 0ull; cfg[3] |= w == 3 ? bitv : 0ull;
+        }
+        tau = (full & ((1 << q0.y) - 1)) ^ am.y;
+      }
+      if (myshot < B)
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+          if (w < P.ncw) corr[myshot * P.ncw + w] = cfg[w];
+      __syncwarp();
+    }
+    return;
+  }
+
+  const int64_t n_groups = (B + SG - 1) >> P.sg_log2;
   for (int64_t g = g_first; g < n_groups; g += g_stride) {
     const int64_t shot0 = g << P.sg_log2;
     for (int i = tid; i < SG * P.nsw; i += T) {
       const int64_t s = shot0 + i / P.nsw;
       sh_syn[i] = s < B ? synd[shot0 * P.nsw + i] : 0ull;
     }
-    if (SEMI == TQEC_SEMIRING_MAXPLUS && !coop_trace)
+    if (SEMI == TQEC_SEMIRING_MAXPLUS)
       for (int i = tid; i < SG * P.ncw; i += T) sh_cfg[i] = 0ull;
-    for (int i = tid; i < SG; i += T) S0[i] = ONE;
     team_sync<WT>();
-    // closed-bit values of every (step, shot): sum_c syndrome_bit(c) << slot(c)
-    for (int i = tid; i < (P.n_steps << P.sg_log2); i += T) {
-      const int t = i >> P.sg_log2, sub = i & (SG - 1);
-      const int32_t *h = X.hdr + t * TQEC_HDR_INTS;
-      const int n_close = ldi<SM>(h + TQEC_H_NCLOSE);
-      const int32_t *CL = X.ints + ldi<SM>(h + TQEC_H_OFF_CLOSE);
-      int v = 0;
-      for (int c = 0; c < n_close; ++c) {
-        const int bit = ldi<SM>(CL + 2 * c + 1);
-        v |= (int)((sh_syn[sub * P.nsw + (bit >> 6)] >> (bit & 63)) & 1ull) << ldi<SM>(CL + 2 * c);
-      }
-      cb[i] = v;
-    }
-    team_sync<WT>();
-
-    double *Sin = S0, *Sout = S1;
-    uint32_t sin_abs = (uint32_t)__cvta_generic_to_shared(S0), sout_abs = (uint32_t)__cvta_generic_to_shared(S1);
-    for (int t = 0; t < P.n_steps; ++t) {
-      const int32_t *h = X.hdr + t * TQEC_HDR_INTS;
-      uint32_t *bpt = bp + ldi<SM>(X.bp_off + t);
-      const int nk = ldi<SM>(h + TQEC_H_NK);
-      const int fo = WT ? ldi<SM>(h + TQEC_H_FAST) : 0;
-      const int32_t *cbt = cb + (t << P.sg_log2);
-      if (WT && fo) {
-        const int32_t *frec = X.ints + (fo - 1);
-        if (nk == 2) fast_step<SEMI, 2, SM>(P, X, h, frec, sin_abs, sout_abs, gtab, cbt, bpt, tid);
-        else if (nk == 1) fast_step<SEMI, 1, SM>(P, X, h, frec, sin_abs, sout_abs, gtab, cbt, bpt, tid);
-        else fast_step<SEMI, 4, SM>(P, X, h, frec, sin_abs, sout_abs, gtab, cbt, bpt, tid);
-      } else {
-        switch (nk) {
-          case 1: run_step<SEMI, 1, SM>(P, X, h, Sin, Sout, cbt, bpt, T, tid); break;
-          case 2: run_step<SEMI, 2, SM>(P, X, h, Sin, Sout, cbt, bpt, T, tid); break;
-          case 4: run_step<SEMI, 4, SM>(P, X, h, Sin, Sout, cbt, bpt, T, tid); break;
-          default: run_step<SEMI, 0, SM>(P, X, h, Sin, Sout, cbt, bpt, T, tid); break;
-        }
-      }
-      team_sync<WT>();
-      double *tmp = Sin; Sin = Sout; Sout = tmp;
-      const uint32_t to = sin_abs; sin_abs = sout_abs; sout_abs = to;
-    }
+    const double *Sin = forward_pass<SEMI, WT>(P, X, S0, sh_syn, gtab, cb, bp, T, tid);
 
     if (SEMI == TQEC_SEMIRING_MAXPLUS) {
-      if (coop_trace) {
-        // warp-cooperative traceback: the back-pointer words of 8 steps are fetched at once (lane l holds words l and
-        // 32 + l of each step, coalesced), then the chain is resolved from registers with one SHFL per step; lane w
-        // accumulates word w of the configuration.
-        const int lane = tid;
-        for (int sub = 0; sub < SG; ++sub) {
-          int tau = 0;
-          uint64_t myw = 0ull;
-          for (int t0 = P.n_steps - 1; t0 >= 0; t0 -= 8) {
-            uint32_t w0[8], w1[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int t = t0 - u;
-              w0[u] = 0u; w1[u] = 0u;
-              if (t >= 0) {
-                const int o0 = ldi<SM>(X.bp_off + t), nw = ldi<SM>(X.bp_off + t + 1) - o0;
-                if (nw > 0) w0[u] = __ldcg(bp + o0 + lane);
-                if (nw > 32) w1[u] = __ldcg(bp + o0 + 32 + lane);
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int t = t0 - u;
-              if (t >= 0) {
-                const int32_t *h = X.hdr + t * TQEC_HDR_INTS;
-                const int kb = ldi<SM>(h + TQEC_H_KB), r = ldi<SM>(h + TQEC_H_R);
-                int k = 0;
-                if (kb) {
-                  const int e = (sub << ldi<SM>(h + TQEC_H_WOUT)) | tau;
-                  const int j = e >> 5, ln = e & 31;
-                  int wi, sh;
-                  if (kb == 1) { wi = j >> 5; sh = j & 31; }
-                  else if (kb == 2) { wi = j >> 4; sh = (j & 15) << 1; }
-                  else { const int pw = 32 / kb; wi = j / pw; sh = (j - wi * pw) * kb; }
-                  uint32_t wv;
-                  if (wi < 2) wv = __shfl_sync(0xffffffffu, wi ? w1[u] : w0[u], ln);
-                  else wv = __ldcg(bp + ldi<SM>(X.bp_off + t) + wi * 32 + ln);
-                  k = (wv >> sh) & ((1u << kb) - 1u);
-                }
-                int a;
-                tau = trace_step<SM>(X, h, tau, cb[(t << P.sg_log2) + sub], k, a);
-                const int32_t *V = X.ints + ldi<SM>(h + TQEC_H_OFF_VARS);
-                for (int j = 0; j < r; ++j)
-                  if ((a >> j) & 1) {
-                    const int v = ldi<SM>(V + j);
-                    if (lane == (v >> 6)) myw |= 1ull << (v & 63);
-                  }
-              }
-            }
+      // one thread per shot walks the back-pointers from the scalar root to the first step
+      for (int sub = tid; sub < SG; sub += T) {
+        int tau = 0;
+        uint64_t *cfg = sh_cfg + sub * P.ncw;
+        for (int t = P.n_steps - 1; t >= 0; --t) {
+          const int32_t *h = X.hdr + t * TQEC_HDR_INTS;
+          const int kb = ldi<SM>(h + TQEC_H_KB), r = ldi<SM>(h + TQEC_H_R);
+          int k = 0;
+          if (kb) {
+            int word, sh;
+            bp_locate((sub << ldi<SM>(h + TQEC_H_WOUT)) | tau, LT, T, kb, word, sh);
+            k = (__ldcg(bp + ldi<SM>(X.bp_off + t) + word) >> sh) & ((1u << kb) - 1u);
           }
-          if (shot0 + sub < B) {
-            if (lane < P.ncw) corr[(shot0 + sub) * P.ncw + lane] = myw;
-            if (lane == 0 && out) out[shot0 + sub] = Sin[sub];
-          }
+          int a;
+          tau = trace_step<SM>(X, h, tau, cb[(t << P.sg_log2) + sub], k, a);
+          const int32_t *V = X.ints + ldi<SM>(h + TQEC_H_OFF_VARS);
+          for (int j = 0; j < r; ++j)
+            if ((a >> j) & 1) {
+              const int v = ldi<SM>(V + j);
+              cfg[v >> 6] |= 1ull << (v & 63);
+            }
         }
-      } else {
-        // one thread per shot walks the back-pointers from the scalar root to the first step
-        for (int sub = tid; sub < SG; sub += T) {
-          int tau = 0;
-          uint64_t *cfg = sh_cfg + sub * P.ncw;
-          for (int t = P.n_steps - 1; t >= 0; --t) {
-            const int32_t *h = X.hdr + t * TQEC_HDR_INTS;
-            const int kb = ldi<SM>(h + TQEC_H_KB), r = ldi<SM>(h + TQEC_H_R);
-            int k = 0;
-            if (kb) {
-              const int e = (sub << ldi<SM>(h + TQEC_H_WOUT)) | tau;
-              const int j = e >> LT, ln = e & (T - 1), per_word = 32 / kb;
-              const uint32_t wv = __ldcg(bp + ldi<SM>(X.bp_off + t) + (j / per_word) * T + ln);
-              k = (wv >> (kb * (j % per_word))) & ((1u << kb) - 1u);
-            }
-            int a;
-            tau = trace_step<SM>(X, h, tau, cb[(t << P.sg_log2) + sub], k, a);
-            const int32_t *V = X.ints + ldi<SM>(h + TQEC_H_OFF_VARS);
-            for (int j = 0; j < r; ++j)
-              if ((a >> j) & 1) {
-                const int v = ldi<SM>(V + j);
-                cfg[v >> 6] |= 1ull << (v & 63);
-              }
-          }
-          if (shot0 + sub < B && out) out[shot0 + sub] = Sin[sub];
-        }
-        team_sync<WT>();
-        for (int i = tid; i < SG * P.ncw; i += T)
-          if (shot0 + i / P.ncw < B) corr[shot0 * P.ncw + i] = sh_cfg[i];
+        if (shot0 + sub < B && out) out[shot0 + sub] = Sin[sub];
       }
+      team_sync<WT>();
+      for (int i = tid; i < SG * P.ncw; i += T)
+        if (shot0 + i / P.ncw < B) corr[shot0 * P.ncw + i] = sh_cfg[i];
     } else {
       const int NO = 1 << P.n_obs;
       for (int i = tid; i < SG * NO; i += T) {
@@ -478,14 +512,15 @@ __global__ void k_frontier_warp(const PlanDev P, const uint64_t *__restrict__ sy
   int32_t *cb = reinterpret_cast<int32_t *>(gtab + 32);
   Tabs X{sm_hdr, sm_ints, sm_bpoff, sm_obs, sm_tables};
   const int64_t team = (int64_t)blockIdx.x * NW + warp;
-  team_run<SEMI, true>(P, X, smem_raw, (int)(P.off_states + state_bytes * warp), sh_syn, sh_cfg, gtab, cb, bp_all + (size_t)team * P.bp_words, 32, 5, lane, team,
+  team_run<SEMI, true>(P, X, smem_raw, (int)(P.off_states + state_bytes * warp), sh_syn, sh_cfg, gtab, cb, bp_all + (size_t)team * P.bp_words * (P.defer ? (32 >> P.sg_log2) : 1), 32, 5, lane, team,
                        (int64_t)gridDim.x * NW, synd, B, corr, out, argmax_out);
 }
 
 int launch_decode(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d_corr, double *d_out,
                   int32_t *d_argmax, cudaStream_t stream) {
   if (B <= 0) return TQEC_OK;
-  const int64_t groups = (B + plan->shots_per_team - 1) / plan->shots_per_team;
+  const int64_t per_group = plan->dev.defer ? 32 : plan->shots_per_team;
+  const int64_t groups = (B + per_group - 1) / per_group;
   const bool mp = plan->semiring == TQEC_SEMIRING_MAXPLUS;
   if (plan->warp_teams) {
     const int64_t ctas = (groups + plan->teams_per_cta - 1) / plan->teams_per_cta;
@@ -734,6 +769,8 @@ extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
   D.n_steps = d->n_steps; D.n_vars = d->n_vars; D.n_checks = d->n_checks; D.n_obs = d->n_obs;
   D.w_max = d->w_max; D.sg_log2 = sg; D.nsw = nsw; D.ncw = ncw; D.bp_words = bp_off[d->n_steps];
   D.n_ints = (int32_t)ints.size(); D.n_tables = (int32_t)tables.size();
+  D.defer = (p->warp_teams && d->semiring == TQEC_SEMIRING_MAXPLUS && nsw <= 4 && ncw <= 4 && sg <= 5 &&
+             std::getenv("TQEC_NO_DEFER") == nullptr) ? 1 : 0;
   D.off_states = (int32_t)off_states; D.off_ints = (int32_t)off_ints; D.off_tables = (int32_t)off_tables; D.off_words = (int32_t)off_words;
   rc = upload(&p->d_hdr, hdr.data(), hdr.size());
   if (!rc) rc = upload(&p->d_ints, ints.data(), ints.size());
@@ -741,7 +778,8 @@ extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
   if (!rc) rc = upload(&p->d_bp_off, bp_off.data(), bp_off.size());
   if (!rc) rc = upload(&p->d_obs_slot, d->obs_slot, (size_t)d->n_obs);
   if (!rc) {
-    const size_t bytes = (size_t)p->grid_max * p->teams_per_cta * (D.bp_words ? D.bp_words : 1) * sizeof(uint32_t);
+    const size_t passes = D.defer ? (size_t)(32 >> sg) : 1;
+    const size_t bytes = (size_t)p->grid_max * p->teams_per_cta * passes * (D.bp_words ? D.bp_words : 1) * sizeof(uint32_t);
     cudaError_t e = cudaMalloc((void **)&p->d_bp, bytes);
     if (e != cudaSuccess) { set_error("cudaMalloc(%zu B back-pointer scratch): %s", bytes, cudaGetErrorString(e)); rc = TQEC_ERR_NOMEM; }
   }
