@@ -38,6 +38,15 @@ METRIC = "syndromes decoded/sec (TNMAP, d=9 surface code)"
 UNIT = "syndromes/s"
 
 
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arms set their thread count
+    explicitly instead)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def env_int(name, default):
     return int(os.environ.get(name, default))
 
@@ -59,7 +68,7 @@ def run_reference(args):
     em = tq.iid_error(P_ERR, t)
     nq, s2q, pix, pri = networks.general_problem_css(t, em.px, em.py, em.pz)
     dp = cref.DensePlan(networks.tnmap_network(nq, s2q, pix, pri), len(s2q), nq, True)
-    threads = cref.max_threads()
+    threads = host_threads()
     # calibrate the bounded sample: ~4 s of wall time per step
     ex, ez = philox.sample_depolarizing(em.px, em.py, em.pz, 9, 0, 4096)
     sx, sz = gf2.css_syndrome(ex, ez, t.stgx.H, t.stgz.H)
@@ -302,7 +311,7 @@ def cpu_baseline(tq, sch, syn_words, args):
     """C port of the frontier recurrence on all host cores, bounded sample of the same syndromes."""
     from oracle import cref
     fp = cref.FrontierPlan(sch)
-    threads = cref.max_threads()
+    threads = host_threads()
     nchk = sch.n_checks
     probe = tq.unpack_bits(syn_words[:4096], nchk)
     t0 = time.perf_counter()
