@@ -112,7 +112,14 @@ def _frontier_schedule(tq):
     t = tq.CSSTannerGraph(tq.SurfaceCode(D, D))
     em = tq.iid_error(P_ERR, t)
     gdp, _ = tq.reduce2general(t, em)
-    return t, em, tq.tnmap_schedule(tq.TNMAP(), gdp)
+    return t, em, tq.tnmap_schedule(tq.TNMAP(optimizer=_order()), gdp)
+
+
+def _order():
+    """BENCH_ORDER=boustro selects the boustrophedon sweep (experiments); default = the planner's choice."""
+    if os.environ.get("BENCH_ORDER") == "boustro":
+        return [i * D + (j if i % 2 == 0 else D - 1 - j) for i in range(D) for j in range(D)]
+    return None
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -178,7 +185,7 @@ def run_ours(args):
 
     B = int(args.shots)
     t, em, _ = _frontier_schedule(tq)
-    mc = tq.MonteCarlo(t, tq.TNMAP(device=local), em)
+    mc = tq.MonteCarlo(t, tq.TNMAP(optimizer=_order(), device=local), em)
     plan = mc.plan
     sch = plan.sch
     geom = plan.geometry()

@@ -1,0 +1,123 @@
+#!/usr/bin/env python
+"""All BASELINE.json configs other than the headline one (which bench.py measures): one JSON line per case.
+
+  1. d=3 surface, TNMAP, p=0.05, 1000 syndromes                       (configs[0])
+  2. d=5 / d=7 surface, TNMAP, p = 0.01..0.10 sweep, 1e6 syndromes     (configs[1])
+  4. DEM TNMMAP on the reference's DEM fixture                          (configs[3]; stim-generated surface-memory DEMs
+                                                                         need stim or the circuit->DEM generator)
+  5. Color488(5) and Steane, TNMAP, batch-size sweep 1..1e6            (configs[4]: latency vs throughput)
+plus TNMMAP (CSS) at d=3/5/7.  Timing: CUDA events around the device-pointer ABI call, inputs resident, 3 warm-ups.
+Logical-error counters come from the fused pipeline (`tqec_mc_run`) and are compared with the CPU port on a subsample.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import tensorqec.jl_b200 as tq            # noqa: E402
+from tensorqec.jl_b200 import _cabi      # noqa: E402
+from oracle import cref, gf2            # noqa: E402
+
+
+def time_map(plan, words, reps=5):
+    B = words.shape[0]
+    d_syn = torch.from_numpy(words.view(np.int64)).cuda()
+    d_cor = torch.empty((B, plan.ncw), dtype=torch.int64, device="cuda")
+    d_lp = torch.empty((B,), dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream()
+    for _ in range(3):
+        plan.decode_map_dev(d_syn.data_ptr(), B, d_cor.data_ptr(), d_lp.data_ptr(), st.cuda_stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(reps):
+        plan.decode_map_dev(d_syn.data_ptr(), B, d_cor.data_ptr(), d_lp.data_ptr(), st.cuda_stream)
+    e1.record(st)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def time_marginal(plan, words, reps=5):
+    B = words.shape[0]
+    d_syn = torch.from_numpy(words.view(np.int64)).cuda()
+    d_mar = torch.empty((B, 1 << plan.sch.n_obs), dtype=torch.float64, device="cuda")
+    d_arg = torch.empty((B,), dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream()
+    for _ in range(3):
+        plan.decode_marginal_dev(d_syn.data_ptr(), B, d_mar.data_ptr(), d_arg.data_ptr(), st.cuda_stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(reps):
+        plan.decode_marginal_dev(d_syn.data_ptr(), B, d_mar.data_ptr(), d_arg.data_ptr(), st.cuda_stream)
+    e1.record(st)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def css_case(name, code, p, B, seed, out):
+    t = tq.CSSTannerGraph(code)
+    em = tq.iid_error(p, t)
+    mc = tq.MonteCarlo(t, tq.TNMAP(), em)
+    plan = mc.plan
+    err = _cabi.sample_errors(_cabi.MODEL_DEPOL, [em.px, em.py, em.pz], seed, 0, B)
+    syn = mc.H.apply(err)
+    ms = time_map(plan, syn)
+    counts, mc_ms = mc.run(B, seed=seed)
+    # CPU port on a subsample: identical corrections => identical counters
+    n = min(B, 20000)
+    bits = tq.unpack_bits(syn[:n], plan.sch.n_checks)
+    t0 = time.perf_counter()
+    _, cfg = cref.FrontierPlan(plan.sch).run(bits, len(os.sched_getaffinity(0)))
+    cpu_rate = n / (time.perf_counter() - t0)
+    corr, _ = plan.decode_map(syn[:n], want_logp=False)
+    same = bool(np.array_equal(tq.unpack_bits(corr, plan.sch.n_vars), cfg))
+    rec = {"case": name, "p": p, "shots": B, "ms": ms, "syndromes_per_s": B / (ms * 1e-3), "pipeline_ms": mc_ms,
+           "pipeline_shots_per_s": B / (mc_ms * 1e-3), "logical": {"x": int(counts[0]), "z": int(counts[1]), "any": int(counts[2])},
+           "ler": counts[2] / B, "cpu_port_syndromes_per_s": cpu_rate, "cpu_threads": len(os.sched_getaffinity(0)),
+           "gpu_equals_cpu_port": same, "geometry": plan.geometry(), "w_max": plan.sch.w_max, "candidates_per_shot": plan.sch.cost}
+    print(json.dumps(rec), file=out, flush=True)
+    return rec
+
+
+def main():
+    out = open(os.path.join(ROOT, "gpurun_out", "configs.jsonl"), "w") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else sys.stdout
+    css_case("config1 d=3 TNMAP", tq.SurfaceCode(3, 3), 0.05, 1000, 0, out)
+    for d in (5, 7):
+        for i, p in enumerate(np.round(np.arange(0.01, 0.1001, 0.01), 2)):
+            css_case(f"config2 d={d} TNMAP sweep", tq.SurfaceCode(d, d), float(p), 1_000_000, 1000 * d + i, out)
+    for name, code in (("Color488(5)", tq.Color488(5)), ("Steane", tq.SteaneCode())):
+        for B in (1, 10, 100, 1000, 10_000, 100_000, 1_000_000):
+            css_case(f"config5 {name} TNMAP batch sweep", code, 0.05, B, 5, out)
+    # TNMMAP, CSS
+    for d, B in ((3, 1_000_000), (5, 1_000_000), (7, 200_000)):
+        t = tq.CSSTannerGraph(tq.SurfaceCode(d, d))
+        em = tq.iid_error(0.05, t)
+        ct = tq.compile(tq.TNMMAP(), t, em)
+        err = _cabi.sample_errors(_cabi.MODEL_DEPOL, [em.px, em.py, em.pz], 77, 0, B)
+        from tensorqec.jl_b200.threshold import css_general_matrices
+        H, _, _ = css_general_matrices(t, ct.lx, ct.lz)
+        syn = _cabi.GF2Matrix(H).apply(err)
+        ms = time_marginal(ct.plan, syn)
+        print(json.dumps({"case": f"TNMMAP d={d} CSS", "shots": B, "ms": ms, "syndromes_per_s": B / (ms * 1e-3),
+                          "geometry": ct.plan.geometry(), "w_max": ct.schedule.w_max, "candidates_per_shot": ct.schedule.cost}),
+              file=out, flush=True)
+    # DEM TNMMAP on the reference's fixture (config 4 input format)
+    dem = tq.parse_dem_file(os.path.join(ROOT, "tests", "golden", "dem.dem"))
+    ct = tq.compile(tq.TNMMAP(), dem)
+    B = 1_000_000
+    ep = _cabi.sample_errors(_cabi.MODEL_FLIP, [np.asarray(dem.error_rates)], 3, 0, B)
+    syn = _cabi.GF2Matrix(ct.tanner.H).apply(ep)
+    ms = time_marginal(ct.plan, syn)
+    print(json.dumps({"case": "config4 DEM fixture TNMMAP (21 mechanisms, 6 detectors)", "shots": B, "ms": ms,
+                      "syndromes_per_s": B / (ms * 1e-3), "geometry": ct.plan.geometry(), "w_max": ct.schedule.w_max}),
+          file=out, flush=True)
+
+
+if __name__ == "__main__":
+    main()

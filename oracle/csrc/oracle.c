@@ -152,12 +152,13 @@ typedef struct {
   const int32_t *obs_slot;
 } frontier_plan;
 
-static int rebuild_full(int tau, int n_close, const int32_t *CL, const uint64_t *syn) {
-  int full = tau;
-  for (int c = 0; c < n_close; ++c) {
-    const int slot = CL[2 * c], sb = bit_of(syn, CL[2 * c + 1]);
-    full = ((full >> slot) << (slot + 1)) | (sb << slot) | (full & ((1 << slot) - 1));
-  }
+/* output index -> full index: bit b goes to slot perm[b] (perm follows the closed list), closed slots take the
+ * shot's syndrome bits */
+static int rebuild_full(int tau, int w_out, int n_close, const int32_t *CL, const uint64_t *syn) {
+  const int32_t *perm = CL + 2 * n_close;
+  int full = 0;
+  for (int b = 0; b < w_out; ++b) full |= ((tau >> b) & 1) << perm[b];
+  for (int c = 0; c < n_close; ++c) full |= bit_of(syn, CL[2 * c + 1]) << CL[2 * c];
   return full;
 }
 
@@ -175,7 +176,7 @@ static double frontier_one(const frontier_plan *P, const uint64_t *syn, double *
     const int inmask = (1 << w_in) - 1;
     uint16_t *bpt = bp ? bp + (size_t)t * stride : NULL;
     for (int tau = 0; tau < (1 << w_out); ++tau) {
-      const int full = rebuild_full(tau, n_close, CL, syn);
+      const int full = rebuild_full(tau, w_out, n_close, CL, syn);
       const int pat = full >> w_in;
       const int low = (full & inmask) ^ ML[pat];
       const double *tb = T + pat * nk;
@@ -214,7 +215,7 @@ static double frontier_one(const frontier_plan *P, const uint64_t *syn, double *
       const int32_t *h = P->hdr + t * HDR_INTS;
       const int w_in = h[H_WIN], r = h[H_R];
       const int k = h[H_KB] ? bp[(size_t)t * stride + tau] : 0;
-      const int full = rebuild_full(tau, h[H_NCLOSE], P->ints + h[H_OFF_CLOSE], syn);
+      const int full = rebuild_full(tau, h[H_WOUT], h[H_NCLOSE], P->ints + h[H_OFF_CLOSE], syn);
       const int pat = full >> w_in;
       const int a = P->ints[h[H_OFF_A0] + pat] ^ P->ints[h[H_OFF_KER] + k];
       for (int j = 0; j < r; ++j)

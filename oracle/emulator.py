@@ -3,12 +3,27 @@
 Executes the flat arrays `hdr / ints / tables` emitted by `tensorqec.jl_b200.schedule._encode` with exactly the
 index arithmetic of the CUDA kernels (include/tqec.h, csrc/tqec_decode.cu): re-insert closed bits, read the opened
 pattern, gather over the coset, strict-greater update, 1 back-pointer of kb bits per output, serial traceback.
+Output bit b of a step lives at full slot perm[b]; the closed slots carry the shot's syndrome bits.
 It exists to check the LOWERING on a CPU-only box; the recurrence itself is checked by frontier.py.
 """
 import numpy as np
 
 (H_R, H_WIN, H_NOPEN, H_NCLOSE, H_WOUT, H_NK, H_KB, H_OFF_T, H_OFF_ML, H_OFF_MK, H_OFF_A0, H_OFF_KER, H_OFF_VARS,
  H_OFF_CLOSE) = range(14)
+
+
+def _scatter(sch, h, tau, syn, w_out, n_close):
+    """output index -> full index: bit b of tau goes to slot perm[b]; closed slots take the shot's syndrome bits.
+    The closed list (slot, syndrome bit) sits at ints[off_close ...], perm[w_out] right behind it."""
+    off = int(h[H_OFF_CLOSE])
+    perm = sch.ints[off + 2 * n_close: off + 2 * n_close + w_out]
+    full = np.zeros_like(tau)
+    for b in range(w_out):
+        full |= ((tau >> b) & 1) << int(perm[b])
+    for c in range(n_close):
+        slot, bit = int(sch.ints[off + 2 * c]), int(sch.ints[off + 2 * c + 1])
+        full |= syn[:, bit][:, None] << slot
+    return full
 
 
 def run(sch, syndromes):
@@ -22,12 +37,7 @@ def run(sch, syndromes):
     for h in sch.hdr:
         w_in, n_open, n_close, w_out, nk = (int(h[i]) for i in (H_WIN, H_NOPEN, H_NCLOSE, H_WOUT, H_NK))
         tau = np.arange(1 << w_out, dtype=np.int64)[None, :].repeat(B, axis=0)
-        full = tau.copy()
-        for c in range(n_close):
-            slot = int(sch.ints[h[H_OFF_CLOSE] + 2 * c])
-            bit = int(sch.ints[h[H_OFF_CLOSE] + 2 * c + 1])
-            low = full & ((1 << slot) - 1)
-            full = ((full >> slot) << (slot + 1)) | (syn[:, bit][:, None] << slot) | low
+        full = _scatter(sch, h, tau, syn, w_out, n_close)
         pat = full >> w_in
         low = (full & ((1 << w_in) - 1)) ^ sch.ints[h[H_OFF_ML] + pat]
         best = None
@@ -61,12 +71,7 @@ def run(sch, syndromes):
         h = sch.hdr[t]
         w_in, n_open, n_close, w_out, nk, r = (int(h[i]) for i in (H_WIN, H_NOPEN, H_NCLOSE, H_WOUT, H_NK, H_R))
         k = bps[t][np.arange(B), tau]
-        full = tau.copy()
-        for c in range(n_close):
-            slot = int(sch.ints[h[H_OFF_CLOSE] + 2 * c])
-            bit = int(sch.ints[h[H_OFF_CLOSE] + 2 * c + 1])
-            low = full & ((1 << slot) - 1)
-            full = ((full >> slot) << (slot + 1)) | (syn[:, bit] << slot) | low
+        full = _scatter(sch, h, tau[:, None], syn, w_out, n_close)[:, 0]
         pat = full >> w_in
         a = sch.ints[h[H_OFF_A0] + pat] ^ sch.ints[h[H_OFF_KER] + k]
         for j in range(r):

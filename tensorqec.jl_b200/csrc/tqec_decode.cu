@@ -35,12 +35,12 @@ __device__ __forceinline__ int insert_bit(int x, int slot, int bit) {
   return ((x >> slot) << (slot + 1)) | (bit << slot) | (x & ((1 << slot) - 1));
 }
 
-// full index of an output index: zeros are inserted at the closed slots (ascending), then the shot's closed-bit values
-// (precomputed once per shot and step in `cb`, already at their final positions) are OR-ed in.
+// full index of an output index: bit b goes to full slot perm[b] (perm[w_out] follows the closed list); the shot's
+// closed-bit values (precomputed once per shot and step in `cb`, already at their slots) are OR-ed in by the caller.
 template <bool SM>
-__device__ __forceinline__ int deposit0(int tau, int n_close, const int32_t *__restrict__ CL) {
-  int full = tau;
-  for (int c = 0; c < n_close; ++c) full = insert_bit(full, ldi<SM>(CL + 2 * c), 0);
+__device__ __forceinline__ int scatter_bits(int tau, int w_out, const int32_t *__restrict__ perm) {
+  int full = 0;
+  for (int b = 0; b < w_out; ++b) full |= ((tau >> b) & 1) << ldi<SM>(perm + b);
   return full;
 }
 
@@ -48,7 +48,8 @@ __device__ __forceinline__ int deposit0(int tau, int n_close, const int32_t *__r
 template <int SEMI, int NK, bool SM>
 __device__ __forceinline__ void run_step(const PlanDev &P, const Tabs &X, const int32_t *__restrict__ h,
                                          const double *__restrict__ Sin, double *__restrict__ Sout,
-                                         const int32_t *__restrict__ cbt, uint32_t *__restrict__ bpt, int T, int tid) {
+                                         const int32_t *__restrict__ cbt, uint32_t *__restrict__ gtab,
+                                         uint32_t *__restrict__ bpt, int T, int tid) {
   const int w_in = ldi<SM>(h + TQEC_H_WIN), n_close = ldi<SM>(h + TQEC_H_NCLOSE), w_out = ldi<SM>(h + TQEC_H_WOUT);
   const int nk = NK > 0 ? NK : ldi<SM>(h + TQEC_H_NK);
   const int kb = ldi<SM>(h + TQEC_H_KB);
@@ -61,9 +62,15 @@ __device__ __forceinline__ void run_step(const PlanDev &P, const Tabs &X, const 
   const int per_word = kb ? 32 / kb : 1;
   uint32_t word = 0;
   int jw = 0, wi = 0;
+  // the scattered image of the five low output bits is tabulated once per step; higher bits are scattered one by one
+  const int32_t *__restrict__ perm = CL + 2 * n_close;
+  const int wl = w_out < 5 ? w_out : 5;
+  if (tid < (1 << wl)) gtab[tid] = (uint32_t)scatter_bits<SM>(tid, wl, perm);
+  if (T == 32) __syncwarp(); else __syncthreads();
   for (int e = tid; e < n_tot; e += T) {
     const int tau = e & outmask, sub = e >> w_out;
-    const int full = deposit0<SM>(tau, n_close, CL) | cbt[sub];
+    int full = (int)gtab[tau & 31] | cbt[sub];
+    for (int b = 5; b < w_out; ++b) full |= ((tau >> b) & 1) << ldi<SM>(perm + b);
     const int pat = full >> w_in;
     const int low = (full & inmask) ^ ldi<SM>(ML + pat);
     const double *__restrict__ tb = Tt + pat * nk;
@@ -114,19 +121,33 @@ __device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
 // per block); the other elements differ from it by the constants dl[u] (the deposited low bits of j).  Addresses are
 // ABSOLUTE shared-memory addresses: the state's base is a multiple of its size, so base, lane part, candidate mask and
 // j part combine with XOR only and an address costs one LOP3.
-template <int SEMI, int NK, int U>
+template <int SEMI, int NK, int U, int CJ>
 __device__ __forceinline__ uint32_t fast_block(uint32_t so, const uint32_t (&ck8)[NK], const double (&tv)[NK],
                                                const uint32_t (&dl)[8], uint32_t gj8) {
+  // CJ > 0 (nk = 2 only): candidate 1 of element u reads exactly what candidate 0 of element u ^ CJ reads (the kernel
+  // candidate flips only low j bits), so each input is loaded once and used by both outputs of the pair.
+  constexpr int NL = CJ > 0 ? 1 : NK;
   double v[U][NK];
 #pragma unroll
   for (int u = 0; u < U; ++u)
 #pragma unroll
-    for (int k = 0; k < NK; ++k) v[u][k] = lds_f64(u == 0 ? (ck8[k] ^ gj8) : xor3(ck8[k], gj8, dl[u]));
+    for (int k = 0; k < NL; ++k) v[u][k] = lds_f64(u == 0 ? (ck8[k] ^ gj8) : xor3(ck8[k], gj8, dl[u]));
+  if (CJ > 0) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u][1 % NK] = v[(u ^ CJ) % U][0];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u][1 % NK] = SEMI == TQEC_SEMIRING_MAXPLUS ? v[u][1 % NK] + tv[1 % NK] : v[u][1 % NK] * tv[1 % NK];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u][0] = SEMI == TQEC_SEMIRING_MAXPLUS ? v[u][0] + tv[0] : v[u][0] * tv[0];
+  } else {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int k = 0; k < NK; ++k) v[u][k] = SEMI == TQEC_SEMIRING_MAXPLUS ? v[u][k] + tv[k] : v[u][k] * tv[k];
+  }
   uint32_t m = 0;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-#pragma unroll
-    for (int k = 0; k < NK; ++k) v[u][k] = SEMI == TQEC_SEMIRING_MAXPLUS ? v[u][k] + tv[k] : v[u][k] * tv[k];
     double best;
     if (SEMI == TQEC_SEMIRING_MAXPLUS) {
       // the smallest candidate index wins exact ties: the right operand of every comparison must be strictly greater
@@ -154,7 +175,7 @@ __device__ __forceinline__ uint32_t fast_block(uint32_t so, const uint32_t (&ck8
   return m;
 }
 
-template <int SEMI, int NK, int U>
+template <int SEMI, int NK, int U, int CJ>
 __device__ __forceinline__ void fast_blocks(int nblk, const double *__restrict__ rec, uint32_t pl8, uint32_t so,
                                             const uint32_t (&dl)[8], const volatile uint32_t *__restrict__ gtab,
                                             uint32_t *__restrict__ bpt, int tid) {
@@ -173,7 +194,7 @@ __device__ __forceinline__ void fast_blocks(int nblk, const double *__restrict__
       ck8[k] = (uint32_t)c2.x ^ pl8;
       if (k + 1 < NK) ck8[k + 1] = (uint32_t)c2.y ^ pl8;
     }
-    const uint32_t m = fast_block<SEMI, NK, U>(so + ((b * U) << 8), ck8, tv, dl, gtab[b * U]);
+    const uint32_t m = fast_block<SEMI, NK, U, CJ>(so + ((b * U) << 8), ck8, tv, dl, gtab[b * U]);
     if (SEMI == TQEC_SEMIRING_MAXPLUS && KB) {
       word |= m << pos;
       pos += U * KB;
@@ -196,21 +217,26 @@ __device__ __forceinline__ void fast_step(const PlanDev &P, const Tabs &X, const
                                           uint32_t *__restrict__ gtab, const int32_t *__restrict__ cbt,
                                           uint32_t *__restrict__ bpt, int tid) {
   const int4 q0 = *reinterpret_cast<const int4 *>(h);            // r, w_in, n_open, n_close
-  const int w_in = q0.y, n_close = q0.w, w_out = ldi<SM>(h + TQEC_H_WOUT);
-  const int32_t *__restrict__ CL = X.ints + ldi<SM>(h + TQEC_H_OFF_CLOSE);
+  const int w_in = q0.y, w_out = ldi<SM>(h + TQEC_H_WOUT);
   const int4 f0 = *reinterpret_cast<const int4 *>(frec);         // dl1, dl2, dl4, nblk
-  const int4 f1 = *reinterpret_cast<const int4 *>(frec + 4);     // U, off_blk
+  const int4 f1 = *reinterpret_cast<const int4 *>(frec + 4);     // U, off_blk, cj, -
+  const int4 f2 = *reinterpret_cast<const int4 *>(frec + 8);     // full slots of output bits 0..3
+  const int4 f3 = *reinterpret_cast<const int4 *>(frec + 12);    // full slot of output bit 4, then bits 5..7
+  const int4 f4 = *reinterpret_cast<const int4 *>(frec + 16);    // full slots of output bits 8, 9 (unused: -1 -> shift by 31 of a 0 bit)
   const int lane = tid;
-  const int inmask = (1 << w_in) - 1, outmask = (1 << w_out) - 1;
-  int pl = tid;                                                  // deposit(tid)
-  const int ge = lane << 5;                                      // first element of this lane's j
-  int gfull = ge & outmask;                                      // deposit(j << 5)
-  for (int c = 0; c < n_close; ++c) {
-    const int slot = ldi<SM>(CL + 2 * c);
-    pl = insert_bit(pl, slot, 0);
-    gfull = insert_bit(gfull, slot, 0);
-  }
-  const int gsub = (ge >> w_out) & ((1 << P.sg_log2) - 1);
+  const int inmask = (1 << w_in) - 1;
+  // lane part: output bits 0..4 are lane bits
+  const int pl = ((lane & 1) << f2.x) | (((lane >> 1) & 1) << f2.y) | (((lane >> 2) & 1) << f2.z) |
+                 (((lane >> 3) & 1) << f2.w) | (((lane >> 4) & 1) << f3.x);
+  // j part of lane's own j (= lane): output bits 5..9 are j bits 0..4 (bits beyond w_out select the shot)
+  const int nj = w_out - 5;                                      // state bits among the j bits
+  int gfull = 0;
+  if (nj > 0) gfull |= (lane & 1) << f3.y;
+  if (nj > 1) gfull |= ((lane >> 1) & 1) << f3.z;
+  if (nj > 2) gfull |= ((lane >> 2) & 1) << f3.w;
+  if (nj > 3) gfull |= ((lane >> 3) & 1) << f4.x;
+  if (nj > 4) gfull |= ((lane >> 4) & 1) << f4.y;
+  const int gsub = ((lane << 5) >> w_out) & ((1 << P.sg_log2) - 1);
   gtab[lane] = (uint32_t)(((gfull | cbt[gsub]) & inmask) << 3);
   const uint32_t pl8 = (uint32_t)(pl << 3) ^ sin_abs;
   uint32_t dl[8];
@@ -219,9 +245,15 @@ __device__ __forceinline__ void fast_step(const PlanDev &P, const Tabs &X, const
   const uint32_t so = sout_abs + (tid << 3);
   const double *__restrict__ rec = X.tables + f1.y;
   __syncwarp();
-  if (f1.x == 8) fast_blocks<SEMI, NK, (NK == 4 ? 4 : 8)>(f0.w, rec, pl8, so, dl, gtab, bpt, tid);
-  else if (f1.x == 4) fast_blocks<SEMI, NK, 4>(f0.w, rec, pl8, so, dl, gtab, bpt, tid);
-  else fast_blocks<SEMI, NK, 1>(f0.w, rec, pl8, so, dl, gtab, bpt, tid);
+  if (NK == 2 && f1.z == 1) {
+    if (f1.x == 8) fast_blocks<SEMI, NK, 8, 1>(f0.w, rec, pl8, so, dl, gtab, bpt, tid);
+    else fast_blocks<SEMI, NK, 4, 1>(f0.w, rec, pl8, so, dl, gtab, bpt, tid);
+  } else if (NK == 2 && f1.z == 3) {
+    if (f1.x == 8) fast_blocks<SEMI, NK, 8, 3>(f0.w, rec, pl8, so, dl, gtab, bpt, tid);
+    else fast_blocks<SEMI, NK, 4, 3>(f0.w, rec, pl8, so, dl, gtab, bpt, tid);
+  } else if (f1.x == 8) fast_blocks<SEMI, NK, (NK == 4 ? 4 : 8), 0>(f0.w, rec, pl8, so, dl, gtab, bpt, tid);
+  else if (f1.x == 4) fast_blocks<SEMI, NK, 4, 0>(f0.w, rec, pl8, so, dl, gtab, bpt, tid);
+  else fast_blocks<SEMI, NK, 1, 0>(f0.w, rec, pl8, so, dl, gtab, bpt, tid);
 }
 
 // ---- one traceback step (shared by both traceback shapes): returns the previous state index and the factor's bits ------
@@ -230,7 +262,7 @@ __device__ __forceinline__ int trace_step(const Tabs &X, const int32_t *__restri
   const int4 q0 = *reinterpret_cast<const int4 *>(h);            // r, w_in, n_open, n_close
   const int w_in = q0.y;
   const int32_t *CL = X.ints + ldi<SM>(h + TQEC_H_OFF_CLOSE);
-  const int full = deposit0<SM>(tau, q0.w, CL) | cbv;
+  const int full = scatter_bits<SM>(tau, ldi<SM>(h + TQEC_H_WOUT), CL + 2 * q0.w) | cbv;
   const int pat = full >> w_in;
   // (assignment, in-state mask) of candidate k for this opened pattern, precomputed by the host
   const int2 am = *reinterpret_cast<const int2 *>(X.ints + ldi<SM>(h + TQEC_H_AM) + 2 * (pat * ldi<SM>(h + TQEC_H_NK) + k));
@@ -279,10 +311,10 @@ __device__ __forceinline__ double *forward_pass(const PlanDev &P, const Tabs &X,
       else fast_step<SEMI, 4, SM>(P, X, h, frec, sin_abs, sout_abs, gtab, cbt, bpt, tid);
     } else {
       switch (nk) {
-        case 1: run_step<SEMI, 1, SM>(P, X, h, Sin, Sout, cbt, bpt, T, tid); break;
-        case 2: run_step<SEMI, 2, SM>(P, X, h, Sin, Sout, cbt, bpt, T, tid); break;
-        case 4: run_step<SEMI, 4, SM>(P, X, h, Sin, Sout, cbt, bpt, T, tid); break;
-        default: run_step<SEMI, 0, SM>(P, X, h, Sin, Sout, cbt, bpt, T, tid); break;
+        case 1: run_step<SEMI, 1, SM>(P, X, h, Sin, Sout, cbt, gtab, bpt, T, tid); break;
+        case 2: run_step<SEMI, 2, SM>(P, X, h, Sin, Sout, cbt, gtab, bpt, T, tid); break;
+        case 4: run_step<SEMI, 4, SM>(P, X, h, Sin, Sout, cbt, gtab, bpt, T, tid); break;
+        default: run_step<SEMI, 0, SM>(P, X, h, Sin, Sout, cbt, gtab, bpt, T, tid); break;
       }
     }
     team_sync<WT>();
@@ -357,11 +389,11 @@ __device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, unsign
           k = (__ldcg(bpq + ldi<SM>(X.bp_off + t) + word) >> sh) & ((1u << kb) - 1u);
         }
         const int32_t *CL = X.ints + q3.y;
-        int full = tau;
+        int full = scatter_bits<SM>(tau, q1.x, CL + 2 * q0.w);
         for (int c = 0; c < q0.w; ++c) {
           const int slot = ldi<SM>(CL + 2 * c), bit = ldi<SM>(CL + 2 * c + 1), w = bit >> 6;
           const uint64_t sw = w == 0 ? syn[0] : (w == 1 ? syn[1] : (w == 2 ? syn[2] : syn[3]));
-          full = insert_bit(full, slot, (int)((sw >> (bit & 63)) & 1ull));
+          full |= (int)((sw >> (bit & 63)) & 1ull) << slot;
         }
         const int pat = full >> q0.y;
         const int2 am = *reinterpret_cast<const int2 *>(X.ints + q3.w + 2 * (pat * q1.y + k));
@@ -556,19 +588,12 @@ static void build_device_tables(const tqec_plan_desc *d, int sg, bool want_fast,
   hdr.assign(d->hdr, d->hdr + (size_t)d->n_steps * TQEC_HDR_INTS);
   ints.assign(d->ints, d->ints + d->n_ints);
   tables.assign(d->tables, d->tables + d->n_tables);
-  const int LT = 5, T = 32;
-  auto dep0 = [&](int x, const int32_t *CL, int n_close) {
-    for (int c = 0; c < n_close; ++c) {
-      const int slot = CL[2 * c];
-      x = ((x >> slot) << (slot + 1)) | (x & ((1 << slot) - 1));
-    }
-    return x;
-  };
+  const int LT = 5;
   for (int t = 0; t < d->n_steps; ++t) {
     int32_t *h = hdr.data() + (size_t)t * TQEC_HDR_INTS;
     const int w_in = h[TQEC_H_WIN], n_open = h[TQEC_H_NOPEN], n_close = h[TQEC_H_NCLOSE], w_out = h[TQEC_H_WOUT];
     const int nk = h[TQEC_H_NK], np = 1 << n_open;
-    const int32_t *CL = d->ints + h[TQEC_H_OFF_CLOSE];
+    const int32_t *perm = d->ints + h[TQEC_H_OFF_CLOSE] + 2 * n_close;
     const int32_t *ML = d->ints + h[TQEC_H_OFF_ML], *MK = d->ints + h[TQEC_H_OFF_MK];
     const int32_t *A0 = d->ints + h[TQEC_H_OFF_A0], *KER = d->ints + h[TQEC_H_OFF_KER];
     if (ints.size() & 1) ints.push_back(0);
@@ -578,21 +603,30 @@ static void build_device_tables(const tqec_plan_desc *d, int sg, bool want_fast,
     h[TQEC_H_FAST] = 0;
     const int lgJ = w_out + sg - LT, lg_jj = w_out - LT - n_open;
     bool ok = want_fast && lgJ >= 0 && lgJ <= 5 && lg_jj >= 0 && (nk == 1 || nk == 2 || nk == 4);
-    for (int c = 0; c < n_close && ok; ++c) if (CL[2 * c] >= w_in) ok = false;
-    if (ok && dep0(T - 1, CL, n_close) >= (1 << w_in)) ok = false;
+    // lane bits must land inside the input state; the opened slots must be the top output bits, in order
+    for (int b = 0; b < 5 && ok; ++b) if (perm[b] >= w_in) ok = false;
+    for (int i = 0; i < n_open && ok; ++i) if (perm[w_out - n_open + i] != w_in + i) ok = false;
     if (!ok) continue;
     const int inmask = (1 << w_in) - 1;
     const int J = 1 << lgJ, njj = 1 << lg_jj;
     const int umax = nk == 4 ? 4 : 8;
     const int U = njj >= umax ? umax : (njj >= 4 ? 4 : 1);
+    auto slot8 = [&](int b) { return b < w_out ? (int32_t)(((1 << perm[b]) & inmask) << 3) : 0; };
+    // pairing (nk = 2): the kernel candidate's mask must be exactly the image of the lowest one or two j bits
+    int cj = 0;
+    if (nk == 2 && U >= 4) {
+      const int m1 = MK[1];
+      if (w_out > 5 && m1 == ((1 << perm[5]) & inmask) && m1 != 0) cj = 1;
+      else if (w_out > 6 && m1 == (((1 << perm[5]) | (1 << perm[6])) & inmask) && perm[5] < w_in && perm[6] < w_in) cj = 3;
+    }
     while (ints.size() & 3) ints.push_back(0);
     h[TQEC_H_FAST] = (int32_t)ints.size() + 1;
-    ints.push_back((dep0(1 << LT, CL, n_close) & inmask) << 3);
-    ints.push_back((dep0(2 << LT, CL, n_close) & inmask) << 3);
-    ints.push_back((dep0(4 << LT, CL, n_close) & inmask) << 3);
+    ints.push_back(slot8(5)); ints.push_back(slot8(6)); ints.push_back(slot8(7));
     ints.push_back(J / U);
     ints.push_back(U == umax ? 8 : U);       // 8 selects the widest block of this candidate count
     ints.push_back((int32_t)tables.size());
+    ints.push_back(cj); ints.push_back(0);
+    for (int b = 0; b < 10; ++b) ints.push_back(b < w_out ? perm[b] : 0);
     ints.push_back(0); ints.push_back(0);
     const double *Tt = d->tables + h[TQEC_H_OFF_T];
     for (int b = 0; b < J / U; ++b) {
@@ -640,12 +674,18 @@ static int validate_desc(const tqec_plan_desc *d) {
       TQEC_REQUIRE((d->ints[offs[1] + k] >> w_in) == 0, "step %d: kernel mask leaves the in-state", t);
     for (int j = 0; j < r; ++j)
       TQEC_REQUIRE(d->ints[offs[4] + j] >= 0 && d->ints[offs[4] + j] < d->n_vars, "step %d: variable id out of range", t);
-    int prev = -1;
+    uint32_t used = 0;
     for (int c = 0; c < n_close; ++c) {
       const int slot = d->ints[offs[5] + 2 * c], bit = d->ints[offs[5] + 2 * c + 1];
-      TQEC_REQUIRE(slot > prev && slot < w_in + n_open, "step %d: closed slots must ascend inside the full index", t);
+      TQEC_REQUIRE(slot >= 0 && slot < w_in + n_open && !((used >> slot) & 1u), "step %d: bad closed slot %d", t, slot);
       TQEC_REQUIRE(bit >= 0 && bit < d->n_checks, "step %d: syndrome bit %d out of range", t, bit);
-      prev = slot;
+      used |= 1u << slot;
+    }
+    TQEC_REQUIRE(offs[5] + 2 * (int64_t)n_close + w_out <= d->n_ints, "step %d: output permutation out of range", t);
+    for (int b = 0; b < w_out; ++b) {
+      const int slot = d->ints[offs[5] + 2 * n_close + b];
+      TQEC_REQUIRE(slot >= 0 && slot < w_in + n_open && !((used >> slot) & 1u), "step %d: output bit %d maps to a bad or repeated slot %d", t, b, slot);
+      used |= 1u << slot;
     }
     w = w_out;
     wmax = wmax > w_in ? wmax : w_in;
@@ -684,7 +724,8 @@ extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
   p->sm_count = prop.multiProcessorCount;
 
   // launch geometry: ~1024 state entries per team; narrow plans pack several shots per team
-  const int target_bits = 10;
+  int target_bits = 10;
+  if (const char *e = std::getenv("TQEC_TARGET_BITS")) { const int v = std::atoi(e); if (v >= 5 && v <= 10) target_bits = v; }
   int sg = d->w_max < target_bits ? target_bits - d->w_max : 0;
   if (sg > 6) sg = 6;
   const int tot_bits = d->w_max + sg;
@@ -711,7 +752,20 @@ extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
   int nw = 0;
   size_t off_states = gap, off_ints = 0, off_tables = 0, off_words = 0, smem_warp = 0;
   if (want_warp) {
-    int cap = 16;
+    // teams per CTA: bounded by the register file (one CTA per SM: teams x 32 threads x registers per thread)
+    int cap = 32;
+    {
+      cudaFuncAttributes fa;
+      const void *wk = d->semiring == TQEC_SEMIRING_MAXPLUS ? (const void *)k_frontier_warp<TQEC_SEMIRING_MAXPLUS>
+                                                            : (const void *)k_frontier_warp<TQEC_SEMIRING_SUMPROD>;
+      if (cudaFuncGetAttributes(&fa, wk) == cudaSuccess && fa.numRegs > 0) {
+        const int regs = (fa.numRegs + 7) & ~7;
+        int by_regs = prop.regsPerBlock / (regs * 32);
+        if (fa.maxThreadsPerBlock / 32 < by_regs) by_regs = fa.maxThreadsPerBlock / 32;
+        if (by_regs < cap) cap = by_regs;
+      }
+      if (cap < 1) cap = 1;
+    }
     if (const char *e = std::getenv("TQEC_TEAMS_PER_CTA")) { const int v = std::atoi(e); if (v >= 1 && v < cap) cap = v; }
     for (int cand = cap; cand >= 1 && nw == 0; --cand) {
       size_t front = 0, tail = gap + state_bytes * cand;

@@ -25,11 +25,13 @@ with variables v_1..v_r and table T[a], a = sum_j a_j 2^j (first label fastest, 
 
 Candidates are enumerated in ascending a; on exact FP64 ties the smallest a wins (documented tie rule).
 
-Index layout used by the kernels.  The state is a dense array over w bits ("slots"); live checks occupy slots
-0..w_in-1 in a fixed order, checks opened by the step take slots w_in.., closed slots are deleted from the index
-(higher slots shift down).  For an output index the kernel (1) re-inserts the closed bits with the shot's syndrome
-values -> `full`, (2) reads the opened part `pat = full >> w_in`, which pins a coset a0[pat] + ker of admissible
-candidates, (3) gathers S_in[(full ^ M[a]) & inmask] for a in that coset.  All tables are emitted here.
+Index layout used by the kernels.  The state is a dense array over w bits ("slots").  A step sees the FULL index:
+slots 0..w_in-1 = the live checks in the order the previous step left them, slots w_in.. = the checks it opens.  Its
+output index is any bit permutation of the surviving full slots (`perm[b]` = full slot of output bit b; closed slots
+are not in the image).  For an output index the kernel (1) scatters its bits to their full slots and ORs in the shot's
+syndrome values at the closed slots -> `full`, (2) reads the opened part `pat = full >> w_in`, which pins a coset
+a0[pat] + ker of admissible candidates, (3) gathers S_in[(full ^ M[a]) & inmask] for a in that coset.  All tables are
+emitted here; the permutation is chosen for the kernels (see the layout comment in `lower`).
 """
 from __future__ import annotations
 
@@ -70,6 +72,7 @@ class Step:
     w_out: int
     opened: List[int]
     closed: List[Tuple[int, int]]            # (slot in the full index, syndrome bit), ascending slot
+    perm: List[int]                          # perm[b] = slot in the full index of output bit b
     M: np.ndarray                            # (2^r,) masks in the full index space
     a0: np.ndarray                           # (2^n_open,) representative candidate per opened pattern, -1 = infeasible
     ker: np.ndarray                          # (nk,) kernel candidates, ascending
@@ -232,6 +235,12 @@ def _evaluate(order, sim):
     return wmax, cost
 
 
+def _score(wmax, cost, n_steps):
+    """Candidate evaluations per shot plus the per-step set-up a team pays once per pass (~290 candidate-equivalents,
+    measured on B200), shared by the 2^(10 - w_max) shots a team packs into one pass."""
+    return cost + 290.0 * n_steps / (1 << max(0, 10 - wmax))
+
+
 def _greedy_order(sim, start):
     nF = len(sim.factors)
     remaining = [len(fs) for fs in sim.c_factors]
@@ -276,7 +285,7 @@ def choose_order(factors, checks, max_starts=24):
     for s in starts[:max_starts]:
         cands.append(_greedy_order(sim, s))
     scored = [(_evaluate(o, sim), i) for i, o in enumerate(cands)]
-    (wmax, cost), i = min(scored, key=lambda x: (x[0][1], x[0][0], x[1]))
+    (wmax, cost), i = min(scored, key=lambda x: (_score(x[0][0], x[0][1], nF), x[0][0], x[1]))
     return cands[i]
 
 
@@ -299,23 +308,14 @@ def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_v
     sim = _Sim(factors, checks)
     remaining = [len(fs) for fs in sim.c_factors]
 
-    live: List[int] = []
-    steps: List[Step] = []
-    # checks with no variable at all: open (and, if clamped, close) at the first step so that a non-zero syndrome
-    # bit on them makes the shot infeasible, as the dense parity tensor would.
+    # pass 1: which checks every step touches / opens / closes (depends on the order only)
     orphan = [ci for ci, fs in enumerate(sim.c_factors) if not fs]
-    cost = 0.0
-    wmax = 0
+    plan = []
+    seen = set()
     for t, fi in enumerate(order):
-        f = factors[fi]
-        r = len(f.vars)
-        touched = list(sim.f_checks[fi])
-        if t == 0:
-            touched = touched + orphan
-        w_in = len(live)
-        opened = [c for c in touched if c not in live]
-        full = live + opened
-        pos = {c: k for k, c in enumerate(full)}
+        touched = list(sim.f_checks[fi]) + (orphan if t == 0 else [])
+        opened = [c for c in touched if c not in seen]
+        seen.update(opened)
         closing = []
         for c in touched:
             if c in orphan:
@@ -325,6 +325,24 @@ def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_v
             remaining[c] -= 1
             if remaining[c] == 0 and checks[c].kind == "syn":
                 closing.append(c)
+        plan.append((touched, opened, closing))
+
+    # pass 2: slot layout.  The output bit order of a step is free (the gather realises any bit permutation at no run
+    # time cost), so it is chosen for the kernels: the five low bits (the lane bits of a warp team) hold checks the
+    # next steps leave alone, the checks flipped by this step's kernel candidates sit right above them (both outputs of
+    # such a pair then belong to one thread), the checks the NEXT step closes sit above those (a closed bit among the
+    # four low bits of the input index would cost 2-way shared-memory bank conflicts), opened checks take the top.
+    live: List[int] = []
+    steps: List[Step] = []
+    cost = 0.0
+    wmax = 0
+    for t, fi in enumerate(order):
+        f = factors[fi]
+        r = len(f.vars)
+        touched, opened, closing = plan[t]
+        w_in = len(live)
+        full = live + opened
+        pos = {c: k for k, c in enumerate(full)}
         closed = sorted((pos[c], checks[c].index) for c in closing)
         m = []
         for v in f.vars:
@@ -343,14 +361,27 @@ def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_v
         for a in range((1 << r) - 1, -1, -1):
             a0[pat[a]] = a                                   # smallest a of each coset
         ker = np.flatnonzero(pat == 0).astype(np.int64)      # ascending, ker[0] = 0
-        live = [c for c in full if c not in closing]
+        kept_old = [c for c in live if c not in closing]
+        kmask = 0
+        for k in ker:
+            kmask |= int(M[k])
+        km = [c for c in kept_old if (kmask >> pos[c]) & 1]
+        nxt = set(plan[t + 1][2]) if t + 1 < len(order) else set()
+        cn = [c for c in kept_old if c in nxt and c not in km]
+        others = [c for c in kept_old if c not in km and c not in cn]
+        if len(others) >= 5:
+            out_old = others[:5] + km + cn + others[5:]
+        else:
+            out_old = others + cn + km
+        live = out_old + [c for c in opened if c not in closing]
+        perm = [pos[c] for c in live]
         w_out = len(live)
         if semiring == MAXPLUS:
             with np.errstate(divide="ignore"):
                 tab = np.log(f.table)
         else:
             tab = f.table.copy()
-        steps.append(Step(fi, tuple(f.vars), w_in, w_out, opened, closed, M, a0, ker, tab))
+        steps.append(Step(fi, tuple(f.vars), w_in, w_out, opened, closed, perm, M, a0, ker, tab))
         cost += float(1 << w_out) * len(ker)
         wmax = max(wmax, w_in, w_out)                        # the full index is never materialised
     if wmax > max_width:
@@ -400,6 +431,7 @@ def _encode(s: Schedule):
         h[H_OFF_CLOSE] = len(ints)
         for slot, bit in st.closed:
             ints += [int(slot), int(bit)]
+        ints += [int(x) for x in st.perm]                    # perm[w_out] follows the closed list
     s.hdr = hdr
     s.ints = np.asarray(ints if ints else [0], dtype=np.int32)
     s.tables = np.asarray(tabs if tabs else [0.0], dtype=np.float64)

@@ -161,7 +161,7 @@ def test_dem_lowering_vs_dense_and_bruteforce(tq):
 
 def test_schedule_cost_table(tq):
     """Frontier width / candidate evaluations per shot of the BASELINE configs (DESIGN.md quotes these)."""
-    expect = {3: (3, 104), 5: (5, 1208), 7: (8, 9528), 9: (10, 64824)}
+    expect = {3: (3, 104), 5: (5, 1208), 7: (8, 9976), 9: (10, 68600)}
     for d, (w, cost) in expect.items():
         t = tq.CSSTannerGraph(tq.SurfaceCode(d, d))
         gdp, _ = tq.reduce2general(t, tq.iid_error(0.05, t))
