@@ -275,9 +275,9 @@ def run_ours(args):
                 pass
         bytes_per_shot = 8 * (nsw + ncw + 1)
         hbm_achieved = bytes_per_shot * B / dur_s / 1e9
-        # DRAM traffic of the decode kernel per shot from the committed ncu capture (profiles/r1f_*: dram read + write over
+        # DRAM traffic of the decode kernel per shot from the committed ncu capture (profiles/r1j_*: dram read + write over
         # 6e5 shots); it is the back-pointer scratch streaming through HBM, the algorithmic I/O is 48 B per shot
-        traffic_per_shot = (5.767726e9 + 5.437252e9) / 6e5
+        traffic_per_shot = (2.518754e9 + 2.831403e9) / 6e5
         roofline = {"bound": "fp64", "achieved": achieved, "peak": peak["dadd_tops"], "unit": "TFLOP/s",
                     "frac": achieved / peak["dadd_tops"], "traffic": traffic_per_shot * B,
                     "kernel": "k_frontier_warp<maxplus>", "ops_per_shot": mul + add,
@@ -285,7 +285,7 @@ def run_ours(args):
                             "(frontier) schedule; max-plus has no tensor-core form",
                     "peak_source": "measured in this run by tqec_fp64_peak (register-resident DADD chains = the FP64 pipe's "
                                    "instruction rate; MEASURED_PEAKS.json has no FP64 entry)",
-                    "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per shot (profiles/r1f_ncu_frontier_v5_summary.csv) x shots per launch",
+                    "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per shot (profiles/r1j_ncu_frontier_v6_summary.csv) x shots per launch",
                     "fp64_peaks": peak,
                     "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                             "frac": hbm_achieved / hbm_peak, "bytes_per_shot": bytes_per_shot, "peak_source": hbm_src}}

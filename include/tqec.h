@@ -44,7 +44,7 @@ extern "C" {
 #define TQEC_SEMIRING_SUMPROD 1 /* TNMMAP: (+, *) on weights, open observable axes  */
 
 #define TQEC_HDR_INTS 16
-/* step header fields (int32 each) */
+/* step header fields (int32 each); entries 14 and 15 are reserved (the library overwrites them on its device copy) */
 enum {
   TQEC_H_R = 0,       /* number of variables of the absorbed factor                                  */
   TQEC_H_WIN = 1,     /* state width (bits) before the step                                          */
@@ -59,7 +59,10 @@ enum {
   TQEC_H_OFF_A0 = 10, /* ints[off + pat]           : variable assignment of the coset representative */
   TQEC_H_OFF_KER = 11,/* ints[off + k]             : variable assignment of kernel candidate k       */
   TQEC_H_OFF_VARS = 12,/* ints[off + j]            : id of the factor's j-th variable (output bit)    */
-  TQEC_H_OFF_CLOSE = 13/* ints[off + 2c], [off+2c+1]: (slot, syndrome bit) of closed check c, slots ascending */
+  TQEC_H_OFF_CLOSE = 13/* ints[off + 2c], [off+2c+1]: (full slot, syndrome bit) of closed check c; then, at
+                          ints[off + 2*n_close + b], b < w_out: perm[b] = full slot of output bit b.  The full index of a
+                          step has slots 0..w_in-1 = the input state bits and w_in.. = the opened checks; the output
+                          index is a bit permutation of the full slots that survive (closed slots are not in the image) */
 };
 
 typedef struct tqec_plan tqec_plan; /* a compiled schedule resident on one device      */

@@ -152,18 +152,23 @@ typedef struct {
   const int32_t *obs_slot;
 } frontier_plan;
 
-/* output index -> full index: bit b goes to slot perm[b] (perm follows the closed list), closed slots take the
- * shot's syndrome bits */
-static int rebuild_full(int tau, int w_out, int n_close, const int32_t *CL, const uint64_t *syn) {
-  const int32_t *perm = CL + 2 * n_close;
+/* output index -> full index: bit b goes to slot perm[b] (perm follows the closed list); the closed slots take the
+ * shot's syndrome bits.  The scatter of every output index is tabulated once per plan (it does not depend on the shot);
+ * the closed-bit values are computed once per step and shot. */
+static int scatter_of(int tau, int w_out, const int32_t *perm) {
   int full = 0;
   for (int b = 0; b < w_out; ++b) full |= ((tau >> b) & 1) << perm[b];
-  for (int c = 0; c < n_close; ++c) full |= bit_of(syn, CL[2 * c + 1]) << CL[2 * c];
   return full;
 }
 
-static double frontier_one(const frontier_plan *P, const uint64_t *syn, double *S0, double *S1, uint16_t *bp,
-                           uint64_t *cfg, double *mar) {
+static int closed_bits(int n_close, const int32_t *CL, const uint64_t *syn) {
+  int v = 0;
+  for (int c = 0; c < n_close; ++c) v |= bit_of(syn, CL[2 * c + 1]) << CL[2 * c];
+  return v;
+}
+
+static double frontier_one(const frontier_plan *P, const int32_t *const *scat, const uint64_t *syn, double *S0, double *S1,
+                           uint16_t *bp, uint64_t *cfg, double *mar) {
   const int maxplus = P->semiring == 0;
   double *Sin = S0, *Sout = S1;
   Sin[0] = maxplus ? 0.0 : 1.0;
@@ -174,9 +179,11 @@ static double frontier_one(const frontier_plan *P, const uint64_t *syn, double *
     const double *T = P->tables + h[H_OFF_T];
     const int32_t *ML = P->ints + h[H_OFF_ML], *MK = P->ints + h[H_OFF_MK], *CL = P->ints + h[H_OFF_CLOSE];
     const int inmask = (1 << w_in) - 1;
+    const int cbv = closed_bits(n_close, CL, syn);
+    const int32_t *sc = scat[t];
     uint16_t *bpt = bp ? bp + (size_t)t * stride : NULL;
     for (int tau = 0; tau < (1 << w_out); ++tau) {
-      const int full = rebuild_full(tau, w_out, n_close, CL, syn);
+      const int full = sc[tau] | cbv;
       const int pat = full >> w_in;
       const int low = (full & inmask) ^ ML[pat];
       const double *tb = T + pat * nk;
@@ -215,7 +222,7 @@ static double frontier_one(const frontier_plan *P, const uint64_t *syn, double *
       const int32_t *h = P->hdr + t * HDR_INTS;
       const int w_in = h[H_WIN], r = h[H_R];
       const int k = h[H_KB] ? bp[(size_t)t * stride + tau] : 0;
-      const int full = rebuild_full(tau, h[H_WOUT], h[H_NCLOSE], P->ints + h[H_OFF_CLOSE], syn);
+      const int full = scat[t][tau] | closed_bits(h[H_NCLOSE], P->ints + h[H_OFF_CLOSE], syn);
       const int pat = full >> w_in;
       const int a = P->ints[h[H_OFF_A0] + pat] ^ P->ints[h[H_OFF_KER] + k];
       for (int j = 0; j < r; ++j)
@@ -236,6 +243,18 @@ int oracle_frontier_run(const frontier_plan *P, const uint64_t *syn, int64_t B, 
   const size_t stride = (size_t)1 << P->w_max;
   const int NO = 1 << P->n_obs;
   int fail = 0;
+  /* per-plan scatter tables (shared, read-only) */
+  int32_t **scat = (int32_t **)calloc((size_t)P->n_steps, sizeof(int32_t *));
+  if (!scat) return 1;
+  for (int t = 0; t < P->n_steps; ++t) {
+    const int32_t *h = P->hdr + t * HDR_INTS;
+    const int w_out = h[H_WOUT];
+    const int32_t *perm = P->ints + h[H_OFF_CLOSE] + 2 * h[H_NCLOSE];
+    scat[t] = (int32_t *)malloc(sizeof(int32_t) * ((size_t)1 << w_out));
+    if (!scat[t]) { fail = 1; break; }
+    for (int tau = 0; tau < (1 << w_out); ++tau) scat[t][tau] = scatter_of(tau, w_out, perm);
+  }
+  if (fail) { for (int t = 0; t < P->n_steps; ++t) free(scat[t]); free(scat); return 1; }
 #ifdef _OPENMP
   if (n_threads > 0) omp_set_num_threads(n_threads);
 #endif
@@ -250,15 +269,17 @@ int oracle_frontier_run(const frontier_plan *P, const uint64_t *syn, int64_t B, 
 #pragma omp for schedule(static)
       for (int64_t b = 0; b < B; ++b) {
         if (P->semiring == 0) {
-          double lp = frontier_one(P, syn + b * sw, S0, S1, bp, cfg_out ? cfg_out + b * cw : NULL, NULL);
+          double lp = frontier_one(P, (const int32_t *const *)scat, syn + b * sw, S0, S1, bp, cfg_out ? cfg_out + b * cw : NULL, NULL);
           if (out) out[b] = lp;
         } else {
-          frontier_one(P, syn + b * sw, S0, S1, NULL, NULL, out + (size_t)b * NO);
+          frontier_one(P, (const int32_t *const *)scat, syn + b * sw, S0, S1, NULL, NULL, out + (size_t)b * NO);
         }
       }
     }
     free(S0); free(S1); free(bp);
   }
+  for (int t = 0; t < P->n_steps; ++t) free(scat[t]);
+  free(scat);
   return fail;
 }
 
