@@ -107,16 +107,18 @@ def main():
         print(json.dumps({"case": f"TNMMAP d={d} CSS", "shots": B, "ms": ms, "syndromes_per_s": B / (ms * 1e-3),
                           "geometry": ct.plan.geometry(), "w_max": ct.schedule.w_max, "candidates_per_shot": ct.schedule.cost}),
               file=out, flush=True)
-    # DEM TNMMAP on the reference's fixture (config 4 input format)
-    dem = tq.parse_dem_file(os.path.join(ROOT, "tests", "golden", "dem.dem"))
-    ct = tq.compile(tq.TNMMAP(), dem)
-    B = 1_000_000
-    ep = _cabi.sample_errors(_cabi.MODEL_FLIP, [np.asarray(dem.error_rates)], 3, 0, B)
-    syn = _cabi.GF2Matrix(ct.tanner.H).apply(ep)
-    ms = time_marginal(ct.plan, syn)
-    print(json.dumps({"case": "config4 DEM fixture TNMMAP (21 mechanisms, 6 detectors)", "shots": B, "ms": ms,
-                      "syndromes_per_s": B / (ms * 1e-3), "geometry": ct.plan.geometry(), "w_max": ct.schedule.w_max}),
-          file=out, flush=True)
+    # DEM TNMMAP (config 4 input format): the reference's fixture + synthetic surface-memory DEMs (benchmarks/make_dem.py)
+    for fname, label, B in (("dem.dem", "reference DEM fixture (21 mechanisms, 6 detectors)", 1_000_000),
+                            ("surface_d3_r3_phenom.dem", "surface memory d=3 x 3 rounds, phenomenological", 1_000_000),
+                            ("surface_d5_r5_phenom.dem", "surface memory d=5 x 5 rounds, phenomenological", 200_000)):
+        dem = tq.parse_dem_file(os.path.join(ROOT, "tests", "golden", fname))
+        ct = tq.compile(tq.TNMMAP(), dem)
+        ep = _cabi.sample_errors(_cabi.MODEL_FLIP, [np.asarray(dem.error_rates)], 3, 0, B)
+        syn = _cabi.GF2Matrix(ct.tanner.H).apply(ep)
+        ms = time_marginal(ct.plan, syn)
+        print(json.dumps({"case": f"config4 DEM TNMMAP: {label}", "shots": B, "ms": ms, "syndromes_per_s": B / (ms * 1e-3),
+                          "geometry": ct.plan.geometry(), "w_max": ct.schedule.w_max,
+                          "candidates_per_shot": ct.schedule.cost}), file=out, flush=True)
 
 
 if __name__ == "__main__":

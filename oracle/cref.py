@@ -191,4 +191,4 @@ class FrontierPlan:
         out = np.zeros((B, 1 << sch.n_obs))
         rc = lib().oracle_frontier_run(C.byref(self.c), _p(words), B, None, _p(out), threads)
         assert rc == 0
-        return out
+        return np.ldexp(out, getattr(sch, "log2_scale", 0))

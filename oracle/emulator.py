@@ -63,7 +63,7 @@ def run(sch, syndromes):
         src = np.zeros_like(idx)
         for i, s in enumerate(sch.obs_slot):
             src |= ((idx >> i) & 1) << s
-        return S[:, src]
+        return np.ldexp(S[:, src], getattr(sch, 'log2_scale', 0))
     logp = S[:, 0]
     config = np.zeros((B, sch.n_vars), dtype=np.uint8)
     tau = np.zeros(B, dtype=np.int64)

@@ -168,6 +168,8 @@ class Plan:
         mar = np.zeros((B, 1 << self.sch.n_obs), dtype=np.float64)
         arg = np.zeros(B, dtype=np.int32)
         check(lib().tqec_decode_marginal(self.h, _ptr(s), B, _ptr(mar), _ptr(arg)))
+        if self.sch.log2_scale:
+            mar = np.ldexp(mar, self.sch.log2_scale)       # undo the static power-of-two scaling of the factor tables
         return mar, arg
 
     def decode_marginal_dev(self, d_synd: int, B: int, d_mar: int, d_argmax: int = 0, stream: int = 0):

@@ -92,6 +92,7 @@ class Schedule:
     checks: List[Check]
     w_max: int = 0
     cost: float = 0.0                        # sum_t 2^w_out * nk  = candidate evaluations per shot
+    log2_scale: int = 0                      # sum-product: the emitted tables are the factors times 2^-e_f; sum of e_f
     # flat encoding for the C-ABI
     hdr: Optional[np.ndarray] = None
     ints: Optional[np.ndarray] = None
@@ -336,6 +337,7 @@ def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_v
     steps: List[Step] = []
     cost = 0.0
     wmax = 0
+    log2_scale = 0
     for t, fi in enumerate(order):
         f = factors[fi]
         r = len(f.vars)
@@ -380,7 +382,14 @@ def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_v
             with np.errstate(divide="ignore"):
                 tab = np.log(f.table)
         else:
+            # static per-step scaling against underflow: every factor is normalised by the power of two below its
+            # largest entry (exact in FP64), the exponents are summed and re-applied by the host after the decode
             tab = f.table.copy()
+            mx = float(tab.max())
+            if mx > 0.0:
+                e = int(np.floor(np.log2(mx)))
+                tab = np.ldexp(tab, -e)
+                log2_scale += e
         steps.append(Step(fi, tuple(f.vars), w_in, w_out, opened, closed, perm, M, a0, ker, tab))
         cost += float(1 << w_out) * len(ker)
         wmax = max(wmax, w_in, w_out)                        # the full index is never materialised
@@ -394,7 +403,7 @@ def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_v
         obs_slot[checks[c].index] = k
     if any(s < 0 for s in obs_slot) or len(live) != n_obs:
         raise ValueError("every observable row must be declared exactly once")
-    sch = Schedule(semiring, n_vars, n_checks, n_obs, steps, obs_slot, order, factors, list(checks), wmax, cost)
+    sch = Schedule(semiring, n_vars, n_checks, n_obs, steps, obs_slot, order, factors, list(checks), wmax, cost, log2_scale)
     _encode(sch)
     return sch
 

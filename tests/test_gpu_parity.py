@@ -260,6 +260,33 @@ def test_dem_tnmmap(tq):
         assert np.allclose(res.marginal[:64].reshape(64, -1), ref, rtol=MAR_RTOL, atol=0)
 
 
+@pytest.mark.parametrize("name,n_dense", [("surface_d3_r3_phenom.dem", 64), ("surface_d5_r5_phenom.dem", 0)])
+def test_dem_surface_memory(tq, name, n_dense):
+    """BASELINE configs[3] shape: surface-code memory DEMs (phenomenological, generated by benchmarks/make_dem.py because
+    stim is not available).  d=5 x 5 rounds has an 11-bit frontier and runs on the CTA-team kernel."""
+    import os
+    dem = tq.parse_dem_file(os.path.join(os.path.dirname(__file__), "golden", name))
+    ct = tq.compile(tq.TNMMAP(), dem)
+    B = 512
+    ep = tq.random_error_pattern(dem, seed=4, shots=B)
+    syn = tq.syndrome_extraction(ep, ct.tanner)
+    res = tq.decode(ct, syn)
+    assert syn == tq.syndrome_extraction(res.error_pattern, ct.tanner)
+    sch = ct.schedule
+    ref = cref.FrontierPlan(sch).run(syn.s)
+    got = res.marginal.reshape(B, -1, order="F")
+    assert np.allclose(got, ref, rtol=MAR_RTOL, atol=0)
+    ref2 = frontier.run(sch.factors, sch.checks, sch.order, 1, syn.s[:8], sch.n_vars)
+    assert np.allclose(got[:8], ref2, rtol=MAR_RTOL, atol=0)
+    if n_dense:
+        net = networks.tnmmap_dem_network(dem.error_rates, dem.flipped_detectors, dem.n_detectors, 1, factorize=True)
+        dref = cref.DensePlan(net, dem.n_detectors, len(dem.error_rates), False).run(syn.s[:n_dense])
+        assert np.allclose(got[:n_dense], dref, rtol=MAR_RTOL, atol=0)
+    # the decoded observable agrees with the true one far more often than not at p = 1 %
+    true_obs = (ep[:, ct.l2q[0]].sum(axis=1) & 1)
+    assert (res.sector == true_obs).mean() > 0.9
+
+
 def test_property_full_size_d9(tq):
     """BASELINE config 3 shape (d=9, p=0.05) at a size the oracle cannot follow shot by shot: size-independent
     properties -- every correction reproduces its syndrome, decoding is idempotent on its own output's syndrome,
@@ -294,3 +321,53 @@ def test_error_behaviour(tq):
         tq.compile(tq.TNMAP(device=99), t)
     empty = tq.decode(ct, tq.CSSSyndrome(np.zeros((0, 4), dtype=np.uint8), np.zeros((0, 4), dtype=np.uint8)))
     assert empty.error_pattern.xerror.shape == (0, 9)
+
+
+def test_cabi_error_codes_and_queries(tq):
+    """The raw C ABI: error codes + messages on misuse, plan queries, device-pointer entry points."""
+    import ctypes as C
+    import torch
+    from tensorqec.jl_b200 import _cabi
+    lib = _cabi.lib()
+    t = tq.CSSTannerGraph(tq.SurfaceCode(3, 3))
+    ct = tq.compile(tq.TNMAP(), t)
+    plan = ct.cd.plan
+    # wrong semiring for the entry point
+    out = np.zeros(4)
+    rc = lib.tqec_decode_marginal(plan.h, out.ctypes.data_as(C.c_void_p), 1, out.ctypes.data_as(C.c_void_p), None)
+    assert rc == -1 and b"sum-product" in lib.tqec_last_error()
+    # NULL buffers
+    assert lib.tqec_decode_map(plan.h, None, 5, None, None) == -1
+    assert lib.tqec_decode_map(plan.h, None, 0, None, None) == 0          # empty batch is fine
+    # malformed schedule: widths that do not chain
+    sch = ct.cd.schedule
+    bad = sch.hdr.copy()
+    bad[1, 1] += 1
+    hdr = np.ascontiguousarray(bad, dtype=np.int32)
+    ints = np.ascontiguousarray(sch.ints, dtype=np.int32)
+    tabs = np.ascontiguousarray(sch.tables, dtype=np.float64)
+    obs = np.zeros(1, dtype=np.int32)
+    d = _cabi.PlanDesc(0, sch.n_vars, sch.n_checks, 0, len(sch.steps), sch.w_max, hdr.ctypes.data_as(C.POINTER(C.c_int32)),
+                       ints.ctypes.data_as(C.POINTER(C.c_int32)), ints.size, tabs.ctypes.data_as(C.POINTER(C.c_double)), tabs.size,
+                       obs.ctypes.data_as(C.POINTER(C.c_int32)), 0)
+    h = C.c_void_p()
+    assert lib.tqec_plan_create(C.byref(d), C.byref(h)) == -1 and not h.value
+    assert b"w_in" in lib.tqec_last_error()
+    # queries
+    g = plan.geometry()
+    assert g["team_threads"] == 32 and g["sm_count"] >= 100 and g["candidates_per_shot"] == 104
+    n0 = plan.query(_cabi.Q_LAUNCHES)
+    # device-pointer entry point on torch memory, asynchronous on the current stream
+    syn = ((np.arange(256)[:, None] >> np.arange(8)) & 1).astype(np.uint8)
+    words = tq.pack_bits(syn)
+    d_syn = torch.from_numpy(words.view(np.int64)).cuda()
+    d_cor = torch.zeros((256, plan.ncw), dtype=torch.int64, device="cuda")
+    d_lp = torch.zeros(256, dtype=torch.float64, device="cuda")
+    plan.decode_map_dev(d_syn.data_ptr(), 256, d_cor.data_ptr(), d_lp.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    corr, lp = plan.decode_map(words)
+    assert np.array_equal(d_cor.cpu().numpy().view(np.uint64), corr) and np.array_equal(d_lp.cpu().numpy(), lp)
+    assert plan.query(_cabi.Q_LAUNCHES) == n0 + 2
+    # GF(2) shape errors surface as Python exceptions before the ABI is reached
+    with pytest.raises(ValueError):
+        tq.syndrome_extraction(np.zeros(5, dtype=np.uint8), t.stgz)
