@@ -31,10 +31,6 @@ struct Tabs {
   const double *tables;
 };
 
-__device__ __forceinline__ int insert_bit(int x, int slot, int bit) {
-  return ((x >> slot) << (slot + 1)) | (bit << slot) | (x & ((1 << slot) - 1));
-}
-
 // full index of an output index: bit b goes to full slot perm[b] (perm[w_out] follows the closed list); the shot's
 // closed-bit values (precomputed once per shot and step in `cb`, already at their slots) are OR-ed in by the caller.
 template <bool SM>
