@@ -2,16 +2,15 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import tensorqec.jl_b200 as tq
+from oracle import cref
 t = tq.CSSTannerGraph(tq.SurfaceCode(3, 3))
-for name, prob in (("classical", t.stgz), ("css", t)):
-    try:
-        ct = tq.compile(tq.TNMAP(), prob)
-        plan = ct.plan if hasattr(ct, "plan") else ct.cd.plan
-        print(name, plan.geometry(), plan.sch.w_max, len(plan.sch.steps))
-        if name == "classical":
-            syn = tq.SimpleSyndrome(np.zeros((5, 4), dtype=np.uint8))
-        else:
-            syn = tq.CSSSyndrome(np.zeros((5, 4), dtype=np.uint8), np.zeros((5, 4), dtype=np.uint8))
-        print(tq.decode(ct, syn).logp)
-    except Exception as e:
-        print(name, "ERR", e)
+ct = tq.compile(tq.TNMAP(), t)
+plan = ct.cd.plan
+sch = plan.sch
+print(plan.geometry(), [(s.w_in, s.w_out, len(s.opened), len(s.closed), len(s.ker)) for s in sch.steps])
+syn = ((np.arange(64)[:, None] >> np.arange(8)) & 1).astype(np.uint8)
+corr, lp = plan.decode_map(tq.pack_bits(syn))
+lp2, cfg2 = cref.FrontierPlan(sch).run(syn)
+print("logp equal:", np.array_equal(lp, lp2), " cfg equal:", np.array_equal(tq.unpack_bits(corr, 18), cfg2))
+bad = np.flatnonzero(lp != lp2)
+print("bad shots", bad[:20], lp[bad[:6]], lp2[bad[:6]])

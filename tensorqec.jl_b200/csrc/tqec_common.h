@@ -49,6 +49,7 @@ struct PlanDev {
   int32_t nsw, ncw;        // syndrome / configuration words per shot
   int32_t bp_words;        // back-pointer words per team
   int32_t n_ints, n_tables; // pool sizes (for the shared-memory copies of warp teams)
+  int32_t sub_minor;       // 1: state entry sigma of shot s at (sigma << sg) | s ("shot in lane"), else (s << w) | sigma
   int32_t defer;           // 1: warp teams run 32 forward sweeps, then trace 32 shots in parallel (one lane each)
   int32_t off_states, off_ints, off_tables, off_words;  // warp-team shared-memory layout (bytes from the dynamic array)
 };

@@ -64,19 +64,22 @@ __device__ __forceinline__ void run_step(const PlanDev &P, const Tabs &X, const 
   if (tid < (1 << wl)) gtab[tid] = (uint32_t)scatter_bits<SM>(tid, wl, perm);
   if (T == 32) __syncwarp(); else __syncthreads();
   for (int e = tid; e < n_tot; e += T) {
-    const int tau = e & outmask, sub = e >> w_out;
+    const int tau = P.sub_minor ? e >> P.sg_log2 : e & outmask;
+    const int sub = P.sub_minor ? e & ((1 << P.sg_log2) - 1) : e >> w_out;
     int full = (int)gtab[tau & 31] | cbt[sub];
     for (int b = 5; b < w_out; ++b) full |= ((tau >> b) & 1) << ldi<SM>(perm + b);
     const int pat = full >> w_in;
     const int low = (full & inmask) ^ ldi<SM>(ML + pat);
     const double *__restrict__ tb = Tt + pat * nk;
-    const double *__restrict__ Sb = Sin + (sub << w_in);
-    const double s0 = Sb[low ^ ldi<SM>(MK)], t0 = ldd<SM>(tb);
+    // state entry sigma of shot sub lives at (sub << w) | sigma, or at (sigma << sg) | sub in the shot-minor layout
+    const int sh = P.sub_minor ? P.sg_log2 : 0;
+    const double *__restrict__ Sb = Sin + (P.sub_minor ? sub : (sub << w_in));
+    const double s0 = Sb[(low ^ ldi<SM>(MK)) << sh], t0 = ldd<SM>(tb);
     double best = SEMI == TQEC_SEMIRING_MAXPLUS ? s0 + t0 : s0 * t0;
     int bk = 0;
 #pragma unroll
     for (int k = 1; k < (NK > 0 ? NK : nk); ++k) {
-      const double s = Sb[low ^ ldi<SM>(MK + k)], tv = ldd<SM>(tb + k);
+      const double s = Sb[(low ^ ldi<SM>(MK + k)) << sh], tv = ldd<SM>(tb + k);
       if (SEMI == TQEC_SEMIRING_MAXPLUS) {
         const double v = s + tv;
         if (v > best) { best = v; bk = k; }      // strict: the smallest candidate wins exact ties
@@ -252,6 +255,62 @@ __device__ __forceinline__ void fast_step(const PlanDev &P, const Tabs &X, const
   else fast_blocks<SEMI, NK, 1, 0>(f0.w, rec, pl8, so, dl, gtab, bpt, tid);
 }
 
+// ---- fast step, shot-minor layout ("shot in lane": plans with w_max <= 5 pack 32 shots per team, lane = shot) ---------------
+// The state of shot `lane` sits at ((sigma << 5) | lane) * 8, so every lane walks ALL output indices tau of its own shot:
+// the index arithmetic is uniform across the warp (host-precomputed per step: UK[tau][k] = source index << 8 and the
+// factor value TV[tau][k]), the only per-lane term is the shot's closed-bit value, bank conflicts cannot occur, and a
+// candidate costs LOP3 + LDS.64 + DADD plus a share of two broadcast table loads.
+template <int SEMI, int NK>
+__device__ __forceinline__ void fast_step_b(const int32_t *__restrict__ brec, const int32_t *__restrict__ ints,
+                                            const double *__restrict__ tables, uint32_t sin_abs, uint32_t sout_abs,
+                                            int cbv, int w_in, uint32_t *__restrict__ bpt, int lane) {
+  constexpr int KB = NK == 1 ? 0 : (NK == 2 ? 1 : 2);
+  const int4 b0 = *reinterpret_cast<const int4 *>(brec);          // n_tau, off_uk, off_tv, -
+  const int n_tau = b0.x;
+  const int32_t *__restrict__ UK = ints + b0.y;
+  const double *__restrict__ TV = tables + b0.z;
+  const uint32_t lc = sin_abs ^ (uint32_t)(lane << 3) ^ (uint32_t)((cbv & ((1 << w_in) - 1)) << 8);
+  const uint32_t so = sout_abs + (lane << 3);
+  uint32_t word = 0;
+  int pos = 0, wi = 0;
+#pragma unroll 4
+  for (int tau = 0; tau < n_tau; ++tau) {
+    double v[NK];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) v[k] = lds_f64(lc ^ (uint32_t)UK[tau * NK + k]);
+#pragma unroll
+    for (int k = 0; k < NK; ++k) v[k] = SEMI == TQEC_SEMIRING_MAXPLUS ? v[k] + TV[tau * NK + k] : v[k] * TV[tau * NK + k];
+    double best;
+    uint32_t bk = 0;
+    if (SEMI == TQEC_SEMIRING_MAXPLUS) {
+      if (NK == 1) {
+        best = v[0];
+      } else if (NK == 2) {
+        const bool p = v[1] > v[0];
+        best = p ? v[1] : v[0];
+        bk = p;
+      } else {
+        const bool p01 = v[1] > v[0], p23 = v[3 % NK] > v[2 % NK];
+        const double b01 = p01 ? v[1] : v[0], b23 = p23 ? v[3 % NK] : v[2 % NK];
+        const bool pf = b23 > b01;
+        best = pf ? b23 : b01;
+        bk = pf ? (2u | (uint32_t)p23) : (uint32_t)p01;
+      }
+    } else {
+      best = v[0];
+#pragma unroll
+      for (int k = 1; k < NK; ++k) best += v[k];
+    }
+    sts_f64(so + (tau << 8), best);
+    if (SEMI == TQEC_SEMIRING_MAXPLUS && KB) {
+      word |= bk << pos;
+      pos += KB;
+      if (pos == 32) { bpt[wi * 32 + lane] = word; word = 0; pos = 0; ++wi; }
+    }
+  }
+  if (SEMI == TQEC_SEMIRING_MAXPLUS && KB && pos) bpt[wi * 32 + lane] = word;
+}
+
 // ---- one traceback step (shared by both traceback shapes): returns the previous state index and the factor's bits ------
 template <bool SM>
 __device__ __forceinline__ int trace_step(const Tabs &X, const int32_t *__restrict__ h, int tau, int cbv, int k, int &a_out) {
@@ -300,7 +359,13 @@ __device__ __forceinline__ double *forward_pass(const PlanDev &P, const Tabs &X,
     const int nk = ldi<SM>(h + TQEC_H_NK);
     const int fo = WT ? ldi<SM>(h + TQEC_H_FAST) : 0;
     const int32_t *cbt = cb + (t << P.sg_log2);
-    if (WT && fo) {
+    if (WT && fo && P.sub_minor) {
+      const int32_t *brec = X.ints + (fo - 1);
+      const int w_in = ldi<SM>(h + TQEC_H_WIN);
+      if (nk == 2) fast_step_b<SEMI, 2>(brec, X.ints, X.tables, sin_abs, sout_abs, cbt[tid], w_in, bpt, tid);
+      else if (nk == 1) fast_step_b<SEMI, 1>(brec, X.ints, X.tables, sin_abs, sout_abs, cbt[tid], w_in, bpt, tid);
+      else fast_step_b<SEMI, 4>(brec, X.ints, X.tables, sin_abs, sout_abs, cbt[tid], w_in, bpt, tid);
+    } else if (WT && fo) {
       const int32_t *frec = X.ints + (fo - 1);
       if (nk == 2) fast_step<SEMI, 2, SM>(P, X, h, frec, sin_abs, sout_abs, gtab, cbt, bpt, tid);
       else if (nk == 1) fast_step<SEMI, 1, SM>(P, X, h, frec, sin_abs, sout_abs, gtab, cbt, bpt, tid);
@@ -381,7 +446,7 @@ __device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, unsign
         int k = 0;
         if (kb) {
           int word, sh;
-          bp_locate((sub << q1.x) | tau, 5, 32, kb, word, sh);
+          bp_locate(P.sub_minor ? ((tau << P.sg_log2) | sub) : ((sub << q1.x) | tau), 5, 32, kb, word, sh);
           k = (__ldcg(bpq + ldi<SM>(X.bp_off + t) + word) >> sh) & ((1u << kb) - 1u);
         }
         const int32_t *CL = X.ints + q3.y;
@@ -435,7 +500,7 @@ __device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, unsign
           int k = 0;
           if (kb) {
             int word, sh;
-            bp_locate((sub << ldi<SM>(h + TQEC_H_WOUT)) | tau, LT, T, kb, word, sh);
+            bp_locate(P.sub_minor ? ((tau << P.sg_log2) | sub) : ((sub << ldi<SM>(h + TQEC_H_WOUT)) | tau), LT, T, kb, word, sh);
             k = (__ldcg(bp + ldi<SM>(X.bp_off + t) + word) >> sh) & ((1u << kb) - 1u);
           }
           int a;
@@ -458,7 +523,7 @@ __device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, unsign
         const int sub = i >> P.n_obs, idx = i & (NO - 1);
         int src = 0;
         for (int o = 0; o < P.n_obs; ++o) src |= ((idx >> o) & 1) << ldi<SM>(X.obs_slot + o);
-        if (shot0 + sub < B) out[(shot0 + sub) * NO + idx] = Sin[(sub << P.n_obs) | src];
+        if (shot0 + sub < B) out[(shot0 + sub) * NO + idx] = Sin[P.sub_minor ? ((src << P.sg_log2) | sub) : ((sub << P.n_obs) | src)];
       }
       if (argmax_out) {
         for (int sub = tid; sub < SG; sub += T) {
@@ -468,7 +533,7 @@ __device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, unsign
           for (int idx = 0; idx < NO; ++idx) {             // first maximal entry (findmax)
             int src = 0;
             for (int o = 0; o < P.n_obs; ++o) src |= ((idx >> o) & 1) << ldi<SM>(X.obs_slot + o);
-            const double v = Sin[(sub << P.n_obs) | src];
+            const double v = Sin[P.sub_minor ? ((src << P.sg_log2) | sub) : ((sub << P.n_obs) | src)];
             if (v > best) { best = v; bi = idx; }
           }
           argmax_out[shot0 + sub] = bi;
@@ -579,7 +644,7 @@ using namespace tqec;
 //                          packed two per double.  A step is fast iff the element index splits into lane bits and j
 //                          bits (see fast_step): 32-thread teams, <= 32 elements per thread, every closed slot below
 //                          w_in, the opened pattern determined by j alone, nk in {1, 2, 4}.
-static void build_device_tables(const tqec_plan_desc *d, int sg, bool want_fast, std::vector<int32_t> &hdr,
+static void build_device_tables(const tqec_plan_desc *d, int sg, bool want_fast, bool sub_minor, std::vector<int32_t> &hdr,
                                 std::vector<int32_t> &ints, std::vector<double> &tables) {
   hdr.assign(d->hdr, d->hdr + (size_t)d->n_steps * TQEC_HDR_INTS);
   ints.assign(d->ints, d->ints + d->n_ints);
@@ -597,6 +662,30 @@ static void build_device_tables(const tqec_plan_desc *d, int sg, bool want_fast,
     for (int pp = 0; pp < np; ++pp)
       for (int k = 0; k < nk; ++k) { ints.push_back(A0[pp] ^ KER[k]); ints.push_back(ML[pp] ^ MK[k]); }
     h[TQEC_H_FAST] = 0;
+    if (sub_minor) {
+      // shot-minor fast step (fast_step_b): uniform per-tau tables; needs nk in {1,2,4} and an opened pattern that does
+      // not depend on the shot (no closed slot among the opened slots)
+      bool okb = want_fast && (nk == 1 || nk == 2 || nk == 4) && w_out <= 5;
+      for (int c = 0; c < n_close && okb; ++c) if (d->ints[h[TQEC_H_OFF_CLOSE] + 2 * c] >= w_in) okb = false;
+      if (!okb) continue;
+      const int inmask_b = (1 << w_in) - 1;
+      const double *Tb = d->tables + h[TQEC_H_OFF_T];
+      while (ints.size() & 3) ints.push_back(0);
+      const size_t rec_at = ints.size();
+      ints.push_back(1 << w_out); ints.push_back(0); ints.push_back((int32_t)tables.size()); ints.push_back(0);
+      ints[rec_at + 1] = (int32_t)ints.size();
+      for (int tau = 0; tau < (1 << w_out); ++tau) {
+        int full = 0;
+        for (int b = 0; b < w_out; ++b) full |= ((tau >> b) & 1) << perm[b];
+        const int pat = full >> w_in;
+        for (int k = 0; k < nk; ++k) {
+          ints.push_back((int32_t)((uint32_t)(((full & inmask_b) ^ ML[pat] ^ MK[k])) << 8));
+          tables.push_back(Tb[pat * nk + k]);
+        }
+      }
+      h[TQEC_H_FAST] = (int32_t)rec_at + 1;
+      continue;
+    }
     const int lgJ = w_out + sg - LT, lg_jj = w_out - LT - n_open;
     bool ok = want_fast && lgJ >= 0 && lgJ <= 5 && lg_jj >= 0 && (nk == 1 || nk == 2 || nk == 4);
     // lane bits must land inside the input state; the opened slots must be the top output bits, in order
@@ -724,6 +813,9 @@ extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
   if (const char *e = std::getenv("TQEC_TARGET_BITS")) { const int v = std::atoi(e); if (v >= 5 && v <= 10) target_bits = v; }
   int sg = d->w_max < target_bits ? target_bits - d->w_max : 0;
   if (sg > 6) sg = 6;
+  // narrow plans (w_max <= 5): 32 shots per team in the shot-minor layout (lane = shot), see fast_step_b
+  const bool narrow = d->w_max <= 5 && std::getenv("TQEC_NO_SUB_MINOR") == nullptr && std::getenv("TQEC_NO_WARP_TEAMS") == nullptr;
+  if (narrow) sg = 5;
   const int tot_bits = d->w_max + sg;
   int T = 32;
   if (tot_bits > 10) T = 1 << (tot_bits - 5 > 8 ? 8 : tot_bits - 5);
@@ -733,7 +825,7 @@ extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
   // device tables: the ABI pools plus, per step, the traceback (assignment, mask) pairs and the fast-step records
   std::vector<int32_t> hdr, ints;
   std::vector<double> tables;
-  build_device_tables(d, sg, want_warp && std::getenv("TQEC_NO_FAST") == nullptr, hdr, ints, tables);
+  build_device_tables(d, sg, want_warp && std::getenv("TQEC_NO_FAST") == nullptr, narrow && want_warp, hdr, ints, tables);
 
   const size_t per_team = team_smem_bytes(d->w_max, sg, nsw, ncw, d->n_steps);
   const size_t budget = (size_t)prop.sharedMemPerBlockOptin;
@@ -819,6 +911,7 @@ extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
   D.n_steps = d->n_steps; D.n_vars = d->n_vars; D.n_checks = d->n_checks; D.n_obs = d->n_obs;
   D.w_max = d->w_max; D.sg_log2 = sg; D.nsw = nsw; D.ncw = ncw; D.bp_words = bp_off[d->n_steps];
   D.n_ints = (int32_t)ints.size(); D.n_tables = (int32_t)tables.size();
+  D.sub_minor = (narrow && p->warp_teams) ? 1 : 0;
   D.defer = (p->warp_teams && d->semiring == TQEC_SEMIRING_MAXPLUS && nsw <= 4 && ncw <= 4 && sg <= 5 &&
              std::getenv("TQEC_NO_DEFER") == nullptr) ? 1 : 0;
   D.off_states = (int32_t)off_states; D.off_ints = (int32_t)off_ints; D.off_tables = (int32_t)off_tables; D.off_words = (int32_t)off_words;
