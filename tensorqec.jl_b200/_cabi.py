@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtqec_cuda.so")
+LIB_PATH = os.environ.get("TQEC_CUDA_LIB", os.path.join(_HERE, "libtqec_cuda.so"))
 
 OK = 0
 MODEL_FLIP, MODEL_DEPOL = 0, 1

@@ -63,6 +63,7 @@ struct tqec_plan {
   int team_threads;
   int warp_teams;        // 1: k_frontier_warp (a team is a warp, tables in shared memory); 0: k_frontier_cta
   int teams_per_cta;
+  int layout;            // warp-team index layout: 0 standard, 1 wide (64 / 128 entries per thread), 2 shot-minor
   int shots_per_team;
   int smem_bytes;
   int grid_max;          // persistent grid size (teams resident on the whole GPU)

@@ -41,7 +41,8 @@ __device__ __forceinline__ int scatter_bits(int tau, int w_out, const int32_t *_
 }
 
 // ---- generic step: any geometry, per-element index arithmetic ------------------------------------------------------
-template <int SEMI, int NK, bool SM>
+// LY = index layout of the plan: 0 standard (<= 32 entries per thread), 1 wide (64 / 128 entries per thread), 2 shot-minor
+template <int SEMI, int NK, bool SM, int LY>
 __device__ __forceinline__ void run_step(const PlanDev &P, const Tabs &X, const int32_t *__restrict__ h,
                                          const double *__restrict__ Sin, double *__restrict__ Sout,
                                          const int32_t *__restrict__ cbt, uint32_t *__restrict__ gtab,
@@ -64,16 +65,16 @@ __device__ __forceinline__ void run_step(const PlanDev &P, const Tabs &X, const 
   if (tid < (1 << wl)) gtab[tid] = (uint32_t)scatter_bits<SM>(tid, wl, perm);
   if (T == 32) __syncwarp(); else __syncthreads();
   for (int e = tid; e < n_tot; e += T) {
-    const int tau = P.sub_minor ? e >> P.sg_log2 : e & outmask;
-    const int sub = P.sub_minor ? e & ((1 << P.sg_log2) - 1) : e >> w_out;
+    const int tau = LY == 2 ? e >> P.sg_log2 : e & outmask;
+    const int sub = LY == 2 ? e & ((1 << P.sg_log2) - 1) : e >> w_out;
     int full = (int)gtab[tau & 31] | cbt[sub];
     for (int b = 5; b < w_out; ++b) full |= ((tau >> b) & 1) << ldi<SM>(perm + b);
     const int pat = full >> w_in;
     const int low = (full & inmask) ^ ldi<SM>(ML + pat);
     const double *__restrict__ tb = Tt + pat * nk;
     // state entry sigma of shot sub lives at (sub << w) | sigma, or at (sigma << sg) | sub in the shot-minor layout
-    const int sh = P.sub_minor ? P.sg_log2 : 0;
-    const double *__restrict__ Sb = Sin + (P.sub_minor ? sub : (sub << w_in));
+    const int sh = LY == 2 ? P.sg_log2 : 0;
+    const double *__restrict__ Sb = Sin + (LY == 2 ? sub : (sub << w_in));
     const double s0 = Sb[(low ^ ldi<SM>(MK)) << sh], t0 = ldd<SM>(tb);
     double best = SEMI == TQEC_SEMIRING_MAXPLUS ? s0 + t0 : s0 * t0;
     int bk = 0;
@@ -210,7 +211,7 @@ __device__ __forceinline__ void fast_blocks(int nblk, const double *__restrict__
 // state's base address (a multiple of the state size, so XOR is enough) and keeps the j-dependent part in a 32-entry
 // per-team table (one broadcast LDS per block).  A candidate then costs LOP3 + LDS.64 + DADD (+ DSETP + 2 FSEL beyond
 // the first).  `sin_abs` / `sout_abs` are absolute shared addresses of the ping-pong states.
-template <int SEMI, int NK, bool SM>
+template <int SEMI, int NK, bool SM, int LY>
 __device__ __forceinline__ void fast_step(const PlanDev &P, const Tabs &X, const int32_t *__restrict__ h,
                                           const int32_t *__restrict__ frec, uint32_t sin_abs, uint32_t sout_abs,
                                           uint32_t *__restrict__ gtab, const int32_t *__restrict__ cbt,
@@ -221,22 +222,36 @@ __device__ __forceinline__ void fast_step(const PlanDev &P, const Tabs &X, const
   const int4 f1 = *reinterpret_cast<const int4 *>(frec + 4);     // U, off_blk, cj, -
   const int4 f2 = *reinterpret_cast<const int4 *>(frec + 8);     // full slots of output bits 0..3
   const int4 f3 = *reinterpret_cast<const int4 *>(frec + 12);    // full slot of output bit 4, then bits 5..7
-  const int4 f4 = *reinterpret_cast<const int4 *>(frec + 16);    // full slots of output bits 8, 9 (unused: -1 -> shift by 31 of a 0 bit)
+  const int4 f4 = *reinterpret_cast<const int4 *>(frec + 16);    // full slots of output bits 8..11 (10, 11: wide states)
   const int lane = tid;
   const int inmask = (1 << w_in) - 1;
   // lane part: output bits 0..4 are lane bits
   const int pl = ((lane & 1) << f2.x) | (((lane >> 1) & 1) << f2.y) | (((lane >> 2) & 1) << f2.z) |
                  (((lane >> 3) & 1) << f2.w) | (((lane >> 4) & 1) << f3.x);
-  // j part of lane's own j (= lane): output bits 5..9 are j bits 0..4 (bits beyond w_out select the shot)
+  // j part: output bits 5.. are j bits 0.. (bits beyond w_out select the shot); lane l fills entries l, l+32, ..
   const int nj = w_out - 5;                                      // state bits among the j bits
-  int gfull = 0;
-  if (nj > 0) gfull |= (lane & 1) << f3.y;
-  if (nj > 1) gfull |= ((lane >> 1) & 1) << f3.z;
-  if (nj > 2) gfull |= ((lane >> 2) & 1) << f3.w;
-  if (nj > 3) gfull |= ((lane >> 3) & 1) << f4.x;
-  if (nj > 4) gfull |= ((lane >> 4) & 1) << f4.y;
-  const int gsub = ((lane << 5) >> w_out) & ((1 << P.sg_log2) - 1);
-  gtab[lane] = (uint32_t)(((gfull | cbt[gsub]) & inmask) << 3);
+  const int J = 1 << (nj + P.sg_log2);
+  {
+    // common case (<= 32 entries per thread): one table entry per lane, straight-line
+    const int j = lane;
+    int gfull = 0;
+    if (nj > 0) gfull |= (j & 1) << f3.y;
+    if (nj > 1) gfull |= ((j >> 1) & 1) << f3.z;
+    if (nj > 2) gfull |= ((j >> 2) & 1) << f3.w;
+    if (nj > 3) gfull |= ((j >> 3) & 1) << f4.x;
+    if (nj > 4) gfull |= ((j >> 4) & 1) << f4.y;
+    const int gsub = (j >> nj) & ((1 << P.sg_log2) - 1);
+    gtab[j] = (uint32_t)(((gfull | cbt[gsub]) & inmask) << 3);
+  }
+  if (LY == 1)
+  for (int j = lane + 32; j < J; j += 32) {                        // wide states: 64 / 128 entries per thread
+    int gfull = ((j & 1) << f3.y) | (((j >> 1) & 1) << f3.z) | (((j >> 2) & 1) << f3.w) | (((j >> 3) & 1) << f4.x) |
+                (((j >> 4) & 1) << f4.y);
+    if (nj > 5) gfull |= ((j >> 5) & 1) << f4.z;
+    if (nj > 6) gfull |= ((j >> 6) & 1) << f4.w;
+    const int gsub = (j >> nj) & ((1 << P.sg_log2) - 1);
+    gtab[j] = (uint32_t)(((gfull | cbt[gsub]) & inmask) << 3);
+  }
   const uint32_t pl8 = (uint32_t)(pl << 3) ^ sin_abs;
   uint32_t dl[8];
   dl[0] = 0; dl[1] = (uint32_t)f0.x; dl[2] = (uint32_t)f0.y; dl[4] = (uint32_t)f0.z;
@@ -327,7 +342,7 @@ __device__ __forceinline__ int trace_step(const Tabs &X, const int32_t *__restri
 
 // ---- the team body ---------------------------------------------------------------------------------------------------
 // forward sweep over all steps for the SG shots whose syndrome words sit in sh_syn; returns the final state
-template <int SEMI, bool WT>
+template <int SEMI, bool WT, int LY>
 __device__ __forceinline__ double *forward_pass(const PlanDev &P, const Tabs &X, double *S0, const uint64_t *sh_syn,
                                                 uint32_t *gtab, int32_t *cb, uint32_t *__restrict__ bp, int T, int tid) {
   constexpr bool SM = WT;
@@ -359,23 +374,23 @@ __device__ __forceinline__ double *forward_pass(const PlanDev &P, const Tabs &X,
     const int nk = ldi<SM>(h + TQEC_H_NK);
     const int fo = WT ? ldi<SM>(h + TQEC_H_FAST) : 0;
     const int32_t *cbt = cb + (t << P.sg_log2);
-    if (WT && fo && P.sub_minor) {
+    if (WT && fo && LY == 2) {
       const int32_t *brec = X.ints + (fo - 1);
       const int w_in = ldi<SM>(h + TQEC_H_WIN);
       if (nk == 2) fast_step_b<SEMI, 2>(brec, X.ints, X.tables, sin_abs, sout_abs, cbt[tid], w_in, bpt, tid);
       else if (nk == 1) fast_step_b<SEMI, 1>(brec, X.ints, X.tables, sin_abs, sout_abs, cbt[tid], w_in, bpt, tid);
       else fast_step_b<SEMI, 4>(brec, X.ints, X.tables, sin_abs, sout_abs, cbt[tid], w_in, bpt, tid);
-    } else if (WT && fo) {
+    } else if (WT && fo && LY != 2) {
       const int32_t *frec = X.ints + (fo - 1);
-      if (nk == 2) fast_step<SEMI, 2, SM>(P, X, h, frec, sin_abs, sout_abs, gtab, cbt, bpt, tid);
-      else if (nk == 1) fast_step<SEMI, 1, SM>(P, X, h, frec, sin_abs, sout_abs, gtab, cbt, bpt, tid);
-      else fast_step<SEMI, 4, SM>(P, X, h, frec, sin_abs, sout_abs, gtab, cbt, bpt, tid);
+      if (nk == 2) fast_step<SEMI, 2, SM, LY>(P, X, h, frec, sin_abs, sout_abs, gtab, cbt, bpt, tid);
+      else if (nk == 1) fast_step<SEMI, 1, SM, LY>(P, X, h, frec, sin_abs, sout_abs, gtab, cbt, bpt, tid);
+      else fast_step<SEMI, 4, SM, LY>(P, X, h, frec, sin_abs, sout_abs, gtab, cbt, bpt, tid);
     } else {
       switch (nk) {
-        case 1: run_step<SEMI, 1, SM>(P, X, h, Sin, Sout, cbt, gtab, bpt, T, tid); break;
-        case 2: run_step<SEMI, 2, SM>(P, X, h, Sin, Sout, cbt, gtab, bpt, T, tid); break;
-        case 4: run_step<SEMI, 4, SM>(P, X, h, Sin, Sout, cbt, gtab, bpt, T, tid); break;
-        default: run_step<SEMI, 0, SM>(P, X, h, Sin, Sout, cbt, gtab, bpt, T, tid); break;
+        case 1: run_step<SEMI, 1, SM, LY>(P, X, h, Sin, Sout, cbt, gtab, bpt, T, tid); break;
+        case 2: run_step<SEMI, 2, SM, LY>(P, X, h, Sin, Sout, cbt, gtab, bpt, T, tid); break;
+        case 4: run_step<SEMI, 4, SM, LY>(P, X, h, Sin, Sout, cbt, gtab, bpt, T, tid); break;
+        default: run_step<SEMI, 0, SM, LY>(P, X, h, Sin, Sout, cbt, gtab, bpt, T, tid); break;
       }
     }
     team_sync<WT>();
@@ -395,7 +410,7 @@ __device__ __forceinline__ void bp_locate(int e, int LT, int T, int kb, int &wor
   word = wi * T + ln;
 }
 
-template <int SEMI, bool WT>
+template <int SEMI, bool WT, int LY>
 __device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, unsigned char *smem, int s0_off, uint64_t *sh_syn,
                                          uint64_t *sh_cfg, uint32_t *gtab, int32_t *cb, uint32_t *__restrict__ bp, int T,
                                          int LT, int tid, int64_t g_first, int64_t g_stride,
@@ -404,35 +419,102 @@ __device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, unsign
   constexpr bool SM = WT;
   const int SG = 1 << P.sg_log2;
   double *S0 = reinterpret_cast<double *>(smem + s0_off);
+  // Deferred traceback (max-plus warp teams): the team runs the forward sweeps of 32 consecutive shots one pass after
+  // the other (each pass packs SG shots), keeping every pass's back-pointers in its own slice of the scratch; then lane
+  // q walks the back-pointers of shot q, so the serial traceback costs one warp-instruction stream per 32 shots, not
+  // per shot.  Lane q keeps its shot's syndrome and configuration words in registers (nsw, ncw <= 4).
+  const bool defer = SEMI == TQEC_SEMIRING_MAXPLUS && WT && P.defer;
+  const int QS = defer ? 32 : SG;                       // shots per group
+  const int NF = defer ? (32 >> P.sg_log2) : 1;         // forward passes per group
+  const int64_t n_groups = (B + QS - 1) / QS;
 
-  if (SEMI == TQEC_SEMIRING_MAXPLUS && WT && P.defer) {
-    // Deferred traceback (warp teams): the team runs the forward sweeps of 32 consecutive shots one pass after the other
-    // (each pass packs SG shots), keeping every pass's back-pointers in its own slice of the scratch; then lane q walks
-    // the back-pointers of shot q, so the serial traceback costs one warp-instruction stream per 32 shots, not per shot.
-    // Lane q keeps its shot's syndrome and configuration words in registers (nsw, ncw <= 4).
-    const int NF = 32 >> P.sg_log2;
-    const int64_t n_super = (B + 31) >> 5;
-    for (int64_t g = g_first; g < n_super; g += g_stride) {
-      const int64_t shot0 = g << 5, myshot = shot0 + tid;
-      uint64_t syn[4] = {0ull, 0ull, 0ull, 0ull};
-      if (myshot < B)
+  for (int64_t g = g_first; g < n_groups; g += g_stride) {
+    const int64_t group0 = g * QS, myshot = group0 + tid;
+    uint64_t syn[4] = {0ull, 0ull, 0ull, 0ull};
+    if (defer && myshot < B)
 #pragma unroll
-        for (int w = 0; w < 4; ++w)
-          if (w < P.nsw) syn[w] = synd[myshot * P.nsw + w];
-      for (int f = 0; f < NF; ++f) {
-        if (shot0 + (f << P.sg_log2) >= B) break;
+      for (int w = 0; w < 4; ++w)
+        if (w < P.nsw) syn[w] = synd[myshot * P.nsw + w];
+
+    for (int f = 0; f < NF; ++f) {
+      const int64_t shot0 = group0 + ((int64_t)f << P.sg_log2);
+      if (shot0 >= B) break;
+      if (defer) {
         if ((tid >> P.sg_log2) == f) {
           const int sub = tid & (SG - 1);
 #pragma unroll
           for (int w = 0; w < 4; ++w)
             if (w < P.nsw) sh_syn[sub * P.nsw + w] = syn[w];
         }
-        __syncwarp();
-        const double *Sfin = forward_pass<SEMI, WT>(P, X, S0, sh_syn, gtab, cb, bp + (size_t)f * P.bp_words, T, tid);
-        if (out && tid < SG && shot0 + (f << P.sg_log2) + tid < B) out[shot0 + (f << P.sg_log2) + tid] = Sfin[tid];
-        __syncwarp();
+      } else {
+        for (int i = tid; i < SG * P.nsw; i += T) {
+          const int64_t s = shot0 + i / P.nsw;
+          sh_syn[i] = s < B ? synd[shot0 * P.nsw + i] : 0ull;
+        }
+        if (SEMI == TQEC_SEMIRING_MAXPLUS)
+          for (int i = tid; i < SG * P.ncw; i += T) sh_cfg[i] = 0ull;
       }
-      // lane q: traceback of shot q
+      team_sync<WT>();
+      const double *Sin = forward_pass<SEMI, WT, LY>(P, X, S0, sh_syn, gtab, cb, bp + (size_t)f * P.bp_words, T, tid);
+
+      if (defer) {
+        if (out && tid < SG && shot0 + tid < B) out[shot0 + tid] = Sin[tid];
+      } else if (SEMI == TQEC_SEMIRING_MAXPLUS) {
+        // one thread per shot walks the back-pointers from the scalar root to the first step
+        for (int sub = tid; sub < SG; sub += T) {
+          int tau = 0;
+          uint64_t *cfg = sh_cfg + sub * P.ncw;
+          for (int t = P.n_steps - 1; t >= 0; --t) {
+            const int32_t *h = X.hdr + t * TQEC_HDR_INTS;
+            const int kb = ldi<SM>(h + TQEC_H_KB), r = ldi<SM>(h + TQEC_H_R);
+            int k = 0;
+            if (kb) {
+              int word, sh;
+              bp_locate(LY == 2 ? ((tau << P.sg_log2) | sub) : ((sub << ldi<SM>(h + TQEC_H_WOUT)) | tau), LT, T, kb, word, sh);
+              k = (__ldcg(bp + ldi<SM>(X.bp_off + t) + word) >> sh) & ((1u << kb) - 1u);
+            }
+            int a;
+            tau = trace_step<SM>(X, h, tau, cb[(t << P.sg_log2) + sub], k, a);
+            const int32_t *V = X.ints + ldi<SM>(h + TQEC_H_OFF_VARS);
+            for (int j = 0; j < r; ++j)
+              if ((a >> j) & 1) {
+                const int v = ldi<SM>(V + j);
+                cfg[v >> 6] |= 1ull << (v & 63);
+              }
+          }
+          if (shot0 + sub < B && out) out[shot0 + sub] = Sin[sub];
+        }
+        team_sync<WT>();
+        for (int i = tid; i < SG * P.ncw; i += T)
+          if (shot0 + i / P.ncw < B) corr[shot0 * P.ncw + i] = sh_cfg[i];
+      } else {
+        const int NO = 1 << P.n_obs;
+        for (int i = tid; i < SG * NO; i += T) {
+          const int sub = i >> P.n_obs, idx = i & (NO - 1);
+          int src = 0;
+          for (int o = 0; o < P.n_obs; ++o) src |= ((idx >> o) & 1) << ldi<SM>(X.obs_slot + o);
+          if (shot0 + sub < B) out[(shot0 + sub) * NO + idx] = Sin[LY == 2 ? ((src << P.sg_log2) | sub) : ((sub << P.n_obs) | src)];
+        }
+        if (argmax_out) {
+          for (int sub = tid; sub < SG; sub += T) {
+            if (shot0 + sub >= B) continue;
+            double best = -1.0;
+            int bi = 0;
+            for (int idx = 0; idx < NO; ++idx) {             // first maximal entry (findmax)
+              int src = 0;
+              for (int o = 0; o < P.n_obs; ++o) src |= ((idx >> o) & 1) << ldi<SM>(X.obs_slot + o);
+              const double v = Sin[LY == 2 ? ((src << P.sg_log2) | sub) : ((sub << P.n_obs) | src)];
+              if (v > best) { best = v; bi = idx; }
+            }
+            argmax_out[shot0 + sub] = bi;
+          }
+        }
+      }
+      team_sync<WT>();
+    }
+
+    if (defer) {
+      // lane q: traceback of shot q of the group
       const int f = tid >> P.sg_log2, sub = tid & (SG - 1);
       const uint32_t *bpq = bp + (size_t)f * P.bp_words;
       uint64_t cfg[4] = {0ull, 0ull, 0ull, 0ull};
@@ -446,7 +528,7 @@ __device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, unsign
         int k = 0;
         if (kb) {
           int word, sh;
-          bp_locate(P.sub_minor ? ((tau << P.sg_log2) | sub) : ((sub << q1.x) | tau), 5, 32, kb, word, sh);
+          bp_locate(LY == 2 ? ((tau << P.sg_log2) | sub) : ((sub << q1.x) | tau), 5, 32, kb, word, sh);
           k = (__ldcg(bpq + ldi<SM>(X.bp_off + t) + word) >> sh) & ((1u << kb) - 1u);
         }
         const int32_t *CL = X.ints + q3.y;
@@ -474,85 +556,23 @@ __device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, unsign
           if (w < P.ncw) corr[myshot * P.ncw + w] = cfg[w];
       __syncwarp();
     }
-    return;
-  }
-
-  const int64_t n_groups = (B + SG - 1) >> P.sg_log2;
-  for (int64_t g = g_first; g < n_groups; g += g_stride) {
-    const int64_t shot0 = g << P.sg_log2;
-    for (int i = tid; i < SG * P.nsw; i += T) {
-      const int64_t s = shot0 + i / P.nsw;
-      sh_syn[i] = s < B ? synd[shot0 * P.nsw + i] : 0ull;
-    }
-    if (SEMI == TQEC_SEMIRING_MAXPLUS)
-      for (int i = tid; i < SG * P.ncw; i += T) sh_cfg[i] = 0ull;
-    team_sync<WT>();
-    const double *Sin = forward_pass<SEMI, WT>(P, X, S0, sh_syn, gtab, cb, bp, T, tid);
-
-    if (SEMI == TQEC_SEMIRING_MAXPLUS) {
-      // one thread per shot walks the back-pointers from the scalar root to the first step
-      for (int sub = tid; sub < SG; sub += T) {
-        int tau = 0;
-        uint64_t *cfg = sh_cfg + sub * P.ncw;
-        for (int t = P.n_steps - 1; t >= 0; --t) {
-          const int32_t *h = X.hdr + t * TQEC_HDR_INTS;
-          const int kb = ldi<SM>(h + TQEC_H_KB), r = ldi<SM>(h + TQEC_H_R);
-          int k = 0;
-          if (kb) {
-            int word, sh;
-            bp_locate(P.sub_minor ? ((tau << P.sg_log2) | sub) : ((sub << ldi<SM>(h + TQEC_H_WOUT)) | tau), LT, T, kb, word, sh);
-            k = (__ldcg(bp + ldi<SM>(X.bp_off + t) + word) >> sh) & ((1u << kb) - 1u);
-          }
-          int a;
-          tau = trace_step<SM>(X, h, tau, cb[(t << P.sg_log2) + sub], k, a);
-          const int32_t *V = X.ints + ldi<SM>(h + TQEC_H_OFF_VARS);
-          for (int j = 0; j < r; ++j)
-            if ((a >> j) & 1) {
-              const int v = ldi<SM>(V + j);
-              cfg[v >> 6] |= 1ull << (v & 63);
-            }
-        }
-        if (shot0 + sub < B && out) out[shot0 + sub] = Sin[sub];
-      }
-      team_sync<WT>();
-      for (int i = tid; i < SG * P.ncw; i += T)
-        if (shot0 + i / P.ncw < B) corr[shot0 * P.ncw + i] = sh_cfg[i];
-    } else {
-      const int NO = 1 << P.n_obs;
-      for (int i = tid; i < SG * NO; i += T) {
-        const int sub = i >> P.n_obs, idx = i & (NO - 1);
-        int src = 0;
-        for (int o = 0; o < P.n_obs; ++o) src |= ((idx >> o) & 1) << ldi<SM>(X.obs_slot + o);
-        if (shot0 + sub < B) out[(shot0 + sub) * NO + idx] = Sin[P.sub_minor ? ((src << P.sg_log2) | sub) : ((sub << P.n_obs) | src)];
-      }
-      if (argmax_out) {
-        for (int sub = tid; sub < SG; sub += T) {
-          if (shot0 + sub >= B) continue;
-          double best = -1.0;
-          int bi = 0;
-          for (int idx = 0; idx < NO; ++idx) {             // first maximal entry (findmax)
-            int src = 0;
-            for (int o = 0; o < P.n_obs; ++o) src |= ((idx >> o) & 1) << ldi<SM>(X.obs_slot + o);
-            const double v = Sin[P.sub_minor ? ((src << P.sg_log2) | sub) : ((sub << P.n_obs) | src)];
-            if (v > best) { best = v; bi = idx; }
-          }
-          argmax_out[shot0 + sub] = bi;
-        }
-      }
-    }
-    team_sync<WT>();
   }
 }
 
-// per-team words: syndrome words, configuration words, the 32-entry j table, closed-bit values per (step, shot)
-__host__ __device__ inline size_t team_words_bytes(int sg, int nsw, int ncw, int n_steps) {
-  const size_t b = ((size_t)1 << sg) * (size_t)(nsw + ncw) * sizeof(uint64_t) + 32 * sizeof(uint32_t) +
+// entries of the per-team j table: one per element a thread owns in a step (32 threads per warp team), at least 32
+__host__ __device__ inline int gtab_entries(int w_max, int sg) {
+  const int tot = w_max + sg;
+  return tot > 10 && tot <= 12 ? 1 << (tot - 5) : 32;
+}
+// per-team words: syndrome words, configuration words, the j table, closed-bit values per (step, shot)
+__host__ __device__ inline size_t team_words_bytes(int w_max, int sg, int nsw, int ncw, int n_steps) {
+  const size_t b = ((size_t)1 << sg) * (size_t)(nsw + ncw) * sizeof(uint64_t) + gtab_entries(w_max, sg) * sizeof(uint32_t) +
                    ((size_t)n_steps << sg) * sizeof(int32_t);
   return (b + 15) & ~(size_t)15;
 }
 // per-team shared memory of a CTA team: state ping-pong + words
 __host__ __device__ inline size_t team_smem_bytes(int w_max, int sg, int nsw, int ncw, int n_steps) {
-  return 2 * ((size_t)1 << (w_max + sg)) * sizeof(double) + team_words_bytes(sg, nsw, ncw, n_steps);
+  return 2 * ((size_t)1 << (w_max + sg)) * sizeof(double) + team_words_bytes(w_max, sg, nsw, ncw, n_steps);
 }
 
 // CTA teams: blockDim.x threads form one team, tables in global memory
@@ -567,14 +587,14 @@ __global__ void k_frontier_cta(const PlanDev P, const uint64_t *__restrict__ syn
   uint64_t *sh_syn = reinterpret_cast<uint64_t *>(smem_raw + ((size_t)16 << (P.w_max + P.sg_log2)));
   uint64_t *sh_cfg = sh_syn + SG * P.nsw;
   uint32_t *gtab = reinterpret_cast<uint32_t *>(sh_cfg + SG * P.ncw);
-  int32_t *cb = reinterpret_cast<int32_t *>(gtab + 32);
+  int32_t *cb = reinterpret_cast<int32_t *>(gtab + gtab_entries(P.w_max, P.sg_log2));
   Tabs X{P.hdr, P.ints, P.bp_off, P.obs_slot, P.tables};
-  team_run<SEMI, false>(P, X, smem_raw, 0, sh_syn, sh_cfg, gtab, cb, bp_all + (size_t)blockIdx.x * P.bp_words, T, LT, tid, blockIdx.x,
+  team_run<SEMI, false, 0>(P, X, smem_raw, 0, sh_syn, sh_cfg, gtab, cb, bp_all + (size_t)blockIdx.x * P.bp_words, T, LT, tid, blockIdx.x,
                         gridDim.x, synd, B, corr, out, argmax_out);
 }
 
 // warp teams: every warp of the CTA is an independent team; the schedule tables are staged in shared memory once
-template <int SEMI>
+template <int SEMI, int LY>
 __global__ void k_frontier_warp(const PlanDev P, const uint64_t *__restrict__ synd, const int64_t B,
                                 uint64_t *__restrict__ corr, double *__restrict__ out, int32_t *__restrict__ argmax_out,
                                 uint32_t *__restrict__ bp_all) {
@@ -586,7 +606,7 @@ __global__ void k_frontier_warp(const PlanDev P, const uint64_t *__restrict__ sy
   // them (the driver reserves the first KiB of the window) and the tail hold the table copies and the per-team words.
   const size_t state_bytes = (size_t)16 << (P.w_max + P.sg_log2);
   if (((uint32_t)__cvta_generic_to_shared(smem_raw) + P.off_states) & (uint32_t)(state_bytes / 2 - 1)) __trap();
-  const size_t words_bytes = team_words_bytes(P.sg_log2, P.nsw, P.ncw, P.n_steps);
+  const size_t words_bytes = team_words_bytes(P.w_max, P.sg_log2, P.nsw, P.ncw, P.n_steps);
   unsigned char *words0 = smem_raw + P.off_words;
   double *sm_tables = reinterpret_cast<double *>(smem_raw + P.off_tables);
   int32_t *sm_hdr = reinterpret_cast<int32_t *>(smem_raw + P.off_ints);   // 16-byte aligned; 64 B per step
@@ -602,10 +622,10 @@ __global__ void k_frontier_warp(const PlanDev P, const uint64_t *__restrict__ sy
   uint64_t *sh_syn = reinterpret_cast<uint64_t *>(words0 + words_bytes * warp);
   uint64_t *sh_cfg = sh_syn + SG * P.nsw;
   uint32_t *gtab = reinterpret_cast<uint32_t *>(sh_cfg + SG * P.ncw);
-  int32_t *cb = reinterpret_cast<int32_t *>(gtab + 32);
+  int32_t *cb = reinterpret_cast<int32_t *>(gtab + gtab_entries(P.w_max, P.sg_log2));
   Tabs X{sm_hdr, sm_ints, sm_bpoff, sm_obs, sm_tables};
   const int64_t team = (int64_t)blockIdx.x * NW + warp;
-  team_run<SEMI, true>(P, X, smem_raw, (int)(P.off_states + state_bytes * warp), sh_syn, sh_cfg, gtab, cb, bp_all + (size_t)team * P.bp_words * (P.defer ? (32 >> P.sg_log2) : 1), 32, 5, lane, team,
+  team_run<SEMI, true, LY>(P, X, smem_raw, (int)(P.off_states + state_bytes * warp), sh_syn, sh_cfg, gtab, cb, bp_all + (size_t)team * P.bp_words * (P.defer ? (32 >> P.sg_log2) : 1), 32, 5, lane, team,
                        (int64_t)gridDim.x * NW, synd, B, corr, out, argmax_out);
 }
 
@@ -619,8 +639,19 @@ int launch_decode(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *
     const int64_t ctas = (groups + plan->teams_per_cta - 1) / plan->teams_per_cta;
     const int grid = (int)(ctas < plan->grid_max ? ctas : plan->grid_max);
     const int threads = 32 * plan->teams_per_cta;
-    if (mp) k_frontier_warp<TQEC_SEMIRING_MAXPLUS><<<grid, threads, plan->smem_bytes, stream>>>(plan->dev, d_synd, B, d_corr, d_out, nullptr, plan->d_bp);
-    else k_frontier_warp<TQEC_SEMIRING_SUMPROD><<<grid, threads, plan->smem_bytes, stream>>>(plan->dev, d_synd, B, nullptr, d_out, d_argmax, plan->d_bp);
+    const int ly = plan->layout;
+#define TQEC_LAUNCH_WARP(SEMI, LY, CORR, ARG) \
+  k_frontier_warp<SEMI, LY><<<grid, threads, plan->smem_bytes, stream>>>(plan->dev, d_synd, B, CORR, d_out, ARG, plan->d_bp)
+    if (mp) {
+      if (ly == 2) TQEC_LAUNCH_WARP(TQEC_SEMIRING_MAXPLUS, 2, d_corr, nullptr);
+      else if (ly == 1) TQEC_LAUNCH_WARP(TQEC_SEMIRING_MAXPLUS, 1, d_corr, nullptr);
+      else TQEC_LAUNCH_WARP(TQEC_SEMIRING_MAXPLUS, 0, d_corr, nullptr);
+    } else {
+      if (ly == 2) TQEC_LAUNCH_WARP(TQEC_SEMIRING_SUMPROD, 2, nullptr, d_argmax);
+      else if (ly == 1) TQEC_LAUNCH_WARP(TQEC_SEMIRING_SUMPROD, 1, nullptr, d_argmax);
+      else TQEC_LAUNCH_WARP(TQEC_SEMIRING_SUMPROD, 0, nullptr, d_argmax);
+    }
+#undef TQEC_LAUNCH_WARP
   } else {
     const int grid = (int)(groups < plan->grid_max ? groups : plan->grid_max);
     if (mp) k_frontier_cta<TQEC_SEMIRING_MAXPLUS><<<grid, plan->team_threads, plan->smem_bytes, stream>>>(plan->dev, d_synd, B, d_corr, d_out, nullptr, plan->d_bp);
@@ -687,7 +718,7 @@ static void build_device_tables(const tqec_plan_desc *d, int sg, bool want_fast,
       continue;
     }
     const int lgJ = w_out + sg - LT, lg_jj = w_out - LT - n_open;
-    bool ok = want_fast && lgJ >= 0 && lgJ <= 5 && lg_jj >= 0 && (nk == 1 || nk == 2 || nk == 4);
+    bool ok = want_fast && lgJ >= 0 && lgJ <= 7 && lg_jj >= 0 && (nk == 1 || nk == 2 || nk == 4);
     // lane bits must land inside the input state; the opened slots must be the top output bits, in order
     for (int b = 0; b < 5 && ok; ++b) if (perm[b] >= w_in) ok = false;
     for (int i = 0; i < n_open && ok; ++i) if (perm[w_out - n_open + i] != w_in + i) ok = false;
@@ -711,8 +742,7 @@ static void build_device_tables(const tqec_plan_desc *d, int sg, bool want_fast,
     ints.push_back(U == umax ? 8 : U);       // 8 selects the widest block of this candidate count
     ints.push_back((int32_t)tables.size());
     ints.push_back(cj); ints.push_back(0);
-    for (int b = 0; b < 10; ++b) ints.push_back(b < w_out ? perm[b] : 0);
-    ints.push_back(0); ints.push_back(0);
+    for (int b = 0; b < 12; ++b) ints.push_back(b < w_out ? perm[b] : 0);
     const double *Tt = d->tables + h[TQEC_H_OFF_T];
     for (int b = 0; b < J / U; ++b) {
       const int grp = (b * U) >> lg_jj, pat = grp & (np - 1), sub = grp >> n_open;
@@ -726,6 +756,14 @@ static void build_device_tables(const tqec_plan_desc *d, int sg, bool want_fast,
       }
     }
   }
+}
+
+static const void *warp_kernel(int semiring, int layout) {
+  if (semiring == TQEC_SEMIRING_MAXPLUS)
+    return layout == 2 ? (const void *)k_frontier_warp<TQEC_SEMIRING_MAXPLUS, 2>
+                       : (layout == 1 ? (const void *)k_frontier_warp<TQEC_SEMIRING_MAXPLUS, 1> : (const void *)k_frontier_warp<TQEC_SEMIRING_MAXPLUS, 0>);
+  return layout == 2 ? (const void *)k_frontier_warp<TQEC_SEMIRING_SUMPROD, 2>
+                     : (layout == 1 ? (const void *)k_frontier_warp<TQEC_SEMIRING_SUMPROD, 1> : (const void *)k_frontier_warp<TQEC_SEMIRING_SUMPROD, 0>);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -818,7 +856,10 @@ extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
   if (narrow) sg = 5;
   const int tot_bits = d->w_max + sg;
   int T = 32;
-  if (tot_bits > 10) T = 1 << (tot_bits - 5 > 8 ? 8 : tot_bits - 5);
+  // up to 2^12 state entries a team is one warp (64 / 128 entries per thread and step); beyond that a 256-thread CTA
+  if (tot_bits > 12 || (tot_bits > 10 && std::getenv("TQEC_NO_WIDE_WARP") != nullptr)) T = 1 << (tot_bits - 5 > 8 ? 8 : tot_bits - 5);
+  const int layout = narrow ? 2 : (tot_bits > 10 ? 1 : 0);   // index layout of the warp-team kernel (see run_step)
+  p->layout = layout;
   const int nsw = words_for(d->n_checks), ncw = words_for(d->n_vars);
   const bool want_warp = T == 32 && std::getenv("TQEC_NO_WARP_TEAMS") == nullptr;
 
@@ -833,7 +874,7 @@ extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
   const size_t state_bytes = (size_t)16 << tot_bits, align = state_bytes / 2;
   const size_t ints_bytes = ((hdr.size() + d->n_steps + 1 + d->n_obs + ints.size()) * 4 + 15) & ~(size_t)15;
   const size_t tables_bytes = (tables.size() * 8 + 15) & ~(size_t)15;
-  const size_t words_team = team_words_bytes(sg, nsw, ncw, d->n_steps);
+  const size_t words_team = team_words_bytes(d->w_max, sg, nsw, ncw, d->n_steps);
   int reserved = 1024;
   cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, d->device);
   const size_t gap = (align - (size_t)reserved % align) % align;
@@ -844,8 +885,7 @@ extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
     int cap = 32;
     {
       cudaFuncAttributes fa;
-      const void *wk = d->semiring == TQEC_SEMIRING_MAXPLUS ? (const void *)k_frontier_warp<TQEC_SEMIRING_MAXPLUS>
-                                                            : (const void *)k_frontier_warp<TQEC_SEMIRING_SUMPROD>;
+      const void *wk = warp_kernel(d->semiring, layout);
       if (cudaFuncGetAttributes(&fa, wk) == cudaSuccess && fa.numRegs > 0) {
         const int regs = (fa.numRegs + 7) & ~7;
         int by_regs = prop.regsPerBlock / (regs * 32);
@@ -879,8 +919,7 @@ extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
   p->smem_bytes = (int)smem;
 
   const void *kern;
-  if (p->warp_teams) kern = d->semiring == TQEC_SEMIRING_MAXPLUS ? (const void *)k_frontier_warp<TQEC_SEMIRING_MAXPLUS>
-                                                                 : (const void *)k_frontier_warp<TQEC_SEMIRING_SUMPROD>;
+  if (p->warp_teams) kern = warp_kernel(d->semiring, layout);
   else kern = d->semiring == TQEC_SEMIRING_MAXPLUS ? (const void *)k_frontier_cta<TQEC_SEMIRING_MAXPLUS>
                                                    : (const void *)k_frontier_cta<TQEC_SEMIRING_SUMPROD>;
   TQEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
