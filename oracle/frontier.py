@@ -3,7 +3,8 @@
 Input is the factor graph and the absorption ORDER only (no slot layout, no lowered tables): the state is a numpy
 array with one size-2 axis per currently open check, keyed by check id, batched over shots.  Per step (factor f with
 variables v_1..v_r, table T[a], a = sum_j a_j 2^j):
-    candidates a = 0, 1, ..., 2^r-1 in ascending order;  cand_a[sigma'] = S[sigma' xor M(a)] (x) T[a], where M(a) flips
+    candidates a in ascending order (or in the schedule's enumeration order, `priority_of`: the tie rule is "first best
+    candidate in enumeration order");  cand_a[sigma'] = S[sigma' xor M(a)] (x) T[a], where M(a) flips
     the axis of every touched check whose variables have odd parity under a; checks opened by the step enter with
     parity 0; the result keeps the FIRST best candidate (strict >, i.e. the smallest a on exact FP64 ties); checks
     whose last variable was absorbed are then indexed at the shot's syndrome bit and dropped.
@@ -27,7 +28,16 @@ def _parity_flips(factor_vars, checks, touched, a):
     return flips
 
 
-def run(factors, checks, order, semiring, syndromes, n_vars, want_config=True):
+def priority_of(sch):
+    """Candidate enumeration order of a lowered schedule, per step: candidate k of opened pattern p is the assignment
+    a0[p] ^ ker[k]; within a pattern the kernels compare k = 0, 1, .. and keep the first best one."""
+    out = []
+    for st in sch.steps:
+        out.append([int(st.a0[p]) ^ int(k) for k in st.ker for p in range(len(st.a0)) if st.a0[p] >= 0])
+    return out
+
+
+def run(factors, checks, order, semiring, syndromes, n_vars, want_config=True, priority=None):
     """factors[i].vars/.table (flat, first variable fastest), checks[c].vars/.kind/.index.
     syndromes: (B, n_syn) 0/1.  Max-plus -> (logp (B,), config (B, n_vars) uint8);  sum-product -> marginal
     (B, 2^n_obs) with sector index = sum_i obs_i << i."""
@@ -55,7 +65,8 @@ def run(factors, checks, order, semiring, syndromes, n_vars, want_config=True):
             axes.append(c)
         best = None
         arg = None
-        for a in range(1 << len(f.vars)):
+        cand_list = range(1 << len(f.vars)) if priority is None else priority[t]
+        for a in cand_list:
             flips = _parity_flips(f.vars, checks, touched, a)
             src = np.flip(S, axis=tuple(axes.index(c) + 1 for c in flips)) if flips else S
             cand = src + T[a] if maxplus else src * T[a]

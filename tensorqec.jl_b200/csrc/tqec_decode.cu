@@ -270,6 +270,68 @@ __device__ __forceinline__ void fast_step(const PlanDev &P, const Tabs &X, const
   else fast_blocks<SEMI, NK, 1, 0>(f0.w, rec, pl8, so, dl, gtab, bpt, tid);
 }
 
+// ---- quad step: two factors absorbed at once (4 candidates per output, 2 opened checks), 16-output blocks -----------------
+// The planner (schedule.py, "quad") arranges that the candidates leaving the closed checks alone form a 4-element group
+// that realises the 4 opened patterns p and whose generators flip exactly the checks at output bits 5 and 6 (u): output
+// (u, p) then reads the inputs L[u ^ (p & PM)][k], k = 0..3, where L is a 4 x 4 patch of the input state (4 values of the
+// two u-checks x the 4 kernel candidates).  A thread's block of 16 outputs (u, p) therefore needs 16 loads -- one per
+// output instead of four -- and every loaded value feeds 4 outputs from registers.  PM says which generator flips a
+// surviving check (3: both; 1 / 2: only the first / second -- the other u bit is then an unrelated check).
+template <int SEMI, int PM>
+__device__ __forceinline__ void quad_step(const Tabs &X, const int32_t *__restrict__ h, const int32_t *__restrict__ qrec,
+                                          uint32_t sin_abs, uint32_t sout_abs, const int32_t *__restrict__ cbt,
+                                          uint32_t *__restrict__ bpt, int lane) {
+  const int w_in = h[TQEC_H_WIN];
+  const int4 r0 = *reinterpret_cast<const int4 *>(qrec);        // byte masks of u bit 0, u bit 1, kernel candidates 1, 2
+  const int4 r1 = *reinterpret_cast<const int4 *>(qrec + 4);    // off_T, blocks per thread (shots per pass), pm, -
+  const int4 f2 = *reinterpret_cast<const int4 *>(qrec + 8);    // full slots of output bits 0..3
+  const int f3 = qrec[12];                                      // full slot of output bit 4
+  const int pl = ((lane & 1) << f2.x) | (((lane >> 1) & 1) << f2.y) | (((lane >> 2) & 1) << f2.z) |
+                 (((lane >> 3) & 1) << f2.w) | (((lane >> 4) & 1) << f3);
+  const double *__restrict__ T = X.tables + r1.x;               // T[p * 4 + k]
+  double tv[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) tv[i] = T[i];
+  const uint32_t inmask = (1u << w_in) - 1u;
+  const uint32_t km[4] = {0u, (uint32_t)r0.z, (uint32_t)r0.w, (uint32_t)(r0.z ^ r0.w)};
+#pragma unroll 1
+  for (int sub = 0; sub < r1.y; ++sub) {
+    const uint32_t base = sin_abs ^ (uint32_t)(pl << 3) ^ ((((uint32_t)cbt[sub] & inmask) | ((uint32_t)sub << w_in)) << 3);
+    const uint32_t so = sout_abs + (lane << 3) + ((uint32_t)sub << 12);
+    uint32_t word = 0;
+    // one row of the patch per iteration (NOT unrolled: the body must stay small enough for the instruction cache):
+    // the 4 inputs L[v][0..3] feed the 4 outputs (u = v ^ (p & PM), p), p = 0..3
+#pragma unroll 1
+    for (int v = 0; v < 4; ++v) {
+      const uint32_t row = base ^ ((v & 1) ? (uint32_t)r0.x : 0u) ^ ((v & 2) ? (uint32_t)r0.y : 0u);
+      double L[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) L[k] = lds_f64(row ^ km[k]);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int u = v ^ (p & PM);
+        double c[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c[k] = SEMI == TQEC_SEMIRING_MAXPLUS ? L[k] + tv[p * 4 + k] : L[k] * tv[p * 4 + k];
+        double best;
+        if (SEMI == TQEC_SEMIRING_MAXPLUS) {
+          // the smallest candidate index wins exact ties
+          const bool p01 = c[1] > c[0], p23 = c[3] > c[2];
+          const double b01 = p01 ? c[1] : c[0], b23 = p23 ? c[3] : c[2];
+          const bool pf = b23 > b01;
+          best = pf ? b23 : b01;
+          const uint32_t bk = pf ? (2u | (uint32_t)p23) : (uint32_t)p01;
+          word |= bk << (2 * (u + 4 * p));
+        } else {
+          best = (c[0] + c[1]) + (c[2] + c[3]);
+        }
+        sts_f64(so + (u << 8) + (p << 10), best);
+      }
+    }
+    if (SEMI == TQEC_SEMIRING_MAXPLUS) bpt[sub * 32 + lane] = word;
+  }
+}
+
 // ---- fast step, shot-minor layout ("shot in lane": plans with w_max <= 5 pack 32 shots per team, lane = shot) ---------------
 // The state of shot `lane` sits at ((sigma << 5) | lane) * 8, so every lane walks ALL output indices tau of its own shot:
 // the index arithmetic is uniform across the warp (host-precomputed per step: UK[tau][k] = source index << 8 and the
@@ -374,13 +436,19 @@ __device__ __forceinline__ double *forward_pass(const PlanDev &P, const Tabs &X,
     const int nk = ldi<SM>(h + TQEC_H_NK);
     const int fo = WT ? ldi<SM>(h + TQEC_H_FAST) : 0;
     const int32_t *cbt = cb + (t << P.sg_log2);
-    if (WT && fo && LY == 2) {
+    if (WT && fo > 0 && LY == 2) {
       const int32_t *brec = X.ints + (fo - 1);
       const int w_in = ldi<SM>(h + TQEC_H_WIN);
       if (nk == 2) fast_step_b<SEMI, 2>(brec, X.ints, X.tables, sin_abs, sout_abs, cbt[tid], w_in, bpt, tid);
       else if (nk == 1) fast_step_b<SEMI, 1>(brec, X.ints, X.tables, sin_abs, sout_abs, cbt[tid], w_in, bpt, tid);
       else fast_step_b<SEMI, 4>(brec, X.ints, X.tables, sin_abs, sout_abs, cbt[tid], w_in, bpt, tid);
-    } else if (WT && fo && LY != 2) {
+    } else if (WT && LY == 0 && fo < 0) {
+      const int32_t *qrec = X.ints + (-fo - 1);
+      const int pm = qrec[6];
+      if (pm == 3) quad_step<SEMI, 3>(X, h, qrec, sin_abs, sout_abs, cbt, bpt, tid);
+      else if (pm == 1) quad_step<SEMI, 1>(X, h, qrec, sin_abs, sout_abs, cbt, bpt, tid);
+      else quad_step<SEMI, 2>(X, h, qrec, sin_abs, sout_abs, cbt, bpt, tid);
+    } else if (WT && fo > 0 && LY != 2) {
       const int32_t *frec = X.ints + (fo - 1);
       if (nk == 2) fast_step<SEMI, 2, SM, LY>(P, X, h, frec, sin_abs, sout_abs, gtab, cbt, bpt, tid);
       else if (nk == 1) fast_step<SEMI, 1, SM, LY>(P, X, h, frec, sin_abs, sout_abs, gtab, cbt, bpt, tid);
@@ -716,6 +784,30 @@ static void build_device_tables(const tqec_plan_desc *d, int sg, bool want_fast,
       }
       h[TQEC_H_FAST] = (int32_t)rec_at + 1;
       continue;
+    }
+    // quad step (quad_step): 16-output blocks (u = output bits 5, 6; p = the two opened bits on top), w_out = 9
+    if (want_fast && nk == 4 && n_open == 2 && w_out == 9 && sg <= 1 && std::getenv("TQEC_NO_QUAD") == nullptr) {
+      bool okq = perm[7] == w_in && perm[8] == w_in + 1 && MK[3] == (MK[1] ^ MK[2]);
+      for (int b = 0; b < 7 && okq; ++b) if (perm[b] >= w_in) okq = false;
+      int pm = 0;
+      for (int cand = 3; cand >= 1 && okq && pm == 0; --cand) {
+        bool m = true;
+        for (int pp = 0; pp < 4 && m; ++pp) {
+          const int want = (((pp & 1) && (cand & 1)) ? (1 << perm[5]) : 0) ^ (((pp & 2) && (cand & 2)) ? (1 << perm[6]) : 0);
+          if (ML[pp] != want) m = false;
+        }
+        if (m) pm = cand;
+      }
+      if (okq && pm) {
+        while (ints.size() & 3) ints.push_back(0);
+        h[TQEC_H_FAST] = -((int32_t)ints.size() + 1);
+        ints.push_back((1 << perm[5]) << 3); ints.push_back((1 << perm[6]) << 3);
+        ints.push_back(MK[1] << 3); ints.push_back(MK[2] << 3);
+        ints.push_back(h[TQEC_H_OFF_T]); ints.push_back(1 << sg); ints.push_back(pm); ints.push_back(0);
+        for (int b = 0; b < 5; ++b) ints.push_back(perm[b]);
+        ints.push_back(0); ints.push_back(0); ints.push_back(0);
+        continue;
+      }
     }
     const int lgJ = w_out + sg - LT, lg_jj = w_out - LT - n_open;
     bool ok = want_fast && lgJ >= 0 && lgJ <= 7 && lg_jj >= 0 && (nk == 1 || nk == 2 || nk == 4);

@@ -77,6 +77,7 @@ class Step:
     a0: np.ndarray                           # (2^n_open,) representative candidate per opened pattern, -1 = infeasible
     ker: np.ndarray                          # (nk,) kernel candidates, ascending
     table: np.ndarray                        # (2^r,) values in the semiring's domain (log for max-plus)
+    quad: bool = False                       # two factors absorbed at once in the 16-output block form
 
 
 @dataclass
@@ -292,7 +293,8 @@ def choose_order(factors, checks, max_starts=24):
 
 # ------------------------------------------------------------------------------------------------------------
 def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_vars: int, n_checks: int,
-          n_obs: int = 0, order: Optional[Sequence[int]] = None, max_width: int = MAX_SMEM_WIDTH) -> Schedule:
+          n_obs: int = 0, order: Optional[Sequence[int]] = None, max_width: int = MAX_SMEM_WIDTH,
+          fuse: Optional[bool] = None, _split=None) -> Schedule:
     """Factor graph -> `Schedule` (see module docstring).  `order` optionally fixes the absorption order of the
     (merged) factors, e.g. the leaf order of a contraction tree chosen by the caller's optimiser."""
     all_check_vars = {v for c in checks for v in c.vars}
@@ -306,6 +308,20 @@ def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_v
     order = list(order)
     if sorted(order) != list(range(len(factors))):
         raise ValueError("order must be a permutation of the (merged) factors")
+    if fuse is None:
+        import os as _os
+        fuse = semiring == MAXPLUS and _os.environ.get("TQEC_NO_FUSE") is None
+    if fuse and _split is None:
+        # absorb consecutive factor pairs as one step where that yields the 16-output block form; pairs that do not are
+        # split again (second lowering)
+        mf, morder, pairs = _merge_pairs(factors, order)
+        trial = lower(mf, checks, semiring, n_vars, n_checks, n_obs, order=morder, max_width=max_width, fuse=True,
+                      _split=set())
+        bad = {i for i, st in enumerate(trial.steps) if pairs[i] is not None and not (st.quad and st.w_out == 9)}
+        if len(bad) < sum(p is not None for p in pairs):
+            mf, morder, pairs = _merge_pairs(factors, order, skip=bad)
+            return lower(mf, checks, semiring, n_vars, n_checks, n_obs, order=morder, max_width=max_width, fuse=True,
+                         _split=bad)
     sim = _Sim(factors, checks)
     remaining = [len(fs) for fs in sim.c_factors]
 
@@ -368,12 +384,47 @@ def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_v
         for k in ker:
             kmask |= int(M[k])
         km = [c for c in kept_old if (kmask >> pos[c]) & 1]
+        # "quad" steps (two factors absorbed at once: 4 candidates per output, 2 checks opened): if the candidates that
+        # leave every closed check alone form a 4-element group that realises all 4 opened patterns and each of its two
+        # generators flips exactly one surviving check, those two checks go to output bits 5, 6 and serve as coset
+        # representatives: a block of 16 outputs (4 values of those bits x 4 opened patterns) then reads exactly 16
+        # inputs, each used by 4 outputs (see quad_step in csrc/tqec_decode.cu).
+        quad = False
+        q5 = q6 = None
+        if len(ker) == 4 and n_open == 2 and r <= 6:
+            cmask = 0
+            for slot, _ in closed:
+                cmask |= 1 << slot
+            inmask = (1 << w_in) - 1
+            kc = [a for a in range(1 << r) if (int(M[a]) & cmask) == 0]
+            reps = {int(pat[a]): a for a in kc}
+            if len(kc) == 4 and len(reps) == 4:
+                c1, c2 = int(M[reps[1]]) & inmask, int(M[reps[2]]) & inmask
+                ok1 = c1 == 0 or (c1 & (c1 - 1)) == 0
+                ok2 = c2 == 0 or (c2 & (c2 - 1)) == 0
+                if ok1 and ok2 and (c1 or c2) and c1 != c2:
+                    q5 = full[c1.bit_length() - 1] if c1 else None      # a generator may flip no surviving check:
+                    q6 = full[c2.bit_length() - 1] if c2 else None      # that output bit then holds any other check
+                    if all(q is None or q in kept_old for q in (q5, q6)):
+                        quad = True
+                        for pp in range(4):
+                            a0[pp] = reps[pp]
+                        km = [q for q in (q5, q6) if q is not None]
         nxt = set(plan[t + 1][2]) if t + 1 < len(order) else set()
         cn = [c for c in kept_old if c in nxt and c not in km]
         others = [c for c in kept_old if c not in km and c not in cn]
-        if len(others) >= 5:
+        if quad and len(others) + len(cn) >= 5 + (q5 is None) + (q6 is None):
+            pool = others + cn                                   # bits 0-4, fillers for an unused generator bit, rest
+            low, pool = pool[:5], pool[5:]
+            b5 = q5 if q5 is not None else pool.pop(0)
+            b6 = q6 if q6 is not None else pool.pop(0)
+            rest_cn = [c for c in pool if c in cn]
+            out_old = low + [b5, b6] + rest_cn + [c for c in pool if c not in cn]
+        elif len(others) >= 5:
+            quad = False if quad else quad
             out_old = others[:5] + km + cn + others[5:]
         else:
+            quad = False
             out_old = others + cn + km
         live = out_old + [c for c in opened if c not in closing]
         perm = [pos[c] for c in live]
@@ -390,7 +441,7 @@ def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_v
                 e = int(np.floor(np.log2(mx)))
                 tab = np.ldexp(tab, -e)
                 log2_scale += e
-        steps.append(Step(fi, tuple(f.vars), w_in, w_out, opened, closed, perm, M, a0, ker, tab))
+        steps.append(Step(fi, tuple(f.vars), w_in, w_out, opened, closed, perm, M, a0, ker, tab, quad))
         cost += float(1 << w_out) * len(ker)
         wmax = max(wmax, w_in, w_out)                        # the full index is never materialised
     if wmax > max_width:
@@ -406,6 +457,31 @@ def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_v
     sch = Schedule(semiring, n_vars, n_checks, n_obs, steps, obs_slot, order, factors, list(checks), wmax, cost, log2_scale)
     _encode(sch)
     return sch
+
+
+def _merge_pairs(factors, order, skip=()):
+    """Absorb consecutive factors of the order two at a time (product table over the union of their variables).
+    -> (factors, order, pairs) with pairs[i] = the two original factor ids merged into new factor i, or None.  `skip`:
+    indices (in the fully paired list) of pairs to leave split."""
+    out, pairs = [], []
+    k = 0
+    idx = 0
+    while k < len(order):
+        grp = order[k:k + 2]
+        k += 2
+        fs = [factors[i] for i in grp]
+        if len(fs) == 2 and len(fs[0].vars) + len(fs[1].vars) <= 4 and idx not in skip:
+            f, g = fs
+            r = len(f.vars)
+            a = np.arange(1 << (r + len(g.vars)))
+            out.append(Factor(tuple(f.vars) + tuple(g.vars), f.table[a & ((1 << r) - 1)] * g.table[a >> r]))
+            pairs.append(tuple(grp))
+        else:
+            for f in fs:
+                out.append(f)
+                pairs.append(None)
+        idx += 1
+    return out, list(range(len(out))), pairs
 
 
 def _encode(s: Schedule):

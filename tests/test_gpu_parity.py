@@ -29,7 +29,7 @@ def test_tnmap_d3_all_syndromes_exhaustive(tq):
     syn = ((np.arange(256)[:, None] >> np.arange(8)) & 1).astype(np.uint8)
     res = tq.decode(ct, tq.CSSSyndrome(syn[:, :4], syn[:, 4:]))
     sch = ct.cd.schedule
-    lp, cfg = frontier.run(sch.factors, sch.checks, sch.order, 0, syn, 18)
+    lp, cfg = frontier.run(sch.factors, sch.checks, sch.order, 0, syn, 18, priority=frontier.priority_of(sch))
     got = np.concatenate([res.error_pattern.xerror, res.error_pattern.zerror], axis=1)
     assert np.array_equal(got, cfg)
     assert np.array_equal(res.logp, lp)
@@ -55,7 +55,7 @@ def test_tnmap_surface_matches_oracle_bit_exact(tq, d, B):
     assert np.array_equal(res.error_pattern.zerror, cfg[:, n:])
     assert np.array_equal(res.logp, lp)
     # the numpy statement of the recurrence agrees with its C port on a subset
-    lp2, cfg2 = frontier.run(sch.factors, sch.checks, sch.order, 0, np.concatenate([sx, sz], axis=1)[:128], 2 * n)
+    lp2, cfg2 = frontier.run(sch.factors, sch.checks, sch.order, 0, np.concatenate([sx, sz], axis=1)[:128], 2 * n, priority=frontier.priority_of(sch))
     assert np.array_equal(lp2, lp[:128]) and np.array_equal(cfg2, cfg[:128])
     # decoded pattern reproduces the syndrome (the reference's own assertion, test/decoding/tndecoder.jl:57)
     assert tq.syndrome_extraction(res.error_pattern, t) == tq.CSSSyndrome(sx, sz)

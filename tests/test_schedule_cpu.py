@@ -24,7 +24,7 @@ def test_tnmap_d3_exhaustive_all_oracles_agree(tq):
     gdp, _ = tq.reduce2general(t, em)
     sch = tq.tnmap_schedule(tq.TNMAP(), gdp)
     syn = ((np.arange(256)[:, None] >> np.arange(8)) & 1).astype(np.uint8)
-    lp_f, cfg_f = frontier.run(sch.factors, sch.checks, sch.order, 0, syn, 18)
+    lp_f, cfg_f = frontier.run(sch.factors, sch.checks, sch.order, 0, syn, 18, priority=frontier.priority_of(sch))
     lp_e, cfg_e = emulator.run(sch, syn)
     lp_c, cfg_c = cref.FrontierPlan(sch).run(syn)
     assert np.array_equal(lp_f, lp_e) and np.array_equal(cfg_f, cfg_e)
@@ -59,7 +59,7 @@ def test_tnmap_lowering_vs_recurrence_and_dense(tq, d):
     sch = tq.tnmap_schedule(tq.TNMAP(), gdp)
     assert sch.w_max <= d + 2
     syn = _random_syndromes(t, em, d, 48)
-    lp_f, cfg_f = frontier.run(sch.factors, sch.checks, sch.order, 0, syn, 2 * d * d)
+    lp_f, cfg_f = frontier.run(sch.factors, sch.checks, sch.order, 0, syn, 2 * d * d, priority=frontier.priority_of(sch))
     lp_e, cfg_e = emulator.run(sch, syn)
     lp_c, cfg_c = cref.FrontierPlan(sch).run(syn)
     assert np.array_equal(lp_f, lp_e) and np.array_equal(cfg_f, cfg_e)
@@ -97,7 +97,7 @@ def test_correlated_and_overlapping_priors(tq):
     sch = tq.tnmap_schedule(tq.TNMAP(), gdp)
     syn = ((np.arange(64)[:, None] >> np.arange(6)) & 1).astype(np.uint8)
     lp, cfg = emulator.run(sch, syn)
-    lp2, cfg2 = frontier.run(sch.factors, sch.checks, sch.order, 0, syn, 14)
+    lp2, cfg2 = frontier.run(sch.factors, sch.checks, sch.order, 0, syn, 14, priority=frontier.priority_of(sch))
     assert np.array_equal(lp, lp2) and np.array_equal(cfg, cfg2)
     en = bruteforce.Enumeration(14, [list(c) for c in gdp.tanner.s2q], ixs, tensors)
     for b in range(64):
