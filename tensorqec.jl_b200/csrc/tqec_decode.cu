@@ -297,19 +297,21 @@ __device__ __forceinline__ void quad_step(const Tabs &X, const int32_t *__restri
 #pragma unroll 1
   for (int sub = 0; sub < r1.y; ++sub) {
     const uint32_t base = sin_abs ^ (uint32_t)(pl << 3) ^ ((((uint32_t)cbt[sub] & inmask) | ((uint32_t)sub << w_in)) << 3);
-    const uint32_t so = sout_abs + (lane << 3) + ((uint32_t)sub << 12);
+    const uint32_t so = sout_abs + (lane << 3) + ((uint32_t)sub << 12);   // bits 8..11 (u, p) of the offset are free
     uint32_t word = 0;
     // one row of the patch per iteration (NOT unrolled: the body must stay small enough for the instruction cache):
-    // the 4 inputs L[v][0..3] feed the 4 outputs (u = v ^ (p & PM), p), p = 0..3
+    // the 4 inputs L[v][0..3] feed the 4 outputs (u = v ^ (p & PM), p), p = 0..3.  Back-pointers of a quad step are
+    // filed under (v, p) -- 2 bits at position 2 * (v + 4 p) of the shot's word -- so that every shift is static.
 #pragma unroll 1
     for (int v = 0; v < 4; ++v) {
       const uint32_t row = base ^ ((v & 1) ? (uint32_t)r0.x : 0u) ^ ((v & 2) ? (uint32_t)r0.y : 0u);
+      const uint32_t so_v = so ^ ((uint32_t)v << 8);
       double L[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) L[k] = lds_f64(row ^ km[k]);
+      uint32_t rb = 0;
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
-        const int u = v ^ (p & PM);
         double c[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) c[k] = SEMI == TQEC_SEMIRING_MAXPLUS ? L[k] + tv[p * 4 + k] : L[k] * tv[p * 4 + k];
@@ -321,12 +323,13 @@ __device__ __forceinline__ void quad_step(const Tabs &X, const int32_t *__restri
           const bool pf = b23 > b01;
           best = pf ? b23 : b01;
           const uint32_t bk = pf ? (2u | (uint32_t)p23) : (uint32_t)p01;
-          word |= bk << (2 * (u + 4 * p));
+          rb |= bk << (8 * p);
         } else {
           best = (c[0] + c[1]) + (c[2] + c[3]);
         }
-        sts_f64(so + (u << 8) + (p << 10), best);
+        sts_f64((so_v ^ (uint32_t)((p & PM) << 8)) + (p << 10), best);       // u = v ^ (p & PM)
       }
+      word |= rb << (2 * v);
     }
     if (SEMI == TQEC_SEMIRING_MAXPLUS) bpt[sub * 32 + lane] = word;
   }
@@ -468,6 +471,14 @@ __device__ __forceinline__ double *forward_pass(const PlanDev &P, const Tabs &X,
   return Sin;
 }
 
+// back-pointers of a quad step (standard layout, w_out = 9): element tau = lane | u << 5 | p << 7 of shot `sub` is
+// filed under (v = u ^ (p & pm), p) in word sub * 32 + lane
+__device__ __forceinline__ void bp_locate_quad(int tau, int sub, int pm, int &word, int &sh) {
+  const int u = (tau >> 5) & 3, p = (tau >> 7) & 3;
+  word = sub * 32 + (tau & 31);
+  sh = 2 * ((u ^ (p & pm)) + 4 * p);
+}
+
 // back-pointer of output element e of a step: word index / shift inside the team's per-step block
 __device__ __forceinline__ void bp_locate(int e, int LT, int T, int kb, int &word, int &sh) {
   const int j = e >> LT, ln = e & (T - 1);
@@ -538,7 +549,9 @@ __device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, unsign
             int k = 0;
             if (kb) {
               int word, sh;
-              bp_locate(LY == 2 ? ((tau << P.sg_log2) | sub) : ((sub << ldi<SM>(h + TQEC_H_WOUT)) | tau), LT, T, kb, word, sh);
+              const int fq = WT ? ldi<SM>(h + TQEC_H_FAST) : 0;
+              if (LY == 0 && fq < 0) bp_locate_quad(tau, sub, ldi<SM>(X.ints + (-fq - 1) + 6), word, sh);
+              else bp_locate(LY == 2 ? ((tau << P.sg_log2) | sub) : ((sub << ldi<SM>(h + TQEC_H_WOUT)) | tau), LT, T, kb, word, sh);
               k = (__ldcg(bp + ldi<SM>(X.bp_off + t) + word) >> sh) & ((1u << kb) - 1u);
             }
             int a;
@@ -596,7 +609,8 @@ __device__ __forceinline__ void team_run(const PlanDev &P, const Tabs &X, unsign
         int k = 0;
         if (kb) {
           int word, sh;
-          bp_locate(LY == 2 ? ((tau << P.sg_log2) | sub) : ((sub << q1.x) | tau), 5, 32, kb, word, sh);
+          if (LY == 0 && q3.z < 0) bp_locate_quad(tau, sub, ldi<SM>(X.ints + (-q3.z - 1) + 6), word, sh);
+          else bp_locate(LY == 2 ? ((tau << P.sg_log2) | sub) : ((sub << q1.x) | tau), 5, 32, kb, word, sh);
           k = (__ldcg(bpq + ldi<SM>(X.bp_off + t) + word) >> sh) & ((1u << kb) - 1u);
         }
         const int32_t *CL = X.ints + q3.y;
