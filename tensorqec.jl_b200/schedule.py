@@ -312,16 +312,23 @@ def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_v
         import os as _os
         fuse = semiring == MAXPLUS and _os.environ.get("TQEC_NO_FUSE") is None
     if fuse and _split is None:
-        # absorb consecutive factor pairs as one step where that yields the 16-output block form; pairs that do not are
-        # split again (second lowering)
-        mf, morder, pairs = _merge_pairs(factors, order)
-        trial = lower(mf, checks, semiring, n_vars, n_checks, n_obs, order=morder, max_width=max_width, fuse=True,
-                      _split=set())
-        bad = {i for i, st in enumerate(trial.steps) if pairs[i] is not None and not (st.quad and st.w_out == 9)}
-        if len(bad) < sum(p is not None for p in pairs):
-            mf, morder, pairs = _merge_pairs(factors, order, skip=bad)
-            return lower(mf, checks, semiring, n_vars, n_checks, n_obs, order=morder, max_width=max_width, fuse=True,
-                         _split=bad)
+        # absorb consecutive factor pairs as one step where that yields the 16-output block form: greedy pairing along
+        # the order; a pair that does not come out in the canonical form is forbidden and the pairing redone from there
+        forbidden = set()
+        best = None
+        for _ in range(4 * len(order) + 4):
+            mf, morder, pairs = _merge_pairs(factors, order, forbidden)
+            if not any(p is not None for p in pairs):
+                break
+            trial = lower(mf, checks, semiring, n_vars, n_checks, n_obs, order=morder, max_width=max_width, fuse=True,
+                          _split=True)
+            bad = [pairs[i] for i, st in enumerate(trial.steps) if pairs[i] is not None and not (st.quad and st.w_out == 9)]
+            if not bad:
+                best = trial
+                break
+            forbidden.add(bad[0])
+        if best is not None and any(st.quad for st in best.steps):
+            return best
     sim = _Sim(factors, checks)
     remaining = [len(fs) for fs in sim.c_factors]
 
@@ -459,28 +466,26 @@ def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_v
     return sch
 
 
-def _merge_pairs(factors, order, skip=()):
-    """Absorb consecutive factors of the order two at a time (product table over the union of their variables).
-    -> (factors, order, pairs) with pairs[i] = the two original factor ids merged into new factor i, or None.  `skip`:
-    indices (in the fully paired list) of pairs to leave split."""
+def _merge_pairs(factors, order, forbidden=()):
+    """Greedy pairing along the order: two consecutive factors are absorbed as one (product table over the union of
+    their variables) unless that pair is forbidden.  -> (factors, order, pairs) with pairs[i] = the two original factor
+    ids merged into new factor i, or None."""
     out, pairs = [], []
     k = 0
-    idx = 0
     while k < len(order):
-        grp = order[k:k + 2]
-        k += 2
-        fs = [factors[i] for i in grp]
-        if len(fs) == 2 and len(fs[0].vars) + len(fs[1].vars) <= 4 and idx not in skip:
-            f, g = fs
+        a = order[k]
+        b = order[k + 1] if k + 1 < len(order) else None
+        if b is not None and (a, b) not in forbidden and len(factors[a].vars) + len(factors[b].vars) <= 4:
+            f, g = factors[a], factors[b]
             r = len(f.vars)
-            a = np.arange(1 << (r + len(g.vars)))
-            out.append(Factor(tuple(f.vars) + tuple(g.vars), f.table[a & ((1 << r) - 1)] * g.table[a >> r]))
-            pairs.append(tuple(grp))
+            idx = np.arange(1 << (r + len(g.vars)))
+            out.append(Factor(tuple(f.vars) + tuple(g.vars), f.table[idx & ((1 << r) - 1)] * g.table[idx >> r]))
+            pairs.append((a, b))
+            k += 2
         else:
-            for f in fs:
-                out.append(f)
-                pairs.append(None)
-        idx += 1
+            out.append(factors[a])
+            pairs.append(None)
+            k += 1
     return out, list(range(len(out))), pairs
 
 
