@@ -68,6 +68,26 @@ enum {
 typedef struct tqec_plan tqec_plan; /* a compiled schedule resident on one device      */
 typedef struct tqec_gf2 tqec_gf2;   /* a bit-packed GF(2) matrix resident on one device */
 
+/* Optional second lowering of a max-plus plan: the in-place patch sweep (tensorqec.jl_b200/sweep.py, executed by
+ * k_sweep).  Same recurrence, same results bit for bit; plans that carry it decode through k_sweep unless the
+ * environment variable TQEC_NO_SWEEP is set.  All tables are host pointers copied by tqec_plan_create. */
+typedef struct {
+  int32_t W;               /* slot bits of the state index                                        */
+  int32_t sg;              /* log2(shots per team pass); W + sg = 10                               */
+  int32_t n_ss;            /* super-steps                                                          */
+  int32_t n_head_bits;     /* syndrome bits the tabulated head depends on (<= 8)                   */
+  int32_t bp_words;        /* back-pointer words per lane per pass                                 */
+  int32_t n_tvals;
+  const int32_t *rec;      /* n_ss * 32: forward records                                           */
+  const int32_t *tb;       /* n_ss * 64: traceback records                                         */
+  const uint32_t *lanetab; /* n_ss * 32: lane byte address | lane shot bits << 16                  */
+  const double *tvals;     /* pooled layer tables                                                  */
+  const int32_t *head_bits;/* n_head_bits syndrome bit indices                                     */
+  const double *head_state;/* 2^n_head_bits * 2^W state values after the head                      */
+  const uint64_t *head_cfg;/* 2^n_head_bits * 2^W * ceil(n_vars/64) partial configurations         */
+  const int32_t *out_index;/* index of the final entry                                             */
+} tqec_sweep_desc;
+
 typedef struct {
   int32_t semiring;        /* TQEC_SEMIRING_*                                                     */
   int32_t n_vars;          /* error variables = bits of a decoded configuration                   */
@@ -82,6 +102,7 @@ typedef struct {
   int64_t n_tables;
   const int32_t *obs_slot; /* n_obs: slot of observable i in the final state                      */
   int32_t device;          /* CUDA device ordinal                                                 */
+  const tqec_sweep_desc *sweep; /* optional (NULL): in-place patch sweep of the same plan          */
 } tqec_plan_desc;
 
 const char *tqec_last_error(void);
@@ -95,7 +116,8 @@ int tqec_plan_destroy(tqec_plan *plan);
 enum {
   TQEC_Q_TEAM_THREADS = 0, TQEC_Q_SHOTS_PER_TEAM = 1, TQEC_Q_SMEM_BYTES = 2, TQEC_Q_GRID = 3,
   TQEC_Q_TEAMS_PER_SM = 4, TQEC_Q_BP_BYTES_PER_TEAM = 5, TQEC_Q_CANDIDATES_PER_SHOT = 6, TQEC_Q_SM_COUNT = 7,
-  TQEC_Q_LAUNCHES = 8 /* kernels launched through this plan so far */
+  TQEC_Q_LAUNCHES = 8, /* kernels launched through this plan so far */
+  TQEC_Q_SWEEP = 9     /* 1 if the plan decodes through the in-place patch sweep (k_sweep) */
 };
 int tqec_plan_query(const tqec_plan *plan, int32_t what, int64_t *out);
 

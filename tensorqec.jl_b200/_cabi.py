@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("TQEC_CUDA_LIB", os.path.join(_HERE, "libtqec_cuda.so"
 OK = 0
 MODEL_FLIP, MODEL_DEPOL = 0, 1
 (Q_TEAM_THREADS, Q_SHOTS_PER_TEAM, Q_SMEM_BYTES, Q_GRID, Q_TEAMS_PER_SM, Q_BP_BYTES_PER_TEAM, Q_CANDIDATES_PER_SHOT,
- Q_SM_COUNT, Q_LAUNCHES) = range(9)
+ Q_SM_COUNT, Q_LAUNCHES, Q_SWEEP) = range(10)
 
 EXPORTS = [
     "tqec_last_error", "tqec_version", "tqec_device_count",
@@ -32,12 +32,20 @@ class TqecError(RuntimeError):
     pass
 
 
+class SweepDesc(C.Structure):
+    _fields_ = [("W", C.c_int32), ("sg", C.c_int32), ("n_ss", C.c_int32), ("n_head_bits", C.c_int32),
+                ("bp_words", C.c_int32), ("n_tvals", C.c_int32),
+                ("rec", C.c_void_p), ("tb", C.c_void_p), ("lanetab", C.c_void_p), ("tvals", C.c_void_p),
+                ("head_bits", C.c_void_p), ("head_state", C.c_void_p), ("head_cfg", C.c_void_p),
+                ("out_index", C.c_void_p)]
+
+
 class PlanDesc(C.Structure):
     _fields_ = [("semiring", C.c_int32), ("n_vars", C.c_int32), ("n_checks", C.c_int32), ("n_obs", C.c_int32),
                 ("n_steps", C.c_int32), ("w_max", C.c_int32),
                 ("hdr", C.POINTER(C.c_int32)), ("ints", C.POINTER(C.c_int32)), ("n_ints", C.c_int64),
                 ("tables", C.POINTER(C.c_double)), ("n_tables", C.c_int64),
-                ("obs_slot", C.POINTER(C.c_int32)), ("device", C.c_int32)]
+                ("obs_slot", C.POINTER(C.c_int32)), ("device", C.c_int32), ("sweep", C.POINTER(SweepDesc))]
 
 
 class McDesc(C.Structure):
@@ -133,7 +141,15 @@ class Plan:
         d = PlanDesc(sch.semiring, sch.n_vars, sch.n_checks, sch.n_obs, len(sch.steps), sch.w_max,
                      hdr.ctypes.data_as(C.POINTER(C.c_int32)), ints.ctypes.data_as(C.POINTER(C.c_int32)), ints.size,
                      tabs.ctypes.data_as(C.POINTER(C.c_double)), tabs.size,
-                     obs.ctypes.data_as(C.POINTER(C.c_int32)), device)
+                     obs.ctypes.data_as(C.POINTER(C.c_int32)), device, None)
+        sw = getattr(sch, "sweep", None)
+        if sw is not None:
+            keep = [_c(sw.rec, np.int32), _c(sw.tb, np.int32), _c(sw.lanetab, np.uint32), _c(sw.tvals, np.float64),
+                    _c(sw.head_bits if sw.head_bits else [0], np.int32), _c(sw.head_state, np.float64),
+                    _c(sw.head_cfg, np.uint64), _c(sw.out_index, np.int32)]
+            sd = SweepDesc(sw.W, sw.sg, len(sw.ssteps), len(sw.head_bits), sw.bp_words, keep[3].size,
+                           *[_ptr(a) for a in keep])
+            d.sweep = C.pointer(sd)
         h = C.c_void_p()
         check(lib().tqec_plan_create(C.byref(d), C.byref(h)))
         self.h = h
@@ -149,7 +165,8 @@ class Plan:
         return {k: self.query(q) for k, q in [("team_threads", Q_TEAM_THREADS), ("shots_per_team", Q_SHOTS_PER_TEAM),
                                                ("smem_bytes", Q_SMEM_BYTES), ("grid", Q_GRID),
                                                ("teams_per_sm", Q_TEAMS_PER_SM), ("bp_bytes_per_team", Q_BP_BYTES_PER_TEAM),
-                                               ("candidates_per_shot", Q_CANDIDATES_PER_SHOT), ("sm_count", Q_SM_COUNT)]}
+                                               ("candidates_per_shot", Q_CANDIDATES_PER_SHOT), ("sm_count", Q_SM_COUNT),
+                                               ("sweep", Q_SWEEP)]}
 
     def decode_map(self, synd_words: np.ndarray, want_logp=True):
         s = _c(synd_words, np.uint64).reshape(-1, self.nsw)

@@ -54,6 +54,17 @@ struct PlanDev {
   int32_t off_states, off_ints, off_tables, off_words;  // warp-team shared-memory layout (bytes from the dynamic array)
 };
 
+// Device view of the in-place patch sweep of a plan (tqec_sweep.cu; tables described in tensorqec.jl_b200/sweep.py).
+struct SweepDev {
+  const int32_t *rec, *tb;
+  const uint32_t *lanetab;
+  const double *tvals, *head_state;
+  const uint64_t *head_cfg;
+  int32_t head_bits[8];
+  int32_t n_ss, W, sg, nh, nsw, ncw, bp_words, n_tvals, out_index0;
+  int32_t off_states, off_rec, off_lanetab, off_tvals, off_words, words_bytes;   // shared-memory layout (bytes)
+};
+
 }  // namespace tqec
 
 struct tqec_plan {
@@ -71,6 +82,11 @@ struct tqec_plan {
   int sm_count;
   double candidates_per_shot;
   int64_t launches;
+  // in-place patch sweep (optional)
+  tqec::SweepDev sw;
+  int has_sweep, sw_teams, sw_smem, sw_maxt;
+  void *d_sw[8];
+  uint32_t *d_sw_bp;
   void *d_hdr, *d_ints, *d_tables, *d_bp_off, *d_obs_slot;
   uint32_t *d_bp;        // back-pointer scratch: grid_max * bp_words
   // host staging for the host-pointer entry points
@@ -94,6 +110,9 @@ namespace tqec {
 int ensure_cap(void **ptr, size_t *cap, size_t bytes);
 int launch_decode(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d_corr, double *d_out,
                   int32_t *d_argmax, cudaStream_t stream);
+int launch_sweep(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d_corr, double *d_out, cudaStream_t stream);
+int sweep_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &prop);
+void sweep_destroy(tqec_plan *p);
 int launch_gf2_apply(tqec_gf2 *m, const uint64_t *d_in, int64_t B, uint64_t *d_out, cudaStream_t stream);
 int launch_sample(int model, int n_sites, const double *d_p, uint64_t seed, int64_t shot_offset, int64_t B,
                   uint64_t *d_err, int words, cudaStream_t stream);

@@ -714,6 +714,7 @@ __global__ void k_frontier_warp(const PlanDev P, const uint64_t *__restrict__ sy
 int launch_decode(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d_corr, double *d_out,
                   int32_t *d_argmax, cudaStream_t stream) {
   if (B <= 0) return TQEC_OK;
+  if (plan->has_sweep && plan->semiring == TQEC_SEMIRING_MAXPLUS) return launch_sweep(plan, d_synd, B, d_corr, d_out, stream);
   const int64_t per_group = plan->dev.defer ? 32 : plan->shots_per_team;
   const int64_t groups = (B + per_group - 1) / per_group;
   const bool mp = plan->semiring == TQEC_SEMIRING_MAXPLUS;
@@ -1075,6 +1076,7 @@ extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
     cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); rc = TQEC_ERR_CUDA; }
   }
+  if (!rc) rc = sweep_create(p, d, prop);
   if (rc) { tqec_plan_destroy(p); return rc; }
   D.hdr = (const int32_t *)p->d_hdr; D.ints = (const int32_t *)p->d_ints; D.tables = (const double *)p->d_tables;
   D.bp_off = (const int32_t *)p->d_bp_off; D.obs_slot = (const int32_t *)p->d_obs_slot;
@@ -1087,6 +1089,7 @@ extern "C" int tqec_plan_destroy(tqec_plan *p) {
   cudaSetDevice(p->device);
   cudaFree(p->d_hdr); cudaFree(p->d_ints); cudaFree(p->d_tables); cudaFree(p->d_bp_off); cudaFree(p->d_obs_slot);
   cudaFree(p->d_bp);
+  sweep_destroy(p);
   for (int i = 0; i < 4; ++i) cudaFree(p->d_io[i]);
   if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
@@ -1097,14 +1100,15 @@ extern "C" int tqec_plan_query(const tqec_plan *p, int32_t what, int64_t *out) {
   TQEC_REQUIRE(p && out, "tqec_plan_query: NULL argument");
   switch (what) {
     case TQEC_Q_TEAM_THREADS: *out = p->team_threads; break;
-    case TQEC_Q_SHOTS_PER_TEAM: *out = p->shots_per_team; break;
-    case TQEC_Q_SMEM_BYTES: *out = p->smem_bytes; break;
-    case TQEC_Q_GRID: *out = p->grid_max; break;
-    case TQEC_Q_TEAMS_PER_SM: *out = p->teams_per_sm; break;
-    case TQEC_Q_BP_BYTES_PER_TEAM: *out = (int64_t)p->dev.bp_words * 4; break;
+    case TQEC_Q_SHOTS_PER_TEAM: *out = p->has_sweep ? (1 << p->sw.sg) : p->shots_per_team; break;
+    case TQEC_Q_SMEM_BYTES: *out = p->has_sweep ? p->sw_smem : p->smem_bytes; break;
+    case TQEC_Q_GRID: *out = p->has_sweep ? p->sm_count : p->grid_max; break;
+    case TQEC_Q_TEAMS_PER_SM: *out = p->has_sweep ? p->sw_teams : p->teams_per_sm; break;
+    case TQEC_Q_BP_BYTES_PER_TEAM: *out = p->has_sweep ? (int64_t)p->sw.bp_words * 128 : (int64_t)p->dev.bp_words * 4; break;
     case TQEC_Q_CANDIDATES_PER_SHOT: *out = (int64_t)p->candidates_per_shot; break;
     case TQEC_Q_SM_COUNT: *out = p->sm_count; break;
     case TQEC_Q_LAUNCHES: *out = p->launches; break;
+    case TQEC_Q_SWEEP: *out = p->has_sweep; break;
     default: set_error("tqec_plan_query: unknown item %d", what); return TQEC_ERR_INVALID;
   }
   return TQEC_OK;

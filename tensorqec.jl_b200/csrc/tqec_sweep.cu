@@ -1,0 +1,399 @@
+// In-place patch sweep (k_sweep): the frontier recurrence with static slots, register patches and a tabulated head.
+// Host side of the lowering and the full description: tensorqec.jl_b200/sweep.py.  Summary of what a warp team does for
+// one pass (2^sg shots, 1024 FP64 state entries = 8 KiB of shared memory, updated in place):
+//   1. copy the head-table row selected by the shots' head syndrome bits into the state (swizzled index, see sw_phys);
+//   2. per super-step: every lane loads 2^M entries that differ in the step's patch bits (address = lane part ^ loop
+//      part ^ closed-syndrome part ^ patch part, all XOR of host-made byte masks), absorbs one or two factors on them in
+//      registers (sweep_layer: Out[j] = max_k R[j ^ F(k)] + T[p(j)][k], static register indices), stores them back to
+//      the same addresses and emits the packed back-pointer bits of the patch;
+//   3. after 32 shots (deferred traceback) lane q walks shot q backwards through the traceback records.
+// Bit-identical to the unfused schedule of schedule.py (same IEEE adds in the same order, strict > on ascending
+// candidates).  Shapes of a super-step come from tqec_sweep_menu.h.
+#include <cstdlib>
+#include <cstring>
+
+#include "tqec_common.h"
+#include "tqec_sweep_menu.h"
+
+namespace tqec {
+
+#define SW_REC_INTS 32
+#define SW_TB_INTS 64
+
+__device__ __forceinline__ double sw_lds(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sw_sts(uint32_t addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v));
+}
+__device__ __forceinline__ uint32_t sw_xor3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// swizzled entry index: bits 4..7 XOR-ed into bits 0..3 (sweep.py:phys)
+__host__ __device__ __forceinline__ uint32_t sw_phys(uint32_t x) { return x ^ ((x >> 4) & 15u); }
+
+// One factor absorbed on a register patch.  Output j reads R[j ^ F(k)] for the 2^NF assignments k of the free variables
+// (ascending k = ascending assignment; strict > keeps the smallest on ties) with the table row picked by the pinned bits
+// of j.  Back-pointer bits of output j: k at bit OFF + j * NF.
+template <int SEMI, int M, int NP, int P0, int P1, int NF, int F0, int F1, int OFF>
+__device__ __forceinline__ void sweep_layer(double (&R)[1 << M], const double *T, uint32_t &bits) {
+  constexpr int N = 1 << M;
+  double O[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const int pidx = (NP > 0 ? ((j >> (P0 < 0 ? 0 : P0)) & 1) : 0) | (NP > 1 ? (((j >> (P1 < 0 ? 0 : P1)) & 1) << 1) : 0);
+    const double *Tp = T + (pidx << NF);
+    if (NF == 0) {
+      O[j] = SEMI == TQEC_SEMIRING_MAXPLUS ? R[j] + Tp[0] : R[j] * Tp[0];
+    } else if (NF == 1) {
+      if (SEMI == TQEC_SEMIRING_MAXPLUS) {
+        const double c0 = R[j] + Tp[0], c1 = R[j ^ F0] + Tp[1];
+        const bool p = c1 > c0;
+        O[j] = p ? c1 : c0;
+        if (p) bits |= 1u << ((OFF + j) & 31);
+      } else {
+        O[j] = R[j] * Tp[0] + R[j ^ F0] * Tp[1];
+      }
+    } else {
+      if (SEMI == TQEC_SEMIRING_MAXPLUS) {
+        const double c0 = R[j] + Tp[0], c1 = R[j ^ F0] + Tp[1], c2 = R[j ^ F1] + Tp[2], c3 = R[j ^ F0 ^ F1] + Tp[3];
+        const bool p01 = c1 > c0, p23 = c3 > c2;
+        const double b01 = p01 ? c1 : c0, b23 = p23 ? c3 : c2;
+        const bool pf = b23 > b01;
+        O[j] = pf ? b23 : b01;
+        const uint32_t bk = pf ? (2u | (uint32_t)p23) : (uint32_t)p01;
+        bits |= bk << ((OFF + 2 * j) & 31);
+      } else {
+        O[j] = ((R[j] * Tp[0] + R[j ^ F0] * Tp[1]) + R[j ^ F1] * Tp[2]) + R[j ^ F0 ^ F1] * Tp[3];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) R[j] = O[j];
+}
+
+template <int SEMI, int M, int NL, int NP0, int P00, int P01, int NF0, int F00, int F01, int NP1, int P10, int P11,
+          int NF1, int F10, int F11>
+__device__ __forceinline__ void sweep_step(const int32_t *__restrict__ rec, const double *__restrict__ tvals,
+                                           uint32_t st_abs, uint32_t lt, const uint16_t *__restrict__ stab_row,
+                                           uint32_t *__restrict__ bpt, int lane) {
+  constexpr int N = 1 << M;
+  constexpr int NT0 = 1 << (NP0 + NF0), NT1 = NL > 1 ? (1 << (NP1 + NF1)) : 1;
+  constexpr int BPP = SEMI == TQEC_SEMIRING_MAXPLUS ? N * (NF0 + (NL > 1 ? NF1 : 0)) : 0;
+  constexpr int IPW = BPP ? 32 / BPP : 1;
+  const int4 r0 = *reinterpret_cast<const int4 *>(rec);         // menu id, iterations, table offset, first bp word
+  const int2 am = *reinterpret_cast<const int2 *>(rec + 4);     // byte masks of patch bits 0..3 (u16 each)
+  const uint32_t a0 = (uint32_t)am.x & 0xffffu, a1 = (uint32_t)am.x >> 16, a2 = (uint32_t)am.y & 0xffffu, a3 = (uint32_t)am.y >> 16;
+  const uint32_t lo[4] = {0u, a0, a1, a0 ^ a1};
+  const uint32_t hi[4] = {0u, a2, a3, a2 ^ a3};
+  double T0[NT0], T1[NT1];
+  const double *tv = tvals + r0.z;
+#pragma unroll
+  for (int i = 0; i < NT0; ++i) T0[i] = tv[i];
+#pragma unroll
+  for (int i = 0; i < NT1; ++i) T1[i] = NL > 1 ? tv[NT0 + i] : 0.0;
+  const uint32_t laddr = st_abs ^ (lt & 0xffffu);
+  const uint32_t lsub = lt >> 16;
+  const uint16_t *la = reinterpret_cast<const uint16_t *>(rec + 8);
+  const uint8_t *ls = reinterpret_cast<const uint8_t *>(rec + 12);
+  uint32_t word = 0;
+#pragma unroll 1
+  for (int it = 0; it < r0.y; ++it) {
+    const uint32_t base = laddr ^ (uint32_t)la[it];
+    const uint32_t inb = base ^ (uint32_t)stab_row[lsub | (uint32_t)ls[it]];
+    double R[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) R[j] = sw_lds(sw_xor3(inb, lo[j & 3], hi[(j >> 2) & 3]));
+    uint32_t bits = 0;
+    sweep_layer<SEMI, M, NP0, P00, P01, NF0, F00, F01, 0>(R, T0, bits);
+    if (NL > 1) sweep_layer<SEMI, M, NP1, P10, P11, NF1, F10, F11, N * NF0>(R, T1, bits);
+#pragma unroll
+    for (int j = 0; j < N; ++j) sw_sts(sw_xor3(base, lo[j & 3], hi[(j >> 2) & 3]), R[j]);
+    if (BPP) {
+      if (IPW == 1) {
+        bpt[(r0.w + it) * 32 + lane] = bits;
+      } else {
+        const int q = it % IPW;
+        word |= bits << (BPP * q);
+        if (q == IPW - 1 || it == r0.y - 1) {
+          bpt[(r0.w + it / IPW) * 32 + lane] = word;
+          word = 0;
+        }
+      }
+    }
+  }
+}
+
+template <int SEMI, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
+k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, uint64_t *__restrict__ corr,
+        double *__restrict__ out, uint32_t *__restrict__ bp_all) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int NW = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int SG = 1 << P.sg, NE = 1 << P.W;
+  if (((uint32_t)__cvta_generic_to_shared(smem_raw) + P.off_states) & 8191u) __trap();
+  int32_t *sm_rec = reinterpret_cast<int32_t *>(smem_raw + P.off_rec);
+  uint32_t *sm_lt = reinterpret_cast<uint32_t *>(smem_raw + P.off_lanetab);
+  double *sm_tv = reinterpret_cast<double *>(smem_raw + P.off_tvals);
+  for (int i = threadIdx.x; i < P.n_ss * SW_REC_INTS; i += blockDim.x) sm_rec[i] = P.rec[i];
+  for (int i = threadIdx.x; i < P.n_ss * 32; i += blockDim.x) sm_lt[i] = P.lanetab[i];
+  for (int i = threadIdx.x; i < P.n_tvals; i += blockDim.x) sm_tv[i] = P.tvals[i];
+  __syncthreads();
+  unsigned char *words = smem_raw + P.off_words + (size_t)P.words_bytes * warp;
+  uint64_t *sh_syn = reinterpret_cast<uint64_t *>(words);
+  uint16_t *stab = reinterpret_cast<uint16_t *>(sh_syn + SG * P.nsw);
+  double *st = reinterpret_cast<double *>(smem_raw + P.off_states + (size_t)8192 * warp);
+  const uint32_t st_abs = (uint32_t)__cvta_generic_to_shared(st);
+  const int NF = 32 >> P.sg;                                     // forward passes per group of 32 shots
+  const int64_t n_groups = (B + 31) / 32;
+  const int64_t team = (int64_t)blockIdx.x * NW + warp, n_teams = (int64_t)gridDim.x * NW;
+  uint32_t *bp = bp_all + (size_t)team * NF * P.bp_words * 32;
+
+  for (int64_t g = team; g < n_groups; g += n_teams) {
+    const int64_t group0 = g * 32, myshot = group0 + lane;
+    uint64_t syn[4] = {0ull, 0ull, 0ull, 0ull};
+    if (myshot < B)
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+        if (w < P.nsw) syn[w] = synd[myshot * P.nsw + w];
+
+    for (int f = 0; f < NF; ++f) {
+      const int64_t shot0 = group0 + ((int64_t)f << P.sg);
+      if (shot0 >= B) break;
+      if ((lane >> P.sg) == f) {
+        const int sub = lane & (SG - 1);
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+          if (w < P.nsw) sh_syn[sub * P.nsw + w] = syn[w];
+      }
+      __syncwarp();
+      // head: copy the tabulated state of the shots' head syndrome pattern
+      for (int sub = 0; sub < SG; ++sub) {
+        int hp = 0;
+        for (int j = 0; j < P.nh; ++j) {
+          const int b = P.head_bits[j];
+          hp |= (int)((sh_syn[sub * P.nsw + (b >> 6)] >> (b & 63)) & 1ull) << j;
+        }
+        const double *src = P.head_state + ((size_t)hp << P.W);
+        for (int e = lane; e < NE; e += 32) st[sw_phys((uint32_t)(e | (sub << P.W)))] = __ldg(src + e);
+      }
+      // closed-bit address masks of every (super-step, shot)
+      for (int idx = lane; idx < (P.n_ss << P.sg); idx += 32) {
+        const int i = idx >> P.sg, sub = idx & (SG - 1);
+        const int32_t *r = sm_rec + i * SW_REC_INTS;
+        uint32_t v = 0;
+        for (int q = 0; q < r[14]; ++q) {
+          const uint32_t c = (uint32_t)r[16 + q], sb = c & 0xffffu;
+          if ((sh_syn[sub * P.nsw + (sb >> 6)] >> (sb & 63)) & 1ull) v ^= c >> 16;
+        }
+        stab[idx] = (uint16_t)v;
+      }
+      __syncwarp();
+      uint32_t *bpf = bp + (size_t)f * P.bp_words * 32;
+      for (int i = 0; i < P.n_ss; ++i) {
+        const int32_t *rec = sm_rec + i * SW_REC_INTS;
+        const uint32_t lt = sm_lt[i * 32 + lane];
+        const uint16_t *srow = stab + (i << P.sg);
+        switch (rec[0]) {
+#define SW_CASE(ID, M, NL, NP0, P00, P01, NF0, F00, F01, NP1, P10, P11, NF1, F10, F11)                                  \
+  case ID:                                                                                                             \
+    sweep_step<SEMI, M, NL, NP0, P00, P01, NF0, F00, F01, NP1, P10, P11, NF1, F10, F11>(rec, sm_tv, st_abs, lt, srow, bpf, lane); \
+    break;
+          TQEC_SWEEP_MENU(SW_CASE)
+#undef SW_CASE
+          default: __trap();
+        }
+        __syncwarp();
+      }
+      if (out && lane < SG && shot0 + lane < B) out[shot0 + lane] = st[sw_phys((uint32_t)(P.out_index0 | (lane << P.W)))];
+      __syncwarp();
+    }
+
+    // deferred traceback: lane q walks shot q of the group
+    {
+      const int f = lane >> P.sg, sub = lane & (SG - 1);
+      const uint32_t *bpq = bp + (size_t)f * P.bp_words * 32;
+      uint64_t cfg[4] = {0ull, 0ull, 0ull, 0ull};
+      uint32_t x = (uint32_t)P.out_index0 | ((uint32_t)sub << P.W);
+      for (int i = P.n_ss - 1; i >= 0; --i) {
+        const int32_t *t = P.tb + (size_t)i * SW_TB_INTS;
+        const int4 t0 = __ldg(reinterpret_cast<const int4 *>(t));          // M, layers, loop bits, bpp
+        const int4 t1 = __ldg(reinterpret_cast<const int4 *>(t + 4));      // wbase, ipw, closed, -
+        const int4 tp = __ldg(reinterpret_cast<const int4 *>(t + 8));      // positions of patch bits
+        const int pos[4] = {tp.x, tp.y, tp.z, tp.w};
+        uint32_t j = 0, ln = 0, it = 0, pm = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (b < t0.x) { j |= ((x >> pos[b]) & 1u) << b; pm |= 1u << pos[b]; }
+#pragma unroll
+        for (int q = 0; q < 5; ++q) ln |= ((x >> __ldg(t + 12 + q)) & 1u) << q;
+        for (int q = 0; q < t0.z; ++q) it |= ((x >> __ldg(t + 17 + q)) & 1u) << q;
+        uint32_t pb = 0;
+        if (t0.w) {
+          const uint32_t wd = __ldcg(bpq + (size_t)(t1.x + it / t1.y) * 32 + ln);
+          pb = wd >> (t0.w * (it % t1.y));
+        }
+        for (int li = t0.y - 1; li >= 0; --li) {
+          const int32_t *L = t + 30 + 12 * li;
+          const int np = __ldg(L), nf = __ldg(L + 1), bo = __ldg(L + 2);
+          const uint32_t k = nf ? ((pb >> (bo + j * nf)) & ((1u << nf) - 1u)) : 0u;
+          for (int q = 0; q < np; ++q) {
+            const int pbit = __ldg(L + 3 + 2 * q), v = __ldg(L + 4 + 2 * q);
+            const uint64_t bitv = (uint64_t)((j >> pbit) & 1u) << (v & 63);
+            const int w = v >> 6;
+            cfg[0] |= w == 0 ? bitv : 0ull; cfg[1] |= w == 1 ? bitv : 0ull;
+            cfg[2] |= w == 2 ? bitv : 0ull; cfg[3] |= w == 3 ? bitv : 0ull;
+          }
+          for (int q = 0; q < nf; ++q) {
+            const int fm = __ldg(L + 7 + 2 * q), v = __ldg(L + 8 + 2 * q);
+            const uint32_t kb = (k >> q) & 1u;
+            const uint64_t bitv = (uint64_t)kb << (v & 63);
+            const int w = v >> 6;
+            cfg[0] |= w == 0 ? bitv : 0ull; cfg[1] |= w == 1 ? bitv : 0ull;
+            cfg[2] |= w == 2 ? bitv : 0ull; cfg[3] |= w == 3 ? bitv : 0ull;
+            if (kb) j ^= (uint32_t)fm;
+          }
+        }
+        x &= ~pm;
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (b < t0.x) x |= ((j >> b) & 1u) << pos[b];
+        for (int q = 0; q < t1.z; ++q) {
+          const int sb = __ldg(t + 22 + 2 * q), ps = __ldg(t + 23 + 2 * q), w = sb >> 6;
+          const uint64_t sw = w == 0 ? syn[0] : (w == 1 ? syn[1] : (w == 2 ? syn[2] : syn[3]));
+          x ^= (uint32_t)((sw >> (sb & 63)) & 1ull) << ps;
+        }
+      }
+      int hp = 0;
+      for (int jb = 0; jb < P.nh; ++jb) {
+        const int b = P.head_bits[jb], w = b >> 6;
+        const uint64_t sw = w == 0 ? syn[0] : (w == 1 ? syn[1] : (w == 2 ? syn[2] : syn[3]));
+        hp |= (int)((sw >> (b & 63)) & 1ull) << jb;
+      }
+      const uint64_t *hc = P.head_cfg + (((size_t)hp << P.W) + (x & (uint32_t)(NE - 1))) * P.ncw;
+      if (myshot < B)
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+          if (w < P.ncw) corr[myshot * P.ncw + w] = cfg[w] | __ldg(hc + w);
+      __syncwarp();
+    }
+  }
+}
+
+int launch_sweep(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d_corr, double *d_out, cudaStream_t stream) {
+  const int64_t groups = (B + 31) / 32;
+  const int64_t ctas = (groups + plan->sw_teams - 1) / plan->sw_teams;
+  const int grid = (int)(ctas < plan->sm_count ? ctas : plan->sm_count);
+  if (plan->sw_maxt == 768)
+    k_sweep<TQEC_SEMIRING_MAXPLUS, 768><<<grid, 32 * plan->sw_teams, plan->sw_smem, stream>>>(plan->sw, d_synd, B, d_corr, d_out, plan->d_sw_bp);
+  else if (plan->sw_maxt == 640)
+    k_sweep<TQEC_SEMIRING_MAXPLUS, 640><<<grid, 32 * plan->sw_teams, plan->sw_smem, stream>>>(plan->sw, d_synd, B, d_corr, d_out, plan->d_sw_bp);
+  else
+    k_sweep<TQEC_SEMIRING_MAXPLUS, 512><<<grid, 32 * plan->sw_teams, plan->sw_smem, stream>>>(plan->sw, d_synd, B, d_corr, d_out, plan->d_sw_bp);
+  TQEC_CUDA(cudaGetLastError());
+  plan->launches += 1;
+  return TQEC_OK;
+}
+
+template <typename T>
+static int sw_upload(void **slot, const T *src, size_t n) {
+  TQEC_CUDA(cudaMalloc(slot, (n ? n : 1) * sizeof(T)));
+  if (n) TQEC_CUDA(cudaMemcpy(*slot, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  return TQEC_OK;
+}
+
+void sweep_destroy(tqec_plan *p) {
+  for (int i = 0; i < 8; ++i) if (p->d_sw[i]) cudaFree(p->d_sw[i]);
+  if (p->d_sw_bp) cudaFree(p->d_sw_bp);
+}
+
+// Validate and upload the sweep tables of a plan descriptor; chooses teams per CTA from shared memory and registers.
+int sweep_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &prop) {
+  const tqec_sweep_desc *s = d->sweep;
+  p->has_sweep = 0;
+  if (!s || std::getenv("TQEC_NO_SWEEP")) return TQEC_OK;
+  TQEC_REQUIRE(d->semiring == TQEC_SEMIRING_MAXPLUS, "sweep tables are supported for max-plus plans only");
+  TQEC_REQUIRE(s->W >= 1 && s->sg >= 0 && s->sg <= 5 && s->W + s->sg == 10, "sweep: W=%d sg=%d must add up to 10 index bits", s->W, s->sg);
+  TQEC_REQUIRE(s->n_ss > 0 && s->rec && s->tb && s->lanetab && s->tvals && s->head_state && s->head_cfg && s->out_index,
+               "sweep: missing table");
+  TQEC_REQUIRE(s->n_head_bits >= 0 && s->n_head_bits <= 8 && (s->n_head_bits == 0 || s->head_bits), "sweep: bad head bits");
+  const int nsw = words_for(d->n_checks), ncw = words_for(d->n_vars);
+  TQEC_REQUIRE(nsw <= 4 && ncw <= 4, "sweep: more than 256 checks / variables");
+  for (int i = 0; i < s->n_ss; ++i) {
+    const int32_t *r = s->rec + (size_t)i * SW_REC_INTS;
+    TQEC_REQUIRE(r[0] >= 0 && r[0] < TQEC_SWEEP_MENU_SIZE, "sweep step %d: unknown shape %d", i, r[0]);
+    TQEC_REQUIRE(r[1] >= 1 && r[1] <= 8, "sweep step %d: bad iteration count %d", i, r[1]);
+    TQEC_REQUIRE(r[2] >= 0 && r[2] + 8 <= s->n_tvals + 8 && r[14] >= 0 && r[14] <= 4, "sweep step %d: bad offsets", i);
+    for (int q = 0; q < r[14]; ++q)
+      TQEC_REQUIRE(((uint32_t)r[16 + q] & 0xffffu) < (uint32_t)d->n_checks, "sweep step %d: syndrome bit out of range", i);
+  }
+  for (int j = 0; j < s->n_head_bits; ++j)
+    TQEC_REQUIRE(s->head_bits[j] >= 0 && s->head_bits[j] < d->n_checks, "sweep: head bit out of range");
+
+  SweepDev &D = p->sw;
+  std::memset(&D, 0, sizeof(D));
+  D.n_ss = s->n_ss; D.W = s->W; D.sg = s->sg; D.nh = s->n_head_bits; D.nsw = nsw; D.ncw = ncw;
+  D.bp_words = s->bp_words > 0 ? s->bp_words : 1; D.n_tvals = s->n_tvals; D.out_index0 = s->out_index[0];
+  for (int j = 0; j < s->n_head_bits; ++j) D.head_bits[j] = s->head_bits[j];
+  const size_t nhp = (size_t)1 << s->n_head_bits, ne = (size_t)1 << s->W;
+  int rc;
+  if ((rc = sw_upload(&p->d_sw[0], s->rec, (size_t)s->n_ss * SW_REC_INTS))) return rc;
+  if ((rc = sw_upload(&p->d_sw[1], s->tb, (size_t)s->n_ss * SW_TB_INTS))) return rc;
+  if ((rc = sw_upload(&p->d_sw[2], s->lanetab, (size_t)s->n_ss * 32))) return rc;
+  if ((rc = sw_upload(&p->d_sw[3], s->tvals, (size_t)s->n_tvals))) return rc;
+  if ((rc = sw_upload(&p->d_sw[4], s->head_state, nhp * ne))) return rc;
+  if ((rc = sw_upload(&p->d_sw[5], s->head_cfg, nhp * ne * ncw))) return rc;
+  D.rec = (const int32_t *)p->d_sw[0]; D.tb = (const int32_t *)p->d_sw[1]; D.lanetab = (const uint32_t *)p->d_sw[2];
+  D.tvals = (const double *)p->d_sw[3]; D.head_state = (const double *)p->d_sw[4]; D.head_cfg = (const uint64_t *)p->d_sw[5];
+
+  // shared-memory layout: [front gap up to the first 8 KiB-aligned absolute address][states][remaining blobs]
+  int reserved = 1024;
+  cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, d->device);
+  const size_t gap = (8192 - (size_t)reserved % 8192) % 8192;
+  const size_t rec_b = ((size_t)s->n_ss * SW_REC_INTS * 4 + 15) & ~(size_t)15, lt_b = (size_t)s->n_ss * 128;
+  const size_t tv_b = ((size_t)s->n_tvals * 8 + 15) & ~(size_t)15;
+  const size_t words_b = (((size_t)nsw << s->sg) * 8 + ((size_t)s->n_ss << s->sg) * 2 + 15) & ~(size_t)15;
+  // register budget variant: 768 threads (80 registers), 640 (96) or 512 (128); TQEC_SWEEP_MAXT overrides the default
+  int maxt = 640;
+  if (const char *e = std::getenv("TQEC_SWEEP_MAXT")) { const int v = std::atoi(e); if (v == 768 || v == 640 || v == 512) maxt = v; }
+  const void *kern = maxt == 768 ? (const void *)k_sweep<TQEC_SEMIRING_MAXPLUS, 768>
+                                 : (maxt == 640 ? (const void *)k_sweep<TQEC_SEMIRING_MAXPLUS, 640> : (const void *)k_sweep<TQEC_SEMIRING_MAXPLUS, 512>);
+  p->sw_maxt = maxt;
+  cudaFuncAttributes fa;
+  TQEC_CUDA(cudaFuncGetAttributes(&fa, kern));
+  int cap = fa.maxThreadsPerBlock / 32;
+  if (fa.numRegs > 0) {
+    const int by_regs = prop.regsPerBlock / (((fa.numRegs + 7) & ~7) * 32);
+    if (by_regs < cap) cap = by_regs;
+  }
+  if (const char *e = std::getenv("TQEC_SWEEP_TEAMS")) { const int v = std::atoi(e); if (v >= 1 && v < cap) cap = v; }
+  const size_t budget = (size_t)prop.sharedMemPerBlockOptin;
+  int nw = 0;
+  size_t offs[4] = {0, 0, 0, 0}, total = 0;
+  for (int cand = cap; cand >= 1 && nw == 0; --cand) {
+    size_t front = 0, tail = gap + (size_t)8192 * cand;
+    const size_t sizes[4] = {rec_b, lt_b, tv_b, words_b * cand};
+    size_t o[4];
+    for (int i = 0; i < 4; ++i) {
+      if (front + sizes[i] <= gap) { o[i] = front; front += sizes[i]; }
+      else { o[i] = tail; tail += sizes[i]; }
+    }
+    if (tail <= budget) { nw = cand; total = tail; for (int i = 0; i < 4; ++i) offs[i] = o[i]; }
+  }
+  if (nw < 1) { sweep_destroy(p); std::memset(p->d_sw, 0, sizeof(p->d_sw)); return TQEC_OK; }   // does not fit: general kernels
+  D.off_states = (int32_t)gap; D.off_rec = (int32_t)offs[0]; D.off_lanetab = (int32_t)offs[1]; D.off_tvals = (int32_t)offs[2];
+  D.off_words = (int32_t)offs[3]; D.words_bytes = (int32_t)words_b;
+  p->sw_teams = nw; p->sw_smem = (int)total;
+  TQEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
+  const size_t bp_bytes = (size_t)p->sm_count * nw * (32 >> s->sg) * D.bp_words * 32 * sizeof(uint32_t);
+  cudaError_t e = cudaMalloc((void **)&p->d_sw_bp, bp_bytes);
+  if (e != cudaSuccess) { set_error("cudaMalloc(%zu B sweep back-pointer scratch): %s", bp_bytes, cudaGetErrorString(e)); return TQEC_ERR_NOMEM; }
+  p->has_sweep = 1;
+  return TQEC_OK;
+}
+
+}  // namespace tqec

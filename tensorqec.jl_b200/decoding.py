@@ -12,12 +12,15 @@ prior tensors, same parity constraints, same open logical axes), lowers it to a 
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass, field
 from typing import Any, List, Optional, Sequence
 
 import numpy as np
 
 from . import _cabi, schedule as S
+from .sweep import lower_sweep
 from .dem import DetectorErrorModel, dem2tanner
 from .error_model import (AbstractErrorModel, CSSErrorPattern, CSSSyndrome, IndependentDepolarizingError,
                           IndependentFlipError, SimpleSyndrome, iid_error)
@@ -184,7 +187,19 @@ def tnmap_schedule(decoder: TNMAP, problem: GeneralDecodingProblem) -> S.Schedul
         if any(not 0 <= v < t.nq for v in f.vars):
             raise IndexError("prior tensor label outside 0..nq-1")
     checks = [S.Check(tuple(c), "syn", s) for s, c in enumerate(t.s2q)]
-    return S.lower(factors, checks, S.MAXPLUS, t.nq, t.ns, 0, order=_order_of(decoder.optimizer, len(factors)))
+    order = _order_of(decoder.optimizer, len(factors))
+    if os.environ.get("TQEC_NO_SWEEP") is None:
+        # preferred lowering: the in-place patch sweep of the unfused schedule (sweep.py); plans whose steps do not fit
+        # its shapes fall through to the general kernels
+        try:
+            su = S.lower(factors, checks, S.MAXPLUS, t.nq, t.ns, 0, order=order, fuse=False)
+            sw = lower_sweep(su) if 6 <= su.w_max <= 10 else None
+        except ValueError:
+            sw = None
+        if sw is not None:
+            su.sweep = sw
+            return su
+    return S.lower(factors, checks, S.MAXPLUS, t.nq, t.ns, 0, order=order)
 
 
 def _compile_tnmap(decoder: TNMAP, problem: GeneralDecodingProblem) -> CompiledTNMAP:
