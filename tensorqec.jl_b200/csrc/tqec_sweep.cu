@@ -11,6 +11,7 @@
 // candidates).  Shapes of a super-step come from tqec_sweep_menu.h.
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 
 #include "tqec_common.h"
 #include "tqec_sweep_menu.h"
@@ -38,42 +39,50 @@ __host__ __device__ __forceinline__ uint32_t sw_phys(uint32_t x) { return x ^ ((
 
 // One factor absorbed on a register patch.  Output j reads R[j ^ F(k)] for the 2^NF assignments k of the free variables
 // (ascending k = ascending assignment; strict > keeps the smallest on ties) with the table row picked by the pinned bits
-// of j.  Back-pointer bits of output j: k at bit OFF + j * NF.
-template <int SEMI, int M, int NP, int P0, int P1, int NF, int F0, int F1, int OFF>
-__device__ __forceinline__ void sweep_layer(double (&R)[1 << M], const double *T, uint32_t &bits) {
-  constexpr int N = 1 << M;
-  double O[N];
-#pragma unroll
-  for (int j = 0; j < N; ++j) {
-    const int pidx = (NP > 0 ? ((j >> (P0 < 0 ? 0 : P0)) & 1) : 0) | (NP > 1 ? (((j >> (P1 < 0 ? 0 : P1)) & 1) << 1) : 0);
-    const double *Tp = T + (pidx << NF);
-    if (NF == 0) {
-      O[j] = SEMI == TQEC_SEMIRING_MAXPLUS ? R[j] + Tp[0] : R[j] * Tp[0];
-    } else if (NF == 1) {
-      if (SEMI == TQEC_SEMIRING_MAXPLUS) {
-        const double c0 = R[j] + Tp[0], c1 = R[j ^ F0] + Tp[1];
-        const bool p = c1 > c0;
-        O[j] = p ? c1 : c0;
-        if (p) bits |= 1u << ((OFF + j) & 31);
-      } else {
-        O[j] = R[j] * Tp[0] + R[j ^ F0] * Tp[1];
-      }
+// of j.  Back-pointer bits of output j: k at bit OFF + j * NF.  The output index J is a template parameter so that the
+// back-pointer mask is an immediate of a predicated OR (one issue slot per bit; the compiler's own lowering of
+// `if (p) bits |= m` costs a SEL plus a share of a LOP3).
+template <int SEMI, int M, int NP, int P0, int P1, int NF, int F0, int F1, int OFF, int J>
+__device__ __forceinline__ void sweep_out(const double (&R)[1 << M], double (&O)[1 << M], const double *T, uint32_t &bits) {
+  constexpr int pidx = (NP > 0 ? ((J >> (P0 < 0 ? 0 : P0)) & 1) : 0) | (NP > 1 ? (((J >> (P1 < 0 ? 0 : P1)) & 1) << 1) : 0);
+  const double *Tp = T + (pidx << NF);
+  if (NF == 0) {
+    O[J] = SEMI == TQEC_SEMIRING_MAXPLUS ? R[J] + Tp[0] : R[J] * Tp[0];
+  } else if (NF == 1) {
+    if (SEMI == TQEC_SEMIRING_MAXPLUS) {
+      constexpr uint32_t m = 1u << ((OFF + J) & 31);
+      const double c0 = R[J] + Tp[0], c1 = R[J ^ F0] + Tp[1];
+      asm("{\n .reg .pred p;\n setp.gt.f64 p, %2, %3;\n selp.f64 %0, %2, %3, p;\n @p or.b32 %1, %1, %4;\n}"
+          : "=d"(O[J]), "+r"(bits) : "d"(c1), "d"(c0), "n"(m));
     } else {
-      if (SEMI == TQEC_SEMIRING_MAXPLUS) {
-        const double c0 = R[j] + Tp[0], c1 = R[j ^ F0] + Tp[1], c2 = R[j ^ F1] + Tp[2], c3 = R[j ^ F0 ^ F1] + Tp[3];
-        const bool p01 = c1 > c0, p23 = c3 > c2;
-        const double b01 = p01 ? c1 : c0, b23 = p23 ? c3 : c2;
-        const bool pf = b23 > b01;
-        O[j] = pf ? b23 : b01;
-        const uint32_t bk = pf ? (2u | (uint32_t)p23) : (uint32_t)p01;
-        bits |= bk << ((OFF + 2 * j) & 31);
-      } else {
-        O[j] = ((R[j] * Tp[0] + R[j ^ F0] * Tp[1]) + R[j ^ F1] * Tp[2]) + R[j ^ F0 ^ F1] * Tp[3];
-      }
+      O[J] = R[J] * Tp[0] + R[J ^ F0] * Tp[1];
+    }
+  } else {
+    if (SEMI == TQEC_SEMIRING_MAXPLUS) {
+      const double c0 = R[J] + Tp[0], c1 = R[J ^ F0] + Tp[1], c2 = R[J ^ F1] + Tp[2], c3 = R[J ^ F0 ^ F1] + Tp[3];
+      const bool p01 = c1 > c0, p23 = c3 > c2;
+      const double b01 = p01 ? c1 : c0, b23 = p23 ? c3 : c2;
+      const bool pf = b23 > b01;
+      O[J] = pf ? b23 : b01;
+      const uint32_t bk = pf ? (2u | (uint32_t)p23) : (uint32_t)p01;
+      bits |= bk << ((OFF + 2 * J) & 31);
+    } else {
+      O[J] = ((R[J] * Tp[0] + R[J ^ F0] * Tp[1]) + R[J ^ F1] * Tp[2]) + R[J ^ F0 ^ F1] * Tp[3];
     }
   }
+}
+
+template <int SEMI, int M, int NP, int P0, int P1, int NF, int F0, int F1, int OFF, int... J>
+__device__ __forceinline__ void sweep_layer_seq(double (&R)[1 << M], const double *T, uint32_t &bits, std::integer_sequence<int, J...>) {
+  double O[1 << M];
+  (sweep_out<SEMI, M, NP, P0, P1, NF, F0, F1, OFF, J>(R, O, T, bits), ...);
 #pragma unroll
-  for (int j = 0; j < N; ++j) R[j] = O[j];
+  for (int j = 0; j < (1 << M); ++j) R[j] = O[j];
+}
+
+template <int SEMI, int M, int NP, int P0, int P1, int NF, int F0, int F1, int OFF>
+__device__ __forceinline__ void sweep_layer(double (&R)[1 << M], const double *T, uint32_t &bits) {
+  sweep_layer_seq<SEMI, M, NP, P0, P1, NF, F0, F1, OFF>(R, T, bits, std::make_integer_sequence<int, (1 << M)>{});
 }
 
 template <int SEMI, int M, int NL, int NP0, int P00, int P01, int NF0, int F00, int F01, int NP1, int P10, int P11,
@@ -101,13 +110,17 @@ __device__ __forceinline__ void sweep_step(const int32_t *__restrict__ rec, cons
   const uint16_t *la = reinterpret_cast<const uint16_t *>(rec + 8);
   const uint8_t *ls = reinterpret_cast<const uint8_t *>(rec + 12);
   uint32_t word = 0;
+  uint32_t base = laddr ^ (uint32_t)la[0];
+  uint32_t inb = base ^ (uint32_t)stab_row[lsub | (uint32_t)ls[0]];
 #pragma unroll 1
   for (int it = 0; it < r0.y; ++it) {
-    const uint32_t base = laddr ^ (uint32_t)la[it];
-    const uint32_t inb = base ^ (uint32_t)stab_row[lsub | (uint32_t)ls[it]];
     double R[N];
 #pragma unroll
     for (int j = 0; j < N; ++j) R[j] = sw_lds(sw_xor3(inb, lo[j & 3], hi[(j >> 2) & 3]));
+    // the next iteration's addresses (two dependent table reads) are looked up while this patch is in flight
+    const int itn = it + 1 < r0.y ? it + 1 : it;
+    const uint32_t base_n = laddr ^ (uint32_t)la[itn];
+    const uint32_t inb_n = base_n ^ (uint32_t)stab_row[lsub | (uint32_t)ls[itn]];
     uint32_t bits = 0;
     sweep_layer<SEMI, M, NP0, P00, P01, NF0, F00, F01, 0>(R, T0, bits);
     if (NL > 1) sweep_layer<SEMI, M, NP1, P10, P11, NF1, F10, F11, N * NF0>(R, T1, bits);
@@ -125,6 +138,8 @@ __device__ __forceinline__ void sweep_step(const int32_t *__restrict__ rec, cons
         }
       }
     }
+    base = base_n;
+    inb = inb_n;
   }
 }
 
@@ -290,6 +305,8 @@ int launch_sweep(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d
   const int grid = (int)(ctas < plan->sm_count ? ctas : plan->sm_count);
   if (plan->sw_maxt == 768)
     k_sweep<TQEC_SEMIRING_MAXPLUS, 768><<<grid, 32 * plan->sw_teams, plan->sw_smem, stream>>>(plan->sw, d_synd, B, d_corr, d_out, plan->d_sw_bp);
+  else if (plan->sw_maxt == 576)
+    k_sweep<TQEC_SEMIRING_MAXPLUS, 576><<<grid, 32 * plan->sw_teams, plan->sw_smem, stream>>>(plan->sw, d_synd, B, d_corr, d_out, plan->d_sw_bp);
   else if (plan->sw_maxt == 640)
     k_sweep<TQEC_SEMIRING_MAXPLUS, 640><<<grid, 32 * plan->sw_teams, plan->sw_smem, stream>>>(plan->sw, d_synd, B, d_corr, d_out, plan->d_sw_bp);
   else
@@ -358,9 +375,10 @@ int sweep_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &pr
   const size_t tv_b = ((size_t)s->n_tvals * 8 + 15) & ~(size_t)15;
   const size_t words_b = (((size_t)nsw << s->sg) * 8 + ((size_t)s->n_ss << s->sg) * 2 + 15) & ~(size_t)15;
   // register budget variant: 768 threads (80 registers), 640 (96) or 512 (128); TQEC_SWEEP_MAXT overrides the default
-  int maxt = 640;
-  if (const char *e = std::getenv("TQEC_SWEEP_MAXT")) { const int v = std::atoi(e); if (v == 768 || v == 640 || v == 512) maxt = v; }
+  int maxt = 512;
+  if (const char *e = std::getenv("TQEC_SWEEP_MAXT")) { const int v = std::atoi(e); if (v == 768 || v == 640 || v == 576 || v == 512) maxt = v; }
   const void *kern = maxt == 768 ? (const void *)k_sweep<TQEC_SEMIRING_MAXPLUS, 768>
+                   : maxt == 576 ? (const void *)k_sweep<TQEC_SEMIRING_MAXPLUS, 576>
                                  : (maxt == 640 ? (const void *)k_sweep<TQEC_SEMIRING_MAXPLUS, 640> : (const void *)k_sweep<TQEC_SEMIRING_MAXPLUS, 512>);
   p->sw_maxt = maxt;
   cudaFuncAttributes fa;
