@@ -275,17 +275,18 @@ def run_ours(args):
                 pass
         bytes_per_shot = 8 * (nsw + ncw + 1)
         hbm_achieved = bytes_per_shot * B / dur_s / 1e9
-        # DRAM traffic of the decode kernel per shot from the committed ncu capture (profiles/r1j_*: dram read + write over
-        # 6e5 shots); it is the back-pointer scratch streaming through HBM, the algorithmic I/O is 48 B per shot
-        traffic_per_shot = (2.518754e9 + 2.831403e9) / 6e5
+        # DRAM traffic of the decode kernel per shot from the newest committed ncu capture (back-pointer scratch streaming
+        # through HBM; the algorithmic I/O is 48 B per shot)
+        traffic_per_shot, traffic_src = _ncu_traffic_per_shot()
+        kname = "k_sweep<maxplus>" if geom.get("sweep") else "k_frontier_warp<maxplus>"
         roofline = {"bound": "fp64", "achieved": achieved, "peak": peak["dadd_tops"], "unit": "TFLOP/s",
-                    "frac": achieved / peak["dadd_tops"], "traffic": traffic_per_shot * B,
-                    "kernel": "k_frontier_warp<maxplus>", "ops_per_shot": mul + add,
+                    "frac": achieved / peak["dadd_tops"], "traffic": traffic_per_shot * B if traffic_per_shot else None,
+                    "kernel": kname, "ops_per_shot": mul + add,
                     "note": "FP64 CUDA-core pipe: one DADD per candidate + one DSETP per extra candidate of the EXECUTED "
                             "(frontier) schedule; max-plus has no tensor-core form",
                     "peak_source": "measured in this run by tqec_fp64_peak (register-resident DADD chains = the FP64 pipe's "
                                    "instruction rate; MEASURED_PEAKS.json has no FP64 entry)",
-                    "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per shot (profiles/r1j_ncu_frontier_v6_summary.csv) x shots per launch",
+                    "traffic_source": traffic_src,
                     "fp64_peaks": peak,
                     "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                             "frac": hbm_achieved / hbm_peak, "bytes_per_shot": bytes_per_shot, "peak_source": hbm_src}}
@@ -312,6 +313,25 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def _ncu_traffic_per_shot():
+    """(bytes per shot, source) from the newest profiles/*_ncu_sweep_*_summary.csv: dram read + write of one captured
+    launch divided by its shots (the header line of the file states the shot count)."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_sweep_*_summary.csv")))
+    if not files:
+        return None, "no ncu capture committed for this kernel"
+    txt = open(files[-1]).read()
+    m = re.search(r"shots=(\d+)", txt)
+    rd = re.search(r"dram__bytes_read.sum,Gbyte,([0-9.]+)", txt)
+    wr = re.search(r"dram__bytes_write.sum,Gbyte,([0-9.]+)", txt)
+    if not (m and rd and wr):
+        return None, f"could not parse {os.path.basename(files[-1])}"
+    per = (float(rd.group(1)) + float(wr.group(1))) * 1e9 / int(m.group(1))
+    return per, (f"ncu dram__bytes_read.sum + dram__bytes_write.sum per shot (profiles/{os.path.basename(files[-1])}) "
+                 f"x shots per launch")
 
 
 def cpu_baseline(tq, sch, syn_words, args):

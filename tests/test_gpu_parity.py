@@ -287,6 +287,30 @@ def test_dem_surface_memory(tq, name, n_dense):
     assert (res.sector == true_obs).mean() > 0.9
 
 
+def test_dem_from_generated_circuit(tq):
+    """BASELINE configs[3] proper: d=3 x 3 rounds rotated-surface memory circuit with circuit-level noise (depolarizing
+    after every Clifford, data depolarizing per round, measurement and reset flips) -> circuit.detector_error_model ->
+    TNMMAP on the GPU (12-bit frontier, wide warp teams) against the C port and the numpy recurrence."""
+    txt = tq.surface_memory_circuit(3, 3, "Z", after_clifford_depolarization=2e-3, before_round_data_depolarization=2e-3,
+                                    before_measure_flip_probability=2e-3, after_reset_flip_probability=2e-3)
+    dem = tq.detector_error_model(tq.parse_stim_string(txt))
+    assert dem.n_detectors == 24 and dem.n_observables == 1
+    ct = tq.compile(tq.TNMMAP(), dem)
+    B = 256
+    ep = tq.random_error_pattern(dem, seed=11, shots=B)
+    syn = tq.syndrome_extraction(ep, ct.tanner)
+    res = tq.decode(ct, syn)
+    assert syn == tq.syndrome_extraction(res.error_pattern, ct.tanner)
+    sch = ct.schedule
+    got = res.marginal.reshape(B, -1, order="F")
+    ref = cref.FrontierPlan(sch).run(syn.s)
+    assert np.allclose(got, ref, rtol=MAR_RTOL, atol=0)
+    ref2 = frontier.run(sch.factors, sch.checks, sch.order, 1, syn.s[:4], sch.n_vars)
+    assert np.allclose(got[:4], ref2, rtol=MAR_RTOL, atol=0)
+    true_obs = (ep[:, ct.l2q[0]].sum(axis=1) & 1)
+    assert (res.sector == true_obs).mean() > 0.97
+
+
 def test_property_full_size_d9(tq):
     """BASELINE config 3 shape (d=9, p=0.05) at a size the oracle cannot follow shot by shot: size-independent
     properties -- every correction reproduces its syndrome, decoding is idempotent on its own output's syndrome,
