@@ -47,6 +47,12 @@ def run(plan, menu, syndromes):
             for q in range(int(r[14])):
                 sb, pm = int(r[16 + q]) & 0xFFFF, (int(r[16 + q]) >> 16) & 0xFFFF
                 stab[i] ^= np.where(ssyn[:, sb] == 1, pm, 0)
+        late = np.zeros((n_ss, SG), dtype=np.int64)               # byte mask | 0x8000 when the late syndrome bit is set
+        for i in range(n_ss):
+            v = int(plan.rec[i][20])
+            if v >= 0:
+                sb, pm, fl = v & 0xFFFF, (v >> 16) & 0x3FFF, (v >> 30) & 1
+                late[i] = np.where(ssyn[:, sb] == 1, pm | (0x8000 if fl else 0x4000), 0)
         bp = np.zeros((max(plan.bp_words, 1), 32), dtype=np.uint64)
         for i in range(n_ss):
             r = [int(v) for v in plan.rec[i]]
@@ -70,12 +76,16 @@ def run(plan, menu, syndromes):
                     base = laddr ^ la[it]
                     sub = lsub | ls[it]
                     inb = base ^ int(stab[i, sub])
+                    lt_ = int(late[i, sub])
+                    outb = base ^ (lt_ & 0x3FFF)
                     R = [state[(inb ^ pa[j]) >> 3] for j in range(1 << M)]
                     bits = 0
                     off = 0
                     to = toff
-                    for pb, fm in layers:
+                    for li, (pb, fm) in enumerate(layers):
                         NP, NF = len(pb), len(fm)
+                        if li == 1 and (lt_ & 0x8000):
+                            to += 1 << (NP + NF)                 # the row-swapped copy of layer 1's table
                         out = [0.0] * (1 << M)
                         for j in range(1 << M):
                             pidx = sum(((j >> pb[q]) & 1) << q for q in range(NP))
@@ -100,7 +110,7 @@ def run(plan, menu, syndromes):
                         off += (1 << M) * NF
                         to += 1 << (NP + NF)
                     for j in range(1 << M):
-                        state[(base ^ pa[j]) >> 3] = R[j]
+                        state[(outb ^ pa[j]) >> 3] = R[j]
                     if bpp:
                         word |= bits << (bpp * (it % ipw))
                         if it % ipw == ipw - 1 or it == n_iter - 1:
@@ -123,6 +133,10 @@ def run(plan, menu, syndromes):
                 j = sum(((x >> pos[b]) & 1) << b for b in range(M))
                 lane = sum(((x >> t[12 + q]) & 1) << q for q in range(5))
                 it = sum(((x >> t[17 + q]) & 1) << q for q in range(nlb))
+                lsyn = 0
+                if t[7] >= 0:
+                    lsyn = int(ssyn[sub, t[7] & 0xFFFF])
+                    j ^= lsyn << (t[7] >> 16)
                 pbits = 0
                 if bpp:
                     pbits = (int(bp[wbase + it // ipw, lane]) >> (bpp * (it % ipw))) & ((1 << bpp) - 1)
@@ -131,7 +145,7 @@ def run(plan, menu, syndromes):
                     NP, NF, bpoff = t[o], t[o + 1], t[o + 2]
                     k = (pbits >> (bpoff + j * NF)) & ((1 << NF) - 1) if NF else 0
                     for q in range(NP):
-                        cfg_out[shot, t[o + 4 + 2 * q]] = (j >> t[o + 3 + 2 * q]) & 1
+                        cfg_out[shot, t[o + 4 + 2 * q]] = ((j >> t[o + 3 + 2 * q]) & 1) ^ (lsyn & (t[o + 11] >> q) & 1)
                     for q in range(NF):
                         cfg_out[shot, t[o + 8 + 2 * q]] = (k >> q) & 1
                         if (k >> q) & 1:

@@ -62,6 +62,7 @@ struct SweepDev {
   const uint64_t *head_cfg;
   int32_t head_bits[8];
   int32_t n_ss, W, sg, nh, nsw, ncw, bp_words, n_tvals, out_index0;
+  int32_t sync_mode;                // CTA barrier between teams: 0 none, 1 per group of 32 shots, 2 per pass
   int32_t off_states, off_rec, off_lanetab, off_tvals, off_words, words_bytes;   // shared-memory layout (bytes)
 };
 

@@ -89,7 +89,7 @@ template <int SEMI, int M, int NL, int NP0, int P00, int P01, int NF0, int F00, 
           int NF1, int F10, int F11>
 __device__ __forceinline__ void sweep_step(const int32_t *__restrict__ rec, const double *__restrict__ tvals,
                                            uint32_t st_abs, uint32_t lt, const uint16_t *__restrict__ stab_row,
-                                           uint32_t *__restrict__ bpt, int lane) {
+                                           const uint16_t *__restrict__ late_row, uint32_t *__restrict__ bpt, int lane) {
   constexpr int N = 1 << M;
   constexpr int NT0 = 1 << (NP0 + NF0), NT1 = NL > 1 ? (1 << (NP1 + NF1)) : 1;
   constexpr int BPP = SEMI == TQEC_SEMIRING_MAXPLUS ? N * (NF0 + (NL > 1 ? NF1 : 0)) : 0;
@@ -99,33 +99,41 @@ __device__ __forceinline__ void sweep_step(const int32_t *__restrict__ rec, cons
   const uint32_t a0 = (uint32_t)am.x & 0xffffu, a1 = (uint32_t)am.x >> 16, a2 = (uint32_t)am.y & 0xffffu, a3 = (uint32_t)am.y >> 16;
   const uint32_t lo[4] = {0u, a0, a1, a0 ^ a1};
   const uint32_t hi[4] = {0u, a2, a3, a2 ^ a3};
-  double T0[NT0], T1[NT1];
+  double T0[NT0];
   const double *tv = tvals + r0.z;
 #pragma unroll
   for (int i = 0; i < NT0; ++i) T0[i] = tv[i];
-#pragma unroll
-  for (int i = 0; i < NT1; ++i) T1[i] = NL > 1 ? tv[NT0 + i] : 0.0;
   const uint32_t laddr = st_abs ^ (lt & 0xffffu);
   const uint32_t lsub = lt >> 16;
   const uint16_t *la = reinterpret_cast<const uint16_t *>(rec + 8);
   const uint8_t *ls = reinterpret_cast<const uint8_t *>(rec + 12);
   uint32_t word = 0;
+  uint32_t sidx = lsub | (uint32_t)ls[0];
   uint32_t base = laddr ^ (uint32_t)la[0];
-  uint32_t inb = base ^ (uint32_t)stab_row[lsub | (uint32_t)ls[0]];
+  uint32_t inb = base ^ (uint32_t)stab_row[sidx];
 #pragma unroll 1
   for (int it = 0; it < r0.y; ++it) {
     double R[N];
 #pragma unroll
     for (int j = 0; j < N; ++j) R[j] = sw_lds(sw_xor3(inb, lo[j & 3], hi[(j >> 2) & 3]));
+    // late syndrome bit of the shot (a check opened by layer 0 and closed by layer 1): byte mask for the store address,
+    // bit 15 = use the row-swapped copy of layer 1's table
+    const uint32_t late = NL > 1 ? (uint32_t)late_row[sidx] : 0u;
+    double T1[NT1];
+    const double *t1 = tv + NT0 + ((late >> 15) ? NT1 : 0);
+#pragma unroll
+    for (int i = 0; i < NT1; ++i) T1[i] = NL > 1 ? t1[i] : 0.0;
+    const uint32_t outb = base ^ (late & 0x3fffu);
     // the next iteration's addresses (two dependent table reads) are looked up while this patch is in flight
     const int itn = it + 1 < r0.y ? it + 1 : it;
+    const uint32_t sidx_n = lsub | (uint32_t)ls[itn];
     const uint32_t base_n = laddr ^ (uint32_t)la[itn];
-    const uint32_t inb_n = base_n ^ (uint32_t)stab_row[lsub | (uint32_t)ls[itn]];
+    const uint32_t inb_n = base_n ^ (uint32_t)stab_row[sidx_n];
     uint32_t bits = 0;
     sweep_layer<SEMI, M, NP0, P00, P01, NF0, F00, F01, 0>(R, T0, bits);
     if (NL > 1) sweep_layer<SEMI, M, NP1, P10, P11, NF1, F10, F11, N * NF0>(R, T1, bits);
 #pragma unroll
-    for (int j = 0; j < N; ++j) sw_sts(sw_xor3(base, lo[j & 3], hi[(j >> 2) & 3]), R[j]);
+    for (int j = 0; j < N; ++j) sw_sts(sw_xor3(outb, lo[j & 3], hi[(j >> 2) & 3]), R[j]);
     if (BPP) {
       if (IPW == 1) {
         bpt[(r0.w + it) * 32 + lane] = bits;
@@ -140,6 +148,7 @@ __device__ __forceinline__ void sweep_step(const int32_t *__restrict__ rec, cons
     }
     base = base_n;
     inb = inb_n;
+    sidx = sidx_n;
   }
 }
 
@@ -168,17 +177,25 @@ k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, ui
   const int64_t team = (int64_t)blockIdx.x * NW + warp, n_teams = (int64_t)gridDim.x * NW;
   uint32_t *bp = bp_all + (size_t)team * NF * P.bp_words * 32;
 
-  for (int64_t g = team; g < n_groups; g += n_teams) {
+  // Every team of the CTA runs the same number of rounds and (optionally) meets the others at a CTA barrier before each
+  // pass / group: passes have identical instruction streams, so teams that start together stay on the same code and
+  // share instruction-cache lines; left alone they drift apart over a long launch (measured: -9 % on larger bodies).
+  const int64_t rounds = (n_groups + n_teams - 1) / n_teams;
+  for (int64_t rd = 0; rd < rounds; ++rd) {
+    const int64_t g = team + rd * n_teams;
+    const bool live = g < n_groups;
+    if (P.sync_mode == 1) __syncthreads();
     const int64_t group0 = g * 32, myshot = group0 + lane;
     uint64_t syn[4] = {0ull, 0ull, 0ull, 0ull};
-    if (myshot < B)
+    if (live && myshot < B)
 #pragma unroll
       for (int w = 0; w < 4; ++w)
         if (w < P.nsw) syn[w] = synd[myshot * P.nsw + w];
 
     for (int f = 0; f < NF; ++f) {
       const int64_t shot0 = group0 + ((int64_t)f << P.sg);
-      if (shot0 >= B) break;
+      if (P.sync_mode == 2) __syncthreads();
+      if (!live || shot0 >= B) continue;
       if ((lane >> P.sg) == f) {
         const int sub = lane & (SG - 1);
 #pragma unroll
@@ -206,17 +223,23 @@ k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, ui
           if ((sh_syn[sub * P.nsw + (sb >> 6)] >> (sb & 63)) & 1ull) v ^= c >> 16;
         }
         stab[idx] = (uint16_t)v;
+        uint32_t lv = 0;
+        if (r[20] >= 0) {
+          const uint32_t c = (uint32_t)r[20], sb = c & 0xffffu;
+          if ((sh_syn[sub * P.nsw + (sb >> 6)] >> (sb & 63)) & 1ull) lv = ((c >> 16) & 0x3fffu) | ((c >> 30) & 1u ? 0x8000u : 0x4000u);
+        }
+        stab[(P.n_ss << P.sg) + idx] = (uint16_t)lv;
       }
       __syncwarp();
       uint32_t *bpf = bp + (size_t)f * P.bp_words * 32;
       for (int i = 0; i < P.n_ss; ++i) {
         const int32_t *rec = sm_rec + i * SW_REC_INTS;
         const uint32_t lt = sm_lt[i * 32 + lane];
-        const uint16_t *srow = stab + (i << P.sg);
+        const uint16_t *srow = stab + (i << P.sg), *lrow = stab + ((P.n_ss + i) << P.sg);
         switch (rec[0]) {
 #define SW_CASE(ID, M, NL, NP0, P00, P01, NF0, F00, F01, NP1, P10, P11, NF1, F10, F11)                                  \
   case ID:                                                                                                             \
-    sweep_step<SEMI, M, NL, NP0, P00, P01, NF0, F00, F01, NP1, P10, P11, NF1, F10, F11>(rec, sm_tv, st_abs, lt, srow, bpf, lane); \
+    sweep_step<SEMI, M, NL, NP0, P00, P01, NF0, F00, F01, NP1, P10, P11, NF1, F10, F11>(rec, sm_tv, st_abs, lt, srow, lrow, bpf, lane); \
     break;
           TQEC_SWEEP_MENU(SW_CASE)
 #undef SW_CASE
@@ -229,7 +252,7 @@ k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, ui
     }
 
     // deferred traceback: lane q walks shot q of the group
-    {
+    if (live) {
       const int f = lane >> P.sg, sub = lane & (SG - 1);
       const uint32_t *bpq = bp + (size_t)f * P.bp_words * 32;
       uint64_t cfg[4] = {0ull, 0ull, 0ull, 0ull};
@@ -237,7 +260,7 @@ k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, ui
       for (int i = P.n_ss - 1; i >= 0; --i) {
         const int32_t *t = P.tb + (size_t)i * SW_TB_INTS;
         const int4 t0 = __ldg(reinterpret_cast<const int4 *>(t));          // M, layers, loop bits, bpp
-        const int4 t1 = __ldg(reinterpret_cast<const int4 *>(t + 4));      // wbase, ipw, closed, -
+        const int4 t1 = __ldg(reinterpret_cast<const int4 *>(t + 4));      // wbase, ipw, closed, late (bit | patch bit << 16)
         const int4 tp = __ldg(reinterpret_cast<const int4 *>(t + 8));      // positions of patch bits
         const int pos[4] = {tp.x, tp.y, tp.z, tp.w};
         uint32_t j = 0, ln = 0, it = 0, pm = 0;
@@ -247,6 +270,13 @@ k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, ui
 #pragma unroll
         for (int q = 0; q < 5; ++q) ln |= ((x >> __ldg(t + 12 + q)) & 1u) << q;
         for (int q = 0; q < t0.z; ++q) it |= ((x >> __ldg(t + 17 + q)) & 1u) << q;
+        uint32_t lsyn = 0;
+        if (t1.w >= 0) {
+          const int sb = t1.w & 0xffff, w = sb >> 6;
+          const uint64_t sw = w == 0 ? syn[0] : (w == 1 ? syn[1] : (w == 2 ? syn[2] : syn[3]));
+          lsyn = (uint32_t)((sw >> (sb & 63)) & 1ull);
+          j ^= lsyn << (t1.w >> 16);
+        }
         uint32_t pb = 0;
         if (t0.w) {
           const uint32_t wd = __ldcg(bpq + (size_t)(t1.x + it / t1.y) * 32 + ln);
@@ -254,11 +284,11 @@ k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, ui
         }
         for (int li = t0.y - 1; li >= 0; --li) {
           const int32_t *L = t + 30 + 12 * li;
-          const int np = __ldg(L), nf = __ldg(L + 1), bo = __ldg(L + 2);
+          const int np = __ldg(L), nf = __ldg(L + 1), bo = __ldg(L + 2), flipm = __ldg(L + 11);
           const uint32_t k = nf ? ((pb >> (bo + j * nf)) & ((1u << nf) - 1u)) : 0u;
           for (int q = 0; q < np; ++q) {
             const int pbit = __ldg(L + 3 + 2 * q), v = __ldg(L + 4 + 2 * q);
-            const uint64_t bitv = (uint64_t)((j >> pbit) & 1u) << (v & 63);
+            const uint64_t bitv = (uint64_t)(((j >> pbit) & 1u) ^ (lsyn & ((uint32_t)flipm >> q) & 1u)) << (v & 63);
             const int w = v >> 6;
             cfg[0] |= w == 0 ? bitv : 0ull; cfg[1] |= w == 1 ? bitv : 0ull;
             cfg[2] |= w == 2 ? bitv : 0ull; cfg[3] |= w == 3 ? bitv : 0ull;
@@ -354,7 +384,9 @@ int sweep_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &pr
   SweepDev &D = p->sw;
   std::memset(&D, 0, sizeof(D));
   D.n_ss = s->n_ss; D.W = s->W; D.sg = s->sg; D.nh = s->n_head_bits; D.nsw = nsw; D.ncw = ncw;
-  D.bp_words = s->bp_words > 0 ? s->bp_words : 1; D.n_tvals = s->n_tvals; D.out_index0 = s->out_index[0];
+  D.bp_words = s->bp_words > 0 ? s->bp_words : 1;
+  D.sync_mode = 1;
+  if (const char *e = std::getenv("TQEC_SWEEP_SYNC")) { const int v = std::atoi(e); if (v >= 0 && v <= 2) D.sync_mode = v; } D.n_tvals = s->n_tvals; D.out_index0 = s->out_index[0];
   for (int j = 0; j < s->n_head_bits; ++j) D.head_bits[j] = s->head_bits[j];
   const size_t nhp = (size_t)1 << s->n_head_bits, ne = (size_t)1 << s->W;
   int rc;
@@ -373,7 +405,7 @@ int sweep_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &pr
   const size_t gap = (8192 - (size_t)reserved % 8192) % 8192;
   const size_t rec_b = ((size_t)s->n_ss * SW_REC_INTS * 4 + 15) & ~(size_t)15, lt_b = (size_t)s->n_ss * 128;
   const size_t tv_b = ((size_t)s->n_tvals * 8 + 15) & ~(size_t)15;
-  const size_t words_b = (((size_t)nsw << s->sg) * 8 + ((size_t)s->n_ss << s->sg) * 2 + 15) & ~(size_t)15;
+  const size_t words_b = (((size_t)nsw << s->sg) * 8 + ((size_t)s->n_ss << s->sg) * 4 + 15) & ~(size_t)15;   // syndromes, early + late masks
   // register budget variant: 768 threads (80 registers), 640 (96) or 512 (128); TQEC_SWEEP_MAXT overrides the default
   int maxt = 512;
   if (const char *e = std::getenv("TQEC_SWEEP_MAXT")) { const int v = std::atoi(e); if (v == 768 || v == 640 || v == 576 || v == 512) maxt = v; }

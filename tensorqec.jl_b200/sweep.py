@@ -44,8 +44,13 @@ TB_INTS = 64            # traceback record per super-step (int32)
 MENU: List[tuple] = [
     (2, (((), (1, 2)),)),
     (2, (((0,), (2,)),)),
+    (2, (((0,), (2,)), ((), (1, 2)))),
+    (2, (((0,), (2,)), ((), (2, 1)))),
+    (2, (((0,), (2,)), ((0,), (2,)))),
     (3, (((), (1, 2)), ((0,), (4,)))),
     (3, (((), (3, 4)),)),
+    (3, (((0,), (6,)),)),
+    (3, (((0,), (2,)), ((), (5, 2)))),
     (3, (((0,), (2,)), ((1,), (5,)))),
     (3, (((0,), (6,)), ((1,), (1,)))),
     (4, (((0,), (6,)), ((1,), (9,)))),
@@ -82,6 +87,7 @@ class SuperStep:
     lanepos: List[int] = field(default_factory=list)    # 5 positions spanned by the lane id
     looppos: List[int] = field(default_factory=list)    # active positions walked by the iteration loop
     conflict: bool = False
+    late: Optional[Tuple[int, int]] = None     # (syndrome bit, patch bit): check opened by layer 0 and closed by layer 1
     wbase: int = 0                             # first back-pointer word (per lane) of the step inside a pass
     bpp: int = 0                               # back-pointer bits per patch
     n_words: int = 0
@@ -362,13 +368,19 @@ def lower_sweep(sch: S.Schedule, max_head_bits: int = MAX_HEAD_BITS) -> Optional
                 return dict.get(self, d, -1)
         menu_ix = _Any(menu_ix)
 
+    allow_late = True
+
     def match(group):
         chains = sorted({ch for g in group for ch in g["chains"]})
         if len(chains) > MAX_PATCH:
             return None
-        if len(group) == 2 and {ch for _, ch in group[0]["pinned"]} & {ch for _, ch in group[1]["closed"]}:
-            return None          # a check opened by the first layer and closed by the second: its syndrome bit cannot be
-                                 # folded into the load address (the slot still holds the first layer's closed check)
+        if len(group) == 2:
+            # a check opened by the first layer and closed by the second cannot be folded into the load address (its
+            # slot still holds the first layer's closed check): its syndrome bit is applied late -- to the second
+            # layer's table rows and to the store address (see SuperStep.late); at most one such check per super-step
+            both = {ch for _, ch in group[0]["pinned"]} & {ch for _, ch in group[1]["closed"]}
+            if len(both) > 1 or (both and not allow_late):
+                return None
         if sch.semiring == S.MAXPLUS and sum(len(g["free"]) for g in group) << len(chains) > 32:
             return None                                        # back-pointers of a patch must fit one 32-bit word
         d, perm = _canonical([(g["pinned"], g["free"]) for g in group], chains)
@@ -376,19 +388,24 @@ def lower_sweep(sch: S.Schedule, max_head_bits: int = MAX_HEAD_BITS) -> Optional
             return None
         return menu_ix[d], perm
 
+    # pairing: fewest super-steps (dynamic programme over the step list; a pair must match a menu shape)
+    nr = len(raw)
+    single = [match(raw[k:k + 1]) for k in range(nr)]
+    pair = [match(raw[k:k + 2]) if k + 1 < nr else None for k in range(nr)]
+    if any(m is None for m in single):
+        return None
+    best = [0] * (nr + 2)
+    take = [1] * nr
+    for k in range(nr - 1, -1, -1):
+        best[k] = 1 + best[k + 1]
+        if pair[k] is not None and 1 + best[k + 2] <= best[k]:
+            best[k], take[k] = 1 + best[k + 2], 2
+
     ssteps: List[SuperStep] = []
     k = 0
-    while k < len(raw):
-        pick = None
-        if k + 1 < len(raw):
-            m = match(raw[k:k + 2])
-            if m is not None:
-                pick = (2, m)
-        if pick is None:
-            m = match(raw[k:k + 1])
-            if m is None:
-                return None
-            pick = (1, m)
+    while k < nr:
+        cnt = take[k]
+        pick = (cnt, pair[k] if cnt == 2 else single[k])
         cnt, (mi, perm) = pick
         bit = {ch: b for b, ch in enumerate(perm)}
         layers = []
@@ -410,6 +427,13 @@ def lower_sweep(sch: S.Schedule, max_head_bits: int = MAX_HEAD_BITS) -> Optional
                     T[(pidx << NF) | kk] = st.table[a]
             layers.append(Layer(g["step"], g["fi"], tuple(f.vars), pinned, free, closed, T))
         ss = SuperStep(layers, list(perm), mi)
+        if cnt == 2:
+            both = {pb for _, pb in layers[0].pinned} & {cb for _, cb in layers[1].closed}
+            if both:
+                b = both.pop()
+                sb = [s_ for s_, cb in layers[1].closed if cb == b][0]
+                ss.late = (sb, b)
+                layers[1].closed = [(s_, cb) for s_, cb in layers[1].closed if cb != b]
         M = len(perm)
         ss.bpp = sum((1 << M) * len(l.free) for l in layers) if sch.semiring == S.MAXPLUS else 0
         ssteps.append(ss)
@@ -451,6 +475,8 @@ def lower_sweep(sch: S.Schedule, max_head_bits: int = MAX_HEAD_BITS) -> Optional
             for _, cb in l.closed:
                 if cb not in reused:
                     alive.discard(ss.chains[cb])
+        if ss.late is not None and ss.late[1] not in {pb for _, pb in ss.layers[1].pinned}:
+            alive.discard(ss.chains[ss.late[1]])
     out_index = [0]
     if sch.semiring == S.SUMPROD:
         obs_pos = [0] * sch.n_obs
@@ -500,6 +526,15 @@ def _encode(p: SweepPlan):
         r[2] = len(tvals)
         for l in ss.layers:
             tvals += [float(x) for x in l.T]
+        flipmask = 0
+        if ss.late is not None:
+            # second copy of layer 1's table with the rows of the pinned variable at the late bit swapped
+            l = ss.layers[1]
+            NF = len(l.free)
+            for q, (_, pb) in enumerate(l.pinned):
+                if pb == ss.late[1]:
+                    flipmask |= 1 << q
+            tvals += [float(l.T[((ix >> NF) ^ flipmask) << NF | (ix & ((1 << NF) - 1))]) for ix in range(len(l.T))]
         r[3] = ss.wbase
         ain = [phys(1 << ss.pos[b]) << 3 for b in range(M)] + [0] * (4 - M)
         r[4] = ain[0] | (ain[1] << 16)
@@ -522,6 +557,9 @@ def _encode(p: SweepPlan):
         r[14] = len(closed)
         for q, (sb, pos) in enumerate(closed):
             r[16 + q] = sb | (phys(1 << pos) << 19)
+        r[20] = -1
+        if ss.late is not None:
+            r[20] = ss.late[0] | (phys(1 << ss.pos[ss.late[1]]) << 19) | (1 << 30 if flipmask else 0)
         for lane in range(32):
             x = 0
             for q, pos in enumerate(ss.lanepos):
@@ -532,6 +570,7 @@ def _encode(p: SweepPlan):
         t[0], t[1], t[2], t[3], t[4] = M, len(ss.layers), len(ss.looppos), ss.bpp, ss.wbase
         t[5] = (32 // ss.bpp) if ss.bpp else 0
         t[6] = len(closed)
+        t[7] = -1 if ss.late is None else (ss.late[0] | (ss.late[1] << 16))
         for b in range(4):
             t[8 + b] = ss.pos[b] if b < M else -1
         for q in range(5):
@@ -552,6 +591,7 @@ def _encode(p: SweepPlan):
                     t[o + 7 + 2 * q], t[o + 8 + 2 * q] = l.free[q][1], l.vars[l.free[q][0]]
                 else:
                     t[o + 7 + 2 * q], t[o + 8 + 2 * q] = 0, -1
+            t[o + 11] = flipmask if (li == 1 and ss.late is not None) else 0
             bpoff += (1 << M) * len(l.free)
     p.rec, p.tb, p.lanetab = rec, tb, lanetab
     p.tvals = np.asarray(tvals if tvals else [0.0], dtype=np.float64)
