@@ -94,6 +94,9 @@ struct tqec_plan {
   void *d_io[4];
   size_t io_cap[4];
   cudaStream_t stream;
+  // host-pointer entry points: copy-in / copy-out streams and per-chunk events of the three-stage pipeline
+  cudaStream_t s_in, s_out;
+  cudaEvent_t ev_in[2], ev_cmp[2];
 };
 
 struct tqec_gf2 {

@@ -1092,6 +1092,12 @@ extern "C" int tqec_plan_destroy(tqec_plan *p) {
   sweep_destroy(p);
   for (int i = 0; i < 4; ++i) cudaFree(p->d_io[i]);
   if (p->stream) cudaStreamDestroy(p->stream);
+  if (p->s_in) cudaStreamDestroy(p->s_in);
+  if (p->s_out) cudaStreamDestroy(p->s_out);
+  for (int i = 0; i < 2; ++i) {
+    if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
+    if (p->ev_cmp[i]) cudaEventDestroy(p->ev_cmp[i]);
+  }
   delete p;
   return TQEC_OK;
 }
@@ -1131,6 +1137,17 @@ extern "C" int tqec_decode_marginal_dev(tqec_plan *p, const uint64_t *d_synd, in
   return launch_decode(p, d_synd, B, nullptr, d_mar, d_argmax, (cudaStream_t)stream);
 }
 
+static int ensure_pipeline(tqec_plan *p) {
+  if (p->s_in) return TQEC_OK;
+  TQEC_CUDA(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
+  TQEC_CUDA(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    TQEC_CUDA(cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
+    TQEC_CUDA(cudaEventCreateWithFlags(&p->ev_cmp[i], cudaEventDisableTiming));
+  }
+  return TQEC_OK;
+}
+
 extern "C" int tqec_decode_map(tqec_plan *p, const uint64_t *synd, int64_t B, uint64_t *corr_out, double *logp_out) {
   TQEC_REQUIRE(p && p->semiring == TQEC_SEMIRING_MAXPLUS, "tqec_decode_map: plan is not a max-plus (TNMAP) plan");
   TQEC_REQUIRE(B >= 0 && (B == 0 || (synd && corr_out)), "tqec_decode_map: NULL buffer");
@@ -1141,10 +1158,28 @@ extern "C" int tqec_decode_map(tqec_plan *p, const uint64_t *synd, int64_t B, ui
   if ((rc = ensure_cap(&p->d_io[0], &p->io_cap[0], sb))) return rc;
   if ((rc = ensure_cap(&p->d_io[1], &p->io_cap[1], cb))) return rc;
   if ((rc = ensure_cap(&p->d_io[2], &p->io_cap[2], lb))) return rc;
-  TQEC_CUDA(cudaMemcpyAsync(p->d_io[0], synd, sb, cudaMemcpyHostToDevice, p->stream));
-  if ((rc = launch_decode(p, (const uint64_t *)p->d_io[0], B, (uint64_t *)p->d_io[1], (double *)p->d_io[2], nullptr, p->stream))) return rc;
-  TQEC_CUDA(cudaMemcpyAsync(corr_out, p->d_io[1], cb, cudaMemcpyDeviceToHost, p->stream));
-  if (logp_out) TQEC_CUDA(cudaMemcpyAsync(logp_out, p->d_io[2], lb, cudaMemcpyDeviceToHost, p->stream));
+  // Chunked three-stage pipeline: H2D of chunk c+1 and D2H of chunk c-1 overlap the decode of chunk c (three streams,
+  // one event pair per chunk; the device buffers hold the whole batch, so chunks never alias).
+  if ((rc = ensure_pipeline(p))) return rc;
+  const int64_t CH = (int64_t)1 << 21;
+  const int nsw = p->dev.nsw, ncw = p->dev.ncw;
+  const uint64_t *d_syn = (const uint64_t *)p->d_io[0];
+  uint64_t *d_cor = (uint64_t *)p->d_io[1];
+  double *d_lp = (double *)p->d_io[2];
+  int slot = 0;
+  for (int64_t o = 0; o < B; o += CH, slot ^= 1) {
+    const int64_t n = B - o < CH ? B - o : CH;
+    TQEC_CUDA(cudaMemcpyAsync((void *)(d_syn + o * nsw), synd + o * nsw, (size_t)n * nsw * 8, cudaMemcpyHostToDevice, p->s_in));
+    TQEC_CUDA(cudaEventRecord(p->ev_in[slot], p->s_in));
+    TQEC_CUDA(cudaStreamWaitEvent(p->stream, p->ev_in[slot], 0));
+    if ((rc = launch_decode(p, d_syn + o * nsw, n, d_cor + o * ncw, d_lp + o, nullptr, p->stream))) return rc;
+    TQEC_CUDA(cudaEventRecord(p->ev_cmp[slot], p->stream));
+    TQEC_CUDA(cudaStreamWaitEvent(p->s_out, p->ev_cmp[slot], 0));
+    TQEC_CUDA(cudaMemcpyAsync(corr_out + o * ncw, d_cor + o * ncw, (size_t)n * ncw * 8, cudaMemcpyDeviceToHost, p->s_out));
+    if (logp_out) TQEC_CUDA(cudaMemcpyAsync(logp_out + o, d_lp + o, (size_t)n * 8, cudaMemcpyDeviceToHost, p->s_out));
+    // (an event slot is re-recorded two chunks later; a stream wait binds to the record that preceded it)
+  }
+  TQEC_CUDA(cudaStreamSynchronize(p->s_out));
   TQEC_CUDA(cudaStreamSynchronize(p->stream));
   return TQEC_OK;
 }

@@ -61,6 +61,38 @@ def test_tnmap_surface_matches_oracle_bit_exact(tq, d, B):
     assert tq.syndrome_extraction(res.error_pattern, t) == tq.CSSSyndrome(sx, sz)
 
 
+@pytest.mark.parametrize("d", [7, 9])
+def test_sweep_kernel_edge_cases(tq, d, monkeypatch):
+    """k_sweep (in-place patch sweep): per-qubit noise (unique maximisers), batch sizes that do not fill a pass / a group
+    of 32 shots, the all-zero and all-one syndromes, and bit-identity with the general kernels on the same unfused
+    schedule (TQEC_NO_SWEEP routes the plan through k_frontier_warp)."""
+    from tensorqec.jl_b200 import _cabi
+    rng = np.random.default_rng(d)
+    n = d * d
+    em = tq.IndependentDepolarizingError(rng.uniform(0.01, 0.1, n), rng.uniform(0.01, 0.1, n), rng.uniform(0.01, 0.1, n))
+    t = tq.CSSTannerGraph(tq.SurfaceCode(d, d))
+    ct = tq.compile(tq.TNMAP(), t, em)
+    sch = ct.cd.schedule
+    assert ct.cd.plan.query(_cabi.Q_SWEEP) == 1 and getattr(sch, "sweep", None) is not None
+    ex, ez, sx, sz = _syndromes(t, em, 77, 1000)
+    syn = np.concatenate([sx, sz], axis=1)
+    syn[0] = 0
+    syn[1] = 1
+    oracle_plan = cref.FrontierPlan(sch)
+    for B in (1, 2, 31, 33, 1000):
+        corr, logp = ct.cd.plan.decode_map(tq.pack_bits(syn[:B]))
+        lp, cfg = oracle_plan.run(syn[:B])
+        assert np.array_equal(tq.unpack_bits(corr, 2 * n), cfg) and np.array_equal(logp, lp)
+    corr, logp = ct.cd.plan.decode_map(tq.pack_bits(syn))
+    # same schedule through the general kernels
+    monkeypatch.setenv("TQEC_NO_SWEEP", "1")
+    plan2 = _cabi.Plan(sch, 0)
+    assert plan2.query(_cabi.Q_SWEEP) == 0
+    corr2, logp2 = plan2.decode_map(tq.pack_bits(syn))
+    assert np.array_equal(corr, corr2) and np.array_equal(logp, logp2)
+    plan2.close()
+
+
 def test_tnmap_matches_dense_reference_value(tq):
     """MAP value equals the dense (reference-style) contraction; the pattern has that weight and the syndrome."""
     d = 5
