@@ -21,12 +21,21 @@ struct TqecError <: Exception
 end
 check(rc::Cint) = rc == 0 ? nothing : throw(TqecError(rc, unsafe_string(ccall((:tqec_last_error, LIB), Cstring, ()))))
 
+# mirror of `tqec_sweep_desc` (include/tqec.h): optional second lowering of a max-plus plan (in-place patch sweep,
+# tensorqec.jl_b200/sweep.py:lower_sweep); pass C_NULL in PlanDesc.sweep to run the general kernels
+struct SweepDesc
+    W::Int32; sg::Int32; n_ss::Int32; n_head_bits::Int32; bp_words::Int32; n_tvals::Int32
+    rec::Ptr{Int32}; tb::Ptr{Int32}; lanetab::Ptr{UInt32}; tvals::Ptr{Float64}
+    head_bits::Ptr{Int32}; head_state::Ptr{Float64}; head_cfg::Ptr{UInt64}; out_index::Ptr{Int32}
+end
+
 # mirror of `tqec_plan_desc` (include/tqec.h)
 struct PlanDesc
     semiring::Int32; n_vars::Int32; n_checks::Int32; n_obs::Int32; n_steps::Int32; w_max::Int32
     hdr::Ptr{Int32}; ints::Ptr{Int32}; n_ints::Int64
     tables::Ptr{Float64}; n_tables::Int64
     obs_slot::Ptr{Int32}; device::Int32
+    sweep::Ptr{SweepDesc}
 end
 
 mutable struct Plan
@@ -35,10 +44,18 @@ mutable struct Plan
     function Plan(sch, device::Integer)          # `sch`: the lowered schedule (see `lower` below)
         href = Ref{Ptr{Cvoid}}(C_NULL)
         GC.@preserve sch begin
-            d = PlanDesc(sch.semiring, sch.n_vars, sch.n_checks, sch.n_obs, sch.n_steps, sch.w_max,
-                         pointer(sch.hdr), pointer(sch.ints), length(sch.ints),
-                         pointer(sch.tables), length(sch.tables), pointer(sch.obs_slot), device)
-            check(ccall((:tqec_plan_create, LIB), Cint, (Ref{PlanDesc}, Ref{Ptr{Cvoid}}), d, href))
+            sw = sch.sweep                         # `nothing`, or the tables of `lower_sweep` (all plain Vectors)
+            swref = sw === nothing ? nothing :
+                Ref(SweepDesc(sw.W, sw.sg, sw.n_ss, length(sw.head_bits), sw.bp_words, length(sw.tvals),
+                              pointer(sw.rec), pointer(sw.tb), pointer(sw.lanetab), pointer(sw.tvals),
+                              pointer(sw.head_bits), pointer(sw.head_state), pointer(sw.head_cfg), pointer(sw.out_index)))
+            GC.@preserve sw swref begin
+                swp = swref === nothing ? Ptr{SweepDesc}(C_NULL) : Base.unsafe_convert(Ptr{SweepDesc}, swref)
+                d = PlanDesc(sch.semiring, sch.n_vars, sch.n_checks, sch.n_obs, sch.n_steps, sch.w_max,
+                             pointer(sch.hdr), pointer(sch.ints), length(sch.ints),
+                             pointer(sch.tables), length(sch.tables), pointer(sch.obs_slot), device, swp)
+                check(ccall((:tqec_plan_create, LIB), Cint, (Ref{PlanDesc}, Ref{Ptr{Cvoid}}), d, href))
+            end
         end
         p = new(href[], cld(max(sch.n_checks, 1), 64), cld(max(sch.n_vars, 1), 64), sch.n_obs)
         finalizer(x -> ccall((:tqec_plan_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), p)
