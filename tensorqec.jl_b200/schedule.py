@@ -367,6 +367,9 @@ def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_v
         touched, opened, closing = plan[t]
         w_in = len(live)
         full = live + opened
+        if len(full) > 40:
+            raise ValueError(f"frontier needs {len(full)} bits > {max_width}: the schedule does not fit the on-chip state "
+                             f"(choose a sweep-like absorption order)")
         pos = {c: k for k, c in enumerate(full)}
         closed = sorted((pos[c], checks[c].index) for c in closing)
         m = []
