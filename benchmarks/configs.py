@@ -95,7 +95,7 @@ def main():
         for B in (1, 10, 100, 1000, 10_000, 100_000, 1_000_000):
             css_case(f"config5 {name} TNMAP batch sweep", code, 0.05, B, 5, out)
     # TNMMAP, CSS
-    for d, B in ((3, 1_000_000), (5, 1_000_000), (7, 200_000)):
+    for d, B in ((3, 1_000_000), (5, 1_000_000), (7, 1_000_000), (9, 400_000)):
         t = tq.CSSTannerGraph(tq.SurfaceCode(d, d))
         em = tq.iid_error(0.05, t)
         ct = tq.compile(tq.TNMMAP(), t, em)
@@ -110,8 +110,15 @@ def main():
     # DEM TNMMAP (config 4 input format): the reference's fixture + synthetic surface-memory DEMs (benchmarks/make_dem.py)
     for fname, label, B in (("dem.dem", "reference DEM fixture (21 mechanisms, 6 detectors)", 1_000_000),
                             ("surface_d3_r3_phenom.dem", "surface memory d=3 x 3 rounds, phenomenological", 1_000_000),
+                            ("generated:3:3", "surface memory d=3 x 3 rounds, circuit-level noise p=1e-3 (circuit.py)", 100_000),
                             ("surface_d5_r5_phenom.dem", "surface memory d=5 x 5 rounds, phenomenological", 200_000)):
-        dem = tq.parse_dem_file(os.path.join(ROOT, "tests", "golden", fname))
+        if fname.startswith("generated:"):
+            _, dd, rr = fname.split(":")
+            dem = tq.detector_error_model(tq.parse_stim_string(tq.surface_memory_circuit(
+                int(dd), int(rr), "Z", after_clifford_depolarization=1e-3, before_round_data_depolarization=1e-3,
+                before_measure_flip_probability=1e-3, after_reset_flip_probability=1e-3)))
+        else:
+            dem = tq.parse_dem_file(os.path.join(ROOT, "tests", "golden", fname))
         ct = tq.compile(tq.TNMMAP(), dem)
         ep = _cabi.sample_errors(_cabi.MODEL_FLIP, [np.asarray(dem.error_rates)], 3, 0, B)
         syn = _cabi.GF2Matrix(ct.tanner.H).apply(ep)

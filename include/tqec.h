@@ -68,14 +68,14 @@ enum {
 typedef struct tqec_plan tqec_plan; /* a compiled schedule resident on one device      */
 typedef struct tqec_gf2 tqec_gf2;   /* a bit-packed GF(2) matrix resident on one device */
 
-/* Optional second lowering of a max-plus plan: the in-place patch sweep (tensorqec.jl_b200/sweep.py, executed by
+/* Optional second lowering of a plan (either semiring): the in-place patch sweep (tensorqec.jl_b200/sweep.py, executed by
  * k_sweep).  Same recurrence, same results bit for bit; plans that carry it decode through k_sweep unless the
  * environment variable TQEC_NO_SWEEP is set.  All tables are host pointers copied by tqec_plan_create. */
 typedef struct {
   int32_t W;               /* slot bits of the state index                                        */
   int32_t sg;              /* log2(shots per team pass); W + sg = 10                               */
   int32_t n_ss;            /* super-steps                                                          */
-  int32_t n_head_bits;     /* syndrome bits the tabulated head depends on (<= 8)                   */
+  int32_t n_head_bits;     /* syndrome bits the tabulated head depends on (<= 12)                  */
   int32_t bp_words;        /* back-pointer words per lane per pass                                 */
   int32_t n_tvals;
   const int32_t *rec;      /* n_ss * 32: forward records                                           */
@@ -84,8 +84,8 @@ typedef struct {
   const double *tvals;     /* pooled layer tables                                                  */
   const int32_t *head_bits;/* n_head_bits syndrome bit indices                                     */
   const double *head_state;/* 2^n_head_bits * 2^W state values after the head                      */
-  const uint64_t *head_cfg;/* 2^n_head_bits * 2^W * ceil(n_vars/64) partial configurations         */
-  const int32_t *out_index;/* index of the final entry                                             */
+  const uint64_t *head_cfg;/* max-plus: 2^n_head_bits * 2^W * ceil(n_vars/64) partial configurations   */
+  const int32_t *out_index;/* 2^n_obs state indices of the output entries (max-plus: one)              */
 } tqec_sweep_desc;
 
 typedef struct {

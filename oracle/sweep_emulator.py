@@ -13,7 +13,7 @@ MAXPLUS = 0
 
 def _layers_of(menu_entry):
     M, layers = menu_entry
-    return M, [(list(pb), list(fm)) for pb, fm in layers]
+    return M, [(list(l[0]), list(l[1]), list(l[2]) if len(l) > 2 else [0] * len(l[0])) for l in layers]
 
 
 def run(plan, menu, syndromes):
@@ -66,7 +66,7 @@ def run(plan, menu, syndromes):
                 for b in range(M):
                     if (j >> b) & 1:
                         pa[j] ^= ain[b]
-            bpp = sum((1 << M) * len(fm) for _, fm in layers) if maxplus else 0
+            bpp = sum((1 << M) * len(fm) for _, fm, _ in layers) if maxplus else 0
             ipw = 32 // bpp if bpp else 1
             for lane in range(32):
                 lt = int(plan.lanetab[i, lane])
@@ -82,7 +82,7 @@ def run(plan, menu, syndromes):
                     bits = 0
                     off = 0
                     to = toff
-                    for li, (pb, fm) in enumerate(layers):
+                    for li, (pb, fm, pk) in enumerate(layers):
                         NP, NF = len(pb), len(fm)
                         if li == 1 and (lt_ & 0x8000):
                             to += 1 << (NP + NF)                 # the row-swapped copy of layer 1's table
@@ -90,8 +90,12 @@ def run(plan, menu, syndromes):
                         for j in range(1 << M):
                             pidx = sum(((j >> pb[q]) & 1) << q for q in range(NP))
                             best, bk = None, 0
+                            pflip = 0
+                            for q in range(NP):
+                                if (j >> pb[q]) & 1:
+                                    pflip ^= pk[q]
                             for k in range(1 << NF):
-                                src = j
+                                src = j ^ pflip
                                 for f in range(NF):
                                     if (k >> f) & 1:
                                         src ^= fm[f]
@@ -141,11 +145,15 @@ def run(plan, menu, syndromes):
                 if bpp:
                     pbits = (int(bp[wbase + it // ipw, lane]) >> (bpp * (it % ipw))) & ((1 << bpp) - 1)
                 for li in range(nl - 1, -1, -1):
-                    o = 30 + 12 * li
+                    o = 30 + 14 * li
                     NP, NF, bpoff = t[o], t[o + 1], t[o + 2]
                     k = (pbits >> (bpoff + j * NF)) & ((1 << NF) - 1) if NF else 0
+                    pflip = 0
                     for q in range(NP):
                         cfg_out[shot, t[o + 4 + 2 * q]] = ((j >> t[o + 3 + 2 * q]) & 1) ^ (lsyn & (t[o + 11] >> q) & 1)
+                        if (j >> t[o + 3 + 2 * q]) & 1:
+                            pflip ^= t[o + 12 + q]
+                    j ^= pflip
                     for q in range(NF):
                         cfg_out[shot, t[o + 8 + 2 * q]] = (k >> q) & 1
                         if (k >> q) & 1:

@@ -60,8 +60,9 @@ struct SweepDev {
   const uint32_t *lanetab;
   const double *tvals, *head_state;
   const uint64_t *head_cfg;
-  int32_t head_bits[8];
-  int32_t n_ss, W, sg, nh, nsw, ncw, bp_words, n_tvals, out_index0;
+  int32_t head_bits[12];
+  int32_t out_index[16];            // state index of output entry i (max-plus: entry 0 only)
+  int32_t n_ss, W, sg, nh, nsw, ncw, bp_words, n_tvals, n_obs;
   int32_t sync_mode;                // CTA barrier between teams: 0 none, 1 per group of 32 shots, 2 per pass
   int32_t off_states, off_rec, off_lanetab, off_tvals, off_words, words_bytes;   // shared-memory layout (bytes)
 };
@@ -114,7 +115,8 @@ namespace tqec {
 int ensure_cap(void **ptr, size_t *cap, size_t bytes);
 int launch_decode(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d_corr, double *d_out,
                   int32_t *d_argmax, cudaStream_t stream);
-int launch_sweep(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d_corr, double *d_out, cudaStream_t stream);
+int launch_sweep(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d_corr, double *d_out, int32_t *d_argmax,
+                 cudaStream_t stream);
 int sweep_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &prop);
 void sweep_destroy(tqec_plan *p);
 int launch_gf2_apply(tqec_gf2 *m, const uint64_t *d_in, int64_t B, uint64_t *d_out, cudaStream_t stream);

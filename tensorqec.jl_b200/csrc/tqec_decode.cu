@@ -714,7 +714,7 @@ __global__ void k_frontier_warp(const PlanDev P, const uint64_t *__restrict__ sy
 int launch_decode(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d_corr, double *d_out,
                   int32_t *d_argmax, cudaStream_t stream) {
   if (B <= 0) return TQEC_OK;
-  if (plan->has_sweep && plan->semiring == TQEC_SEMIRING_MAXPLUS) return launch_sweep(plan, d_synd, B, d_corr, d_out, stream);
+  if (plan->has_sweep) return launch_sweep(plan, d_synd, B, d_corr, d_out, d_argmax, stream);
   const int64_t per_group = plan->dev.defer ? 32 : plan->shots_per_team;
   const int64_t groups = (B + per_group - 1) / per_group;
   const bool mp = plan->semiring == TQEC_SEMIRING_MAXPLUS;

@@ -42,20 +42,22 @@ __host__ __device__ __forceinline__ uint32_t sw_phys(uint32_t x) { return x ^ ((
 // of j.  Back-pointer bits of output j: k at bit OFF + j * NF.  The output index J is a template parameter so that the
 // back-pointer mask is an immediate of a predicated OR (one issue slot per bit; the compiler's own lowering of
 // `if (p) bits |= m` costs a SEL plus a share of a LOP3).
-template <int SEMI, int M, int NP, int P0, int P1, int NF, int F0, int F1, int OFF, int J>
+template <int SEMI, int M, int NP, int P0, int P1, int NF, int F0, int F1, int K0, int K1, int OFF, int JO>
 __device__ __forceinline__ void sweep_out(const double (&R)[1 << M], double (&O)[1 << M], const double *T, uint32_t &bits) {
-  constexpr int pidx = (NP > 0 ? ((J >> (P0 < 0 ? 0 : P0)) & 1) : 0) | (NP > 1 ? (((J >> (P1 < 0 ? 0 : P1)) & 1) << 1) : 0);
+  constexpr int pidx = (NP > 0 ? ((JO >> (P0 < 0 ? 0 : P0)) & 1) : 0) | (NP > 1 ? (((JO >> (P1 < 0 ? 0 : P1)) & 1) << 1) : 0);
+  // output JO reads the inputs J ^ F(k), J = JO with the other bits flipped that its pinned variables (when 1) flip
+  constexpr int J = JO ^ ((pidx & 1) ? K0 : 0) ^ ((pidx & 2) ? K1 : 0);
   const double *Tp = T + (pidx << NF);
   if (NF == 0) {
-    O[J] = SEMI == TQEC_SEMIRING_MAXPLUS ? R[J] + Tp[0] : R[J] * Tp[0];
+    O[JO] = SEMI == TQEC_SEMIRING_MAXPLUS ? R[J] + Tp[0] : R[J] * Tp[0];
   } else if (NF == 1) {
     if (SEMI == TQEC_SEMIRING_MAXPLUS) {
-      constexpr uint32_t m = 1u << ((OFF + J) & 31);
+      constexpr uint32_t m = 1u << ((OFF + JO) & 31);
       const double c0 = R[J] + Tp[0], c1 = R[J ^ F0] + Tp[1];
       asm("{\n .reg .pred p;\n setp.gt.f64 p, %2, %3;\n selp.f64 %0, %2, %3, p;\n @p or.b32 %1, %1, %4;\n}"
-          : "=d"(O[J]), "+r"(bits) : "d"(c1), "d"(c0), "n"(m));
+          : "=d"(O[JO]), "+r"(bits) : "d"(c1), "d"(c0), "n"(m));
     } else {
-      O[J] = R[J] * Tp[0] + R[J ^ F0] * Tp[1];
+      O[JO] = R[J] * Tp[0] + R[J ^ F0] * Tp[1];
     }
   } else {
     if (SEMI == TQEC_SEMIRING_MAXPLUS) {
@@ -63,36 +65,38 @@ __device__ __forceinline__ void sweep_out(const double (&R)[1 << M], double (&O)
       const bool p01 = c1 > c0, p23 = c3 > c2;
       const double b01 = p01 ? c1 : c0, b23 = p23 ? c3 : c2;
       const bool pf = b23 > b01;
-      O[J] = pf ? b23 : b01;
+      O[JO] = pf ? b23 : b01;
       const uint32_t bk = pf ? (2u | (uint32_t)p23) : (uint32_t)p01;
-      bits |= bk << ((OFF + 2 * J) & 31);
+      bits |= bk << ((OFF + 2 * JO) & 31);
     } else {
-      O[J] = ((R[J] * Tp[0] + R[J ^ F0] * Tp[1]) + R[J ^ F1] * Tp[2]) + R[J ^ F0 ^ F1] * Tp[3];
+      O[JO] = ((R[J] * Tp[0] + R[J ^ F0] * Tp[1]) + R[J ^ F1] * Tp[2]) + R[J ^ F0 ^ F1] * Tp[3];
     }
   }
 }
 
-template <int SEMI, int M, int NP, int P0, int P1, int NF, int F0, int F1, int OFF, int... J>
+template <int SEMI, int M, int NP, int P0, int P1, int NF, int F0, int F1, int K0, int K1, int OFF, int... J>
 __device__ __forceinline__ void sweep_layer_seq(double (&R)[1 << M], const double *T, uint32_t &bits, std::integer_sequence<int, J...>) {
   double O[1 << M];
-  (sweep_out<SEMI, M, NP, P0, P1, NF, F0, F1, OFF, J>(R, O, T, bits), ...);
+  (sweep_out<SEMI, M, NP, P0, P1, NF, F0, F1, K0, K1, OFF, J>(R, O, T, bits), ...);
 #pragma unroll
   for (int j = 0; j < (1 << M); ++j) R[j] = O[j];
 }
 
-template <int SEMI, int M, int NP, int P0, int P1, int NF, int F0, int F1, int OFF>
+template <int SEMI, int M, int NP, int P0, int P1, int NF, int F0, int F1, int K0, int K1, int OFF>
 __device__ __forceinline__ void sweep_layer(double (&R)[1 << M], const double *T, uint32_t &bits) {
-  sweep_layer_seq<SEMI, M, NP, P0, P1, NF, F0, F1, OFF>(R, T, bits, std::make_integer_sequence<int, (1 << M)>{});
+  sweep_layer_seq<SEMI, M, NP, P0, P1, NF, F0, F1, K0, K1, OFF>(R, T, bits, std::make_integer_sequence<int, (1 << M)>{});
 }
 
-template <int SEMI, int M, int NL, int NP0, int P00, int P01, int NF0, int F00, int F01, int NP1, int P10, int P11,
-          int NF1, int F10, int F11>
+template <int SEMI, int M, int NL, int NP0, int P00, int P01, int NF0, int F00, int F01, int K00, int K01, int NP1,
+          int P10, int P11, int NF1, int F10, int F11, int K10, int K11>
 __device__ __forceinline__ void sweep_step(const int32_t *__restrict__ rec, const double *__restrict__ tvals,
                                            uint32_t st_abs, uint32_t lt, const uint16_t *__restrict__ stab_row,
                                            const uint16_t *__restrict__ late_row, uint32_t *__restrict__ bpt, int lane) {
   constexpr int N = 1 << M;
   constexpr int NT0 = 1 << (NP0 + NF0), NT1 = NL > 1 ? (1 << (NP1 + NF1)) : 1;
-  constexpr int BPP = SEMI == TQEC_SEMIRING_MAXPLUS ? N * (NF0 + (NL > 1 ? NF1 : 0)) : 0;
+  // back-pointers exist for max-plus only; shapes whose bits would not fit one word are sum-product-only shapes
+  constexpr int BPP0 = SEMI == TQEC_SEMIRING_MAXPLUS ? N * (NF0 + (NL > 1 ? NF1 : 0)) : 0;
+  constexpr int BPP = BPP0 <= 32 ? BPP0 : 0;
   constexpr int IPW = BPP ? 32 / BPP : 1;
   const int4 r0 = *reinterpret_cast<const int4 *>(rec);         // menu id, iterations, table offset, first bp word
   const int2 am = *reinterpret_cast<const int2 *>(rec + 4);     // byte masks of patch bits 0..3 (u16 each)
@@ -130,8 +134,8 @@ __device__ __forceinline__ void sweep_step(const int32_t *__restrict__ rec, cons
     const uint32_t base_n = laddr ^ (uint32_t)la[itn];
     const uint32_t inb_n = base_n ^ (uint32_t)stab_row[sidx_n];
     uint32_t bits = 0;
-    sweep_layer<SEMI, M, NP0, P00, P01, NF0, F00, F01, 0>(R, T0, bits);
-    if (NL > 1) sweep_layer<SEMI, M, NP1, P10, P11, NF1, F10, F11, N * NF0>(R, T1, bits);
+    sweep_layer<SEMI, M, NP0, P00, P01, NF0, F00, F01, K00, K01, 0>(R, T0, bits);
+    if (NL > 1) sweep_layer<SEMI, M, NP1, P10, P11, NF1, F10, F11, K10, K11, N * NF0>(R, T1, bits);
 #pragma unroll
     for (int j = 0; j < N; ++j) sw_sts(sw_xor3(outb, lo[j & 3], hi[(j >> 2) & 3]), R[j]);
     if (BPP) {
@@ -155,7 +159,7 @@ __device__ __forceinline__ void sweep_step(const int32_t *__restrict__ rec, cons
 template <int SEMI, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, uint64_t *__restrict__ corr,
-        double *__restrict__ out, uint32_t *__restrict__ bp_all) {
+        double *__restrict__ out, int32_t *__restrict__ argmax_out, uint32_t *__restrict__ bp_all) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int NW = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int SG = 1 << P.sg, NE = 1 << P.W;
@@ -237,9 +241,11 @@ k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, ui
         const uint32_t lt = sm_lt[i * 32 + lane];
         const uint16_t *srow = stab + (i << P.sg), *lrow = stab + ((P.n_ss + i) << P.sg);
         switch (rec[0]) {
-#define SW_CASE(ID, M, NL, NP0, P00, P01, NF0, F00, F01, NP1, P10, P11, NF1, F10, F11)                                  \
+#define SW_CASE(ID, M, NL, NP0, P00, P01, NF0, F00, F01, K00, K01, NP1, P10, P11, NF1, F10, F11, K10, K11)               \
   case ID:                                                                                                             \
-    sweep_step<SEMI, M, NL, NP0, P00, P01, NF0, F00, F01, NP1, P10, P11, NF1, F10, F11>(rec, sm_tv, st_abs, lt, srow, lrow, bpf, lane); \
+    if (SEMI == TQEC_SEMIRING_SUMPROD || ID < TQEC_SWEEP_MENU_MAXPLUS)   /* keeps the max-plus kernel's code small */    \
+      sweep_step<SEMI, M, NL, NP0, P00, P01, NF0, F00, F01, K00, K01, NP1, P10, P11, NF1, F10, F11, K10, K11>(         \
+          rec, sm_tv, st_abs, lt, srow, lrow, bpf, lane);                                                             \
     break;
           TQEC_SWEEP_MENU(SW_CASE)
 #undef SW_CASE
@@ -247,16 +253,34 @@ k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, ui
         }
         __syncwarp();
       }
-      if (out && lane < SG && shot0 + lane < B) out[shot0 + lane] = st[sw_phys((uint32_t)(P.out_index0 | (lane << P.W)))];
+      if (SEMI == TQEC_SEMIRING_MAXPLUS) {
+        if (out && lane < SG && shot0 + lane < B) out[shot0 + lane] = st[sw_phys((uint32_t)(P.out_index[0] | (lane << P.W)))];
+      } else {
+        // marginals over the open observable slots (observable 0 fastest) and their first maximal entry (findmax)
+        const int NO = 1 << P.n_obs;
+        for (int i = lane; i < (SG << P.n_obs); i += 32) {
+          const int sub = i >> P.n_obs, idx = i & (NO - 1);
+          if (shot0 + sub < B) out[(shot0 + sub) * NO + idx] = st[sw_phys((uint32_t)(P.out_index[idx] | (sub << P.W)))];
+        }
+        if (argmax_out && lane < SG && shot0 + lane < B) {
+          double best = -1.0;
+          int bi = 0;
+          for (int idx = 0; idx < NO; ++idx) {
+            const double v = st[sw_phys((uint32_t)(P.out_index[idx] | (lane << P.W)))];
+            if (v > best) { best = v; bi = idx; }
+          }
+          argmax_out[shot0 + lane] = bi;
+        }
+      }
       __syncwarp();
     }
 
     // deferred traceback: lane q walks shot q of the group
-    if (live) {
+    if (SEMI == TQEC_SEMIRING_MAXPLUS && live) {
       const int f = lane >> P.sg, sub = lane & (SG - 1);
       const uint32_t *bpq = bp + (size_t)f * P.bp_words * 32;
       uint64_t cfg[4] = {0ull, 0ull, 0ull, 0ull};
-      uint32_t x = (uint32_t)P.out_index0 | ((uint32_t)sub << P.W);
+      uint32_t x = (uint32_t)P.out_index[0] | ((uint32_t)sub << P.W);
       for (int i = P.n_ss - 1; i >= 0; --i) {
         const int32_t *t = P.tb + (size_t)i * SW_TB_INTS;
         const int4 t0 = __ldg(reinterpret_cast<const int4 *>(t));          // M, layers, loop bits, bpp
@@ -283,11 +307,13 @@ k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, ui
           pb = wd >> (t0.w * (it % t1.y));
         }
         for (int li = t0.y - 1; li >= 0; --li) {
-          const int32_t *L = t + 30 + 12 * li;
+          const int32_t *L = t + 30 + 14 * li;
           const int np = __ldg(L), nf = __ldg(L + 1), bo = __ldg(L + 2), flipm = __ldg(L + 11);
           const uint32_t k = nf ? ((pb >> (bo + j * nf)) & ((1u << nf) - 1u)) : 0u;
+          uint32_t pflip = 0;
           for (int q = 0; q < np; ++q) {
             const int pbit = __ldg(L + 3 + 2 * q), v = __ldg(L + 4 + 2 * q);
+            if ((j >> pbit) & 1u) pflip ^= (uint32_t)__ldg(L + 12 + q);
             const uint64_t bitv = (uint64_t)(((j >> pbit) & 1u) ^ (lsyn & ((uint32_t)flipm >> q) & 1u)) << (v & 63);
             const int w = v >> 6;
             cfg[0] |= w == 0 ? bitv : 0ull; cfg[1] |= w == 1 ? bitv : 0ull;
@@ -302,6 +328,7 @@ k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, ui
             cfg[2] |= w == 2 ? bitv : 0ull; cfg[3] |= w == 3 ? bitv : 0ull;
             if (kb) j ^= (uint32_t)fm;
           }
+          j ^= pflip;
         }
         x &= ~pm;
 #pragma unroll
@@ -329,19 +356,21 @@ k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, ui
   }
 }
 
-int launch_sweep(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d_corr, double *d_out, cudaStream_t stream) {
+template <int SEMI>
+static const void *sweep_kernel(int maxt) {
+  return maxt == 768 ? (const void *)k_sweep<SEMI, 768> : maxt == 640 ? (const void *)k_sweep<SEMI, 640> : (const void *)k_sweep<SEMI, 512>;
+}
+
+int launch_sweep(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d_corr, double *d_out, int32_t *d_argmax,
+                 cudaStream_t stream) {
   const int64_t groups = (B + 31) / 32;
   const int64_t ctas = (groups + plan->sw_teams - 1) / plan->sw_teams;
   const int grid = (int)(ctas < plan->sm_count ? ctas : plan->sm_count);
-  if (plan->sw_maxt == 768)
-    k_sweep<TQEC_SEMIRING_MAXPLUS, 768><<<grid, 32 * plan->sw_teams, plan->sw_smem, stream>>>(plan->sw, d_synd, B, d_corr, d_out, plan->d_sw_bp);
-  else if (plan->sw_maxt == 576)
-    k_sweep<TQEC_SEMIRING_MAXPLUS, 576><<<grid, 32 * plan->sw_teams, plan->sw_smem, stream>>>(plan->sw, d_synd, B, d_corr, d_out, plan->d_sw_bp);
-  else if (plan->sw_maxt == 640)
-    k_sweep<TQEC_SEMIRING_MAXPLUS, 640><<<grid, 32 * plan->sw_teams, plan->sw_smem, stream>>>(plan->sw, d_synd, B, d_corr, d_out, plan->d_sw_bp);
-  else
-    k_sweep<TQEC_SEMIRING_MAXPLUS, 512><<<grid, 32 * plan->sw_teams, plan->sw_smem, stream>>>(plan->sw, d_synd, B, d_corr, d_out, plan->d_sw_bp);
-  TQEC_CUDA(cudaGetLastError());
+  const void *kern = plan->semiring == TQEC_SEMIRING_MAXPLUS ? sweep_kernel<TQEC_SEMIRING_MAXPLUS>(plan->sw_maxt)
+                                                             : sweep_kernel<TQEC_SEMIRING_SUMPROD>(plan->sw_maxt);
+  void *args[] = {(void *)&plan->sw, (void *)&d_synd, (void *)&B, (void *)&d_corr, (void *)&d_out, (void *)&d_argmax,
+                  (void *)&plan->d_sw_bp};
+  TQEC_CUDA(cudaLaunchKernel(kern, dim3(grid), dim3(32 * plan->sw_teams), args, (size_t)plan->sw_smem, stream));
   plan->launches += 1;
   return TQEC_OK;
 }
@@ -363,16 +392,16 @@ int sweep_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &pr
   const tqec_sweep_desc *s = d->sweep;
   p->has_sweep = 0;
   if (!s || std::getenv("TQEC_NO_SWEEP")) return TQEC_OK;
-  TQEC_REQUIRE(d->semiring == TQEC_SEMIRING_MAXPLUS, "sweep tables are supported for max-plus plans only");
   TQEC_REQUIRE(s->W >= 1 && s->sg >= 0 && s->sg <= 5 && s->W + s->sg == 10, "sweep: W=%d sg=%d must add up to 10 index bits", s->W, s->sg);
   TQEC_REQUIRE(s->n_ss > 0 && s->rec && s->tb && s->lanetab && s->tvals && s->head_state && s->head_cfg && s->out_index,
                "sweep: missing table");
-  TQEC_REQUIRE(s->n_head_bits >= 0 && s->n_head_bits <= 8 && (s->n_head_bits == 0 || s->head_bits), "sweep: bad head bits");
+  TQEC_REQUIRE(s->n_head_bits >= 0 && s->n_head_bits <= 12 && (s->n_head_bits == 0 || s->head_bits), "sweep: bad head bits");
   const int nsw = words_for(d->n_checks), ncw = words_for(d->n_vars);
   TQEC_REQUIRE(nsw <= 4 && ncw <= 4, "sweep: more than 256 checks / variables");
   for (int i = 0; i < s->n_ss; ++i) {
     const int32_t *r = s->rec + (size_t)i * SW_REC_INTS;
-    TQEC_REQUIRE(r[0] >= 0 && r[0] < TQEC_SWEEP_MENU_SIZE, "sweep step %d: unknown shape %d", i, r[0]);
+    TQEC_REQUIRE(r[0] >= 0 && r[0] < (d->semiring == TQEC_SEMIRING_MAXPLUS ? TQEC_SWEEP_MENU_MAXPLUS : TQEC_SWEEP_MENU_SIZE),
+                 "sweep step %d: unknown shape %d", i, r[0]);
     TQEC_REQUIRE(r[1] >= 1 && r[1] <= 8, "sweep step %d: bad iteration count %d", i, r[1]);
     TQEC_REQUIRE(r[2] >= 0 && r[2] + 8 <= s->n_tvals + 8 && r[14] >= 0 && r[14] <= 4, "sweep step %d: bad offsets", i);
     for (int q = 0; q < r[14]; ++q)
@@ -386,7 +415,9 @@ int sweep_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &pr
   D.n_ss = s->n_ss; D.W = s->W; D.sg = s->sg; D.nh = s->n_head_bits; D.nsw = nsw; D.ncw = ncw;
   D.bp_words = s->bp_words > 0 ? s->bp_words : 1;
   D.sync_mode = 1;
-  if (const char *e = std::getenv("TQEC_SWEEP_SYNC")) { const int v = std::atoi(e); if (v >= 0 && v <= 2) D.sync_mode = v; } D.n_tvals = s->n_tvals; D.out_index0 = s->out_index[0];
+  if (const char *e = std::getenv("TQEC_SWEEP_SYNC")) { const int v = std::atoi(e); if (v >= 0 && v <= 2) D.sync_mode = v; } D.n_tvals = s->n_tvals; D.n_obs = d->n_obs;
+  TQEC_REQUIRE(d->n_obs <= 4, "sweep: more than 4 open observables");
+  for (int i = 0; i < (1 << d->n_obs); ++i) D.out_index[i] = s->out_index[i];
   for (int j = 0; j < s->n_head_bits; ++j) D.head_bits[j] = s->head_bits[j];
   const size_t nhp = (size_t)1 << s->n_head_bits, ne = (size_t)1 << s->W;
   int rc;
@@ -395,7 +426,7 @@ int sweep_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &pr
   if ((rc = sw_upload(&p->d_sw[2], s->lanetab, (size_t)s->n_ss * 32))) return rc;
   if ((rc = sw_upload(&p->d_sw[3], s->tvals, (size_t)s->n_tvals))) return rc;
   if ((rc = sw_upload(&p->d_sw[4], s->head_state, nhp * ne))) return rc;
-  if ((rc = sw_upload(&p->d_sw[5], s->head_cfg, nhp * ne * ncw))) return rc;
+  if ((rc = sw_upload(&p->d_sw[5], s->head_cfg, d->semiring == TQEC_SEMIRING_MAXPLUS ? nhp * ne * ncw : (size_t)1))) return rc;
   D.rec = (const int32_t *)p->d_sw[0]; D.tb = (const int32_t *)p->d_sw[1]; D.lanetab = (const uint32_t *)p->d_sw[2];
   D.tvals = (const double *)p->d_sw[3]; D.head_state = (const double *)p->d_sw[4]; D.head_cfg = (const uint64_t *)p->d_sw[5];
 
@@ -406,12 +437,11 @@ int sweep_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &pr
   const size_t rec_b = ((size_t)s->n_ss * SW_REC_INTS * 4 + 15) & ~(size_t)15, lt_b = (size_t)s->n_ss * 128;
   const size_t tv_b = ((size_t)s->n_tvals * 8 + 15) & ~(size_t)15;
   const size_t words_b = (((size_t)nsw << s->sg) * 8 + ((size_t)s->n_ss << s->sg) * 4 + 15) & ~(size_t)15;   // syndromes, early + late masks
-  // register budget variant: 768 threads (80 registers), 640 (96) or 512 (128); TQEC_SWEEP_MAXT overrides the default
+  // register budget variant: 512 threads (128 registers), 640 (96) or 768 (80); TQEC_SWEEP_MAXT overrides the default
   int maxt = 512;
-  if (const char *e = std::getenv("TQEC_SWEEP_MAXT")) { const int v = std::atoi(e); if (v == 768 || v == 640 || v == 576 || v == 512) maxt = v; }
-  const void *kern = maxt == 768 ? (const void *)k_sweep<TQEC_SEMIRING_MAXPLUS, 768>
-                   : maxt == 576 ? (const void *)k_sweep<TQEC_SEMIRING_MAXPLUS, 576>
-                                 : (maxt == 640 ? (const void *)k_sweep<TQEC_SEMIRING_MAXPLUS, 640> : (const void *)k_sweep<TQEC_SEMIRING_MAXPLUS, 512>);
+  if (const char *e = std::getenv("TQEC_SWEEP_MAXT")) { const int v = std::atoi(e); if (v == 768 || v == 640 || v == 512) maxt = v; }
+  const void *kern = d->semiring == TQEC_SEMIRING_MAXPLUS ? sweep_kernel<TQEC_SEMIRING_MAXPLUS>(maxt)
+                                                          : sweep_kernel<TQEC_SEMIRING_SUMPROD>(maxt);
   p->sw_maxt = maxt;
   cudaFuncAttributes fa;
   TQEC_CUDA(cudaFuncGetAttributes(&fa, kern));

@@ -202,6 +202,18 @@ def tnmap_schedule(decoder: TNMAP, problem: GeneralDecodingProblem) -> S.Schedul
     return S.lower(factors, checks, S.MAXPLUS, t.nq, t.ns, 0, order=order)
 
 
+def _attach_sweep(sch: S.Schedule, max_head_bits: int = 10):
+    """Sum-product plans are never fused, so the schedule itself is what `lower_sweep` expects; plans it declines keep
+    running on the general kernels."""
+    if os.environ.get("TQEC_NO_SWEEP") is None and 6 <= sch.w_max <= 10:
+        try:
+            sw = lower_sweep(sch, max_head_bits=max_head_bits)
+        except ValueError:
+            sw = None
+        if sw is not None:
+            sch.sweep = sw
+
+
 def _compile_tnmap(decoder: TNMAP, problem: GeneralDecodingProblem) -> CompiledTNMAP:
     return CompiledTNMAP(tnmap_schedule(decoder, problem), problem.tanner.nq, decoder.device)
 
@@ -270,6 +282,7 @@ def tnmmap_css_schedule(decoder: TNMMAP, problem: IndependentDepolarizingDecodin
     checks += [S.Check(tuple(int(q) + n for q in np.flatnonzero(lx[i])), "obs", i) for i in range(k)]
     checks += [S.Check(tuple(int(q) for q in np.flatnonzero(lz[i])), "obs", k + i) for i in range(k)]
     sch = S.lower(factors, checks, S.SUMPROD, 2 * n, nsx + nsz, 2 * k, order=_order_of(decoder.optimizer, n))
+    _attach_sweep(sch)
     # error_pattern (tndecoder.jl:167-174): any solution of the syndrome equations, moved into the decoded sector
     Rz, _ = gf2_right_inverse(tanner.stgz.H)            # ex = Rz sz
     Rx, _ = gf2_right_inverse(tanner.stgx.H)            # ez = Rx sx

@@ -38,7 +38,8 @@ MAX_HEAD_BITS = 6       # syndrome bits the head table may depend on
 REC_INTS = 32           # forward record per super-step (int32)
 TB_INTS = 64            # traceback record per super-step (int32)
 
-# Register-level shapes compiled into k_sweep: (M, ((pinned bits), (free masks)) per layer).  Canonical form = the
+# Register-level shapes compiled into k_sweep: (M, ((pinned bits), (free masks)[, (extra flip masks of the pinned
+# variables)]) per layer).  Canonical form = the
 # lexicographically smallest descriptor over all orderings of the patch bits.  Keep in sync with tqec_sweep_menu.h
 # (tests/test_sweep_cpu.py compares the two).
 MENU: List[tuple] = [
@@ -54,9 +55,15 @@ MENU: List[tuple] = [
     (3, (((0,), (2,)), ((1,), (5,)))),
     (3, (((0,), (6,)), ((1,), (1,)))),
     (4, (((0,), (6,)), ((1,), (9,)))),
+    (4, (((0,), (14,)),)),
+    (4, (((0,), (6,), (8,)),)),
+    (4, (((0,), (2,)), ((1,), (5,), (8,)))),
+    (4, (((0,), (2,)), ((2,), (10,), (1,)))),
+    (4, (((0,), (6,)), ((), (9, 6)))),
 ]
 
 
+MENU_MAXPLUS = 12       # shapes 0..11 are compiled into the max-plus kernel; later ones are sum-product only
 _DISCOVER = None
 
 
@@ -76,6 +83,8 @@ class Layer:
     free: List[Tuple[int, int]]                # (variable index j, patch-local flip mask)
     closed: List[Tuple[int, int]]              # (syndrome bit, patch bit)
     T: np.ndarray = None                       # [2^NP * 2^NF] values: index pidx * 2^NF + k
+    pk: List[int] = field(default_factory=list)  # per pinned variable: patch bits it flips besides its own (checks it
+                                               # touches that stay open or close without being re-opened)
 
 
 @dataclass
@@ -146,11 +155,15 @@ def _roles(factors, checks, order):
 
 
 def _classify(f, touched, opened, closing, checks):
-    """-> (pinned [(j, opened check, closed check)], free [(j, touched checks)]) or None if the step cannot run in place."""
+    """-> (pinned [(j, opened check, closed check, other checks)], free [(j, touched checks)]) or None if the step cannot
+    run in place.  A PINNED variable touches exactly one opened check (which no other variable touches) and a closing
+    check whose slot the opened one inherits; the other checks it touches are flipped when it is 1.  A FREE variable
+    touches no opened check."""
     opened, closing = set(opened), set(closing)
     if opened & closing:
         return None
     pinned, free = [], []
+    donors = set()
     for j, v in enumerate(f.vars):
         tv = [c for c in touched if v in checks[c].vars]
         ov = [c for c in tv if c in opened]
@@ -160,28 +173,26 @@ def _classify(f, touched, opened, closing, checks):
         if len(ov) != 1 or sum(1 for w in f.vars if w in checks[ov[0]].vars) != 1:
             return None
         rest = [c for c in tv if c != ov[0]]
-        if len(rest) != 1 or rest[0] not in closing:
+        cand = [c for c in rest if c in closing and c not in donors]
+        if not cand:
             return None
-        pinned.append((j, ov[0], rest[0]))
-    used = [c for _, _, c in pinned]
-    if len(set(used)) != len(used):
-        return None
-    for j, _, c in pinned:                                     # the inherited slot must see exactly one pinned variable
-        if any(f.vars[j2] in checks[c].vars for j2, _, _ in pinned if j2 != j):
-            return None
+        donors.add(cand[0])
+        pinned.append((j, ov[0], cand[0], [c for c in rest if c != cand[0]]))
     if len(pinned) > 2 or len(free) > 2:
         return None
     return pinned, free
 
 
 def _descriptor(layers_raw, chain_order):
-    """Descriptor of a group for a given ordering of its patch chains."""
+    """Descriptor of a group for a given ordering of its patch chains: per layer (pinned bits, free masks[, masks of the
+    other bits each pinned variable flips -- only when some are non-zero])."""
     bit = {ch: b for b, ch in enumerate(chain_order)}
     desc = []
-    for pinned, free in layers_raw:
+    for pinned, free, pk in layers_raw:
         pb = tuple(bit[ch] for _, ch in pinned)
         fm = tuple(sum(1 << bit[ch] for ch in chs) for _, chs in free)
-        desc.append((pb, fm))
+        pm = tuple(sum(1 << bit[ch] for ch in chs) for chs in pk)
+        desc.append((pb, fm, pm) if any(pm) else (pb, fm))
     return (len(chain_order), tuple(desc))
 
 
@@ -345,18 +356,20 @@ def lower_sweep(sch: S.Schedule, max_head_bits: int = MAX_HEAD_BITS) -> Optional
         fi, touched, opened, closing = roles[t]
         pinned, free = cls[t]
         f = factors[fi]
-        lp = [(j, chain_of[c]) for j, o, c in pinned]
+        lp = [(j, chain_of[c]) for j, o, c, _ in pinned]
+        lk = [[chain_of[c] for c in extra] for _, _, _, extra in pinned]
         lf = [(j, [chain_of[c] for c in tv]) for j, tv in free]
         lc = [(checks[c].index, chain_of[c]) for c in closing]
-        chains = sorted({ch for _, ch in lp} | {ch for _, chs in lf for ch in chs} | {ch for _, ch in lc})
-        for j, o, c in pinned:
+        chains = sorted({ch for _, ch in lp} | {ch for chs in lk for ch in chs} | {ch for _, chs in lf for ch in chs} |
+                        {ch for _, ch in lc})
+        for j, o, c, _ in pinned:
             chain_of[o] = chain_of[c]
-        raw.append(dict(step=t, fi=fi, pinned=lp, free=lf, closed=lc, chains=chains))
+        raw.append(dict(step=t, fi=fi, pinned=lp, pk=lk, free=lf, closed=lc, chains=chains))
         if len(chains) > MAX_PATCH or len(chains) == 0:
             return None
     # an observable must still be alive at the end, everything else dead
     final_live = [c for c in chain_of if checks[c].kind == "obs"]
-    menu_ix = {m: i for i, m in enumerate(MENU)}
+    menu_ix = {m: i for i, m in enumerate(MENU) if sch.semiring == S.SUMPROD or i < MENU_MAXPLUS}
     if _DISCOVER is not None:                                  # development aid: record the shapes a plan would need
         class _Any(dict):
             def __contains__(self, d):
@@ -383,7 +396,7 @@ def lower_sweep(sch: S.Schedule, max_head_bits: int = MAX_HEAD_BITS) -> Optional
                 return None
         if sch.semiring == S.MAXPLUS and sum(len(g["free"]) for g in group) << len(chains) > 32:
             return None                                        # back-pointers of a patch must fit one 32-bit word
-        d, perm = _canonical([(g["pinned"], g["free"]) for g in group], chains)
+        d, perm = _canonical([(g["pinned"], g["free"], g["pk"]) for g in group], chains)
         if d not in menu_ix:
             return None
         return menu_ix[d], perm
@@ -392,14 +405,18 @@ def lower_sweep(sch: S.Schedule, max_head_bits: int = MAX_HEAD_BITS) -> Optional
     nr = len(raw)
     single = [match(raw[k:k + 1]) for k in range(nr)]
     pair = [match(raw[k:k + 2]) if k + 1 < nr else None for k in range(nr)]
-    if any(m is None for m in single):
-        return None
+    INF = 10 ** 9
     best = [0] * (nr + 2)
-    take = [1] * nr
+    best[nr + 1] = INF
+    take = [0] * nr
     for k in range(nr - 1, -1, -1):
-        best[k] = 1 + best[k + 1]
+        best[k] = INF
+        if single[k] is not None and 1 + best[k + 1] < best[k]:
+            best[k], take[k] = 1 + best[k + 1], 1
         if pair[k] is not None and 1 + best[k + 2] <= best[k]:
             best[k], take[k] = 1 + best[k + 2], 2
+    if best[0] >= INF:
+        return None                                            # some step fits no compiled shape
 
     ssteps: List[SuperStep] = []
     k = 0
@@ -415,6 +432,7 @@ def lower_sweep(sch: S.Schedule, max_head_bits: int = MAX_HEAD_BITS) -> Optional
             pinned = [(j, bit[ch]) for j, ch in g["pinned"]]
             free = [(j, sum(1 << bit[ch] for ch in chs)) for j, chs in g["free"]]
             closed = [(sb, bit[ch]) for sb, ch in g["closed"]]
+            pk = [sum(1 << bit[ch] for ch in chs) for chs in g["pk"]]
             NP, NF = len(pinned), len(free)
             T = np.zeros(1 << (NP + NF))
             for pidx in range(1 << NP):
@@ -425,7 +443,7 @@ def lower_sweep(sch: S.Schedule, max_head_bits: int = MAX_HEAD_BITS) -> Optional
                     for q, (j, _) in enumerate(free):
                         a |= ((kk >> q) & 1) << j
                     T[(pidx << NF) | kk] = st.table[a]
-            layers.append(Layer(g["step"], g["fi"], tuple(f.vars), pinned, free, closed, T))
+            layers.append(Layer(g["step"], g["fi"], tuple(f.vars), pinned, free, closed, T, pk))
         ss = SuperStep(layers, list(perm), mi)
         if cnt == 2:
             both = {pb for _, pb in layers[0].pinned} & {cb for _, cb in layers[1].closed}
@@ -580,7 +598,7 @@ def _encode(p: SweepPlan):
             t[22 + 2 * q], t[23 + 2 * q] = sb, pos
         bpoff = 0
         for li, l in enumerate(ss.layers):
-            o = 30 + 12 * li
+            o = 30 + 14 * li
             t[o], t[o + 1], t[o + 2] = len(l.pinned), len(l.free), bpoff
             for q in range(2):
                 if q < len(l.pinned):
@@ -592,6 +610,8 @@ def _encode(p: SweepPlan):
                 else:
                     t[o + 7 + 2 * q], t[o + 8 + 2 * q] = 0, -1
             t[o + 11] = flipmask if (li == 1 and ss.late is not None) else 0
+            for q in range(len(l.pinned)):
+                t[o + 12 + q] = l.pk[q] if q < len(l.pk) else 0
             bpoff += (1 << M) * len(l.free)
     p.rec, p.tb, p.lanetab = rec, tb, lanetab
     p.tvals = np.asarray(tvals if tvals else [0.0], dtype=np.float64)

@@ -213,6 +213,23 @@ def test_tnmmap_surface_vs_dense_reference(tq, d):
     assert np.allclose(mar, ref, rtol=MAR_RTOL, atol=1e-300)
 
 
+def test_tnmmap_d9_through_the_sweep(tq):
+    """TNMMAP (CSS) at d = 9: 10-bit state, one shot per team pass, 10-bit head table, sum-product layers of k_sweep --
+    against the C port of the recurrence at the north-star tolerance, and against the general kernels."""
+    from tensorqec.jl_b200 import _cabi
+    t, em = _css_case(tq, tq.SurfaceCode(9, 9))
+    ct = tq.compile(tq.TNMMAP(), t, em)
+    assert ct.plan.query(_cabi.Q_SWEEP) == 1
+    ex, ez, sx, sz = _syndromes(t, em, 99, 300)
+    res = tq.decode(ct, tq.CSSSyndrome(sx, sz))
+    sch = ct.schedule
+    ref = cref.FrontierPlan(sch).run(np.concatenate([sx, sz], axis=1))
+    got = res.marginal.reshape(300, -1, order="F")
+    assert np.allclose(got, ref, rtol=MAR_RTOL, atol=0)
+    assert np.array_equal(res.sector, np.argmax(ref, axis=1))
+    assert tq.syndrome_extraction(res.error_pattern, t) == tq.CSSSyndrome(sx, sz)
+
+
 def test_gf2_kernels_bit_exact(tq):
     rng = np.random.default_rng(0)
     for rows, cols in [(2, 5), (40, 81), (80, 162), (130, 300), (1, 1)]:

@@ -60,6 +60,22 @@ def test_sweep_generic_noise_and_single_shot(tq):
         assert np.array_equal(lp, lp0) and np.array_equal(cfg, cfg0)
 
 
+@pytest.mark.parametrize("d,B", [(5, 48), (7, 12), (9, 3)])
+def test_sweep_sum_product_tnmmap_bit_exact(tq, d, B):
+    """TNMMAP (CSS) through the sweep: open observable slots, pinned variables that also flip an observable, a 10-bit
+    head table; marginals equal the recurrence oracle bit for bit (same multiplications and additions in the same order)."""
+    from tensorqec.jl_b200 import sweep as SW
+    t = tq.CSSTannerGraph(tq.SurfaceCode(d, d))
+    em = tq.iid_error(0.05, t)
+    lx, lz, sch, R, L, FIX = tq.tnmmap_css_schedule(tq.TNMMAP(), tq.get_problem(t, em))
+    pl = getattr(sch, "sweep", None)
+    assert pl is not None and pl.semiring == 1 and len(pl.out_index) == 4
+    syn = _syndromes(t, em, 7 * d, B)
+    mar = sweep_emulator.run(pl, SW.MENU, syn)
+    ref = frontier.run(sch.factors, sch.checks, sch.order, 1, syn, sch.n_vars)
+    assert np.array_equal(mar, np.ldexp(ref, -sch.log2_scale))
+
+
 def test_sweep_plan_geometry(tq):
     from tensorqec.jl_b200 import sweep as SW
     t, em, su, pl = _plan(tq, 9)
@@ -83,16 +99,19 @@ def test_sweep_menu_header_matches_planner():
     from tensorqec.jl_b200 import sweep as SW
     txt = open(os.path.join(ROOT, "tensorqec.jl_b200", "csrc", "tqec_sweep_menu.h")).read()
     rows = re.findall(r"X\(([-\d,\s]+)\)", txt)
-    rows = [r for r in rows if len(r.split(",")) == 15]
+    rows = [r for r in rows if len(r.split(",")) == 19]
     assert len(rows) == len(SW.MENU) == int(re.search(r"TQEC_SWEEP_MENU_SIZE (\d+)", txt).group(1))
     for r, (M, layers) in zip(rows, SW.MENU):
         v = [int(x) for x in r.split(",")]
         assert v[0] == rows.index(r) and v[1] == M and v[2] == len(layers)
-        for li, (pb, fm) in enumerate(layers):
-            o = 3 + 6 * li
+        for li, layer in enumerate(layers):
+            pb, fm = layer[0], layer[1]
+            pk = list(layer[2]) if len(layer) > 2 else []
+            o = 3 + 8 * li
             assert v[o] == len(pb) and v[o + 3] == len(fm)
             assert [x for x in v[o + 1:o + 3] if x >= 0] == list(pb)
             assert [x for x in v[o + 4:o + 6] if x > 0] == list(fm)
+            assert v[o + 6:o + 8] == (pk + [0, 0])[:2]
 
 
 def test_tnmap_compile_prefers_sweep_and_env_disables_it(tq, monkeypatch):
