@@ -262,7 +262,7 @@ def test_sampler_bit_exact_and_offset_invariant(tq):
     assert one.shape == (100,)
 
 
-@pytest.mark.parametrize("d,shots", [(3, 20000), (5, 20000)])
+@pytest.mark.parametrize("d,shots", [(3, 20000), (5, 20000), (7, 6000)])
 def test_fused_pipeline_counts_bit_exact(tq, d, shots):
     t, em = _css_case(tq, tq.SurfaceCode(d, d))
     mc = tq.MonteCarlo(t, tq.TNMAP(), em)
