@@ -23,11 +23,19 @@ namespace tqec {
 
 __device__ __forceinline__ double sw_lds(uint32_t addr) {
   double v;
+#ifdef TQEC_DIAG_NOMEM   // diagnosis only (wrong results): no shared-memory traffic, the value depends on the address
+  v = __hiloint2double((int)addr | 0xbff00000, (int)addr);
+#else
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+#endif
   return v;
 }
 __device__ __forceinline__ void sw_sts(uint32_t addr, double v) {
+#ifdef TQEC_DIAG_NOMEM
+  if (v == 1.2345 && addr == 77) asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v));
+#else
   asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v));
+#endif
 }
 __device__ __forceinline__ uint32_t sw_xor3(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t d;
@@ -53,9 +61,17 @@ __device__ __forceinline__ void sweep_out(const double (&R)[1 << M], double (&O)
   } else if (NF == 1) {
     if (SEMI == TQEC_SEMIRING_MAXPLUS) {
       constexpr uint32_t m = 1u << ((OFF + JO) & 31);
+#ifdef TQEC_SWEEP_PRED_DADD
+      // variant: the winner is recomputed by a predicated add instead of two 32-bit selects (5 issue slots and 4
+      // FP64-pipe instructions per output instead of 6 and 3); same value bit for bit
+      asm("{\n .reg .pred p;\n .reg .f64 c1;\n add.f64 %0, %2, %3;\n add.f64 c1, %4, %5;\n setp.gt.f64 p, c1, %0;\n"
+          " @p add.f64 %0, %4, %5;\n @p or.b32 %1, %1, %6;\n}"
+          : "=&d"(O[JO]), "+r"(bits) : "d"(R[J]), "d"(Tp[0]), "d"(R[J ^ F0]), "d"(Tp[1]), "n"(m));
+#else
       const double c0 = R[J] + Tp[0], c1 = R[J ^ F0] + Tp[1];
       asm("{\n .reg .pred p;\n setp.gt.f64 p, %2, %3;\n selp.f64 %0, %2, %3, p;\n @p or.b32 %1, %1, %4;\n}"
           : "=d"(O[JO]), "+r"(bits) : "d"(c1), "d"(c0), "n"(m));
+#endif
     } else {
       O[JO] = R[J] * Tp[0] + R[J ^ F0] * Tp[1];
     }
@@ -134,8 +150,10 @@ __device__ __forceinline__ void sweep_step(const int32_t *__restrict__ rec, cons
     const uint32_t base_n = laddr ^ (uint32_t)la[itn];
     const uint32_t inb_n = base_n ^ (uint32_t)stab_row[sidx_n];
     uint32_t bits = 0;
+#ifndef TQEC_DIAG_NOLAYERS   // diagnosis only (wrong results): load / store skeleton without the arithmetic
     sweep_layer<SEMI, M, NP0, P00, P01, NF0, F00, F01, K00, K01, 0>(R, T0, bits);
     if (NL > 1) sweep_layer<SEMI, M, NP1, P10, P11, NF1, F10, F11, K10, K11, N * NF0>(R, T1, bits);
+#endif
 #pragma unroll
     for (int j = 0; j < N; ++j) sw_sts(sw_xor3(outb, lo[j & 3], hi[(j >> 2) & 3]), R[j]);
     if (BPP) {
