@@ -106,6 +106,8 @@ class TNMAP(AbstractGeneralDecoder):
     prior factors (e.g. the leaf order of a contraction tree found by the caller's TreeSA / GreedyMethod)."""
     optimizer: Any = None
     device: int = 0
+    head_bits: int = 10          # syndrome bits the tabulated head of the sweep lowering may depend on (sweep.py): more
+                                 # bits = fewer steps per shot, a larger table (2^bits x 2^W entries) and a slower compile
 
     def __repr__(self):
         return "TNMAP"
@@ -193,7 +195,7 @@ def tnmap_schedule(decoder: TNMAP, problem: GeneralDecodingProblem) -> S.Schedul
         # its shapes fall through to the general kernels
         try:
             su = S.lower(factors, checks, S.MAXPLUS, t.nq, t.ns, 0, order=order, fuse=False)
-            sw = lower_sweep(su) if 6 <= su.w_max <= 10 else None
+            sw = lower_sweep(su, max_head_bits=int(os.environ.get("TQEC_HEAD_BITS", decoder.head_bits))) if 6 <= su.w_max <= 10 else None
         except ValueError:
             sw = None
         if sw is not None:

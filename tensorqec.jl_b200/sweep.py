@@ -208,15 +208,16 @@ def _canonical(layers_raw, chains):
 def _head_eval(sch, h, roles, head_bits, live_order):
     """Tabulate the first h steps for every value of the syndrome bits they close.
     -> state (2^nh, 2^W) in slot order `live_order` (bit k of the index = parity of check live_order[k]) and, for
-    max-plus, the partial configuration (bool (2^nh, 2^W, n_vars))."""
+    max-plus, the partial configuration of every entry as packed words (uint64 (2^nh, 2^W, ceil(n_vars/64)))."""
     maxplus = sch.semiring == S.MAXPLUS
     nh = len(head_bits)
     B = 1 << nh
     hp = np.arange(B)
     syn_of = {b: ((hp >> j) & 1) for j, b in enumerate(head_bits)}
+    ncw = max(1, (sch.n_vars + 63) // 64)
     axes: List[int] = []
     St = np.full((B,), 0.0 if maxplus else 1.0)
-    cfg = np.zeros((B, sch.n_vars), dtype=bool) if maxplus else None
+    cfg = np.zeros((B, ncw), dtype=np.uint64) if maxplus else None
     zero = -np.inf if maxplus else 0.0
     for t in range(h):
         fi, touched, opened, closing = roles[t]
@@ -227,7 +228,7 @@ def _head_eval(sch, h, roles, head_bits, live_order):
             if maxplus:
                 cfg = np.stack([cfg, cfg], axis=-2)
             axes.append(c)
-        best = arg = None
+        best = None
         for a in range(1 << len(f.vars)):
             flips = []
             for c in touched:
@@ -240,20 +241,20 @@ def _head_eval(sch, h, roles, head_bits, live_order):
             ax = tuple(axes.index(c) + 1 for c in flips)
             src = np.flip(St, axis=ax) if ax else St
             cand = src + T[a] if maxplus else src * T[a]
+            if maxplus:
+                # every variable belongs to exactly one factor, so its bit is still clear: OR in the assignment
+                amask = np.zeros(ncw, dtype=np.uint64)
+                for j, v in enumerate(f.vars):
+                    if (a >> j) & 1:
+                        amask[v >> 6] |= np.uint64(1) << np.uint64(v & 63)
+                csrc = (np.flip(cfg, axis=ax) if ax else cfg) | amask
             if best is None:
                 best = cand.copy()
                 if maxplus:
-                    arg = np.zeros(St.shape, dtype=np.int64)
-                    csrc = np.flip(cfg, axis=ax) if ax else cfg
-                    bcfg = csrc.copy()
-                    for j, v in enumerate(f.vars):
-                        bcfg[..., v] = (a >> j) & 1
+                    bcfg = csrc
             elif maxplus:
-                upd = cand > best
+                upd = cand > best                              # strict: the smallest assignment wins exact ties
                 best = np.where(upd, cand, best)
-                csrc = (np.flip(cfg, axis=ax) if ax else cfg).copy()
-                for j, v in enumerate(f.vars):
-                    csrc[..., v] = (a >> j) & 1
                 bcfg = np.where(upd[..., None], csrc, bcfg)
             else:
                 best = best + cand
@@ -274,7 +275,7 @@ def _head_eval(sch, h, roles, head_bits, live_order):
     W = len(live_order)
     St = np.transpose(St, [0] + permu[::-1]).reshape(B, 1 << W)
     if maxplus:
-        cfg = np.transpose(cfg, [0] + permu[::-1] + [cfg.ndim - 1]).reshape(B, 1 << W, sch.n_vars)
+        cfg = np.transpose(cfg, [0] + permu[::-1] + [cfg.ndim - 1]).reshape(B, 1 << W, ncw)
     return St, cfg
 
 
@@ -515,10 +516,7 @@ def lower_sweep(sch: S.Schedule, max_head_bits: int = MAX_HEAD_BITS) -> Optional
     hs = np.ascontiguousarray(hs[:, src])
     ncw = max(1, (sch.n_vars + 63) // 64)
     if hc is not None:
-        hc = hc[:, src, :]
-        pad = np.zeros(hc.shape[:2] + (ncw * 64,), dtype=np.uint8)
-        pad[..., :sch.n_vars] = hc
-        hcw = np.ascontiguousarray(np.packbits(pad, axis=-1, bitorder="little")).view("<u8").reshape(hc.shape[0], hc.shape[1], ncw)
+        hcw = np.ascontiguousarray(hc[:, src, :])
     else:
         hcw = np.zeros((hs.shape[0], 1, ncw), dtype=np.uint64)
     plan = SweepPlan(sch.semiring, sch.n_vars, sch.n_checks, sch.n_obs, W, sg, h, head_bits, hs, hcw, ssteps, wbase,
