@@ -93,6 +93,23 @@ def test_sweep_kernel_edge_cases(tq, d, monkeypatch):
     plan2.close()
 
 
+def test_sweep_kernel_long_head(tq):
+    """The 12-bit tabulated head bench.py uses (17 of the 81 steps of d = 9 become a table look-up): same corrections and
+    log-weights, bit for bit, as the C port of the full recurrence and as the default 10-bit head."""
+    t, em = _css_case(tq, tq.SurfaceCode(9, 9))
+    ex, ez, sx, sz = _syndromes(t, em, 4242, 700)
+    syn = tq.CSSSyndrome(sx, sz)
+    res = {}
+    for bits in (10, 12):
+        ct = tq.compile(tq.TNMAP(head_bits=bits), t, em)
+        assert len(ct.cd.schedule.sweep.head_bits) == bits
+        res[bits] = tq.decode(ct, syn)
+    lp, cfg = cref.FrontierPlan(ct.cd.schedule).run(np.concatenate([sx, sz], axis=1))
+    for bits in (10, 12):
+        got = np.concatenate([res[bits].error_pattern.xerror, res[bits].error_pattern.zerror], axis=1)
+        assert np.array_equal(got, cfg) and np.array_equal(res[bits].logp, lp)
+
+
 def test_tnmap_matches_dense_reference_value(tq):
     """MAP value equals the dense (reference-style) contraction; the pattern has that weight and the syndrome."""
     d = 5

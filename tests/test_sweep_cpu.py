@@ -46,6 +46,20 @@ def test_sweep_emulator_matches_recurrence_bit_exact(tq, d, B):
     assert np.array_equal((cfg @ H.T) % 2, syn)                  # every correction reproduces its syndrome
 
 
+@pytest.mark.parametrize("bits", [6, 8, 12])
+def test_sweep_head_bits_do_not_change_results(tq, bits):
+    """A longer tabulated head (TNMAP(head_bits=...)) removes steps from the per-shot path, not from the arithmetic: the
+    emulator's results stay bit-identical to the recurrence for every head length."""
+    from tensorqec.jl_b200 import sweep as SW
+    t, em, su, _ = _plan(tq, 7)
+    pl = SW.lower_sweep(su, max_head_bits=bits)
+    assert pl is not None and len(pl.head_bits) <= bits and pl.head_state.shape[0] == 1 << len(pl.head_bits)
+    syn = _syndromes(t, em, 31, 24)
+    lp, cfg = sweep_emulator.run(pl, SW.MENU, syn)
+    lp0, cfg0 = frontier.run(su.factors, su.checks, su.order, 0, syn, su.n_vars)
+    assert np.array_equal(lp, lp0) and np.array_equal(cfg, cfg0)
+
+
 def test_sweep_generic_noise_and_single_shot(tq):
     """Per-qubit noise (no ties): one shot, odd batch sizes, shots that do not fill a team pass."""
     from tensorqec.jl_b200 import sweep as SW
