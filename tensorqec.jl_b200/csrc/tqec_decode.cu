@@ -1194,10 +1194,27 @@ extern "C" int tqec_decode_marginal(tqec_plan *p, const uint64_t *synd, int64_t 
   if ((rc = ensure_cap(&p->d_io[0], &p->io_cap[0], sb))) return rc;
   if ((rc = ensure_cap(&p->d_io[1], &p->io_cap[1], mb))) return rc;
   if ((rc = ensure_cap(&p->d_io[2], &p->io_cap[2], ab))) return rc;
-  TQEC_CUDA(cudaMemcpyAsync(p->d_io[0], synd, sb, cudaMemcpyHostToDevice, p->stream));
-  if ((rc = launch_decode(p, (const uint64_t *)p->d_io[0], B, nullptr, (double *)p->d_io[1], (int32_t *)p->d_io[2], p->stream))) return rc;
-  TQEC_CUDA(cudaMemcpyAsync(mar_out, p->d_io[1], mb, cudaMemcpyDeviceToHost, p->stream));
-  if (argmax_out) TQEC_CUDA(cudaMemcpyAsync(argmax_out, p->d_io[2], ab, cudaMemcpyDeviceToHost, p->stream));
+  // same chunked three-stage pipeline as tqec_decode_map
+  if ((rc = ensure_pipeline(p))) return rc;
+  const int64_t CH = (int64_t)1 << 21;
+  const int nsw = p->dev.nsw;
+  const int64_t NO = (int64_t)1 << p->dev.n_obs;
+  const uint64_t *d_syn = (const uint64_t *)p->d_io[0];
+  double *d_mar = (double *)p->d_io[1];
+  int32_t *d_arg = (int32_t *)p->d_io[2];
+  int slot = 0;
+  for (int64_t o = 0; o < B; o += CH, slot ^= 1) {
+    const int64_t n = B - o < CH ? B - o : CH;
+    TQEC_CUDA(cudaMemcpyAsync((void *)(d_syn + o * nsw), synd + o * nsw, (size_t)n * nsw * 8, cudaMemcpyHostToDevice, p->s_in));
+    TQEC_CUDA(cudaEventRecord(p->ev_in[slot], p->s_in));
+    TQEC_CUDA(cudaStreamWaitEvent(p->stream, p->ev_in[slot], 0));
+    if ((rc = launch_decode(p, d_syn + o * nsw, n, nullptr, d_mar + o * NO, d_arg + o, p->stream))) return rc;
+    TQEC_CUDA(cudaEventRecord(p->ev_cmp[slot], p->stream));
+    TQEC_CUDA(cudaStreamWaitEvent(p->s_out, p->ev_cmp[slot], 0));
+    TQEC_CUDA(cudaMemcpyAsync(mar_out + o * NO, d_mar + o * NO, (size_t)n * NO * 8, cudaMemcpyDeviceToHost, p->s_out));
+    if (argmax_out) TQEC_CUDA(cudaMemcpyAsync(argmax_out + o, d_arg + o, (size_t)n * 4, cudaMemcpyDeviceToHost, p->s_out));
+  }
+  TQEC_CUDA(cudaStreamSynchronize(p->s_out));
   TQEC_CUDA(cudaStreamSynchronize(p->stream));
   return TQEC_OK;
 }
