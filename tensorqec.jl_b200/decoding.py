@@ -195,7 +195,7 @@ def tnmap_schedule(decoder: TNMAP, problem: GeneralDecodingProblem) -> S.Schedul
         # its shapes fall through to the general kernels
         try:
             su = S.lower(factors, checks, S.MAXPLUS, t.nq, t.ns, 0, order=order, fuse=False)
-            sw = lower_sweep(su, max_head_bits=int(os.environ.get("TQEC_HEAD_BITS", decoder.head_bits))) if 6 <= su.w_max <= 10 else None
+            sw = lower_sweep(su, max_head_bits=int(os.environ.get("TQEC_HEAD_BITS", decoder.head_bits))) if int(os.environ.get("TQEC_SWEEP_MINW", "5")) <= su.w_max <= 10 else None
         except ValueError:
             sw = None
         if sw is not None:
@@ -207,7 +207,7 @@ def tnmap_schedule(decoder: TNMAP, problem: GeneralDecodingProblem) -> S.Schedul
 def _attach_sweep(sch: S.Schedule, max_head_bits: int = 10):
     """Sum-product plans are never fused, so the schedule itself is what `lower_sweep` expects; plans it declines keep
     running on the general kernels."""
-    if os.environ.get("TQEC_NO_SWEEP") is None and 6 <= sch.w_max <= 10:
+    if os.environ.get("TQEC_NO_SWEEP") is None and 5 <= sch.w_max <= 10:
         try:
             sw = lower_sweep(sch, max_head_bits=max_head_bits)
         except ValueError:
