@@ -117,7 +117,9 @@ enum {
   TQEC_Q_TEAM_THREADS = 0, TQEC_Q_SHOTS_PER_TEAM = 1, TQEC_Q_SMEM_BYTES = 2, TQEC_Q_GRID = 3,
   TQEC_Q_TEAMS_PER_SM = 4, TQEC_Q_BP_BYTES_PER_TEAM = 5, TQEC_Q_CANDIDATES_PER_SHOT = 6, TQEC_Q_SM_COUNT = 7,
   TQEC_Q_LAUNCHES = 8, /* kernels launched through this plan so far */
-  TQEC_Q_SWEEP = 9     /* 1 if the plan decodes through the in-place patch sweep (k_sweep) */
+  TQEC_Q_SWEEP = 9,    /* 1 if the plan decodes through the in-place patch sweep (k_sweep) */
+  TQEC_Q_TABLE = 10    /* 1 if the plan is fully tabulated (n_checks <= 16): decode is a table look-up filled once, at
+                          plan creation, by the plan's own kernels; TQEC_NO_TABLE=1 in the environment disables it */
 };
 int tqec_plan_query(const tqec_plan *plan, int32_t what, int64_t *out);
 

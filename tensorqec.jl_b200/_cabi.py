@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("TQEC_CUDA_LIB", os.path.join(_HERE, "libtqec_cuda.so"
 OK = 0
 MODEL_FLIP, MODEL_DEPOL = 0, 1
 (Q_TEAM_THREADS, Q_SHOTS_PER_TEAM, Q_SMEM_BYTES, Q_GRID, Q_TEAMS_PER_SM, Q_BP_BYTES_PER_TEAM, Q_CANDIDATES_PER_SHOT,
- Q_SM_COUNT, Q_LAUNCHES, Q_SWEEP) = range(10)
+ Q_SM_COUNT, Q_LAUNCHES, Q_SWEEP, Q_TABLE) = range(11)
 
 EXPORTS = [
     "tqec_last_error", "tqec_version", "tqec_device_count",
@@ -166,7 +166,7 @@ class Plan:
                                                ("smem_bytes", Q_SMEM_BYTES), ("grid", Q_GRID),
                                                ("teams_per_sm", Q_TEAMS_PER_SM), ("bp_bytes_per_team", Q_BP_BYTES_PER_TEAM),
                                                ("candidates_per_shot", Q_CANDIDATES_PER_SHOT), ("sm_count", Q_SM_COUNT),
-                                               ("sweep", Q_SWEEP)]}
+                                               ("sweep", Q_SWEEP), ("table", Q_TABLE)]}
 
     def decode_map(self, synd_words: np.ndarray, want_logp=True):
         s = _c(synd_words, np.uint64).reshape(-1, self.nsw)

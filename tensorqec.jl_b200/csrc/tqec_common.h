@@ -87,6 +87,11 @@ struct tqec_plan {
   // in-place patch sweep (optional)
   tqec::SweepDev sw;
   int has_sweep, sw_teams, sw_smem, sw_maxt;
+  // fully tabulated plan (n_checks <= 16): outputs of every syndrome, filled once by the plan's own kernels
+  int has_table;
+  uint64_t *d_tab_corr;
+  double *d_tab_out;
+  int32_t *d_tab_arg;
   void *d_sw[8];
   uint32_t *d_sw_bp;
   void *d_hdr, *d_ints, *d_tables, *d_bp_off, *d_obs_slot;

@@ -711,9 +711,40 @@ __global__ void k_frontier_warp(const PlanDev P, const uint64_t *__restrict__ sy
                        (int64_t)gridDim.x * NW, synd, B, corr, out, argmax_out);
 }
 
+// ---- fully tabulated plans -------------------------------------------------------------------------------------------
+// A plan with at most TQEC_TABLE_BITS syndrome bits is decoded ONCE for every syndrome at compile time (by the kernels
+// above, so the table holds exactly their outputs) and `decode` becomes a gather: HBM-bound, 8 B in and 8..40 B out per
+// shot.  This is the tabulated head of the sweep taken to its end (and the reference's own TableDecoder,
+// src/decoding/truthtable.jl, built from the MAP decoder instead of from error enumeration).
+#define TQEC_TABLE_BITS 16
+__global__ void k_lookup(const uint64_t *__restrict__ synd, int64_t B, int nsw, uint64_t mask,
+                         const uint64_t *__restrict__ tab_corr, int ncw, const double *__restrict__ tab_out, int n_out,
+                         const int32_t *__restrict__ tab_arg, uint64_t *__restrict__ corr, double *__restrict__ out,
+                         int32_t *__restrict__ argmax_out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t s = synd[i * nsw] & mask;
+    if (corr)
+      for (int w = 0; w < ncw; ++w) corr[i * ncw + w] = __ldg(tab_corr + s * ncw + w);
+    if (out)
+      for (int k = 0; k < n_out; ++k) out[i * n_out + k] = __ldg(tab_out + s * n_out + k);
+    if (argmax_out) argmax_out[i] = __ldg(tab_arg + s);
+  }
+}
+
 int launch_decode(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d_corr, double *d_out,
                   int32_t *d_argmax, cudaStream_t stream) {
   if (B <= 0) return TQEC_OK;
+  if (plan->has_table) {
+    const bool mp = plan->semiring == TQEC_SEMIRING_MAXPLUS;
+    const int64_t want = (B + 255) / 256;
+    const int grid = (int)(want < (int64_t)plan->sm_count * 16 ? want : (int64_t)plan->sm_count * 16);
+    k_lookup<<<grid, 256, 0, stream>>>(d_synd, B, plan->dev.nsw, ((uint64_t)1 << plan->dev.n_checks) - 1, plan->d_tab_corr,
+                                       plan->dev.ncw, plan->d_tab_out, mp ? 1 : (1 << plan->dev.n_obs), plan->d_tab_arg,
+                                       mp ? d_corr : nullptr, d_out, mp ? nullptr : d_argmax);
+    TQEC_CUDA(cudaGetLastError());
+    plan->launches += 1;
+    return TQEC_OK;
+  }
   if (plan->has_sweep) return launch_sweep(plan, d_synd, B, d_corr, d_out, d_argmax, stream);
   const int64_t per_group = plan->dev.defer ? 32 : plan->shots_per_team;
   const int64_t groups = (B + per_group - 1) / per_group;
@@ -1080,6 +1111,28 @@ extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
   if (rc) { tqec_plan_destroy(p); return rc; }
   D.hdr = (const int32_t *)p->d_hdr; D.ints = (const int32_t *)p->d_ints; D.tables = (const double *)p->d_tables;
   D.bp_off = (const int32_t *)p->d_bp_off; D.obs_slot = (const int32_t *)p->d_obs_slot;
+  if (d->n_checks >= 1 && d->n_checks <= TQEC_TABLE_BITS && std::getenv("TQEC_NO_TABLE") == nullptr) {
+    // decode every syndrome once with the kernels of this plan; decode() is a table look-up from here on
+    const int64_t N = (int64_t)1 << d->n_checks;
+    const bool mp = d->semiring == TQEC_SEMIRING_MAXPLUS;
+    const int n_out = mp ? 1 : (1 << d->n_obs);
+    std::vector<uint64_t> all((size_t)N);
+    for (int64_t s = 0; s < N; ++s) all[(size_t)s] = (uint64_t)s;
+    uint64_t *d_all = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d_all, (size_t)N * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_tab_corr, (size_t)N * ncw * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_tab_out, (size_t)N * n_out * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_tab_arg, (size_t)N * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(d_all, all.data(), (size_t)N * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(p->d_tab_corr, 0, (size_t)N * ncw * 8);
+    if (e != cudaSuccess) { set_error("tabulating the plan: %s", cudaGetErrorString(e)); cudaFree(d_all); tqec_plan_destroy(p); return TQEC_ERR_NOMEM; }
+    rc = launch_decode(p, d_all, N, mp ? p->d_tab_corr : nullptr, p->d_tab_out, mp ? nullptr : p->d_tab_arg, p->stream);
+    if (!rc && cudaStreamSynchronize(p->stream) != cudaSuccess) { set_error("tabulating the plan: %s", cudaGetErrorString(cudaGetLastError())); rc = TQEC_ERR_CUDA; }
+    cudaFree(d_all);
+    if (rc) { tqec_plan_destroy(p); return rc; }
+    p->has_table = 1;
+    p->launches = 0;
+  }
   *out = p;
   return TQEC_OK;
 }
@@ -1089,6 +1142,7 @@ extern "C" int tqec_plan_destroy(tqec_plan *p) {
   cudaSetDevice(p->device);
   cudaFree(p->d_hdr); cudaFree(p->d_ints); cudaFree(p->d_tables); cudaFree(p->d_bp_off); cudaFree(p->d_obs_slot);
   cudaFree(p->d_bp);
+  cudaFree(p->d_tab_corr); cudaFree(p->d_tab_out); cudaFree(p->d_tab_arg);
   sweep_destroy(p);
   for (int i = 0; i < 4; ++i) cudaFree(p->d_io[i]);
   if (p->stream) cudaStreamDestroy(p->stream);
@@ -1115,6 +1169,7 @@ extern "C" int tqec_plan_query(const tqec_plan *p, int32_t what, int64_t *out) {
     case TQEC_Q_SM_COUNT: *out = p->sm_count; break;
     case TQEC_Q_LAUNCHES: *out = p->launches; break;
     case TQEC_Q_SWEEP: *out = p->has_sweep; break;
+    case TQEC_Q_TABLE: *out = p->has_table; break;
     default: set_error("tqec_plan_query: unknown item %d", what); return TQEC_ERR_INVALID;
   }
   return TQEC_OK;

@@ -144,6 +144,46 @@ def test_tnmap_small_codes(tq, code):
     assert tq.syndrome_extraction(res.error_pattern, t) == tq.CSSSyndrome(sx, sz)
 
 
+@pytest.mark.parametrize("code", ["surface3", "steane", "color488_5"])
+def test_tabulated_plans_equal_the_kernels(tq, code, monkeypatch):
+    """Plans with <= 16 syndrome bits are decoded once per syndrome at plan creation and served from that table
+    (TQEC_Q_TABLE): the table holds the kernels' own outputs, so both paths agree bit for bit -- on every syndrome of the
+    code for the small ones -- and with the oracle."""
+    from tensorqec.jl_b200 import _cabi
+    c = {"surface3": tq.SurfaceCode(3, 3), "steane": tq.SteaneCode(), "color488_5": tq.Color488(5)}[code]
+    t, em = _css_case(tq, c)
+    ct = tq.compile(tq.TNMAP(), t, em)
+    sch = ct.cd.schedule
+    assert ct.cd.plan.query(_cabi.Q_TABLE) == 1
+    ns = sch.n_checks
+    if ns <= 8:
+        syn = ((np.arange(1 << ns)[:, None] >> np.arange(ns)) & 1).astype(np.uint8)
+    else:
+        ex, ez, sx, sz = _syndromes(t, em, 21, 3000)
+        syn = np.concatenate([sx, sz], axis=1)
+    corr, logp = ct.cd.plan.decode_map(tq.pack_bits(syn))
+    monkeypatch.setenv("TQEC_NO_TABLE", "1")
+    plan2 = _cabi.Plan(sch, 0)
+    assert plan2.query(_cabi.Q_TABLE) == 0
+    corr2, logp2 = plan2.decode_map(tq.pack_bits(syn))
+    plan2.close()
+    assert np.array_equal(corr, corr2) and np.array_equal(logp, logp2)
+    lp, cfg = cref.FrontierPlan(sch).run(syn)
+    assert np.array_equal(tq.unpack_bits(corr, sch.n_vars), cfg) and np.array_equal(logp, lp)
+    # sum-product plans are tabulated the same way
+    if code == "surface3":
+        monkeypatch.delenv("TQEC_NO_TABLE")
+        ctm = tq.compile(tq.TNMMAP(), t, em)
+        assert ctm.plan.query(_cabi.Q_TABLE) == 1
+        mar, arg = ctm.plan.decode_marginal(tq.pack_bits(syn))
+        monkeypatch.setenv("TQEC_NO_TABLE", "1")
+        plan3 = _cabi.Plan(ctm.schedule, 0)
+        assert plan3.query(_cabi.Q_TABLE) == 0
+        mar3, arg3 = plan3.decode_marginal(tq.pack_bits(syn))
+        plan3.close()
+        assert np.array_equal(mar, mar3) and np.array_equal(arg, arg3)
+
+
 def test_tnmap_single_shot_and_classical(tq):
     t = tq.CSSTannerGraph(tq.SurfaceCode(3, 3))
     ct = tq.compile(tq.TNMAP(), t.stgz)                      # classical problem, iid_error(0.05, n) default
