@@ -8,7 +8,10 @@
 //      the same addresses and emits the packed back-pointer bits of the patch;
 //   3. after 32 shots (deferred traceback) lane q walks shot q backwards through the traceback records.
 // Bit-identical to the unfused schedule of schedule.py (same IEEE adds in the same order, strict > on ascending
-// candidates).  Shapes of a super-step come from tqec_sweep_menu.h.
+// candidates).  Shapes of a super-step come from tqec_sweep_menu.h.  Sum-product plans (TNMMAP) run the same code with
+// multiply / add layers, no back-pointers and no traceback; their open observable slots index the output marginals.
+// All teams of a CTA run the same number of rounds and meet at a CTA barrier once per group of 32 shots (sync_mode):
+// passes have identical instruction streams, so teams that stay in step share instruction-cache lines.
 #include <cstdlib>
 #include <cstring>
 #include <utility>

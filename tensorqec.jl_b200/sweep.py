@@ -15,6 +15,13 @@ The recurrence is the one of schedule.py (one factor absorbed per step, candidat
   * HEAD TABLE.  The first steps (narrow states, checks opened into fresh slots) depend on a handful of syndrome bits
     only; their result is tabulated at compile time for every value of those bits (state + partial configuration per
     entry) and a pass starts by copying one table row.
+  * LATE FOLD.  A check opened by the first layer of a super-step and closed by the second cannot be folded into the
+    load address (its slot still holds the first layer's closed check); its syndrome bit is applied to the second
+    layer's table rows (a row-swapped copy of the table, chosen per shot) and to the store address instead.
+  * PINNED / FREE VARIABLES.  A variable that opens a check is pinned to that check's output bit (the opened check
+    inherits the slot of a check the same variable closes) and may flip further patch bits when it is 1; a variable
+    that opens nothing is a candidate dimension (butterfly over its flip mask).  Observable checks of sum-product
+    plans are never closed: their slots stay live and index the output marginals.
   * The register-level wiring of a super-step (patch size, pinned bits, flip masks) must be one of the shapes compiled
     into the kernel (`MENU`, mirrored by csrc/tqec_sweep_menu.h).  Plans with any other step shape are not lowered
     (`lower_sweep` returns None) and run on the general kernels of csrc/tqec_decode.cu.
