@@ -103,6 +103,8 @@ typedef struct {
   const int32_t *obs_slot; /* n_obs: slot of observable i in the final state                      */
   int32_t device;          /* CUDA device ordinal                                                 */
   const tqec_sweep_desc *sweep; /* optional (NULL): in-place patch sweep of the same plan          */
+  int32_t table_bits;      /* plans with n_checks <= table_bits are fully tabulated at creation (0 = default 16,
+                              at most 26; table = 2^n_checks x (configuration words + outputs))    */
 } tqec_plan_desc;
 
 const char *tqec_last_error(void);

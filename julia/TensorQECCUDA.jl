@@ -36,6 +36,7 @@ struct PlanDesc
     tables::Ptr{Float64}; n_tables::Int64
     obs_slot::Ptr{Int32}; device::Int32
     sweep::Ptr{SweepDesc}
+    table_bits::Int32          # plans with n_checks <= table_bits are fully tabulated at creation (0 = default 16)
 end
 
 mutable struct Plan
@@ -53,7 +54,7 @@ mutable struct Plan
                 swp = swref === nothing ? Ptr{SweepDesc}(C_NULL) : Base.unsafe_convert(Ptr{SweepDesc}, swref)
                 d = PlanDesc(sch.semiring, sch.n_vars, sch.n_checks, sch.n_obs, sch.n_steps, sch.w_max,
                              pointer(sch.hdr), pointer(sch.ints), length(sch.ints),
-                             pointer(sch.tables), length(sch.tables), pointer(sch.obs_slot), device, swp)
+                             pointer(sch.tables), length(sch.tables), pointer(sch.obs_slot), device, swp, Int32(0))
                 check(ccall((:tqec_plan_create, LIB), Cint, (Ref{PlanDesc}, Ref{Ptr{Cvoid}}), d, href))
             end
         end

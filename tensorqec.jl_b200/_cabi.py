@@ -45,7 +45,8 @@ class PlanDesc(C.Structure):
                 ("n_steps", C.c_int32), ("w_max", C.c_int32),
                 ("hdr", C.POINTER(C.c_int32)), ("ints", C.POINTER(C.c_int32)), ("n_ints", C.c_int64),
                 ("tables", C.POINTER(C.c_double)), ("n_tables", C.c_int64),
-                ("obs_slot", C.POINTER(C.c_int32)), ("device", C.c_int32), ("sweep", C.POINTER(SweepDesc))]
+                ("obs_slot", C.POINTER(C.c_int32)), ("device", C.c_int32), ("sweep", C.POINTER(SweepDesc)),
+                ("table_bits", C.c_int32)]
 
 
 class McDesc(C.Structure):
@@ -141,7 +142,7 @@ class Plan:
         d = PlanDesc(sch.semiring, sch.n_vars, sch.n_checks, sch.n_obs, len(sch.steps), sch.w_max,
                      hdr.ctypes.data_as(C.POINTER(C.c_int32)), ints.ctypes.data_as(C.POINTER(C.c_int32)), ints.size,
                      tabs.ctypes.data_as(C.POINTER(C.c_double)), tabs.size,
-                     obs.ctypes.data_as(C.POINTER(C.c_int32)), device, None)
+                     obs.ctypes.data_as(C.POINTER(C.c_int32)), device, None, int(getattr(sch, "table_bits", 0) or 0))
         sw = getattr(sch, "sweep", None)
         if sw is not None:
             keep = [_c(sw.rec, np.int32), _c(sw.tb, np.int32), _c(sw.lanetab, np.uint32), _c(sw.tvals, np.float64),

@@ -1111,7 +1111,8 @@ extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
   if (rc) { tqec_plan_destroy(p); return rc; }
   D.hdr = (const int32_t *)p->d_hdr; D.ints = (const int32_t *)p->d_ints; D.tables = (const double *)p->d_tables;
   D.bp_off = (const int32_t *)p->d_bp_off; D.obs_slot = (const int32_t *)p->d_obs_slot;
-  if (d->n_checks >= 1 && d->n_checks <= TQEC_TABLE_BITS && std::getenv("TQEC_NO_TABLE") == nullptr) {
+  const int table_bits = d->table_bits <= 0 ? TQEC_TABLE_BITS : (d->table_bits > 26 ? 26 : d->table_bits);
+  if (d->n_checks >= 1 && d->n_checks <= table_bits && std::getenv("TQEC_NO_TABLE") == nullptr) {
     // decode every syndrome once with the kernels of this plan; decode() is a table look-up from here on
     const int64_t N = (int64_t)1 << d->n_checks;
     const bool mp = d->semiring == TQEC_SEMIRING_MAXPLUS;

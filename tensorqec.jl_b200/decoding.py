@@ -106,6 +106,8 @@ class TNMAP(AbstractGeneralDecoder):
     prior factors (e.g. the leaf order of a contraction tree found by the caller's TreeSA / GreedyMethod)."""
     optimizer: Any = None
     device: int = 0
+    table_bits: int = 16         # plans with at most this many syndrome bits are decoded once per syndrome at compile time
+                                 # and served from that table (k_lookup); up to 26 (table of 2^bits entries)
     head_bits: int = 10          # syndrome bits the tabulated head of the sweep lowering may depend on (sweep.py): more
                                  # bits = fewer steps per shot, a larger table (2^bits x 2^W entries) and a slower compile
 
@@ -128,6 +130,7 @@ class TNMMAP(AbstractGeneralDecoder):
     optimizer: Any = None
     factorize: bool = True
     device: int = 0
+    table_bits: int = 16         # as for TNMAP: problems with at most this many syndrome / detector bits are tabulated
 
     def __repr__(self):
         return "TNMMAP"
@@ -200,8 +203,11 @@ def tnmap_schedule(decoder: TNMAP, problem: GeneralDecodingProblem) -> S.Schedul
             sw = None
         if sw is not None:
             su.sweep = sw
+            su.table_bits = decoder.table_bits
             return su
-    return S.lower(factors, checks, S.MAXPLUS, t.nq, t.ns, 0, order=order)
+    sch = S.lower(factors, checks, S.MAXPLUS, t.nq, t.ns, 0, order=order)
+    sch.table_bits = decoder.table_bits
+    return sch
 
 
 def _attach_sweep(sch: S.Schedule, max_head_bits: int = 10):
@@ -285,6 +291,7 @@ def tnmmap_css_schedule(decoder: TNMMAP, problem: IndependentDepolarizingDecodin
     checks += [S.Check(tuple(int(q) for q in np.flatnonzero(lz[i])), "obs", k + i) for i in range(k)]
     sch = S.lower(factors, checks, S.SUMPROD, 2 * n, nsx + nsz, 2 * k, order=_order_of(decoder.optimizer, n))
     _attach_sweep(sch)
+    sch.table_bits = decoder.table_bits
     # error_pattern (tndecoder.jl:167-174): any solution of the syndrome equations, moved into the decoded sector
     Rz, _ = gf2_right_inverse(tanner.stgz.H)            # ex = Rz sz
     Rx, _ = gf2_right_inverse(tanner.stgx.H)            # ez = Rx sx
@@ -377,6 +384,7 @@ def tnmmap_dem_schedule(decoder: TNMMAP, dem: DetectorErrorModel):
     checks = [S.Check(tuple(c), "syn", d) for d, c in enumerate(tanner.s2q)]
     checks += [S.Check(tuple(c), "obs", l) for l, c in enumerate(l2q)]
     sch = S.lower(factors, checks, S.SUMPROD, ne, nd, len(l2q), order=_order_of(decoder.optimizer, ne))
+    sch.table_bits = decoder.table_bits
     R, _ = gf2_right_inverse(tanner.H)
     L = np.zeros((len(l2q), ne), dtype=np.uint8)
     for l, c in enumerate(l2q):

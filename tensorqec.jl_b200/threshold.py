@@ -40,7 +40,7 @@ class MonteCarlo:
         if not isinstance(decoder, TNMAP):
             raise TypeError("the fused Monte-Carlo pipeline drives the TNMAP decoder")
         device = decoder.device if device is None else device
-        decoder = TNMAP(decoder.optimizer, device, decoder.head_bits)
+        decoder = TNMAP(decoder.optimizer, device, decoder.table_bits, decoder.head_bits)
         self.device = device
         if isinstance(tanner, CSSTannerGraph):
             em = iid_error(0.05, tanner) if em is None else em
