@@ -33,7 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 D = 9
-HEAD_BITS = 12          # compile-time knob of the sweep lowering: the first 17 steps are tabulated (16.8 MB + 50 MB tables)
+HEAD_BITS = 14          # compile-time knob of the sweep lowering: the first 19 steps are tabulated (67 MB + 201 MB tables, 4 s)
 P_ERR = 0.05
 METRIC = "syndromes decoded/sec (TNMAP, d=9 surface code)"
 UNIT = "syndromes/s"

@@ -75,7 +75,7 @@ typedef struct {
   int32_t W;               /* slot bits of the state index                                        */
   int32_t sg;              /* log2(shots per team pass); W + sg = 10                               */
   int32_t n_ss;            /* super-steps                                                          */
-  int32_t n_head_bits;     /* syndrome bits the tabulated head depends on (<= 12)                  */
+  int32_t n_head_bits;     /* syndrome bits the tabulated head depends on (<= 16)                  */
   int32_t bp_words;        /* back-pointer words per lane per pass                                 */
   int32_t n_tvals;
   const int32_t *rec;      /* n_ss * 32: forward records                                           */

@@ -60,7 +60,7 @@ struct SweepDev {
   const uint32_t *lanetab;
   const double *tvals, *head_state;
   const uint64_t *head_cfg;
-  int32_t head_bits[12];
+  int32_t head_bits[16];
   int32_t out_index[16];            // state index of output entry i (max-plus: entry 0 only)
   int32_t n_ss, W, sg, nh, nsw, ncw, bp_words, n_tvals, n_obs;
   int32_t sync_mode;                // CTA barrier between teams: 0 none, 1 per group of 32 shots, 2 per pass

@@ -416,7 +416,7 @@ int sweep_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &pr
   TQEC_REQUIRE(s->W >= 1 && s->sg >= 0 && s->sg <= 5 && s->W + s->sg == 10, "sweep: W=%d sg=%d must add up to 10 index bits", s->W, s->sg);
   TQEC_REQUIRE(s->n_ss > 0 && s->rec && s->tb && s->lanetab && s->tvals && s->head_state && s->head_cfg && s->out_index,
                "sweep: missing table");
-  TQEC_REQUIRE(s->n_head_bits >= 0 && s->n_head_bits <= 12 && (s->n_head_bits == 0 || s->head_bits), "sweep: bad head bits");
+  TQEC_REQUIRE(s->n_head_bits >= 0 && s->n_head_bits <= 16 && (s->n_head_bits == 0 || s->head_bits), "sweep: bad head bits");
   const int nsw = words_for(d->n_checks), ncw = words_for(d->n_vars);
   TQEC_REQUIRE(nsw <= 4 && ncw <= 4, "sweep: more than 256 checks / variables");
   for (int i = 0; i < s->n_ss; ++i) {

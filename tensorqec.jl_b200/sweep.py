@@ -215,16 +215,16 @@ def _canonical(layers_raw, chains):
 def _head_eval(sch, h, roles, head_bits, live_order):
     """Tabulate the first h steps for every value of the syndrome bits they close.
     -> state (2^nh, 2^W) in slot order `live_order` (bit k of the index = parity of check live_order[k]) and, for
-    max-plus, the partial configuration of every entry as packed words (uint64 (2^nh, 2^W, ceil(n_vars/64)))."""
+    max-plus, the partial configuration of every entry as packed words (uint64 (2^nh, 2^W, ceil(n_vars/64))).
+    A closed check's axis is not indexed by a known syndrome bit but kept as a batch axis ("value of that syndrome
+    bit"), so the batch grows only as bits are closed and the early steps are evaluated once."""
     maxplus = sch.semiring == S.MAXPLUS
     nh = len(head_bits)
-    B = 1 << nh
-    hp = np.arange(B)
-    syn_of = {b: ((hp >> j) & 1) for j, b in enumerate(head_bits)}
     ncw = max(1, (sch.n_vars + 63) // 64)
-    axes: List[int] = []
-    St = np.full((B,), 0.0 if maxplus else 1.0)
-    cfg = np.zeros((B, ncw), dtype=np.uint64) if maxplus else None
+    batch: List[int] = []                           # syndrome bits closed so far = leading axes, in closing order
+    axes: List[int] = []                            # open checks = trailing axes
+    St = np.full((), 0.0 if maxplus else 1.0)
+    cfg = np.zeros((ncw,), dtype=np.uint64) if maxplus else None
     zero = -np.inf if maxplus else 0.0
     for t in range(h):
         fi, touched, opened, closing = roles[t]
@@ -235,6 +235,7 @@ def _head_eval(sch, h, roles, head_bits, live_order):
             if maxplus:
                 cfg = np.stack([cfg, cfg], axis=-2)
             axes.append(c)
+        nb = len(batch)
         best = None
         for a in range(1 << len(f.vars)):
             flips = []
@@ -245,7 +246,7 @@ def _head_eval(sch, h, roles, head_bits, live_order):
                         p ^= (a >> j) & 1
                 if p:
                     flips.append(c)
-            ax = tuple(axes.index(c) + 1 for c in flips)
+            ax = tuple(nb + axes.index(c) for c in flips)
             src = np.flip(St, axis=ax) if ax else St
             cand = src + T[a] if maxplus else src * T[a]
             if maxplus:
@@ -269,20 +270,21 @@ def _head_eval(sch, h, roles, head_bits, live_order):
         if maxplus:
             cfg = bcfg
         for c in closing:
-            k = axes.index(c) + 1
-            bit = syn_of[sch.checks[c].index].astype(np.intp)
-            ix = bit.reshape([B] + [1] * (St.ndim - 1))
-            St = np.take_along_axis(St, ix, axis=k).squeeze(axis=k)
+            # the check's parity must equal its syndrome bit: its axis becomes the batch axis of that bit
+            k = nb + axes.index(c)
+            St = np.moveaxis(St, k, nb)
             if maxplus:
-                cfg = np.take_along_axis(cfg, ix[..., None], axis=k).squeeze(axis=k)
-            axes.pop(k - 1)
-    # reorder axes to live_order, first slot fastest
-    assert sorted(axes) == sorted(live_order)
-    permu = [axes.index(c) + 1 for c in live_order]
+                cfg = np.moveaxis(cfg, k, nb)
+            axes.remove(c)
+            batch.append(sch.checks[c].index)
+            nb += 1
+    assert batch == list(head_bits) and sorted(axes) == sorted(live_order)
     W = len(live_order)
-    St = np.transpose(St, [0] + permu[::-1]).reshape(B, 1 << W)
+    # head pattern bit j = batch axis j, state index bit k = check live_order[k]: slowest axis first for a C reshape
+    permu = list(range(nh - 1, -1, -1)) + [nh + axes.index(c) for c in reversed(live_order)]
+    St = np.ascontiguousarray(np.transpose(St, permu)).reshape(1 << nh, 1 << W)
     if maxplus:
-        cfg = np.transpose(cfg, [0] + permu[::-1] + [cfg.ndim - 1]).reshape(B, 1 << W, ncw)
+        cfg = np.ascontiguousarray(np.transpose(cfg, permu + [cfg.ndim - 1])).reshape(1 << nh, 1 << W, ncw)
     return St, cfg
 
 
