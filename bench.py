@@ -256,6 +256,31 @@ def run_ours(args):
     # results of both paths agree (same kernel, same inputs)
     same = bool(torch.equal(h_cor, d_cor.cpu()) and torch.equal(h_lp, d_lp.cpu()))
 
+    # ---- ablation: the same decode with the shortest tabulated head (6 syndrome bits, 11 of the 81 steps looked up) ------
+    ablation = None
+    if rank == 0 and geom.get("sweep"):
+        gdp_a, _ = tq.reduce2general(t, em)
+        sch_a = tq.tnmap_schedule(tq.TNMAP(optimizer=_order(), device=local, head_bits=6), gdp_a)
+        plan_a = _cabi.Plan(sch_a, local)
+        d_cor_a = torch.empty_like(d_cor)
+        d_lp_a = torch.empty_like(d_lp)
+        for _ in range(2):
+            plan_a.decode_map_dev(d_syn.data_ptr(), B, d_cor_a.data_ptr(), d_lp_a.data_ptr(), stream.cuda_stream)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(2):
+            plan_a.decode_map_dev(d_syn.data_ptr(), B, d_cor_a.data_ptr(), d_lp_a.data_ptr(), stream.cuda_stream)
+        a1.record(stream)
+        torch.cuda.synchronize()
+        ablation = {"head_bits": 6, "tabulated_head_steps": sch_a.sweep.head_steps,
+                    "value_one_gpu": B * 2 / (a0.elapsed_time(a1) * 1e-3), "unit": UNIT,
+                    "identical_results": bool(torch.equal(d_cor_a, d_cor) and torch.equal(d_lp_a, d_lp))}
+        plan_a.close()
+        del d_cor_a, d_lp_a
+    if world > 1:
+        dist.barrier()
+
     # ---- logical error counters through the fused pipeline + the one collective -------------------------------------
     ler_shots = min(B, 1 << 20)
     counts, mc_ms = mc.run(ler_shots, seed=9, shot_offset=rank * ler_shots)
@@ -314,6 +339,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "head_ablation": ablation,
             "logical_errors": {"shots": int(counts[3]), "x": int(counts[0]), "z": int(counts[1]), "any": int(counts[2]),
                                "pipeline_ms_rank0": mc_ms},
         }
