@@ -88,6 +88,42 @@ typedef struct {
   const int32_t *out_index;/* 2^n_obs state indices of the output entries (max-plus: one)              */
 } tqec_sweep_desc;
 
+/* Optional lowering of a sum-product plan for the GLOBAL-MEMORY executor (tensorqec.jl_b200/wide.py, executed by
+ * k_wide_pass): plans whose frontier does not fit on chip (14..31 bits; the state, 2^w FP64 entries per shot, lives in
+ * HBM).  Steps are grouped into passes; a pass loads a tile of 2^t_in entries per value of its spectator bits, runs
+ * its steps in shared memory in tile-local coordinates and stores 2^t_out entries.  A descriptor that carries `wide`
+ * needs no `hdr` / `ints` / `tables` (n_steps = 0).  All tables are host pointers copied by tqec_plan_create. */
+#define TQEC_WIDE_PASS_INTS 16
+#define TQEC_WIDE_STEP_INTS 16
+enum { /* pass header */
+  TQEC_WP_WIN = 0, TQEC_WP_WOUT = 1,         /* global state width before / after the pass                           */
+  TQEC_WP_TIN = 2, TQEC_WP_TOUT = 3,         /* tile width before / after                                            */
+  TQEC_WP_NSTEPS = 4, TQEC_WP_STEP0 = 5,     /* the pass's steps in step_hdr                                         */
+  TQEC_WP_TINMASK = 6, TQEC_WP_TOUTMASK = 7, /* positions of the tile bits in the global index before / after        */
+  TQEC_WP_OFF_INTS = 8, TQEC_WP_N_INTS = 9,  /* the pass's block of `ints` (step offsets are relative to it)         */
+  TQEC_WP_OFF_TAB = 10, TQEC_WP_N_TAB = 11   /* the pass's block of `tables`                                         */
+};
+enum { /* local step header: tile-local widths; tables as in the TQEC_H_* step header */
+  TQEC_WL_WIN = 0, TQEC_WL_NOPEN = 1, TQEC_WL_NCLOSE = 2, TQEC_WL_WOUT = 3, TQEC_WL_NK = 4,
+  TQEC_WL_OFF_T = 5,     /* tables[off + pat*nk + k]                                                                 */
+  TQEC_WL_OFF_ML = 6,    /* ints[off + pat]                                                                          */
+  TQEC_WL_OFF_MK = 7,    /* ints[off + k]                                                                            */
+  TQEC_WL_OFF_CLOSE = 8, /* ints[off + 2c], [off + 2c + 1] = (full slot, syndrome bit) of closed check c             */
+  TQEC_WL_KEEPMASK = 9   /* full slots that survive; output bit b is the b-th set bit (monotone permutation)         */
+};
+typedef struct {
+  int32_t n_pass, n_steps;
+  int32_t w_cap;           /* widest global state over the plan (bits, <= 31)                     */
+  int32_t t_max;           /* widest tile (bits, <= 13)                                           */
+  const int32_t *pass_hdr; /* n_pass * TQEC_WIDE_PASS_INTS                                        */
+  const int32_t *step_hdr; /* n_steps * TQEC_WIDE_STEP_INTS                                       */
+  const int32_t *ints;
+  int64_t n_ints;
+  const double *tables;
+  int64_t n_tables;
+  const int32_t *obs_pos;  /* n_obs: position of observable i in the final index                  */
+} tqec_wide_desc;
+
 typedef struct {
   int32_t semiring;        /* TQEC_SEMIRING_*                                                     */
   int32_t n_vars;          /* error variables = bits of a decoded configuration                   */
@@ -104,7 +140,8 @@ typedef struct {
   int32_t device;          /* CUDA device ordinal                                                 */
   const tqec_sweep_desc *sweep; /* optional (NULL): in-place patch sweep of the same plan          */
   int32_t table_bits;      /* plans with n_checks <= table_bits are fully tabulated at creation (0 = default 16,
-                              at most 26; table = 2^n_checks x (configuration words + outputs))    */
+                              -1 = never, at most 26; table = 2^n_checks x (configuration words + outputs)) */
+  const tqec_wide_desc *wide; /* optional (NULL): global-memory lowering; takes precedence over hdr / sweep */
 } tqec_plan_desc;
 
 const char *tqec_last_error(void);
@@ -120,8 +157,10 @@ enum {
   TQEC_Q_TEAMS_PER_SM = 4, TQEC_Q_BP_BYTES_PER_TEAM = 5, TQEC_Q_CANDIDATES_PER_SHOT = 6, TQEC_Q_SM_COUNT = 7,
   TQEC_Q_LAUNCHES = 8, /* kernels launched through this plan so far */
   TQEC_Q_SWEEP = 9,    /* 1 if the plan decodes through the in-place patch sweep (k_sweep) */
-  TQEC_Q_TABLE = 10    /* 1 if the plan is fully tabulated (n_checks <= 16): decode is a table look-up filled once, at
+  TQEC_Q_TABLE = 10,   /* 1 if the plan is fully tabulated (n_checks <= 16): decode is a table look-up filled once, at
                           plan creation, by the plan's own kernels; TQEC_NO_TABLE=1 in the environment disables it */
+  TQEC_Q_WIDE = 11,    /* 1 if the plan decodes through the global-memory executor (k_wide_pass) */
+  TQEC_Q_WIDE_BATCH = 12 /* shots whose states are resident in HBM at a time (global-memory executor) */
 };
 int tqec_plan_query(const tqec_plan *plan, int32_t what, int64_t *out);
 

@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("TQEC_CUDA_LIB", os.path.join(_HERE, "libtqec_cuda.so"
 OK = 0
 MODEL_FLIP, MODEL_DEPOL = 0, 1
 (Q_TEAM_THREADS, Q_SHOTS_PER_TEAM, Q_SMEM_BYTES, Q_GRID, Q_TEAMS_PER_SM, Q_BP_BYTES_PER_TEAM, Q_CANDIDATES_PER_SHOT,
- Q_SM_COUNT, Q_LAUNCHES, Q_SWEEP, Q_TABLE) = range(11)
+ Q_SM_COUNT, Q_LAUNCHES, Q_SWEEP, Q_TABLE, Q_WIDE, Q_WIDE_BATCH) = range(13)
 
 EXPORTS = [
     "tqec_last_error", "tqec_version", "tqec_device_count",
@@ -40,13 +40,19 @@ class SweepDesc(C.Structure):
                 ("out_index", C.c_void_p)]
 
 
+class WideDesc(C.Structure):
+    _fields_ = [("n_pass", C.c_int32), ("n_steps", C.c_int32), ("w_cap", C.c_int32), ("t_max", C.c_int32),
+                ("pass_hdr", C.c_void_p), ("step_hdr", C.c_void_p), ("ints", C.c_void_p), ("n_ints", C.c_int64),
+                ("tables", C.c_void_p), ("n_tables", C.c_int64), ("obs_pos", C.c_void_p)]
+
+
 class PlanDesc(C.Structure):
     _fields_ = [("semiring", C.c_int32), ("n_vars", C.c_int32), ("n_checks", C.c_int32), ("n_obs", C.c_int32),
                 ("n_steps", C.c_int32), ("w_max", C.c_int32),
                 ("hdr", C.POINTER(C.c_int32)), ("ints", C.POINTER(C.c_int32)), ("n_ints", C.c_int64),
                 ("tables", C.POINTER(C.c_double)), ("n_tables", C.c_int64),
                 ("obs_slot", C.POINTER(C.c_int32)), ("device", C.c_int32), ("sweep", C.POINTER(SweepDesc)),
-                ("table_bits", C.c_int32)]
+                ("table_bits", C.c_int32), ("wide", C.POINTER(WideDesc))]
 
 
 class McDesc(C.Structure):
@@ -135,6 +141,22 @@ class Plan:
         require_device(device)
         self.sch = sch
         self.device = device
+        self.nsw = max(1, (sch.n_checks + 63) // 64)
+        self.ncw = max(1, (sch.n_vars + 63) // 64)
+        tb = getattr(sch, "table_bits", None)
+        table_bits = 0 if tb is None else (-1 if int(tb) <= 0 else int(tb))   # ABI: 0 = library default, -1 = never
+        if hasattr(sch, "pass_hdr"):
+            # global-memory lowering (wide.py): the descriptor carries only the `wide` tables
+            keep = [_c(sch.pass_hdr, np.int32), _c(sch.step_hdr, np.int32), _c(sch.ints, np.int32),
+                    _c(sch.tables, np.float64), _c(sch.obs_pos if sch.obs_pos else [0], np.int32)]
+            wd = WideDesc(len(sch.passes), keep[1].shape[0], sch.w_cap, sch.t_max, _ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]),
+                          keep[2].size, _ptr(keep[3]), keep[3].size, _ptr(keep[4]))
+            d = PlanDesc(sch.semiring, sch.n_vars, sch.n_checks, sch.n_obs, 0, sch.w_cap, None, None, 0, None, 0, None,
+                         device, None, table_bits, C.pointer(wd))
+            h = C.c_void_p()
+            check(lib().tqec_plan_create(C.byref(d), C.byref(h)))
+            self.h = h
+            return
         hdr = _c(sch.hdr, np.int32)
         ints = _c(sch.ints, np.int32)
         tabs = _c(sch.tables, np.float64)
@@ -142,7 +164,7 @@ class Plan:
         d = PlanDesc(sch.semiring, sch.n_vars, sch.n_checks, sch.n_obs, len(sch.steps), sch.w_max,
                      hdr.ctypes.data_as(C.POINTER(C.c_int32)), ints.ctypes.data_as(C.POINTER(C.c_int32)), ints.size,
                      tabs.ctypes.data_as(C.POINTER(C.c_double)), tabs.size,
-                     obs.ctypes.data_as(C.POINTER(C.c_int32)), device, None, int(getattr(sch, "table_bits", 0) or 0))
+                     obs.ctypes.data_as(C.POINTER(C.c_int32)), device, None, table_bits, None)
         sw = getattr(sch, "sweep", None)
         if sw is not None:
             keep = [_c(sw.rec, np.int32), _c(sw.tb, np.int32), _c(sw.lanetab, np.uint32), _c(sw.tvals, np.float64),
@@ -154,8 +176,6 @@ class Plan:
         h = C.c_void_p()
         check(lib().tqec_plan_create(C.byref(d), C.byref(h)))
         self.h = h
-        self.nsw = max(1, (sch.n_checks + 63) // 64)
-        self.ncw = max(1, (sch.n_vars + 63) // 64)
 
     def query(self, what: int) -> int:
         v = C.c_int64(0)
@@ -167,7 +187,7 @@ class Plan:
                                                ("smem_bytes", Q_SMEM_BYTES), ("grid", Q_GRID),
                                                ("teams_per_sm", Q_TEAMS_PER_SM), ("bp_bytes_per_team", Q_BP_BYTES_PER_TEAM),
                                                ("candidates_per_shot", Q_CANDIDATES_PER_SHOT), ("sm_count", Q_SM_COUNT),
-                                               ("sweep", Q_SWEEP), ("table", Q_TABLE)]}
+                                               ("sweep", Q_SWEEP), ("table", Q_TABLE), ("wide", Q_WIDE)]}
 
     def decode_map(self, synd_words: np.ndarray, want_logp=True):
         s = _c(synd_words, np.uint64).reshape(-1, self.nsw)

@@ -67,6 +67,14 @@ struct SweepDev {
   int32_t off_states, off_rec, off_lanetab, off_tvals, off_words, words_bytes;   // shared-memory layout (bytes)
 };
 
+// Device view of the global-memory lowering of a plan (tqec_wide.cu; tables described in tensorqec.jl_b200/wide.py).
+struct WideDev {
+  const int32_t *pass_hdr, *step_hdr, *ints;
+  const double *tables;
+  int32_t n_pass, n_steps, w_cap, t_max, n_obs, nsw;
+  int32_t obs_pos[16];
+};
+
 }  // namespace tqec
 
 struct tqec_plan {
@@ -94,6 +102,13 @@ struct tqec_plan {
   int32_t *d_tab_arg;
   void *d_sw[8];
   uint32_t *d_sw_bp;
+  // global-memory executor (optional): two state arrays of wd_batch << w_cap doubles, allocated at the first decode
+  tqec::WideDev wd;
+  int has_wide, wd_smem, wd_grid;
+  void *d_wd[4];
+  double *d_wd_state[2];
+  int64_t wd_batch;
+  int wd_full;            // the state arrays already take all the memory the executor may use
   void *d_hdr, *d_ints, *d_tables, *d_bp_off, *d_obs_slot;
   uint32_t *d_bp;        // back-pointer scratch: grid_max * bp_words
   // host staging for the host-pointer entry points
@@ -124,6 +139,9 @@ int launch_sweep(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d
                  cudaStream_t stream);
 int sweep_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &prop);
 void sweep_destroy(tqec_plan *p);
+int wide_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &prop);
+void wide_destroy(tqec_plan *p);
+int launch_wide(tqec_plan *plan, const uint64_t *d_synd, int64_t B, double *d_out, int32_t *d_argmax, cudaStream_t stream);
 int launch_gf2_apply(tqec_gf2 *m, const uint64_t *d_in, int64_t B, uint64_t *d_out, cudaStream_t stream);
 int launch_sample(int model, int n_sites, const double *d_p, uint64_t seed, int64_t shot_offset, int64_t B,
                   uint64_t *d_err, int words, cudaStream_t stream);

@@ -745,6 +745,7 @@ int launch_decode(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *
     plan->launches += 1;
     return TQEC_OK;
   }
+  if (plan->has_wide) return launch_wide(plan, d_synd, B, d_out, d_argmax, stream);
   if (plan->has_sweep) return launch_sweep(plan, d_synd, B, d_corr, d_out, d_argmax, stream);
   const int64_t per_group = plan->dev.defer ? 32 : plan->shots_per_team;
   const int64_t groups = (B + per_group - 1) / per_group;
@@ -909,10 +910,11 @@ static int validate_desc(const tqec_plan_desc *d) {
   TQEC_REQUIRE(d != nullptr, "tqec_plan_create: desc is NULL");
   TQEC_REQUIRE(d->semiring == TQEC_SEMIRING_MAXPLUS || d->semiring == TQEC_SEMIRING_SUMPROD,
                "tqec_plan_create: unknown semiring %d", d->semiring);
-  TQEC_REQUIRE(d->n_steps > 0 && d->hdr && d->ints && d->tables, "tqec_plan_create: empty schedule");
   TQEC_REQUIRE(d->n_vars >= 0 && d->n_checks >= 0 && d->n_obs >= 0 && d->n_obs <= 16,
                "tqec_plan_create: bad sizes (n_vars=%d n_checks=%d n_obs=%d)", d->n_vars, d->n_checks, d->n_obs);
   TQEC_REQUIRE(d->semiring == TQEC_SEMIRING_SUMPROD || d->n_obs == 0, "tqec_plan_create: max-plus plans have no open axes");
+  if (d->wide) return TQEC_OK;                                   // validated by wide_create
+  TQEC_REQUIRE(d->n_steps > 0 && d->hdr && d->ints && d->tables, "tqec_plan_create: empty schedule");
   TQEC_REQUIRE(d->n_obs == 0 || d->obs_slot, "tqec_plan_create: obs_slot is NULL");
   int w = 0, wmax = 0;
   for (int t = 0; t < d->n_steps; ++t) {
@@ -966,6 +968,39 @@ static int upload(void **dst, const T *src, size_t n) {
   return TQEC_OK;
 }
 
+// Plans with few syndrome bits: decode every syndrome once with the kernels of this plan; decode() is a table look-up
+// from here on.  table_bits: 0 = default (TQEC_TABLE_BITS), < 0 = never, at most 26.
+static int tabulate_plan(tqec_plan *p, const tqec_plan_desc *d) {
+  if (d->table_bits < 0) return TQEC_OK;
+  const int ncw = words_for(d->n_vars);
+  int rc = TQEC_OK;
+  const int table_bits = d->table_bits == 0 ? TQEC_TABLE_BITS : (d->table_bits > 26 ? 26 : d->table_bits);
+  if (d->n_checks >= 1 && d->n_checks <= table_bits && std::getenv("TQEC_NO_TABLE") == nullptr) {
+    const int64_t N = (int64_t)1 << d->n_checks;
+    const bool mp = d->semiring == TQEC_SEMIRING_MAXPLUS;
+    const int n_out = mp ? 1 : (1 << d->n_obs);
+    // cap the table by bytes as well: (configuration words + outputs + argmax) per syndrome, at most 2 GiB
+    if ((double)N * (ncw * 8.0 + n_out * 8.0 + 4.0) > 2147483648.0) return TQEC_OK;
+    std::vector<uint64_t> all((size_t)N);
+    for (int64_t s = 0; s < N; ++s) all[(size_t)s] = (uint64_t)s;
+    uint64_t *d_all = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d_all, (size_t)N * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_tab_corr, (size_t)N * ncw * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_tab_out, (size_t)N * n_out * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_tab_arg, (size_t)N * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(d_all, all.data(), (size_t)N * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(p->d_tab_corr, 0, (size_t)N * ncw * 8);
+    if (e != cudaSuccess) { set_error("tabulating the plan: %s", cudaGetErrorString(e)); cudaFree(d_all); return TQEC_ERR_NOMEM; }
+    rc = launch_decode(p, d_all, N, mp ? p->d_tab_corr : nullptr, p->d_tab_out, mp ? nullptr : p->d_tab_arg, p->stream);
+    if (!rc && cudaStreamSynchronize(p->stream) != cudaSuccess) { set_error("tabulating the plan: %s", cudaGetErrorString(cudaGetLastError())); rc = TQEC_ERR_CUDA; }
+    cudaFree(d_all);
+    if (rc) return rc;
+    p->has_table = 1;
+    p->launches = 0;
+  }
+  return TQEC_OK;
+}
+
 extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
   TQEC_REQUIRE(out != nullptr, "tqec_plan_create: out is NULL");
   *out = nullptr;
@@ -983,6 +1018,19 @@ extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
   p->device = d->device;
   p->semiring = d->semiring;
   p->sm_count = prop.multiProcessorCount;
+  if (d->wide) {
+    // global-memory executor: none of the on-chip machinery below applies
+    p->dev.n_vars = d->n_vars; p->dev.n_checks = d->n_checks; p->dev.n_obs = d->n_obs;
+    p->dev.nsw = words_for(d->n_checks); p->dev.ncw = words_for(d->n_vars);
+    cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); delete p; return TQEC_ERR_CUDA; }
+    rc = wide_create(p, d, prop);
+    if (rc) { tqec_plan_destroy(p); return rc; }
+    rc = tabulate_plan(p, d);
+    if (rc) { tqec_plan_destroy(p); return rc; }
+    *out = p;
+    return TQEC_OK;
+  }
 
   // launch geometry: ~1024 state entries per team; narrow plans pack several shots per team
   int target_bits = 10;
@@ -1111,29 +1159,8 @@ extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
   if (rc) { tqec_plan_destroy(p); return rc; }
   D.hdr = (const int32_t *)p->d_hdr; D.ints = (const int32_t *)p->d_ints; D.tables = (const double *)p->d_tables;
   D.bp_off = (const int32_t *)p->d_bp_off; D.obs_slot = (const int32_t *)p->d_obs_slot;
-  const int table_bits = d->table_bits <= 0 ? TQEC_TABLE_BITS : (d->table_bits > 26 ? 26 : d->table_bits);
-  if (d->n_checks >= 1 && d->n_checks <= table_bits && std::getenv("TQEC_NO_TABLE") == nullptr) {
-    // decode every syndrome once with the kernels of this plan; decode() is a table look-up from here on
-    const int64_t N = (int64_t)1 << d->n_checks;
-    const bool mp = d->semiring == TQEC_SEMIRING_MAXPLUS;
-    const int n_out = mp ? 1 : (1 << d->n_obs);
-    std::vector<uint64_t> all((size_t)N);
-    for (int64_t s = 0; s < N; ++s) all[(size_t)s] = (uint64_t)s;
-    uint64_t *d_all = nullptr;
-    cudaError_t e = cudaMalloc((void **)&d_all, (size_t)N * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_tab_corr, (size_t)N * ncw * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_tab_out, (size_t)N * n_out * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_tab_arg, (size_t)N * 4);
-    if (e == cudaSuccess) e = cudaMemcpy(d_all, all.data(), (size_t)N * 8, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemset(p->d_tab_corr, 0, (size_t)N * ncw * 8);
-    if (e != cudaSuccess) { set_error("tabulating the plan: %s", cudaGetErrorString(e)); cudaFree(d_all); tqec_plan_destroy(p); return TQEC_ERR_NOMEM; }
-    rc = launch_decode(p, d_all, N, mp ? p->d_tab_corr : nullptr, p->d_tab_out, mp ? nullptr : p->d_tab_arg, p->stream);
-    if (!rc && cudaStreamSynchronize(p->stream) != cudaSuccess) { set_error("tabulating the plan: %s", cudaGetErrorString(cudaGetLastError())); rc = TQEC_ERR_CUDA; }
-    cudaFree(d_all);
-    if (rc) { tqec_plan_destroy(p); return rc; }
-    p->has_table = 1;
-    p->launches = 0;
-  }
+  rc = tabulate_plan(p, d);
+  if (rc) { tqec_plan_destroy(p); return rc; }
   *out = p;
   return TQEC_OK;
 }
@@ -1145,6 +1172,7 @@ extern "C" int tqec_plan_destroy(tqec_plan *p) {
   cudaFree(p->d_bp);
   cudaFree(p->d_tab_corr); cudaFree(p->d_tab_out); cudaFree(p->d_tab_arg);
   sweep_destroy(p);
+  wide_destroy(p);
   for (int i = 0; i < 4; ++i) cudaFree(p->d_io[i]);
   if (p->stream) cudaStreamDestroy(p->stream);
   if (p->s_in) cudaStreamDestroy(p->s_in);
@@ -1171,6 +1199,8 @@ extern "C" int tqec_plan_query(const tqec_plan *p, int32_t what, int64_t *out) {
     case TQEC_Q_LAUNCHES: *out = p->launches; break;
     case TQEC_Q_SWEEP: *out = p->has_sweep; break;
     case TQEC_Q_TABLE: *out = p->has_table; break;
+    case TQEC_Q_WIDE: *out = p->has_wide; break;
+    case TQEC_Q_WIDE_BATCH: *out = p->wd_batch; break;
     default: set_error("tqec_plan_query: unknown item %d", what); return TQEC_ERR_INVALID;
   }
   return TQEC_OK;

@@ -1,0 +1,357 @@
+// Global-memory executor (k_wide_pass): sum-product frontier plans whose state does not fit on chip (14..31 bits).
+// Host side of the lowering and the full description: tensorqec.jl_b200/wide.py.  Per batch of shots the state lives in
+// two HBM arrays (entry sigma of shot b at (b << w_cap) | sigma, ping-pong).  One launch per PASS: for every value of
+// the pass's spectator bits and every shot, a CTA
+//   1. gathers the 2^t_in tile entries (bit deposit of the local index at the tile positions; the lowest index bits are
+//      always tile bits, so loads come in contiguous runs of 128 B),
+//   2. runs the pass's steps on the tile in shared memory (ping-pong; the generic gather of the frontier recurrence in
+//      tile-local coordinates: full = deposit(tau) | closed syndrome bits, candidates = coset of the opened pattern),
+//   3. scatters the 2^t_out entries of the result to the other array.
+// HBM traffic = one read + one write of the state per pass (instead of per step): 16 * 2^w bytes per pass and shot.
+#include <cstdlib>
+#include <cstring>
+
+#include "tqec_common.h"
+
+namespace tqec {
+
+#define WD_MAX_STEPS 64
+
+struct WidePassArgs {
+  const double *gin;
+  double *gout;
+  const uint64_t *synd;      // syndromes of the batch's first shot
+  int64_t nb;                // shots in the batch
+  const int32_t *pass;       // this pass's header
+  const int32_t *step_hdr, *ints;
+  const double *tables;
+  int32_t nsw, w_cap, t_max;
+};
+
+// deposit the low bits of x at the set bits of mask (software pdep; mask has at most 31 bits)
+__host__ __device__ __forceinline__ uint32_t wd_pdep(uint32_t x, uint32_t mask) {
+  uint32_t out = 0;
+  while (mask) {
+    const uint32_t low = mask & (0u - mask);
+    if (x & 1u) out |= low;
+    x >>= 1;
+    mask ^= low;
+  }
+  return out;
+}
+
+// one local step on the tile: Sout[tau] = sum_k Sin[(full & inmask) ^ ML[pat] ^ MK[k]] * T[pat * nk + k]
+template <int NK>
+__device__ __forceinline__ void wd_step(const int32_t *__restrict__ q, const int32_t *__restrict__ I, const double *__restrict__ T,
+                                        const uint32_t *__restrict__ sc, uint32_t cb, const double *__restrict__ Sin,
+                                        double *__restrict__ Sout, int tid, int NT) {
+  const int w_in = q[TQEC_WL_WIN], n_open = q[TQEC_WL_NOPEN], w_out = q[TQEC_WL_WOUT];
+  const int nk = NK > 0 ? NK : q[TQEC_WL_NK];
+  const int32_t *ML = I + q[TQEC_WL_OFF_ML], *MK = I + q[TQEC_WL_OFF_MK];
+  const double *Tt = T + q[TQEC_WL_OFF_T];
+  const uint32_t inmask = (1u << w_in) - 1u;
+  const int n = 1 << w_out;
+  if (n_open == 0) {
+    // nothing opened: one coset for every output, masks and factor values live in registers
+    const uint32_t m0 = (uint32_t)ML[0] ^ (uint32_t)MK[0], m1 = NK == 2 ? ((uint32_t)ML[0] ^ (uint32_t)MK[1]) : 0u;
+    const double t0 = Tt[0], t1 = NK == 2 ? Tt[1] : 0.0;
+    if (NK == 1 || NK == 2) {
+      for (int tau = tid; tau < n; tau += NT) {
+        const uint32_t low = (sc[tau & 63] | sc[64 + (tau >> 6)] | cb) & inmask;
+        double acc = Sin[low ^ m0] * t0;
+        if (NK == 2) acc += Sin[low ^ m1] * t1;
+        Sout[tau] = acc;
+      }
+      return;
+    }
+  }
+  for (int tau = tid; tau < n; tau += NT) {
+    const uint32_t full = sc[tau & 63] | sc[64 + (tau >> 6)] | cb;
+    const uint32_t pat = full >> w_in;
+    const uint32_t low = (full & inmask) ^ (uint32_t)ML[pat];
+    const double *tb = Tt + pat * nk;
+    double acc = Sin[low ^ (uint32_t)MK[0]] * tb[0];
+    for (int k = 1; k < nk; ++k) acc += Sin[low ^ (uint32_t)MK[k]] * tb[k];
+    Sout[tau] = acc;
+  }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_wide_pass(const WidePassArgs A) {
+  extern __shared__ __align__(16) unsigned char wd_smem[];
+  const int tid = threadIdx.x;
+  const int32_t *ph = A.pass;
+  const int w_in = ph[TQEC_WP_WIN], w_out = ph[TQEC_WP_WOUT], t_in = ph[TQEC_WP_TIN], t_out = ph[TQEC_WP_TOUT];
+  const int ns = ph[TQEC_WP_NSTEPS], s0 = ph[TQEC_WP_STEP0];
+  const uint32_t tin = (uint32_t)ph[TQEC_WP_TINMASK], tout = (uint32_t)ph[TQEC_WP_TOUTMASK];
+  const int n_ints = ph[TQEC_WP_N_INTS], n_tab = ph[TQEC_WP_N_TAB];
+  double *S0 = reinterpret_cast<double *>(wd_smem);
+  double *S1 = S0 + ((size_t)1 << A.t_max);
+  double *sT = S1 + ((size_t)1 << A.t_max);
+  int32_t *sI = reinterpret_cast<int32_t *>(sT + ((n_tab + 1) & ~1));
+  int32_t *sQ = sI + ((n_ints + 3) & ~3);                        // step headers of the pass
+  uint32_t *dep = reinterpret_cast<uint32_t *>(sQ + ns * TQEC_WIDE_STEP_INTS);   // [0..127] input, [128..255] output deposits
+  uint32_t *sc = dep + 256;                                      // two scatter tables of 128 entries (double-buffered)
+  uint32_t *cbs = sc + 256;                                      // closed-bit value of every step for the current shot
+  for (int i = tid; i < n_tab; i += NT) sT[i] = A.tables[ph[TQEC_WP_OFF_TAB] + i];
+  for (int i = tid; i < n_ints; i += NT) sI[i] = A.ints[ph[TQEC_WP_OFF_INTS] + i];
+  for (int i = tid; i < ns * TQEC_WIDE_STEP_INTS; i += NT) sQ[i] = A.step_hdr[(size_t)s0 * TQEC_WIDE_STEP_INTS + i];
+  if (tid < 128) {
+    const uint32_t x = tid < 64 ? (uint32_t)tid : ((uint32_t)(tid - 64) << 6);
+    dep[tid] = wd_pdep(x, tin);
+    dep[128 + tid] = wd_pdep(x, tout);
+  }
+  __syncthreads();
+  const int n_spec = w_in - t_in;
+  const uint32_t spec_in = (w_in >= 32 ? 0xffffffffu : ((1u << w_in) - 1u)) & ~tin;
+  const uint32_t spec_out = (w_out >= 32 ? 0xffffffffu : ((1u << w_out) - 1u)) & ~tout;
+  const int64_t n_tiles = A.nb << n_spec;
+  const int n_in = 1 << t_in, n_out = 1 << t_out;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t b = tile >> n_spec;
+    const uint32_t sp = (uint32_t)(tile & (((int64_t)1 << n_spec) - 1));
+    const double *gi = A.gin + ((size_t)b << A.w_cap) + wd_pdep(sp, spec_in);
+    double *go = A.gout + ((size_t)b << A.w_cap) + wd_pdep(sp, spec_out);
+    if (tid < ns) {
+      const int32_t *q = sQ + tid * TQEC_WIDE_STEP_INTS;
+      const int32_t *CL = sI + q[TQEC_WL_OFF_CLOSE];
+      const uint64_t *syn = A.synd + (size_t)b * A.nsw;
+      uint32_t v = 0;
+      for (int c = 0; c < q[TQEC_WL_NCLOSE]; ++c) {
+        const int sb = CL[2 * c + 1];
+        v |= (uint32_t)((__ldg(syn + (sb >> 6)) >> (sb & 63)) & 1ull) << CL[2 * c];
+      }
+      cbs[tid] = v;
+    }
+    if (tid >= 128 && tid < 256) {                               // scatter table of the first step
+      const int i = tid - 128;
+      const uint32_t x = i < 64 ? (uint32_t)i : ((uint32_t)(i - 64) << 6);
+      sc[i] = wd_pdep(x, (uint32_t)sQ[TQEC_WL_KEEPMASK]);
+    }
+    for (int l = tid; l < n_in; l += NT) S0[l] = __ldcs(gi + (dep[l & 63] | dep[64 + (l >> 6)]));
+    __syncthreads();
+    double *Sin = S0, *Sout = S1;
+    for (int s = 0; s < ns; ++s) {
+      const int32_t *q = sQ + s * TQEC_WIDE_STEP_INTS;
+      const uint32_t *scs = sc + ((s & 1) << 7);
+      if (s + 1 < ns && tid < 128) {                             // scatter table of the next step (other buffer)
+        const uint32_t x = tid < 64 ? (uint32_t)tid : ((uint32_t)(tid - 64) << 6);
+        sc[(((s + 1) & 1) << 7) + tid] = wd_pdep(x, (uint32_t)q[TQEC_WIDE_STEP_INTS + TQEC_WL_KEEPMASK]);
+      }
+      const int nk = q[TQEC_WL_NK];
+      if (nk == 1) wd_step<1>(q, sI, sT, scs, cbs[s], Sin, Sout, tid, NT);
+      else if (nk == 2) wd_step<2>(q, sI, sT, scs, cbs[s], Sin, Sout, tid, NT);
+      else wd_step<0>(q, sI, sT, scs, cbs[s], Sin, Sout, tid, NT);
+      __syncthreads();
+      double *tmp = Sin; Sin = Sout; Sout = tmp;
+    }
+    for (int l = tid; l < n_out; l += NT) __stcs(go + (dep[128 + (l & 63)] | dep[192 + (l >> 6)]), Sin[l]);
+    __syncthreads();
+  }
+}
+
+__global__ void k_wide_init(double *g, int64_t nb, int w_cap) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nb) g[(size_t)i << w_cap] = 1.0;
+}
+
+// marginals over the open observable slots (observable 0 fastest) and their first maximal entry (findmax)
+__global__ void k_wide_out(const WideDev P, const double *__restrict__ g, int64_t nb, double *__restrict__ out,
+                           int32_t *__restrict__ argmax_out) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const int NO = 1 << P.n_obs;
+  double best = -1.0;
+  int bi = 0;
+  for (int idx = 0; idx < NO; ++idx) {
+    uint32_t src = 0;
+    for (int o = 0; o < P.n_obs; ++o) src |= ((uint32_t)(idx >> o) & 1u) << P.obs_pos[o];
+    const double v = g[((size_t)b << P.w_cap) + src];
+    out[b * NO + idx] = v;
+    if (v > best) { best = v; bi = idx; }
+  }
+  if (argmax_out) argmax_out[b] = bi;
+}
+
+static const int WD_THREADS = 256;
+
+static size_t wide_smem_bytes(int t_max, int n_tab, int n_ints, int ns) {
+  size_t b = ((size_t)16 << t_max);
+  b += (size_t)((n_tab + 1) & ~1) * 8;
+  b += (size_t)((n_ints + 3) & ~3) * 4;
+  b += (size_t)ns * TQEC_WIDE_STEP_INTS * 4;
+  b += (256 + 256 + WD_MAX_STEPS) * 4;
+  return (b + 15) & ~(size_t)15;
+}
+
+template <typename T>
+static int wd_upload(void **slot, const T *src, size_t n) {
+  TQEC_CUDA(cudaMalloc(slot, (n ? n : 1) * sizeof(T)));
+  if (n) TQEC_CUDA(cudaMemcpy(*slot, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  return TQEC_OK;
+}
+
+void wide_destroy(tqec_plan *p) {
+  for (int i = 0; i < 4; ++i) if (p->d_wd[i]) cudaFree(p->d_wd[i]);
+  for (int i = 0; i < 2; ++i) if (p->d_wd_state[i]) cudaFree(p->d_wd_state[i]);
+}
+
+// Validate and upload the global-memory lowering of a plan descriptor.
+int wide_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &prop) {
+  const tqec_wide_desc *w = d->wide;
+  p->has_wide = 0;
+  TQEC_REQUIRE(d->semiring == TQEC_SEMIRING_SUMPROD, "wide: the global-memory executor runs sum-product plans only");
+  TQEC_REQUIRE(w->n_pass > 0 && w->n_steps > 0 && w->pass_hdr && w->step_hdr && w->ints && w->tables, "wide: missing table");
+  TQEC_REQUIRE(w->w_cap >= 0 && w->w_cap <= 31 && w->t_max >= 1 && w->t_max <= 13, "wide: w_cap=%d t_max=%d out of range", w->w_cap, w->t_max);
+  TQEC_REQUIRE(d->n_obs == 0 || w->obs_pos, "wide: obs_pos is NULL");
+  size_t smem = 0;
+  int wcur = 0, step = 0;
+  for (int i = 0; i < w->n_pass; ++i) {
+    const int32_t *h = w->pass_hdr + (size_t)i * TQEC_WIDE_PASS_INTS;
+    const int w_in = h[TQEC_WP_WIN], w_out = h[TQEC_WP_WOUT], t_in = h[TQEC_WP_TIN], t_out = h[TQEC_WP_TOUT], ns = h[TQEC_WP_NSTEPS];
+    TQEC_REQUIRE(w_in == wcur, "wide pass %d: w_in=%d does not continue the previous width %d", i, w_in, wcur);
+    TQEC_REQUIRE(w_in <= w->w_cap && w_out <= w->w_cap && t_in <= w->t_max && t_out <= w->t_max && t_in <= w_in && t_out <= w_out &&
+                     w_in - t_in == w_out - t_out,
+                 "wide pass %d: inconsistent widths (w %d -> %d, tile %d -> %d)", i, w_in, w_out, t_in, t_out);
+    TQEC_REQUIRE(__builtin_popcount((uint32_t)h[TQEC_WP_TINMASK]) == t_in && ((uint64_t)(uint32_t)h[TQEC_WP_TINMASK] >> w_in) == 0 &&
+                     __builtin_popcount((uint32_t)h[TQEC_WP_TOUTMASK]) == t_out && ((uint64_t)(uint32_t)h[TQEC_WP_TOUTMASK] >> w_out) == 0,
+                 "wide pass %d: bad tile masks", i);
+    TQEC_REQUIRE(ns >= 1 && ns <= WD_MAX_STEPS && h[TQEC_WP_STEP0] == step && step + ns <= w->n_steps, "wide pass %d: bad step range", i);
+    const int64_t oi = h[TQEC_WP_OFF_INTS], ni = h[TQEC_WP_N_INTS], ot = h[TQEC_WP_OFF_TAB], nt = h[TQEC_WP_N_TAB];
+    TQEC_REQUIRE(oi >= 0 && ni >= 0 && oi + ni <= w->n_ints && ot >= 0 && nt >= 0 && ot + nt <= w->n_tables, "wide pass %d: pool block out of range", i);
+    int t = t_in;
+    for (int s = 0; s < ns; ++s) {
+      const int32_t *q = w->step_hdr + (size_t)(step + s) * TQEC_WIDE_STEP_INTS;
+      const int lw_in = q[TQEC_WL_WIN], n_open = q[TQEC_WL_NOPEN], n_close = q[TQEC_WL_NCLOSE], lw_out = q[TQEC_WL_WOUT], nk = q[TQEC_WL_NK];
+      TQEC_REQUIRE(lw_in == t && n_open >= 0 && n_open <= 10 && n_close >= 0 && lw_out == lw_in + n_open - n_close && lw_out >= 0 &&
+                       lw_out <= w->t_max && lw_in + n_open <= 31,
+                   "wide step %d: inconsistent widths", step + s);
+      TQEC_REQUIRE(nk >= 1 && nk <= 1024, "wide step %d: bad candidate count %d", step + s, nk);
+      const int64_t np = (int64_t)1 << n_open;
+      TQEC_REQUIRE(q[TQEC_WL_OFF_T] >= 0 && q[TQEC_WL_OFF_T] + np * nk <= nt, "wide step %d: table offset out of range", step + s);
+      TQEC_REQUIRE(q[TQEC_WL_OFF_ML] >= 0 && q[TQEC_WL_OFF_ML] + np <= ni && q[TQEC_WL_OFF_MK] >= 0 && q[TQEC_WL_OFF_MK] + nk <= ni &&
+                       q[TQEC_WL_OFF_CLOSE] >= 0 && q[TQEC_WL_OFF_CLOSE] + 2 * (int64_t)n_close <= ni,
+                   "wide step %d: int table out of range", step + s);
+      const int32_t *I = w->ints + oi;
+      for (int pp = 0; pp < np; ++pp) TQEC_REQUIRE(((uint32_t)I[q[TQEC_WL_OFF_ML] + pp] >> lw_in) == 0, "wide step %d: mask leaves the tile", step + s);
+      for (int k = 0; k < nk; ++k) TQEC_REQUIRE(((uint32_t)I[q[TQEC_WL_OFF_MK] + k] >> lw_in) == 0, "wide step %d: mask leaves the tile", step + s);
+      uint32_t used = 0;
+      for (int c = 0; c < n_close; ++c) {
+        const int slot = I[q[TQEC_WL_OFF_CLOSE] + 2 * c], bit = I[q[TQEC_WL_OFF_CLOSE] + 2 * c + 1];
+        TQEC_REQUIRE(slot >= 0 && slot < lw_in + n_open && !((used >> slot) & 1u), "wide step %d: bad closed slot", step + s);
+        TQEC_REQUIRE(bit >= 0 && bit < d->n_checks, "wide step %d: syndrome bit out of range", step + s);
+        used |= 1u << slot;
+      }
+      const uint32_t keep = (uint32_t)q[TQEC_WL_KEEPMASK];
+      TQEC_REQUIRE((keep & used) == 0 && __builtin_popcount(keep) == lw_out && ((uint64_t)keep >> (lw_in + n_open)) == 0,
+                   "wide step %d: bad keep mask", step + s);
+      t = lw_out;
+    }
+    TQEC_REQUIRE(t == t_out, "wide pass %d: steps end at tile width %d, header says %d", i, t, t_out);
+    const size_t need = wide_smem_bytes(w->t_max, (int)nt, (int)ni, ns);
+    if (need > smem) smem = need;
+    wcur = w_out;
+    step += ns;
+  }
+  TQEC_REQUIRE(wcur == d->n_obs && step == w->n_steps, "wide: final state has %d bits but n_obs=%d", wcur, d->n_obs);
+  for (int o = 0; o < d->n_obs; ++o) TQEC_REQUIRE(w->obs_pos[o] >= 0 && w->obs_pos[o] < d->n_obs, "wide: obs_pos[%d] out of range", o);
+  if (smem > (size_t)prop.sharedMemPerBlockOptin) {
+    set_error("wide: a pass needs %zu B of shared memory > %zu available", smem, (size_t)prop.sharedMemPerBlockOptin);
+    return TQEC_ERR_UNSUPPORTED;
+  }
+  WideDev &D = p->wd;
+  std::memset(&D, 0, sizeof(D));
+  D.n_pass = w->n_pass; D.n_steps = w->n_steps; D.w_cap = w->w_cap; D.t_max = w->t_max; D.n_obs = d->n_obs; D.nsw = words_for(d->n_checks);
+  for (int o = 0; o < d->n_obs; ++o) D.obs_pos[o] = w->obs_pos[o];
+  int rc;
+  if ((rc = wd_upload(&p->d_wd[0], w->pass_hdr, (size_t)w->n_pass * TQEC_WIDE_PASS_INTS))) return rc;
+  if ((rc = wd_upload(&p->d_wd[1], w->step_hdr, (size_t)w->n_steps * TQEC_WIDE_STEP_INTS))) return rc;
+  if ((rc = wd_upload(&p->d_wd[2], w->ints, (size_t)w->n_ints))) return rc;
+  if ((rc = wd_upload(&p->d_wd[3], w->tables, (size_t)w->n_tables))) return rc;
+  D.pass_hdr = (const int32_t *)p->d_wd[0]; D.step_hdr = (const int32_t *)p->d_wd[1]; D.ints = (const int32_t *)p->d_wd[2];
+  D.tables = (const double *)p->d_wd[3];
+  p->wd_smem = (int)smem;
+  TQEC_CUDA(cudaFuncSetAttribute(k_wide_pass<WD_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  TQEC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wide_pass<WD_THREADS>, WD_THREADS, smem));
+  if (per_sm < 1) per_sm = 1;
+  p->wd_grid = per_sm * p->sm_count;
+  p->teams_per_sm = per_sm;
+  p->team_threads = WD_THREADS;
+  p->smem_bytes = (int)smem;
+  p->grid_max = p->wd_grid;
+  // candidate evaluations per shot
+  double cand = 0.0;
+  for (int i = 0; i < w->n_pass; ++i) {
+    const int32_t *h = w->pass_hdr + (size_t)i * TQEC_WIDE_PASS_INTS;
+    const int n_spec = h[TQEC_WP_WIN] - h[TQEC_WP_TIN];
+    for (int s = 0; s < h[TQEC_WP_NSTEPS]; ++s) {
+      const int32_t *q = w->step_hdr + (size_t)(h[TQEC_WP_STEP0] + s) * TQEC_WIDE_STEP_INTS;
+      cand += std::ldexp(1.0, n_spec + q[TQEC_WL_WOUT]) * q[TQEC_WL_NK];
+    }
+  }
+  p->candidates_per_shot = cand;
+  p->has_wide = 1;
+  return TQEC_OK;
+}
+
+// Shots whose states fit the device at once: 80 % of the free memory (TQEC_WIDE_MEM_GB overrides), two arrays, at most
+// 4096 shots.  The arrays are allocated at the first decode and grown when a larger batch arrives.
+static int wide_reserve(tqec_plan *p, int64_t want) {
+  if (p->wd_batch >= want || (p->wd_batch > 0 && p->wd_full)) return TQEC_OK;
+  const size_t per_shot = (size_t)16 << p->wd.w_cap;
+  for (int i = 0; i < 2; ++i) { if (p->d_wd_state[i]) cudaFree(p->d_wd_state[i]); p->d_wd_state[i] = nullptr; }
+  p->wd_batch = 0;
+  size_t free_b = 0, total_b = 0;
+  TQEC_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  double budget = 0.8 * (double)free_b;
+  if (const char *e = std::getenv("TQEC_WIDE_MEM_GB")) { const double v = std::atof(e) * 1e9; if (v > 0 && v < budget) budget = v; }
+  int64_t nb = (int64_t)(budget / (double)per_shot);
+  if (nb > 4096) nb = 4096;
+  p->wd_full = nb <= want;
+  if (nb > want) nb = want;
+  if (nb < 1) {
+    set_error("wide: one shot needs %zu B of state, %zu B free on the device", per_shot, free_b);
+    return TQEC_ERR_NOMEM;
+  }
+  for (int i = 0; i < 2; ++i) {
+    cudaError_t e = cudaMalloc((void **)&p->d_wd_state[i], (size_t)nb * (per_shot / 2));
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu B wide state): %s", (size_t)nb * (per_shot / 2), cudaGetErrorString(e));
+      return TQEC_ERR_NOMEM;
+    }
+  }
+  p->wd_batch = nb;
+  return TQEC_OK;
+}
+
+int launch_wide(tqec_plan *plan, const uint64_t *d_synd, int64_t B, double *d_out, int32_t *d_argmax, cudaStream_t stream) {
+  int rc = wide_reserve(plan, B);
+  if (rc) return rc;
+  const WideDev &D = plan->wd;
+  const int NO = 1 << D.n_obs;
+  for (int64_t o = 0; o < B; o += plan->wd_batch) {
+    const int64_t nb = B - o < plan->wd_batch ? B - o : plan->wd_batch;
+    k_wide_init<<<(unsigned)((nb + 255) / 256), 256, 0, stream>>>(plan->d_wd_state[0], nb, D.w_cap);
+    int cur = 0;
+    for (int i = 0; i < D.n_pass; ++i) {
+      WidePassArgs A;
+      A.gin = plan->d_wd_state[cur]; A.gout = plan->d_wd_state[cur ^ 1];
+      A.synd = d_synd + (size_t)o * D.nsw; A.nb = nb;
+      A.pass = D.pass_hdr + (size_t)i * TQEC_WIDE_PASS_INTS; A.step_hdr = D.step_hdr; A.ints = D.ints; A.tables = D.tables;
+      A.nsw = D.nsw; A.w_cap = D.w_cap; A.t_max = D.t_max;
+      // tiles of the pass: the host copy of the header is not kept, so size the grid for the widest case and let the
+      // kernel's tile loop run short
+      k_wide_pass<WD_THREADS><<<plan->wd_grid, WD_THREADS, plan->wd_smem, stream>>>(A);
+      cur ^= 1;
+      plan->launches += 1;
+    }
+    k_wide_out<<<(unsigned)((nb + 127) / 128), 128, 0, stream>>>(D, plan->d_wd_state[cur], nb, d_out + (size_t)o * NO,
+                                                                 d_argmax ? d_argmax + o : nullptr);
+    TQEC_CUDA(cudaGetLastError());
+    plan->launches += 2;
+  }
+  return TQEC_OK;
+}
+
+}  // namespace tqec

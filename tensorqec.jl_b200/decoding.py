@@ -21,6 +21,7 @@ import numpy as np
 
 from . import _cabi, schedule as S
 from .sweep import lower_sweep
+from .wide import lower_wide
 from .dem import DetectorErrorModel, dem2tanner
 from .error_model import (AbstractErrorModel, CSSErrorPattern, CSSSyndrome, IndependentDepolarizingError,
                           IndependentFlipError, SimpleSyndrome, iid_error)
@@ -210,10 +211,23 @@ def tnmap_schedule(decoder: TNMAP, problem: GeneralDecodingProblem) -> S.Schedul
     return sch
 
 
-def _attach_sweep(sch: S.Schedule, max_head_bits: int = 10):
+def _lower_sumprod(factors, checks, n_vars, n_checks, n_obs, order):
+    """Sum-product plan of a marginal network: the on-chip schedule (schedule.py) when the frontier fits 13 bits, else
+    the global-memory lowering (wide.py).  The order is chosen once and shared by both."""
+    all_check_vars = {v for c in checks for v in c.vars}
+    merged = S.merge_overlapping(list(factors), n_vars, all_check_vars)
+    order = S.map_order(factors, merged, order) if order is not None else S.choose_order(merged, checks)
+    w_max, _ = S._evaluate(order, S._Sim(merged, checks))
+    if w_max <= S.MAX_SMEM_WIDTH and os.environ.get("TQEC_FORCE_WIDE") is None:
+        return S.lower(merged, checks, S.SUMPROD, n_vars, n_checks, n_obs, order=order)
+    return lower_wide(merged, checks, S.SUMPROD, n_vars, n_checks, n_obs, order=order,
+                      t_max=int(os.environ.get("TQEC_WIDE_TMAX", "12")))
+
+
+def _attach_sweep(sch, max_head_bits: int = 10):
     """Sum-product plans are never fused, so the schedule itself is what `lower_sweep` expects; plans it declines keep
     running on the general kernels."""
-    if os.environ.get("TQEC_NO_SWEEP") is None and 5 <= sch.w_max <= 10:
+    if os.environ.get("TQEC_NO_SWEEP") is None and hasattr(sch, "steps") and 5 <= sch.w_max <= 10:
         try:
             sw = lower_sweep(sch, max_head_bits=max_head_bits)
         except ValueError:
@@ -289,7 +303,7 @@ def tnmmap_css_schedule(decoder: TNMMAP, problem: IndependentDepolarizingDecodin
     # open axes, in the reference's output order iy (tndecoder.jl:134): lx-parities of Z errors, then lz-parities of X errors
     checks += [S.Check(tuple(int(q) + n for q in np.flatnonzero(lx[i])), "obs", i) for i in range(k)]
     checks += [S.Check(tuple(int(q) for q in np.flatnonzero(lz[i])), "obs", k + i) for i in range(k)]
-    sch = S.lower(factors, checks, S.SUMPROD, 2 * n, nsx + nsz, 2 * k, order=_order_of(decoder.optimizer, n))
+    sch = _lower_sumprod(factors, checks, 2 * n, nsx + nsz, 2 * k, _order_of(decoder.optimizer, n))
     _attach_sweep(sch)
     sch.table_bits = decoder.table_bits
     # error_pattern (tndecoder.jl:167-174): any solution of the syndrome equations, moved into the decoded sector
@@ -383,7 +397,7 @@ def tnmmap_dem_schedule(decoder: TNMMAP, dem: DetectorErrorModel):
     factors = [S.Factor((e,), np.array([1.0 - p, p])) for e, p in enumerate(dem.error_rates)]
     checks = [S.Check(tuple(c), "syn", d) for d, c in enumerate(tanner.s2q)]
     checks += [S.Check(tuple(c), "obs", l) for l, c in enumerate(l2q)]
-    sch = S.lower(factors, checks, S.SUMPROD, ne, nd, len(l2q), order=_order_of(decoder.optimizer, ne))
+    sch = _lower_sumprod(factors, checks, ne, nd, len(l2q), _order_of(decoder.optimizer, ne))
     sch.table_bits = decoder.table_bits
     R, _ = gf2_right_inverse(tanner.H)
     L = np.zeros((len(l2q), ne), dtype=np.uint8)

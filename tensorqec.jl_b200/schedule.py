@@ -49,6 +49,7 @@ HDR_INTS = 16
 
 MAX_FACTOR_RANK = 10
 MAX_SMEM_WIDTH = 13            # 2 * 2^13 * 8 B = 128 KiB of ping-pong state per team
+MAX_WIDE_WIDTH = 31            # the global-memory executor (wide.py, k_wide_pass): state of 2^w FP64 entries in HBM
 
 
 @dataclass
@@ -173,6 +174,27 @@ def merge_overlapping(factors: Sequence[Factor], n_vars: int, check_vars) -> Lis
     return out
 
 
+def map_order(original: Sequence[Factor], merged: Sequence[Factor], order: Sequence[int]) -> List[int]:
+    """A caller's absorption order refers to ITS prior tensors (e.g. the leaf order of an OMEinsum tree); the schedule
+    absorbs the merged factors (overlapping priors multiplied, unity factors appended).  Each merged factor takes the
+    place of the first of its members in the caller's order; factors the caller does not know come last."""
+    order = [int(i) for i in order]
+    if sorted(order) != list(range(len(original))):
+        raise ValueError("order must be a permutation of the prior tensors")
+    home = {}
+    for mi, f in enumerate(merged):
+        for v in f.vars:
+            home[v] = mi
+    out: List[int] = []
+    for i in order:
+        for v in original[i].vars:
+            mi = home[v]
+            if mi not in out:
+                out.append(mi)
+    out += [mi for mi in range(len(merged)) if mi not in out]
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------
 class _Sim:
     """Incremental frontier simulation used by the ordering heuristic."""
@@ -276,29 +298,98 @@ def _greedy_order(sim, start):
     return order
 
 
+def spectral_orders(sim) -> List[List[int]]:
+    """Sweep orders from the Fiedler vector of the check graph (two checks are adjacent when a factor touches both):
+    the second eigenvector of its Laplacian is a smooth coordinate along the longest extent of the graph, and absorbing
+    the factors in the order of the largest coordinate among their checks sweeps a front across it.  For the 3-D
+    detector graphs of circuit-level models this finds fronts far narrower than the local greedy search (d = 5 x 5
+    rounds surface-code memory: 29 bits against 35).  Observable rows are left out (they touch factors all along a
+    logical operator and would short-circuit the graph); connected components are swept one after the other."""
+    nF = len(sim.factors)
+    ids = [c for c, ch in enumerate(sim.checks) if ch.kind == "syn"]
+    if len(ids) < 3:
+        return []
+    loc = {c: k for k, c in enumerate(ids)}
+    n = len(ids)
+    A = np.zeros((n, n))
+    for fc in sim.f_checks:
+        fc = [loc[c] for c in fc if c in loc]
+        for a in fc:
+            for b in fc:
+                if a != b:
+                    A[a, b] = 1.0
+    comp = [-1] * n
+    comps = []
+    for s0 in range(n):
+        if comp[s0] >= 0:
+            continue
+        comp[s0] = len(comps)
+        stack, members = [s0], []
+        while stack:
+            u = stack.pop()
+            members.append(u)
+            for v in np.flatnonzero(A[u]):
+                if comp[v] < 0:
+                    comp[v] = len(comps)
+                    stack.append(int(v))
+        comps.append(sorted(members))
+    x = np.zeros(n)
+    base = 0.0
+    for members in comps:
+        if len(members) >= 3:
+            sub = A[np.ix_(members, members)]
+            _, vecs = np.linalg.eigh(np.diag(sub.sum(axis=1)) - sub)
+            v = vecs[:, 1]
+            if v[int(np.argmax(np.abs(v)))] < 0:                  # eigenvectors are defined up to a sign: fix it
+                v = -v
+            v = v - v.min()
+        else:
+            v = np.arange(len(members), dtype=np.float64)
+        x[members] = base + v
+        base += float(v.max()) + 1.0
+    out = []
+    for xx in (x, -x):
+        hi = [max((xx[loc[c]] for c in sim.f_checks[i] if c in loc), default=0.0) for i in range(nF)]
+        out.append(sorted(range(nF), key=lambda i: (hi[i], i)))
+    return out
+
+
 def choose_order(factors, checks, max_starts=24):
     """Pick the absorption order: the best (by candidate evaluations per shot) of the natural order, its reverse,
-    and greedy minimum-frontier sweeps from several starting factors."""
+    greedy minimum-frontier sweeps from several starting factors, and the spectral sweeps."""
     sim = _Sim(factors, checks)
     nF = len(factors)
     cands = [list(range(nF)), list(range(nF - 1, -1, -1))]
+    if nF > 600:
+        max_starts = 6                                            # the greedy search is quadratic in the factor count
     deg = sorted(range(nF), key=lambda i: (len(sim.f_checks[i]), i))
     starts = list(dict.fromkeys(deg[: max_starts // 2] + [0, nF - 1] + list(range(0, nF, max(1, nF // (max_starts // 2))))))
     for s in starts[:max_starts]:
         cands.append(_greedy_order(sim, s))
     scored = [(_evaluate(o, sim), i) for i, o in enumerate(cands)]
     (wmax, cost), i = min(scored, key=lambda x: (_score(x[0][0], x[0][1], nF), x[0][0], x[1]))
+    if wmax > MAX_SMEM_WIDTH:
+        # too wide for the on-chip kernels: the plan will run on the global-memory executor, where only the width and
+        # the candidate count matter; add the spectral sweeps (never consulted for plans that fit on chip, so their
+        # orders -- and the kernels' tie-breaks -- are unchanged)
+        n0 = len(cands)
+        cands += spectral_orders(sim)
+        scored += [(_evaluate(o, sim), n0 + k) for k, o in enumerate(cands[n0:])]
+        (wmax, cost), i = min(scored, key=lambda x: (x[0][0], x[0][1], x[1]))
     return cands[i]
 
 
 # ------------------------------------------------------------------------------------------------------------
 def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_vars: int, n_checks: int,
           n_obs: int = 0, order: Optional[Sequence[int]] = None, max_width: int = MAX_SMEM_WIDTH,
-          fuse: Optional[bool] = None, _split=None) -> Schedule:
+          fuse: Optional[bool] = None, _split=None, stable: bool = False) -> Schedule:
     """Factor graph -> `Schedule` (see module docstring).  `order` optionally fixes the absorption order of the
-    (merged) factors, e.g. the leaf order of a contraction tree chosen by the caller's optimiser."""
+    (merged) factors, e.g. the leaf order of a contraction tree chosen by the caller's optimiser.  `stable` keeps the
+    surviving checks in their relative order and puts opened checks on top (a monotone `perm`): the layout of the
+    global-memory executor (wide.py), where a bit permutation is data movement instead of address arithmetic."""
     all_check_vars = {v for c in checks for v in c.vars}
-    factors = merge_overlapping(list(factors), n_vars, all_check_vars)
+    original = list(factors)
+    factors = merge_overlapping(original, n_vars, all_check_vars)
     checks = [Check(tuple(dict.fromkeys(c.vars)), c.kind, c.index) for c in checks]
     for c in checks:
         if c.kind not in ("syn", "obs"):
@@ -306,11 +397,15 @@ def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_v
     if order is None:
         order = choose_order(factors, checks)
     order = list(order)
+    if len(order) == len(original) and len(original) != len(factors):
+        order = map_order(original, factors, order)              # the caller's order refers to its own prior tensors
     if sorted(order) != list(range(len(factors))):
         raise ValueError("order must be a permutation of the (merged) factors")
     if fuse is None:
         import os as _os
         fuse = semiring == MAXPLUS and _os.environ.get("TQEC_NO_FUSE") is None
+    if stable:
+        fuse = False
     if fuse and _split is None:
         # absorb consecutive factor pairs as one step where that yields the 16-output block form: greedy pairing along
         # the order; a pair that does not come out in the canonical form is forbidden and the pairing redone from there
@@ -367,8 +462,8 @@ def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_v
         touched, opened, closing = plan[t]
         w_in = len(live)
         full = live + opened
-        if len(full) > 40:
-            raise ValueError(f"frontier needs {len(full)} bits > {max_width}: the schedule does not fit the on-chip state "
+        if len(full) > MAX_WIDE_WIDTH:
+            raise ValueError(f"frontier needs {len(full)} bits > {MAX_WIDE_WIDTH}: no executor holds such a state "
                              f"(choose a sweep-like absorption order)")
         pos = {c: k for k, c in enumerate(full)}
         closed = sorted((pos[c], checks[c].index) for c in closing)
@@ -423,7 +518,10 @@ def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_v
         nxt = set(plan[t + 1][2]) if t + 1 < len(order) else set()
         cn = [c for c in kept_old if c in nxt and c not in km]
         others = [c for c in kept_old if c not in km and c not in cn]
-        if quad and len(others) + len(cn) >= 5 + (q5 is None) + (q6 is None):
+        if stable:
+            quad = False
+            out_old = kept_old
+        elif quad and len(others) + len(cn) >= 5 + (q5 is None) + (q6 is None):
             pool = others + cn                                   # bits 0-4, fillers for an unused generator bit, rest
             low, pool = pool[:5], pool[5:]
             b5 = q5 if q5 is not None else pool.pop(0)
@@ -455,8 +553,7 @@ def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_v
         cost += float(1 << w_out) * len(ker)
         wmax = max(wmax, w_in, w_out)                        # the full index is never materialised
     if wmax > max_width:
-        raise ValueError(f"frontier needs {wmax} bits > {max_width}: the schedule does not fit the on-chip state "
-                         f"(wider plans need the global-memory executor, not built yet)")
+        raise ValueError(f"frontier needs {wmax} bits > {max_width}: the schedule does not fit the on-chip state")
     obs_slot = [-1] * n_obs
     for k, c in enumerate(live):
         if checks[c].kind != "obs":

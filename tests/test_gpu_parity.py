@@ -417,6 +417,42 @@ def test_dem_from_generated_circuit(tq):
     assert (res.sector == true_obs).mean() > 0.97
 
 
+@pytest.mark.parametrize("t_max", [8, 12])
+def test_wide_executor_circuit_level_d3(tq, monkeypatch, t_max):
+    """The global-memory executor (k_wide_pass) on a plan the on-chip kernels also run: circuit-level d=3 x 3 rounds DEM
+    forced through the wide lowering, with 8-bit tiles (passes with up to 4 spectator bits: 16 tiles per shot) and with
+    12-bit tiles, against the recurrence oracle, its emulator and the on-chip kernels."""
+    from oracle import wide_emulator
+    from tensorqec.jl_b200 import _cabi
+    txt = tq.surface_memory_circuit(3, 3, "Z", after_clifford_depolarization=2e-3, before_round_data_depolarization=2e-3,
+                                    before_measure_flip_probability=2e-3, after_reset_flip_probability=2e-3)
+    dem = tq.detector_error_model(tq.parse_stim_string(txt))
+    on_chip = tq.compile(tq.TNMMAP(table_bits=0), dem)
+    assert on_chip.plan.query(_cabi.Q_WIDE) == 0
+    monkeypatch.setenv("TQEC_FORCE_WIDE", "1")
+    monkeypatch.setenv("TQEC_WIDE_TMAX", str(t_max))
+    ct = tq.compile(tq.TNMMAP(table_bits=0), dem)
+    assert ct.plan.query(_cabi.Q_WIDE) == 1 and ct.plan.query(_cabi.Q_TABLE) == 0
+    B = 300
+    ep = tq.random_error_pattern(dem, seed=11, shots=B)
+    syn = tq.syndrome_extraction(ep, ct.tanner)
+    res = tq.decode(ct, syn)
+    assert syn == tq.syndrome_extraction(res.error_pattern, ct.tanner)
+    wp = ct.schedule
+    got = res.marginal.reshape(B, -1, order="F")
+    ref = frontier.run(wp.factors, wp.checks, wp.order, 1, syn.s[:16], wp.n_vars)
+    assert np.allclose(got[:16], ref, rtol=MAR_RTOL, atol=0)
+    emu = wide_emulator.run(wp, syn.s[:16])
+    assert np.allclose(got[:16], emu, rtol=1e-13, atol=0)           # same operations in the same order (FMA contraction aside)
+    chip = tq.decode(on_chip, syn)
+    assert np.allclose(got, chip.marginal.reshape(B, -1, order="F"), rtol=MAR_RTOL, atol=0)
+    assert np.array_equal(res.sector, chip.sector)
+    # single shot and an empty batch
+    one = tq.decode(ct, tq.SimpleSyndrome(syn.s[7]))
+    assert np.allclose(one.marginal.reshape(-1, order="F"), got[7], rtol=1e-15, atol=0)
+    assert ct.plan.query(_cabi.Q_WIDE_BATCH) >= 1
+
+
 def test_property_full_size_d9(tq):
     """BASELINE config 3 shape (d=9, p=0.05) at a size the oracle cannot follow shot by shot: size-independent
     properties -- every correction reproduces its syndrome, decoding is idempotent on its own output's syndrome,

@@ -1,0 +1,69 @@
+"""CPU tests of the global-memory lowering (tensorqec.jl_b200/wide.py): the flat pass / step tables, executed by the
+table-level emulator exactly as `k_wide_pass` reads them, against the recurrence oracle written over named axes."""
+import numpy as np
+import pytest
+
+import tensorqec.jl_b200 as tq
+from oracle import frontier, wide_emulator
+from tensorqec.jl_b200 import decoding, schedule as S, wide as W
+
+
+def _dem_graph(dem):
+    tanner = tq.dem2tanner(dem)
+    ne, nd = tanner.nq, tanner.ns
+    l2q = [[e for e in range(ne) if l in dem.flipped_detectors[e]] for l in dem.logical_list]
+    factors = [S.Factor((e,), np.array([1.0 - p, p])) for e, p in enumerate(dem.error_rates)]
+    checks = [S.Check(tuple(c), "syn", d) for d, c in enumerate(tanner.s2q)]
+    checks += [S.Check(tuple(c), "obs", l) for l, c in enumerate(l2q)]
+    return factors, checks, ne, nd, len(l2q), tanner
+
+
+@pytest.mark.parametrize("t_max,low", [(8, 4), (8, 2), (12, 4)])
+def test_wide_tables_match_recurrence_circuit_level_d3(t_max, low):
+    txt = tq.surface_memory_circuit(3, 3, "Z", 0.01, 0.01, 0.01, 0.01)
+    dem = tq.detector_error_model(tq.parse_stim_string(txt))
+    factors, checks, ne, nd, no, tanner = _dem_graph(dem)
+    wp = W.lower_wide(factors, checks, S.SUMPROD, ne, nd, no, t_max=t_max, low_bits=low)
+    assert all(p.t_peak <= t_max for p in wp.passes)
+    assert sum(len(p.steps) for p in wp.passes) == ne
+    if t_max == 8:
+        assert any(p.w_in > p.t_in for p in wp.passes), "no pass with spectator bits: the tile path is not exercised"
+    rng = np.random.RandomState(3)
+    e = (rng.rand(6, ne) < np.array(dem.error_rates) * 8).astype(np.uint8)
+    syn = (e @ tanner.H.T.astype(np.int64)) % 2
+    got = wide_emulator.run(wp, syn)
+    ref = frontier.run(wp.factors, wp.checks, wp.order, 1, syn, ne)
+    assert np.allclose(got, ref, rtol=1e-13, atol=0)
+
+
+def test_wide_tables_css_tnmmap_rank2_factors():
+    """CSS marginal network (rank-2 priors, 2 open observables, up to 4 candidates per output) through the wide lowering."""
+    t = tq.CSSTannerGraph(tq.SurfaceCode(5, 5))
+    em = tq.iid_error(0.03, t)
+    prob = decoding.IndependentDepolarizingDecodingProblem(t, em)
+    n = 25
+    lx, lz = tq.logical_operator(t)
+    factors = [S.Factor((i, i + n), S.flat_table(decoding.single_qubit_tensor(em.px[i], em.py[i], em.pz[i]))) for i in range(n)]
+    checks = [S.Check(tuple(q + n for q in c), "syn", i) for i, c in enumerate(t.stgx.s2q)]
+    checks += [S.Check(tuple(c), "syn", 12 + i) for i, c in enumerate(t.stgz.s2q)]
+    checks += [S.Check(tuple(int(q) + n for q in np.flatnonzero(lx[0])), "obs", 0)]
+    checks += [S.Check(tuple(int(q) for q in np.flatnonzero(lz[0])), "obs", 1)]
+    wp = W.lower_wide(factors, checks, S.SUMPROD, 2 * n, 24, 2, t_max=5, low_bits=1)
+    assert len(wp.passes) > 3
+    rng = np.random.RandomState(5)
+    syn = rng.randint(0, 2, size=(5, 24)).astype(np.uint8)
+    got = wide_emulator.run(wp, syn)
+    ref = frontier.run(wp.factors, wp.checks, wp.order, 1, syn, 2 * n)
+    assert np.allclose(got, ref, rtol=1e-13, atol=0)
+
+
+def test_spectral_order_narrows_the_3d_detector_graph():
+    """d = 5 x 5 rounds circuit-level memory (BASELINE configs[3]): the spectral sweep finds a 29-bit front."""
+    txt = tq.surface_memory_circuit(5, 5, "Z", 0.001, 0.001, 0.001, 0.001)
+    dem = tq.detector_error_model(tq.parse_stim_string(txt))
+    factors, checks, ne, nd, no, _ = _dem_graph(dem)
+    sim = S._Sim(factors, checks)
+    best = min(S._evaluate(o, sim)[0] for o in S.spectral_orders(sim))
+    assert best <= 29
+    wp = W.lower_wide(factors, checks, S.SUMPROD, ne, nd, no, order=min(S.spectral_orders(sim), key=lambda o: S._evaluate(o, sim)))
+    assert wp.w_cap <= 29 and wp.bytes_per_shot < 1.2e11
