@@ -190,11 +190,13 @@ int tqec_gf2_apply_dev(tqec_gf2 *m, const uint64_t *d_in, int64_t n_shots, uint6
  * e1 xor e2.  counts (may be NULL) += {#shots with bit 0, #shots with bit 1, #shots with any, #shots}. */
 int tqec_logical_flags(tqec_gf2 *L, const int32_t *row_class, const uint64_t *e1, const uint64_t *e2,
                        int64_t n_shots, uint8_t *flags_out, int64_t counts[4]);
-/* TNMMAP error pattern: e = R * synd (any solution of H e = synd), then for every observable row i of L whose
- * parity on e differs from bit i of sector[shot], e ^= fix[i] (fix = the conjugate logical, packed like e).
- * R: n_vars x n_checks; L, FIX: n_obs x n_vars. */
+/* TNMMAP error pattern: e = R * synd (any solution of H e = synd), then moved into sector[shot] by the rows of FIX:
+ * undetectable patterns (H f = 0) whose sector flips d_j = L f_j are in reduced echelon form (the lowest set bit of d_j
+ * is its pivot, no other row has it) -- for a CSS code the conjugate logicals, in general a basis of the reachable
+ * flips (joint flips of several observables included).  R: n_vars x n_checks; L: n_obs x n_vars (n_obs <= 16);
+ * FIX: at most n_obs rows x n_vars.  ok_out (may be NULL): B bytes, 1 iff e ends in the requested sector. */
 int tqec_coset_rep(tqec_gf2 *R, tqec_gf2 *L, tqec_gf2 *FIX, const uint64_t *synd, const int32_t *sector,
-                   int64_t n_shots, uint64_t *err_out);
+                   int64_t n_shots, uint64_t *err_out, uint8_t *ok_out);
 
 /* ---- sampling --------------------------------------------------------------------------------------------- */
 #define TQEC_MODEL_FLIP 0  /* IndependentFlipError: bit i flips iff u < p0[i]            (error_model.jl:69-71)  */

@@ -25,6 +25,7 @@ def lib():
         _lib = C.CDLL(_SO)
         _lib.oracle_dense_run.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
         _lib.oracle_frontier_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
+        _lib.oracle_frontier_wide_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
     return _lib
 
 
@@ -176,6 +177,16 @@ class FrontierPlan:
         k = self._keep
         self.c = _FrontierC(sch.semiring, sch.n_vars, sch.n_checks, sch.n_obs, len(sch.steps), sch.w_max, _p(k["hdr"]),
                             _p(k["ints"]), _p(k["tables"]), _p(k["obs"]))
+
+    def run_wide(self, syndromes, threads=0):
+        """Sum-product plans of any width up to 31 bits lowered with the stable layout: one shot at a time, threads
+        over the state entries (oracle_frontier_wide_run)."""
+        words = _pack(syndromes)
+        B = words.shape[0]
+        out = np.zeros((B, 1 << self.sch.n_obs))
+        rc = lib().oracle_frontier_wide_run(C.byref(self.c), _p(words), B, _p(out), threads)
+        assert rc == 0, f"oracle_frontier_wide_run failed ({rc})"
+        return np.ldexp(out, getattr(self.sch, "log2_scale", 0))
 
     def run(self, syndromes, threads=0, want_config=True):
         words = _pack(syndromes)

@@ -283,6 +283,64 @@ int oracle_frontier_run(const frontier_plan *P, const uint64_t *syn, int64_t B, 
   return fail;
 }
 
+/* (3) oracle_frontier_wide_run: the same recurrence for plans whose state has up to 2^31 entries (circuit-level detector
+ *     error models): one shot at a time, OpenMP over the OUTPUT entries of a step, no per-step scatter tables -- the
+ *     schedule must be lowered with the stable layout (monotone perm: schedule.lower(..., stable=True)), so that the
+ *     scatter is one bit deposit.  Sum-product only.  Used to make the d = 5 x 5 rounds golden marginals
+ *     (tests/golden/make_dem_d5_golden.py) with an absorption order DIFFERENT from the one the CUDA path uses. */
+#include <immintrin.h>
+int oracle_frontier_wide_run(const frontier_plan *P, const uint64_t *syn, int64_t B, double *out, int n_threads) {
+  if (P->semiring == 0) return 2;
+  const int sw = (P->n_checks + 63) / 64 > 0 ? (P->n_checks + 63) / 64 : 1;
+  const size_t stride = (size_t)1 << P->w_max;
+  const int NO = 1 << P->n_obs;
+  double *S0 = (double *)malloc(sizeof(double) * stride), *S1 = (double *)malloc(sizeof(double) * stride);
+  if (!S0 || !S1) { free(S0); free(S1); return 1; }
+#ifdef _OPENMP
+  if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+  int bad = 0;
+  for (int64_t b = 0; b < B && !bad; ++b) {
+    const uint64_t *sy = syn + b * sw;
+    double *Sin = S0, *Sout = S1;
+    Sin[0] = 1.0;
+    for (int t = 0; t < P->n_steps; ++t) {
+      const int32_t *h = P->hdr + t * HDR_INTS;
+      const int w_in = h[H_WIN], w_out = h[H_WOUT], nk = h[H_NK], n_close = h[H_NCLOSE];
+      const double *T = P->tables + h[H_OFF_T];
+      const int32_t *ML = P->ints + h[H_OFF_ML], *MK = P->ints + h[H_OFF_MK], *CL = P->ints + h[H_OFF_CLOSE];
+      const int32_t *perm = CL + 2 * n_close;
+      uint32_t keep = 0;
+      for (int q = 0; q < w_out; ++q) {
+        if (q > 0 && perm[q] <= perm[q - 1]) bad = 1;            /* not the stable layout */
+        keep |= 1u << perm[q];
+      }
+      if (bad) break;
+      const uint32_t inmask = (uint32_t)(((uint64_t)1 << w_in) - 1);
+      const uint32_t cbv = (uint32_t)closed_bits(n_close, CL, sy);
+      const int64_t n = (int64_t)1 << w_out;
+#pragma omp parallel for schedule(static)
+      for (int64_t tau = 0; tau < n; ++tau) {
+        const uint32_t full = _pdep_u32((uint32_t)tau, keep) | cbv;
+        const uint32_t pat = full >> w_in;
+        const uint32_t low = (full & inmask) ^ (uint32_t)ML[pat];
+        const double *tb = T + (size_t)pat * nk;
+        double acc = Sin[low ^ (uint32_t)MK[0]] * tb[0];
+        for (int k = 1; k < nk; ++k) acc += Sin[low ^ (uint32_t)MK[k]] * tb[k];
+        Sout[tau] = acc;
+      }
+      double *tmp = Sin; Sin = Sout; Sout = tmp;
+    }
+    for (int idx = 0; idx < NO; ++idx) {
+      int src = 0;
+      for (int o = 0; o < P->n_obs; ++o) src |= ((idx >> o) & 1) << P->obs_slot[o];
+      out[(size_t)b * NO + idx] = Sin[src];
+    }
+  }
+  free(S0); free(S1);
+  return bad ? 3 : 0;
+}
+
 int oracle_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -89,7 +89,7 @@ def lib():
     L.tqec_gf2_apply.argtypes = [vp, vp, i64, vp]
     L.tqec_gf2_apply_dev.argtypes = [vp, vp, i64, vp, vp]
     L.tqec_logical_flags.argtypes = [vp, vp, vp, vp, i64, vp, vp]
-    L.tqec_coset_rep.argtypes = [vp, vp, vp, vp, vp, i64, vp]
+    L.tqec_coset_rep.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp]
     L.tqec_sample_errors.argtypes = [i32, i32, vp, vp, vp, u64, i64, i64, vp, i32]
     L.tqec_mc_run.argtypes = [C.POINTER(McDesc), u64, i64, i64, vp, vp]
     L.tqec_fp64_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -279,14 +279,16 @@ class GF2Matrix:
             pass
 
 
-def coset_rep(R: GF2Matrix, L, FIX, synd_words, sector) -> np.ndarray:
+def coset_rep(R: GF2Matrix, L, FIX, synd_words, sector):
+    """-> (error words, ok): ok[b] = the pattern lies in the requested sector."""
     s = _c(synd_words, np.uint64).reshape(-1, R.cw)
     B = s.shape[0]
     out = np.zeros((B, R.rw), dtype=np.uint64)
+    ok = np.ones(B, dtype=np.uint8)
     sec = _c(sector, np.int32)
     check(lib().tqec_coset_rep(R.h, L.h if L is not None else None, FIX.h if FIX is not None else None, _ptr(s),
-                               _ptr(sec), B, _ptr(out)))
-    return out
+                               _ptr(sec), B, _ptr(out), _ptr(ok)))
+    return out, ok.astype(bool)
 
 
 def sample_errors(model: int, probs, seed: int, shot_offset: int, B: int, device: int = 0) -> np.ndarray:

@@ -201,17 +201,35 @@ int launch_flags(tqec_gf2 *L, const int32_t *d_row_class, const uint64_t *d_e1, 
 }
 
 // ---- TNMMAP error pattern: e = R s, then move it into the decoded logical sector --------------------------------
-__global__ void k_coset_fix(const uint64_t *__restrict__ Lrows, const uint64_t *__restrict__ Frows, int n_obs, int cw,
-                            const int32_t *__restrict__ sector, int64_t B, uint64_t *__restrict__ err) {
+__global__ void k_coset_fix(const uint64_t *__restrict__ Lrows, const uint64_t *__restrict__ Frows, int n_obs, int n_fix,
+                            int cw, const int32_t *__restrict__ sector, int64_t B, uint64_t *__restrict__ err,
+                            uint8_t *__restrict__ ok_out) {
   const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (s >= B) return;
-  const int sec = sector[s];
+  // sector of the representative, relative to the requested one
+  uint32_t delta = (uint32_t)sector[s];
   for (int i = 0; i < n_obs; ++i) {
     uint64_t acc = 0;
     for (int w = 0; w < cw; ++w) acc ^= Lrows[i * cw + w] & err[s * cw + w];
-    if ((__popcll(acc) & 1) != ((sec >> i) & 1))
-      for (int w = 0; w < cw; ++w) err[s * cw + w] ^= Frows[i * cw + w];
+    delta ^= (uint32_t)(__popcll(acc) & 1) << i;
   }
+  // The fix rows are undetectable patterns whose sector flips d_j = L f_j are in reduced echelon form (the lowest set
+  // bit of d_j is its pivot and no other row has that bit): one pass moves the representative into the requested sector
+  // whenever the difference lies in their span -- including differences that only a JOINT flip of several observables
+  // can realise.
+  for (int j = 0; j < n_fix && delta; ++j) {
+    uint32_t dj = 0;
+    for (int i = 0; i < n_obs; ++i) {
+      uint64_t acc = 0;
+      for (int w = 0; w < cw; ++w) acc ^= Lrows[i * cw + w] & Frows[j * cw + w];
+      dj |= (uint32_t)(__popcll(acc) & 1) << i;
+    }
+    if (delta & dj & (0u - dj)) {
+      for (int w = 0; w < cw; ++w) err[s * cw + w] ^= Frows[j * cw + w];
+      delta ^= dj;
+    }
+  }
+  if (ok_out) ok_out[s] = delta == 0;
 }
 
 }  // namespace tqec
@@ -313,12 +331,12 @@ extern "C" int tqec_logical_flags(tqec_gf2 *L, const int32_t *row_class, const u
 }
 
 extern "C" int tqec_coset_rep(tqec_gf2 *R, tqec_gf2 *L, tqec_gf2 *FIX, const uint64_t *synd, const int32_t *sector,
-                              int64_t B, uint64_t *err_out) {
+                              int64_t B, uint64_t *err_out, uint8_t *ok_out) {
   TQEC_REQUIRE(R && B >= 0 && (B == 0 || (synd && err_out)), "tqec_coset_rep: NULL argument");
   TQEC_REQUIRE((L == nullptr) == (FIX == nullptr), "tqec_coset_rep: L and FIX go together");
   if (L) {
-    TQEC_REQUIRE(L->cols == R->rows && FIX->cols == R->rows && L->rows == FIX->rows && sector,
-                 "tqec_coset_rep: L / FIX must be n_obs x n_vars and sector non-NULL");
+    TQEC_REQUIRE(L->cols == R->rows && FIX->cols == R->rows && FIX->rows <= L->rows && L->rows <= 16 && sector,
+                 "tqec_coset_rep: L must be n_obs x n_vars (n_obs <= 16), FIX at most n_obs x n_vars, sector non-NULL");
     TQEC_REQUIRE(L->device == R->device && FIX->device == R->device, "tqec_coset_rep: matrices live on different devices");
   }
   if (B == 0) return TQEC_OK;
@@ -333,10 +351,15 @@ extern "C" int tqec_coset_rep(tqec_gf2 *R, tqec_gf2 *L, tqec_gf2 *FIX, const uin
     if ((rc = ensure_cap(&R->d_io[2], &R->io_cap[2], (size_t)B * 4))) return rc;
     TQEC_CUDA(cudaMemcpyAsync(R->d_io[2], sector, (size_t)B * 4, cudaMemcpyHostToDevice, R->stream));
     const int threads = 128;
-    k_coset_fix<<<(unsigned)((B + threads - 1) / threads), threads, 0, R->stream>>>(L->d_rows, FIX->d_rows, L->rows, L->cw,
-                                                                                   (const int32_t *)R->d_io[2], B, (uint64_t *)R->d_io[1]);
+    if (ok_out && (rc = ensure_cap(&R->d_io[3], &R->io_cap[3], (size_t)B))) return rc;
+    k_coset_fix<<<(unsigned)((B + threads - 1) / threads), threads, 0, R->stream>>>(L->d_rows, FIX->d_rows, L->rows, FIX->rows, L->cw,
+                                                                                   (const int32_t *)R->d_io[2], B, (uint64_t *)R->d_io[1],
+                                                                                   ok_out ? (uint8_t *)R->d_io[3] : nullptr);
     TQEC_CUDA(cudaGetLastError());
     R->launches += 1;
+    if (ok_out) TQEC_CUDA(cudaMemcpyAsync(ok_out, R->d_io[3], (size_t)B, cudaMemcpyDeviceToHost, R->stream));
+  } else if (ok_out) {
+    std::memset(ok_out, 1, (size_t)B);
   }
   TQEC_CUDA(cudaMemcpyAsync(err_out, R->d_io[1], ob, cudaMemcpyDeviceToHost, R->stream));
   TQEC_CUDA(cudaStreamSynchronize(R->stream));

@@ -26,7 +26,8 @@ from .dem import DetectorErrorModel, dem2tanner
 from .error_model import (AbstractErrorModel, CSSErrorPattern, CSSSyndrome, IndependentDepolarizingError,
                           IndependentFlipError, SimpleSyndrome, iid_error)
 from .mod2 import as_bits, pack_bits, unpack_bits
-from .tanner import AbstractTannerGraph, CSSTannerGraph, SimpleTannerGraph, gf2_right_inverse, logical_operator
+from .tanner import (AbstractTannerGraph, CSSTannerGraph, SimpleTannerGraph, gf2_right_inverse, gf2_sector_fixes,
+                     logical_operator)
 
 
 # ---- problems (interfaces.jl:6-51) ---------------------------------------------------------------------------
@@ -332,8 +333,9 @@ def _decode_tnmmap_css(ct: CompiledTNMMAP, syndrome: CSSSyndrome) -> DecodingRes
     words = pack_bits(bits)
     mar, pos = ct.plan.decode_marginal(words)
     n = ct.tanner.stgx.nq
-    e = unpack_bits(_cabi.coset_rep(ct.R, ct.L, ct.FIX, words, pos), 2 * n)
-    ok = mar.max(axis=1) > 0
+    ew, in_sector = _cabi.coset_rep(ct.R, ct.L, ct.FIX, words, pos)
+    e = unpack_bits(ew, 2 * n)
+    ok = (mar.max(axis=1) > 0) & in_sector
     k2 = ct.schedule.n_obs
     marr = mar.reshape((mar.shape[0],) + (2,) * k2, order="F")
     if single:
@@ -342,35 +344,6 @@ def _decode_tnmmap_css(ct: CompiledTNMMAP, syndrome: CSSSyndrome) -> DecodingRes
 
 
 # ---- TNMMAP, detector error model (tndecoder.jl:176-271) -----------------------------------------------------------------
-def _gf2_solve(A: np.ndarray, b: np.ndarray):
-    """One solution x of A x = b over GF(2), or None."""
-    A = np.concatenate([as_bits(A).copy(), as_bits(b).reshape(-1, 1)], axis=1)
-    m, n1 = A.shape
-    n = n1 - 1
-    piv = []
-    r = 0
-    for c in range(n):
-        nz = np.flatnonzero(A[r:, c]) if r < m else np.zeros(0, dtype=int)
-        if nz.size == 0:
-            continue
-        p = r + int(nz[0])
-        if p != r:
-            A[[r, p]] = A[[p, r]]
-        for kx in np.flatnonzero(A[:, c]):
-            if kx != r:
-                A[kx] ^= A[r]
-        piv.append(c)
-        r += 1
-        if r == m:
-            break
-    if A[r:, n].any():
-        return None
-    x = np.zeros(n, dtype=np.uint8)
-    for i, c in enumerate(piv):
-        x[c] = A[i, n]
-    return x
-
-
 class CompiledDEMTNMMAP(CompiledDecoder):
     def __init__(self, tanner, l2q, sch, R, L, FIX, device):
         self.tanner, self.l2q = tanner, l2q
@@ -405,15 +378,10 @@ def tnmmap_dem_schedule(decoder: TNMMAP, dem: DetectorErrorModel):
         L[l, c] = 1
     # The reference "repairs" a wrong observable by flipping every mechanism that touches it (tndecoder.jl:257-258,
     # 266-267), which also changes the detectors.  Here the repair is an undetectable combination of
-    # mechanisms that flips exactly that observable (H f = 0, L f = e_l), when one exists.
-    FIX = np.zeros_like(L)
-    A = np.vstack([tanner.H, L])
-    for l in range(len(l2q)):
-        b = np.zeros(nd + len(l2q), dtype=np.uint8)
-        b[nd + l] = 1
-        f = _gf2_solve(A, b)
-        if f is not None:
-            FIX[l] = f
+    # mechanisms (H f = 0) with the required sector flip L f; `gf2_sector_fixes` returns a basis of all reachable flips,
+    # so joint flips of several observables are found too, and an unreachable sector is reported (success_tag False)
+    # instead of returning a pattern in the wrong sector.
+    FIX = gf2_sector_fixes(tanner.H, L)
     return tanner, l2q, sch, R, L, FIX
 
 
@@ -426,8 +394,9 @@ def _decode_tnmmap_dem(ct: CompiledDEMTNMMAP, syndrome: SimpleSyndrome) -> Decod
     single = as_bits(syndrome.s).ndim == 1
     words = pack_bits(_syndrome_bits(syndrome.s, ct.tanner.ns))
     mar, pos = ct.plan.decode_marginal(words)
-    e = unpack_bits(_cabi.coset_rep(ct.R, ct.L, ct.FIX, words, pos), ct.tanner.nq)
-    ok = mar.max(axis=1) > 0
+    ew, in_sector = _cabi.coset_rep(ct.R, ct.L, ct.FIX, words, pos)
+    e = unpack_bits(ew, ct.tanner.nq)
+    ok = (mar.max(axis=1) > 0) & in_sector                      # False: no undetectable pattern reaches the decoded sector
     k = ct.schedule.n_obs
     marr = mar.reshape((mar.shape[0],) + (2,) * k, order="F")
     if single:

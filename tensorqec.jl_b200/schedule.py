@@ -456,6 +456,7 @@ def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_v
     cost = 0.0
     wmax = 0
     log2_scale = 0
+    log2_run = 0.0
     for t, fi in enumerate(order):
         f = factors[fi]
         r = len(f.vars)
@@ -541,12 +542,16 @@ def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_v
             with np.errstate(divide="ignore"):
                 tab = np.log(f.table)
         else:
-            # static per-step scaling against underflow: every factor is normalised by the power of two below its
-            # largest entry (exact in FP64), the exponents are summed and re-applied by the host after the decode
+            # static per-step scaling: every factor is multiplied by a power of two (exact in FP64) chosen so that the
+            # running product of the factors' largest entries stays within [2^-1/2, 2^1/2] -- the state can never
+            # overflow however many factors there are (1605 at d = 5 x 5 rounds circuit level) and starts from the best
+            # place against underflow; the exponents are summed and re-applied by the host after the decode
             tab = f.table.copy()
             mx = float(tab.max())
             if mx > 0.0:
-                e = int(np.floor(np.log2(mx)))
+                log2_run += float(np.log2(mx))
+                e = int(np.rint(log2_run))
+                log2_run -= e
                 tab = np.ldexp(tab, -e)
                 log2_scale += e
         steps.append(Step(fi, tuple(f.vars), w_in, w_out, opened, closed, perm, M, a0, ker, tab, quad))

@@ -234,3 +234,49 @@ def gf2_right_inverse(H: np.ndarray):
     for i, c in enumerate(piv_cols):
         R[c] = T[i]
     return R, len(piv_cols)
+
+
+def gf2_sector_fixes(H: np.ndarray, L: np.ndarray) -> np.ndarray:
+    """Undetectable patterns that move between logical sectors: rows f_j with H f_j = 0 whose sector flips
+    d_j = L f_j form a basis, in REDUCED ECHELON form (the lowest set bit of d_j is its pivot; no other row has that
+    bit), of the reachable flips {L f : H f = 0}.  `tqec_coset_rep` walks these rows once to move the representative
+    R s into the decoded sector -- also when only a joint flip of several observables is undetectable, which a
+    per-observable solve (H f = 0, L f = e_l) cannot express.  -> (r, n) uint8, r <= rows(L)."""
+    H, L = as_bits(H), as_bits(L)
+    n = H.shape[1]
+    k = L.shape[0]
+    if k == 0:
+        return np.zeros((0, n), dtype=np.uint8)
+    # null space of H by elimination on [H^T | I]: rows whose H^T part vanishes carry a kernel vector on the right
+    A = np.concatenate([H.T.copy(), np.eye(n, dtype=np.uint8)], axis=1)
+    m = H.shape[0]
+    r = 0
+    for c in range(m):
+        nz = np.flatnonzero(A[r:, c]) if r < n else np.zeros(0, dtype=int)
+        if nz.size == 0:
+            continue
+        p = r + int(nz[0])
+        if p != r:
+            A[[r, p]] = A[[p, r]]
+        rows = np.flatnonzero(A[:, c])
+        rows = rows[rows != r]
+        A[rows] ^= A[r]
+        r += 1
+        if r == n:
+            break
+    ker = A[r:, m:]                                             # (n - rank, n), H ker^T = 0
+    D = ((ker.astype(np.int64) @ L.T.astype(np.int64)) & 1).astype(np.uint8)    # sector flip of every kernel vector
+    M = np.concatenate([D, ker], axis=1)                        # reduced row echelon form on the sector part
+    r = 0
+    for j in range(k):
+        nz = np.flatnonzero(M[r:, j]) if r < M.shape[0] else np.zeros(0, dtype=int)
+        if nz.size == 0:
+            continue
+        p = r + int(nz[0])
+        if p != r:
+            M[[r, p]] = M[[p, r]]
+        rows = np.flatnonzero(M[:, j])
+        rows = rows[rows != r]
+        M[rows] ^= M[r]
+        r += 1
+    return np.ascontiguousarray(M[:r, k:])

@@ -177,11 +177,14 @@ def lower_wide(factors: Sequence[S.Factor], checks: Sequence[S.Check], semiring:
     # static power-of-two scaling of every factor (schedule.lower does the same): exact, undone by the host
     tabs = []
     log2_scale = 0
+    log2_run = 0.0
     for fi, *_ in roles:
         tab = np.asarray(factors[fi].table, dtype=np.float64).copy()
         mx = float(tab.max())
         if mx > 0.0:
-            e = int(np.floor(np.log2(mx)))
+            log2_run += float(np.log2(mx))                        # running product of the maxima stays near 1
+            e = int(np.rint(log2_run))
+            log2_run -= e
             tab = np.ldexp(tab, -e)
             log2_scale += e
         tabs.append(tab)

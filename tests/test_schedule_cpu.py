@@ -192,3 +192,28 @@ def test_fails_loudly_without_gpu(tq):
         tq.syndrome_extraction(np.zeros(9, dtype=np.uint8), t.stgz)
     with pytest.raises(tq.TqecError):
         tq.random_error_pattern(tq.iid_error(0.1, 10))
+
+
+def test_sector_fixes_span_every_reachable_flip():
+    """gf2_sector_fixes: undetectable patterns whose sector flips are a reduced-echelon basis of ALL reachable flips,
+    joint flips of several observables included (the per-observable solve it replaces missed those)."""
+    from tensorqec.jl_b200.tanner import gf2_sector_fixes
+    rng = np.random.RandomState(0)
+    joint_only = 0
+    for _ in range(120):
+        n, m, k = rng.randint(4, 12), rng.randint(1, 6), rng.randint(1, 4)
+        H = rng.randint(0, 2, (m, n)).astype(np.uint8)
+        L = rng.randint(0, 2, (k, n)).astype(np.uint8)
+        F = gf2_sector_fixes(H, L)
+        assert not ((H.astype(int) @ F.T.astype(int)) & 1).any()
+        D = (F.astype(int) @ L.T.astype(int)) & 1
+        piv = [int(np.flatnonzero(d)[0]) for d in D]
+        assert piv == sorted(set(piv)) and all(D[:, pv].sum() == 1 for pv in piv)
+        X = ((np.arange(1 << n)[:, None] >> np.arange(n)) & 1).astype(int)
+        ker = X[~((X @ H.T.astype(int)) & 1).any(axis=1)]
+        reach = {tuple(r) for r in (ker @ L.T.astype(int)) & 1}
+        assert len(reach) == 1 << len(F)
+        unit = [tuple(int(i == l) for i in range(k)) for l in range(k)]
+        if any(sum(r) > 1 for r in reach) and not all(u in reach for u in unit if any(r[unit.index(u)] for r in reach)):
+            joint_only += 1
+    assert joint_only > 0, "the fuzz never produced a joint-only flip"
