@@ -11,7 +11,9 @@
  * 64*w + k -- the `compresscol` layout of the reference's own packed product (src/codes/mod2.jl:58-71).
  *
  * Reference interfaces replaced (paths relative to the reference repo, TensorQEC.jl v2.2.1):
- *   tqec_plan_create        compile(::TNMAP, ::GeneralDecodingProblem)                 src/decoding/tndecoder.jl:46-50
+ *   tqec_plan_compile       compile(decoder, problem)  (factor graph in, plan out)     src/decoding/interfaces.jl:67-79, 129-142
+ *   tqec_plan_create        (the same from an already lowered schedule)
+ *                           compile(::TNMAP, ::GeneralDecodingProblem)                 src/decoding/tndecoder.jl:46-50
  *                           compile(::TNMMAP, ::IndependentDepolarizingDecodingProblem) src/decoding/tndecoder.jl:97-146
  *                           compile(::TNMMAP, ::DetectorErrorModel)                     src/decoding/tndecoder.jl:186-219
  *                           (the contraction order found by OMEinsum's optimize_code becomes the step order)
@@ -66,6 +68,7 @@ enum {
 };
 
 typedef struct tqec_plan tqec_plan; /* a compiled schedule resident on one device      */
+typedef struct tqec_comm tqec_comm; /* one rank of a job: NCCL communicator + stream   */
 typedef struct tqec_gf2 tqec_gf2;   /* a bit-packed GF(2) matrix resident on one device */
 
 /* Optional second lowering of a plan (either semiring): the in-place patch sweep (tensorqec.jl_b200/sweep.py, executed by
@@ -142,6 +145,9 @@ typedef struct {
   int32_t table_bits;      /* plans with n_checks <= table_bits are fully tabulated at creation (0 = default 16,
                               -1 = never, at most 26; table = 2^n_checks x (configuration words + outputs)) */
   const tqec_wide_desc *wide; /* optional (NULL): global-memory lowering; takes precedence over hdr / sweep */
+  int32_t log2_scale;      /* sum-product: the factor tables were pre-multiplied by powers of two against under- and
+                              overflow and their exponents sum to -log2_scale; the library multiplies every marginal
+                              it returns (host and *_dev entry points alike) by 2^log2_scale */
 } tqec_plan_desc;
 
 const char *tqec_last_error(void);
@@ -164,14 +170,72 @@ enum {
 };
 int tqec_plan_query(const tqec_plan *plan, int32_t what, int64_t *out);
 
+/* ---- compile: factor graph -> plan, entirely inside the library -------------------------------------------- */
+/* The decoder's factor graph exactly as the reference builds its tensor network: prior factors over binary error
+ * variables (`single_qubit_tensor`, src/decoding/general_decoding.jl:5; `[1-p, p]`, src/decoding/tndecoder.jl:202-205;
+ * any `SimpleTensorNetwork` of a GeneralDecodingProblem) and parity rows (checks / detectors clamped by a syndrome bit,
+ * logical rows left open: src/decoding/tndecoder.jl:33-50, 97-146, 186-219).  tqec_plan_compile lowers it (frontier
+ * schedule, in-place patch sweep with its tabulated head, or global-memory passes -- whichever the frontier width
+ * calls for) and creates the plan: what `compile(decoder, problem)` does (src/decoding/interfaces.jl:67-79, 129-142).
+ * A host binding therefore needs no lowering code of its own: it lists factors and rows and, optionally, passes the
+ * leaf order of the contraction tree its optimiser chose (OMEinsum's `optimize_code`) as `order`. */
+typedef struct {
+  int32_t semiring;            /* TQEC_SEMIRING_*                                                             */
+  int32_t n_vars, n_checks, n_obs;
+  int32_t n_factors;
+  const int32_t *factor_ptr;   /* n_factors + 1: factor f has variables factor_vars[factor_ptr[f] .. factor_ptr[f+1]) */
+  const int32_t *factor_vars;  /* 0-based variable ids                                                        */
+  const double *factor_tables; /* concatenated; 2^rank entries per factor, first variable fastest (column-major,
+                                  the layout of a Julia array)                                                */
+  int32_t n_rows;              /* parity rows: the n_checks clamped ones and the n_obs open ones, in any order  */
+  const int32_t *row_ptr;      /* n_rows + 1                                                                  */
+  const int32_t *row_vars;
+  const int32_t *row_kind;     /* 0: clamped by syndrome bit row_index; 1: open output axis row_index          */
+  const int32_t *row_index;
+  const int32_t *order;        /* NULL, or n_factors entries: absorption order of the prior factors            */
+  int32_t head_bits;           /* syndrome bits the tabulated head of the sweep may depend on (0 = default 12 for
+                                  max-plus, 10 for sum-product; at most 16)                                    */
+  int32_t table_bits;          /* as in tqec_plan_desc                                                         */
+  int32_t device;
+  int32_t flags;               /* TQEC_COMPILE_*                                                               */
+  int32_t wide_t_max;          /* tile bits of the global-memory executor (0 = default 12)                     */
+} tqec_problem_desc;
+#define TQEC_COMPILE_NO_SWEEP 1   /* never use the in-place patch sweep                                        */
+#define TQEC_COMPILE_NO_FUSE 2    /* general max-plus kernels: one factor per step                             */
+#define TQEC_COMPILE_FORCE_WIDE 4 /* sum-product: global-memory executor even if the frontier fits on chip     */
+
+typedef struct tqec_lowered tqec_lowered; /* host-side result of the lowering (no device memory)               */
+int tqec_lower(const tqec_problem_desc *prob, tqec_lowered **out);
+int tqec_lowered_destroy(tqec_lowered *lw);
+/* Tables of a lowering, for inspection and for tests (the Python lowering is kept as the oracle of the C++ one):
+ * *data points into the handle (valid until it is destroyed), *count = number of elements. */
+enum {
+  TQEC_LW_META = 0,        /* int32[16]: kind (0 schedule, 1 schedule + sweep, 2 wide), n_steps, w_max, log2_scale,
+                              sweep {W, sg, n_ss, n_head_bits, bp_words, head_steps, conflicts}, wide {n_pass, n_steps,
+                              w_cap, t_max}, table_bits                                                        */
+  TQEC_LW_COST = 1,        /* double[2]: candidate evaluations per shot, HBM bytes per shot (wide)              */
+  TQEC_LW_ORDER = 2,       /* int32: absorption order of the merged factors                                    */
+  TQEC_LW_HDR = 3, TQEC_LW_INTS = 4, TQEC_LW_TABLES = 5 /* double */, TQEC_LW_OBS_SLOT = 6,
+  TQEC_LW_SW_REC = 7, TQEC_LW_SW_TB = 8, TQEC_LW_SW_LANETAB = 9, TQEC_LW_SW_TVALS = 10 /* double */,
+  TQEC_LW_SW_HEAD_BITS = 11, TQEC_LW_SW_HEAD_STATE = 12 /* double */, TQEC_LW_SW_HEAD_CFG = 13 /* uint64 */,
+  TQEC_LW_SW_OUT_INDEX = 14,
+  TQEC_LW_WD_PASS_HDR = 15, TQEC_LW_WD_STEP_HDR = 16, TQEC_LW_WD_INTS = 17, TQEC_LW_WD_TABLES = 18 /* double */,
+  TQEC_LW_WD_OBS_POS = 19
+};
+int tqec_lowered_get(const tqec_lowered *lw, int32_t what, const void **data, int64_t *count);
+int tqec_plan_from_lowered(const tqec_lowered *lw, int32_t device, tqec_plan **out);
+/* = tqec_lower + tqec_plan_from_lowered + tqec_lowered_destroy */
+int tqec_plan_compile(const tqec_problem_desc *prob, tqec_plan **out);
+
 /* ---- decoding --------------------------------------------------------------------------------------------- */
 /* TNMAP: synd = B * ceil(n_checks/64) words; corr_out = B * ceil(n_vars/64) words (bit v = variable v of the most
  * probable configuration); logp_out (may be NULL) = B log-weights of that configuration (-inf: infeasible). */
 int tqec_decode_map(tqec_plan *plan, const uint64_t *synd, int64_t n_shots, uint64_t *corr_out, double *logp_out);
 int tqec_decode_map_dev(tqec_plan *plan, const uint64_t *d_synd, int64_t n_shots, uint64_t *d_corr, double *d_logp,
                         void *stream);
-/* TNMMAP: mar_out = B * 2^n_obs weights, entry index = sum_i obs_i << i (observable 0 fastest = the reference's
- * column-major `mar`, tndecoder.jl:134); argmax_out (may be NULL) = first maximal entry per shot (findmax). */
+/* TNMMAP: mar_out = B * 2^n_obs weights (the static scaling of the plan's tables already undone), entry index =
+ * sum_i obs_i << i (observable 0 fastest = the reference's column-major `mar`, tndecoder.jl:134); argmax_out (may be
+ * NULL) = first maximal entry per shot (findmax). */
 int tqec_decode_marginal(tqec_plan *plan, const uint64_t *synd, int64_t n_shots, double *mar_out,
                          int32_t *argmax_out);
 int tqec_decode_marginal_dev(tqec_plan *plan, const uint64_t *d_synd, int64_t n_shots, double *d_mar,
@@ -218,11 +282,24 @@ typedef struct {
   int32_t n_sites;         /* qubits (DEPOL: n_vars = 2 n_sites) or bits (FLIP)        */
   const double *p0, *p1, *p2;
   int64_t chunk;           /* shots per internal batch (0 = library default)           */
+  tqec_comm *comm;         /* optional (NULL): all-reduce the counters over the job's ranks before returning */
 } tqec_mc_desc;
 /* counts += {logical X-type failures, logical Z-type failures, any failure, shots} over shots
- * shot_offset .. shot_offset + n_shots - 1.  elapsed_ms (may be NULL) = device time of the whole pipeline. */
+ * shot_offset .. shot_offset + n_shots - 1 -- of THIS rank, or, with `comm`, summed over all ranks (one ncclAllReduce of
+ * the four device counters on the pipeline's stream, inside elapsed_ms).  elapsed_ms (may be NULL) = device time of
+ * the whole pipeline. */
 int tqec_mc_run(const tqec_mc_desc *mc, uint64_t seed, int64_t shot_offset, int64_t n_shots, int64_t counts[4],
                 float *elapsed_ms);
+
+/* ---- multi-GPU: shots shard over ranks (one process per GPU), the counters are the only thing exchanged ---------- */
+/* Replaces the job farm of src/multiprocessing.jl:41-52.  Rank 0 makes the id (128 bytes = ncclUniqueId) and hands it to
+ * the other ranks by whatever means the host has (Distributed.jl, MPI, a file); every rank then calls tqec_comm_init.
+ * NCCL is loaded at run time (libnccl.so.2); without it these calls return TQEC_ERR_UNSUPPORTED. */
+int tqec_comm_unique_id(void *id_out_128_bytes);
+int tqec_comm_init(int32_t nranks, int32_t rank, const void *unique_id_128_bytes, int32_t device, tqec_comm **out);
+int tqec_comm_destroy(tqec_comm *comm);
+/* counts[0..3] <- sum over ranks (in place; every rank calls it with its own counters) */
+int tqec_comm_allreduce_counts(tqec_comm *comm, int64_t counts[4]);
 
 /* ---- measurement helper -------------------------------------------------------------------------------------- */
 /* FP64 CUDA-core peak of the device, measured with register-resident chains: DADD instructions/s (T/s), DFMA

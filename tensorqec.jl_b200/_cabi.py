@@ -25,6 +25,8 @@ EXPORTS = [
     "tqec_decode_map", "tqec_decode_map_dev", "tqec_decode_marginal", "tqec_decode_marginal_dev",
     "tqec_gf2_create", "tqec_gf2_destroy", "tqec_gf2_apply", "tqec_gf2_apply_dev",
     "tqec_logical_flags", "tqec_coset_rep", "tqec_sample_errors", "tqec_mc_run", "tqec_fp64_peak",
+    "tqec_lower", "tqec_lowered_destroy", "tqec_lowered_get", "tqec_plan_from_lowered", "tqec_plan_compile",
+    "tqec_comm_unique_id", "tqec_comm_init", "tqec_comm_destroy", "tqec_comm_allreduce_counts",
 ]
 
 
@@ -52,14 +54,30 @@ class PlanDesc(C.Structure):
                 ("hdr", C.POINTER(C.c_int32)), ("ints", C.POINTER(C.c_int32)), ("n_ints", C.c_int64),
                 ("tables", C.POINTER(C.c_double)), ("n_tables", C.c_int64),
                 ("obs_slot", C.POINTER(C.c_int32)), ("device", C.c_int32), ("sweep", C.POINTER(SweepDesc)),
-                ("table_bits", C.c_int32), ("wide", C.POINTER(WideDesc))]
+                ("table_bits", C.c_int32), ("wide", C.POINTER(WideDesc)), ("log2_scale", C.c_int32)]
+
+
+class ProblemDesc(C.Structure):
+    _fields_ = [("semiring", C.c_int32), ("n_vars", C.c_int32), ("n_checks", C.c_int32), ("n_obs", C.c_int32),
+                ("n_factors", C.c_int32), ("factor_ptr", C.c_void_p), ("factor_vars", C.c_void_p),
+                ("factor_tables", C.c_void_p), ("n_rows", C.c_int32), ("row_ptr", C.c_void_p), ("row_vars", C.c_void_p),
+                ("row_kind", C.c_void_p), ("row_index", C.c_void_p), ("order", C.c_void_p), ("head_bits", C.c_int32),
+                ("table_bits", C.c_int32), ("device", C.c_int32), ("flags", C.c_int32), ("wide_t_max", C.c_int32)]
+
+
+COMPILE_NO_SWEEP, COMPILE_NO_FUSE, COMPILE_FORCE_WIDE = 1, 2, 4
+(LW_META, LW_COST, LW_ORDER, LW_HDR, LW_INTS, LW_TABLES, LW_OBS_SLOT, LW_SW_REC, LW_SW_TB, LW_SW_LANETAB, LW_SW_TVALS,
+ LW_SW_HEAD_BITS, LW_SW_HEAD_STATE, LW_SW_HEAD_CFG, LW_SW_OUT_INDEX, LW_WD_PASS_HDR, LW_WD_STEP_HDR, LW_WD_INTS,
+ LW_WD_TABLES, LW_WD_OBS_POS) = range(20)
+_LW_DTYPE = {LW_COST: np.float64, LW_TABLES: np.float64, LW_SW_TVALS: np.float64, LW_SW_HEAD_STATE: np.float64,
+             LW_SW_HEAD_CFG: np.uint64, LW_SW_LANETAB: np.uint32, LW_WD_TABLES: np.float64}
 
 
 class McDesc(C.Structure):
     _fields_ = [("plan", C.c_void_p), ("H", C.c_void_p), ("L", C.c_void_p), ("row_class", C.POINTER(C.c_int32)),
                 ("model", C.c_int32), ("n_sites", C.c_int32),
                 ("p0", C.POINTER(C.c_double)), ("p1", C.POINTER(C.c_double)), ("p2", C.POINTER(C.c_double)),
-                ("chunk", C.c_int64)]
+                ("chunk", C.c_int64), ("comm", C.c_void_p)]
 
 
 _lib = None
@@ -93,6 +111,15 @@ def lib():
     L.tqec_sample_errors.argtypes = [i32, i32, vp, vp, vp, u64, i64, i64, vp, i32]
     L.tqec_mc_run.argtypes = [C.POINTER(McDesc), u64, i64, i64, vp, vp]
     L.tqec_fp64_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.tqec_lower.argtypes = [C.POINTER(ProblemDesc), C.POINTER(vp)]
+    L.tqec_lowered_destroy.argtypes = [vp]
+    L.tqec_lowered_get.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64)]
+    L.tqec_plan_from_lowered.argtypes = [vp, i32, C.POINTER(vp)]
+    L.tqec_plan_compile.argtypes = [C.POINTER(ProblemDesc), C.POINTER(vp)]
+    L.tqec_comm_unique_id.argtypes = [vp]
+    L.tqec_comm_init.argtypes = [i32, i32, vp, i32, C.POINTER(vp)]
+    L.tqec_comm_destroy.argtypes = [vp]
+    L.tqec_comm_allreduce_counts.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -134,13 +161,100 @@ def _c(a, dtype):
     return np.ascontiguousarray(a, dtype=dtype)
 
 
+class Problem:
+    """A decoding factor graph marshalled for `tqec_lower` / `tqec_plan_compile` (include/tqec.h: tqec_problem_desc).
+    factors: objects with .vars / .table (flat, first variable fastest); checks: objects with .vars / .kind ("syn" |
+    "obs") / .index -- the same lists the Python lowering takes (schedule.Factor / schedule.Check)."""
+
+    def __init__(self, factors, checks, semiring, n_vars, n_checks, n_obs, order=None, head_bits=0, table_bits=0,
+                 device=0, flags=0, wide_t_max=0):
+        fptr = np.zeros(len(factors) + 1, dtype=np.int32)
+        fv, ft = [], []
+        for i, f in enumerate(factors):
+            fv += [int(v) for v in f.vars]
+            ft.append(np.asarray(f.table, dtype=np.float64).reshape(-1))
+            fptr[i + 1] = len(fv)
+        rptr = np.zeros(len(checks) + 1, dtype=np.int32)
+        rv = []
+        for i, c in enumerate(checks):
+            rv += [int(v) for v in c.vars]
+            rptr[i + 1] = len(rv)
+        self._keep = [fptr, _c(fv if fv else [0], np.int32), _c(np.concatenate(ft) if ft else [0.0], np.float64), rptr,
+                      _c(rv if rv else [0], np.int32), _c([0 if c.kind == "syn" else 1 for c in checks] or [0], np.int32),
+                      _c([c.index for c in checks] or [0], np.int32),
+                      _c(order, np.int32) if order is not None else None]
+        k = self._keep
+        self.desc = ProblemDesc(semiring, n_vars, n_checks, n_obs, len(factors), _ptr(k[0]), _ptr(k[1]), _ptr(k[2]),
+                                len(checks), _ptr(k[3]), _ptr(k[4]), _ptr(k[5]), _ptr(k[6]),
+                                _ptr(k[7]) if k[7] is not None else None, head_bits, table_bits, device, flags, wide_t_max)
+
+
+class Lowered:
+    """Owning handle of a `tqec_lowered`: the C++ lowering's tables (host memory only; works without a GPU)."""
+
+    def __init__(self, problem: Problem):
+        h = C.c_void_p()
+        check(lib().tqec_lower(C.byref(problem.desc), C.byref(h)))
+        self.h = h
+
+    def get(self, what: int) -> np.ndarray:
+        ptr, n = C.c_void_p(), C.c_int64(0)
+        check(lib().tqec_lowered_get(self.h, what, C.byref(ptr), C.byref(n)))
+        dt = np.dtype(_LW_DTYPE.get(what, np.int32))
+        if n.value == 0:
+            return np.zeros(0, dtype=dt)
+        buf = (C.c_char * (n.value * dt.itemsize)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dt).copy()
+
+    @property
+    def meta(self):
+        m = self.get(LW_META)
+        return dict(kind=int(m[0]), n_steps=int(m[1]), w_max=int(m[2]), log2_scale=int(m[3]), W=int(m[4]), sg=int(m[5]),
+                    n_ss=int(m[6]), n_head_bits=int(m[7]), bp_words=int(m[8]), head_steps=int(m[9]), conflicts=int(m[10]),
+                    n_pass=int(m[11]), wide_steps=int(m[12]), w_cap=int(m[13]), t_max=int(m[14]), table_bits=int(m[15]))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().tqec_lowered_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Plan:
     """Owning handle of a `tqec_plan`."""
+
+    @classmethod
+    def compile(cls, problem: "Problem"):
+        """Factor graph -> plan through the library's own lowering (tqec_lower + tqec_plan_from_lowered): the path a
+        non-Python host takes with tqec_plan_compile.  The lowering's summary stays available as `plan.lowered`."""
+        d = problem.desc
+        require_device(d.device)
+        self = cls.__new__(cls)
+        self.sch = None
+        self.device = d.device
+        self.n_obs = d.n_obs
+        self.nsw = max(1, (d.n_checks + 63) // 64)
+        self.ncw = max(1, (d.n_vars + 63) // 64)
+        lw = Lowered(problem)
+        self.lowered = lw.meta
+        self.order = [int(i) for i in lw.get(LW_ORDER)]
+        self.cost = [float(x) for x in lw.get(LW_COST)]
+        h = C.c_void_p()
+        check(lib().tqec_plan_from_lowered(lw.h, d.device, C.byref(h)))
+        lw.close()
+        self.h = h
+        return self
 
     def __init__(self, sch, device: int = 0):
         require_device(device)
         self.sch = sch
         self.device = device
+        self.n_obs = sch.n_obs
         self.nsw = max(1, (sch.n_checks + 63) // 64)
         self.ncw = max(1, (sch.n_vars + 63) // 64)
         tb = getattr(sch, "table_bits", None)
@@ -152,7 +266,7 @@ class Plan:
             wd = WideDesc(len(sch.passes), keep[1].shape[0], sch.w_cap, sch.t_max, _ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]),
                           keep[2].size, _ptr(keep[3]), keep[3].size, _ptr(keep[4]))
             d = PlanDesc(sch.semiring, sch.n_vars, sch.n_checks, sch.n_obs, 0, sch.w_cap, None, None, 0, None, 0, None,
-                         device, None, table_bits, C.pointer(wd))
+                         device, None, table_bits, C.pointer(wd), int(sch.log2_scale))
             h = C.c_void_p()
             check(lib().tqec_plan_create(C.byref(d), C.byref(h)))
             self.h = h
@@ -164,7 +278,8 @@ class Plan:
         d = PlanDesc(sch.semiring, sch.n_vars, sch.n_checks, sch.n_obs, len(sch.steps), sch.w_max,
                      hdr.ctypes.data_as(C.POINTER(C.c_int32)), ints.ctypes.data_as(C.POINTER(C.c_int32)), ints.size,
                      tabs.ctypes.data_as(C.POINTER(C.c_double)), tabs.size,
-                     obs.ctypes.data_as(C.POINTER(C.c_int32)), device, None, table_bits, None)
+                     obs.ctypes.data_as(C.POINTER(C.c_int32)), device, None, table_bits, None,
+                     int(getattr(sch, "log2_scale", 0) or 0))
         sw = getattr(sch, "sweep", None)
         if sw is not None:
             keep = [_c(sw.rec, np.int32), _c(sw.tb, np.int32), _c(sw.lanetab, np.uint32), _c(sw.tvals, np.float64),
@@ -203,12 +318,10 @@ class Plan:
     def decode_marginal(self, synd_words: np.ndarray):
         s = _c(synd_words, np.uint64).reshape(-1, self.nsw)
         B = s.shape[0]
-        mar = np.zeros((B, 1 << self.sch.n_obs), dtype=np.float64)
+        mar = np.zeros((B, 1 << self.n_obs), dtype=np.float64)
         arg = np.zeros(B, dtype=np.int32)
         check(lib().tqec_decode_marginal(self.h, _ptr(s), B, _ptr(mar), _ptr(arg)))
-        if self.sch.log2_scale:
-            mar = np.ldexp(mar, self.sch.log2_scale)       # undo the static power-of-two scaling of the factor tables
-        return mar, arg
+        return mar, arg                                    # (the library has undone the static scaling of the tables)
 
     def decode_marginal_dev(self, d_synd: int, B: int, d_mar: int, d_argmax: int = 0, stream: int = 0):
         check(lib().tqec_decode_marginal_dev(self.h, d_synd, B, d_mar, d_argmax or None, stream or None))
@@ -304,13 +417,51 @@ def sample_errors(model: int, probs, seed: int, shot_offset: int, B: int, device
     return out
 
 
+class Comm:
+    """Owning handle of a `tqec_comm`: this rank's NCCL communicator inside the library.  `unique_id()` on rank 0, ship
+    the 128 bytes to the other ranks, then `Comm(nranks, rank, id, device)` on every rank."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_char * 128)()
+        check(lib().tqec_comm_unique_id(buf))
+        return bytes(buf)
+
+    def __init__(self, nranks: int, rank: int, unique_id: bytes, device: int = 0):
+        require_device(device)
+        if len(unique_id) != 128:
+            raise ValueError("an NCCL unique id has 128 bytes")
+        h = C.c_void_p()
+        check(lib().tqec_comm_init(nranks, rank, C.c_char_p(unique_id), device, C.byref(h)))
+        self.h, self.nranks, self.rank, self.device = h, nranks, rank, device
+
+    def allreduce_counts(self, counts) -> np.ndarray:
+        c = _c(counts, np.int64).copy()
+        if c.size != 4:
+            raise ValueError("four counters")
+        check(lib().tqec_comm_allreduce_counts(self.h, _ptr(c)))
+        return c
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().tqec_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def mc_run(plan: Plan, H: GF2Matrix, L: GF2Matrix, row_class, model: int, probs, seed: int, shot_offset: int,
-           n_shots: int, chunk: int = 0):
+           n_shots: int, chunk: int = 0, comm: "Comm" = None):
     ps = [_c(p, np.float64) for p in probs]
     cls = _c(row_class, np.int32)
     dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
     d = McDesc(plan.h, H.h, L.h, cls.ctypes.data_as(C.POINTER(C.c_int32)), model, ps[0].size, dp(ps[0]),
-               dp(ps[1]) if model == MODEL_DEPOL else None, dp(ps[2]) if model == MODEL_DEPOL else None, chunk)
+               dp(ps[1]) if model == MODEL_DEPOL else None, dp(ps[2]) if model == MODEL_DEPOL else None, chunk,
+               comm.h if comm is not None else None)
     counts = np.zeros(4, dtype=np.int64)
     ms = C.c_float(0.0)
     check(lib().tqec_mc_run(C.byref(d), C.c_uint64(seed & (2 ** 64 - 1)), shot_offset, n_shots, _ptr(counts),

@@ -81,6 +81,7 @@ struct tqec_plan {
   tqec::PlanDev dev;
   int device;
   int semiring;
+  int log2_scale;        // sum-product: marginals are multiplied by 2^log2_scale on the way out
   int team_threads;
   int warp_teams;        // 1: k_frontier_warp (a team is a warp, tables in shared memory); 0: k_frontier_cta
   int teams_per_cta;
@@ -141,6 +142,7 @@ int sweep_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &pr
 void sweep_destroy(tqec_plan *p);
 int wide_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &prop);
 void wide_destroy(tqec_plan *p);
+int comm_allreduce_dev(tqec_comm *c, unsigned long long *d_counts, cudaStream_t stream);
 int launch_wide(tqec_plan *plan, const uint64_t *d_synd, int64_t B, double *d_out, int32_t *d_argmax, cudaStream_t stream);
 int launch_gf2_apply(tqec_gf2 *m, const uint64_t *d_in, int64_t B, uint64_t *d_out, cudaStream_t stream);
 int launch_sample(int model, int n_sites, const double *d_p, uint64_t seed, int64_t shot_offset, int64_t B,

@@ -1,0 +1,252 @@
+// C ABI of the lowering: tqec_lower / tqec_lowered_get / tqec_plan_from_lowered / tqec_plan_compile (include/tqec.h).
+// Chooses the lowering the way tensorqec.jl_b200/decoding.py does:
+//   max-plus (TNMAP)    : unfused schedule + in-place patch sweep when the frontier has 5..10 bits and every step fits a
+//                         compiled shape; otherwise the fused schedule for the general kernels;
+//   sum-product (TNMMAP): schedule (+ sweep when it fits) up to 13 bits, global-memory passes beyond.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+
+#include "tqec_common.h"
+#include "tqec_lower.h"
+
+using namespace tqec;
+using namespace tqec::lower;
+
+struct tqec_lowered {
+  int kind = 0;            // 0 schedule, 1 schedule + sweep, 2 wide
+  int semiring = 0, n_vars = 0, n_checks = 0, n_obs = 0, table_bits = 0;
+  Schedule sch;
+  SweepPlan sw;
+  WidePlan wd;
+  std::vector<int32_t> meta, order32, obs32, head_bits32, out_index32;
+  std::vector<double> cost;
+};
+
+static int env_int(const char *name, int dflt) {
+  const char *e = std::getenv(name);
+  return e ? std::atoi(e) : dflt;
+}
+
+static void read_problem(const tqec_problem_desc *d, Problem &P) {
+  if (!d) throw std::runtime_error("problem descriptor is NULL");
+  if (d->semiring != TQEC_SEMIRING_MAXPLUS && d->semiring != TQEC_SEMIRING_SUMPROD) throw std::runtime_error("unknown semiring");
+  if (d->n_vars < 0 || d->n_checks < 0 || d->n_obs < 0 || d->n_obs > 16) throw std::runtime_error("bad sizes");
+  if (d->semiring == TQEC_SEMIRING_MAXPLUS && d->n_obs != 0) throw std::runtime_error("max-plus plans have no open axes");
+  if (d->n_factors < 0 || (d->n_factors > 0 && (!d->factor_ptr || !d->factor_vars || !d->factor_tables)))
+    throw std::runtime_error("factor arrays missing");
+  if (d->n_rows < 0 || (d->n_rows > 0 && (!d->row_ptr || !d->row_kind || !d->row_index))) throw std::runtime_error("row arrays missing");
+  P.semiring = d->semiring; P.n_vars = d->n_vars; P.n_checks = d->n_checks; P.n_obs = d->n_obs;
+  size_t toff = 0;
+  for (int f = 0; f < d->n_factors; ++f) {
+    const int a = d->factor_ptr[f], b = d->factor_ptr[f + 1];
+    if (a < 0 || b < a || b - a > 10) throw std::runtime_error("factor " + std::to_string(f) + ": bad variable range (rank <= 10)");
+    Factor F;
+    for (int k = a; k < b; ++k) {
+      const int v = d->factor_vars[k];
+      if (v < 0 || v >= d->n_vars) throw std::runtime_error("factor " + std::to_string(f) + ": variable id out of range");
+      F.vars.push_back(v);
+    }
+    F.table.assign(d->factor_tables + toff, d->factor_tables + toff + ((size_t)1 << (b - a)));
+    toff += (size_t)1 << (b - a);
+    P.factors.push_back(F);
+  }
+  int n_syn = 0, n_obs = 0;
+  for (int r = 0; r < d->n_rows; ++r) {
+    const int a = d->row_ptr[r], b = d->row_ptr[r + 1];
+    if (a < 0 || b < a) throw std::runtime_error("row " + std::to_string(r) + ": bad variable range");
+    Check C;
+    C.kind = d->row_kind[r]; C.index = d->row_index[r];
+    if (C.kind == 0) { if (C.index < 0 || C.index >= d->n_checks) throw std::runtime_error("row " + std::to_string(r) + ": syndrome bit out of range"); ++n_syn; }
+    else if (C.kind == 1) { if (C.index < 0 || C.index >= d->n_obs) throw std::runtime_error("row " + std::to_string(r) + ": observable index out of range"); ++n_obs; }
+    else throw std::runtime_error("row " + std::to_string(r) + ": unknown kind");
+    for (int k = a; k < b; ++k) {
+      const int v = d->row_vars[k];
+      if (v < 0 || v >= d->n_vars) throw std::runtime_error("row " + std::to_string(r) + ": variable id out of range");
+      C.vars.push_back(v);
+    }
+    P.checks.push_back(C);
+  }
+  if (n_obs != d->n_obs) throw std::runtime_error("every observable row must be declared exactly once");
+  if (d->order) {
+    P.has_order = true;
+    P.order.assign(d->order, d->order + d->n_factors);
+  }
+}
+
+static void lower_problem(const tqec_problem_desc *d, tqec_lowered &L) {
+  Problem P;
+  read_problem(d, P);
+  L.semiring = P.semiring; L.n_vars = P.n_vars; L.n_checks = P.n_checks; L.n_obs = P.n_obs; L.table_bits = d->table_bits;
+  const bool no_sweep = (d->flags & TQEC_COMPILE_NO_SWEEP) || std::getenv("TQEC_NO_SWEEP");
+  const std::vector<int> *order = P.has_order ? &P.order : nullptr;
+  if (P.semiring == TQEC_SEMIRING_MAXPLUS) {
+    const int head_bits = env_int("TQEC_HEAD_BITS", d->head_bits > 0 ? d->head_bits : 12);
+    if (!no_sweep) {
+      bool ok = false;
+      Schedule su;
+      try {
+        su = lower_schedule(P.factors, P.checks, P.semiring, P.n_vars, P.n_checks, 0, order, 13, 0, false);
+        if (env_int("TQEC_SWEEP_MINW", 5) <= su.w_max && su.w_max <= 10) ok = lower_sweep(su, head_bits, L.sw);
+      } catch (const std::runtime_error &) {
+        ok = false;
+      }
+      if (ok) { L.kind = 1; L.sch = su; return; }
+    }
+    const int fuse = (d->flags & TQEC_COMPILE_NO_FUSE) ? 0 : -1;
+    L.sch = lower_schedule(P.factors, P.checks, P.semiring, P.n_vars, P.n_checks, 0, order, 13, fuse, false);
+    L.kind = 0;
+    return;
+  }
+  // sum-product: one order for either executor
+  std::vector<Factor> merged = merge_overlapping(P.factors, P.n_vars, P.checks);
+  std::vector<Check> checks;
+  for (auto &c : P.checks) {
+    Check q;
+    q.kind = c.kind; q.index = c.index;
+    for (int v : c.vars)
+      if (std::find(q.vars.begin(), q.vars.end(), v) == q.vars.end()) q.vars.push_back(v);
+    checks.push_back(q);
+  }
+  std::vector<int> ord = P.has_order ? map_order(P.factors, merged, P.order) : choose_order(merged, checks);
+  const int w_max = evaluate_order(merged, checks, ord).first;
+  const bool force_wide = (d->flags & TQEC_COMPILE_FORCE_WIDE) || std::getenv("TQEC_FORCE_WIDE");
+  if (w_max <= 13 && !force_wide) {
+    L.sch = lower_schedule(merged, checks, P.semiring, P.n_vars, P.n_checks, P.n_obs, &ord, 13, 0, false);
+    L.kind = 0;
+    if (!no_sweep && L.sch.w_max >= 5 && L.sch.w_max <= 10) {
+      bool ok = false;
+      try { ok = lower_sweep(L.sch, d->head_bits > 0 ? d->head_bits : 10, L.sw); } catch (const std::runtime_error &) { ok = false; }
+      if (ok) L.kind = 1;
+    }
+    return;
+  }
+  const int t_max = env_int("TQEC_WIDE_TMAX", d->wide_t_max > 0 ? d->wide_t_max : 12);
+  L.wd = lower_wide(merged, checks, P.semiring, P.n_vars, P.n_checks, P.n_obs, &ord, t_max, 4);
+  L.kind = 2;
+}
+
+static void finish(tqec_lowered &L) {
+  L.meta.assign(16, 0);
+  L.meta[0] = L.kind;
+  if (L.kind == 2) {
+    L.meta[1] = L.wd.n_steps; L.meta[2] = L.wd.w_cap; L.meta[3] = L.wd.log2_scale;
+    L.meta[11] = L.wd.n_pass; L.meta[12] = L.wd.n_steps; L.meta[13] = L.wd.w_cap; L.meta[14] = L.wd.t_max;
+    L.cost = {L.wd.cost, L.wd.bytes_per_shot};
+    L.order32.assign(L.wd.order.begin(), L.wd.order.end());
+    L.obs32.assign(L.wd.obs_pos.begin(), L.wd.obs_pos.end());
+  } else {
+    L.meta[1] = (int32_t)L.sch.steps.size(); L.meta[2] = L.sch.w_max; L.meta[3] = L.sch.log2_scale;
+    L.cost = {L.sch.cost, 0.0};
+    L.order32.assign(L.sch.order.begin(), L.sch.order.end());
+    L.obs32.assign(L.sch.obs_slot.begin(), L.sch.obs_slot.end());
+    if (L.kind == 1) {
+      L.meta[4] = L.sw.W; L.meta[5] = L.sw.sg; L.meta[6] = L.sw.n_ss; L.meta[7] = (int32_t)L.sw.head_bits.size();
+      L.meta[8] = L.sw.bp_words; L.meta[9] = L.sw.head_steps; L.meta[10] = L.sw.conflicts;
+      L.head_bits32.assign(L.sw.head_bits.begin(), L.sw.head_bits.end());
+      L.out_index32.assign(L.sw.out_index.begin(), L.sw.out_index.end());
+    }
+  }
+  L.meta[15] = L.table_bits;
+  if (L.obs32.empty()) L.obs32.push_back(0);
+  if (L.head_bits32.empty()) L.head_bits32.push_back(0);
+}
+
+extern "C" int tqec_lower(const tqec_problem_desc *prob, tqec_lowered **out) {
+  TQEC_REQUIRE(out != nullptr, "tqec_lower: out is NULL");
+  *out = nullptr;
+  tqec_lowered *L = new tqec_lowered();
+  try {
+    lower_problem(prob, *L);
+    finish(*L);
+  } catch (const std::exception &e) {
+    delete L;
+    const bool unsupported = std::strstr(e.what(), "frontier needs") != nullptr || std::strstr(e.what(), "tile bits") != nullptr;
+    set_error("tqec_lower: %s", e.what());
+    return unsupported ? TQEC_ERR_UNSUPPORTED : TQEC_ERR_INVALID;
+  }
+  *out = L;
+  return TQEC_OK;
+}
+
+extern "C" int tqec_lowered_destroy(tqec_lowered *lw) {
+  delete lw;
+  return TQEC_OK;
+}
+
+extern "C" int tqec_lowered_get(const tqec_lowered *L, int32_t what, const void **data, int64_t *count) {
+  TQEC_REQUIRE(L && data && count, "tqec_lowered_get: NULL argument");
+#define LW_RET(vec) do { *data = (vec).data(); *count = (int64_t)(vec).size(); return TQEC_OK; } while (0)
+  switch (what) {
+    case TQEC_LW_META: LW_RET(L->meta);
+    case TQEC_LW_COST: LW_RET(L->cost);
+    case TQEC_LW_ORDER: LW_RET(L->order32);
+    case TQEC_LW_HDR: LW_RET(L->sch.hdr);
+    case TQEC_LW_INTS: LW_RET(L->sch.ints);
+    case TQEC_LW_TABLES: LW_RET(L->sch.tables);
+    case TQEC_LW_OBS_SLOT: LW_RET(L->obs32);
+    case TQEC_LW_SW_REC: LW_RET(L->sw.rec);
+    case TQEC_LW_SW_TB: LW_RET(L->sw.tb);
+    case TQEC_LW_SW_LANETAB: LW_RET(L->sw.lanetab);
+    case TQEC_LW_SW_TVALS: LW_RET(L->sw.tvals);
+    case TQEC_LW_SW_HEAD_BITS: LW_RET(L->head_bits32);
+    case TQEC_LW_SW_HEAD_STATE: LW_RET(L->sw.head_state);
+    case TQEC_LW_SW_HEAD_CFG: LW_RET(L->sw.head_cfg);
+    case TQEC_LW_SW_OUT_INDEX: LW_RET(L->out_index32);
+    case TQEC_LW_WD_PASS_HDR: LW_RET(L->wd.pass_hdr);
+    case TQEC_LW_WD_STEP_HDR: LW_RET(L->wd.step_hdr);
+    case TQEC_LW_WD_INTS: LW_RET(L->wd.ints);
+    case TQEC_LW_WD_TABLES: LW_RET(L->wd.tables);
+    case TQEC_LW_WD_OBS_POS: LW_RET(L->obs32);
+    default: break;
+  }
+#undef LW_RET
+  set_error("tqec_lowered_get: unknown item %d", what);
+  return TQEC_ERR_INVALID;
+}
+
+extern "C" int tqec_plan_from_lowered(const tqec_lowered *L, int32_t device, tqec_plan **out) {
+  TQEC_REQUIRE(L && out, "tqec_plan_from_lowered: NULL argument");
+  tqec_plan_desc d;
+  std::memset(&d, 0, sizeof(d));
+  d.semiring = L->semiring; d.n_vars = L->n_vars; d.n_checks = L->n_checks; d.n_obs = L->n_obs;
+  d.device = device; d.table_bits = L->table_bits;
+  tqec_sweep_desc sd;
+  tqec_wide_desc wd;
+  if (L->kind == 2) {
+    std::memset(&wd, 0, sizeof(wd));
+    wd.n_pass = L->wd.n_pass; wd.n_steps = L->wd.n_steps; wd.w_cap = L->wd.w_cap; wd.t_max = L->wd.t_max;
+    wd.pass_hdr = L->wd.pass_hdr.data(); wd.step_hdr = L->wd.step_hdr.data();
+    wd.ints = L->wd.ints.data(); wd.n_ints = (int64_t)L->wd.ints.size();
+    wd.tables = L->wd.tables.data(); wd.n_tables = (int64_t)L->wd.tables.size();
+    wd.obs_pos = L->obs32.data();
+    d.wide = &wd; d.w_max = L->wd.w_cap; d.log2_scale = L->wd.log2_scale;
+  } else {
+    d.n_steps = (int32_t)L->sch.steps.size(); d.w_max = L->sch.w_max;
+    d.hdr = L->sch.hdr.data(); d.ints = L->sch.ints.data(); d.n_ints = (int64_t)L->sch.ints.size();
+    d.tables = L->sch.tables.data(); d.n_tables = (int64_t)L->sch.tables.size();
+    d.obs_slot = L->obs32.data(); d.log2_scale = L->sch.log2_scale;
+    if (L->kind == 1) {
+      std::memset(&sd, 0, sizeof(sd));
+      sd.W = L->sw.W; sd.sg = L->sw.sg; sd.n_ss = L->sw.n_ss; sd.n_head_bits = (int32_t)L->sw.head_bits.size();
+      sd.bp_words = L->sw.bp_words; sd.n_tvals = (int32_t)L->sw.tvals.size();
+      sd.rec = L->sw.rec.data(); sd.tb = L->sw.tb.data(); sd.lanetab = L->sw.lanetab.data(); sd.tvals = L->sw.tvals.data();
+      sd.head_bits = L->head_bits32.data(); sd.head_state = L->sw.head_state.data(); sd.head_cfg = L->sw.head_cfg.data();
+      sd.out_index = L->out_index32.data();
+      d.sweep = &sd;
+    }
+  }
+  return tqec_plan_create(&d, out);
+}
+
+extern "C" int tqec_plan_compile(const tqec_problem_desc *prob, tqec_plan **out) {
+  TQEC_REQUIRE(prob && out, "tqec_plan_compile: NULL argument");
+  *out = nullptr;
+  tqec_lowered *L = nullptr;
+  int rc = tqec_lower(prob, &L);
+  if (rc) return rc;
+  rc = tqec_plan_from_lowered(L, prob->device, out);
+  tqec_lowered_destroy(L);
+  return rc;
+}

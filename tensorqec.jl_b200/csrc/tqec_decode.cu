@@ -731,8 +731,32 @@ __global__ void k_lookup(const uint64_t *__restrict__ synd, int64_t B, int nsw, 
   }
 }
 
+// undo the static power-of-two scaling of a sum-product plan's tables (exact)
+__global__ void k_scale_out(double *__restrict__ out, int64_t n, int e) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = ldexp(out[i], e);
+}
+
+static int launch_decode_raw(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d_corr, double *d_out,
+                             int32_t *d_argmax, cudaStream_t stream);
+
 int launch_decode(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d_corr, double *d_out,
                   int32_t *d_argmax, cudaStream_t stream) {
+  int rc = launch_decode_raw(plan, d_synd, B, d_corr, d_out, d_argmax, stream);
+  if (rc || B <= 0) return rc;
+  // tabulated plans hold already rescaled values (the table was filled through this function)
+  if (plan->semiring == TQEC_SEMIRING_SUMPROD && plan->log2_scale != 0 && !plan->has_table && d_out) {
+    const int64_t n = B << plan->dev.n_obs;
+    const int64_t want = (n + 255) / 256;
+    const int grid = (int)(want < (int64_t)plan->sm_count * 8 ? want : (int64_t)plan->sm_count * 8);
+    k_scale_out<<<grid, 256, 0, stream>>>(d_out, n, plan->log2_scale);
+    TQEC_CUDA(cudaGetLastError());
+  }
+  return TQEC_OK;
+}
+
+static int launch_decode_raw(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d_corr, double *d_out,
+                             int32_t *d_argmax, cudaStream_t stream) {
   if (B <= 0) return TQEC_OK;
   if (plan->has_table) {
     const bool mp = plan->semiring == TQEC_SEMIRING_MAXPLUS;
@@ -1017,6 +1041,7 @@ extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
   std::memset(p, 0, sizeof(*p));
   p->device = d->device;
   p->semiring = d->semiring;
+  p->log2_scale = d->semiring == TQEC_SEMIRING_SUMPROD ? d->log2_scale : 0;
   p->sm_count = prop.multiProcessorCount;
   if (d->wide) {
     // global-memory executor: none of the on-chip machinery below applies

@@ -453,15 +453,22 @@ extern "C" int tqec_mc_run(const tqec_mc_desc *mc, uint64_t seed, int64_t shot_o
     if (!rc) rc = launch_flags(mc->L, d_cls, d_err, d_cor, b, nullptr, d_counts, st);
   }
   unsigned long long h[4] = {0, 0, 0, 0};
+  if (rc == TQEC_OK && mc->comm) {
+    // the one collective: device counters {x, z, any, shots} summed over the ranks, on the pipeline's stream
+    const unsigned long long ns = (unsigned long long)n_shots;
+    MC_TRY(cudaMemcpyAsync(d_counts + 3, &ns, 8, cudaMemcpyHostToDevice, st));
+    if (rc == TQEC_OK) rc = comm_allreduce_dev(mc->comm, d_counts, st);
+  }
   if (rc == TQEC_OK) {
     MC_TRY(cudaEventRecord(e1, st));
-    MC_TRY(cudaMemcpyAsync(h, d_counts, 24, cudaMemcpyDeviceToHost, st));
+    MC_TRY(cudaMemcpyAsync(h, d_counts, 32, cudaMemcpyDeviceToHost, st));
     MC_TRY(cudaStreamSynchronize(st));
     if (rc == TQEC_OK && elapsed_ms) MC_TRY(cudaEventElapsedTime(elapsed_ms, e0, e1));
   }
 #undef MC_TRY
   if (rc == TQEC_OK) {
-    counts[0] += (int64_t)h[0]; counts[1] += (int64_t)h[1]; counts[2] += (int64_t)h[2]; counts[3] += n_shots;
+    counts[0] += (int64_t)h[0]; counts[1] += (int64_t)h[1]; counts[2] += (int64_t)h[2];
+    counts[3] += mc->comm ? (int64_t)h[3] : n_shots;
   }
   cudaFree(d_err); cudaFree(d_syn); cudaFree(d_cor); cudaFree(d_counts); cudaFree(d_cls); cudaFree(d_p);
   if (e0) cudaEventDestroy(e0);

@@ -178,28 +178,69 @@ def extract_decoding(cgdp: CSSToGeneralDecodingProblem, error_pattern: np.ndarra
 
 
 # ---- TNMAP (tndecoder.jl:16-57) -------------------------------------------------------------------------------------
-class CompiledTNMAP(CompiledDecoder):
-    def __init__(self, sch: S.Schedule, qubit_num: int, device: int):
-        self.schedule = sch
-        self.qubit_num = qubit_num
-        self.plan = _cabi.Plan(sch, device)
-        self.device = device
+def _table_bits_abi(tb) -> int:
+    """decoder.table_bits -> ABI value (0 = library default, -1 = never)."""
+    return 0 if tb is None else (-1 if int(tb) <= 0 else int(tb))
 
 
-def tnmap_schedule(decoder: TNMAP, problem: GeneralDecodingProblem) -> S.Schedule:
-    """Host-only part of compile(::TNMAP, ::GeneralDecodingProblem): factor graph -> lowered schedule."""
+class _LazySchedule:
+    """`compile` lowers the factor graph INSIDE libtqec_cuda.so (tqec_lower, csrc/tqec_lower*.cpp).  The Python
+    lowering (schedule.py / sweep.py / wide.py) is the test oracle of that code and emits bit-identical tables
+    (tests/test_lower_cpp.py); `.schedule` runs it on demand -- with the absorption order the library chose -- for
+    tests and inspection.  TQEC_PY_LOWERING=1 makes `compile` upload the Python tables instead."""
+
+    def _init_plan(self, problem_args, py_lower, device, decoder):
+        self._py_lower = py_lower
+        self._schedule = None
+        if os.environ.get("TQEC_PY_LOWERING") is not None:
+            self._schedule = py_lower(None)
+            self.plan = _cabi.Plan(self._schedule, device)
+        else:
+            factors, checks, semiring, n_vars, n_checks, n_obs, order = problem_args
+            prob = _cabi.Problem(factors, checks, semiring, n_vars, n_checks, n_obs, order=order,
+                                 head_bits=int(getattr(decoder, "head_bits", 0) or 0),
+                                 table_bits=_table_bits_abi(decoder.table_bits), device=device)
+            self.plan = _cabi.Plan.compile(prob)
+
+    @property
+    def schedule(self):
+        if self._schedule is None:
+            self._schedule = self._py_lower(self.plan.order)
+        return self._schedule
+
+
+class CompiledTNMAP(CompiledDecoder, _LazySchedule):
+    def __init__(self, decoder: "TNMAP", problem: "GeneralDecodingProblem"):
+        factors, checks = _tnmap_graph(problem)
+        t = problem.tanner
+        self.qubit_num = t.nq
+        self.n_checks = t.ns
+        self.device = decoder.device
+        order = _order_of(decoder.optimizer, len(factors))
+        self._init_plan((factors, checks, S.MAXPLUS, t.nq, t.ns, 0, order),
+                        lambda o: _tnmap_lower(decoder, factors, checks, t.nq, t.ns, order if o is None else o),
+                        decoder.device, decoder)
+
+
+def _tnmap_graph(problem: GeneralDecodingProblem):
+    """The factor graph of compile(::TNMAP, ::GeneralDecodingProblem) (tndecoder.jl:33-50): one factor per prior tensor,
+    one clamped parity row per check."""
     t = problem.tanner
     factors = [S.Factor(tuple(int(v) for v in ix), S.flat_table(tt)) for ix, tt in zip(problem.ptn.ixs, problem.ptn.tensors)]
     for f in factors:
         if any(not 0 <= v < t.nq for v in f.vars):
             raise IndexError("prior tensor label outside 0..nq-1")
     checks = [S.Check(tuple(c), "syn", s) for s, c in enumerate(t.s2q)]
-    order = _order_of(decoder.optimizer, len(factors))
+    return factors, checks
+
+
+def _tnmap_lower(decoder, factors, checks, nq, ns, order) -> S.Schedule:
+    """Python lowering of a TNMAP factor graph (the oracle of tqec_lower for max-plus plans)."""
     if os.environ.get("TQEC_NO_SWEEP") is None:
         # preferred lowering: the in-place patch sweep of the unfused schedule (sweep.py); plans whose steps do not fit
         # its shapes fall through to the general kernels
         try:
-            su = S.lower(factors, checks, S.MAXPLUS, t.nq, t.ns, 0, order=order, fuse=False)
+            su = S.lower(factors, checks, S.MAXPLUS, nq, ns, 0, order=order, fuse=False)
             sw = lower_sweep(su, max_head_bits=int(os.environ.get("TQEC_HEAD_BITS", decoder.head_bits))) if int(os.environ.get("TQEC_SWEEP_MINW", "5")) <= su.w_max <= 10 else None
         except ValueError:
             sw = None
@@ -207,9 +248,15 @@ def tnmap_schedule(decoder: TNMAP, problem: GeneralDecodingProblem) -> S.Schedul
             su.sweep = sw
             su.table_bits = decoder.table_bits
             return su
-    sch = S.lower(factors, checks, S.MAXPLUS, t.nq, t.ns, 0, order=order)
+    sch = S.lower(factors, checks, S.MAXPLUS, nq, ns, 0, order=order)
     sch.table_bits = decoder.table_bits
     return sch
+
+
+def tnmap_schedule(decoder: TNMAP, problem: GeneralDecodingProblem) -> S.Schedule:
+    """Host-only part of compile(::TNMAP, ::GeneralDecodingProblem) in Python: factor graph -> lowered schedule."""
+    factors, checks = _tnmap_graph(problem)
+    return _tnmap_lower(decoder, factors, checks, problem.tanner.nq, problem.tanner.ns, _order_of(decoder.optimizer, len(factors)))
 
 
 def _lower_sumprod(factors, checks, n_vars, n_checks, n_obs, order):
@@ -217,7 +264,10 @@ def _lower_sumprod(factors, checks, n_vars, n_checks, n_obs, order):
     the global-memory lowering (wide.py).  The order is chosen once and shared by both."""
     all_check_vars = {v for c in checks for v in c.vars}
     merged = S.merge_overlapping(list(factors), n_vars, all_check_vars)
-    order = S.map_order(factors, merged, order) if order is not None else S.choose_order(merged, checks)
+    if order is None:
+        order = S.choose_order(merged, checks)
+    elif len(order) == len(factors) and len(factors) != len(merged):
+        order = S.map_order(factors, merged, order)
     w_max, _ = S._evaluate(order, S._Sim(merged, checks))
     if w_max <= S.MAX_SMEM_WIDTH and os.environ.get("TQEC_FORCE_WIDE") is None:
         return S.lower(merged, checks, S.SUMPROD, n_vars, n_checks, n_obs, order=order)
@@ -238,7 +288,7 @@ def _attach_sweep(sch, max_head_bits: int = 10):
 
 
 def _compile_tnmap(decoder: TNMAP, problem: GeneralDecodingProblem) -> CompiledTNMAP:
-    return CompiledTNMAP(tnmap_schedule(decoder, problem), problem.tanner.nq, decoder.device)
+    return CompiledTNMAP(decoder, problem)
 
 
 def _syndrome_bits(s, n) -> np.ndarray:
@@ -251,7 +301,7 @@ def _syndrome_bits(s, n) -> np.ndarray:
 
 def _decode_tnmap(ct: CompiledTNMAP, syndrome: SimpleSyndrome) -> DecodingResult:
     single = as_bits(syndrome.s).ndim == 1
-    bits = _syndrome_bits(syndrome.s, ct.schedule.n_checks)
+    bits = _syndrome_bits(syndrome.s, ct.n_checks)
     corr, logp = ct.plan.decode_map(pack_bits(bits))
     cfg = unpack_bits(corr, ct.qubit_num)
     ok = np.isfinite(logp)
@@ -268,11 +318,15 @@ class CompiledGeneralDecoder(CompiledDecoder):
 
 
 # ---- TNMMAP, CSS (tndecoder.jl:85-174) --------------------------------------------------------------------------------
-class CompiledTNMMAP(CompiledDecoder):
-    def __init__(self, tanner, lx, lz, sch, R, L, FIX, device):
-        self.tanner, self.lx, self.lz = tanner, lx, lz
-        self.schedule = sch
-        self.plan = _cabi.Plan(sch, device)
+class CompiledTNMMAP(CompiledDecoder, _LazySchedule):
+    def __init__(self, decoder: "TNMMAP", problem: "IndependentDepolarizingDecodingProblem"):
+        lx, lz, factors, checks, dims, R, L, FIX = _tnmmap_css_graph(problem)
+        self.tanner, self.lx, self.lz = problem.tanner, lx, lz
+        n_vars, n_checks, self.n_obs = dims
+        device = decoder.device
+        order = _order_of(decoder.optimizer, len(factors))
+        self._init_plan((factors, checks, S.SUMPROD, n_vars, n_checks, self.n_obs, order),
+                        lambda o: _sumprod_lower(decoder, factors, checks, dims, order if o is None else o), device, decoder)
         self.R = _cabi.GF2Matrix(R, device)
         self.L = _cabi.GF2Matrix(L, device)
         self.FIX = _cabi.GF2Matrix(FIX, device)
@@ -285,13 +339,22 @@ class CompiledTNMMAP(CompiledDecoder):
         bits = np.concatenate([_syndrome_bits(syndrome.sx, self.tanner.stgx.ns),
                                _syndrome_bits(syndrome.sz, self.tanner.stgz.ns)], axis=1)
         mar, _ = self.plan.decode_marginal(pack_bits(bits))
-        k2 = self.schedule.n_obs
+        k2 = self.n_obs
         out = mar.reshape((mar.shape[0],) + (2,) * k2, order="F") if k2 else mar
         return out[0] if single else out
 
 
-def tnmmap_css_schedule(decoder: TNMMAP, problem: IndependentDepolarizingDecodingProblem):
-    """Host-only part of the CSS TNMMAP compile -> (lx, lz, schedule, R, L, FIX)."""
+def _sumprod_lower(decoder, factors, checks, dims, order):
+    """Python lowering of a marginal network (the oracle of tqec_lower for sum-product plans)."""
+    sch = _lower_sumprod(factors, checks, dims[0], dims[1], dims[2], order)
+    _attach_sweep(sch)
+    sch.table_bits = decoder.table_bits
+    return sch
+
+
+def _tnmmap_css_graph(problem: IndependentDepolarizingDecodingProblem):
+    """The marginal network of compile(::TNMMAP, CSS) (tndecoder.jl:97-146) as a factor graph, and the matrices of
+    error_pattern (:167-174) -> (lx, lz, factors, checks, (n_vars, n_checks, n_obs), R, L, FIX)."""
     tanner = problem.tanner
     n = tanner.stgx.nq
     nsx, nsz = tanner.stgx.ns, tanner.stgz.ns
@@ -304,9 +367,6 @@ def tnmmap_css_schedule(decoder: TNMMAP, problem: IndependentDepolarizingDecodin
     # open axes, in the reference's output order iy (tndecoder.jl:134): lx-parities of Z errors, then lz-parities of X errors
     checks += [S.Check(tuple(int(q) + n for q in np.flatnonzero(lx[i])), "obs", i) for i in range(k)]
     checks += [S.Check(tuple(int(q) for q in np.flatnonzero(lz[i])), "obs", k + i) for i in range(k)]
-    sch = _lower_sumprod(factors, checks, 2 * n, nsx + nsz, 2 * k, _order_of(decoder.optimizer, n))
-    _attach_sweep(sch)
-    sch.table_bits = decoder.table_bits
     # error_pattern (tndecoder.jl:167-174): any solution of the syndrome equations, moved into the decoded sector
     Rz, _ = gf2_right_inverse(tanner.stgz.H)            # ex = Rz sz
     Rx, _ = gf2_right_inverse(tanner.stgx.H)            # ez = Rx sx
@@ -319,12 +379,17 @@ def tnmmap_css_schedule(decoder: TNMMAP, problem: IndependentDepolarizingDecodin
     FIX[:k, n:] = lz
     L[k:, :n] = lz                                       # sector bit k + i = lz[i] . ex ; repaired by ex += lx[i]
     FIX[k:, :n] = lx
-    return lx, lz, sch, R, L, FIX
+    return lx, lz, factors, checks, (2 * n, nsx + nsz, 2 * k), R, L, FIX
+
+
+def tnmmap_css_schedule(decoder: TNMMAP, problem: IndependentDepolarizingDecodingProblem):
+    """Host-only part of the CSS TNMMAP compile in Python -> (lx, lz, schedule, R, L, FIX)."""
+    lx, lz, factors, checks, dims, R, L, FIX = _tnmmap_css_graph(problem)
+    return lx, lz, _sumprod_lower(decoder, factors, checks, dims, _order_of(decoder.optimizer, len(factors))), R, L, FIX
 
 
 def _compile_tnmmap_css(decoder: TNMMAP, problem: IndependentDepolarizingDecodingProblem) -> CompiledTNMMAP:
-    lx, lz, sch, R, L, FIX = tnmmap_css_schedule(decoder, problem)
-    return CompiledTNMMAP(problem.tanner, lx, lz, sch, R, L, FIX, decoder.device)
+    return CompiledTNMMAP(decoder, problem)
 
 
 def _decode_tnmmap_css(ct: CompiledTNMMAP, syndrome: CSSSyndrome) -> DecodingResult:
@@ -336,7 +401,7 @@ def _decode_tnmmap_css(ct: CompiledTNMMAP, syndrome: CSSSyndrome) -> DecodingRes
     ew, in_sector = _cabi.coset_rep(ct.R, ct.L, ct.FIX, words, pos)
     e = unpack_bits(ew, 2 * n)
     ok = (mar.max(axis=1) > 0) & in_sector
-    k2 = ct.schedule.n_obs
+    k2 = ct.n_obs
     marr = mar.reshape((mar.shape[0],) + (2,) * k2, order="F")
     if single:
         return DecodingResult(bool(ok[0]), CSSErrorPattern(e[0, :n], e[0, n:]), marginal=marr[0], sector=int(pos[0]))
@@ -344,11 +409,15 @@ def _decode_tnmmap_css(ct: CompiledTNMMAP, syndrome: CSSSyndrome) -> DecodingRes
 
 
 # ---- TNMMAP, detector error model (tndecoder.jl:176-271) -----------------------------------------------------------------
-class CompiledDEMTNMMAP(CompiledDecoder):
-    def __init__(self, tanner, l2q, sch, R, L, FIX, device):
+class CompiledDEMTNMMAP(CompiledDecoder, _LazySchedule):
+    def __init__(self, decoder: "TNMMAP", dem: DetectorErrorModel):
+        tanner, l2q, factors, checks, dims, R, L, FIX = _tnmmap_dem_graph(dem)
         self.tanner, self.l2q = tanner, l2q
-        self.schedule = sch
-        self.plan = _cabi.Plan(sch, device)
+        self.n_obs = dims[2]
+        device = decoder.device
+        order = _order_of(decoder.optimizer, len(factors))
+        self._init_plan((factors, checks, S.SUMPROD, dims[0], dims[1], dims[2], order),
+                        lambda o: _sumprod_lower(decoder, factors, checks, dims, order if o is None else o), device, decoder)
         self.R = _cabi.GF2Matrix(R, device)
         self.L = _cabi.GF2Matrix(L, device)
         self.FIX = _cabi.GF2Matrix(FIX, device)
@@ -357,21 +426,20 @@ class CompiledDEMTNMMAP(CompiledDecoder):
     def marginal(self, syndrome: SimpleSyndrome) -> np.ndarray:
         single = as_bits(syndrome.s).ndim == 1
         mar, _ = self.plan.decode_marginal(pack_bits(_syndrome_bits(syndrome.s, self.tanner.ns)))
-        k = self.schedule.n_obs
+        k = self.n_obs
         out = mar.reshape((mar.shape[0],) + (2,) * k, order="F") if k else mar
         return out[0] if single else out
 
 
-def tnmmap_dem_schedule(decoder: TNMMAP, dem: DetectorErrorModel):
-    """Host-only part of the DEM TNMMAP compile -> (tanner, l2q, schedule, R, L, FIX)."""
+def _tnmmap_dem_graph(dem: DetectorErrorModel):
+    """The marginal network of compile(::TNMMAP, ::DetectorErrorModel) (tndecoder.jl:186-219) as a factor graph
+    -> (tanner, l2q, factors, checks, (n_vars, n_checks, n_obs), R, L, FIX)."""
     tanner = dem2tanner(dem)
     ne, nd = tanner.nq, tanner.ns
     l2q = [[e for e in range(ne) if l in dem.flipped_detectors[e]] for l in dem.logical_list]
     factors = [S.Factor((e,), np.array([1.0 - p, p])) for e, p in enumerate(dem.error_rates)]
     checks = [S.Check(tuple(c), "syn", d) for d, c in enumerate(tanner.s2q)]
     checks += [S.Check(tuple(c), "obs", l) for l, c in enumerate(l2q)]
-    sch = _lower_sumprod(factors, checks, ne, nd, len(l2q), _order_of(decoder.optimizer, ne))
-    sch.table_bits = decoder.table_bits
     R, _ = gf2_right_inverse(tanner.H)
     L = np.zeros((len(l2q), ne), dtype=np.uint8)
     for l, c in enumerate(l2q):
@@ -382,12 +450,17 @@ def tnmmap_dem_schedule(decoder: TNMMAP, dem: DetectorErrorModel):
     # so joint flips of several observables are found too, and an unreachable sector is reported (success_tag False)
     # instead of returning a pattern in the wrong sector.
     FIX = gf2_sector_fixes(tanner.H, L)
-    return tanner, l2q, sch, R, L, FIX
+    return tanner, l2q, factors, checks, (ne, nd, len(l2q)), R, L, FIX
+
+
+def tnmmap_dem_schedule(decoder: TNMMAP, dem: DetectorErrorModel):
+    """Host-only part of the DEM TNMMAP compile in Python -> (tanner, l2q, schedule, R, L, FIX)."""
+    tanner, l2q, factors, checks, dims, R, L, FIX = _tnmmap_dem_graph(dem)
+    return tanner, l2q, _sumprod_lower(decoder, factors, checks, dims, _order_of(decoder.optimizer, len(factors))), R, L, FIX
 
 
 def _compile_tnmmap_dem(decoder: TNMMAP, dem: DetectorErrorModel) -> CompiledDEMTNMMAP:
-    tanner, l2q, sch, R, L, FIX = tnmmap_dem_schedule(decoder, dem)
-    return CompiledDEMTNMMAP(tanner, l2q, sch, R, L, FIX, decoder.device)
+    return CompiledDEMTNMMAP(decoder, dem)
 
 
 def _decode_tnmmap_dem(ct: CompiledDEMTNMMAP, syndrome: SimpleSyndrome) -> DecodingResult:
@@ -397,7 +470,7 @@ def _decode_tnmmap_dem(ct: CompiledDEMTNMMAP, syndrome: SimpleSyndrome) -> Decod
     ew, in_sector = _cabi.coset_rep(ct.R, ct.L, ct.FIX, words, pos)
     e = unpack_bits(ew, ct.tanner.nq)
     ok = (mar.max(axis=1) > 0) & in_sector                      # False: no undetectable pattern reaches the decoded sector
-    k = ct.schedule.n_obs
+    k = ct.n_obs
     marr = mar.reshape((mar.shape[0],) + (2,) * k, order="F")
     if single:
         return DecodingResult(bool(ok[0]), e[0], marginal=marr[0], sector=int(pos[0]))

@@ -35,6 +35,7 @@ emitted here; the permutation is chosen for the kernels (see the layout comment 
 """
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
@@ -108,6 +109,14 @@ class Schedule:
 
 
 # ------------------------------------------------------------------------------------------------------------
+def libm_log(table) -> np.ndarray:
+    """Log-weights of a factor through the C library's `log`, one entry at a time (log 0 = -inf).  numpy's vectorised
+    log (SIMD kernels chosen by CPU features) differs from it in the last bit on ~0.3 % of arguments; the C++ lowering
+    inside libtqec_cuda.so (csrc/tqec_lower.cpp) calls the same libm, so both lowerings emit identical tables."""
+    return np.array([math.log(x) if x > 0.0 else -math.inf for x in np.asarray(table, dtype=np.float64).reshape(-1)],
+                    dtype=np.float64)
+
+
 def flat_table(t) -> np.ndarray:
     """Tensor with one axis per variable (reference layout, column-major) -> flat array indexed by a."""
     t = np.asarray(t, dtype=np.float64)
@@ -539,8 +548,7 @@ def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_v
         perm = [pos[c] for c in live]
         w_out = len(live)
         if semiring == MAXPLUS:
-            with np.errstate(divide="ignore"):
-                tab = np.log(f.table)
+            tab = libm_log(f.table)
         else:
             # static per-step scaling: every factor is multiplied by a power of two (exact in FP64) chosen so that the
             # running product of the factors' largest entries stays within [2^-1/2, 2^1/2] -- the state can never
@@ -549,7 +557,7 @@ def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_v
             tab = f.table.copy()
             mx = float(tab.max())
             if mx > 0.0:
-                log2_run += float(np.log2(mx))
+                log2_run += math.log2(mx)
                 e = int(np.rint(log2_run))
                 log2_run -= e
                 tab = np.ldexp(tab, -e)

@@ -43,12 +43,29 @@ def allreduce_counts(counts, device=None) -> np.ndarray:
     return t.cpu().numpy()
 
 
-def sharded_mc_run(mc, n_shots: int, seed: int = 0, chunk: int = 0):
+def library_comm(device: int):
+    """This rank's communicator INSIDE libtqec_cuda.so (`tqec_comm_init`): rank 0 makes the NCCL unique id, the default
+    torch.distributed group only carries its 128 bytes to the other ranks (a Julia host would use Distributed.jl for
+    that).  -> `_cabi.Comm`, or None in a single-process run."""
+    dist, rank, world = _dist()
+    if world == 1:
+        return None
+    import torch
+    from . import _cabi
+    box = [_cabi.Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return _cabi.Comm(world, rank, box[0], device)
+
+
+def sharded_mc_run(mc, n_shots: int, seed: int = 0, chunk: int = 0, comm=None):
     """Run `mc` (a threshold.MonteCarlo bound to this rank's GPU) on this rank's share of `n_shots` and all-reduce
-    the counters.  -> (global counts[4], local device ms, (lo, hi))."""
+    the counters: inside the fused pipeline when `comm` (from `library_comm`) is given, else through torch.distributed.
+    -> (global counts[4], local device ms, (lo, hi))."""
     _, rank, world = _dist()
     lo, hi = shard_range(n_shots, rank, world)
-    counts, ms = mc.run(hi - lo, seed, shot_offset=lo, chunk=chunk)
+    counts, ms = mc.run(hi - lo, seed, shot_offset=lo, chunk=chunk, comm=comm)
+    if comm is not None:
+        return counts, ms, (lo, hi)
     return allreduce_counts(counts, mc.device), ms, (lo, hi)
 
 

@@ -299,10 +299,21 @@ def _assign_positions(groups, W, seed=0):
                 c += 1
         return c
 
-    rng = np.random.RandomState(seed)
+    state = (seed + 1) & 0xFFFFFFFFFFFFFFFF
+
+    def shuffled():
+        # Fisher-Yates driven by a 64-bit LCG (Knuth's MMIX constants): the same few lines in csrc/tqec_lower_sweep.cpp
+        nonlocal state
+        q = list(range(W))
+        for i in range(W - 1, 0, -1):
+            state = (state * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+            j = (state >> 33) % (i + 1)
+            q[i], q[j] = q[j], q[i]
+        return q
+
     best_p, best_c = list(range(W)), None
     for restart in range(40):
-        p = list(rng.permutation(W)) if restart else list(range(W))
+        p = shuffled() if restart else list(range(W))
         c = cost(p)
         improved = True
         while improved and c:

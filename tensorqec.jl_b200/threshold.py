@@ -70,10 +70,11 @@ class MonteCarlo:
         self.H = _cabi.GF2Matrix(H, device)
         self.L = _cabi.GF2Matrix(L, device)
 
-    def run(self, shots: int, seed: int = 0, shot_offset: int = 0, chunk: int = 0):
-        """-> (counts[4] = {X-type failures, Z-type failures, any failure, shots}, device milliseconds)."""
+    def run(self, shots: int, seed: int = 0, shot_offset: int = 0, chunk: int = 0, comm=None):
+        """-> (counts[4] = {X-type failures, Z-type failures, any failure, shots}, device milliseconds).  With `comm`
+        (a `_cabi.Comm`) the counters are summed over the job's ranks inside the pipeline (one ncclAllReduce)."""
         return _cabi.mc_run(self.plan, self.H, self.L, self.row_class, self.model, self.probs, seed, shot_offset,
-                            int(shots), chunk)
+                            int(shots), chunk, comm)
 
 
 def multi_round_qec(tanner, decoder, em, tanner_check=None, *, rounds: int = 10, seed: int = 0, device=None):

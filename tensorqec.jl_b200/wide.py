@@ -25,6 +25,7 @@ Sum-product plans only (TNMMAP, DEM or CSS); max-plus plans of this width would 
 """
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
@@ -182,7 +183,7 @@ def lower_wide(factors: Sequence[S.Factor], checks: Sequence[S.Check], semiring:
         tab = np.asarray(factors[fi].table, dtype=np.float64).copy()
         mx = float(tab.max())
         if mx > 0.0:
-            log2_run += float(np.log2(mx))                        # running product of the maxima stays near 1
+            log2_run += math.log2(mx)                             # running product of the maxima stays near 1
             e = int(np.rint(log2_run))
             log2_run -= e
             tab = np.ldexp(tab, -e)

@@ -16,3 +16,9 @@ def pytest_configure(config):
 def tq():
     import tensorqec.jl_b200 as tq
     return tq
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    import pathlib
+    return pathlib.Path(ROOT) / "tests" / "golden"

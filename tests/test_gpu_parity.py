@@ -527,6 +527,88 @@ def test_dem_error_pattern_lands_in_the_reported_sector(tq):
     assert checked > 50
 
 
+@pytest.mark.parametrize("d", [3, 5, 9])
+def test_library_compile_equals_python_lowering(tq, d, monkeypatch):
+    """`compile` lowers inside libtqec_cuda.so (tqec_lower -> tqec_plan_from_lowered; also the single call
+    tqec_plan_compile a Julia host makes): decodes are bit-identical to a plan uploaded from the Python lowering's
+    tables, for TNMAP (max-plus, traceback) and TNMMAP (sum-product), and to the recurrence oracle."""
+    import ctypes as C
+    from tensorqec.jl_b200 import _cabi, decoding as D, schedule as S
+    t, em = _css_case(tq, tq.SurfaceCode(d, d))
+    ex, ez, sx, sz = _syndromes(t, em, 77 + d, 500)
+    syn = tq.CSSSyndrome(sx, sz)
+    lib_map = tq.compile(tq.TNMAP(table_bits=0), t, em)
+    lib_mar = tq.compile(tq.TNMMAP(table_bits=0), t, em)
+    assert lib_map.cd._schedule is None and lib_mar._schedule is None     # no Python lowering ran
+    r_map, r_mar = tq.decode(lib_map, syn), tq.decode(lib_mar, syn)
+    monkeypatch.setenv("TQEC_PY_LOWERING", "1")
+    py_map = tq.compile(tq.TNMAP(table_bits=0), t, em)
+    py_mar = tq.compile(tq.TNMMAP(table_bits=0), t, em)
+    monkeypatch.delenv("TQEC_PY_LOWERING")
+    assert py_map.cd._schedule is not None
+    p_map, p_mar = tq.decode(py_map, syn), tq.decode(py_mar, syn)
+    assert np.array_equal(r_map.error_pattern.xerror, p_map.error_pattern.xerror)
+    assert np.array_equal(r_map.error_pattern.zerror, p_map.error_pattern.zerror)
+    assert np.array_equal(r_map.logp, p_map.logp)
+    assert np.array_equal(r_mar.marginal, p_mar.marginal) and np.array_equal(r_mar.sector, p_mar.sector)
+    assert lib_map.cd.plan.query(_cabi.Q_SWEEP) == py_map.cd.plan.query(_cabi.Q_SWEEP) == (1 if d >= 5 else 0)
+    lp, cfg = cref.FrontierPlan(py_map.cd.schedule).run(np.concatenate([sx, sz], axis=1))
+    assert np.array_equal(r_map.logp, lp) and np.array_equal(r_map.error_pattern.xerror, cfg[:, :d * d])
+    # the one-call entry point, raw
+    gdp, _ = tq.reduce2general(t, em)
+    factors, checks = D._tnmap_graph(gdp)
+    prob = _cabi.Problem(factors, checks, S.MAXPLUS, gdp.tanner.nq, gdp.tanner.ns, 0, table_bits=-1)
+    h = C.c_void_p()
+    _cabi.check(_cabi.lib().tqec_plan_compile(C.byref(prob.desc), C.byref(h)))
+    words = tq.pack_bits(np.concatenate([sx, sz], axis=1))
+    corr = np.zeros((500, max(1, (2 * d * d + 63) // 64)), dtype=np.uint64)
+    logp = np.zeros(500)
+    _cabi.check(_cabi.lib().tqec_decode_map(h, words.ctypes.data_as(C.c_void_p), 500, corr.ctypes.data_as(C.c_void_p),
+                                            logp.ctypes.data_as(C.c_void_p)))
+    _cabi.lib().tqec_plan_destroy(h)
+    assert np.array_equal(logp, lp) and np.array_equal(tq.unpack_bits(corr, 2 * d * d), cfg)
+
+
+def test_library_communicator_single_rank(tq):
+    """tqec_comm_* with one rank: the NCCL all-reduce inside the fused Monte-Carlo pipeline leaves the counters as they
+    are, and the stand-alone all-reduce returns its input (the 2 / 4 / 8-rank case runs under torchrun in bench.py)."""
+    from tensorqec.jl_b200 import _cabi
+    t, em = _css_case(tq, tq.SurfaceCode(5, 5))
+    mc = tq.MonteCarlo(t, tq.TNMAP(), em)
+    comm = _cabi.Comm(1, 0, _cabi.Comm.unique_id(), 0)
+    a, _ = mc.run(5000, seed=3)
+    b, _ = mc.run(5000, seed=3, comm=comm)
+    assert np.array_equal(a, b) and b[3] == 5000
+    assert np.array_equal(comm.allreduce_counts([1, 2, 3, 4]), [1, 2, 3, 4])
+    comm.close()
+
+
+def test_dem_d5_circuit_level_against_golden(tq, golden_dir):
+    """BASELINE configs[3] at full size: d = 5 x 5 rounds rotated-surface memory circuit with circuit-level noise
+    (1605 mechanisms, 120 detectors, 29-bit frontier) -> detector_error_model -> compile(TNMMAP) -> global-memory executor.
+    16 detector patterns against marginals the CPU oracle computed along the REVERSED absorption order
+    (tests/golden/make_dem_d5_golden.py; ~1 minute per shot on 8 cores), rtol 1e-10."""
+    import json
+    from tensorqec.jl_b200 import _cabi
+    g = json.load(open(golden_dir / "dem_d5_r5_golden.json"))
+    txt = tq.surface_memory_circuit(5, 5, "Z", 1e-3, 1e-3, 1e-3, 1e-3)
+    dem = tq.detector_error_model(tq.parse_stim_string(txt))
+    assert len(dem.error_rates) == g["n_mechanisms"] and dem.n_detectors == g["n_detectors"]
+    ct = tq.compile(tq.TNMMAP(), dem)
+    assert ct.plan.query(_cabi.Q_WIDE) == 1 and ct.plan.lowered["w_cap"] <= 29
+    B = len(g["detectors"])
+    syn = np.zeros((B, dem.n_detectors), dtype=np.uint8)
+    for b, dets in enumerate(g["detectors"]):
+        syn[b, dets] = 1
+    ref = np.array([[float.fromhex(x) for x in row] for row in g["marginal"]])
+    res = tq.decode(ct, tq.SimpleSyndrome(syn))
+    got = res.marginal.reshape(B, -1, order="F")
+    assert np.allclose(got, ref, rtol=MAR_RTOL, atol=0)
+    assert np.array_equal(res.sector, ref.argmax(axis=1))
+    assert (res.sector == np.array(g["true_observable"])).mean() >= 0.8
+    assert tq.SimpleSyndrome(syn) == tq.syndrome_extraction(res.error_pattern, ct.tanner) and np.all(res.success_tag)
+
+
 def test_property_full_size_d9(tq):
     """BASELINE config 3 shape (d=9, p=0.05) at a size the oracle cannot follow shot by shot: size-independent
     properties -- every correction reproduces its syndrome, decoding is idempotent on its own output's syndrome,
