@@ -1,22 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- syndromes decoded per second, TNMAP, d=9 rotated surface code, depolarizing p=0.05 (BASELINE configs[2]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--shots S]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--shots S] [--scaling strong|weak]
 
-One STEP = one pass of the decode hot path over one batch of S syndromes per GPU (default 1e7, the BASELINE batch).
-  value   : whole-job syndromes/s with the bit-packed syndromes already resident in HBM (one kernel launch per step,
-            timed with CUDA events on the launching stream, max over ranks).
+One STEP = one pass of the decode hot path over the job's batch of S syndromes (default 1e7, the BASELINE batch),
+sharded over the N ranks as contiguous global shot ranges (`--scaling strong`, the default: BASELINE configs[2] says
+"1e7 syndromes sharded over 1/2/4/8 GPUs"; `--scaling weak` gives every rank S syndromes).  At N = 1 both are the same.
+  value   : whole-job syndromes/s with the bit-packed syndromes already resident in HBM (one kernel launch per step and
+            rank, timed with CUDA events on the launching stream, max over ranks).
   e2e     : the same metric through the C-ABI call a Julia / Python host makes (`tqec_decode_map`) with HOST buffers
             (pinned): H2D of the syndromes + kernel + D2H of corrections and log-weights inside the timed region.
+  mc_e2e  : the fused Monte-Carlo pipeline (`tqec_mc_run`: Philox sampling -> syndrome extraction -> decode -> logical
+            check) over the same shot ranges WITH the one collective -- the NCCL all-reduce of the four counters, issued
+            by the library on the pipeline's stream -- inside the timed region.
+  api_e2e : (rank 0, N = 1) the user-level call `tq.decode(compiled, CSSSyndrome(sx, sz))` with one byte per bit in host
+            memory, i.e. including the host-side packing and unpacking around the C-ABI call.
   roofline: the decode kernel against the FP64 CUDA-core pipe (max-plus = one DADD + one DSETP per candidate); the
             denominator is measured in this run by `tqec_fp64_peak` because MEASURED_PEAKS.json has no FP64 entry;
-            the HBM view (algorithmic bytes per shot vs the measured copy bandwidth) is reported beside it.
+            `traffic` is measured in this run too (one ncu pass over one launch of the same plan, rank 0, N = 1).
   cpu_baseline: the C port of the same frontier recurrence (oracle/csrc/oracle.c) on all host cores, bounded sample.
 `--impl reference` times the reference's algorithm on the host cores: pairwise contraction of the DENSE network
 (unity vectors, dense parity tensors, greedy tree) one shot at a time, OpenMP over shots -- a compiled, optimistic
 stand-in for the Julia reference, which cannot run in this image (no Julia toolchain).
-Multi-GPU: one process per GPU (torchrun), shots sharded as contiguous global ranges, no data-path collective; the
-only exchange is the all-reduce of the logical-error counters of the fused Monte-Carlo pipeline (outside the timing).
+Multi-GPU: one process per GPU (torchrun), no data-path collective; the decoder is compiled with its shipped defaults.
 """
 import argparse
 import json
@@ -33,7 +39,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 D = 9
-HEAD_BITS = 14          # compile-time knob of the sweep lowering: the first 19 steps are tabulated (67 MB + 201 MB tables, 4 s)
+HEAD_BITS = int(os.environ["BENCH_HEAD_BITS"]) if os.environ.get("BENCH_HEAD_BITS") else None   # None = TNMAP's shipped default
 P_ERR = 0.05
 METRIC = "syndromes decoded/sec (TNMAP, d=9 surface code)"
 UNIT = "syndromes/s"
@@ -52,9 +58,16 @@ def env_int(name, default):
     return int(os.environ.get(name, default))
 
 
-def workload_name(shots):
-    return (f"d={D} rotated surface code, TNMAP, code-capacity depolarizing p={P_ERR}, {shots:.0e} syndromes per GPU "
-            f"per step, contiguous global shot ranges per rank (BASELINE configs[2])")
+def workload_name(shots, scaling="strong"):
+    per = "per step, sharded over the ranks" if scaling == "strong" else "per GPU per step"
+    return (f"d={D} rotated surface code, TNMAP, code-capacity depolarizing p={P_ERR}, {shots:.0e} syndromes {per}, "
+            f"contiguous global shot ranges per rank (BASELINE configs[2])")
+
+
+def _tnmap(tq, **kw):
+    if HEAD_BITS is not None:
+        kw["head_bits"] = HEAD_BITS
+    return tq.TNMAP(optimizer=_order(), **kw)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -97,9 +110,9 @@ def run_reference(args):
     sample = f"{n} syndromes per step (Philox seed 9, shots 0..{n - 1}), dense greedy tree sc=16, {dp.ops_per_shot:.3g} candidate ops per shot, forward + traceback"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.shots), "arm": "reference algorithm restated in C (oracle/csrc/oracle.c: "
+        "config": {"workload": workload_name(args.shots, args.scaling), "arm": "reference algorithm restated in C (oracle/csrc/oracle.c: "
                    "dense pairwise contraction, one shot at a time, OpenMP over shots) on the host cores; the Julia "
                    "reference cannot run in this image", "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
@@ -114,7 +127,7 @@ def _frontier_schedule(tq):
     t = tq.CSSTannerGraph(tq.SurfaceCode(D, D))
     em = tq.iid_error(P_ERR, t)
     gdp, _ = tq.reduce2general(t, em)
-    return t, em, tq.tnmap_schedule(tq.TNMAP(optimizer=_order(), head_bits=HEAD_BITS), gdp)
+    return t, em, tq.tnmap_schedule(_tnmap(tq), gdp)
 
 
 def _order():
@@ -185,31 +198,17 @@ def run_ours(args):
     import tensorqec.jl_b200 as tq
     from tensorqec.jl_b200 import _cabi, sharding
 
-    B = int(args.shots)
-    t, em, _ = _frontier_schedule(tq)
-    mc = tq.MonteCarlo(t, tq.TNMAP(optimizer=_order(), device=local, head_bits=HEAD_BITS), em)
+    total = int(args.shots)
+    strong = args.scaling == "strong"
+    t = tq.CSSTannerGraph(tq.SurfaceCode(D, D))
+    em = tq.iid_error(P_ERR, t)
+    t_c0 = time.perf_counter()
+    mc = tq.MonteCarlo(t, _tnmap(tq, device=local), em)
+    compile_s = time.perf_counter() - t_c0
     plan = mc.plan
-    sch = plan.sch
     geom = plan.geometry()
     nsw, ncw = plan.nsw, plan.ncw
-
-    # synthetic input: Philox errors -> syndromes for this rank's global shot range, produced by the library itself
-    lo = rank * B
-    err_words = _cabi.sample_errors(_cabi.MODEL_DEPOL, [em.px, em.py, em.pz], 9, lo, B, local)
-    syn_words = mc.H.apply(err_words)
-    h_syn = torch.from_numpy(syn_words.view(np.int64)).pin_memory()
-    h_cor = torch.empty((B, ncw), dtype=torch.int64).pin_memory()
-    h_lp = torch.empty((B,), dtype=torch.float64).pin_memory()
-    d_syn = h_syn.cuda(non_blocking=False)
-    d_cor = torch.empty((B, ncw), dtype=torch.int64, device="cuda")
-    d_lp = torch.empty((B,), dtype=torch.float64, device="cuda")
-    stream = torch.cuda.current_stream()
-
-    def step_resident():
-        plan.decode_map_dev(d_syn.data_ptr(), B, d_cor.data_ptr(), d_lp.data_ptr(), stream.cuda_stream)
-
-    def step_e2e():
-        _cabi.check(_cabi.lib().tqec_decode_map(plan.h, h_syn.data_ptr(), B, h_cor.data_ptr(), h_lp.data_ptr()))
+    comm = sharding.library_comm(local)              # NCCL communicator inside libtqec_cuda.so (None at N = 1)
 
     def barrier():
         torch.cuda.synchronize()
@@ -224,25 +223,60 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
 
-    # ---- value: resident inputs, device-timed --------------------------------------------------------------------
-    for _ in range(args.warmup):
-        step_resident()
-    launches0 = plan.query(_cabi.Q_LAUNCHES)
-    sampler = ClockSampler(local)
-    barrier()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_resident()
-    e1.record(stream)
-    barrier()
-    clocks = sampler.stop()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = plan.query(_cabi.Q_LAUNCHES) - launches0
-    value = world * B * args.steps / (ms_total * 1e-3)
+    stream = torch.cuda.current_stream()
 
-    # ---- e2e: host buffers through the C-ABI call ------------------------------------------------------------------
+    def make_inputs(lo, B):
+        """Philox errors -> syndromes for the global shot range [lo, lo + B), produced by the library itself."""
+        err_words = _cabi.sample_errors(_cabi.MODEL_DEPOL, [em.px, em.py, em.pz], 9, lo, B, local)
+        syn_words = mc.H.apply(err_words)
+        h_syn = torch.from_numpy(syn_words.view(np.int64)).pin_memory()
+        return syn_words, h_syn
+
+    def timed_resident(lo, B, steps, warmup):
+        """K timed launches over resident inputs.  When one step's buffers are smaller than the L2 (strong scaling at
+        large N) the steps rotate over enough distinct input / output buffers (further shot ranges of the same size)
+        that the footprint exceeds 256 MB, so no step finds its inputs in L2."""
+        per_step = B * (nsw + ncw + 1) * 8
+        n_buf = max(1, min(16, -(-260_000_000 // per_step)))
+        bufs = []
+        for k in range(n_buf):
+            syn_words, h_syn = make_inputs(lo + k * total * max(world, 1), B)
+            bufs.append((syn_words, h_syn, h_syn.cuda(non_blocking=False), torch.empty((B, ncw), dtype=torch.int64, device="cuda"),
+                         torch.empty((B,), dtype=torch.float64, device="cuda")))
+
+        def step(i):
+            _, _, d_syn, d_cor, d_lp = bufs[i % n_buf]
+            plan.decode_map_dev(d_syn.data_ptr(), B, d_cor.data_ptr(), d_lp.data_ptr(), stream.cuda_stream)
+        for i in range(warmup):
+            step(i)
+        n0 = plan.query(_cabi.Q_LAUNCHES)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            step(i)
+        e1.record(stream)
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        if n_buf > 1:
+            step(0)                                   # leave buffer 0 holding the results of ITS inputs for the e2e comparison
+            torch.cuda.synchronize()
+        return ms, plan.query(_cabi.Q_LAUNCHES) - n0, bufs[0], n_buf
+
+    # ---- value: resident inputs, device-timed ----------------------------------------------------------------------
+    lo, hi = sharding.shard_range(total, rank, world) if strong else (rank * total, (rank + 1) * total)
+    B = hi - lo
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_total, launches, (syn_words, h_syn, d_syn, d_cor, d_lp), n_buf = timed_resident(lo, B, args.steps, args.warmup)
+    clocks = sampler.stop()
+    job_shots = total if strong else total * world
+    value = job_shots * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: host buffers through the C-ABI call --------------------------------------------------------------------
+    h_cor = torch.empty((B, ncw), dtype=torch.int64).pin_memory()
+    h_lp = torch.empty((B,), dtype=torch.float64).pin_memory()
+    step_e2e = lambda: _cabi.check(_cabi.lib().tqec_decode_map(plan.h, h_syn.data_ptr(), B, h_cor.data_ptr(), h_lp.data_ptr()))
     for _ in range(min(args.warmup, 2)):
         step_e2e()
     barrier()
@@ -252,42 +286,73 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    e2e_value = world * B * args.steps / e2e_s
-    # results of both paths agree (same kernel, same inputs)
-    same = bool(torch.equal(h_cor, d_cor.cpu()) and torch.equal(h_lp, d_lp.cpu()))
+    e2e_value = job_shots * args.steps / e2e_s
+    same = bool(torch.equal(h_cor, d_cor.cpu()) and torch.equal(h_lp, d_lp.cpu()))   # both paths: same kernel, same inputs
 
-    # ---- ablation: the same decode with the shortest tabulated head (6 syndrome bits, 11 of the 81 steps looked up) ------
-    ablation = None
-    if rank == 0 and geom.get("sweep"):
-        gdp_a, _ = tq.reduce2general(t, em)
-        sch_a = tq.tnmap_schedule(tq.TNMAP(optimizer=_order(), device=local, head_bits=6), gdp_a)
-        plan_a = _cabi.Plan(sch_a, local)
-        d_cor_a = torch.empty_like(d_cor)
-        d_lp_a = torch.empty_like(d_lp)
-        for _ in range(2):
-            plan_a.decode_map_dev(d_syn.data_ptr(), B, d_cor_a.data_ptr(), d_lp_a.data_ptr(), stream.cuda_stream)
-        torch.cuda.synchronize()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record(stream)
-        for _ in range(2):
-            plan_a.decode_map_dev(d_syn.data_ptr(), B, d_cor_a.data_ptr(), d_lp_a.data_ptr(), stream.cuda_stream)
-        a1.record(stream)
-        torch.cuda.synchronize()
-        ablation = {"head_bits": 6, "tabulated_head_steps": sch_a.sweep.head_steps,
-                    "value_one_gpu": B * 2 / (a0.elapsed_time(a1) * 1e-3), "unit": UNIT,
-                    "identical_results": bool(torch.equal(d_cor_a, d_cor) and torch.equal(d_lp_a, d_lp))}
-        plan_a.close()
-        del d_cor_a, d_lp_a
-    if world > 1:
-        dist.barrier()
+    # ---- mc_e2e: sample -> syndrome -> decode -> check -> all-reduce, all inside the timed region ----------------------------
+    mc_steps = max(2, min(args.steps, 5))
+    mc.run(B, seed=9, shot_offset=lo, comm=comm)
+    barrier()
+    t0 = time.perf_counter()
+    mc_dev_ms = 0.0
+    for _ in range(mc_steps):
+        counts, ms1 = mc.run(B, seed=9, shot_offset=lo, comm=comm)
+        mc_dev_ms += ms1
+    mc_s = max_over_ranks(time.perf_counter() - t0)
+    mc_dev_ms = max_over_ranks(mc_dev_ms)
+    barrier()
+    if comm is None and world > 1:
+        counts = sharding.allreduce_counts(counts, local)
+    mc_e2e = {"value": job_shots * mc_steps / mc_s, "unit": UNIT, "device_value": job_shots * mc_steps / (mc_dev_ms * 1e-3),
+              "steps": mc_steps, "collective": ("ncclAllReduce of 4 x uint64 inside tqec_mc_run, every step" if comm is not None
+                                                else "none (single rank)"),
+              "counts": {"shots": int(counts[3]), "x": int(counts[0]), "z": int(counts[1]), "any": int(counts[2])}}
 
-    # ---- logical error counters through the fused pipeline + the one collective -------------------------------------
-    ler_shots = min(B, 1 << 20)
-    counts, mc_ms = mc.run(ler_shots, seed=9, shot_offset=rank * ler_shots)
-    counts = sharding.allreduce_counts(counts, local)
+    # ---- weak-scaling leg beside a strong-scaling headline -----------------------------------------------------------------
+    weak = None
+    if world > 1 and strong:
+        del d_syn, d_cor, d_lp
+        torch.cuda.empty_cache()
+        ms_w, _, keep, _ = timed_resident(rank * total, total, 2, 1)
+        weak = {"value": total * world * 2 / (ms_w * 1e-3), "unit": UNIT, "shots_per_gpu_per_step": total, "steps": 2}
+        del keep
 
+    # ---- rank 0 extras: user-level API, head ablation, traffic, CPU baseline -----------------------------------------------------
     line = None
     if rank == 0:
+        api = None
+        if world == 1:
+            nb = min(B, 2_000_000)
+            bits = tq.unpack_bits(syn_words[:nb], mc.H.rows)
+            nsx = t.stgx.ns
+            syn_obj = tq.CSSSyndrome(bits[:, :nsx], bits[:, nsx:])
+            tq.decode(mc.compiled, syn_obj)
+            t0 = time.perf_counter()
+            res = tq.decode(mc.compiled, syn_obj)
+            dt = time.perf_counter() - t0
+            api = {"value": nb / dt, "unit": UNIT, "shots": nb, "api": "tq.decode(compiled, CSSSyndrome(sx, sz)): one byte per "
+                   "bit in host memory in and out (bit packing inside the call)", "matches": bool(np.array_equal(
+                       res.logp, h_lp.numpy()[:nb]))}
+        ablation = None
+        if world == 1 and geom.get("sweep") and os.environ.get("BENCH_NO_ABLATION") is None:
+            mc_a = tq.MonteCarlo(t, tq.TNMAP(optimizer=_order(), device=local, head_bits=6), em)
+            d_syn_a = h_syn.cuda()
+            d_cor_a = torch.empty((B, ncw), dtype=torch.int64, device="cuda")
+            d_lp_a = torch.empty((B,), dtype=torch.float64, device="cuda")
+            run_a = lambda: mc_a.plan.decode_map_dev(d_syn_a.data_ptr(), B, d_cor_a.data_ptr(), d_lp_a.data_ptr(), stream.cuda_stream)
+            for _ in range(2):
+                run_a()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            for _ in range(2):
+                run_a()
+            a1.record(stream)
+            torch.cuda.synchronize()
+            ablation = {"head_bits": 6, "value_one_gpu": B * 2 / (a0.elapsed_time(a1) * 1e-3), "unit": UNIT,
+                        "identical_results": bool(torch.equal(d_cor_a.cpu(), h_cor) and torch.equal(d_lp_a.cpu(), h_lp))}
+            del d_syn_a, d_cor_a, d_lp_a, mc_a
+        sch = mc.compiled.cd.schedule                     # the Python lowering of the same plan (oracle of the library's): op counts
         peak = _cabi.fp64_peak(local)
         mul_all, add_all = sch.ops_per_shot()
         # executed per shot: the steps after the tabulated head (the head's steps are a table look-up, not arithmetic)
@@ -306,12 +371,10 @@ def run_ours(args):
                 pass
         bytes_per_shot = 8 * (nsw + ncw + 1)
         hbm_achieved = bytes_per_shot * B / dur_s / 1e9
-        # DRAM traffic of the decode kernel per shot from the newest committed ncu capture (back-pointer scratch streaming
-        # through HBM; the algorithmic I/O is 48 B per shot)
-        traffic_per_shot, traffic_src = _ncu_traffic_per_shot()
+        traffic, traffic_src = (None, "skipped (N > 1)") if world > 1 else measure_traffic(B)
         kname = "k_sweep<maxplus>" if geom.get("sweep") else "k_frontier_warp<maxplus>"
         roofline = {"bound": "fp64", "achieved": achieved, "peak": peak["dadd_tops"], "unit": "TFLOP/s",
-                    "frac": achieved / peak["dadd_tops"], "traffic": traffic_per_shot * B if traffic_per_shot else None,
+                    "frac": achieved / peak["dadd_tops"], "traffic": traffic,
                     "kernel": kname, "ops_per_shot": mul + add, "schedule_ops_per_shot": mul_all + add_all,
                     "tabulated_head_steps": h0,
                     "note": "FP64 CUDA-core pipe: one DADD per candidate + one DSETP per extra candidate of the EXECUTED "
@@ -325,13 +388,15 @@ def run_ours(args):
         cpu = cpu_baseline(tq, sch, syn_words, args)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(B), "shots_per_gpu_per_step": B,
-                       "l2": f"inputs larger than L2: {B * nsw * 8 / 1e6:.0f} MB of syndromes in, {B * (ncw + 1) * 8 / 1e6:.0f} MB out per step",
+            "config": {"workload": workload_name(total, args.scaling), "shots_per_step": job_shots, "shots_per_gpu_per_step": B,
+                       "l2": f"inputs larger than L2: {B * nsw * 8 / 1e6:.0f} MB of syndromes in, {B * (ncw + 1) * 8 / 1e6:.0f} MB out per GPU and step"
+                             + (f"; the steps rotate over {n_buf} distinct buffer sets (>= 260 MB footprint)" if n_buf > 1 else ""),
                        "schedule": {"steps": len(sch.steps), "w_max": sch.w_max, "candidates_per_shot": sch.cost,
-                                    "head_bits": HEAD_BITS, "note": "roofline ops count only the steps executed per shot (the "
-                                    "tabulated head is a table look-up)"},
+                                    "head_bits": len(sch.sweep.head_bits) if getattr(sch, "sweep", None) is not None else 0,
+                                    "lowering": "tqec_lower (C++, inside libtqec_cuda.so)", "compile_s": compile_s,
+                                    "note": "roofline ops count only the steps executed per shot (the tabulated head is a table look-up)"},
                        "launch": geom},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * nsw * 8, "d2h_bytes_per_step": B * (ncw + 1) * 8,
@@ -339,34 +404,65 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "mc_e2e": mc_e2e,
+            "api_e2e": api,
+            "weak": weak,
             "head_ablation": ablation,
-            "logical_errors": {"shots": int(counts[3]), "x": int(counts[0]), "z": int(counts[1]), "any": int(counts[2]),
-                               "pipeline_ms_rank0": mc_ms},
+            "logical_errors": mc_e2e["counts"],
         }
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
+        if comm is not None:
+            comm.close()
         dist.destroy_process_group()
     return 0
 
 
-def _ncu_traffic_per_shot():
-    """(bytes per shot, source) from the newest profiles/*_ncu_sweep_*_summary.csv: dram read + write of one captured
-    launch divided by its shots (the header line of the file states the shot count)."""
-    import glob
-    import re
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_sweep_*_summary.csv")))
-    if not files:
-        return None, "no ncu capture committed for this kernel"
-    txt = open(files[-1]).read()
-    m = re.search(r"shots=(\d+)", txt)
-    rd = re.search(r"dram__bytes_read.sum,Gbyte,([0-9.]+)", txt)
-    wr = re.search(r"dram__bytes_write.sum,Gbyte,([0-9.]+)", txt)
-    if not (m and rd and wr):
-        return None, f"could not parse {os.path.basename(files[-1])}"
-    per = (float(rd.group(1)) + float(wr.group(1))) * 1e9 / int(m.group(1))
-    return per, (f"ncu dram__bytes_read.sum + dram__bytes_write.sum per shot (profiles/{os.path.basename(files[-1])}) "
-                 f"x shots per launch")
+def measure_traffic(B):
+    """DRAM bytes of ONE decode launch over B shots of the same plan, measured now: one `ncu` pass (two counters, no
+    clock control) around `bench.py --traffic-probe`.  -> (bytes per launch or None, how it was obtained)."""
+    import csv
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    shots = min(B, 2_000_000)
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:k_sweep|k_frontier",
+           "-c", "1", "--launch-skip", "2", "--csv", sys.executable, os.path.abspath(__file__), "--traffic-probe", str(shots)]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=240).stdout
+    except Exception as e:                                   # noqa: BLE001
+        return None, f"ncu failed: {e}"
+    tot = 0.0
+    found = 0
+    for row in csv.reader(out.splitlines()):
+        if len(row) > 3 and row[-3].startswith("dram__bytes_"):
+            unit, val = row[-2], float(row[-1].replace(",", ""))
+            tot += val * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+            found += 1
+    if found < 2:
+        return None, "ncu printed no DRAM counters (profiling not permitted?)"
+    return tot * B / shots, (f"ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch over {shots} shots of this plan, "
+                             f"measured in this run and scaled to {B} shots")
+
+
+def traffic_probe(shots):
+    """Child of measure_traffic: four launches of the benchmark plan on `shots` syndromes (ncu profiles the third)."""
+    import torch
+    import tensorqec.jl_b200 as tq
+    from tensorqec.jl_b200 import _cabi
+    t = tq.CSSTannerGraph(tq.SurfaceCode(D, D))
+    em = tq.iid_error(P_ERR, t)
+    mc = tq.MonteCarlo(t, _tnmap(tq), em)
+    err = _cabi.sample_errors(_cabi.MODEL_DEPOL, [em.px, em.py, em.pz], 9, 0, shots, 0)
+    d_syn = torch.from_numpy(mc.H.apply(err).view(np.int64)).cuda()
+    d_cor = torch.empty((shots, mc.plan.ncw), dtype=torch.int64, device="cuda")
+    d_lp = torch.empty((shots,), dtype=torch.float64, device="cuda")
+    for _ in range(4):
+        mc.plan.decode_map_dev(d_syn.data_ptr(), shots, d_cor.data_ptr(), d_lp.data_ptr(), 0)
+    torch.cuda.synchronize()
+    return 0
 
 
 def cpu_baseline(tq, sch, syn_words, args):
@@ -394,9 +490,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--shots", type=float, default=1e7, help="syndromes per GPU per step")
+    ap.add_argument("--shots", type=float, default=1e7, help="syndromes per step (whole job if strong, per GPU if weak)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--traffic-probe", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--cpu-shots", type=int, default=0, help="override the bounded CPU sample size")
     args = ap.parse_args()
+    if args.traffic_probe:
+        return traffic_probe(args.traffic_probe)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
