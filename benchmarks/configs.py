@@ -45,7 +45,7 @@ def time_map(plan, words, reps=5):
 def time_marginal(plan, words, reps=5):
     B = words.shape[0]
     d_syn = torch.from_numpy(words.view(np.int64)).cuda()
-    d_mar = torch.empty((B, 1 << plan.sch.n_obs), dtype=torch.float64, device="cuda")
+    d_mar = torch.empty((B, 1 << plan.n_obs), dtype=torch.float64, device="cuda")
     d_arg = torch.empty((B,), dtype=torch.int32, device="cuda")
     st = torch.cuda.current_stream()
     for _ in range(3):
@@ -60,6 +60,34 @@ def time_marginal(plan, words, reps=5):
     return e0.elapsed_time(e1) / reps
 
 
+PEAK = {}
+
+
+def roofline(sch, geom, ms, B):
+    """Executed FP64 operations of one launch against the FP64 pipe rate measured on this device: max-plus = one DADD per
+    candidate + one DSETP per extra candidate vs the DADD instruction rate; sum-product = one multiply per candidate +
+    one add per extra candidate vs the DFMA rate (2 flops per instruction).  Tabulated head steps are not executed."""
+    if not PEAK:
+        PEAK.update(_cabi.fp64_peak(0))
+    if hasattr(sch, "passes"):                                  # global-memory executor: HBM-bound by construction
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6550.0
+        ach = sch.bytes_per_shot * B / (ms * 1e-3) / 1e9
+        flops = sch.cost * 2 * B / (ms * 1e-3) / 1e12
+        return {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "kernel": "k_wide_pass",
+                "bytes_per_shot": sch.bytes_per_shot, "fp64_tflops": flops, "fp64_frac_of_dfma": flops / PEAK["dfma_tflops"]}
+    if geom.get("table"):
+        return None
+    h0 = sch.sweep.head_steps if (getattr(sch, "sweep", None) is not None and geom.get("sweep")) else 0
+    mul = sum((1 << st.w_out) * len(st.ker) for st in sch.steps[h0:])
+    add = sum((1 << st.w_out) * (len(st.ker) - 1) for st in sch.steps[h0:])
+    ach = (mul + add) * B / (ms * 1e-3) / 1e12
+    if sch.semiring == 0:
+        return {"bound": "fp64", "achieved": ach, "peak": PEAK["dadd_tops"], "unit": "TFLOP/s", "frac": ach / PEAK["dadd_tops"],
+                "kernel": "k_sweep<maxplus>" if geom.get("sweep") else "k_frontier<maxplus>", "ops_per_shot": mul + add}
+    return {"bound": "fp64", "achieved": ach, "peak": PEAK["dfma_tflops"], "unit": "TFLOP/s", "frac": ach / PEAK["dfma_tflops"],
+            "kernel": "k_sweep<sumprod>" if geom.get("sweep") else "k_frontier<sumprod>", "ops_per_shot": mul + add}
+
+
 def css_case(name, code, p, B, seed, out):
     t = tq.CSSTannerGraph(code)
     em = tq.iid_error(p, t)
@@ -71,16 +99,18 @@ def css_case(name, code, p, B, seed, out):
     counts, mc_ms = mc.run(B, seed=seed)
     # CPU port on a subsample: identical corrections => identical counters
     n = min(B, 20000)
-    bits = tq.unpack_bits(syn[:n], plan.sch.n_checks)
+    sch = mc.compiled.cd.schedule if hasattr(mc.compiled, "cd") else mc.compiled.schedule
+    bits = tq.unpack_bits(syn[:n], sch.n_checks)
     t0 = time.perf_counter()
-    _, cfg = cref.FrontierPlan(plan.sch).run(bits, len(os.sched_getaffinity(0)))
+    _, cfg = cref.FrontierPlan(sch).run(bits, len(os.sched_getaffinity(0)))
     cpu_rate = n / (time.perf_counter() - t0)
     corr, _ = plan.decode_map(syn[:n], want_logp=False)
-    same = bool(np.array_equal(tq.unpack_bits(corr, plan.sch.n_vars), cfg))
+    same = bool(np.array_equal(tq.unpack_bits(corr, sch.n_vars), cfg))
     rec = {"case": name, "p": p, "shots": B, "ms": ms, "syndromes_per_s": B / (ms * 1e-3), "pipeline_ms": mc_ms,
            "pipeline_shots_per_s": B / (mc_ms * 1e-3), "logical": {"x": int(counts[0]), "z": int(counts[1]), "any": int(counts[2])},
            "ler": counts[2] / B, "cpu_port_syndromes_per_s": cpu_rate, "cpu_threads": len(os.sched_getaffinity(0)),
-           "gpu_equals_cpu_port": same, "geometry": plan.geometry(), "w_max": plan.sch.w_max, "candidates_per_shot": plan.sch.cost}
+           "gpu_equals_cpu_port": same, "geometry": plan.geometry(), "w_max": sch.w_max, "candidates_per_shot": sch.cost,
+           "roofline": roofline(sch, plan.geometry(), ms, B)}
     print(json.dumps(rec), file=out, flush=True)
     return rec
 
@@ -105,13 +135,16 @@ def main():
         syn = _cabi.GF2Matrix(H).apply(err)
         ms = time_marginal(ct.plan, syn)
         print(json.dumps({"case": f"TNMMAP d={d} CSS", "shots": B, "ms": ms, "syndromes_per_s": B / (ms * 1e-3),
-                          "geometry": ct.plan.geometry(), "w_max": ct.schedule.w_max, "candidates_per_shot": ct.schedule.cost}),
+                          "geometry": ct.plan.geometry(), "w_max": ct.schedule.w_max, "candidates_per_shot": ct.schedule.cost,
+                          "roofline": roofline(ct.schedule, ct.plan.geometry(), ms, B)}),
               file=out, flush=True)
     # DEM TNMMAP (config 4 input format): the reference's fixture + synthetic surface-memory DEMs (benchmarks/make_dem.py)
     for fname, label, B in (("dem.dem", "reference DEM fixture (21 mechanisms, 6 detectors)", 1_000_000),
                             ("surface_d3_r3_phenom.dem", "surface memory d=3 x 3 rounds, phenomenological", 1_000_000),
                             ("generated:3:3", "surface memory d=3 x 3 rounds, circuit-level noise p=1e-3 (circuit.py)", 100_000),
-                            ("surface_d5_r5_phenom.dem", "surface memory d=5 x 5 rounds, phenomenological", 200_000)):
+                            ("surface_d5_r5_phenom.dem", "surface memory d=5 x 5 rounds, phenomenological", 200_000),
+                            ("generated:5:5", "surface memory d=5 x 5 rounds, circuit-level noise p=1e-3 (circuit.py): 1605 "
+                                              "mechanisms, 120 detectors, 29-bit frontier, global-memory executor", 8)):
         if fname.startswith("generated:"):
             _, dd, rr = fname.split(":")
             dem = tq.detector_error_model(tq.parse_stim_string(tq.surface_memory_circuit(
@@ -122,10 +155,12 @@ def main():
         ct = tq.compile(tq.TNMMAP(), dem)
         ep = _cabi.sample_errors(_cabi.MODEL_FLIP, [np.asarray(dem.error_rates)], 3, 0, B)
         syn = _cabi.GF2Matrix(ct.tanner.H).apply(ep)
-        ms = time_marginal(ct.plan, syn)
+        ms = time_marginal(ct.plan, syn, reps=2 if B < 100 else 5)
+        sch = ct.schedule
         print(json.dumps({"case": f"config4 DEM TNMMAP: {label}", "shots": B, "ms": ms, "syndromes_per_s": B / (ms * 1e-3),
-                          "geometry": ct.plan.geometry(), "w_max": ct.schedule.w_max,
-                          "candidates_per_shot": ct.schedule.cost}), file=out, flush=True)
+                          "geometry": ct.plan.geometry(), "w_max": getattr(sch, "w_max", None) or getattr(sch, "w_cap", None),
+                          "candidates_per_shot": sch.cost, "roofline": roofline(sch, ct.plan.geometry(), ms, B)}),
+              file=out, flush=True)
         if fname.startswith("generated:") and dem.n_detectors <= 24:
             # the same problem fully tabulated (opt-in: 2^24 detector patterns decoded once at compile time)
             t0 = time.perf_counter()

@@ -241,6 +241,14 @@ int tqec_decode_marginal(tqec_plan *plan, const uint64_t *synd, int64_t n_shots,
 int tqec_decode_marginal_dev(tqec_plan *plan, const uint64_t *d_synd, int64_t n_shots, double *d_mar,
                              int32_t *d_argmax, void *stream);
 
+/* The same two calls with ONE BYTE PER BIT in host memory, the layout of the reference's own containers (Mod2 wraps
+ * Bool, src/codes/mod2.jl:20-41; a batch `Matrix{Mod2}` holds one shot per column = n_bits contiguous bytes per shot):
+ * synd_bits = B * n_checks bytes, corr_bits = B * n_vars bytes.  The bytes cross PCIe as they are and are packed /
+ * unpacked on the device next to the decode kernel (host-side packing of 1e7 shots costs more than decoding them). */
+int tqec_decode_map_bytes(tqec_plan *plan, const uint8_t *synd_bits, int64_t n_shots, uint8_t *corr_bits, double *logp_out);
+int tqec_decode_marginal_bytes(tqec_plan *plan, const uint8_t *synd_bits, int64_t n_shots, double *mar_out,
+                               int32_t *argmax_out);
+
 /* ---- GF(2) ------------------------------------------------------------------------------------------------ */
 /* rows x cols matrix, each row packed into ceil(cols/64) words. */
 int tqec_gf2_create(int32_t rows, int32_t cols, const uint64_t *packed_rows, int32_t device, tqec_gf2 **out);

@@ -27,6 +27,7 @@ EXPORTS = [
     "tqec_logical_flags", "tqec_coset_rep", "tqec_sample_errors", "tqec_mc_run", "tqec_fp64_peak",
     "tqec_lower", "tqec_lowered_destroy", "tqec_lowered_get", "tqec_plan_from_lowered", "tqec_plan_compile",
     "tqec_comm_unique_id", "tqec_comm_init", "tqec_comm_destroy", "tqec_comm_allreduce_counts",
+    "tqec_decode_map_bytes", "tqec_decode_marginal_bytes",
 ]
 
 
@@ -116,6 +117,8 @@ def lib():
     L.tqec_lowered_get.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64)]
     L.tqec_plan_from_lowered.argtypes = [vp, i32, C.POINTER(vp)]
     L.tqec_plan_compile.argtypes = [C.POINTER(ProblemDesc), C.POINTER(vp)]
+    L.tqec_decode_map_bytes.argtypes = [vp, vp, i64, vp, vp]
+    L.tqec_decode_marginal_bytes.argtypes = [vp, vp, i64, vp, vp]
     L.tqec_comm_unique_id.argtypes = [vp]
     L.tqec_comm_init.argtypes = [i32, i32, vp, i32, C.POINTER(vp)]
     L.tqec_comm_destroy.argtypes = [vp]
@@ -311,6 +314,23 @@ class Plan:
         logp = np.zeros(B, dtype=np.float64) if want_logp else None
         check(lib().tqec_decode_map(self.h, _ptr(s), B, _ptr(corr), _ptr(logp) if want_logp else None))
         return corr, logp
+
+    def decode_map_bits(self, synd_bits: np.ndarray, n_vars: int):
+        """(B, n_checks) uint8 0/1 -> ((B, n_vars) uint8, logp): one byte per bit both ways, packed on the device."""
+        s = _c(synd_bits, np.uint8)
+        B = s.shape[0]
+        corr = np.empty((B, n_vars), dtype=np.uint8)
+        logp = np.empty(B, dtype=np.float64)
+        check(lib().tqec_decode_map_bytes(self.h, _ptr(s), B, _ptr(corr), _ptr(logp)))
+        return corr, logp
+
+    def decode_marginal_bits(self, synd_bits: np.ndarray):
+        s = _c(synd_bits, np.uint8)
+        B = s.shape[0]
+        mar = np.empty((B, 1 << self.n_obs), dtype=np.float64)
+        arg = np.empty(B, dtype=np.int32)
+        check(lib().tqec_decode_marginal_bytes(self.h, _ptr(s), B, _ptr(mar), _ptr(arg)))
+        return mar, arg
 
     def decode_map_dev(self, d_synd: int, B: int, d_corr: int, d_logp: int = 0, stream: int = 0):
         check(lib().tqec_decode_map_dev(self.h, d_synd, B, d_corr, d_logp or None, stream or None))

@@ -1329,3 +1329,90 @@ extern "C" int tqec_decode_marginal(tqec_plan *p, const uint64_t *synd, int64_t 
   TQEC_CUDA(cudaStreamSynchronize(p->stream));
   return TQEC_OK;
 }
+
+// ---- byte-per-bit entry points: Vector{Mod2} / numpy uint8 in and out, packing done on the device ------------------------
+// The reference's containers hold one byte per bit (Mod2 wraps Bool: src/codes/mod2.jl:20-41; a batch is a Matrix{Mod2}
+// with one shot per column = `n_bits` contiguous bytes per shot).  Packing 1e7 x 80 bits on the host costs more than the
+// decode; here the bytes go over PCIe as they are and two small kernels convert them next to the decode kernel.
+namespace tqec {
+__global__ void k_pack_bits(const uint8_t *__restrict__ bytes, int64_t B, int n_bits, int words, uint64_t *__restrict__ out) {
+  const int64_t n = B * words;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t shot = i / words;
+    const int w = (int)(i - shot * words);
+    const uint8_t *src = bytes + shot * n_bits + 64 * w;
+    const int m = n_bits - 64 * w < 64 ? n_bits - 64 * w : 64;
+    uint64_t v = 0;
+    for (int k = 0; k < m; ++k) v |= (uint64_t)(src[k] & 1u) << k;
+    out[i] = v;
+  }
+}
+__global__ void k_unpack_bits(const uint64_t *__restrict__ wordsv, int64_t B, int n_bits, int words, uint8_t *__restrict__ out) {
+  const int64_t n = B * (int64_t)n_bits;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t shot = i / n_bits;
+    const int b = (int)(i - shot * n_bits);
+    out[i] = (uint8_t)((wordsv[shot * words + (b >> 6)] >> (b & 63)) & 1ull);
+  }
+}
+static int grid_for(int64_t n, int sm) {
+  const int64_t want = (n + 255) / 256;
+  return (int)(want < (int64_t)sm * 16 ? (want > 0 ? want : 1) : (int64_t)sm * 16);
+}
+}  // namespace tqec
+
+// shared body: bytes in -> pack -> decode -> (unpack) -> out, chunked on the plan's stream
+static int decode_bytes(tqec_plan *p, const uint8_t *synd_bits, int64_t B, uint8_t *corr_bits, double *out, int32_t *argmax_out) {
+  const bool mp = p->semiring == TQEC_SEMIRING_MAXPLUS;
+  const int nc = p->dev.n_checks, nv = p->dev.n_vars, nsw = p->dev.nsw, ncw = p->dev.ncw;
+  const int64_t NO = mp ? 1 : ((int64_t)1 << p->dev.n_obs);
+  const int64_t CH = (int64_t)1 << 20;
+  const int64_t nb = B < CH ? B : CH;
+  int rc;
+  // staging: [0] syndrome bytes, [1] packed syndromes + packed corrections, [2] outputs, [3] correction bytes + argmax
+  if ((rc = ensure_cap(&p->d_io[0], &p->io_cap[0], (size_t)nb * (nc ? nc : 1)))) return rc;
+  if ((rc = ensure_cap(&p->d_io[1], &p->io_cap[1], (size_t)nb * (nsw + ncw) * 8))) return rc;
+  if ((rc = ensure_cap(&p->d_io[2], &p->io_cap[2], (size_t)nb * NO * 8))) return rc;
+  if ((rc = ensure_cap(&p->d_io[3], &p->io_cap[3], (size_t)nb * ((nv ? nv : 1) + 4)))) return rc;
+  uint8_t *d_sb = (uint8_t *)p->d_io[0];
+  uint64_t *d_syn = (uint64_t *)p->d_io[1], *d_cor = d_syn + (size_t)nb * nsw;
+  double *d_out = (double *)p->d_io[2];
+  uint8_t *d_cb = (uint8_t *)p->d_io[3];
+  int32_t *d_arg = (int32_t *)(d_cb + (((size_t)nb * (nv ? nv : 1) + 3) & ~(size_t)3));
+  cudaStream_t st = p->stream;
+  for (int64_t o = 0; o < B; o += nb) {
+    const int64_t n = B - o < nb ? B - o : nb;
+    TQEC_CUDA(cudaMemcpyAsync(d_sb, synd_bits + (size_t)o * nc, (size_t)n * nc, cudaMemcpyHostToDevice, st));
+    k_pack_bits<<<grid_for(n * nsw, p->sm_count), 256, 0, st>>>(d_sb, n, nc, nsw, d_syn);
+    TQEC_CUDA(cudaGetLastError());
+    if ((rc = launch_decode(p, d_syn, n, mp ? d_cor : nullptr, d_out, mp ? nullptr : d_arg, st))) return rc;
+    if (mp) {
+      k_unpack_bits<<<grid_for(n * nv, p->sm_count), 256, 0, st>>>(d_cor, n, nv, ncw, d_cb);
+      TQEC_CUDA(cudaGetLastError());
+      TQEC_CUDA(cudaMemcpyAsync(corr_bits + (size_t)o * nv, d_cb, (size_t)n * nv, cudaMemcpyDeviceToHost, st));
+      if (out) TQEC_CUDA(cudaMemcpyAsync(out + o, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    } else {
+      TQEC_CUDA(cudaMemcpyAsync(out + o * NO, d_out, (size_t)n * NO * 8, cudaMemcpyDeviceToHost, st));
+      if (argmax_out) TQEC_CUDA(cudaMemcpyAsync(argmax_out + o, d_arg, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    }
+    p->launches += mp ? 2 : 1;
+  }
+  TQEC_CUDA(cudaStreamSynchronize(st));
+  return TQEC_OK;
+}
+
+extern "C" int tqec_decode_map_bytes(tqec_plan *p, const uint8_t *synd_bits, int64_t B, uint8_t *corr_bits, double *logp_out) {
+  TQEC_REQUIRE(p && p->semiring == TQEC_SEMIRING_MAXPLUS, "tqec_decode_map_bytes: plan is not a max-plus (TNMAP) plan");
+  TQEC_REQUIRE(B >= 0 && (B == 0 || (synd_bits && corr_bits)), "tqec_decode_map_bytes: NULL buffer");
+  if (B == 0) return TQEC_OK;
+  TQEC_CUDA(cudaSetDevice(p->device));
+  return decode_bytes(p, synd_bits, B, corr_bits, logp_out, nullptr);
+}
+
+extern "C" int tqec_decode_marginal_bytes(tqec_plan *p, const uint8_t *synd_bits, int64_t B, double *mar_out, int32_t *argmax_out) {
+  TQEC_REQUIRE(p && p->semiring == TQEC_SEMIRING_SUMPROD, "tqec_decode_marginal_bytes: plan is not a sum-product (TNMMAP) plan");
+  TQEC_REQUIRE(B >= 0 && (B == 0 || (synd_bits && mar_out)), "tqec_decode_marginal_bytes: NULL buffer");
+  if (B == 0) return TQEC_OK;
+  TQEC_CUDA(cudaSetDevice(p->device));
+  return decode_bytes(p, synd_bits, B, nullptr, mar_out, argmax_out);
+}

@@ -302,8 +302,7 @@ def _syndrome_bits(s, n) -> np.ndarray:
 def _decode_tnmap(ct: CompiledTNMAP, syndrome: SimpleSyndrome) -> DecodingResult:
     single = as_bits(syndrome.s).ndim == 1
     bits = _syndrome_bits(syndrome.s, ct.n_checks)
-    corr, logp = ct.plan.decode_map(pack_bits(bits))
-    cfg = unpack_bits(corr, ct.qubit_num)
+    cfg, logp = ct.plan.decode_map_bits(bits, ct.qubit_num)     # one byte per bit both ways; packed on the device
     ok = np.isfinite(logp)
     if single:
         return DecodingResult(bool(ok[0]), cfg[0], logp=logp[0])
