@@ -13,8 +13,8 @@ from .decoding import (TNMAP, TNMMAP, AbstractDecoder, AbstractGeneralDecoder, C
                        IndependentDepolarizingDecodingProblem, NoOptimizer, SimpleTensorNetwork, compile, decode,
                        extract_decoding, get_problem, reduce2general, single_qubit_tensor, tnmap_schedule,
                        tnmmap_css_schedule, tnmmap_dem_schedule)
-from .circuit import (StimCircuit, dem_to_string, detector_error_model, parse_stim_file, parse_stim_string,
-                      surface_memory_circuit)
+from .circuit import (StimCircuit, circuit_to_string, dem_to_string, detector_error_model, dump_stim_file, parse_stim_file,
+                      parse_stim_string, surface_memory_circuit)
 from .dem import DetectorErrorModel, dem2tanner, parse_dem_file, parse_dem_string
 from .error_model import (CSSErrorPattern, CSSSyndrome, IndependentDepolarizingError, IndependentFlipError,
                           SimpleSyndrome, check_logical_error, iid_error, random_error_pattern, syndrome_extraction)

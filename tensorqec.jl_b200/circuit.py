@@ -38,6 +38,7 @@ _MEASURE = {"M": "Z", "MZ": "Z", "MX": "X", "MY": "Y", "MR": "Z", "MRZ": "Z", "M
 _RESET = {"R", "RZ", "RX", "RY"}
 _NOISE = {"X_ERROR", "Y_ERROR", "Z_ERROR", "DEPOLARIZE1", "DEPOLARIZE2"}
 _ANNOT = {"TICK", "QUBIT_COORDS", "SHIFT_COORDS"}
+_FEEDBACK = {"CX": "X", "CNOT": "X", "ZCX": "X", "CZ": "Z", "ZCZ": "Z", "CY": "Y", "ZCY": "Y"}
 
 
 @dataclass
@@ -128,8 +129,23 @@ def parse_stim_string(content: str, n_qubits: Optional[int] = None) -> StimCircu
             continue
         if name not in _GATES_1Q | _GATES_2Q | set(_MEASURE) | _RESET | _NOISE:
             raise ValueError(f"Unknown instruction: {name}")
+        if name in _FEEDBACK and any(t.startswith("rec[") for t in toks):
+            # classically controlled Pauli (stim_parser.jl:236-263: `condition(measure, X | Z, nothing)`): pairs of
+            # (rec[-k], qubit); stored with the ABSOLUTE record index as first target
+            if len(toks) % 2:
+                raise ValueError(f"{name} needs pairs of targets")
+            for a, b in zip(toks[0::2], toks[1::2]):
+                mm = re.match(r"^rec\[(-\d+)\]$", a)
+                if not mm or not re.match(r"^\d+$", b):
+                    raise ValueError(f"{name}: unsupported target pair {a!r} {b!r}")
+                k = circ.n_measurements + int(mm.group(1))
+                if k < 0:
+                    raise ValueError(f"{name}: {a} looks back before the first measurement")
+                circ.instructions.append(Instruction("FEEDBACK_" + _FEEDBACK[name], (), (k, int(b))))
+                max_q = max(max_q, int(b))
+            continue
         if any(not re.match(r"^!?\d+$", t) for t in toks):
-            raise ValueError(f"{name}: unsupported target in {ln!r} (classically controlled gates are not supported)")
+            raise ValueError(f"{name}: unsupported target in {ln!r}")
         qs = tuple(int(t.lstrip("!")) for t in toks)
         if name in _GATES_2Q | {"DEPOLARIZE2"} and len(qs) % 2:
             raise ValueError(f"{name} needs pairs of qubits")
@@ -185,6 +201,13 @@ def detector_error_model(circ: StimCircuit) -> DetectorErrorModel:
             bit = 1 << (n_det + int(ins.args[0]))
             for k in t:
                 rec[k] = rec.get(k, 0) ^ bit
+        elif nm.startswith("FEEDBACK_"):
+            # a Pauli applied iff an earlier measurement read 1: a flipped record applies it wrongly, so the record
+            # inherits what that Pauli would flip from here on
+            k, q = t
+            pa = nm[-1]
+            eff = (sx[q] if pa in "XY" else 0) ^ (sz[q] if pa in "ZY" else 0)
+            rec[k] = rec.get(k, 0) ^ eff
         elif nm in _MEASURE:
             m_idx -= 1
             q, r = t[0], rec.get(m_idx, 0)
@@ -286,6 +309,35 @@ def dem_to_string(dem: DetectorErrorModel) -> str:
         toks = [f"D{d}" if d < n_det else f"L{d - n_det}" for d in fl]
         out.append(f"error({p!r}) " + " ".join(toks))
     return "\n".join(out) + "\n"
+
+
+def circuit_to_string(circ: StimCircuit) -> str:
+    """Stim text of a parsed circuit (REPEAT blocks stay flattened; `rec[-k]` look-backs are recomputed from the absolute
+    record indices).  `parse_stim_string(circuit_to_string(c))` reproduces `c` instruction for instruction."""
+    out: List[str] = []
+    n_meas = 0
+    for ins in circ.instructions:
+        nm = ins.name
+        if nm in ("DETECTOR", "OBSERVABLE_INCLUDE"):
+            recs = " ".join(f"rec[{k - n_meas}]" for k in ins.targets)
+            head = "DETECTOR" if nm == "DETECTOR" else f"OBSERVABLE_INCLUDE({int(ins.args[0])})"
+            out.append((head + " " + recs).rstrip())
+        elif nm.startswith("FEEDBACK_"):
+            k, q = ins.targets
+            out.append(f"C{nm[-1]} rec[{k - n_meas}] {q}")
+        else:
+            arg = "(" + ", ".join(repr(a) for a in ins.args) + ")" if ins.args else ""
+            out.append((nm + arg + " " + " ".join(str(q) for q in ins.targets)).rstrip())
+            if nm in _MEASURE:
+                n_meas += len(ins.targets)
+    return "\n".join(out) + "\n"
+
+
+def dump_stim_file(circ: StimCircuit, filename: str) -> None:
+    """stim_parser.jl:378-437 (`dump_stim_file`), for this package's circuit container: every instruction the parser
+    reads is written back (the reference writes H / X / Y / Z / M / CX / DETECTOR / OBSERVABLE_INCLUDE only)."""
+    with open(filename, "w") as fh:
+        fh.write(circuit_to_string(circ))
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -134,3 +134,39 @@ def test_generated_dem_lowers_to_a_tnmmap_schedule(tq):
     # the coset-representative matrix solves H e = s for every detector pattern the mechanisms can produce
     H = tanner.H
     assert np.array_equal((H @ R) % 2 @ H % 2, H % 2)
+
+
+@pytest.mark.parametrize("name,nq,n_meas,n_det", [("teleportation", 100, 2, 0), ("repetition", 7, 3007, 3006),
+                                                   ("noisy_repetition", 7, 3004, 3003), ("noisy_surface", 26, 8009, 8000)])
+def test_reference_stim_fixtures_parse_and_round_trip(tq, golden_dir, tmp_path, name, nq, n_meas, n_det):
+    """The circuits of test/stim_parser/stim_parser.jl:52-75 (stim's own documentation examples): REPEAT blocks of 1000
+    rounds flattened, `rec[-k]` look-back, classically controlled Paulis (teleportation); `dump_stim_file`
+    (stim_parser.jl:378-437) writes a file that parses back to the same instruction list."""
+    circ = tq.parse_stim_file(str(golden_dir / "stim" / f"{name}.stim"), nq)
+    assert (circ.n_qubits, circ.n_measurements, circ.n_detectors) == (nq, n_meas, n_det)
+    out = tmp_path / "dump.stim"
+    tq.dump_stim_file(circ, str(out))
+    back = tq.parse_stim_file(str(out), nq)
+    assert back.instructions == circ.instructions and back.n_observables == circ.n_observables
+
+
+def test_feedback_pauli_enters_the_error_model(tq):
+    """A measurement whose outcome steers a later Pauli: flipping the record applies the Pauli wrongly, so the record
+    flip inherits the detectors that Pauli flips.  Here M(0.1) on qubit 0 controls an X on qubit 1, which is then
+    measured and compared with a detector: the mechanism {D0} has probability 0.1."""
+    circ = tq.parse_stim_string("R 0 1\nM(0.1) 0\nCX rec[-1] 1\nM 1\nDETECTOR rec[-1]\n")
+    dem = tq.detector_error_model(circ)
+    assert dem.flipped_detectors == [[0]] and abs(dem.error_rates[0] - 0.1) < 1e-15
+    # without the feedback the measurement error is invisible
+    dem0 = tq.detector_error_model(tq.parse_stim_string("R 0 1\nM(0.1) 0\nM 1\nDETECTOR rec[-1]\n"))
+    assert dem0.flipped_detectors == []
+
+
+def test_noisy_repetition_fixture_gives_a_chain_dem(tq, golden_dir):
+    """stim's noisy repetition-code example (1000 rounds): every mechanism of its detector error model flips at most two
+    detectors (a matching graph), and the observable is touched."""
+    circ = tq.parse_stim_file(str(golden_dir / "stim" / "noisy_repetition.stim"), 7)
+    dem = tq.detector_error_model(circ)
+    assert dem.n_detectors == 3003 and dem.n_observables == 1
+    assert max(sum(1 for d in f if d < 3003) for f in dem.flipped_detectors) <= 2
+    assert any(3003 in f for f in dem.flipped_detectors)
