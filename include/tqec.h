@@ -145,10 +145,17 @@ typedef struct {
   int32_t table_bits;      /* plans with n_checks <= table_bits are fully tabulated at creation (0 = default 16,
                               -1 = never, at most 26; table = 2^n_checks x (configuration words + outputs)) */
   const tqec_wide_desc *wide; /* optional (NULL): global-memory lowering; takes precedence over hdr / sweep */
+  int32_t flags;           /* TQEC_PLAN_*                                                                    */
   int32_t log2_scale;      /* sum-product: the factor tables were pre-multiplied by powers of two against under- and
                               overflow and their exponents sum to -log2_scale; the library multiplies every marginal
                               it returns (host and *_dev entry points alike) by 2^log2_scale */
 } tqec_plan_desc;
+
+#define TQEC_PLAN_DYNAMIC_RESCALE 1 /* global-memory executor: per-shot dynamic rescaling.  After every pass the largest
+                                      state entry of each shot is known; when it has fallen below 2^-300 the next pass
+                                      multiplies the shot's state by a power of two (exact) and an int32 exponent per shot
+                                      absorbs it, so neither the marginals' ratio nor the argmax is lost to underflow
+                                      however unlikely the syndrome.  The static scaling (log2_scale) stays in place. */
 
 const char *tqec_last_error(void);
 int tqec_version(void);
@@ -203,6 +210,8 @@ typedef struct {
 #define TQEC_COMPILE_NO_SWEEP 1   /* never use the in-place patch sweep                                        */
 #define TQEC_COMPILE_NO_FUSE 2    /* general max-plus kernels: one factor per step                             */
 #define TQEC_COMPILE_FORCE_WIDE 4 /* sum-product: global-memory executor even if the frontier fits on chip     */
+#define TQEC_COMPILE_DYNAMIC_RESCALE 8 /* sum-product: global-memory executor with per-shot dynamic rescaling
+                                     (TQEC_PLAN_DYNAMIC_RESCALE); implies FORCE_WIDE                           */
 
 typedef struct tqec_lowered tqec_lowered; /* host-side result of the lowering (no device memory)               */
 int tqec_lower(const tqec_problem_desc *prob, tqec_lowered **out);
@@ -241,6 +250,10 @@ int tqec_decode_marginal(tqec_plan *plan, const uint64_t *synd, int64_t n_shots,
 int tqec_decode_marginal_dev(tqec_plan *plan, const uint64_t *d_synd, int64_t n_shots, double *d_mar,
                              int32_t *d_argmax, void *stream);
 
+/* TNMMAP with the exponents kept apart: true marginal = mar_out[b][i] * 2^log2_out[b].  For plans compiled with dynamic
+ * rescaling the entries of mar_out stay in the FP64 range even when the syndrome's probability does not. */
+int tqec_decode_marginal_log2(tqec_plan *plan, const uint64_t *synd, int64_t n_shots, double *mar_out, int32_t *log2_out,
+                              int32_t *argmax_out);
 /* The same two calls with ONE BYTE PER BIT in host memory, the layout of the reference's own containers (Mod2 wraps
  * Bool, src/codes/mod2.jl:20-41; a batch `Matrix{Mod2}` holds one shot per column = n_bits contiguous bytes per shot):
  * synd_bits = B * n_checks bytes, corr_bits = B * n_vars bytes.  The bytes cross PCIe as they are and are packed /
@@ -314,6 +327,9 @@ int tqec_comm_allreduce_counts(tqec_comm *comm, int64_t counts[4]);
  * TFLOP/s (2 flops each), and the max-plus candidate rate counted as 2 ops (add + compare) in Tops/s.  Roofline
  * denominator of the decode kernels (MEASURED_PEAKS.json has no FP64 entry). */
 int tqec_fp64_peak(int32_t device, double *dadd_tops, double *dfma_tflops, double *maxplus_tops);
+/* FP64 tensor-core rate (mma.sync m8n8k4 f64 = DMMA.8x8x4, 512 flops per warp instruction), TFLOP/s: measured beside the
+ * DFMA rate to decide whether any sum-product step should run as a dense product (none does). */
+int tqec_dmma_peak(int32_t device, double *dmma_tflops);
 
 #ifdef __cplusplus
 }

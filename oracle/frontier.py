@@ -39,7 +39,7 @@ def priority_of(sch):
     return out
 
 
-def run(factors, checks, order, semiring, syndromes, n_vars, want_config=True, priority=None):
+def run(factors, checks, order, semiring, syndromes, n_vars, want_config=True, priority=None, rescale=False):
     """factors[i].vars/.table (flat, first variable fastest), checks[c].vars/.kind/.index.
     syndromes: (B, n_syn) 0/1.  Max-plus -> (logp (B,), config (B, n_vars) uint8);  sum-product -> marginal
     (B, 2^n_obs) with sector index = sum_i obs_i << i."""
@@ -52,6 +52,7 @@ def run(factors, checks, order, semiring, syndromes, n_vars, want_config=True, p
     remaining = [len(x) for x in c_factors]
     axes = []                                                    # check ids, axis k+1 of S <-> axes[k]
     S = np.full((B,), 0.0 if maxplus else 1.0)
+    exps = np.zeros(B, dtype=np.int64)
     trace = []
     orphan = [ci for ci, fs in enumerate(c_factors) if not fs]
     for t, fi in enumerate(order):
@@ -84,6 +85,12 @@ def run(factors, checks, order, semiring, syndromes, n_vars, want_config=True, p
             else:
                 best = best + cand
         S = best
+        if rescale and not maxplus:
+            # dynamic rescaling, per shot: pull the largest entry back to [1, 2) and book the exponent
+            mx = S.reshape(B, -1).max(axis=1)
+            e = np.where(mx > 0, np.floor(np.log2(np.where(mx > 0, mx, 1.0))), 0).astype(np.int64)
+            S = np.ldexp(S, (-e).reshape([B] + [1] * (S.ndim - 1)).astype(np.int32))
+            exps = exps + e
         closing = []
         for c in touched + (orphan if t == 0 else []):
             if c in orphan:
@@ -109,7 +116,8 @@ def run(factors, checks, order, semiring, syndromes, n_vars, want_config=True, p
         # remaining axes are observables; order them by observable index, first observable fastest
         obs_order = sorted(range(len(axes)), key=lambda k: checks[axes[k]].index)
         S = np.transpose(S, [0] + [k + 1 for k in obs_order])
-        return S.reshape(B, -1, order="F") if S.ndim > 1 else S.reshape(B, 1)
+        S = S.reshape(B, -1, order="F") if S.ndim > 1 else S.reshape(B, 1)
+        return (S, exps) if rescale else S
     assert S.ndim == 1
     logp = S
     if not want_config:

@@ -27,7 +27,7 @@ EXPORTS = [
     "tqec_logical_flags", "tqec_coset_rep", "tqec_sample_errors", "tqec_mc_run", "tqec_fp64_peak",
     "tqec_lower", "tqec_lowered_destroy", "tqec_lowered_get", "tqec_plan_from_lowered", "tqec_plan_compile",
     "tqec_comm_unique_id", "tqec_comm_init", "tqec_comm_destroy", "tqec_comm_allreduce_counts",
-    "tqec_decode_map_bytes", "tqec_decode_marginal_bytes",
+    "tqec_decode_map_bytes", "tqec_decode_marginal_bytes", "tqec_dmma_peak", "tqec_decode_marginal_log2",
 ]
 
 
@@ -55,7 +55,7 @@ class PlanDesc(C.Structure):
                 ("hdr", C.POINTER(C.c_int32)), ("ints", C.POINTER(C.c_int32)), ("n_ints", C.c_int64),
                 ("tables", C.POINTER(C.c_double)), ("n_tables", C.c_int64),
                 ("obs_slot", C.POINTER(C.c_int32)), ("device", C.c_int32), ("sweep", C.POINTER(SweepDesc)),
-                ("table_bits", C.c_int32), ("wide", C.POINTER(WideDesc)), ("log2_scale", C.c_int32)]
+                ("table_bits", C.c_int32), ("wide", C.POINTER(WideDesc)), ("flags", C.c_int32), ("log2_scale", C.c_int32)]
 
 
 class ProblemDesc(C.Structure):
@@ -66,7 +66,8 @@ class ProblemDesc(C.Structure):
                 ("table_bits", C.c_int32), ("device", C.c_int32), ("flags", C.c_int32), ("wide_t_max", C.c_int32)]
 
 
-COMPILE_NO_SWEEP, COMPILE_NO_FUSE, COMPILE_FORCE_WIDE = 1, 2, 4
+COMPILE_NO_SWEEP, COMPILE_NO_FUSE, COMPILE_FORCE_WIDE, COMPILE_DYNAMIC_RESCALE = 1, 2, 4, 8
+PLAN_DYNAMIC_RESCALE = 1
 (LW_META, LW_COST, LW_ORDER, LW_HDR, LW_INTS, LW_TABLES, LW_OBS_SLOT, LW_SW_REC, LW_SW_TB, LW_SW_LANETAB, LW_SW_TVALS,
  LW_SW_HEAD_BITS, LW_SW_HEAD_STATE, LW_SW_HEAD_CFG, LW_SW_OUT_INDEX, LW_WD_PASS_HDR, LW_WD_STEP_HDR, LW_WD_INTS,
  LW_WD_TABLES, LW_WD_OBS_POS) = range(20)
@@ -117,6 +118,7 @@ def lib():
     L.tqec_lowered_get.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64)]
     L.tqec_plan_from_lowered.argtypes = [vp, i32, C.POINTER(vp)]
     L.tqec_plan_compile.argtypes = [C.POINTER(ProblemDesc), C.POINTER(vp)]
+    L.tqec_decode_marginal_log2.argtypes = [vp, vp, i64, vp, vp, vp]
     L.tqec_decode_map_bytes.argtypes = [vp, vp, i64, vp, vp]
     L.tqec_decode_marginal_bytes.argtypes = [vp, vp, i64, vp, vp]
     L.tqec_comm_unique_id.argtypes = [vp]
@@ -153,7 +155,10 @@ def fp64_peak(device: int = 0):
     require_device(device)
     a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)
     check(lib().tqec_fp64_peak(device, C.byref(a), C.byref(b), C.byref(c)))
-    return {"dadd_tops": a.value, "dfma_tflops": b.value, "maxplus_tops": c.value}
+    d = C.c_double(0)
+    lib().tqec_dmma_peak.argtypes = [C.c_int32, C.POINTER(C.c_double)]
+    check(lib().tqec_dmma_peak(device, C.byref(d)))
+    return {"dadd_tops": a.value, "dfma_tflops": b.value, "maxplus_tops": c.value, "dmma_tflops": d.value}
 
 
 def _ptr(a: np.ndarray):
@@ -269,7 +274,7 @@ class Plan:
             wd = WideDesc(len(sch.passes), keep[1].shape[0], sch.w_cap, sch.t_max, _ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]),
                           keep[2].size, _ptr(keep[3]), keep[3].size, _ptr(keep[4]))
             d = PlanDesc(sch.semiring, sch.n_vars, sch.n_checks, sch.n_obs, 0, sch.w_cap, None, None, 0, None, 0, None,
-                         device, None, table_bits, C.pointer(wd), int(sch.log2_scale))
+                         device, None, table_bits, C.pointer(wd), int(getattr(sch, "plan_flags", 0)), int(sch.log2_scale))
             h = C.c_void_p()
             check(lib().tqec_plan_create(C.byref(d), C.byref(h)))
             self.h = h
@@ -281,7 +286,7 @@ class Plan:
         d = PlanDesc(sch.semiring, sch.n_vars, sch.n_checks, sch.n_obs, len(sch.steps), sch.w_max,
                      hdr.ctypes.data_as(C.POINTER(C.c_int32)), ints.ctypes.data_as(C.POINTER(C.c_int32)), ints.size,
                      tabs.ctypes.data_as(C.POINTER(C.c_double)), tabs.size,
-                     obs.ctypes.data_as(C.POINTER(C.c_int32)), device, None, table_bits, None,
+                     obs.ctypes.data_as(C.POINTER(C.c_int32)), device, None, table_bits, None, 0,
                      int(getattr(sch, "log2_scale", 0) or 0))
         sw = getattr(sch, "sweep", None)
         if sw is not None:
@@ -342,6 +347,16 @@ class Plan:
         arg = np.zeros(B, dtype=np.int32)
         check(lib().tqec_decode_marginal(self.h, _ptr(s), B, _ptr(mar), _ptr(arg)))
         return mar, arg                                    # (the library has undone the static scaling of the tables)
+
+    def decode_marginal_log2(self, synd_words: np.ndarray):
+        """-> (mantissas (B, 2^n_obs), log2 (B,), argmax): true marginal = mantissa * 2^log2 (tqec_decode_marginal_log2)."""
+        s = _c(synd_words, np.uint64).reshape(-1, self.nsw)
+        B = s.shape[0]
+        mar = np.zeros((B, 1 << self.n_obs), dtype=np.float64)
+        lg = np.zeros(B, dtype=np.int32)
+        arg = np.zeros(B, dtype=np.int32)
+        check(lib().tqec_decode_marginal_log2(self.h, _ptr(s), B, _ptr(mar), _ptr(lg), _ptr(arg)))
+        return mar, lg, arg
 
     def decode_marginal_dev(self, d_synd: int, B: int, d_mar: int, d_argmax: int = 0, stream: int = 0):
         check(lib().tqec_decode_marginal_dev(self.h, d_synd, B, d_mar, d_argmax or None, stream or None))

@@ -108,6 +108,9 @@ struct tqec_plan {
   int has_wide, wd_smem, wd_grid;
   void *d_wd[4];
   double *d_wd_state[2];
+  unsigned long long *d_wd_max;   // dynamic rescaling: per-shot maxima of the last two passes
+  int32_t *d_wd_exp;              // ... and per-shot accumulated exponents
+  int wd_dynamic;
   int64_t wd_batch;
   int wd_full;            // the state arrays already take all the memory the executor may use
   void *d_hdr, *d_ints, *d_tables, *d_bp_off, *d_obs_slot;
@@ -143,7 +146,8 @@ void sweep_destroy(tqec_plan *p);
 int wide_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &prop);
 void wide_destroy(tqec_plan *p);
 int comm_allreduce_dev(tqec_comm *c, unsigned long long *d_counts, cudaStream_t stream);
-int launch_wide(tqec_plan *plan, const uint64_t *d_synd, int64_t B, double *d_out, int32_t *d_argmax, cudaStream_t stream);
+int launch_wide(tqec_plan *plan, const uint64_t *d_synd, int64_t B, double *d_out, int32_t *d_argmax, cudaStream_t stream,
+                int32_t *d_log2 = nullptr);
 int launch_gf2_apply(tqec_gf2 *m, const uint64_t *d_in, int64_t B, uint64_t *d_out, cudaStream_t stream);
 int launch_sample(int model, int n_sites, const double *d_p, uint64_t seed, int64_t shot_offset, int64_t B,
                   uint64_t *d_err, int words, cudaStream_t stream);

@@ -16,7 +16,7 @@ using namespace tqec::lower;
 
 struct tqec_lowered {
   int kind = 0;            // 0 schedule, 1 schedule + sweep, 2 wide
-  int semiring = 0, n_vars = 0, n_checks = 0, n_obs = 0, table_bits = 0;
+  int semiring = 0, n_vars = 0, n_checks = 0, n_obs = 0, table_bits = 0, plan_flags = 0;
   Schedule sch;
   SweepPlan sw;
   WidePlan wd;
@@ -111,7 +111,9 @@ static void lower_problem(const tqec_problem_desc *d, tqec_lowered &L) {
   }
   std::vector<int> ord = P.has_order ? map_order(P.factors, merged, P.order) : choose_order(merged, checks);
   const int w_max = evaluate_order(merged, checks, ord).first;
-  const bool force_wide = (d->flags & TQEC_COMPILE_FORCE_WIDE) || std::getenv("TQEC_FORCE_WIDE");
+  const bool dynamic = (d->flags & TQEC_COMPILE_DYNAMIC_RESCALE) != 0;
+  if (dynamic) L.plan_flags |= TQEC_PLAN_DYNAMIC_RESCALE;
+  const bool force_wide = dynamic || (d->flags & TQEC_COMPILE_FORCE_WIDE) || std::getenv("TQEC_FORCE_WIDE");
   if (w_max <= 13 && !force_wide) {
     L.sch = lower_schedule(merged, checks, P.semiring, P.n_vars, P.n_checks, P.n_obs, &ord, 13, 0, false);
     L.kind = 0;
@@ -211,7 +213,7 @@ extern "C" int tqec_plan_from_lowered(const tqec_lowered *L, int32_t device, tqe
   tqec_plan_desc d;
   std::memset(&d, 0, sizeof(d));
   d.semiring = L->semiring; d.n_vars = L->n_vars; d.n_checks = L->n_checks; d.n_obs = L->n_obs;
-  d.device = device; d.table_bits = L->table_bits;
+  d.device = device; d.table_bits = L->table_bits; d.flags = L->plan_flags;
   tqec_sweep_desc sd;
   tqec_wide_desc wd;
   if (L->kind == 2) {

@@ -1416,3 +1416,32 @@ extern "C" int tqec_decode_marginal_bytes(tqec_plan *p, const uint8_t *synd_bits
   TQEC_CUDA(cudaSetDevice(p->device));
   return decode_bytes(p, synd_bits, B, nullptr, mar_out, argmax_out);
 }
+
+// TNMMAP with the exponents kept apart (see include/tqec.h): the marginals are returned as mantissas, the per-shot
+// power of two (dynamic exponent + the plan's static log2_scale) in log2_out.
+extern "C" int tqec_decode_marginal_log2(tqec_plan *p, const uint64_t *synd, int64_t B, double *mar_out, int32_t *log2_out,
+                                         int32_t *argmax_out) {
+  TQEC_REQUIRE(p && p->semiring == TQEC_SEMIRING_SUMPROD, "tqec_decode_marginal_log2: plan is not a sum-product (TNMMAP) plan");
+  TQEC_REQUIRE(B >= 0 && (B == 0 || (synd && mar_out && log2_out)), "tqec_decode_marginal_log2: NULL buffer");
+  if (B == 0) return TQEC_OK;
+  if (!(p->has_wide && p->wd_dynamic) || p->has_table) {
+    const int rc = tqec_decode_marginal(p, synd, B, mar_out, argmax_out);
+    for (int64_t b = 0; b < B; ++b) log2_out[b] = 0;
+    return rc;
+  }
+  TQEC_CUDA(cudaSetDevice(p->device));
+  const int64_t NO = (int64_t)1 << p->dev.n_obs;
+  int rc;
+  if ((rc = ensure_cap(&p->d_io[0], &p->io_cap[0], (size_t)B * p->dev.nsw * 8))) return rc;
+  if ((rc = ensure_cap(&p->d_io[1], &p->io_cap[1], (size_t)B * NO * 8))) return rc;
+  if ((rc = ensure_cap(&p->d_io[2], &p->io_cap[2], (size_t)B * 4))) return rc;
+  if ((rc = ensure_cap(&p->d_io[3], &p->io_cap[3], (size_t)B * 4))) return rc;
+  TQEC_CUDA(cudaMemcpyAsync(p->d_io[0], synd, (size_t)B * p->dev.nsw * 8, cudaMemcpyHostToDevice, p->stream));
+  if ((rc = launch_wide(p, (const uint64_t *)p->d_io[0], B, (double *)p->d_io[1], (int32_t *)p->d_io[2], p->stream, (int32_t *)p->d_io[3]))) return rc;
+  TQEC_CUDA(cudaMemcpyAsync(mar_out, p->d_io[1], (size_t)B * NO * 8, cudaMemcpyDeviceToHost, p->stream));
+  TQEC_CUDA(cudaMemcpyAsync(log2_out, p->d_io[3], (size_t)B * 4, cudaMemcpyDeviceToHost, p->stream));
+  if (argmax_out) TQEC_CUDA(cudaMemcpyAsync(argmax_out, p->d_io[2], (size_t)B * 4, cudaMemcpyDeviceToHost, p->stream));
+  TQEC_CUDA(cudaStreamSynchronize(p->stream));
+  for (int64_t b = 0; b < B; ++b) log2_out[b] += p->log2_scale;
+  return TQEC_OK;
+}

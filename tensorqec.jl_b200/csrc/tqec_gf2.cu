@@ -539,3 +539,57 @@ extern "C" int tqec_fp64_peak(int32_t device, double *dadd_tops, double *dfma_tf
   cudaFree(d_out);
   return TQEC_OK;
 }
+
+// ---- FP64 tensor-core (DMMA) rate: the other possible roof of the sum-product steps ---------------------------------------
+// mma.sync.aligned.m8n8k4.row.col.f64 (SASS DMMA.8x8x4): 512 flops per warp instruction, four independent accumulator
+// chains per warp, register resident.  Used by DESIGN.md to settle whether any step of the frontier schedule should
+// run as a dense product on the tensor cores (north_star: "FP64 DMMA ... only on steps that are dense GEMMs of useful
+// size"); there is no tcgen05 FP64 path on sm_100a.
+__global__ void k_dmma_peak(double *out, int iters, double seed) {
+  double a = seed + threadIdx.x * 1e-9, b = 1.0000001;
+  double c[4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { c[i][0] = seed * i; c[i][1] = seed + i; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                   : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s += c[i][0] + c[i][1];
+  if (s == 12345.678) out[0] = s;
+}
+
+extern "C" int tqec_dmma_peak(int32_t device, double *dmma_tflops) {
+  TQEC_REQUIRE(dmma_tflops, "tqec_dmma_peak: NULL output");
+  int ndev = 0;
+  TQEC_CUDA(cudaGetDeviceCount(&ndev));
+  TQEC_REQUIRE(device >= 0 && device < ndev, "tqec_dmma_peak: device %d not present (%d visible)", device, ndev);
+  TQEC_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  TQEC_CUDA(cudaGetDeviceProperties(&prop, device));
+  double *d_out = nullptr;
+  TQEC_CUDA(cudaMalloc((void **)&d_out, 64));
+  cudaEvent_t e0, e1;
+  TQEC_CUDA(cudaEventCreate(&e0));
+  TQEC_CUDA(cudaEventCreate(&e1));
+  const int threads = 512, blocks = prop.multiProcessorCount * 4, iters = 1 << 13;
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    TQEC_CUDA(cudaEventRecord(e0, 0));
+    k_dmma_peak<<<blocks, threads>>>(d_out, iters, 1.0);
+    TQEC_CUDA(cudaEventRecord(e1, 0));
+    TQEC_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    TQEC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  const double flops = (double)blocks * (threads / 32) * iters * 4.0 * 512.0;
+  *dmma_tflops = flops / (best * 1e-3) / 1e12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  return TQEC_OK;
+}

@@ -26,6 +26,11 @@ struct WidePassArgs {
   const int32_t *step_hdr, *ints;
   const double *tables;
   int32_t nsw, w_cap, t_max;
+  // dynamic per-shot rescaling (optional): largest state entry of every shot after the previous pass (bit pattern of a
+  // non-negative double), the same for this pass (filled with atomicMax), and the shots' accumulated exponents
+  const unsigned long long *max_in;
+  unsigned long long *max_out;
+  int32_t *exps;
 };
 
 // deposit the low bits of x at the set bits of mask (software pdep; mask has at most 31 bits)
@@ -131,6 +136,18 @@ __global__ void __launch_bounds__(NT) k_wide_pass(const WidePassArgs A) {
     const uint32_t sp = (uint32_t)(tile & (((int64_t)1 << n_spec) - 1));
     const double *gi = A.gin + ((size_t)b << A.w_cap) + wd_pdep(sp, spec_in);
     double *go = A.gout + ((size_t)b << A.w_cap) + wd_pdep(sp, spec_out);
+    // Dynamic rescaling: when the shot's largest entry has fallen below 2^-300, every tile of the shot multiplies what it
+    // loads by the same power of two (exact) and the shot's exponent absorbs it -- all tiles read the same maximum, so
+    // they take the same decision; tile 0 of the shot books it.
+    double scale = 1.0;
+    if (A.max_in) {
+      const double mx = __longlong_as_double((long long)A.max_in[b]);
+      if (mx > 0.0 && mx < 4.909093465297727e-91) {              // 2^-300
+        const int k = -ilogb(mx);
+        scale = ldexp(1.0, k);
+        if (sp == 0 && tid == 0) A.exps[b] -= k;
+      }
+    }
     if (tid < ns) {
       const int32_t *q = sQ + tid * TQEC_WIDE_STEP_INTS;
       const int32_t *CL = sI + q[TQEC_WL_OFF_CLOSE];
@@ -147,7 +164,7 @@ __global__ void __launch_bounds__(NT) k_wide_pass(const WidePassArgs A) {
       const uint32_t x = i < 64 ? (uint32_t)i : ((uint32_t)(i - 64) << 6);
       sc[i] = wd_pdep(x, (uint32_t)sQ[TQEC_WL_KEEPMASK]);
     }
-    for (int l = tid; l < n_in; l += NT) S0[l] = __ldcs(gi + (dep[l & 63] | dep[64 + (l >> 6)]));
+    for (int l = tid; l < n_in; l += NT) S0[l] = __ldcs(gi + (dep[l & 63] | dep[64 + (l >> 6)])) * scale;
     __syncthreads();
     double *Sin = S0, *Sout = S1;
     for (int s = 0; s < ns; ++s) {
@@ -170,19 +187,32 @@ __global__ void __launch_bounds__(NT) k_wide_pass(const WidePassArgs A) {
       __syncthreads();
       double *tmp = Sin; Sin = Sout; Sout = tmp;
     }
-    for (int l = tid; l < n_out; l += NT) __stcs(go + (dep[128 + (l & 63)] | dep[192 + (l >> 6)]), Sin[l]);
+    double tmax = 0.0;
+    for (int l = tid; l < n_out; l += NT) {
+      const double v = Sin[l];
+      __stcs(go + (dep[128 + (l & 63)] | dep[192 + (l >> 6)]), v);
+      tmax = fmax(tmax, v);
+    }
+    if (A.max_out) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+      if ((tid & 31) == 0 && tmax > 0.0) atomicMax(A.max_out + b, (unsigned long long)__double_as_longlong(tmax));
+    }
     __syncthreads();
   }
 }
 
-__global__ void k_wide_init(double *g, int64_t nb, int w_cap) {
+__global__ void k_wide_init(double *g, int64_t nb, int w_cap, unsigned long long *mx, int32_t *exps) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nb) g[(size_t)i << w_cap] = 1.0;
+  if (i < nb) {
+    g[(size_t)i << w_cap] = 1.0;
+    if (mx) { mx[i] = (unsigned long long)__double_as_longlong(1.0); exps[i] = 0; }
+  }
 }
 
 // marginals over the open observable slots (observable 0 fastest) and their first maximal entry (findmax)
 __global__ void k_wide_out(const WideDev P, const double *__restrict__ g, int64_t nb, double *__restrict__ out,
-                           int32_t *__restrict__ argmax_out) {
+                           int32_t *__restrict__ argmax_out, const int32_t *__restrict__ exps, int32_t *__restrict__ log2_out) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   const int NO = 1 << P.n_obs;
@@ -192,10 +222,13 @@ __global__ void k_wide_out(const WideDev P, const double *__restrict__ g, int64_
     uint32_t src = 0;
     for (int o = 0; o < P.n_obs; ++o) src |= ((uint32_t)(idx >> o) & 1u) << P.obs_pos[o];
     const double v = g[((size_t)b << P.w_cap) + src];
-    out[b * NO + idx] = v;
+    // with a separate exponent output the mantissas are returned as they are; otherwise the exponent is applied here
+    // (values below the FP64 range flush to zero, like the reference's; the argmax is taken on the mantissas)
+    out[b * NO + idx] = (exps && !log2_out) ? ldexp(v, exps[b]) : v;
     if (v > best) { best = v; bi = idx; }
   }
   if (argmax_out) argmax_out[b] = bi;
+  if (log2_out) log2_out[b] = exps ? exps[b] : 0;
 }
 
 static const int WD_THREADS = 256;
@@ -219,6 +252,8 @@ static int wd_upload(void **slot, const T *src, size_t n) {
 void wide_destroy(tqec_plan *p) {
   for (int i = 0; i < 4; ++i) if (p->d_wd[i]) cudaFree(p->d_wd[i]);
   for (int i = 0; i < 2; ++i) if (p->d_wd_state[i]) cudaFree(p->d_wd_state[i]);
+  if (p->d_wd_max) cudaFree(p->d_wd_max);
+  if (p->d_wd_exp) cudaFree(p->d_wd_exp);
 }
 
 // Validate and upload the global-memory lowering of a plan descriptor.
@@ -316,6 +351,7 @@ int wide_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &pro
     }
   }
   p->candidates_per_shot = cand;
+  p->wd_dynamic = (d->flags & TQEC_PLAN_DYNAMIC_RESCALE) ? 1 : 0;
   p->has_wide = 1;
   return TQEC_OK;
 }
@@ -326,6 +362,8 @@ static int wide_reserve(tqec_plan *p, int64_t want) {
   if (p->wd_batch >= want || (p->wd_batch > 0 && p->wd_full)) return TQEC_OK;
   const size_t per_shot = (size_t)16 << p->wd.w_cap;
   for (int i = 0; i < 2; ++i) { if (p->d_wd_state[i]) cudaFree(p->d_wd_state[i]); p->d_wd_state[i] = nullptr; }
+  if (p->d_wd_max) { cudaFree(p->d_wd_max); p->d_wd_max = nullptr; }
+  if (p->d_wd_exp) { cudaFree(p->d_wd_exp); p->d_wd_exp = nullptr; }
   p->wd_batch = 0;
   size_t free_b = 0, total_b = 0;
   TQEC_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -346,18 +384,25 @@ static int wide_reserve(tqec_plan *p, int64_t want) {
       return TQEC_ERR_NOMEM;
     }
   }
+  if (p->wd_dynamic) {
+    TQEC_CUDA(cudaMalloc((void **)&p->d_wd_max, (size_t)nb * 2 * sizeof(unsigned long long)));
+    TQEC_CUDA(cudaMalloc((void **)&p->d_wd_exp, (size_t)nb * sizeof(int32_t)));
+  }
   p->wd_batch = nb;
   return TQEC_OK;
 }
 
-int launch_wide(tqec_plan *plan, const uint64_t *d_synd, int64_t B, double *d_out, int32_t *d_argmax, cudaStream_t stream) {
+int launch_wide(tqec_plan *plan, const uint64_t *d_synd, int64_t B, double *d_out, int32_t *d_argmax, cudaStream_t stream,
+                int32_t *d_log2) {
   int rc = wide_reserve(plan, B);
   if (rc) return rc;
   const WideDev &D = plan->wd;
   const int NO = 1 << D.n_obs;
+  const bool dyn = plan->wd_dynamic != 0;
   for (int64_t o = 0; o < B; o += plan->wd_batch) {
     const int64_t nb = B - o < plan->wd_batch ? B - o : plan->wd_batch;
-    k_wide_init<<<(unsigned)((nb + 255) / 256), 256, 0, stream>>>(plan->d_wd_state[0], nb, D.w_cap);
+    unsigned long long *mx[2] = {dyn ? plan->d_wd_max : nullptr, dyn ? plan->d_wd_max + plan->wd_batch : nullptr};
+    k_wide_init<<<(unsigned)((nb + 255) / 256), 256, 0, stream>>>(plan->d_wd_state[0], nb, D.w_cap, mx[0], plan->d_wd_exp);
     int cur = 0;
     for (int i = 0; i < D.n_pass; ++i) {
       WidePassArgs A;
@@ -365,6 +410,8 @@ int launch_wide(tqec_plan *plan, const uint64_t *d_synd, int64_t B, double *d_ou
       A.synd = d_synd + (size_t)o * D.nsw; A.nb = nb;
       A.pass = D.pass_hdr + (size_t)i * TQEC_WIDE_PASS_INTS; A.step_hdr = D.step_hdr; A.ints = D.ints; A.tables = D.tables;
       A.nsw = D.nsw; A.w_cap = D.w_cap; A.t_max = D.t_max;
+      A.max_in = mx[cur]; A.max_out = mx[cur ^ 1]; A.exps = plan->d_wd_exp;
+      if (dyn) TQEC_CUDA(cudaMemsetAsync(mx[cur ^ 1], 0, (size_t)nb * sizeof(unsigned long long), stream));
       // tiles of the pass: the host copy of the header is not kept, so size the grid for the widest case and let the
       // kernel's tile loop run short
       k_wide_pass<WD_THREADS><<<plan->wd_grid, WD_THREADS, plan->wd_smem, stream>>>(A);
@@ -372,7 +419,8 @@ int launch_wide(tqec_plan *plan, const uint64_t *d_synd, int64_t B, double *d_ou
       plan->launches += 1;
     }
     k_wide_out<<<(unsigned)((nb + 127) / 128), 128, 0, stream>>>(D, plan->d_wd_state[cur], nb, d_out + (size_t)o * NO,
-                                                                 d_argmax ? d_argmax + o : nullptr);
+                                                                 d_argmax ? d_argmax + o : nullptr, dyn ? plan->d_wd_exp : nullptr,
+                                                                 d_log2 ? d_log2 + o : nullptr);
     TQEC_CUDA(cudaGetLastError());
     plan->launches += 2;
   }

@@ -133,6 +133,9 @@ class TNMMAP(AbstractGeneralDecoder):
     factorize: bool = True
     device: int = 0
     table_bits: int = 16         # as for TNMAP: problems with at most this many syndrome / detector bits are tabulated
+    dynamic_rescale: bool = False  # per-shot dynamic rescaling (int32 exponent per shot) against FP64 underflow on extremely
+                                 # unlikely syndromes; runs the plan on the global-memory executor (slower; tables are static-
+                                 # ally scaled in any case, which covers every BASELINE config)
 
     def __repr__(self):
         return "TNMMAP"
@@ -197,9 +200,11 @@ class _LazySchedule:
             self.plan = _cabi.Plan(self._schedule, device)
         else:
             factors, checks, semiring, n_vars, n_checks, n_obs, order = problem_args
+            dyn = bool(getattr(decoder, "dynamic_rescale", False))
             prob = _cabi.Problem(factors, checks, semiring, n_vars, n_checks, n_obs, order=order,
                                  head_bits=int(getattr(decoder, "head_bits", 0) or 0),
-                                 table_bits=_table_bits_abi(decoder.table_bits), device=device)
+                                 table_bits=-1 if dyn else _table_bits_abi(decoder.table_bits), device=device,
+                                 flags=_cabi.COMPILE_DYNAMIC_RESCALE if dyn else 0)
             self.plan = _cabi.Plan.compile(prob)
 
     @property

@@ -609,6 +609,37 @@ def test_dem_d5_circuit_level_against_golden(tq, golden_dir):
     assert tq.SimpleSyndrome(syn) == tq.syndrome_extraction(res.error_pattern, ct.tanner) and np.all(res.success_tag)
 
 
+def test_dynamic_rescaling_survives_fp64_underflow(tq):
+    """TNMMAP, d = 9, p = 1e-12 per Pauli, syndromes of weight ~40 and the all-ones syndrome: their probabilities lie far
+    below the FP64 range (1e-480 and less), so the statically scaled plan returns zeros and an arbitrary sector.  With
+    TNMMAP(dynamic_rescale=True) the global-memory executor carries an int32 exponent per shot: mantissas and exponents
+    match the recurrence oracle run with per-step renormalisation (rtol 1e-10), and the decoded sector is the argmax."""
+    d = 9
+    t = tq.CSSTannerGraph(tq.SurfaceCode(d, d))
+    em = tq.iid_error(1e-12, t)
+    rng = np.random.default_rng(12)
+    syn = rng.integers(0, 2, size=(6, 80), dtype=np.uint8)
+    syn[0] = 1
+    syn[1] = 0
+    s = tq.CSSSyndrome(syn[:, :40], syn[:, 40:])
+    static = tq.compile(tq.TNMMAP(table_bits=0), t, em)
+    r0 = tq.decode(static, s)
+    assert (r0.marginal.reshape(6, -1)[0] == 0).all() and r0.marginal.reshape(6, -1)[1].max() > 0.99   # underflow vs the trivial syndrome
+    ct = tq.compile(tq.TNMMAP(table_bits=0, dynamic_rescale=True), t, em)
+    from tensorqec.jl_b200 import _cabi
+    assert ct.plan.query(_cabi.Q_WIDE) == 1
+    mant, lg, arg = ct.plan.decode_marginal_log2(tq.pack_bits(syn))
+    sch = ct.schedule
+    ref_m, ref_e = frontier.run(sch.factors, sch.checks, sch.order, 1, syn, sch.n_vars, rescale=True)
+    assert (mant.max(axis=1) > 0).all() and lg[0] < -1500 and lg[1] > -60
+    ratio = (mant / ref_m) * np.exp2((lg.astype(np.int64) - ref_e)[:, None].astype(np.float64))
+    assert np.allclose(ratio[ref_m > 0], 1.0, rtol=MAR_RTOL, atol=0)
+    assert np.array_equal(arg, ref_m.argmax(axis=1))
+    # through decode(): sectors are right although the probabilities themselves flush to zero
+    r1 = tq.decode(ct, s)
+    assert np.array_equal(r1.sector, arg) and tq.syndrome_extraction(r1.error_pattern, t) == s
+
+
 def test_property_full_size_d9(tq):
     """BASELINE config 3 shape (d=9, p=0.05) at a size the oracle cannot follow shot by shot: size-independent
     properties -- every correction reproduces its syndrome, decoding is idempotent on its own output's syndrome,
