@@ -283,6 +283,16 @@ int tqec_logical_flags(tqec_gf2 *L, const int32_t *row_class, const uint64_t *e1
 int tqec_coset_rep(tqec_gf2 *R, tqec_gf2 *L, tqec_gf2 *FIX, const uint64_t *synd, const int32_t *sector,
                    int64_t n_shots, uint64_t *err_out, uint8_t *ok_out);
 
+/* ---- lookup-table decoder (a batched baseline sharing the GF(2) front / back end) ----------- */
+/* The reference's TableDecoder (src/decoding/truthtable.jl:138-166): syndrome -> error pattern, decode = look-up.  Keys:
+ * n_entries * ceil(n_checks/64) words, strictly increasing (most significant word = last word); values: n_entries *
+ * ceil(n_vars/64) words.  found_out (may be NULL): 1 if the syndrome is in the table (else the pattern is zero). */
+typedef struct tqec_table tqec_table;
+int tqec_table_create(int64_t n_entries, int32_t n_checks, int32_t n_vars, const uint64_t *keys_sorted,
+                      const uint64_t *values, int32_t device, tqec_table **out);
+int tqec_table_destroy(tqec_table *table);
+int tqec_table_decode(tqec_table *table, const uint64_t *synd, int64_t n_shots, uint64_t *corr_out, uint8_t *found_out);
+
 /* ---- sampling --------------------------------------------------------------------------------------------- */
 #define TQEC_MODEL_FLIP 0  /* IndependentFlipError: bit i flips iff u < p0[i]            (error_model.jl:69-71)  */
 #define TQEC_MODEL_DEPOL 1 /* IndependentDepolarizingError on n qubits: one u per qubit, Y tested first:

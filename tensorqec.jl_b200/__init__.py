@@ -16,6 +16,7 @@ from .decoding import (TNMAP, TNMMAP, AbstractDecoder, AbstractGeneralDecoder, C
 from .circuit import (StimCircuit, circuit_to_string, dem_to_string, detector_error_model, dump_stim_file, parse_stim_file,
                       parse_stim_string, surface_memory_circuit)
 from .dem import DetectorErrorModel, dem2tanner, parse_dem_file, parse_dem_string
+from .truthtable import TableDecoder, TruthTable, load_table, make_table, save_table
 from .error_model import (CSSErrorPattern, CSSSyndrome, IndependentDepolarizingError, IndependentFlipError,
                           SimpleSyndrome, check_logical_error, iid_error, random_error_pattern, syndrome_extraction)
 from .mod2 import Mod2, bitmul, pack_bits, unpack_bits

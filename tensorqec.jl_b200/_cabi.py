@@ -28,6 +28,7 @@ EXPORTS = [
     "tqec_lower", "tqec_lowered_destroy", "tqec_lowered_get", "tqec_plan_from_lowered", "tqec_plan_compile",
     "tqec_comm_unique_id", "tqec_comm_init", "tqec_comm_destroy", "tqec_comm_allreduce_counts",
     "tqec_decode_map_bytes", "tqec_decode_marginal_bytes", "tqec_dmma_peak", "tqec_decode_marginal_log2",
+    "tqec_table_create", "tqec_table_destroy", "tqec_table_decode",
 ]
 
 
@@ -121,6 +122,9 @@ def lib():
     L.tqec_decode_marginal_log2.argtypes = [vp, vp, i64, vp, vp, vp]
     L.tqec_decode_map_bytes.argtypes = [vp, vp, i64, vp, vp]
     L.tqec_decode_marginal_bytes.argtypes = [vp, vp, i64, vp, vp]
+    L.tqec_table_create.argtypes = [i64, i32, i32, vp, vp, i32, C.POINTER(vp)]
+    L.tqec_table_destroy.argtypes = [vp]
+    L.tqec_table_decode.argtypes = [vp, vp, i64, vp, vp]
     L.tqec_comm_unique_id.argtypes = [vp]
     L.tqec_comm_init.argtypes = [i32, i32, vp, i32, C.POINTER(vp)]
     L.tqec_comm_destroy.argtypes = [vp]
@@ -450,6 +454,40 @@ def sample_errors(model: int, probs, seed: int, shot_offset: int, B: int, device
     check(lib().tqec_sample_errors(model, n, _ptr(ps[0]), p1, p2, C.c_uint64(seed & (2 ** 64 - 1)), shot_offset, B,
                                    _ptr(out), device))
     return out
+
+
+class Table:
+    """Owning handle of a `tqec_table` (sorted syndrome keys -> error words, resident on one device)."""
+
+    def __init__(self, keys: np.ndarray, values: np.ndarray, n_checks: int, n_vars: int, device: int = 0):
+        require_device(device)
+        self.nsw, self.ncw = max(1, (n_checks + 63) // 64), max(1, (n_vars + 63) // 64)
+        k = _c(keys, np.uint64).reshape(-1, self.nsw)
+        v = _c(values, np.uint64).reshape(-1, self.ncw)
+        if k.shape[0] != v.shape[0]:
+            raise ValueError("one value per key")
+        h = C.c_void_p()
+        check(lib().tqec_table_create(k.shape[0], n_checks, n_vars, _ptr(k), _ptr(v), device, C.byref(h)))
+        self.h = h
+
+    def decode(self, synd_words: np.ndarray):
+        s = _c(synd_words, np.uint64).reshape(-1, self.nsw)
+        B = s.shape[0]
+        corr = np.zeros((B, self.ncw), dtype=np.uint64)
+        found = np.zeros(B, dtype=np.uint8)
+        check(lib().tqec_table_decode(self.h, _ptr(s), B, _ptr(corr), _ptr(found)))
+        return corr, found.astype(bool)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().tqec_table_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Comm:

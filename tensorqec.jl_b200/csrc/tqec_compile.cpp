@@ -125,7 +125,8 @@ static void lower_problem(const tqec_problem_desc *d, tqec_lowered &L) {
     return;
   }
   const int t_max = env_int("TQEC_WIDE_TMAX", d->wide_t_max > 0 ? d->wide_t_max : 12);
-  L.wd = lower_wide(merged, checks, P.semiring, P.n_vars, P.n_checks, P.n_obs, &ord, t_max, 4);
+  // dynamic rescaling acts between passes: keep the worst-case drop inside one pass below 2^-600
+  L.wd = lower_wide(merged, checks, P.semiring, P.n_vars, P.n_checks, P.n_obs, &ord, t_max, 4, dynamic ? 600.0 : 0.0);
   L.kind = 2;
 }
 

@@ -593,3 +593,101 @@ extern "C" int tqec_dmma_peak(int32_t device, double *dmma_tflops) {
   cudaFree(d_out);
   return TQEC_OK;
 }
+
+// ---- lookup-table decoder (the reference's TableDecoder, src/decoding/truthtable.jl) -------------------------------------
+// The table maps syndromes to error patterns; keys are sorted (most significant word last compares first) and a shot is
+// decoded by binary search: HBM / L2 latency bound, log2(entries) dependent loads per shot.
+struct tqec_table {
+  int device, nsw, ncw;
+  int64_t n;
+  uint64_t *d_keys, *d_vals;
+  void *d_io[3];
+  size_t io_cap[3];
+  cudaStream_t stream;
+  int64_t launches;
+};
+
+namespace tqec {
+__device__ __forceinline__ int key_cmp(const uint64_t *a, const uint64_t *b, int nsw) {
+  for (int w = nsw - 1; w >= 0; --w) {
+    if (a[w] < b[w]) return -1;
+    if (a[w] > b[w]) return 1;
+  }
+  return 0;
+}
+__global__ void k_table_lookup(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ vals, int64_t n, int nsw, int ncw,
+                               const uint64_t *__restrict__ synd, int64_t B, uint64_t *__restrict__ corr, uint8_t *__restrict__ found) {
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < B; s += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t *q = synd + s * nsw;
+    int64_t lo = 0, hi = n - 1, at = -1;
+    while (lo <= hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      const int c = key_cmp(keys + mid * nsw, q, nsw);
+      if (c == 0) { at = mid; break; }
+      if (c < 0) lo = mid + 1; else hi = mid - 1;
+    }
+    for (int w = 0; w < ncw; ++w) corr[s * ncw + w] = at >= 0 ? vals[at * ncw + w] : 0ull;
+    if (found) found[s] = at >= 0;
+  }
+}
+}  // namespace tqec
+
+extern "C" int tqec_table_create(int64_t n_entries, int32_t n_checks, int32_t n_vars, const uint64_t *keys_sorted,
+                                 const uint64_t *values, int32_t device, tqec_table **out) {
+  TQEC_REQUIRE(out && n_entries >= 0 && n_checks >= 0 && n_vars >= 0 && (n_entries == 0 || (keys_sorted && values)),
+               "tqec_table_create: bad arguments");
+  *out = nullptr;
+  const int nsw = words_for(n_checks), ncw = words_for(n_vars);
+  for (int64_t i = 1; i < n_entries; ++i) {
+    int c = 0;
+    for (int w = nsw - 1; w >= 0 && c == 0; --w)
+      c = keys_sorted[(i - 1) * nsw + w] < keys_sorted[i * nsw + w] ? -1 : (keys_sorted[(i - 1) * nsw + w] > keys_sorted[i * nsw + w] ? 1 : 0);
+    TQEC_REQUIRE(c < 0, "tqec_table_create: keys must be strictly increasing (entry %lld)", (long long)i);
+  }
+  int ndev = 0;
+  TQEC_CUDA(cudaGetDeviceCount(&ndev));
+  TQEC_REQUIRE(device >= 0 && device < ndev, "tqec_table_create: device %d not present (%d visible)", device, ndev);
+  TQEC_CUDA(cudaSetDevice(device));
+  tqec_table *t = new tqec_table();
+  std::memset(t, 0, sizeof(*t));
+  t->device = device; t->nsw = nsw; t->ncw = ncw; t->n = n_entries;
+  cudaError_t e = cudaMalloc((void **)&t->d_keys, (size_t)(n_entries ? n_entries : 1) * nsw * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&t->d_vals, (size_t)(n_entries ? n_entries : 1) * ncw * 8);
+  if (e == cudaSuccess && n_entries) e = cudaMemcpy(t->d_keys, keys_sorted, (size_t)n_entries * nsw * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && n_entries) e = cudaMemcpy(t->d_vals, values, (size_t)n_entries * ncw * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { set_error("tqec_table_create: %s", cudaGetErrorString(e)); cudaFree(t->d_keys); cudaFree(t->d_vals); delete t; return TQEC_ERR_CUDA; }
+  *out = t;
+  return TQEC_OK;
+}
+
+extern "C" int tqec_table_destroy(tqec_table *t) {
+  if (!t) return TQEC_OK;
+  cudaSetDevice(t->device);
+  cudaFree(t->d_keys); cudaFree(t->d_vals);
+  for (int i = 0; i < 3; ++i) cudaFree(t->d_io[i]);
+  if (t->stream) cudaStreamDestroy(t->stream);
+  delete t;
+  return TQEC_OK;
+}
+
+extern "C" int tqec_table_decode(tqec_table *t, const uint64_t *synd, int64_t B, uint64_t *corr_out, uint8_t *found_out) {
+  TQEC_REQUIRE(t && B >= 0 && (B == 0 || (synd && corr_out)), "tqec_table_decode: NULL argument");
+  if (B == 0) return TQEC_OK;
+  TQEC_CUDA(cudaSetDevice(t->device));
+  int rc;
+  if ((rc = ensure_cap(&t->d_io[0], &t->io_cap[0], (size_t)B * t->nsw * 8))) return rc;
+  if ((rc = ensure_cap(&t->d_io[1], &t->io_cap[1], (size_t)B * t->ncw * 8))) return rc;
+  if ((rc = ensure_cap(&t->d_io[2], &t->io_cap[2], (size_t)B))) return rc;
+  TQEC_CUDA(cudaMemcpyAsync(t->d_io[0], synd, (size_t)B * t->nsw * 8, cudaMemcpyHostToDevice, t->stream));
+  const int64_t want = (B + 255) / 256;
+  k_table_lookup<<<(unsigned)(want < 4096 ? want : 4096), 256, 0, t->stream>>>(t->d_keys, t->d_vals, t->n, t->nsw, t->ncw,
+                                                                              (const uint64_t *)t->d_io[0], B, (uint64_t *)t->d_io[1],
+                                                                              (uint8_t *)t->d_io[2]);
+  TQEC_CUDA(cudaGetLastError());
+  t->launches += 1;
+  TQEC_CUDA(cudaMemcpyAsync(corr_out, t->d_io[1], (size_t)B * t->ncw * 8, cudaMemcpyDeviceToHost, t->stream));
+  if (found_out) TQEC_CUDA(cudaMemcpyAsync(found_out, t->d_io[2], (size_t)B, cudaMemcpyDeviceToHost, t->stream));
+  TQEC_CUDA(cudaStreamSynchronize(t->stream));
+  return TQEC_OK;
+}

@@ -92,7 +92,7 @@ Schedule lower_schedule(const std::vector<Factor> &factors, const std::vector<Ch
 // -> false when the plan does not fit the in-place form (the caller keeps the general kernels)
 bool lower_sweep(const Schedule &sch, int max_head_bits, SweepPlan &out);
 WidePlan lower_wide(const std::vector<Factor> &factors, const std::vector<Check> &checks, int semiring, int n_vars, int n_checks,
-                    int n_obs, const std::vector<int> *order, int t_max, int low_bits);
+                    int n_obs, const std::vector<int> *order, int t_max, int low_bits, double max_drop_bits = 0.0);
 
 }  // namespace lower
 }  // namespace tqec

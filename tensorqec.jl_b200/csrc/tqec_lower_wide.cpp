@@ -71,7 +71,7 @@ static LocalStep local_step(std::vector<int> &live, const Factor &f, const WRole
 }
 
 WidePlan lower_wide(const std::vector<Factor> &factors_in, const std::vector<Check> &checks_in, int semiring, int n_vars, int n_checks,
-                    int n_obs, const std::vector<int> *order_in, int t_max, int low_bits) {
+                    int n_obs, const std::vector<int> *order_in, int t_max, int low_bits, double max_drop_bits) {
   if (semiring != TQEC_SEMIRING_SUMPROD) throw std::runtime_error("the global-memory executor runs sum-product plans only");
   std::vector<Factor> factors = merge_overlapping(factors_in, n_vars, checks_in);
   std::vector<Check> checks;
@@ -137,6 +137,13 @@ WidePlan lower_wide(const std::vector<Factor> &factors_in, const std::vector<Che
     }
     tabs.push_back(tab);
   }
+  std::vector<double> drops;   // log2(largest / smallest non-zero entry) of every step's table
+  for (auto &tab : tabs) {
+    double mx = 0.0, mn = 0.0;
+    for (double x : tab)
+      if (x > 0.0) { mx = std::max(mx, x); mn = mn == 0.0 ? x : std::min(mn, x); }
+    drops.push_back(mx > 0.0 ? std::log2(mx / mn) : 0.0);
+  }
 
   struct SimOut { bool ok = false; std::set<int> tile; std::vector<int> g; int peak = 0; };
   auto simulate = [&](int t0, int t1, const std::vector<int> &glive, int lb) {
@@ -167,6 +174,11 @@ WidePlan lower_wide(const std::vector<Factor> &factors_in, const std::vector<Che
       if (w + (int)R.closing.size() > MAX_WIDE_WIDTH) return so;
     }
     if (peak > t_max) return so;
+    if (max_drop_bits > 0 && t1 - t0 > 1) {
+      double acc = 0.0;
+      for (int t = t0; t < t1; ++t) acc += drops[t];
+      if (acc > max_drop_bits) return so;
+    }
     so.ok = true; so.g = g; so.peak = peak;
     return so;
   };

@@ -264,7 +264,7 @@ def tnmap_schedule(decoder: TNMAP, problem: GeneralDecodingProblem) -> S.Schedul
     return _tnmap_lower(decoder, factors, checks, problem.tanner.nq, problem.tanner.ns, _order_of(decoder.optimizer, len(factors)))
 
 
-def _lower_sumprod(factors, checks, n_vars, n_checks, n_obs, order):
+def _lower_sumprod(factors, checks, n_vars, n_checks, n_obs, order, dynamic=False):
     """Sum-product plan of a marginal network: the on-chip schedule (schedule.py) when the frontier fits 13 bits, else
     the global-memory lowering (wide.py).  The order is chosen once and shared by both."""
     all_check_vars = {v for c in checks for v in c.vars}
@@ -274,10 +274,10 @@ def _lower_sumprod(factors, checks, n_vars, n_checks, n_obs, order):
     elif len(order) == len(factors) and len(factors) != len(merged):
         order = S.map_order(factors, merged, order)
     w_max, _ = S._evaluate(order, S._Sim(merged, checks))
-    if w_max <= S.MAX_SMEM_WIDTH and os.environ.get("TQEC_FORCE_WIDE") is None:
+    if w_max <= S.MAX_SMEM_WIDTH and os.environ.get("TQEC_FORCE_WIDE") is None and not dynamic:
         return S.lower(merged, checks, S.SUMPROD, n_vars, n_checks, n_obs, order=order)
     return lower_wide(merged, checks, S.SUMPROD, n_vars, n_checks, n_obs, order=order,
-                      t_max=int(os.environ.get("TQEC_WIDE_TMAX", "12")))
+                      t_max=int(os.environ.get("TQEC_WIDE_TMAX", "12")), max_drop_bits=600.0 if dynamic else 0.0)
 
 
 def _attach_sweep(sch, max_head_bits: int = 10):
@@ -350,7 +350,7 @@ class CompiledTNMMAP(CompiledDecoder, _LazySchedule):
 
 def _sumprod_lower(decoder, factors, checks, dims, order):
     """Python lowering of a marginal network (the oracle of tqec_lower for sum-product plans)."""
-    sch = _lower_sumprod(factors, checks, dims[0], dims[1], dims[2], order)
+    sch = _lower_sumprod(factors, checks, dims[0], dims[1], dims[2], order, dynamic=bool(getattr(decoder, "dynamic_rescale", False)))
     _attach_sweep(sch)
     sch.table_bits = decoder.table_bits
     return sch
@@ -500,6 +500,9 @@ def compile(decoder: AbstractDecoder, problem, pvec: Optional[AbstractErrorModel
             t = problem.tanner
             tn = SimpleTensorNetwork([[i] for i in range(t.nq)], [np.array([1.0 - p, p]) for p in problem.pvec.p])
             return _compile_tnmap(decoder, GeneralDecodingProblem(t, tn))
+    from .truthtable import TableDecoder, compile_table
+    if isinstance(decoder, TableDecoder) and isinstance(problem, IndependentDepolarizingDecodingProblem):
+        return compile_table(decoder, problem)                                 # truthtable.jl:205-208
     if isinstance(decoder, TNMMAP):
         if isinstance(problem, IndependentDepolarizingDecodingProblem):
             return _compile_tnmmap_css(decoder, problem)
@@ -530,6 +533,9 @@ def decode(first, *args):
         out = extract_decoding(ct.reduction, res.error_pattern)
         out.success_tag, out.logp = res.success_tag, res.logp
         return out
+    from .truthtable import CompiledTable, decode_table
+    if isinstance(ct, CompiledTable) and isinstance(syn, CSSSyndrome):
+        return decode_table(ct, syn)
     if isinstance(ct, CompiledTNMAP) and isinstance(syn, SimpleSyndrome):
         return _decode_tnmap(ct, syn)
     if isinstance(ct, CompiledTNMMAP) and isinstance(syn, CSSSyndrome):

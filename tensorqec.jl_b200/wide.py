@@ -161,8 +161,11 @@ def _local_step(live, f, fi, touched, opened, closing, checks, table):
 
 
 def lower_wide(factors: Sequence[S.Factor], checks: Sequence[S.Check], semiring: int, n_vars: int, n_checks: int,
-               n_obs: int, order: Optional[Sequence[int]] = None, t_max: int = T_MAX, low_bits: int = LOW_BITS) -> WidePlan:
-    """Factor graph -> `WidePlan`.  Factors are merged / completed as in schedule.lower; `order` as there."""
+               n_obs: int, order: Optional[Sequence[int]] = None, t_max: int = T_MAX, low_bits: int = LOW_BITS,
+               max_drop_bits: float = 0.0) -> WidePlan:
+    """Factor graph -> `WidePlan`.  Factors are merged / completed as in schedule.lower; `order` as there.
+    `max_drop_bits` > 0 (dynamic rescaling, which acts between passes): a pass ends before the product of its steps'
+    largest / smallest non-zero factor entries exceeds 2^max_drop_bits, so no shot can underflow inside one pass."""
     if semiring != S.SUMPROD:
         raise ValueError("the global-memory executor runs sum-product plans only")
     all_check_vars = {v for c in checks for v in c.vars}
@@ -189,6 +192,10 @@ def lower_wide(factors: Sequence[S.Factor], checks: Sequence[S.Check], semiring:
             tab = np.ldexp(tab, -e)
             log2_scale += e
         tabs.append(tab)
+    drops = []
+    for tab in tabs:
+        nz = tab[tab > 0]
+        drops.append(float(np.log2(nz.max() / nz.min())) if nz.size else 0.0)
 
     def simulate(t0, t1, glive, lb):
         """-> None if steps t0..t1-1 do not fit one tile, else (tile checks, global live after, local peak width)."""
@@ -209,6 +216,8 @@ def lower_wide(factors: Sequence[S.Factor], checks: Sequence[S.Check], semiring:
             if w + len(closing) > S.MAX_WIDE_WIDTH:
                 return None
         if peak > t_max:
+            return None
+        if max_drop_bits > 0 and t1 - t0 > 1 and sum(drops[t0:t1]) > max_drop_bits:
             return None
         return tile, g, peak
 

@@ -217,3 +217,43 @@ def test_sector_fixes_span_every_reachable_flip():
         if any(sum(r) > 1 for r in reach) and not all(u in reach for u in unit if any(r[unit.index(u)] for r in reach)):
             joint_only += 1
     assert joint_only > 0, "the fuzz never produced a joint-only flip"
+
+
+def test_table_decoder_enumeration_matches_the_reference_loop(tq, tmp_path):
+    """make_table (truthtable.jl:51-90) vectorised vs the reference's triple loop written out: weights 0..d in order,
+    qubit subsets lexicographic, per-qubit Paulis X, Y, Z; a syndrome keeps its first pattern unless a later one is
+    strictly more probable.  save_table / load_table round trip (truthtable.jl:138-166)."""
+    import itertools
+    t = tq.CSSTannerGraph(tq.SurfaceCode(3, 3))
+    rng = np.random.default_rng(1)
+    em = tq.IndependentDepolarizingError(rng.uniform(0.01, 0.08, 9), rng.uniform(0.01, 0.08, 9), rng.uniform(0.01, 0.08, 9))
+    for pvec in (tq.iid_error(0.05, t), em, None):
+        tb = tq.make_table(t, 2, pvec)
+        Hx, Hz = t.stgx.H.astype(int), t.stgz.H.astype(int)
+
+        def prob(x, z):
+            if pvec is None:
+                return 0.0
+            p = 1.0
+            for i in range(9):
+                p = p * [[1 - pvec.px[i] - pvec.py[i] - pvec.pz[i], pvec.pz[i]], [pvec.px[i], pvec.py[i]]][x[i]][z[i]]
+            return p
+        best = {}
+        for k in range(3):
+            for combo in itertools.combinations(range(9), k):
+                for i in range(3 ** k):
+                    x, z = np.zeros(9, dtype=int), np.zeros(9, dtype=int)
+                    for j, q in enumerate(combo):
+                        dg = (i // 3 ** j) % 3
+                        x[q], z[q] = dg <= 1, dg >= 1
+                    key = tuple(np.concatenate([(Hx @ z) % 2, (Hz @ x) % 2]))
+                    if key not in best or prob(*best[key]) < prob(x, z):
+                        best[key] = (x, z)
+        assert len(tb) == len(best)
+        for kb, ev in zip(tq.unpack_bits(tb.keys, 8), tq.unpack_bits(tb.values, 18)):
+            x, z = best[tuple(kb)]
+            assert np.array_equal(ev[:9], x) and np.array_equal(ev[9:], z)
+    f = str(tmp_path / "table.txt")
+    tq.save_table(tb, f)
+    tb2 = tq.load_table(f, 9, 8)
+    assert np.array_equal(tb2.keys, tb.keys) and np.array_equal(tb2.values, tb.values)
