@@ -11,7 +11,7 @@
 namespace tqec {
 namespace lower {
 
-static const int MAX_PASS_STEPS = 48;
+static const int MAX_PASS_STEPS = 240;
 static const int MAX_WIDE_WIDTH = 31;
 
 static bool hasv(const std::vector<int> &v, int x) { return std::find(v.begin(), v.end(), x) != v.end(); }

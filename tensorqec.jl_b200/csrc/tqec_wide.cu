@@ -15,7 +15,7 @@
 
 namespace tqec {
 
-#define WD_MAX_STEPS 64
+#define WD_MAX_STEPS 256
 
 struct WidePassArgs {
   const double *gin;
@@ -100,6 +100,64 @@ __device__ __forceinline__ void wd_pure_step(const int32_t *__restrict__ q, cons
   }
 }
 
+// Up to three consecutive pure steps whose masks are linearly independent are FUSED: a thread loads the 2^G entries of
+// one orbit of span{m_0..m_{G-1}} into registers, applies the G butterflies there (step j pairs the orbit members that
+// differ in generator j; same operations in the same order as G separate steps) and stores the orbit back: one shared-
+// memory round trip and one barrier for G steps.  `pivots`: the leading bits of the masks' echelon form; the orbit
+// representative is the member with all pivot bits clear.
+template <int G>
+__device__ __forceinline__ void wd_pure_group(const int32_t *__restrict__ q, const int32_t *__restrict__ I, const double *__restrict__ T,
+                                              double *__restrict__ S, uint32_t pivots, int tid, int NT) {
+  uint32_t m[G], cm[1 << G];
+  double t0[G], t1[G];
+  int piv[G];
+#pragma unroll
+  for (int j = 0; j < G; ++j) {
+    const int32_t *qj = q + j * TQEC_WIDE_STEP_INTS;
+    m[j] = (uint32_t)I[qj[TQEC_WL_OFF_MK] + 1];
+    t0[j] = T[qj[TQEC_WL_OFF_T]];
+    t1[j] = T[qj[TQEC_WL_OFF_T] + 1];
+    piv[j] = __ffs(pivots) - 1;                                  // ascending
+    pivots &= pivots - 1;
+  }
+#pragma unroll
+  for (int k = 0; k < (1 << G); ++k) {
+    uint32_t x = 0;
+#pragma unroll
+    for (int j = 0; j < G; ++j)
+      if ((k >> j) & 1) x ^= m[j];
+    cm[k] = x;
+  }
+  const int n_orb = 1 << (q[TQEC_WL_WOUT] - G);
+  for (int i = tid; i < n_orb; i += NT) {
+    uint32_t tau = (uint32_t)i;
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const uint32_t lowmask = (1u << piv[j]) - 1u;
+      tau = ((tau & ~lowmask) << 1) | (tau & lowmask);
+    }
+    double v[1 << G];
+#pragma unroll
+    for (int k = 0; k < (1 << G); ++k) v[k] = S[tau ^ cm[k]];
+#pragma unroll
+    for (int j = 0; j < G; ++j)
+#pragma unroll
+      for (int k = 0; k < (1 << G); ++k)
+        if (!((k >> j) & 1)) {
+          const double a = v[k], b = v[k | (1 << j)];
+          v[k] = fma(b, t1[j], a * t0[j]);
+          v[k | (1 << j)] = fma(a, t1[j], b * t0[j]);
+        }
+#pragma unroll
+    for (int k = 0; k < (1 << G); ++k) S[tau ^ cm[k]] = v[k];
+  }
+}
+
+__device__ __forceinline__ bool wd_is_pure(const int32_t *q, const int32_t *I) {
+  return q[TQEC_WL_NK] == 2 && q[TQEC_WL_NOPEN] == 0 && q[TQEC_WL_NCLOSE] == 0 && I[q[TQEC_WL_OFF_MK]] == 0 &&
+         I[q[TQEC_WL_OFF_ML]] == 0 && I[q[TQEC_WL_OFF_MK] + 1] != 0;
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NT) k_wide_pass(const WidePassArgs A) {
   extern __shared__ __align__(16) unsigned char wd_smem[];
@@ -117,6 +175,7 @@ __global__ void __launch_bounds__(NT) k_wide_pass(const WidePassArgs A) {
   uint32_t *dep = reinterpret_cast<uint32_t *>(sQ + ns * TQEC_WIDE_STEP_INTS);   // [0..127] input, [128..255] output deposits
   uint32_t *sc = dep + 256;                                      // two scatter tables of 128 entries (double-buffered)
   uint32_t *cbs = sc + 256;                                      // closed-bit value of every step for the current shot
+  uint32_t *grp = cbs + WD_MAX_STEPS;                            // per step: 0 = generic, (pivot mask << 2) | G = head of a fused pure group
   for (int i = tid; i < n_tab; i += NT) sT[i] = A.tables[ph[TQEC_WP_OFF_TAB] + i];
   for (int i = tid; i < n_ints; i += NT) sI[i] = A.ints[ph[TQEC_WP_OFF_INTS] + i];
   for (int i = tid; i < ns * TQEC_WIDE_STEP_INTS; i += NT) sQ[i] = A.step_hdr[(size_t)s0 * TQEC_WIDE_STEP_INTS + i];
@@ -124,6 +183,30 @@ __global__ void __launch_bounds__(NT) k_wide_pass(const WidePassArgs A) {
     const uint32_t x = tid < 64 ? (uint32_t)tid : ((uint32_t)(tid - 64) << 6);
     dep[tid] = wd_pdep(x, tin);
     dep[128 + tid] = wd_pdep(x, tout);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // group consecutive pure steps (up to three, masks linearly independent): echelon form by leading bits
+    int s = 0;
+    while (s < ns) {
+      grp[s] = 0;
+      if (!wd_is_pure(sQ + s * TQEC_WIDE_STEP_INTS, sI)) { ++s; continue; }
+      uint32_t b[3], pm = 0;
+      int g = 0;
+      while (g < 3 && s + g < ns && wd_is_pure(sQ + (s + g) * TQEC_WIDE_STEP_INTS, sI)) {
+        uint32_t x = (uint32_t)sI[sQ[(s + g) * TQEC_WIDE_STEP_INTS + TQEC_WL_OFF_MK] + 1];
+        for (int pass2 = 0; pass2 < 2; ++pass2)
+          for (int j = 0; j < g; ++j)
+            if ((x >> (31 - __clz(b[j]))) & 1u) x ^= b[j];
+        if (x == 0) break;                                       // dependent on the masks already in the group
+        b[g] = x;
+        pm |= 1u << (31 - __clz(x));
+        ++g;
+      }
+      grp[s] = (pm << 2) | (uint32_t)g;
+      for (int j = 1; j < g; ++j) grp[s + j] = 0;
+      s += g;
+    }
   }
   __syncthreads();
   const int n_spec = w_in - t_in;
@@ -167,25 +250,31 @@ __global__ void __launch_bounds__(NT) k_wide_pass(const WidePassArgs A) {
     for (int l = tid; l < n_in; l += NT) S0[l] = __ldcs(gi + (dep[l & 63] | dep[64 + (l >> 6)])) * scale;
     __syncthreads();
     double *Sin = S0, *Sout = S1;
-    for (int s = 0; s < ns; ++s) {
+    for (int s = 0; s < ns;) {
       const int32_t *q = sQ + s * TQEC_WIDE_STEP_INTS;
       const uint32_t *scs = sc + ((s & 1) << 7);
-      if (s + 1 < ns && tid < 128) {                             // scatter table of the next step (other buffer)
+      const int g = (int)(grp[s] & 3u);
+      const int nxt = s + (g ? g : 1);
+      if (nxt < ns && tid < 128) {                               // scatter table of the next step to run (other buffer)
         const uint32_t x = tid < 64 ? (uint32_t)tid : ((uint32_t)(tid - 64) << 6);
-        sc[(((s + 1) & 1) << 7) + tid] = wd_pdep(x, (uint32_t)q[TQEC_WIDE_STEP_INTS + TQEC_WL_KEEPMASK]);
+        sc[((nxt & 1) << 7) + tid] = wd_pdep(x, (uint32_t)sQ[nxt * TQEC_WIDE_STEP_INTS + TQEC_WL_KEEPMASK]);
       }
-      const int nk = q[TQEC_WL_NK];
-      if (nk == 2 && q[TQEC_WL_NOPEN] == 0 && q[TQEC_WL_NCLOSE] == 0 && sI[q[TQEC_WL_OFF_MK]] == 0 && sI[q[TQEC_WL_OFF_ML]] == 0 &&
-          sI[q[TQEC_WL_OFF_MK] + 1] != 0) {
-        wd_pure_step(q, sI, sT, Sin, tid, NT);
+      if (g) {
+        const uint32_t pm = grp[s] >> 2;
+        if (g == 3) wd_pure_group<3>(q, sI, sT, Sin, pm, tid, NT);
+        else if (g == 2) wd_pure_group<2>(q, sI, sT, Sin, pm, tid, NT);
+        else wd_pure_step(q, sI, sT, Sin, tid, NT);
         __syncthreads();
+        s = nxt;
         continue;
       }
+      const int nk = q[TQEC_WL_NK];
       if (nk == 1) wd_step<1>(q, sI, sT, scs, cbs[s], Sin, Sout, tid, NT);
       else if (nk == 2) wd_step<2>(q, sI, sT, scs, cbs[s], Sin, Sout, tid, NT);
       else wd_step<0>(q, sI, sT, scs, cbs[s], Sin, Sout, tid, NT);
       __syncthreads();
       double *tmp = Sin; Sin = Sout; Sout = tmp;
+      s = nxt;
     }
     double tmax = 0.0;
     for (int l = tid; l < n_out; l += NT) {
@@ -238,7 +327,7 @@ static size_t wide_smem_bytes(int t_max, int n_tab, int n_ints, int ns) {
   b += (size_t)((n_tab + 1) & ~1) * 8;
   b += (size_t)((n_ints + 3) & ~3) * 4;
   b += (size_t)ns * TQEC_WIDE_STEP_INTS * 4;
-  b += (256 + 256 + WD_MAX_STEPS) * 4;
+  b += (256 + 256 + 2 * WD_MAX_STEPS) * 4;
   return (b + 15) & ~(size_t)15;
 }
 

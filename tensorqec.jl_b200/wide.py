@@ -35,7 +35,7 @@ from . import schedule as S
 
 T_MAX = 12               # tile bits: 2 * 2^12 * 8 B = 64 KiB of ping-pong state per CTA, three CTAs per SM
 LOW_BITS = 4             # contiguous run of global loads / stores: 2^4 entries = 128 B
-MAX_PASS_STEPS = 48
+MAX_PASS_STEPS = 240
 PASS_INTS = 16           # pass header (int32)
 STEP_INTS = 16           # local step header (int32)
 (P_WIN, P_WOUT, P_TIN, P_TOUT, P_NSTEPS, P_STEP0, P_TINMASK, P_TOUTMASK, P_OFF_INTS, P_N_INTS, P_OFF_TAB, P_N_TAB) = range(12)
