@@ -114,7 +114,9 @@ static void lower_problem(const tqec_problem_desc *d, tqec_lowered &L) {
   const bool dynamic = (d->flags & TQEC_COMPILE_DYNAMIC_RESCALE) != 0;
   if (dynamic) L.plan_flags |= TQEC_PLAN_DYNAMIC_RESCALE;
   const bool force_wide = dynamic || (d->flags & TQEC_COMPILE_FORCE_WIDE) || std::getenv("TQEC_FORCE_WIDE");
-  if (w_max <= 13 && !force_wide) {
+  // on chip up to 11 bits; from 12 bits on the global-memory executor's tile kernel is faster (a 12-bit plan is one tile)
+  const int onchip = std::min(env_int("TQEC_SUMPROD_ONCHIP_WIDTH", 11), 13);
+  if (w_max <= onchip && !force_wide) {
     L.sch = lower_schedule(merged, checks, P.semiring, P.n_vars, P.n_checks, P.n_obs, &ord, 13, 0, false);
     L.kind = 0;
     if (!no_sweep && L.sch.w_max >= 5 && L.sch.w_max <= 10) {
@@ -134,7 +136,7 @@ static void finish(tqec_lowered &L) {
   L.meta.assign(16, 0);
   L.meta[0] = L.kind;
   if (L.kind == 2) {
-    L.meta[1] = L.wd.n_steps; L.meta[2] = L.wd.w_cap; L.meta[3] = L.wd.log2_scale;
+    L.meta[1] = L.wd.n_steps; L.meta[2] = L.wd.w_peak; L.meta[3] = L.wd.log2_scale;
     L.meta[11] = L.wd.n_pass; L.meta[12] = L.wd.n_steps; L.meta[13] = L.wd.w_cap; L.meta[14] = L.wd.t_max;
     L.cost = {L.wd.cost, L.wd.bytes_per_shot};
     L.order32.assign(L.wd.order.begin(), L.wd.order.end());

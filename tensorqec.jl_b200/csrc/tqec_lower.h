@@ -66,7 +66,7 @@ struct SweepPlan {
 
 struct WidePlan {
   int semiring = 0, n_vars = 0, n_checks = 0, n_obs = 0;
-  int w_cap = 0, t_max = 0, n_pass = 0, n_steps = 0, log2_scale = 0;
+  int w_cap = 0, w_peak = 0, t_max = 0, n_pass = 0, n_steps = 0, log2_scale = 0;   // w_cap: between passes (HBM); w_peak: any step
   std::vector<int> obs_pos, order;
   double cost = 0.0, bytes_per_shot = 0.0;
   std::vector<int32_t> pass_hdr, step_hdr, ints;

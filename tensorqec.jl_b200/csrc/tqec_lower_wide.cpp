@@ -228,6 +228,7 @@ WidePlan lower_wide(const std::vector<Factor> &factors_in, const std::vector<Che
       q[TQEC_WL_KEEPMASK] = (int32_t)ls.keepmask;
       P.step_hdr.insert(P.step_hdr.end(), q, q + TQEC_WIDE_STEP_INTS);
       cost += std::ldexp(1.0, n_spec + ls.w_out) * ls.nk;
+      P.w_peak = std::max(P.w_peak, n_spec + ls.w_out);
       ++step_count;
     }
     int32_t hdr[TQEC_WIDE_PASS_INTS] = {0};

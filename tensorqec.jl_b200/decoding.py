@@ -206,6 +206,12 @@ class _LazySchedule:
                                  table_bits=-1 if dyn else _table_bits_abi(decoder.table_bits), device=device,
                                  flags=_cabi.COMPILE_DYNAMIC_RESCALE if dyn else 0)
             self.plan = _cabi.Plan.compile(prob)
+            lw = self.plan.lowered
+            if lw["kind"] == 0 and lw["w_max"] >= 5 and not self.plan.query(_cabi.Q_TABLE):
+                import warnings
+                warnings.warn(f"{type(decoder).__name__}: this plan (frontier {lw['w_max']} bits) does not fit the in-place patch sweep "
+                              f"(k_sweep) and decodes through the general frontier kernels, at roughly half the throughput; "
+                              f"odd-distance rotated surface codes in the library's own order do fit", RuntimeWarning, stacklevel=4)
 
     @property
     def schedule(self):
@@ -265,8 +271,9 @@ def tnmap_schedule(decoder: TNMAP, problem: GeneralDecodingProblem) -> S.Schedul
 
 
 def _lower_sumprod(factors, checks, n_vars, n_checks, n_obs, order, dynamic=False):
-    """Sum-product plan of a marginal network: the on-chip schedule (schedule.py) when the frontier fits 13 bits, else
-    the global-memory lowering (wide.py).  The order is chosen once and shared by both."""
+    """Sum-product plan of a marginal network: the on-chip schedule (schedule.py) when the frontier has at most 11 bits,
+    else the global-memory lowering (wide.py; measured faster from 12 bits on: its tile kernel fuses runs of two-candidate
+    steps into register butterflies and a 12-bit plan is a single tile).  The order is chosen once and shared by both."""
     all_check_vars = {v for c in checks for v in c.vars}
     merged = S.merge_overlapping(list(factors), n_vars, all_check_vars)
     if order is None:
@@ -274,7 +281,8 @@ def _lower_sumprod(factors, checks, n_vars, n_checks, n_obs, order, dynamic=Fals
     elif len(order) == len(factors) and len(factors) != len(merged):
         order = S.map_order(factors, merged, order)
     w_max, _ = S._evaluate(order, S._Sim(merged, checks))
-    if w_max <= S.MAX_SMEM_WIDTH and os.environ.get("TQEC_FORCE_WIDE") is None and not dynamic:
+    onchip = min(int(os.environ.get("TQEC_SUMPROD_ONCHIP_WIDTH", S.MAX_SUMPROD_ONCHIP_WIDTH)), S.MAX_SMEM_WIDTH)
+    if w_max <= onchip and os.environ.get("TQEC_FORCE_WIDE") is None and not dynamic:
         return S.lower(merged, checks, S.SUMPROD, n_vars, n_checks, n_obs, order=order)
     return lower_wide(merged, checks, S.SUMPROD, n_vars, n_checks, n_obs, order=order,
                       t_max=int(os.environ.get("TQEC_WIDE_TMAX", "12")), max_drop_bits=600.0 if dynamic else 0.0)

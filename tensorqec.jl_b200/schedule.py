@@ -50,6 +50,7 @@ HDR_INTS = 16
 
 MAX_FACTOR_RANK = 10
 MAX_SMEM_WIDTH = 13            # 2 * 2^13 * 8 B = 128 KiB of ping-pong state per team
+MAX_SUMPROD_ONCHIP_WIDTH = 11  # sum-product plans wider than this run on the global-memory executor (measured faster from 12 bits)
 MAX_WIDE_WIDTH = 31            # the global-memory executor (wide.py, k_wide_pass): state of 2^w FP64 entries in HBM
 
 

@@ -76,7 +76,8 @@ class WidePlan:
     n_vars: int
     n_checks: int
     n_obs: int
-    w_cap: int                                 # widest global state over the plan (bits)
+    w_cap: int                                 # widest global state between passes (bits): what lives in HBM
+    w_max: int                                 # widest state at any step, inside passes too (frontier width of the order)
     t_max: int
     passes: List[WidePass]
     obs_pos: List[int]                         # position of observable i in the final index
@@ -224,6 +225,7 @@ def lower_wide(factors: Sequence[S.Factor], checks: Sequence[S.Check], semiring:
     passes: List[WidePass] = []
     glive: List[int] = []
     w_cap = 0
+    w_peak = 0
     cost = 0.0
     traffic = 0.0
     t = 0
@@ -255,6 +257,7 @@ def lower_wide(factors: Sequence[S.Factor], checks: Sequence[S.Check], semiring:
         n_spec = len(glive) - t_in
         for ls in lsteps:
             cost += float(1 << (n_spec + ls.w_out)) * ls.nk
+            w_peak = max(w_peak, n_spec + ls.w_out)
         traffic += 8.0 * ((1 << len(glive)) + (1 << len(gout)))
         passes.append(WidePass(t, t1, len(glive), len(gout), tin_mask, tout_mask, t_in, len(L), peak, lsteps))
         w_cap = max(w_cap, len(glive), len(gout))
@@ -267,7 +270,7 @@ def lower_wide(factors: Sequence[S.Factor], checks: Sequence[S.Check], semiring:
         obs_pos[checks[c].index] = k
     if any(p < 0 for p in obs_pos) or len(glive) != n_obs:
         raise ValueError("every observable row must be declared exactly once")
-    plan = WidePlan(semiring, n_vars, n_checks, n_obs, w_cap, t_max, passes, obs_pos, log2_scale, order, factors, list(checks),
+    plan = WidePlan(semiring, n_vars, n_checks, n_obs, w_cap, w_peak, t_max, passes, obs_pos, log2_scale, order, factors, list(checks),
                     cost, traffic)
     _encode(plan)
     return plan

@@ -433,25 +433,36 @@ def test_dem_surface_memory(tq, name, n_dense):
 def test_dem_from_generated_circuit(tq):
     """BASELINE configs[3] proper: d=3 x 3 rounds rotated-surface memory circuit with circuit-level noise (depolarizing
     after every Clifford, data depolarizing per round, measurement and reset flips) -> circuit.detector_error_model ->
-    TNMMAP on the GPU (12-bit frontier, wide warp teams) against the C port and the numpy recurrence."""
+    TNMMAP on the GPU (12-bit frontier: one tile of the global-memory executor by default, the on-chip CTA kernels when
+    asked) against the C port of the recurrence and its numpy statement."""
     txt = tq.surface_memory_circuit(3, 3, "Z", after_clifford_depolarization=2e-3, before_round_data_depolarization=2e-3,
                                     before_measure_flip_probability=2e-3, after_reset_flip_probability=2e-3)
     dem = tq.detector_error_model(tq.parse_stim_string(txt))
     assert dem.n_detectors == 24 and dem.n_observables == 1
-    ct = tq.compile(tq.TNMMAP(), dem)
+    import os
+    from tensorqec.jl_b200 import _cabi
     B = 256
-    ep = tq.random_error_pattern(dem, seed=11, shots=B)
-    syn = tq.syndrome_extraction(ep, ct.tanner)
-    res = tq.decode(ct, syn)
-    assert syn == tq.syndrome_extraction(res.error_pattern, ct.tanner)
-    sch = ct.schedule
-    got = res.marginal.reshape(B, -1, order="F")
-    ref = cref.FrontierPlan(sch).run(syn.s)
-    assert np.allclose(got, ref, rtol=MAR_RTOL, atol=0)
-    ref2 = frontier.run(sch.factors, sch.checks, sch.order, 1, syn.s[:4], sch.n_vars)
-    assert np.allclose(got[:4], ref2, rtol=MAR_RTOL, atol=0)
-    true_obs = (ep[:, ct.l2q[0]].sum(axis=1) & 1)
-    assert (res.sector == true_obs).mean() > 0.97
+    for onchip in (False, True):
+        if onchip:
+            os.environ["TQEC_SUMPROD_ONCHIP_WIDTH"] = "13"
+        try:
+            ct = tq.compile(tq.TNMMAP(table_bits=0), dem)
+            sch = ct.schedule
+        finally:
+            os.environ.pop("TQEC_SUMPROD_ONCHIP_WIDTH", None)
+        assert ct.plan.query(_cabi.Q_WIDE) == (0 if onchip else 1)
+        ep = tq.random_error_pattern(dem, seed=11, shots=B)
+        syn = tq.syndrome_extraction(ep, ct.tanner)
+        res = tq.decode(ct, syn)
+        assert syn == tq.syndrome_extraction(res.error_pattern, ct.tanner)
+        got = res.marginal.reshape(B, -1, order="F")
+        if onchip:
+            ref = cref.FrontierPlan(sch).run(syn.s)
+            assert np.allclose(got, ref, rtol=MAR_RTOL, atol=0)
+        ref2 = frontier.run(sch.factors, sch.checks, sch.order, 1, syn.s[:8], sch.n_vars)
+        assert np.allclose(got[:8], ref2, rtol=MAR_RTOL, atol=0)
+        true_obs = (ep[:, ct.l2q[0]].sum(axis=1) & 1)
+        assert (res.sector == true_obs).mean() > 0.97
 
 
 @pytest.mark.parametrize("t_max", [8, 12])
@@ -464,8 +475,10 @@ def test_wide_executor_circuit_level_d3(tq, monkeypatch, t_max):
     txt = tq.surface_memory_circuit(3, 3, "Z", after_clifford_depolarization=2e-3, before_round_data_depolarization=2e-3,
                                     before_measure_flip_probability=2e-3, after_reset_flip_probability=2e-3)
     dem = tq.detector_error_model(tq.parse_stim_string(txt))
+    monkeypatch.setenv("TQEC_SUMPROD_ONCHIP_WIDTH", "13")        # this 12-bit plan defaults to the global-memory executor
     on_chip = tq.compile(tq.TNMMAP(table_bits=0), dem)
     assert on_chip.plan.query(_cabi.Q_WIDE) == 0
+    monkeypatch.delenv("TQEC_SUMPROD_ONCHIP_WIDTH")
     monkeypatch.setenv("TQEC_FORCE_WIDE", "1")
     monkeypatch.setenv("TQEC_WIDE_TMAX", str(t_max))
     ct = tq.compile(tq.TNMMAP(table_bits=0), dem)
