@@ -8,7 +8,8 @@ import tensorqec.jl_b200 as tq
 from tensorqec.jl_b200 import _cabi
 from benchmarks.configs import time_marginal
 
-for d, B in ((5, 1000000), (7, 1000000), (9, 400000)):
+CASES = ((int(sys.argv[1]), int(sys.argv[2])),) if len(sys.argv) > 2 else ((5, 1000000), (7, 1000000), (9, 400000))
+for d, B in CASES:
     t = tq.CSSTannerGraph(tq.SurfaceCode(d, d))
     em = tq.iid_error(0.05, t)
     ct = tq.compile(tq.TNMMAP(), t, em)

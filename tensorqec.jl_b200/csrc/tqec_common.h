@@ -8,11 +8,23 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "tqec.h"
 
 namespace tqec {
 
 void set_error(const char *fmt, ...);
+
+// NVTX range covering a scope: the library's entry points show up as named ranges in Nsight Systems / Compute timelines
+// (plan compile, plan create, decode, fused Monte-Carlo pipeline).  Header-only NVTX v3: no link dependency; without a
+// profiler attached a range costs a few nanoseconds.
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange &) = delete;
+  NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 #define TQEC_CUDA(call)                                                                      \
   do {                                                                                       \

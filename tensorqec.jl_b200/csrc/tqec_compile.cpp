@@ -159,6 +159,7 @@ static void finish(tqec_lowered &L) {
 }
 
 extern "C" int tqec_lower(const tqec_problem_desc *prob, tqec_lowered **out) {
+  tqec::NvtxRange nvtx_range("tqec_lower");
   TQEC_REQUIRE(out != nullptr, "tqec_lower: out is NULL");
   *out = nullptr;
   tqec_lowered *L = new tqec_lowered();

@@ -1026,6 +1026,7 @@ static int tabulate_plan(tqec_plan *p, const tqec_plan_desc *d) {
 }
 
 extern "C" int tqec_plan_create(const tqec_plan_desc *d, tqec_plan **out) {
+  tqec::NvtxRange nvtx_range("tqec_plan_create");
   TQEC_REQUIRE(out != nullptr, "tqec_plan_create: out is NULL");
   *out = nullptr;
   int rc = validate_desc(d);
@@ -1260,6 +1261,7 @@ static int ensure_pipeline(tqec_plan *p) {
 }
 
 extern "C" int tqec_decode_map(tqec_plan *p, const uint64_t *synd, int64_t B, uint64_t *corr_out, double *logp_out) {
+  tqec::NvtxRange nvtx_range("tqec_decode_map");
   TQEC_REQUIRE(p && p->semiring == TQEC_SEMIRING_MAXPLUS, "tqec_decode_map: plan is not a max-plus (TNMAP) plan");
   TQEC_REQUIRE(B >= 0 && (B == 0 || (synd && corr_out)), "tqec_decode_map: NULL buffer");
   if (B == 0) return TQEC_OK;
@@ -1296,6 +1298,7 @@ extern "C" int tqec_decode_map(tqec_plan *p, const uint64_t *synd, int64_t B, ui
 }
 
 extern "C" int tqec_decode_marginal(tqec_plan *p, const uint64_t *synd, int64_t B, double *mar_out, int32_t *argmax_out) {
+  tqec::NvtxRange nvtx_range("tqec_decode_marginal");
   TQEC_REQUIRE(p && p->semiring == TQEC_SEMIRING_SUMPROD, "tqec_decode_marginal: plan is not a sum-product (TNMMAP) plan");
   TQEC_REQUIRE(B >= 0 && (B == 0 || (synd && mar_out)), "tqec_decode_marginal: NULL buffer");
   if (B == 0) return TQEC_OK;
@@ -1363,6 +1366,7 @@ static int grid_for(int64_t n, int sm) {
 
 // shared body: bytes in -> pack -> decode -> (unpack) -> out, chunked on the plan's stream
 static int decode_bytes(tqec_plan *p, const uint8_t *synd_bits, int64_t B, uint8_t *corr_bits, double *out, int32_t *argmax_out) {
+  tqec::NvtxRange nvtx_range("tqec_decode_bytes");
   const bool mp = p->semiring == TQEC_SEMIRING_MAXPLUS;
   const int nc = p->dev.n_checks, nv = p->dev.n_vars, nsw = p->dev.nsw, ncw = p->dev.ncw;
   const int64_t NO = mp ? 1 : ((int64_t)1 << p->dev.n_obs);

@@ -403,6 +403,7 @@ extern "C" int tqec_sample_errors(int32_t model, int32_t n_sites, const double *
 // ---- fused pipeline -------------------------------------------------------------------------------------------
 extern "C" int tqec_mc_run(const tqec_mc_desc *mc, uint64_t seed, int64_t shot_offset, int64_t n_shots, int64_t counts[4],
                            float *elapsed_ms) {
+  tqec::NvtxRange nvtx_range("tqec_mc_run");
   TQEC_REQUIRE(mc && mc->plan && mc->H && mc->L && mc->row_class && counts, "tqec_mc_run: NULL argument");
   tqec_plan *P = mc->plan;
   TQEC_REQUIRE(P->semiring == TQEC_SEMIRING_MAXPLUS, "tqec_mc_run: needs a max-plus (TNMAP) plan");

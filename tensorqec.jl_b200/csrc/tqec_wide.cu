@@ -483,6 +483,7 @@ static int wide_reserve(tqec_plan *p, int64_t want) {
 
 int launch_wide(tqec_plan *plan, const uint64_t *d_synd, int64_t B, double *d_out, int32_t *d_argmax, cudaStream_t stream,
                 int32_t *d_log2) {
+  tqec::NvtxRange nvtx_range("tqec_wide_decode");
   int rc = wide_reserve(plan, B);
   if (rc) return rc;
   const WideDev &D = plan->wd;
