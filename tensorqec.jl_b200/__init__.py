@@ -17,6 +17,9 @@ from .circuit import (StimCircuit, circuit_to_string, dem_to_string, detector_er
                       parse_stim_string, surface_memory_circuit)
 from .dem import DetectorErrorModel, dem2tanner, parse_dem_file, parse_dem_string
 from .truthtable import TableDecoder, TruthTable, load_table, make_table, save_table
+from .encoder import (CompiledInference, CSSBimatrix, clifford_network, correction_pauli_string, encode_circuit, encode_stabilizers,
+                      generate_syndrome_dict, inference, pauli_string_map_iter, stabilizers2bimatrix, syndrome_inference,
+                      syndrome_transform)
 from .error_model import (CSSErrorPattern, CSSSyndrome, IndependentDepolarizingError, IndependentFlipError,
                           SimpleSyndrome, check_logical_error, iid_error, random_error_pattern, syndrome_extraction)
 from .mod2 import Mod2, bitmul, pack_bits, unpack_bits

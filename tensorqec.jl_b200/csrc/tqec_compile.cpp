@@ -100,7 +100,7 @@ static void lower_problem(const tqec_problem_desc *d, tqec_lowered &L) {
     return;
   }
   // sum-product: one order for either executor
-  std::vector<Factor> merged = merge_overlapping(P.factors, P.n_vars, P.checks);
+  std::vector<Factor> merged = merge_overlapping(P.factors, P.n_vars, P.checks, true);
   std::vector<Check> checks;
   for (auto &c : P.checks) {
     Check q;

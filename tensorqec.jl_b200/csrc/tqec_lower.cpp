@@ -22,7 +22,8 @@ static const int MAX_WIDE_WIDTH = 31;
 static bool contains(const std::vector<int> &v, int x) { return std::find(v.begin(), v.end(), x) != v.end(); }
 
 // ---- merge_overlapping (schedule.py) -----------------------------------------------------------------------------------
-std::vector<Factor> merge_overlapping(const std::vector<Factor> &factors, int n_vars, const std::vector<Check> &checks) {
+std::vector<Factor> merge_overlapping(const std::vector<Factor> &factors, int n_vars, const std::vector<Check> &checks,
+                                      bool allow_negative) {
   (void)n_vars;
   const int nf = (int)factors.size();
   std::vector<int> parent(nf);
@@ -94,7 +95,7 @@ std::vector<Factor> merge_overlapping(const std::vector<Factor> &factors, int n_
     if ((int)f.vars.size() > MAX_FACTOR_RANK) fail("prior factor of rank " + std::to_string(f.vars.size()) + " > 10 is not supported");
     if (f.table.size() != ((size_t)1 << f.vars.size())) fail("factor table must have 2^rank entries");
     for (double x : f.table)
-      if (!(x >= 0.0) || !std::isfinite(x)) fail("prior factor entries must be finite and non-negative");
+      if (!std::isfinite(x) || (x < 0.0 && !allow_negative)) fail("prior factor entries must be finite and non-negative");
   }
   return out;
 }
@@ -503,7 +504,8 @@ static MergedPairs merge_pairs(const std::vector<Factor> &factors, const std::ve
 
 static Schedule lower_impl(const std::vector<Factor> &factors_in, const std::vector<Check> &checks_in, int semiring, int n_vars,
                            int n_checks, int n_obs, const std::vector<int> *order_in, int max_width, int fuse, bool split, bool stable) {
-  std::vector<Factor> factors = merge_overlapping(factors_in, n_vars, checks_in);
+  // signed factors (Clifford-network inference) are legal for sum-product plans
+  std::vector<Factor> factors = merge_overlapping(factors_in, n_vars, checks_in, semiring == TQEC_SEMIRING_SUMPROD);
   std::vector<Check> checks;
   for (auto &c : checks_in) {
     Check d;
@@ -709,7 +711,7 @@ static Schedule lower_impl(const std::vector<Factor> &factors_in, const std::vec
       for (double &x : st.table) x = std::log(x);
     } else {
       double mx = 0.0;
-      for (double x : st.table) mx = std::max(mx, x);
+      for (double x : st.table) mx = std::max(mx, std::fabs(x));
       if (mx > 0.0) {
         log2_run += std::log2(mx);
         const int e = (int)std::nearbyint(log2_run);

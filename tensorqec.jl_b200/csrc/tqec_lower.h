@@ -82,7 +82,8 @@ struct Problem {
 };
 
 // All functions throw std::runtime_error with a message on invalid input (the ABI layer turns it into an error code).
-std::vector<Factor> merge_overlapping(const std::vector<Factor> &factors, int n_vars, const std::vector<Check> &checks);
+std::vector<Factor> merge_overlapping(const std::vector<Factor> &factors, int n_vars, const std::vector<Check> &checks,
+                                      bool allow_negative = false);
 std::vector<int> map_order(const std::vector<Factor> &original, const std::vector<Factor> &merged, const std::vector<int> &order);
 std::vector<int> choose_order(const std::vector<Factor> &factors, const std::vector<Check> &checks, int max_starts = 24);
 std::pair<int, double> evaluate_order(const std::vector<Factor> &factors, const std::vector<Check> &checks, const std::vector<int> &order);

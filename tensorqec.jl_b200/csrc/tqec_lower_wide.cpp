@@ -73,7 +73,7 @@ static LocalStep local_step(std::vector<int> &live, const Factor &f, const WRole
 WidePlan lower_wide(const std::vector<Factor> &factors_in, const std::vector<Check> &checks_in, int semiring, int n_vars, int n_checks,
                     int n_obs, const std::vector<int> *order_in, int t_max, int low_bits, double max_drop_bits) {
   if (semiring != TQEC_SEMIRING_SUMPROD) throw std::runtime_error("the global-memory executor runs sum-product plans only");
-  std::vector<Factor> factors = merge_overlapping(factors_in, n_vars, checks_in);
+  std::vector<Factor> factors = merge_overlapping(factors_in, n_vars, checks_in, true);
   std::vector<Check> checks;
   for (auto &c : checks_in) {
     Check d;
@@ -127,7 +127,7 @@ WidePlan lower_wide(const std::vector<Factor> &factors_in, const std::vector<Che
   for (auto &R : roles) {
     std::vector<double> tab = factors[R.fi].table;
     double mx = 0.0;
-    for (double x : tab) mx = std::max(mx, x);
+    for (double x : tab) mx = std::max(mx, std::fabs(x));
     if (mx > 0.0) {
       log2_run += std::log2(mx);
       const int e = (int)std::nearbyint(log2_run);
@@ -140,8 +140,10 @@ WidePlan lower_wide(const std::vector<Factor> &factors_in, const std::vector<Che
   std::vector<double> drops;   // log2(largest / smallest non-zero entry) of every step's table
   for (auto &tab : tabs) {
     double mx = 0.0, mn = 0.0;
-    for (double x : tab)
+    for (double x0 : tab) {
+      const double x = std::fabs(x0);
       if (x > 0.0) { mx = std::max(mx, x); mn = mn == 0.0 ? x : std::min(mn, x); }
+    }
     drops.push_back(mx > 0.0 ? std::log2(mx / mn) : 0.0);
   }
 

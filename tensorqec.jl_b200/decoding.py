@@ -275,7 +275,7 @@ def _lower_sumprod(factors, checks, n_vars, n_checks, n_obs, order, dynamic=Fals
     else the global-memory lowering (wide.py; measured faster from 12 bits on: its tile kernel fuses runs of two-candidate
     steps into register butterflies and a 12-bit plan is a single tile).  The order is chosen once and shared by both."""
     all_check_vars = {v for c in checks for v in c.vars}
-    merged = S.merge_overlapping(list(factors), n_vars, all_check_vars)
+    merged = S.merge_overlapping(list(factors), n_vars, all_check_vars, allow_negative=True)
     if order is None:
         order = S.choose_order(merged, checks)
     elif len(order) == len(factors) and len(factors) != len(merged):

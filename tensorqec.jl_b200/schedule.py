@@ -124,7 +124,7 @@ def flat_table(t) -> np.ndarray:
     return t.reshape(-1, order="F").copy()
 
 
-def merge_overlapping(factors: Sequence[Factor], n_vars: int, check_vars) -> List[Factor]:
+def merge_overlapping(factors: Sequence[Factor], n_vars: int, check_vars, allow_negative: bool = False) -> List[Factor]:
     """Make the prior factors a partition of the variables: multiply factors that share a variable into one
     (exact; the reference contracts the same product), add an all-ones factor for variables no prior mentions
     (TensorInference's per-variable unity tensor)."""
@@ -179,7 +179,7 @@ def merge_overlapping(factors: Sequence[Factor], n_vars: int, check_vars) -> Lis
             raise ValueError(f"prior factor of rank {len(f.vars)} > {MAX_FACTOR_RANK} is not supported")
         if f.table.shape != (1 << len(f.vars),):
             raise ValueError("factor table must have 2^rank entries")
-        if (f.table < 0).any() or not np.isfinite(f.table).all():
+        if not np.isfinite(f.table).all() or ((f.table < 0).any() and not allow_negative):
             raise ValueError("prior factor entries must be finite and non-negative")
     return out
 
@@ -399,7 +399,8 @@ def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_v
     global-memory executor (wide.py), where a bit permutation is data movement instead of address arithmetic."""
     all_check_vars = {v for c in checks for v in c.vars}
     original = list(factors)
-    factors = merge_overlapping(original, n_vars, all_check_vars)
+    # signed factors (Clifford-network inference: Pauli-representation tensors have entries +-1) are legal for sum-product
+    factors = merge_overlapping(original, n_vars, all_check_vars, allow_negative=semiring == SUMPROD)
     checks = [Check(tuple(dict.fromkeys(c.vars)), c.kind, c.index) for c in checks]
     for c in checks:
         if c.kind not in ("syn", "obs"):
@@ -556,7 +557,7 @@ def lower(factors: Sequence[Factor], checks: Sequence[Check], semiring: int, n_v
             # overflow however many factors there are (1605 at d = 5 x 5 rounds circuit level) and starts from the best
             # place against underflow; the exponents are summed and re-applied by the host after the decode
             tab = f.table.copy()
-            mx = float(tab.max())
+            mx = float(np.abs(tab).max())
             if mx > 0.0:
                 log2_run += math.log2(mx)
                 e = int(np.rint(log2_run))

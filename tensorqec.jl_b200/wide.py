@@ -170,7 +170,7 @@ def lower_wide(factors: Sequence[S.Factor], checks: Sequence[S.Check], semiring:
     if semiring != S.SUMPROD:
         raise ValueError("the global-memory executor runs sum-product plans only")
     all_check_vars = {v for c in checks for v in c.vars}
-    factors = S.merge_overlapping(list(factors), n_vars, all_check_vars)
+    factors = S.merge_overlapping(list(factors), n_vars, all_check_vars, allow_negative=True)
     checks = [S.Check(tuple(dict.fromkeys(c.vars)), c.kind, c.index) for c in checks]
     if order is None:
         order = S.choose_order(factors, checks)
@@ -185,7 +185,7 @@ def lower_wide(factors: Sequence[S.Factor], checks: Sequence[S.Check], semiring:
     log2_run = 0.0
     for fi, *_ in roles:
         tab = np.asarray(factors[fi].table, dtype=np.float64).copy()
-        mx = float(tab.max())
+        mx = float(np.abs(tab).max())
         if mx > 0.0:
             log2_run += math.log2(mx)                             # running product of the maxima stays near 1
             e = int(np.rint(log2_run))
@@ -195,7 +195,7 @@ def lower_wide(factors: Sequence[S.Factor], checks: Sequence[S.Check], semiring:
         tabs.append(tab)
     drops = []
     for tab in tabs:
-        nz = tab[tab > 0]
+        nz = np.abs(tab[tab != 0])
         drops.append(float(np.log2(nz.max() / nz.min())) if nz.size else 0.0)
 
     def simulate(t0, t1, glive, lb):

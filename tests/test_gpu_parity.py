@@ -685,6 +685,46 @@ def test_table_decoder_batched_lookup(tq):
         assert not fl.any()
 
 
+@pytest.mark.parametrize("code", ["steane", "surface3"])
+def test_encoder_network_inference(tq, code):
+    """`syndrome_inference` on the encoder (Clifford) network -- labels of dimension 4 as bit pairs, gate
+    tensors as parity relations + sign tables -- through the sum-product executor (Steane: 14-bit frontier; 9-qubit
+    surface code: 18 bits on the global-memory executor), batched over syndromes, against brute-force enumeration of the
+    reference's network (all 4^n Pauli strings; rtol 1e-10).  Then the reference's own test flow in the Pauli frame
+    (test/decoding/inferenceswithencoder.jl:80-130): a single-qubit error -> measured syndrome -> inference ->
+    correction clears the syndrome and leaves no logical operator."""
+    from oracle import encoder_bruteforce as bf
+    from tensorqec.jl_b200 import encoder as E
+    t = tq.CSSTannerGraph(tq.SteaneCode() if code == "steane" else tq.SurfaceCode(3, 3))
+    n = t.stgx.nq
+    qc, data, b = E.encode_stabilizers(t)
+    measured = sorted(b.ordering[: b.matrix.shape[0]])
+    p = [[0.85, 0.05, 0.05, 0.05]] * n
+    ci = E.CompiledInference(qc, n, p, measured)
+    rng = np.random.default_rng(8)
+    syn = rng.integers(0, 2, size=(12, len(measured)), dtype=np.uint8)
+    syn[0] = 0
+    mar = ci.marginals(syn)
+    for bidx in (0, 1, 5, 11):
+        ref = bf.marginals(qc, n, p, {q: int(syn[bidx, i]) for i, q in enumerate(measured)})
+        for k in range(n):
+            assert np.allclose(mar[k][bidx], ref[k], rtol=MAR_RTOL, atol=1e-14), (k, bidx)
+    # the reference's flow: X (then Z, Y) on one qubit, syndromes from commutation with the code's generators
+    lx, lz = tq.logical_operator(t)
+    for q, pauli in ((3, 1), (n - 1, 3), (1, 2)):
+        ex = np.zeros(n, dtype=np.uint8)
+        ez = np.zeros(n, dtype=np.uint8)
+        ex[q], ez[q] = pauli in (1, 2), pauli in (2, 3)
+        sx, sz = gf2.css_syndrome(ex[None], ez[None], t.stgx.H, t.stgz.H)
+        outcome = 1 - 2 * np.concatenate([sx[0], sz[0]]).astype(int)            # +1 / -1 per generator (X-type first)
+        corr = E.inference(outcome, b, qc, p)
+        cx = np.array([int(a in (1, 2)) for a in corr], dtype=np.uint8)
+        cz = np.array([int(a in (2, 3)) for a in corr], dtype=np.uint8)
+        rsx, rsz = gf2.css_syndrome((ex ^ cx)[None], (ez ^ cz)[None], t.stgx.H, t.stgz.H)
+        assert not rsx.any() and not rsz.any()
+        assert not gf2.check_logical_error_css(ex[None], ez[None], cx[None], cz[None], lx, lz).any()
+
+
 def test_property_full_size_d9(tq):
     """BASELINE config 3 shape (d=9, p=0.05) at a size the oracle cannot follow shot by shot: size-independent
     properties -- every correction reproduces its syndrome, decoding is idempotent on its own output's syndrome,
