@@ -127,6 +127,8 @@ struct tqec_plan {
   int wd_full;            // the state arrays already take all the memory the executor may use
   void *d_hdr, *d_ints, *d_tables, *d_bp_off, *d_obs_slot;
   uint32_t *d_bp;        // back-pointer scratch: grid_max * bp_words
+  void *d_mc;            // scratch of the fused Monte-Carlo pipeline (tqec_mc_run), reused across calls
+  size_t mc_cap;
   // host staging for the host-pointer entry points
   void *d_io[4];
   size_t io_cap[4];

@@ -1199,6 +1199,7 @@ extern "C" int tqec_plan_destroy(tqec_plan *p) {
   cudaFree(p->d_tab_corr); cudaFree(p->d_tab_out); cudaFree(p->d_tab_arg);
   sweep_destroy(p);
   wide_destroy(p);
+  cudaFree(p->d_mc);
   for (int i = 0; i < 4; ++i) cudaFree(p->d_io[i]);
   if (p->stream) cudaStreamDestroy(p->stream);
   if (p->s_in) cudaStreamDestroy(p->s_in);

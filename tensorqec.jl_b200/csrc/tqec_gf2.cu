@@ -433,10 +433,22 @@ extern "C" int tqec_mc_run(const tqec_mc_desc *mc, uint64_t seed, int64_t shot_o
       rc = TQEC_ERR_CUDA;                                                                     \
     }                                                                                         \
   } while (0)
-  MC_TRY(cudaMalloc((void **)&d_err, (size_t)chunk * ew * 8));
-  MC_TRY(cudaMalloc((void **)&d_syn, (size_t)chunk * sw * 8));
-  MC_TRY(cudaMalloc((void **)&d_cor, (size_t)chunk * ew * 8));
-  MC_TRY(cudaMalloc((void **)&d_counts, 32));
+  // per-chunk scratch is owned by the plan and reused across calls (allocation used to cost more than a chunk's decode)
+  {
+    const size_t need = (size_t)chunk * (2 * ew + sw) * 8 + 64;
+    if (P->mc_cap < need) {
+      if (P->d_mc) cudaFree(P->d_mc);
+      P->d_mc = nullptr; P->mc_cap = 0;
+      MC_TRY(cudaMalloc(&P->d_mc, need));
+      if (rc == TQEC_OK) P->mc_cap = need;
+    }
+    if (rc == TQEC_OK) {
+      d_counts = (unsigned long long *)P->d_mc;
+      d_err = (uint64_t *)((char *)P->d_mc + 64);
+      d_syn = d_err + (size_t)chunk * ew;
+      d_cor = d_syn + (size_t)chunk * sw;
+    }
+  }
   MC_TRY(cudaMalloc((void **)&d_cls, (size_t)(mc->L->rows ? mc->L->rows : 1) * 4));
   MC_TRY(cudaEventCreate(&e0));
   MC_TRY(cudaEventCreate(&e1));
@@ -471,7 +483,7 @@ extern "C" int tqec_mc_run(const tqec_mc_desc *mc, uint64_t seed, int64_t shot_o
     counts[0] += (int64_t)h[0]; counts[1] += (int64_t)h[1]; counts[2] += (int64_t)h[2];
     counts[3] += mc->comm ? (int64_t)h[3] : n_shots;
   }
-  cudaFree(d_err); cudaFree(d_syn); cudaFree(d_cor); cudaFree(d_counts); cudaFree(d_cls); cudaFree(d_p);
+  cudaFree(d_cls); cudaFree(d_p);
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
   return rc;
