@@ -293,6 +293,17 @@ int tqec_table_create(int64_t n_entries, int32_t n_checks, int32_t n_vars, const
 int tqec_table_destroy(tqec_table *table);
 int tqec_table_decode(tqec_table *table, const uint64_t *synd, int64_t n_shots, uint64_t *corr_out, uint8_t *found_out);
 
+/* ---- belief propagation + OSD --------------------------------------------------------------- */
+/* The reference's BPDecoder (src/decoding/bposd.jl): tanh-rule sum-product on log-likelihood ratios, flooding schedule,
+ * messages clamped to [-10, 10], at most max_iter iterations, order-0 OSD when it does not converge (osd != 0).  The
+ * Tanner graph in CSR form: check s touches bits s_adj[s_ptr[s] .. s_ptr[s+1]); p[q] = flip probability of bit q.
+ * flags_out (may be NULL): bit 0 = BP converged, bit 1 = the pattern comes from OSD; 0 = neither (zero pattern). */
+typedef struct tqec_bp tqec_bp;
+int tqec_bp_create(int32_t n_bits, int32_t n_checks, const int32_t *s_ptr, const int32_t *s_adj, const double *p,
+                   int32_t max_iter, int32_t osd, int32_t device, tqec_bp **out);
+int tqec_bp_destroy(tqec_bp *bp);
+int tqec_bp_decode(tqec_bp *bp, const uint64_t *synd, int64_t n_shots, uint64_t *corr_out, uint8_t *flags_out);
+
 /* ---- sampling --------------------------------------------------------------------------------------------- */
 #define TQEC_MODEL_FLIP 0  /* IndependentFlipError: bit i flips iff u < p0[i]            (error_model.jl:69-71)  */
 #define TQEC_MODEL_DEPOL 1 /* IndependentDepolarizingError on n qubits: one u per qubit, Y tested first:

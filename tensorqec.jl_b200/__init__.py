@@ -16,6 +16,7 @@ from .decoding import (TNMAP, TNMMAP, AbstractDecoder, AbstractGeneralDecoder, C
 from .circuit import (StimCircuit, circuit_to_string, dem_to_string, detector_error_model, dump_stim_file, parse_stim_file,
                       parse_stim_string, surface_memory_circuit)
 from .dem import DetectorErrorModel, dem2tanner, parse_dem_file, parse_dem_string
+from .bposd import BPDecoder
 from .truthtable import TableDecoder, TruthTable, load_table, make_table, save_table
 from .encoder import (CompiledInference, CSSBimatrix, clifford_network, correction_pauli_string, encode_circuit, encode_stabilizers,
                       generate_syndrome_dict, inference, pauli_string_map_iter, stabilizers2bimatrix, syndrome_inference,

@@ -28,7 +28,7 @@ EXPORTS = [
     "tqec_lower", "tqec_lowered_destroy", "tqec_lowered_get", "tqec_plan_from_lowered", "tqec_plan_compile",
     "tqec_comm_unique_id", "tqec_comm_init", "tqec_comm_destroy", "tqec_comm_allreduce_counts",
     "tqec_decode_map_bytes", "tqec_decode_marginal_bytes", "tqec_dmma_peak", "tqec_decode_marginal_log2",
-    "tqec_table_create", "tqec_table_destroy", "tqec_table_decode",
+    "tqec_table_create", "tqec_table_destroy", "tqec_table_decode", "tqec_bp_create", "tqec_bp_destroy", "tqec_bp_decode",
 ]
 
 

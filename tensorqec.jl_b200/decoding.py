@@ -508,6 +508,9 @@ def compile(decoder: AbstractDecoder, problem, pvec: Optional[AbstractErrorModel
             t = problem.tanner
             tn = SimpleTensorNetwork([[i] for i in range(t.nq)], [np.array([1.0 - p, p]) for p in problem.pvec.p])
             return _compile_tnmap(decoder, GeneralDecodingProblem(t, tn))
+    from .bposd import BPDecoder, compile_bp
+    if isinstance(decoder, BPDecoder) and isinstance(problem, ClassicalDecodingProblem):
+        return compile_bp(decoder, problem)                                    # bposd.jl:30-35
     from .truthtable import TableDecoder, compile_table
     if isinstance(decoder, TableDecoder) and isinstance(problem, IndependentDepolarizingDecodingProblem):
         return compile_table(decoder, problem)                                 # truthtable.jl:205-208
@@ -541,6 +544,9 @@ def decode(first, *args):
         out = extract_decoding(ct.reduction, res.error_pattern)
         out.success_tag, out.logp = res.success_tag, res.logp
         return out
+    from .bposd import CompiledBP, decode_bp
+    if isinstance(ct, CompiledBP) and isinstance(syn, SimpleSyndrome):
+        return decode_bp(ct, syn)
     from .truthtable import CompiledTable, decode_table
     if isinstance(ct, CompiledTable) and isinstance(syn, CSSSyndrome):
         return decode_table(ct, syn)

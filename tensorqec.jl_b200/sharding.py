@@ -52,9 +52,21 @@ def library_comm(device: int):
         return None
     import torch
     from . import _cabi
+    import os
+    import sys
     box = [_cabi.Comm.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
-    return _cabi.Comm(world, rank, box[0], device)
+    # ncclCommInitRank prints a "NCCL version ..." banner on the C-level stdout of rank 0; callers (bench.py) promise a
+    # clean stdout, so the banner is sent to stderr
+    sys.stdout.flush()
+    saved = os.dup(1)
+    try:
+        os.dup2(2, 1)
+        comm = _cabi.Comm(world, rank, box[0], device)
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+    return comm
 
 
 def sharded_mc_run(mc, n_shots: int, seed: int = 0, chunk: int = 0, comm=None):

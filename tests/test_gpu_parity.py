@@ -725,6 +725,37 @@ def test_encoder_network_inference(tq, code):
         assert not gf2.check_logical_error_css(ex[None], ez[None], cx[None], cz[None], lx, lz).any()
 
 
+def test_bp_osd_decoder(tq):
+    """BPDecoder (bposd.jl) batched on the GPU against the numpy restatement of the reference's loops: the reference's own
+    example (test/decoding/bposd.jl:5-14), then the Z-check graph of the d = 5 surface code at p = 5 %: every returned
+    pattern reproduces its syndrome (OSD guarantees it), the BP-converged flags and the patterns agree with the oracle
+    (the tanh / atanh of the two implementations may differ in the last bit, hence a 99 % bar instead of equality)."""
+    from oracle import bposd as obp
+    tanner = tq.SimpleTannerGraph(7, [[0, 1, 2, 3], [1, 2, 4, 6], [2, 3, 4, 5]])
+    ct = tq.compile(tq.BPDecoder(), tanner)
+    e0 = np.array([1, 0, 0, 0, 0, 0, 0], dtype=np.uint8)
+    res = tq.decode(ct, tq.syndrome_extraction(e0, tanner))
+    assert res.success_tag and np.array_equal(res.error_pattern, e0)
+    t = tq.CSSTannerGraph(tq.SurfaceCode(5, 5)).stgz
+    em = tq.iid_error(0.05, 25)
+    ct = tq.compile(tq.BPDecoder(), t, em)
+    ep = tq.random_error_pattern(em, seed=4, shots=3000)
+    syn = tq.syndrome_extraction(ep, t)
+    res = tq.decode(ct, syn)
+    assert np.all(res.success_tag)
+    assert tq.syndrome_extraction(res.error_pattern, t) == syn
+    nobp = tq.decode(tq.compile(tq.BPDecoder(100, False), t, em), syn)
+    conv = np.asarray(nobp.success_tag)
+    assert 0.5 < conv.mean() < 1.0 and not nobp.error_pattern[~conv].any()
+    H = t.H.astype(np.uint8)
+    agree = same_flag = 0
+    for b in range(300):
+        ok, e, by_bp = obp.decode(H, t.s2q, t.q2s, em.p, syn.s[b])
+        agree += np.array_equal(e, res.error_pattern[b])
+        same_flag += bool(by_bp) == bool(conv[b])
+    assert agree >= 297 and same_flag >= 297
+
+
 def test_property_full_size_d9(tq):
     """BASELINE config 3 shape (d=9, p=0.05) at a size the oracle cannot follow shot by shot: size-independent
     properties -- every correction reproduces its syndrome, decoding is idempotent on its own output's syndrome,
