@@ -77,9 +77,40 @@ class MonteCarlo:
                             int(shots), chunk, comm)
 
 
-def multi_round_qec(tanner, decoder, em, tanner_check=None, *, rounds: int = 10, seed: int = 0, device=None):
+def _unfused_css(tanner, decoder, em, rounds, seed, reference_prior):
+    """Any other decoder the package compiles for a CSS code (TNMMAP, TableDecoder, ...): sample -> syndrome -> decode ->
+    check as separate batched calls (each on the GPU), in chunks."""
+    from .error_model import check_logical_error, random_error_pattern, syndrome_extraction
+    from .decoding import compile as _compile, decode as _decode
+    ct = _compile(decoder, tanner) if reference_prior else _compile(decoder, tanner, em)
+    lx, lz = logical_operator(tanner)
+    counts = np.zeros(4, dtype=np.int64)
+    chunk = 1 << 18
+    for lo in range(0, rounds, chunk):
+        nb = min(chunk, rounds - lo)
+        ep = random_error_pattern(em, seed=seed, shots=nb, shot_offset=lo)
+        res = _decode(ct, syndrome_extraction(ep, tanner))
+        fx = check_logical_error(ep.xerror, res.error_pattern.xerror, lz)
+        fz = check_logical_error(ep.zerror, res.error_pattern.zerror, lx)
+        counts += [int(fx.sum()), int(fz.sum()), int((fx | fz).sum()), nb]
+    return counts
+
+
+def multi_round_qec(tanner, decoder, em, tanner_check=None, *, rounds: int = 10, seed: int = 0, device=None,
+                    reference_prior: bool = False):
     """threshold.jl:1-19 -> (logical_xerror/rounds, logical_zerror/rounds, logical_error/rounds) for a CSS code;
-    threshold.jl:21-33 -> logical_xerror/rounds for a classical code checked against `tanner_check.H`."""
+    threshold.jl:21-33 -> logical_xerror/rounds for a classical code checked against `tanner_check.H`.
+    TNMAP runs the fused device pipeline (`tqec_mc_run`); any other decoder runs the same four stages as separate
+    batched calls.  The decoder is compiled for the sampling model `em`; `reference_prior=True` reproduces the
+    reference, which compiles with `iid_error(0.05)` whatever `em` is (threshold.jl:5: `compile(decoder, tanner)`)."""
+    if isinstance(tanner, CSSTannerGraph) and not isinstance(decoder, TNMAP):
+        counts = _unfused_css(tanner, decoder, em, rounds, seed, reference_prior)
+        return counts[0] / rounds, counts[1] / rounds, counts[2] / rounds
+    if reference_prior and isinstance(tanner, CSSTannerGraph):
+        mc = MonteCarlo(tanner, decoder, iid_error(0.05, tanner), device=device)
+        mc.model, mc.probs = _cabi.MODEL_DEPOL, [em.px, em.py, em.pz]     # sample from `em`, decode with the default prior
+        counts, _ = mc.run(rounds, seed)
+        return counts[0] / rounds, counts[1] / rounds, counts[2] / rounds
     if isinstance(tanner, CSSTannerGraph):
         counts, _ = MonteCarlo(tanner, decoder, em, device=device).run(rounds, seed)
         return counts[0] / rounds, counts[1] / rounds, counts[2] / rounds

@@ -756,6 +756,19 @@ def test_bp_osd_decoder(tq):
     assert agree >= 297 and same_flag >= 297
 
 
+def test_multi_round_qec_accepts_other_decoders(tq):
+    """threshold.jl:1-19 takes any decoder: TNMAP runs fused, TNMMAP / TableDecoder run the four stages as separate batched
+    calls on the same Philox shots, so the TNMAP and TNMMAP rates are close and the shots are identical."""
+    t = tq.CSSTannerGraph(tq.SurfaceCode(3, 3))
+    em = tq.iid_error(0.03, t)
+    a = tq.multi_round_qec(t, tq.TNMAP(), em, rounds=20000, seed=5)
+    b = tq.multi_round_qec(t, tq.TNMMAP(), em, rounds=20000, seed=5)
+    c = tq.multi_round_qec(t, tq.TableDecoder(2), em, rounds=20000, seed=5)
+    assert 0 < a[2] < 0.1 and abs(a[2] - b[2]) < 0.01 and c[2] >= a[2] - 0.01
+    r = tq.multi_round_qec(t, tq.TNMAP(), em, rounds=20000, seed=5, reference_prior=True)
+    assert abs(r[2] - a[2]) < 0.02                               # decoding with the default 5 % prior instead of 3 %
+
+
 def test_property_full_size_d9(tq):
     """BASELINE config 3 shape (d=9, p=0.05) at a size the oracle cannot follow shot by shot: size-independent
     properties -- every correction reproduces its syndrome, decoding is idempotent on its own output's syndrome,
