@@ -45,6 +45,23 @@ __device__ __forceinline__ uint32_t sw_xor3(uint32_t a, uint32_t b, uint32_t c) 
   asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
 }
+// ---- TMA (1-D bulk copy) of a tabulated head row into the team's state, completion on an mbarrier ----------------------------
+__device__ __forceinline__ void sw_mbar_init(uint32_t bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void sw_mbar_expect(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sw_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void sw_mbar_wait(uint32_t bar, uint32_t phase) {
+  asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+               ::"r"(bar), "r"(phase) : "memory");
+}
+
 // swizzled entry index: bits 4..7 XOR-ed into bits 0..3 (sweep.py:phys)
 __host__ __device__ __forceinline__ uint32_t sw_phys(uint32_t x) { return x ^ ((x >> 4) & 15u); }
 
@@ -197,6 +214,11 @@ k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, ui
   uint16_t *stab = reinterpret_cast<uint16_t *>(sh_syn + SG * P.nsw);
   double *st = reinterpret_cast<double *>(smem_raw + P.off_states + (size_t)8192 * warp);
   const uint32_t st_abs = (uint32_t)__cvta_generic_to_shared(st);
+  // head rows arrive by TMA when the table is stored pre-swizzled (W >= 8: the swizzle then stays inside one shot's row)
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(words + P.words_bytes - 16);
+  uint32_t bar_phase = 0;
+  if (P.head_tma && lane == 0) sw_mbar_init(bar);
+  __syncwarp();
   const int NF = 32 >> P.sg;                                     // forward passes per group of 32 shots
   const int64_t n_groups = (B + 31) / 32;
   const int64_t team = (int64_t)blockIdx.x * NW + warp, n_teams = (int64_t)gridDim.x * NW;
@@ -229,14 +251,30 @@ k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, ui
       }
       __syncwarp();
       // head: copy the tabulated state of the shots' head syndrome pattern
-      for (int sub = 0; sub < SG; ++sub) {
-        int hp = 0;
-        for (int j = 0; j < P.nh; ++j) {
-          const int b = P.head_bits[j];
-          hp |= (int)((sh_syn[sub * P.nsw + (b >> 6)] >> (b & 63)) & 1ull) << j;
+      if (P.head_tma) {
+        // one bulk copy (TMA) per shot: rows are stored in the state's swizzled order, so a row lands as it is
+        if (lane == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the state was last written by ordinary stores
+          sw_mbar_expect(bar, (uint32_t)(SG * NE * 8));
+          for (int sub = 0; sub < SG; ++sub) {
+            int hp = 0;
+            for (int j = 0; j < P.nh; ++j) {
+              const int b = P.head_bits[j];
+              hp |= (int)((sh_syn[sub * P.nsw + (b >> 6)] >> (b & 63)) & 1ull) << j;
+            }
+            sw_bulk_g2s(st_abs + (uint32_t)((sub << P.W) * 8), P.head_state + ((size_t)hp << P.W), (uint32_t)(NE * 8), bar);
+          }
         }
-        const double *src = P.head_state + ((size_t)hp << P.W);
-        for (int e = lane; e < NE; e += 32) st[sw_phys((uint32_t)(e | (sub << P.W)))] = __ldg(src + e);
+      } else {
+        for (int sub = 0; sub < SG; ++sub) {
+          int hp = 0;
+          for (int j = 0; j < P.nh; ++j) {
+            const int b = P.head_bits[j];
+            hp |= (int)((sh_syn[sub * P.nsw + (b >> 6)] >> (b & 63)) & 1ull) << j;
+          }
+          const double *src = P.head_state + ((size_t)hp << P.W);
+          for (int e = lane; e < NE; e += 32) st[sw_phys((uint32_t)(e | (sub << P.W)))] = __ldg(src + e);
+        }
       }
       // closed-bit address masks of every (super-step, shot)
       for (int idx = lane; idx < (P.n_ss << P.sg); idx += 32) {
@@ -254,6 +292,10 @@ k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, ui
           if ((sh_syn[sub * P.nsw + (sb >> 6)] >> (sb & 63)) & 1ull) lv = ((c >> 16) & 0x3fffu) | ((c >> 30) & 1u ? 0x8000u : 0x4000u);
         }
         stab[(P.n_ss << P.sg) + idx] = (uint16_t)lv;
+      }
+      if (P.head_tma) {                                          // the copy overlapped the mask computation above
+        sw_mbar_wait(bar, bar_phase);
+        bar_phase ^= 1u;
       }
       __syncwarp();
       uint32_t *bpf = bp + (size_t)f * P.bp_words * 32;
@@ -446,7 +488,16 @@ int sweep_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &pr
   if ((rc = sw_upload(&p->d_sw[1], s->tb, (size_t)s->n_ss * SW_TB_INTS))) return rc;
   if ((rc = sw_upload(&p->d_sw[2], s->lanetab, (size_t)s->n_ss * 32))) return rc;
   if ((rc = sw_upload(&p->d_sw[3], s->tvals, (size_t)s->n_tvals))) return rc;
-  if ((rc = sw_upload(&p->d_sw[4], s->head_state, nhp * ne))) return rc;
+  // W >= 8: the swizzle (index bits 4..7 into bits 0..3) stays inside one shot's row, so the rows are stored in the
+  // state's swizzled order and a row is fetched by one bulk copy (TMA); TQEC_SWEEP_NO_TMA=1 keeps the load / store loop
+  const bool head_tma = s->W >= 8 && std::getenv("TQEC_SWEEP_NO_TMA") == nullptr;
+  if (head_tma) {
+    std::vector<double> sw(nhp * ne);
+    for (size_t h = 0; h < nhp; ++h)
+      for (size_t e = 0; e < ne; ++e) sw[h * ne + sw_phys((uint32_t)e)] = s->head_state[h * ne + e];
+    if ((rc = sw_upload(&p->d_sw[4], sw.data(), nhp * ne))) return rc;
+  } else if ((rc = sw_upload(&p->d_sw[4], s->head_state, nhp * ne))) return rc;
+  D.head_tma = head_tma ? 1 : 0;
   if ((rc = sw_upload(&p->d_sw[5], s->head_cfg, d->semiring == TQEC_SEMIRING_MAXPLUS ? nhp * ne * ncw : (size_t)1))) return rc;
   D.rec = (const int32_t *)p->d_sw[0]; D.tb = (const int32_t *)p->d_sw[1]; D.lanetab = (const uint32_t *)p->d_sw[2];
   D.tvals = (const double *)p->d_sw[3]; D.head_state = (const double *)p->d_sw[4]; D.head_cfg = (const uint64_t *)p->d_sw[5];
@@ -457,7 +508,7 @@ int sweep_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &pr
   const size_t gap = (8192 - (size_t)reserved % 8192) % 8192;
   const size_t rec_b = ((size_t)s->n_ss * SW_REC_INTS * 4 + 15) & ~(size_t)15, lt_b = (size_t)s->n_ss * 128;
   const size_t tv_b = ((size_t)s->n_tvals * 8 + 15) & ~(size_t)15;
-  const size_t words_b = (((size_t)nsw << s->sg) * 8 + ((size_t)s->n_ss << s->sg) * 4 + 15) & ~(size_t)15;   // syndromes, early + late masks
+  const size_t words_b = ((((size_t)nsw << s->sg) * 8 + ((size_t)s->n_ss << s->sg) * 4 + 15) & ~(size_t)15) + 16;   // syndromes, early + late masks, mbarrier
   // register budget variant: 512 threads (128 registers), 640 (96) or 768 (80); TQEC_SWEEP_MAXT overrides the default
   int maxt = 512;
   if (const char *e = std::getenv("TQEC_SWEEP_MAXT")) { const int v = std::atoi(e); if (v == 768 || v == 640 || v == 512) maxt = v; }
