@@ -77,6 +77,7 @@ struct SweepDev {
   int32_t n_ss, W, sg, nh, nsw, ncw, bp_words, n_tvals, n_obs;
   int32_t sync_mode;                // CTA barrier between teams: 0 none, 1 per group of 32 shots, 2 per pass
   int32_t head_tma;                 // 1: head rows are stored pre-swizzled and fetched by cp.async.bulk (TMA)
+  int32_t grp;                      // shots per deferred-traceback group (2^sg .. 32): the back-pointer ring of a team holds this many
   int32_t off_states, off_rec, off_lanetab, off_tvals, off_words, words_bytes;   // shared-memory layout (bytes)
 };
 

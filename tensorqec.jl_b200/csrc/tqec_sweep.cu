@@ -219,8 +219,10 @@ k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, ui
   uint32_t bar_phase = 0;
   if (P.head_tma && lane == 0) sw_mbar_init(bar);
   __syncwarp();
-  const int NF = 32 >> P.sg;                                     // forward passes per group of 32 shots
-  const int64_t n_groups = (B + 31) / 32;
+  const int G = P.grp;                                           // shots per deferred-traceback group (lane q < G walks shot q)
+  const int NF = G >> P.sg;                                      // forward passes per group
+  const int64_t n_groups = (B + G - 1) / G;
+  const int sync_every = 32 / G;                                 // the CTA barrier stays at one per 32 shots
   const int64_t team = (int64_t)blockIdx.x * NW + warp, n_teams = (int64_t)gridDim.x * NW;
   uint32_t *bp = bp_all + (size_t)team * NF * P.bp_words * 32;
 
@@ -231,8 +233,8 @@ k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, ui
   for (int64_t rd = 0; rd < rounds; ++rd) {
     const int64_t g = team + rd * n_teams;
     const bool live = g < n_groups;
-    if (P.sync_mode == 1) __syncthreads();
-    const int64_t group0 = g * 32, myshot = group0 + lane;
+    if (P.sync_mode == 1 && rd % sync_every == 0) __syncthreads();
+    const int64_t group0 = g * G, myshot = lane < G ? group0 + lane : B;
     uint64_t syn[4] = {0ull, 0ull, 0ull, 0ull};
     if (live && myshot < B)
 #pragma unroll
@@ -339,7 +341,7 @@ k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, ui
     }
 
     // deferred traceback: lane q walks shot q of the group
-    if (SEMI == TQEC_SEMIRING_MAXPLUS && live) {
+    if (SEMI == TQEC_SEMIRING_MAXPLUS && live && lane < G) {
       const int f = lane >> P.sg, sub = lane & (SG - 1);
       const uint32_t *bpq = bp + (size_t)f * P.bp_words * 32;
       uint64_t cfg[4] = {0ull, 0ull, 0ull, 0ull};
@@ -414,8 +416,8 @@ k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, ui
 #pragma unroll
         for (int w = 0; w < 4; ++w)
           if (w < P.ncw) corr[myshot * P.ncw + w] = cfg[w] | __ldg(hc + w);
-      __syncwarp();
     }
+    __syncwarp();
   }
 }
 
@@ -426,7 +428,7 @@ static const void *sweep_kernel(int maxt) {
 
 int launch_sweep(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d_corr, double *d_out, int32_t *d_argmax,
                  cudaStream_t stream) {
-  const int64_t groups = (B + 31) / 32;
+  const int64_t groups = (B + plan->sw.grp - 1) / plan->sw.grp;
   const int64_t ctas = (groups + plan->sw_teams - 1) / plan->sw_teams;
   const int grid = (int)(ctas < plan->sm_count ? ctas : plan->sm_count);
   const void *kern = plan->semiring == TQEC_SEMIRING_MAXPLUS ? sweep_kernel<TQEC_SEMIRING_MAXPLUS>(plan->sw_maxt)
@@ -498,6 +500,10 @@ int sweep_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &pr
     if ((rc = sw_upload(&p->d_sw[4], sw.data(), nhp * ne))) return rc;
   } else if ((rc = sw_upload(&p->d_sw[4], s->head_state, nhp * ne))) return rc;
   D.head_tma = head_tma ? 1 : 0;
+  // shots per deferred-traceback group: 32 keeps every lane busy in the traceback; a smaller group shrinks the team's
+  // back-pointer ring (groups of 8: 87 MB at d = 9, L2 resident) at the price of idle lanes in the traceback
+  D.grp = 32;
+  if (const char *e = std::getenv("TQEC_SWEEP_GROUP")) { const int v = std::atoi(e); if ((v == 32 || v == 16 || v == 8 || v == 4 || v == 2) && v >= (1 << s->sg)) D.grp = v; }
   if ((rc = sw_upload(&p->d_sw[5], s->head_cfg, d->semiring == TQEC_SEMIRING_MAXPLUS ? nhp * ne * ncw : (size_t)1))) return rc;
   D.rec = (const int32_t *)p->d_sw[0]; D.tb = (const int32_t *)p->d_sw[1]; D.lanetab = (const uint32_t *)p->d_sw[2];
   D.tvals = (const double *)p->d_sw[3]; D.head_state = (const double *)p->d_sw[4]; D.head_cfg = (const uint64_t *)p->d_sw[5];
@@ -541,7 +547,7 @@ int sweep_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &pr
   D.off_words = (int32_t)offs[3]; D.words_bytes = (int32_t)words_b;
   p->sw_teams = nw; p->sw_smem = (int)total;
   TQEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
-  const size_t bp_bytes = (size_t)p->sm_count * nw * (32 >> s->sg) * D.bp_words * 32 * sizeof(uint32_t);
+  const size_t bp_bytes = (size_t)p->sm_count * nw * (D.grp >> s->sg) * D.bp_words * 32 * sizeof(uint32_t);
   cudaError_t e = cudaMalloc((void **)&p->d_sw_bp, bp_bytes);
   if (e != cudaSuccess) { set_error("cudaMalloc(%zu B sweep back-pointer scratch): %s", bp_bytes, cudaGetErrorString(e)); return TQEC_ERR_NOMEM; }
   p->has_sweep = 1;
