@@ -125,7 +125,18 @@ typedef struct {
   const double *tables;
   int64_t n_tables;
   const int32_t *obs_pos;  /* n_obs: position of observable i in the final index                  */
+  /* Optional second encoding of the passes made of rank-1 factors only (detector error models), executed by k_wide_bf
+   * as register butterflies (tqec_lower_wide.cpp:bf_encode_pass describes the blocks).  bf_off == NULL: none. */
+  const int32_t *bf_off;   /* n_pass: offset of the pass's block in bf_ints, or -1 (k_wide_pass runs the pass)   */
+  const int32_t *bf_ints;
+  int64_t n_bf_ints;
+  const double *bf_vals;   /* ratios r = t1 / t0: per group TQEC_BF_G unit steps, then its dependent steps */
+  int64_t n_bf_vals;
+  double bf_mant;          /* product of the t0 normalised away = bf_mant * 2^bf_log2; applied to the output when   */
+  int32_t bf_log2;         /* the butterfly passes are in use                                                     */
 } tqec_wide_desc;
+#define TQEC_BF_G 5            /* dimensions of a butterfly group: a thread holds 2^5 state entries in registers */
+#define TQEC_BF_GROUP_INTS 16  /* group record: n_free, dep0, n_dep, close0, n_closes, basis[5], zero mask, val0, -, order */
 
 typedef struct {
   int32_t semiring;        /* TQEC_SEMIRING_*                                                     */
@@ -229,7 +240,9 @@ enum {
   TQEC_LW_SW_HEAD_BITS = 11, TQEC_LW_SW_HEAD_STATE = 12 /* double */, TQEC_LW_SW_HEAD_CFG = 13 /* uint64 */,
   TQEC_LW_SW_OUT_INDEX = 14,
   TQEC_LW_WD_PASS_HDR = 15, TQEC_LW_WD_STEP_HDR = 16, TQEC_LW_WD_INTS = 17, TQEC_LW_WD_TABLES = 18 /* double */,
-  TQEC_LW_WD_OBS_POS = 19
+  TQEC_LW_WD_OBS_POS = 19,
+  TQEC_LW_WD_BF_OFF = 20, TQEC_LW_WD_BF_INTS = 21, TQEC_LW_WD_BF_VALS = 22 /* double */,
+  TQEC_LW_WD_BF_SCALE = 23 /* double[2]: bf_mant, bf_log2 */
 };
 int tqec_lowered_get(const tqec_lowered *lw, int32_t what, const void **data, int64_t *count);
 int tqec_plan_from_lowered(const tqec_lowered *lw, int32_t device, tqec_plan **out);

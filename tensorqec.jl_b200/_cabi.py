@@ -47,7 +47,10 @@ class SweepDesc(C.Structure):
 class WideDesc(C.Structure):
     _fields_ = [("n_pass", C.c_int32), ("n_steps", C.c_int32), ("w_cap", C.c_int32), ("t_max", C.c_int32),
                 ("pass_hdr", C.c_void_p), ("step_hdr", C.c_void_p), ("ints", C.c_void_p), ("n_ints", C.c_int64),
-                ("tables", C.c_void_p), ("n_tables", C.c_int64), ("obs_pos", C.c_void_p)]
+                ("tables", C.c_void_p), ("n_tables", C.c_int64), ("obs_pos", C.c_void_p),
+                # butterfly encoding of rank-1 passes: produced by the library's own lowering only (NULL from Python)
+                ("bf_off", C.c_void_p), ("bf_ints", C.c_void_p), ("n_bf_ints", C.c_int64), ("bf_vals", C.c_void_p),
+                ("n_bf_vals", C.c_int64), ("bf_mant", C.c_double), ("bf_log2", C.c_int32)]
 
 
 class PlanDesc(C.Structure):
@@ -71,9 +74,10 @@ COMPILE_NO_SWEEP, COMPILE_NO_FUSE, COMPILE_FORCE_WIDE, COMPILE_DYNAMIC_RESCALE =
 PLAN_DYNAMIC_RESCALE = 1
 (LW_META, LW_COST, LW_ORDER, LW_HDR, LW_INTS, LW_TABLES, LW_OBS_SLOT, LW_SW_REC, LW_SW_TB, LW_SW_LANETAB, LW_SW_TVALS,
  LW_SW_HEAD_BITS, LW_SW_HEAD_STATE, LW_SW_HEAD_CFG, LW_SW_OUT_INDEX, LW_WD_PASS_HDR, LW_WD_STEP_HDR, LW_WD_INTS,
- LW_WD_TABLES, LW_WD_OBS_POS) = range(20)
+ LW_WD_TABLES, LW_WD_OBS_POS, LW_WD_BF_OFF, LW_WD_BF_INTS, LW_WD_BF_VALS, LW_WD_BF_SCALE) = range(24)
 _LW_DTYPE = {LW_COST: np.float64, LW_TABLES: np.float64, LW_SW_TVALS: np.float64, LW_SW_HEAD_STATE: np.float64,
-             LW_SW_HEAD_CFG: np.uint64, LW_SW_LANETAB: np.uint32, LW_WD_TABLES: np.float64}
+             LW_SW_HEAD_CFG: np.uint64, LW_SW_LANETAB: np.uint32, LW_WD_TABLES: np.float64, LW_WD_BF_VALS: np.float64,
+             LW_WD_BF_SCALE: np.float64}
 
 
 class McDesc(C.Structure):

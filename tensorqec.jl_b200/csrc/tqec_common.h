@@ -87,6 +87,9 @@ struct WideDev {
   const double *tables;
   int32_t n_pass, n_steps, w_cap, t_max, n_obs, nsw;
   int32_t obs_pos[16];
+  const int32_t *bf_ints;   // butterfly encoding (k_wide_bf); bf_off is kept on the host (one launch per pass)
+  const double *bf_vals;
+  double out_mant;          // marginals are multiplied by this on the way out (1.0 unless butterfly passes are in use)
 };
 
 }  // namespace tqec
@@ -120,7 +123,9 @@ struct tqec_plan {
   // global-memory executor (optional): two state arrays of wd_batch << w_cap doubles, allocated at the first decode
   tqec::WideDev wd;
   int has_wide, wd_smem, wd_grid;
-  void *d_wd[4];
+  int wd_bf_smem, wd_bf_grid;      // k_wide_bf launch configuration (0: no butterfly passes)
+  int32_t *wd_bf_off;              // host, per pass: offset of its block in bf_ints or -1 (NULL: no butterfly passes)
+  void *d_wd[6];
   double *d_wd_state[2];
   unsigned long long *d_wd_max;   // dynamic rescaling: per-shot maxima of the last two passes
   int32_t *d_wd_exp;              // ... and per-shot accumulated exponents

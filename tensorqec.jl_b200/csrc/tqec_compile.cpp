@@ -21,7 +21,7 @@ struct tqec_lowered {
   SweepPlan sw;
   WidePlan wd;
   std::vector<int32_t> meta, order32, obs32, head_bits32, out_index32;
-  std::vector<double> cost;
+  std::vector<double> cost, bf_scale;
 };
 
 static int env_int(const char *name, int dflt) {
@@ -139,6 +139,7 @@ static void finish(tqec_lowered &L) {
     L.meta[1] = L.wd.n_steps; L.meta[2] = L.wd.w_peak; L.meta[3] = L.wd.log2_scale;
     L.meta[11] = L.wd.n_pass; L.meta[12] = L.wd.n_steps; L.meta[13] = L.wd.w_cap; L.meta[14] = L.wd.t_max;
     L.cost = {L.wd.cost, L.wd.bytes_per_shot};
+    L.bf_scale = {L.wd.bf_mant, (double)L.wd.bf_log2};
     L.order32.assign(L.wd.order.begin(), L.wd.order.end());
     L.obs32.assign(L.wd.obs_pos.begin(), L.wd.obs_pos.end());
   } else {
@@ -205,6 +206,10 @@ extern "C" int tqec_lowered_get(const tqec_lowered *L, int32_t what, const void 
     case TQEC_LW_WD_INTS: LW_RET(L->wd.ints);
     case TQEC_LW_WD_TABLES: LW_RET(L->wd.tables);
     case TQEC_LW_WD_OBS_POS: LW_RET(L->obs32);
+    case TQEC_LW_WD_BF_OFF: LW_RET(L->wd.bf_off);
+    case TQEC_LW_WD_BF_INTS: LW_RET(L->wd.bf_ints);
+    case TQEC_LW_WD_BF_VALS: LW_RET(L->wd.bf_vals);
+    case TQEC_LW_WD_BF_SCALE: LW_RET(L->bf_scale);
     default: break;
   }
 #undef LW_RET
@@ -227,6 +232,10 @@ extern "C" int tqec_plan_from_lowered(const tqec_lowered *L, int32_t device, tqe
     wd.ints = L->wd.ints.data(); wd.n_ints = (int64_t)L->wd.ints.size();
     wd.tables = L->wd.tables.data(); wd.n_tables = (int64_t)L->wd.tables.size();
     wd.obs_pos = L->obs32.data();
+    wd.bf_off = L->wd.bf_off.empty() ? nullptr : L->wd.bf_off.data();
+    wd.bf_ints = L->wd.bf_ints.data(); wd.n_bf_ints = (int64_t)L->wd.bf_ints.size();
+    wd.bf_vals = L->wd.bf_vals.data(); wd.n_bf_vals = (int64_t)L->wd.bf_vals.size();
+    wd.bf_mant = L->wd.bf_mant; wd.bf_log2 = L->wd.bf_log2;
     d.wide = &wd; d.w_max = L->wd.w_cap; d.log2_scale = L->wd.log2_scale;
   } else {
     d.n_steps = (int32_t)L->sch.steps.size(); d.w_max = L->sch.w_max;

@@ -71,6 +71,12 @@ struct WidePlan {
   double cost = 0.0, bytes_per_shot = 0.0;
   std::vector<int32_t> pass_hdr, step_hdr, ints;
   std::vector<double> tables;
+  // butterfly encoding of the passes k_wide_bf can run (tqec_lower_wide.cpp:bf_encode_pass): bf_off[pass] = offset of the
+  // pass's block in bf_ints or -1; the product of the normalised-away factor entries is bf_mant * 2^bf_log2
+  std::vector<int32_t> bf_off, bf_ints;
+  std::vector<double> bf_vals;
+  double bf_mant = 1.0;
+  int bf_log2 = 0;
 };
 
 struct Problem {

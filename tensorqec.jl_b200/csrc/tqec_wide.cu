@@ -292,6 +292,276 @@ __global__ void __launch_bounds__(NT) k_wide_pass(const WidePassArgs A) {
   }
 }
 
+// ---- butterfly passes (k_wide_bf) ------------------------------------------------------------------------------------------
+// Passes made of rank-1 factors only (the mechanisms of a detector error model) run here instead of k_wide_pass; the
+// encoding is produced by tqec_lower_wide.cpp:bf_encode_pass (read its header first).  Per tile:
+//   * the 2^t_in input entries arrive by cp.async (16 bytes per request, issued one tile ahead into the other half of a
+//     double buffer) at index = their tile-local index (input bit i sits at position i), swizzled by bf_phys; the rest of
+//     the 2^12 entries is zero-filled;
+//   * per GROUP a thread takes one coset of the group's TQEC_BF_G-dimensional span into 2^G registers (Gray-code walks:
+//     one XOR per address), zeroes the members the group record names (a reused position reopens), applies the G unit
+//     steps  v[k] += r v[k ^ (1 << j)]  (straight-line code, one FP64 FMA per entry and step; r = 0 for a padding
+//     dimension) and the dependent steps (switch on the coordinate vector), and writes the coset back: one shared-memory
+//     round trip and one barrier per group of typically five steps;
+//   * closed checks are not compacted away: the running mask XP (closed position x syndrome bit, in swizzled byte
+//     offsets) is XOR-ed into every address, so the live half of the tile is the one the addresses reach;
+//   * the 2^t_out surviving entries are gathered through the position of every output bit and stored.
+// All address components are XOR-linear byte offsets into the tile.
+#define BF_NT 128
+#define BF_NE (1 << TQEC_BF_G)
+#define BF_MAX_GROUPS 32
+#define BF_MAX_STEPS 96    /* dependent steps of a pass */
+#define BF_MAX_CLOSES 64
+#define BF_TILE_BYTES 32768
+
+struct WideBfArgs {
+  const double *gin;
+  double *gout;
+  const uint64_t *synd;
+  int64_t nb;
+  const int32_t *pass;       // the pass's header in pass_hdr (widths, tile masks)
+  const int32_t *bf;         // the pass's butterfly block
+  const double *vals;        // bf_vals
+  int32_t nsw, w_cap;
+  const unsigned long long *max_in;
+  unsigned long long *max_out;
+  int32_t *exps;
+};
+
+struct BfGroupS {
+  double r[TQEC_BF_G];               // ratios of the unit steps
+  uint32_t zmask;                    // coset members zeroed at the load
+  uint16_t orb_lo[16], orb_hi[16];   // swizzled byte offset of the coset representative: lo[i & 15] ^ hi[i >> 4]
+  uint16_t bP[8];                    // swizzled byte offsets of the basis vectors
+  int16_t n_free, dep0, n_dep, close0, n_closes, pad;
+};
+
+__host__ __device__ __forceinline__ uint32_t bf_phys(uint32_t x) { return x ^ ((x >> 4) & 14u); }
+__host__ __device__ constexpr int bf_ctz(int k) { return (k & 1) ? 0 : (k & 2) ? 1 : (k & 4) ? 2 : (k & 8) ? 3 : (k & 16) ? 4 : 5; }
+
+template <int C>
+__device__ __forceinline__ void bf_pair(double (&v)[BF_NE], const double r) {
+  constexpr int LOW = C & -C;
+#pragma unroll
+  for (int k = 0; k < BF_NE; ++k)
+    if (!(k & LOW)) {
+      const double a = v[k], b = v[k ^ C];
+      v[k] = fma(r, b, a);
+      v[k ^ C] = fma(r, a, b);
+    }
+}
+
+__device__ __forceinline__ void bf_cp_async16(uint32_t dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(BF_NT, 3) k_wide_bf(const WideBfArgs A) {
+  extern __shared__ __align__(16) unsigned char bf_dyn[];      // two tiles of 2^12 doubles
+  __shared__ uint32_t dep_in[128], dep_out[128];
+  __shared__ uint32_t sdep_in[288], sdep_out[288];         // deposit of the tile number's spectator part: 7 + 7 + 5 bits
+  __shared__ uint16_t tout[128];
+  __shared__ uint32_t s_xp[BF_MAX_GROUPS + 1];               // address mask of the closed checks before every group (per tile)
+  __shared__ BfGroupS grp[BF_MAX_GROUPS];
+  __shared__ double s_r[BF_MAX_STEPS];
+  __shared__ int32_t s_code[BF_MAX_STEPS];
+  __shared__ uint16_t s_closeP[BF_MAX_CLOSES], s_closeB[BF_MAX_CLOSES];
+  const int tid = threadIdx.x;
+  const int32_t *ph = A.pass, *bf = A.bf;
+  const int w_in = ph[TQEC_WP_WIN], w_out = ph[TQEC_WP_WOUT], t_in = ph[TQEC_WP_TIN], t_out = ph[TQEC_WP_TOUT];
+  const uint32_t tin = (uint32_t)ph[TQEC_WP_TINMASK], toutm = (uint32_t)ph[TQEC_WP_TOUTMASK];
+  const int n_groups = bf[0], n_dep = bf[1], n_closes = bf[2];
+  const int32_t *pout = bf + 8, *grec = bf + 20, *drec = grec + n_groups * TQEC_BF_GROUP_INTS, *crec = drec + n_dep;
+  {
+    const uint32_t x = tid < 64 ? (uint32_t)tid : ((uint32_t)(tid - 64) << 6);
+    dep_in[tid] = wd_pdep(x, tin);
+    dep_out[tid] = wd_pdep(x, toutm);
+    uint32_t idx = 0;
+    for (int i = 0; i < 12; ++i)
+      if (((x >> i) & 1u) && pout[i] >= 0) idx |= 1u << pout[i];
+    tout[tid] = (uint16_t)(bf_phys(idx) << 3);
+  }
+  for (int g = tid; g < n_groups; g += BF_NT) {
+    const int32_t *rec = grec + g * TQEC_BF_GROUP_INTS;
+    BfGroupS &G = grp[g];
+    G.n_free = (int16_t)rec[0]; G.dep0 = (int16_t)rec[1]; G.n_dep = (int16_t)rec[2]; G.close0 = (int16_t)rec[3]; G.n_closes = (int16_t)rec[4];
+    G.zmask = (uint32_t)rec[10];
+    for (int j = 0; j < TQEC_BF_G; ++j) G.r[j] = A.vals[rec[11] + j];
+    for (int i = 0; i < rec[2]; ++i) s_r[rec[1] + i] = A.vals[rec[11] + TQEC_BF_G + i];
+    const uint32_t ord = (uint32_t)rec[13];
+    for (int i = 0; i < 16; ++i) {
+      uint32_t lo = 0, hi = 0;
+      for (int b = 0; b < 4; ++b) {
+        if (((i >> b) & 1) && b < rec[0]) lo |= 1u << ((ord >> (4 * b)) & 15u);
+        if (((i >> b) & 1) && b + 4 < rec[0]) hi |= 1u << ((ord >> (4 * (b + 4))) & 15u);
+      }
+      G.orb_lo[i] = (uint16_t)(bf_phys(lo) << 3);
+      G.orb_hi[i] = (uint16_t)(bf_phys(hi) << 3);
+    }
+    for (int j = 0; j < 8; ++j) G.bP[j] = j < TQEC_BF_G ? (uint16_t)(bf_phys((uint32_t)rec[5 + j]) << 3) : (uint16_t)0;
+  }
+  for (int i = tid; i < n_dep; i += BF_NT) s_code[i] = drec[i];
+  for (int i = tid; i < n_closes; i += BF_NT) {
+    s_closeP[i] = (uint16_t)(bf_phys(1u << crec[2 * i]) << 3);
+    s_closeB[i] = (uint16_t)crec[2 * i + 1];
+  }
+  const int n_spec = w_in - t_in;
+  const uint32_t spec_in = (w_in >= 32 ? 0xffffffffu : ((1u << w_in) - 1u)) & ~tin;
+  const uint32_t spec_out = (w_out >= 32 ? 0xffffffffu : ((1u << w_out) - 1u)) & ~toutm;
+  for (int i = tid; i < 288; i += BF_NT) {
+    const uint32_t x = (uint32_t)(i & 127) << (7 * (i >> 7));
+    sdep_in[i] = wd_pdep(x, spec_in);
+    sdep_out[i] = wd_pdep(x, spec_out);
+  }
+  const int64_t n_tiles = A.nb << n_spec;
+  const int n_in = 1 << t_in, n_out = 1 << t_out;
+  const uint32_t dyn_abs = (uint32_t)__cvta_generic_to_shared(bf_dyn);
+  const bool pairs = (tin & 1u) != 0;                            // tile bit 0 = index bit 0: entries come in 16-byte pairs
+  const bool out_pairs = (toutm & 1u) != 0 && pout[0] == 0 && t_out >= 1;
+  __syncthreads();
+
+  // tile -> buffer `which`: asynchronous copies of the input entries, zeros everywhere else
+  auto fetch = [&](int64_t tile, int which) {
+    const int64_t b = tile >> n_spec;
+    const uint32_t sp = (uint32_t)(tile & (((int64_t)1 << n_spec) - 1));
+    const double *gi = A.gin + ((size_t)b << A.w_cap) + (sdep_in[sp & 127] | sdep_in[128 + ((sp >> 7) & 127)] | sdep_in[256 + (sp >> 14)]);
+    unsigned char *Sb = bf_dyn + which * BF_TILE_BYTES;
+    const uint32_t sabs = dyn_abs + (uint32_t)(which * BF_TILE_BYTES);
+    if (pairs) {
+#pragma unroll 4
+      for (int q = tid; q < (n_in >> 1); q += BF_NT) {
+        const int l = q << 1;
+        bf_cp_async16(sabs + (bf_phys((uint32_t)l) << 3), gi + (dep_in[l & 63] | dep_in[64 + (l >> 6)]));
+      }
+    } else {
+      for (int l = tid; l < n_in; l += BF_NT)
+        *reinterpret_cast<double *>(Sb + (bf_phys((uint32_t)l) << 3)) = __ldcs(gi + (dep_in[l & 63] | dep_in[64 + (l >> 6)]));
+    }
+    for (int q = ((n_in + 1) >> 1) + tid; q < 2048; q += BF_NT)   // (a tile of one entry: its odd neighbour is zeroed below)
+      *reinterpret_cast<double2 *>(Sb + (bf_phys((uint32_t)(q << 1)) << 3)) = make_double2(0.0, 0.0);
+    if (n_in == 1 && tid == 0) *reinterpret_cast<double *>(Sb + 8) = 0.0;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int which = 0;
+  if ((int64_t)blockIdx.x < n_tiles) fetch(blockIdx.x, 0);
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, which ^= 1) {
+    const int64_t b = tile >> n_spec;
+    const uint32_t sp = (uint32_t)(tile & (((int64_t)1 << n_spec) - 1));
+    double *go = A.gout + ((size_t)b << A.w_cap) + (sdep_out[sp & 127] | sdep_out[128 + ((sp >> 7) & 127)] | sdep_out[256 + (sp >> 14)]);
+    const uint64_t *syn = A.synd + (size_t)b * A.nsw;
+    unsigned char *Sb = bf_dyn + which * BF_TILE_BYTES;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                             // this tile has landed; everyone is done with the other buffer
+    if (tid <= n_groups) {                                       // address masks of the shot's closed checks (read after the first group's barrier)
+      const int upto = tid < n_groups ? grp[tid].close0 : n_closes;
+      uint32_t x = 0;
+      for (int c = 0; c < upto; ++c) {
+        const int sb = s_closeB[c];
+        if ((__ldg(syn + (sb >> 6)) >> (sb & 63)) & 1ull) x ^= (uint32_t)s_closeP[c];
+      }
+      s_xp[tid] = x;
+    }
+    if (tile + gridDim.x < n_tiles) fetch(tile + gridDim.x, which ^ 1);
+    if (A.max_in) {                                              // dynamic rescaling, as in k_wide_pass
+      const double mx = __longlong_as_double((long long)A.max_in[b]);
+      if (mx > 0.0 && mx < 4.909093465297727e-91) {
+        const int k = -ilogb(mx);
+        const double scale = ldexp(1.0, k);
+        if (sp == 0 && tid == 0) A.exps[b] -= k;
+        for (int l = tid; l < n_in; l += BF_NT) *reinterpret_cast<double *>(Sb + (bf_phys((uint32_t)l) << 3)) *= scale;
+        __syncthreads();
+      }
+    }
+    uint32_t XP = 0;
+    for (int g = 0; g < n_groups; ++g) {
+      const BfGroupS &G = grp[g];
+      const int n_orb = 1 << G.n_free;
+      uint32_t bP[TQEC_BF_G];
+#pragma unroll
+      for (int j = 0; j < TQEC_BF_G; ++j) bP[j] = G.bP[j];
+      for (int i = tid; i < n_orb; i += BF_NT) {
+        const uint32_t base = ((uint32_t)G.orb_lo[i & 15] ^ (uint32_t)G.orb_hi[i >> 4]) ^ XP;
+        double v[BF_NE];
+        // addresses: four independent Gray-code walks over the three low coordinates, one per value of the two high ones
+        uint32_t offs[4] = {base, base ^ bP[3], base ^ bP[4], base ^ bP[3] ^ bP[4]};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int gk = k ^ (k >> 1);
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            if (k) offs[h] ^= bP[bf_ctz(k)];
+            v[gk | (h << 3)] = *reinterpret_cast<const double *>(Sb + offs[h]);
+          }
+        }
+        const uint32_t Z = G.zmask;
+        if (Z) {                                                 // a reused position reopens: its dead half holds stale entries
+#pragma unroll
+          for (int k = 0; k < BF_NE; ++k)
+            if ((Z >> k) & 1u) v[k] = 0.0;
+        }
+        bf_pair<1>(v, G.r[0]);
+        bf_pair<2>(v, G.r[1]);
+        bf_pair<4>(v, G.r[2]);
+        bf_pair<8>(v, G.r[3]);
+        bf_pair<16>(v, G.r[4]);
+        for (int s = G.dep0; s < G.dep0 + G.n_dep; ++s) {
+          const double r = s_r[s];
+          switch (s_code[s]) {
+#define BF_CASE(C) case C: bf_pair<C>(v, r); break;
+            BF_CASE(1) BF_CASE(2) BF_CASE(3) BF_CASE(4) BF_CASE(5) BF_CASE(6) BF_CASE(7) BF_CASE(8) BF_CASE(9) BF_CASE(10)
+            BF_CASE(11) BF_CASE(12) BF_CASE(13) BF_CASE(14) BF_CASE(15) BF_CASE(16) BF_CASE(17) BF_CASE(18) BF_CASE(19)
+            BF_CASE(20) BF_CASE(21) BF_CASE(22) BF_CASE(23) BF_CASE(24) BF_CASE(25) BF_CASE(26) BF_CASE(27) BF_CASE(28)
+            BF_CASE(29) BF_CASE(30) BF_CASE(31)
+#undef BF_CASE
+            default: break;
+          }
+        }
+        // the walks ended at Gray code 4 (k = 7); walk back
+#pragma unroll
+        for (int k = 7; k >= 0; --k) {
+          const int gk = k ^ (k >> 1);
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            *reinterpret_cast<double *>(Sb + offs[h]) = v[gk | (h << 3)];
+            if (k) offs[h] ^= bP[bf_ctz(k)];
+          }
+        }
+      }
+      __syncthreads();
+      XP = s_xp[g + 1];
+    }
+    if (A.max_out) {
+      double tmax = 0.0;
+      for (int l = tid; l < n_out; l += BF_NT) {
+        const uint32_t off = ((uint32_t)tout[l & 63] ^ (uint32_t)tout[64 + (l >> 6)]) ^ XP;
+        const double v = *reinterpret_cast<const double *>(Sb + off);
+        __stcs(go + (dep_out[l & 63] | dep_out[64 + (l >> 6)]), v);
+        tmax = fmax(tmax, v);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+      if ((tid & 31) == 0 && tmax > 0.0) atomicMax(A.max_out + b, (unsigned long long)__double_as_longlong(tmax));
+    } else if (out_pairs) {
+      // output bit 0 is index bit 0 and sits at position 0: neighbours in the state are neighbours in the tile (swapped when
+      // the closed checks flipped position 0)
+#pragma unroll 4
+      for (int q = tid; q < (n_out >> 1); q += BF_NT) {
+        const int l = q << 1;
+        const uint32_t off = ((uint32_t)tout[l & 63] ^ (uint32_t)tout[64 + (l >> 6)]) ^ XP;
+        double2 x = *reinterpret_cast<const double2 *>(Sb + (off & ~8u));
+        if (off & 8u) { const double t = x.x; x.x = x.y; x.y = t; }
+        __stcs(reinterpret_cast<double2 *>(go + (dep_out[l & 63] | dep_out[64 + (l >> 6)])), x);
+      }
+    } else {
+#pragma unroll 4
+      for (int l = tid; l < n_out; l += BF_NT) {
+        const uint32_t off = ((uint32_t)tout[l & 63] ^ (uint32_t)tout[64 + (l >> 6)]) ^ XP;
+        __stcs(go + (dep_out[l & 63] | dep_out[64 + (l >> 6)]), *reinterpret_cast<const double *>(Sb + off));
+      }
+    }
+  }
+}
+
 __global__ void k_wide_init(double *g, int64_t nb, int w_cap, unsigned long long *mx, int32_t *exps) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nb) {
@@ -311,7 +581,7 @@ __global__ void k_wide_out(const WideDev P, const double *__restrict__ g, int64_
   for (int idx = 0; idx < NO; ++idx) {
     uint32_t src = 0;
     for (int o = 0; o < P.n_obs; ++o) src |= ((uint32_t)(idx >> o) & 1u) << P.obs_pos[o];
-    const double v = g[((size_t)b << P.w_cap) + src];
+    const double v = g[((size_t)b << P.w_cap) + src] * P.out_mant;
     // with a separate exponent output the mantissas are returned as they are; otherwise the exponent is applied here
     // (values below the FP64 range flush to zero, like the reference's; the argmax is taken on the mantissas)
     out[b * NO + idx] = (exps && !log2_out) ? ldexp(v, exps[b]) : v;
@@ -340,7 +610,8 @@ static int wd_upload(void **slot, const T *src, size_t n) {
 }
 
 void wide_destroy(tqec_plan *p) {
-  for (int i = 0; i < 4; ++i) if (p->d_wd[i]) cudaFree(p->d_wd[i]);
+  for (int i = 0; i < 6; ++i) if (p->d_wd[i]) cudaFree(p->d_wd[i]);
+  if (p->wd_bf_off) { std::free(p->wd_bf_off); p->wd_bf_off = nullptr; }
   for (int i = 0; i < 2; ++i) if (p->d_wd_state[i]) cudaFree(p->d_wd_state[i]);
   if (p->d_wd_max) cudaFree(p->d_wd_max);
   if (p->d_wd_exp) cudaFree(p->d_wd_exp);
@@ -420,6 +691,56 @@ int wide_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &pro
   if ((rc = wd_upload(&p->d_wd[3], w->tables, (size_t)w->n_tables))) return rc;
   D.pass_hdr = (const int32_t *)p->d_wd[0]; D.step_hdr = (const int32_t *)p->d_wd[1]; D.ints = (const int32_t *)p->d_wd[2];
   D.tables = (const double *)p->d_wd[3];
+  // butterfly encoding of the rank-1 passes (TQEC_WIDE_NO_BF=1 keeps every pass on k_wide_pass)
+  D.out_mant = 1.0;
+  p->wd_bf_off = nullptr; p->wd_bf_grid = 0;
+  if (w->bf_off && w->bf_ints && w->bf_vals && std::getenv("TQEC_WIDE_NO_BF") == nullptr) {
+    bool any = false;
+    for (int i = 0; i < w->n_pass; ++i) {
+      const int32_t o = w->bf_off[i];
+      if (o < 0) continue;
+      any = true;
+      TQEC_REQUIRE((int64_t)o + 20 <= w->n_bf_ints, "wide: butterfly block of pass %d out of range", i);
+      const int32_t *bfp = w->bf_ints + o;
+      const int ng = bfp[0], ns = bfp[1], nc = bfp[2];
+      TQEC_REQUIRE(ng >= 1 && ng <= BF_MAX_GROUPS && ns >= 0 && ns <= BF_MAX_STEPS && nc >= 0 && nc <= BF_MAX_CLOSES && bfp[4] <= 12 &&
+                       bfp[7] == TQEC_BF_G &&
+                       (int64_t)o + 20 + (int64_t)ng * TQEC_BF_GROUP_INTS + ns + 2 * (int64_t)nc <= w->n_bf_ints,
+                   "wide: bad butterfly block for pass %d", i);
+      const int32_t *h = w->pass_hdr + (size_t)i * TQEC_WIDE_PASS_INTS;
+      TQEC_REQUIRE(h[TQEC_WP_TIN] <= 12 && h[TQEC_WP_TOUT] <= 12 && bfp[5] == h[TQEC_WP_TIN] && bfp[6] == h[TQEC_WP_TOUT],
+                   "wide: butterfly block of pass %d does not match its header", i);
+      const int32_t *grec = bfp + 20, *crec = grec + ng * TQEC_BF_GROUP_INTS + ns;
+      int s_sum = 0, c_sum = 0;
+      for (int g = 0; g < ng; ++g) {
+        const int32_t *r = grec + g * TQEC_BF_GROUP_INTS;
+        TQEC_REQUIRE(r[0] >= 0 && r[0] <= 8 && r[1] == s_sum && r[2] >= 0 && r[3] == c_sum && r[4] >= 0 && r[11] >= 0 &&
+                         (int64_t)r[11] + TQEC_BF_G + r[2] <= w->n_bf_vals,
+                     "wide: bad butterfly group %d of pass %d", g, i);
+        for (int j = 0; j < TQEC_BF_G; ++j) TQEC_REQUIRE(r[5 + j] > 0 && r[5 + j] < 4096, "wide: bad basis vector in pass %d", i);
+        s_sum += r[2]; c_sum += r[4];
+      }
+      TQEC_REQUIRE(s_sum == ns && c_sum == nc, "wide: butterfly groups of pass %d do not cover its steps", i);
+      for (int q = 0; q < ns; ++q) TQEC_REQUIRE(crec[q - ns] > 0 && crec[q - ns] < (1 << TQEC_BF_G), "wide: bad dependent step in pass %d", i);
+      for (int c = 0; c < nc; ++c)
+        TQEC_REQUIRE(crec[2 * c] >= 0 && crec[2 * c] < 12 && crec[2 * c + 1] >= 0 && crec[2 * c + 1] < d->n_checks, "wide: bad close record in pass %d", i);
+    }
+    if (any) {
+      if ((rc = wd_upload(&p->d_wd[4], w->bf_ints, (size_t)w->n_bf_ints))) return rc;
+      if ((rc = wd_upload(&p->d_wd[5], w->bf_vals, (size_t)w->n_bf_vals))) return rc;
+      D.bf_ints = (const int32_t *)p->d_wd[4]; D.bf_vals = (const double *)p->d_wd[5];
+      p->wd_bf_off = (int32_t *)std::malloc(sizeof(int32_t) * (size_t)w->n_pass);
+      std::memcpy(p->wd_bf_off, w->bf_off, sizeof(int32_t) * (size_t)w->n_pass);
+      D.out_mant = w->bf_mant;
+      p->log2_scale += w->bf_log2;
+      int per_sm_bf = 0;
+      TQEC_CUDA(cudaFuncSetAttribute(k_wide_bf, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * BF_TILE_BYTES));
+      TQEC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_bf, k_wide_bf, BF_NT, 2 * BF_TILE_BYTES));
+      if (per_sm_bf < 1) per_sm_bf = 1;
+      if (const char *e = std::getenv("TQEC_WIDE_BF_CTAS")) { const int v = std::atoi(e); if (v >= 1 && v < per_sm_bf) per_sm_bf = v; }
+      p->wd_bf_grid = per_sm_bf * p->sm_count;
+    }
+  }
   p->wd_smem = (int)smem;
   TQEC_CUDA(cudaFuncSetAttribute(k_wide_pass<WD_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
@@ -505,6 +826,13 @@ int launch_wide(tqec_plan *plan, const uint64_t *d_synd, int64_t B, double *d_ou
       if (dyn) TQEC_CUDA(cudaMemsetAsync(mx[cur ^ 1], 0, (size_t)nb * sizeof(unsigned long long), stream));
       // tiles of the pass: the host copy of the header is not kept, so size the grid for the widest case and let the
       // kernel's tile loop run short
+      if (plan->wd_bf_off && plan->wd_bf_off[i] >= 0) {
+        WideBfArgs Bf;
+        Bf.gin = A.gin; Bf.gout = A.gout; Bf.synd = A.synd; Bf.nb = nb; Bf.pass = A.pass;
+        Bf.bf = D.bf_ints + plan->wd_bf_off[i]; Bf.vals = D.bf_vals; Bf.nsw = D.nsw; Bf.w_cap = D.w_cap;
+        Bf.max_in = A.max_in; Bf.max_out = A.max_out; Bf.exps = A.exps;
+        k_wide_bf<<<plan->wd_bf_grid, BF_NT, 2 * BF_TILE_BYTES, stream>>>(Bf);
+      } else
       k_wide_pass<WD_THREADS><<<plan->wd_grid, WD_THREADS, plan->wd_smem, stream>>>(A);
       cur ^= 1;
       plan->launches += 1;

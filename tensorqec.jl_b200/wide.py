@@ -212,8 +212,8 @@ def lower_wide(factors: Sequence[S.Factor], checks: Sequence[S.Check], semiring:
         peak = w
         for t in range(t0, t1):
             _, touched, opened, closing = roles[t]
+            peak = max(peak, w + len(opened))                     # opened checks coexist with the ones this step closes
             w = w + len(opened) - len(closing)
-            peak = max(peak, w)
             if w + len(closing) > S.MAX_WIDE_WIDTH:
                 return None
         if peak > t_max:
@@ -242,6 +242,14 @@ def lower_wide(factors: Sequence[S.Factor], checks: Sequence[S.Check], semiring:
         if best is None:
             raise ValueError(f"wide lowering: step {t} alone needs more than {t_max} tile bits")
         t1, (tile, gout, peak) = best
+        # spare tile bits go to the lowest untouched spectators: larger tiles, longer contiguous runs in HBM
+        room = t_max - peak
+        for c in glive:
+            if room <= 0:
+                break
+            if c not in tile:
+                tile.add(c)
+                room -= 1
         tin_mask = sum(1 << k for k, c in enumerate(glive) if c in tile)
         tout_mask = sum(1 << k for k, c in enumerate(gout) if c in tile)
         L = [c for c in glive if c in tile]
