@@ -67,3 +67,32 @@ def test_spectral_order_narrows_the_3d_detector_graph():
     assert best <= 29
     wp = W.lower_wide(factors, checks, S.SUMPROD, ne, nd, no, order=min(S.spectral_orders(sim), key=lambda o: S._evaluate(o, sim)))
     assert wp.w_cap <= 29 and wp.bytes_per_shot < 1.2e11
+
+
+@pytest.mark.parametrize("t_max", [12, 9, 7])
+def test_butterfly_encoding_of_the_library_lowering_matches_recurrence(t_max):
+    """The library's own lowering (C++) adds a butterfly encoding to every pass made of rank-1 factors (k_wide_bf): fixed
+    positions, closed checks folded into the addresses, cosets of 2^5 entries, ratios r = t1 / t0 with the product of the
+    t0 in the output scale.  The emulator executes those tables the way the kernel does; against the recurrence oracle
+    and against the same plan's generic tables (k_wide_pass)."""
+    from tensorqec.jl_b200 import _cabi
+    txt = tq.surface_memory_circuit(3, 3, "Z", 0.01, 0.01, 0.01, 0.01)
+    dem = tq.detector_error_model(tq.parse_stim_string(txt))
+    factors, checks, ne, nd, no, tanner = _dem_graph(dem)
+    lw = _cabi.Lowered(_cabi.Problem(factors, checks, S.SUMPROD, ne, nd, no, flags=_cabi.COMPILE_FORCE_WIDE, wide_t_max=t_max))
+    off = lw.get(_cabi.LW_WD_BF_OFF)
+    assert len(off) == lw.meta["n_pass"] and (off >= 0).all(), "every pass of a detector error model is a butterfly pass"
+    bi = lw.get(_cabi.LW_WD_BF_INTS)
+    if t_max == 7:
+        zs = [int(bi[o + 20 + 16 * g + 10]) for o in off for g in range(int(bi[o]))]
+        assert any(zs), "no position is reused: the zeroing of reopened positions is not exercised"
+    rng = np.random.RandomState(7)
+    e = (rng.rand(6, ne) < np.array(dem.error_rates) * 8).astype(np.uint8)
+    syn = (e @ tanner.H.T.astype(np.int64)) % 2
+    got = wide_emulator.run_lowered(lw, no, syn, butterfly=True)
+    generic = wide_emulator.run_lowered(lw, no, syn, butterfly=False)
+    order = [int(i) for i in lw.get(_cabi.LW_ORDER)]
+    merged = S.merge_overlapping(list(factors), ne, {v for c in checks for v in c.vars}, allow_negative=True)
+    ref = frontier.run(merged, checks, order, 1, syn, ne)
+    assert np.allclose(generic, ref, rtol=1e-13, atol=0)
+    assert np.allclose(got, ref, rtol=1e-12, atol=0)
