@@ -34,14 +34,18 @@ def time_marginal(plan, words, reps=3):
 
 def main():
     cases = [("circuit d=3x3", tq.detector_error_model(tq.parse_stim_string(tq.surface_memory_circuit(3, 3, "Z", 1e-3, 1e-3, 1e-3, 1e-3))), 100_000),
-             ("phenom d=5x5", tq.parse_dem_file(os.path.join(ROOT, "tests", "golden", "surface_d5_r5_phenom.dem")), 100_000)]
+             ("phenom d=5x5", tq.parse_dem_file(os.path.join(ROOT, "tests", "golden", "surface_d5_r5_phenom.dem")), 100_000),
+             ("phenom d=3x3", tq.parse_dem_file(os.path.join(ROOT, "tests", "golden", "surface_d3_r3_phenom.dem")), 1_000_000),
+             ("colour d=3 r=2", tq.parse_dem_file(os.path.join(ROOT, "tests", "golden", "color_memory_xyz_d3_r2.dem")), 1_000_000)]
     for name, dem, B in cases:
         ref = None
         for path in ("on-chip", "wide"):
+            os.environ["TQEC_SUMPROD_ONCHIP_WIDTH"] = "13"        # "on-chip": never the global-memory executor below 14 bits
             if path == "wide":
                 os.environ["TQEC_FORCE_WIDE"] = "1"
             ct = tq.compile(tq.TNMMAP(table_bits=0), dem)
             os.environ.pop("TQEC_FORCE_WIDE", None)
+            os.environ.pop("TQEC_SUMPROD_ONCHIP_WIDTH", None)
             ep = _cabi.sample_errors(_cabi.MODEL_FLIP, [np.asarray(dem.error_rates)], 3, 0, B)
             syn = _cabi.GF2Matrix(ct.tanner.H).apply(ep)
             ms, mar = time_marginal(ct.plan, syn)

@@ -11,7 +11,9 @@ want = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__block
         'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'smsp__warps_active.avg.per_cycle_active', 'smsp__warps_eligible.avg.per_cycle_active', 'sm__cycles_elapsed.avg',
-        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__inst_executed_pipe_fp64.sum', 'dram__throughput.avg.pct_of_peak_sustained_elapsed']
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__inst_executed_pipe_fp64.sum', 'dram__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active']
 print("metric,unit,value")
 for w in want:
     if w in m: print(f"{w},{m[w][1]},{m[w][0]}")

@@ -392,6 +392,10 @@ WidePlan lower_wide(const std::vector<Factor> &factors_in, const std::vector<Che
     return so;
   };
 
+  // plans made of rank-1 factors only (detector error models) keep a pass within what one butterfly block holds
+  bool all_rank1 = true;
+  for (auto &f : factors) all_rank1 = all_rank1 && f.vars.size() == 1;
+  const int max_pass_steps = all_rank1 ? 96 : MAX_PASS_STEPS;
   WidePlan P;
   P.semiring = semiring; P.n_vars = n_vars; P.n_checks = n_checks; P.n_obs = n_obs; P.t_max = t_max;
   std::vector<int> glive;
@@ -402,7 +406,7 @@ WidePlan lower_wide(const std::vector<Factor> &factors_in, const std::vector<Che
     int best_t1 = 0;
     SimOut best;
     for (int lb = low_bits; lb >= 0 && !have; --lb) {
-      for (int t1 = t + 1; t1 <= std::min(n, t + MAX_PASS_STEPS); ++t1) {
+      for (int t1 = t + 1; t1 <= std::min(n, t + max_pass_steps); ++t1) {
         SimOut r = simulate(t, t1, glive, lb);
         if (!r.ok) break;
         best = r; best_t1 = t1; have = true;

@@ -271,9 +271,9 @@ def tnmap_schedule(decoder: TNMAP, problem: GeneralDecodingProblem) -> S.Schedul
 
 
 def _lower_sumprod(factors, checks, n_vars, n_checks, n_obs, order, dynamic=False):
-    """Sum-product plan of a marginal network: the on-chip schedule (schedule.py) when the frontier has at most 11 bits,
-    else the global-memory lowering (wide.py; measured faster from 12 bits on: its tile kernel fuses runs of two-candidate
-    steps into register butterflies and a 12-bit plan is a single tile).  The order is chosen once and shared by both."""
+    """Sum-product plan of a marginal network: the on-chip schedule (schedule.py) when the frontier has at most 11 bits
+    (9 for plans of rank-1 factors), else the global-memory lowering (wide.py; measured faster from there on: a plan of
+    up to 12 bits is a single tile).  The order is chosen once and shared by both."""
     all_check_vars = {v for c in checks for v in c.vars}
     merged = S.merge_overlapping(list(factors), n_vars, all_check_vars, allow_negative=True)
     if order is None:
@@ -281,7 +281,10 @@ def _lower_sumprod(factors, checks, n_vars, n_checks, n_obs, order, dynamic=Fals
     elif len(order) == len(factors) and len(factors) != len(merged):
         order = S.map_order(factors, merged, order)
     w_max, _ = S._evaluate(order, S._Sim(merged, checks))
-    onchip = min(int(os.environ.get("TQEC_SUMPROD_ONCHIP_WIDTH", S.MAX_SUMPROD_ONCHIP_WIDTH)), S.MAX_SMEM_WIDTH)
+    # plans made of rank-1 factors only (detector error models) run as register butterflies on the global-memory
+    # executor (k_wide_bf, library lowering): measured faster from 10 bits on
+    dflt = 9 if all(len(f.vars) == 1 for f in merged) else S.MAX_SUMPROD_ONCHIP_WIDTH
+    onchip = min(int(os.environ.get("TQEC_SUMPROD_ONCHIP_WIDTH", dflt)), S.MAX_SMEM_WIDTH)
     if w_max <= onchip and os.environ.get("TQEC_FORCE_WIDE") is None and not dynamic:
         return S.lower(merged, checks, S.SUMPROD, n_vars, n_checks, n_obs, order=order)
     return lower_wide(merged, checks, S.SUMPROD, n_vars, n_checks, n_obs, order=order,

@@ -222,6 +222,8 @@ def lower_wide(factors: Sequence[S.Factor], checks: Sequence[S.Check], semiring:
             return None
         return tile, g, peak
 
+    # plans made of rank-1 factors only (detector error models) keep a pass within what one butterfly block holds
+    max_pass_steps = 96 if all(len(f.vars) == 1 for f in factors) else MAX_PASS_STEPS
     passes: List[WidePass] = []
     glive: List[int] = []
     w_cap = 0
@@ -232,7 +234,7 @@ def lower_wide(factors: Sequence[S.Factor], checks: Sequence[S.Check], semiring:
     while t < n:
         best = None
         for lb in range(low_bits, -1, -1):
-            for t1 in range(t + 1, min(n, t + MAX_PASS_STEPS) + 1):
+            for t1 in range(t + 1, min(n, t + max_pass_steps) + 1):
                 r = simulate(t, t1, glive, lb)
                 if r is None:
                     break

@@ -406,7 +406,8 @@ def test_dem_tnmmap(tq):
 @pytest.mark.parametrize("name,n_dense", [("surface_d3_r3_phenom.dem", 64), ("surface_d5_r5_phenom.dem", 0)])
 def test_dem_surface_memory(tq, name, n_dense):
     """BASELINE configs[3] shape: surface-code memory DEMs (phenomenological, generated by benchmarks/make_dem.py because
-    stim is not available).  d=5 x 5 rounds has an 11-bit frontier and runs on the CTA-team kernel."""
+    stim is not available).  d=5 x 5 rounds has an 11-bit frontier: since round 2 a plan of rank-1 factors that wide runs
+    on the butterfly executor (k_wide_bf, one tile per shot)."""
     import os
     dem = tq.parse_dem_file(os.path.join(os.path.dirname(__file__), "golden", name))
     ct = tq.compile(tq.TNMMAP(), dem)
@@ -416,7 +417,13 @@ def test_dem_surface_memory(tq, name, n_dense):
     res = tq.decode(ct, syn)
     assert syn == tq.syndrome_extraction(res.error_pattern, ct.tanner)
     sch = ct.schedule
-    ref = cref.FrontierPlan(sch).run(syn.s)
+    from tensorqec.jl_b200 import _cabi, schedule as S
+    if name.startswith("surface_d5"):
+        assert ct.plan.query(_cabi.Q_WIDE) == 1, "an 11-bit plan of rank-1 factors should run as register butterflies (k_wide_bf)"
+    # the C port executes the on-chip step tables: lower them for the same order when the plan itself went to the
+    # global-memory executor
+    csch = sch if hasattr(sch, "hdr") else S.lower(sch.factors, sch.checks, S.SUMPROD, sch.n_vars, sch.n_checks, sch.n_obs, order=sch.order)
+    ref = cref.FrontierPlan(csch).run(syn.s)
     got = res.marginal.reshape(B, -1, order="F")
     assert np.allclose(got, ref, rtol=MAR_RTOL, atol=0)
     ref2 = frontier.run(sch.factors, sch.checks, sch.order, 1, syn.s[:8], sch.n_vars)

@@ -98,10 +98,26 @@ def test_tnmmap_css_tables_identical(d):
 
 
 @pytest.mark.parametrize("name", ["dem.dem", "surface_d3_r3_phenom.dem", "surface_d5_r5_phenom.dem"])
-def test_dem_tables_identical(name, golden_dir):
+def test_dem_tables_identical(name, golden_dir, monkeypatch):
+    # the on-chip schedule (by default plans of rank-1 factors move to the global-memory executor from 10 bits on)
+    monkeypatch.setenv("TQEC_SUMPROD_ONCHIP_WIDTH", "11")
     factors, checks, dims = _dem_graph(tq.parse_dem_file(str(golden_dir / name)))
     py = D._sumprod_lower(tq.TNMMAP(), factors, checks, dims, None)
     _check_schedule(_cabi.Lowered(_cabi.Problem(factors, checks, S.SUMPROD, *dims)), py)
+
+
+def test_rank1_plans_of_ten_bits_and_more_go_to_the_butterfly_executor(golden_dir):
+    """Phenomenological d = 5 x 5 rounds (11-bit frontier): both lowerings route it to the global-memory executor, the
+    generic tables are identical and every pass carries a butterfly block."""
+    factors, checks, dims = _dem_graph(tq.parse_dem_file(str(golden_dir / "surface_d5_r5_phenom.dem")))
+    py = D._lower_sumprod(factors, checks, dims[0], dims[1], dims[2], None)
+    lw = _cabi.Lowered(_cabi.Problem(factors, checks, S.SUMPROD, *dims))
+    m = lw.meta
+    assert m["kind"] == 2 and hasattr(py, "passes") and (m["n_pass"], m["w_cap"]) == (len(py.passes), py.w_cap)
+    for what, arr in [(_cabi.LW_WD_PASS_HDR, py.pass_hdr), (_cabi.LW_WD_STEP_HDR, py.step_hdr), (_cabi.LW_WD_INTS, py.ints),
+                      (_cabi.LW_WD_TABLES, py.tables)]:
+        assert _same(lw.get(what), arr), what
+    assert (lw.get(_cabi.LW_WD_BF_OFF) >= 0).all()
 
 
 @pytest.mark.parametrize("t_max", [8, 12])
