@@ -142,7 +142,9 @@ struct tqec_plan {
   cudaStream_t stream;
   // host-pointer entry points: copy-in / copy-out streams and per-chunk events of the three-stage pipeline
   cudaStream_t s_in, s_out;
-  cudaEvent_t ev_in[2], ev_cmp[2];
+  cudaEvent_t ev_in[2], ev_cmp[2], ev_out[2];
+  void *h_pin[3];        // pinned host staging of the byte-per-bit entry points (two slots each)
+  size_t h_pin_cap[3];
 };
 
 struct tqec_gf2 {

@@ -15,6 +15,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <thread>
+
 #include "tqec_common.h"
 
 namespace tqec {
@@ -1201,12 +1203,14 @@ extern "C" int tqec_plan_destroy(tqec_plan *p) {
   wide_destroy(p);
   cudaFree(p->d_mc);
   for (int i = 0; i < 4; ++i) cudaFree(p->d_io[i]);
+  for (int i = 0; i < 3; ++i) if (p->h_pin[i]) cudaFreeHost(p->h_pin[i]);
   if (p->stream) cudaStreamDestroy(p->stream);
   if (p->s_in) cudaStreamDestroy(p->s_in);
   if (p->s_out) cudaStreamDestroy(p->s_out);
   for (int i = 0; i < 2; ++i) {
     if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
     if (p->ev_cmp[i]) cudaEventDestroy(p->ev_cmp[i]);
+    if (p->ev_out[i]) cudaEventDestroy(p->ev_out[i]);
   }
   delete p;
   return TQEC_OK;
@@ -1257,6 +1261,7 @@ static int ensure_pipeline(tqec_plan *p) {
   for (int i = 0; i < 2; ++i) {
     TQEC_CUDA(cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
     TQEC_CUDA(cudaEventCreateWithFlags(&p->ev_cmp[i], cudaEventDisableTiming));
+    TQEC_CUDA(cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming));
   }
   return TQEC_OK;
 }
@@ -1365,44 +1370,113 @@ static int grid_for(int64_t n, int sm) {
 }
 }  // namespace tqec
 
-// shared body: bytes in -> pack -> decode -> (unpack) -> out, chunked on the plan's stream
+// host-side copy between the caller's (pageable) arrays and the pinned staging buffers, split over a few threads: one
+// core moves ~10 GB/s, the decode of a chunk needs ~18 GB/s of bytes at d = 9
+static void par_memcpy(void *dst, const void *src, size_t n) {
+  const size_t MIN_PART = (size_t)4 << 20;
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t parts = n / MIN_PART;
+  if (parts > 6) parts = 6;
+  if (hw && parts > hw) parts = hw;
+  if (parts <= 1) { std::memcpy(dst, src, n); return; }
+  std::vector<std::thread> th;
+  const size_t step = ((n / parts) + 63) & ~(size_t)63;
+  for (size_t i = 1; i < parts; ++i) {
+    const size_t o = i * step, m = o >= n ? 0 : (i + 1 == parts ? n - o : (o + step > n ? n - o : step));
+    if (m) th.emplace_back([=] { std::memcpy((char *)dst + o, (const char *)src + o, m); });
+  }
+  std::memcpy(dst, src, step < n ? step : n);
+  for (auto &t : th) t.join();
+}
+
+static int ensure_pinned(void **slot, size_t *cap, size_t bytes) {
+  if (*cap >= bytes) return TQEC_OK;
+  if (*slot) cudaFreeHost(*slot);
+  *slot = nullptr; *cap = 0;
+  cudaError_t e = cudaMallocHost(slot, bytes);
+  if (e != cudaSuccess) { tqec::set_error("cudaMallocHost(%zu B staging): %s", bytes, cudaGetErrorString(e)); return TQEC_ERR_NOMEM; }
+  *cap = bytes;
+  return TQEC_OK;
+}
+
+// shared body: bytes in -> pack -> decode -> (unpack) -> out.  Three-stage pipeline over chunks of 2^19 shots with two
+// slots: the caller's arrays are pageable, so every chunk goes through pinned staging buffers (host copy by par_memcpy,
+// then a true asynchronous transfer); H2D of chunk c + 1, the kernels of chunk c, D2H of chunk c - 1 and the host copies
+// overlap.
 static int decode_bytes(tqec_plan *p, const uint8_t *synd_bits, int64_t B, uint8_t *corr_bits, double *out, int32_t *argmax_out) {
   tqec::NvtxRange nvtx_range("tqec_decode_bytes");
   const bool mp = p->semiring == TQEC_SEMIRING_MAXPLUS;
   const int nc = p->dev.n_checks, nv = p->dev.n_vars, nsw = p->dev.nsw, ncw = p->dev.ncw;
   const int64_t NO = mp ? 1 : ((int64_t)1 << p->dev.n_obs);
-  const int64_t CH = (int64_t)1 << 20;
+  const int64_t CH = (int64_t)1 << 19;
   const int64_t nb = B < CH ? B : CH;
+  const size_t nc1 = (size_t)(nc ? nc : 1), nv1 = (size_t)(nv ? nv : 1);
   int rc;
-  // staging: [0] syndrome bytes, [1] packed syndromes + packed corrections, [2] outputs, [3] correction bytes + argmax
-  if ((rc = ensure_cap(&p->d_io[0], &p->io_cap[0], (size_t)nb * (nc ? nc : 1)))) return rc;
-  if ((rc = ensure_cap(&p->d_io[1], &p->io_cap[1], (size_t)nb * (nsw + ncw) * 8))) return rc;
-  if ((rc = ensure_cap(&p->d_io[2], &p->io_cap[2], (size_t)nb * NO * 8))) return rc;
-  if ((rc = ensure_cap(&p->d_io[3], &p->io_cap[3], (size_t)nb * ((nv ? nv : 1) + 4)))) return rc;
-  uint8_t *d_sb = (uint8_t *)p->d_io[0];
-  uint64_t *d_syn = (uint64_t *)p->d_io[1], *d_cor = d_syn + (size_t)nb * nsw;
-  double *d_out = (double *)p->d_io[2];
-  uint8_t *d_cb = (uint8_t *)p->d_io[3];
-  int32_t *d_arg = (int32_t *)(d_cb + (((size_t)nb * (nv ? nv : 1) + 3) & ~(size_t)3));
-  cudaStream_t st = p->stream;
-  for (int64_t o = 0; o < B; o += nb) {
-    const int64_t n = B - o < nb ? B - o : nb;
-    TQEC_CUDA(cudaMemcpyAsync(d_sb, synd_bits + (size_t)o * nc, (size_t)n * nc, cudaMemcpyHostToDevice, st));
-    k_pack_bits<<<grid_for(n * nsw, p->sm_count), 256, 0, st>>>(d_sb, n, nc, nsw, d_syn);
-    TQEC_CUDA(cudaGetLastError());
-    if ((rc = launch_decode(p, d_syn, n, mp ? d_cor : nullptr, d_out, mp ? nullptr : d_arg, st))) return rc;
-    if (mp) {
-      k_unpack_bits<<<grid_for(n * nv, p->sm_count), 256, 0, st>>>(d_cor, n, nv, ncw, d_cb);
+  if ((rc = ensure_pipeline(p))) return rc;
+  // device staging, two slots each: [0] syndrome bytes, [1] packed syndromes + packed corrections, [2] outputs,
+  // [3] correction bytes (max-plus) or argmax (sum-product)
+  const size_t sz0 = (size_t)nb * nc1, sz1 = (size_t)nb * (nsw + ncw) * 8, sz2 = (size_t)nb * NO * 8;
+  const size_t sz3 = mp ? (((size_t)nb * nv1 + 15) & ~(size_t)15) : (size_t)nb * 4;
+  if ((rc = ensure_cap(&p->d_io[0], &p->io_cap[0], 2 * sz0))) return rc;
+  if ((rc = ensure_cap(&p->d_io[1], &p->io_cap[1], 2 * sz1))) return rc;
+  if ((rc = ensure_cap(&p->d_io[2], &p->io_cap[2], 2 * sz2))) return rc;
+  if ((rc = ensure_cap(&p->d_io[3], &p->io_cap[3], 2 * sz3))) return rc;
+  // pinned host staging, two slots: [0] syndrome bytes in, [1] outputs (doubles), [2] correction bytes / argmax out
+  if ((rc = ensure_pinned(&p->h_pin[0], &p->h_pin_cap[0], 2 * sz0))) return rc;
+  if ((rc = ensure_pinned(&p->h_pin[1], &p->h_pin_cap[1], 2 * sz2))) return rc;
+  if ((rc = ensure_pinned(&p->h_pin[2], &p->h_pin_cap[2], 2 * sz3))) return rc;
+  const int64_t n_chunks = (B + nb - 1) / nb;
+  bool ev_out_used[2] = {false, false};
+  for (int64_t c = 0; c <= n_chunks; ++c) {
+    const int slot = (int)(c & 1);
+    if (c < n_chunks) {
+      const int64_t o = c * nb, n = B - o < nb ? B - o : nb;
+      uint8_t *d_sb = (uint8_t *)p->d_io[0] + slot * sz0;
+      uint64_t *d_syn = (uint64_t *)((char *)p->d_io[1] + slot * sz1), *d_cor = d_syn + (size_t)nb * nsw;
+      double *d_out = (double *)((char *)p->d_io[2] + slot * sz2);
+      uint8_t *d_x = (uint8_t *)p->d_io[3] + slot * sz3;
+      uint8_t *h_in = (uint8_t *)p->h_pin[0] + slot * sz0;
+      if (c >= 2) TQEC_CUDA(cudaEventSynchronize(p->ev_in[slot]));      // the staging buffer's previous transfer has left
+      par_memcpy(h_in, synd_bits + (size_t)o * nc, (size_t)n * nc);
+      if (c >= 2) TQEC_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_cmp[slot], 0));   // chunk c - 2 has consumed the device slot
+      TQEC_CUDA(cudaMemcpyAsync(d_sb, h_in, (size_t)n * nc, cudaMemcpyHostToDevice, p->s_in));
+      TQEC_CUDA(cudaEventRecord(p->ev_in[slot], p->s_in));
+      TQEC_CUDA(cudaStreamWaitEvent(p->stream, p->ev_in[slot], 0));
+      if (ev_out_used[slot]) TQEC_CUDA(cudaStreamWaitEvent(p->stream, p->ev_out[slot], 0));   // chunk c - 2's results have left
+      k_pack_bits<<<grid_for(n * nsw, p->sm_count), 256, 0, p->stream>>>(d_sb, n, nc, nsw, d_syn);
       TQEC_CUDA(cudaGetLastError());
-      TQEC_CUDA(cudaMemcpyAsync(corr_bits + (size_t)o * nv, d_cb, (size_t)n * nv, cudaMemcpyDeviceToHost, st));
-      if (out) TQEC_CUDA(cudaMemcpyAsync(out + o, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    } else {
-      TQEC_CUDA(cudaMemcpyAsync(out + o * NO, d_out, (size_t)n * NO * 8, cudaMemcpyDeviceToHost, st));
-      if (argmax_out) TQEC_CUDA(cudaMemcpyAsync(argmax_out + o, d_arg, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+      if ((rc = launch_decode(p, d_syn, n, mp ? d_cor : nullptr, d_out, mp ? nullptr : (int32_t *)d_x, p->stream))) return rc;
+      if (mp) {
+        k_unpack_bits<<<grid_for(n * nv, p->sm_count), 256, 0, p->stream>>>(d_cor, n, nv, ncw, d_x);
+        TQEC_CUDA(cudaGetLastError());
+      }
+      TQEC_CUDA(cudaEventRecord(p->ev_cmp[slot], p->stream));
+      TQEC_CUDA(cudaStreamWaitEvent(p->s_out, p->ev_cmp[slot], 0));
+      if (mp) {
+        TQEC_CUDA(cudaMemcpyAsync((uint8_t *)p->h_pin[2] + slot * sz3, d_x, (size_t)n * nv, cudaMemcpyDeviceToHost, p->s_out));
+        if (out) TQEC_CUDA(cudaMemcpyAsync((char *)p->h_pin[1] + slot * sz2, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost, p->s_out));
+      } else {
+        TQEC_CUDA(cudaMemcpyAsync((char *)p->h_pin[1] + slot * sz2, d_out, (size_t)n * NO * 8, cudaMemcpyDeviceToHost, p->s_out));
+        if (argmax_out) TQEC_CUDA(cudaMemcpyAsync((uint8_t *)p->h_pin[2] + slot * sz3, d_x, (size_t)n * 4, cudaMemcpyDeviceToHost, p->s_out));
+      }
+      TQEC_CUDA(cudaEventRecord(p->ev_out[slot], p->s_out));
+      ev_out_used[slot] = true;
+      p->launches += mp ? 2 : 1;
     }
-    p->launches += mp ? 2 : 1;
+    if (c >= 1) {                                                // results of the previous chunk: pinned staging -> caller's arrays
+      const int ps = (int)((c - 1) & 1);
+      const int64_t o = (c - 1) * nb, n = B - o < nb ? B - o : nb;
+      TQEC_CUDA(cudaEventSynchronize(p->ev_out[ps]));
+      if (mp) {
+        par_memcpy(corr_bits + (size_t)o * nv, (uint8_t *)p->h_pin[2] + ps * sz3, (size_t)n * nv);
+        if (out) std::memcpy(out + o, (char *)p->h_pin[1] + ps * sz2, (size_t)n * 8);
+      } else {
+        par_memcpy(out + o * NO, (char *)p->h_pin[1] + ps * sz2, (size_t)n * NO * 8);
+        if (argmax_out) std::memcpy(argmax_out + o, (uint8_t *)p->h_pin[2] + ps * sz3, (size_t)n * 4);
+      }
+    }
   }
-  TQEC_CUDA(cudaStreamSynchronize(st));
+  TQEC_CUDA(cudaStreamSynchronize(p->stream));
   return TQEC_OK;
 }
 

@@ -307,8 +307,13 @@ def _compile_tnmap(decoder: TNMAP, problem: GeneralDecodingProblem) -> CompiledT
     return CompiledTNMAP(decoder, problem)
 
 
+class _ValidatedBits(np.ndarray):
+    """uint8 0/1 array that already went through as_bits (skips a second validation pass over a large batch)."""
+    _tqec_validated = True
+
+
 def _syndrome_bits(s, n) -> np.ndarray:
-    b = as_bits(s)
+    b = s if isinstance(s, _ValidatedBits) else as_bits(s)
     b = b[None, :] if b.ndim == 1 else b
     if b.shape[1] != n:
         raise ValueError(f"syndrome has {b.shape[1]} bits, the decoder expects {n}")
@@ -316,8 +321,10 @@ def _syndrome_bits(s, n) -> np.ndarray:
 
 
 def _decode_tnmap(ct: CompiledTNMAP, syndrome: SimpleSyndrome) -> DecodingResult:
-    single = as_bits(syndrome.s).ndim == 1
-    bits = _syndrome_bits(syndrome.s, ct.n_checks)
+    raw = syndrome.s
+    bits = raw if isinstance(raw, _ValidatedBits) else as_bits(raw).view(_ValidatedBits)   # validated once: 1e7 shots are 0.8 GB
+    single = bits.ndim == 1
+    bits = _syndrome_bits(bits, ct.n_checks)
     cfg, logp = ct.plan.decode_map_bits(bits, ct.qubit_num)     # one byte per bit both ways; packed on the device
     ok = np.isfinite(logp)
     if single:
@@ -543,7 +550,7 @@ def decode(first, *args):
         if not isinstance(syn, CSSSyndrome):
             raise TypeError("a CSS-compiled decoder decodes a CSSSyndrome")
         sx, sz = as_bits(syn.sx), as_bits(syn.sz)
-        res = decode(ct.cd, SimpleSyndrome(np.concatenate([sx, sz], axis=-1)))
+        res = decode(ct.cd, SimpleSyndrome(np.concatenate([sx, sz], axis=-1).view(_ValidatedBits)))
         out = extract_decoding(ct.reduction, res.error_pattern)
         out.success_tag, out.logp = res.success_tag, res.logp
         return out

@@ -60,14 +60,27 @@ class Mod2:
 
 def as_bits(v) -> np.ndarray:
     """Anything bit-like (list of 0/1, bools, Mod2) -> uint8 array of 0/1."""
+    if getattr(v, "_tqec_validated", False):                    # already checked (decoding._ValidatedBits)
+        return v
     if isinstance(v, np.ndarray) and v.dtype != object:
         a = v.astype(np.uint8, copy=False)
     else:
         a = np.array([[int(x) for x in row] if isinstance(row, (list, tuple, np.ndarray)) else int(row) for row in v],
                      dtype=np.uint8) if len(v) else np.zeros(0, dtype=np.uint8)
-    if a.size and a.max() > 1:
+    if a.size and _has_non_bit(a):
         raise ValueError("bits must be 0/1")
     return a
+
+
+def _has_non_bit(a: np.ndarray) -> bool:
+    """Any byte above 1?  One pass at memory bandwidth (eight bytes per word) instead of a bytewise max."""
+    if a.flags.c_contiguous and a.size >= 64:
+        flat = a.reshape(-1)
+        n8 = flat.size & ~7
+        if np.bitwise_or.reduce(flat[:n8].view(np.uint64)) & np.uint64(0xFEFEFEFEFEFEFEFE):
+            return True
+        return bool(n8 < flat.size and flat[n8:].max() > 1)
+    return bool(a.max() > 1)
 
 
 def words_for(nbits: int) -> int:
