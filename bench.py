@@ -383,6 +383,12 @@ def run_ours(args):
                                    "instruction rate; MEASURED_PEAKS.json has no FP64 entry)",
                     "traffic_source": traffic_src,
                     "fp64_peaks": peak,
+                    # the same ops against what the device sustains on the max-plus instruction mix itself: register-resident
+                    # chains of 2 DADD + DSETP + 2 FSEL (sm_100a has no FP64 max / 64-bit select); FP64, ALU and FMA pipes each
+                    # take one warp instruction per two cycles (benchmarks/micro/issue_model.cu), so the selects cap this mix
+                    # at ~0.64 of the DADD rate before any load, store or address instruction
+                    "semiring": {"peak": peak["maxplus_tops"], "unit": "Tops/s", "frac": achieved / peak["maxplus_tops"],
+                                 "peak_source": "measured in this run by tqec_fp64_peak (max-plus candidate chains)"},
                     "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                             "frac": hbm_achieved / hbm_peak, "bytes_per_shot": bytes_per_shot, "peak_source": hbm_src}}
         cpu = cpu_baseline(tq, sch, syn_words, args)

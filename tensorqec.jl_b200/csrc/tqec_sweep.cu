@@ -23,9 +23,6 @@ namespace tqec {
 
 #define SW_REC_INTS 32
 #define SW_TB_INTS 64
-#ifndef TQEC_SWEEP_PRED_MASK
-#define TQEC_SWEEP_PRED_MASK 0x00   /* bit (JO mod 8) set: that output recomputes its winner instead of selecting it */
-#endif
 
 __device__ __forceinline__ double sw_lds(uint32_t addr) {
   double v;
@@ -84,20 +81,13 @@ __device__ __forceinline__ void sweep_out(const double (&R)[1 << M], double (&O)
   } else if (NF == 1) {
     if (SEMI == TQEC_SEMIRING_MAXPLUS) {
       constexpr uint32_t m = 1u << ((OFF + JO) & 31);
-      // Two forms of the same candidate pair, bit-identical results.  SELECT: the winner is moved by selp.f64 (two FSEL:
-      // 3 FP64-pipe + 3 ALU-pipe instructions per output).  RECOMPUTE: the winner is recomputed by a predicated add
-      // (4 FP64-pipe + 1 ALU-pipe instruction).  FP64 pipe and ALU pipe each take one warp instruction per two cycles
-      // (benchmarks/micro/issue_model.cu) and the ALU pipe also carries every address LOP3, so the outputs whose bit is
-      // set in TQEC_SWEEP_PRED_MASK (index JO mod 8) use RECOMPUTE to balance the two pipes.
-      if constexpr (((TQEC_SWEEP_PRED_MASK) >> (JO & 7)) & 1) {
-        asm("{\n .reg .pred p;\n .reg .f64 c1;\n add.f64 %0, %2, %3;\n add.f64 c1, %4, %5;\n setp.gt.f64 p, c1, %0;\n"
-            " @p add.f64 %0, %4, %5;\n @p or.b32 %1, %1, %6;\n}"
-            : "=&d"(O[JO]), "+r"(bits) : "d"(R[J]), "d"(Tp[0]), "d"(R[J ^ F0]), "d"(Tp[1]), "n"(m));
-      } else {
-        const double c0 = R[J] + Tp[0], c1 = R[J ^ F0] + Tp[1];
-        asm("{\n .reg .pred p;\n setp.gt.f64 p, %2, %3;\n selp.f64 %0, %2, %3, p;\n @p or.b32 %1, %1, %4;\n}"
-            : "=d"(O[JO]), "+r"(bits) : "d"(c1), "d"(c0), "n"(m));
-      }
+      // c0 / c1 in ascending assignment order, strict > keeps the smaller assignment on ties; the back-pointer bit is one
+      // predicated OR with an immediate mask.  (A variant that recomputes the winner with a predicated add instead of
+      // selecting it -- FP64 pipe instead of ALU pipe -- cannot be expressed: ptxas merges the second add with the first
+      // and emits the same DSETP + 2 FSEL, also for a DFMA by an opaque 1.0, which it hoists out of the predicate.)
+      const double c0 = R[J] + Tp[0], c1 = R[J ^ F0] + Tp[1];
+      asm("{\n .reg .pred p;\n setp.gt.f64 p, %2, %3;\n selp.f64 %0, %2, %3, p;\n @p or.b32 %1, %1, %4;\n}"
+          : "=d"(O[JO]), "+r"(bits) : "d"(c1), "d"(c0), "n"(m));
     } else {
       O[JO] = R[J] * Tp[0] + R[J ^ F0] * Tp[1];
     }

@@ -661,6 +661,33 @@ def test_dynamic_rescaling_survives_fp64_underflow(tq):
     assert np.array_equal(r1.sector, arg) and tq.syndrome_extraction(r1.error_pattern, t) == s
 
 
+def test_dynamic_rescaling_on_butterfly_passes(tq):
+    """The same on the butterfly executor (k_wide_bf): phenomenological d = 3 x 3 rounds DEM with every mechanism at
+    p = 1e-60; detector patterns that need seven mechanisms have probabilities near 1e-420.  The lowering ends
+    a pass before its ratios r = p / (1 - p) can take a shot below the FP64 range, the kernel rescales between passes."""
+    import os
+    from tensorqec.jl_b200 import _cabi
+    from tensorqec.jl_b200.dem import DetectorErrorModel
+    dem0 = tq.parse_dem_file(os.path.join(os.path.dirname(__file__), "golden", "surface_d3_r3_phenom.dem"))
+    dem = DetectorErrorModel([1e-60] * len(dem0.error_rates), dem0.flipped_detectors, dem0.detector_list, dem0.logical_list)
+    ct = tq.compile(tq.TNMMAP(table_bits=0, dynamic_rescale=True), dem)
+    assert ct.plan.query(_cabi.Q_WIDE) == 1
+    nd = dem.n_detectors
+    rng = np.random.default_rng(21)
+    ep = (rng.random((6, len(dem.error_rates))) < 0.2).astype(np.uint8)
+    syn = (ep @ ct.tanner.H.T.astype(np.int64) % 2).astype(np.uint8)
+    syn[1] = 0
+    assert syn.shape[1] == nd
+    mant, lg, arg = ct.plan.decode_marginal_log2(tq.pack_bits(syn))
+    sch = ct.schedule
+    ref_m, ref_e = frontier.run(sch.factors, sch.checks, sch.order, 1, syn, sch.n_vars, rescale=True)
+    assert (mant.max(axis=1) > 0).all() and lg.min() < -1100 and lg[1] > -60
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ratio = (mant / ref_m) * np.exp2((lg.astype(np.int64) - ref_e)[:, None].astype(np.float64))
+    assert np.allclose(ratio[ref_m > 0], 1.0, rtol=MAR_RTOL, atol=0)
+    assert np.array_equal(arg, ref_m.argmax(axis=1))
+
+
 def test_table_decoder_batched_lookup(tq):
     """TableDecoder (truthtable.jl) on the GPU: d = 5 surface code, all errors up to weight 2 tabulated; every sampled
     syndrome found in the table decodes to the tabulated pattern (which reproduces the syndrome), the others report
