@@ -357,28 +357,56 @@ __device__ __forceinline__ void bf_cp_async16(uint32_t dst, const void *src) {
 
 __global__ void __launch_bounds__(BF_NT, 3) k_wide_bf(const WideBfArgs A) {
   extern __shared__ __align__(16) unsigned char bf_dyn[];      // two tiles of 2^12 doubles
-  __shared__ uint32_t dep_in[128], dep_out[128];
+  __shared__ uint32_t dep_in[128];
   __shared__ uint32_t sdep_in[288], sdep_out[288];         // deposit of the tile number's spectator part: 7 + 7 + 5 bits
-  __shared__ uint16_t tout[128];
+  // the last group stores straight to the state: offsets and logical tile indices of its coset representatives and basis
+  __shared__ uint32_t gout_lo[16], gout_hi[16], gb_out[8];
+  __shared__ uint16_t elog_lo[16], elog_hi[16], b_log[8];
+  __shared__ uint32_t s_cmask;
   __shared__ uint32_t s_xp[BF_MAX_GROUPS + 1];               // address mask of the closed checks before every group (per tile)
   __shared__ BfGroupS grp[BF_MAX_GROUPS];
   __shared__ double s_r[BF_MAX_STEPS];
   __shared__ int32_t s_code[BF_MAX_STEPS];
   __shared__ uint16_t s_closeP[BF_MAX_CLOSES], s_closeB[BF_MAX_CLOSES];
+  __shared__ uint8_t s_closePos[BF_MAX_CLOSES];
   const int tid = threadIdx.x;
   const int32_t *ph = A.pass, *bf = A.bf;
-  const int w_in = ph[TQEC_WP_WIN], w_out = ph[TQEC_WP_WOUT], t_in = ph[TQEC_WP_TIN], t_out = ph[TQEC_WP_TOUT];
+  const int w_in = ph[TQEC_WP_WIN], w_out = ph[TQEC_WP_WOUT], t_in = ph[TQEC_WP_TIN];
   const uint32_t tin = (uint32_t)ph[TQEC_WP_TINMASK], toutm = (uint32_t)ph[TQEC_WP_TOUTMASK];
   const int n_groups = bf[0], n_dep = bf[1], n_closes = bf[2];
   const int32_t *pout = bf + 8, *grec = bf + 20, *drec = grec + n_groups * TQEC_BF_GROUP_INTS, *crec = drec + n_dep;
   {
     const uint32_t x = tid < 64 ? (uint32_t)tid : ((uint32_t)(tid - 64) << 6);
     dep_in[tid] = wd_pdep(x, tin);
-    dep_out[tid] = wd_pdep(x, toutm);
+  }
+  // logical tile index -> offset in the output state: the bit at position pout[i] goes to the i-th set bit of toutm
+  auto out_off = [&](uint32_t e) {
     uint32_t idx = 0;
     for (int i = 0; i < 12; ++i)
-      if (((x >> i) & 1u) && pout[i] >= 0) idx |= 1u << pout[i];
-    tout[tid] = (uint16_t)(bf_phys(idx) << 3);
+      if (pout[i] >= 0 && ((e >> pout[i]) & 1u)) idx |= 1u << i;
+    return wd_pdep(idx, toutm);
+  };
+  if (tid < 16) {
+    const int32_t *rl = grec + (n_groups - 1) * TQEC_BF_GROUP_INTS;
+    uint32_t llo = 0, lhi = 0;
+    for (int b = 0; b < 4; ++b) {
+      if (((tid >> b) & 1) && b < rl[0]) llo |= 1u << (((uint32_t)rl[13] >> (4 * b)) & 15u);
+      if (((tid >> b) & 1) && b + 4 < rl[0]) lhi |= 1u << (((uint32_t)rl[13] >> (4 * (b + 4))) & 15u);
+    }
+    gout_lo[tid] = out_off(llo); gout_hi[tid] = out_off(lhi);
+    elog_lo[tid] = (uint16_t)llo; elog_hi[tid] = (uint16_t)lhi;
+    if (tid < 8) {
+      gb_out[tid] = tid < TQEC_BF_G ? out_off((uint32_t)rl[5 + tid]) : 0u;
+      b_log[tid] = tid < TQEC_BF_G ? (uint16_t)rl[5 + tid] : (uint16_t)0;
+    }
+    if (tid == 0) {
+      // a member of the last group's cosets survives when every bit outside the output positions has its dead value: the
+      // syndrome bit at a position this group closes, zero elsewhere (padding dimensions, positions closed earlier)
+      uint32_t outpos = 0;
+      for (int i = 0; i < 12; ++i)
+        if (pout[i] >= 0) outpos |= 1u << pout[i];
+      s_cmask = 0xfffu & ~outpos;
+    }
   }
   for (int g = tid; g < n_groups; g += BF_NT) {
     const int32_t *rec = grec + g * TQEC_BF_GROUP_INTS;
@@ -401,8 +429,9 @@ __global__ void __launch_bounds__(BF_NT, 3) k_wide_bf(const WideBfArgs A) {
   }
   for (int i = tid; i < n_dep; i += BF_NT) s_code[i] = drec[i];
   for (int i = tid; i < n_closes; i += BF_NT) {
-    s_closeP[i] = (uint16_t)(bf_phys(1u << crec[2 * i]) << 3);
+    s_closeP[i] = (uint16_t)(bf_phys(1u << crec[2 * i]) << 3) | (uint16_t)0;
     s_closeB[i] = (uint16_t)crec[2 * i + 1];
+    s_closePos[i] = (uint8_t)crec[2 * i];
   }
   const int n_spec = w_in - t_in;
   const uint32_t spec_in = (w_in >= 32 ? 0xffffffffu : ((1u << w_in) - 1u)) & ~tin;
@@ -413,10 +442,9 @@ __global__ void __launch_bounds__(BF_NT, 3) k_wide_bf(const WideBfArgs A) {
     sdep_out[i] = wd_pdep(x, spec_out);
   }
   const int64_t n_tiles = A.nb << n_spec;
-  const int n_in = 1 << t_in, n_out = 1 << t_out;
+  const int n_in = 1 << t_in;
   const uint32_t dyn_abs = (uint32_t)__cvta_generic_to_shared(bf_dyn);
   const bool pairs = (tin & 1u) != 0;                            // tile bit 0 = index bit 0: entries come in 16-byte pairs
-  const bool out_pairs = (toutm & 1u) != 0 && pout[0] == 0 && t_out >= 1;
   __syncthreads();
 
   // tile -> buffer `which`: asynchronous copies of the input entries, zeros everywhere else
@@ -473,6 +501,13 @@ __global__ void __launch_bounds__(BF_NT, 3) k_wide_bf(const WideBfArgs A) {
       }
     }
     uint32_t XP = 0;
+    double tmax = 0.0;
+    // syndrome bits of the checks the last group closes, at their positions
+    uint32_t sc_last = 0;
+    for (int c = grp[n_groups - 1].close0; c < n_closes; ++c) {
+      const int sb = s_closeB[c];
+      if ((__ldg(syn + (sb >> 6)) >> (sb & 63)) & 1ull) sc_last |= 1u << s_closePos[c];
+    }
     for (int g = 0; g < n_groups; ++g) {
       const BfGroupS &G = grp[g];
       const int n_orb = 1 << G.n_free;
@@ -516,48 +551,63 @@ __global__ void __launch_bounds__(BF_NT, 3) k_wide_bf(const WideBfArgs A) {
             default: break;
           }
         }
-        // the walks ended at Gray code 4 (k = 7); walk back
+        if (g == n_groups - 1) {
+          // last group: straight to the state in HBM.  The output offset of a coset member is XOR-linear in its coordinates
+          // like its address; a member survives when its bits outside the output positions have their dead values
+          uint32_t gbo[TQEC_BF_G], bl[TQEC_BF_G];
 #pragma unroll
-        for (int k = 7; k >= 0; --k) {
-          const int gk = k ^ (k >> 1);
+          for (int j = 0; j < TQEC_BF_G; ++j) { gbo[j] = gb_out[j]; bl[j] = b_log[j]; }
+          const uint32_t cmask = s_cmask;
+          const uint32_t ebase = ((uint32_t)elog_lo[i & 15] | (uint32_t)elog_hi[i >> 4]) ^ sc_last;   // syndrome pre-XOR-ed: survivors have (e & cmask) == 0
+          const uint32_t obase = gout_lo[i & 15] | gout_hi[i >> 4];
+          uint32_t e4[4] = {ebase, ebase ^ bl[3], ebase ^ bl[4], ebase ^ bl[3] ^ bl[4]};
+          uint32_t o4[4] = {obase, obase ^ gbo[3], obase ^ gbo[4], obase ^ gbo[3] ^ gbo[4]};
+          if (A.max_out) {                                     // dynamic rescaling: also track the shot's largest stored entry
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            *reinterpret_cast<double *>(Sb + offs[h]) = v[gk | (h << 3)];
-            if (k) offs[h] ^= bP[bf_ctz(k)];
+            for (int k = 0; k < 8; ++k) {
+              const int gk = k ^ (k >> 1);
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                if (k) { e4[h] ^= bl[bf_ctz(k)]; o4[h] ^= gbo[bf_ctz(k)]; }
+                if ((e4[h] & cmask) == 0) {
+                  __stcs(go + o4[h], v[gk | (h << 3)]);
+                  tmax = fmax(tmax, v[gk | (h << 3)]);
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int gk = k ^ (k >> 1);
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                if (k) { e4[h] ^= bl[bf_ctz(k)]; o4[h] ^= gbo[bf_ctz(k)]; }
+                if ((e4[h] & cmask) == 0) __stcs(go + o4[h], v[gk | (h << 3)]);
+              }
+            }
+          }
+        } else {
+          // the walks ended at Gray code 4 (k = 7); walk back
+#pragma unroll
+          for (int k = 7; k >= 0; --k) {
+            const int gk = k ^ (k >> 1);
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              *reinterpret_cast<double *>(Sb + offs[h]) = v[gk | (h << 3)];
+              if (k) offs[h] ^= bP[bf_ctz(k)];
+            }
           }
         }
       }
-      __syncthreads();
-      XP = s_xp[g + 1];
+      if (g < n_groups - 1) {
+        __syncthreads();
+        XP = s_xp[g + 1];
+      }
     }
     if (A.max_out) {
-      double tmax = 0.0;
-      for (int l = tid; l < n_out; l += BF_NT) {
-        const uint32_t off = ((uint32_t)tout[l & 63] ^ (uint32_t)tout[64 + (l >> 6)]) ^ XP;
-        const double v = *reinterpret_cast<const double *>(Sb + off);
-        __stcs(go + (dep_out[l & 63] | dep_out[64 + (l >> 6)]), v);
-        tmax = fmax(tmax, v);
-      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
       if ((tid & 31) == 0 && tmax > 0.0) atomicMax(A.max_out + b, (unsigned long long)__double_as_longlong(tmax));
-    } else if (out_pairs) {
-      // output bit 0 is index bit 0 and sits at position 0: neighbours in the state are neighbours in the tile (swapped when
-      // the closed checks flipped position 0)
-#pragma unroll 4
-      for (int q = tid; q < (n_out >> 1); q += BF_NT) {
-        const int l = q << 1;
-        const uint32_t off = ((uint32_t)tout[l & 63] ^ (uint32_t)tout[64 + (l >> 6)]) ^ XP;
-        double2 x = *reinterpret_cast<const double2 *>(Sb + (off & ~8u));
-        if (off & 8u) { const double t = x.x; x.x = x.y; x.y = t; }
-        __stcs(reinterpret_cast<double2 *>(go + (dep_out[l & 63] | dep_out[64 + (l >> 6)])), x);
-      }
-    } else {
-#pragma unroll 4
-      for (int l = tid; l < n_out; l += BF_NT) {
-        const uint32_t off = ((uint32_t)tout[l & 63] ^ (uint32_t)tout[64 + (l >> 6)]) ^ XP;
-        __stcs(go + (dep_out[l & 63] | dep_out[64 + (l >> 6)]), *reinterpret_cast<const double *>(Sb + off));
-      }
     }
   }
 }

@@ -96,3 +96,42 @@ def test_butterfly_encoding_of_the_library_lowering_matches_recurrence(t_max):
     ref = frontier.run(merged, checks, order, 1, syn, ne)
     assert np.allclose(generic, ref, rtol=1e-13, atol=0)
     assert np.allclose(got, ref, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_butterfly_encoding_on_random_hypergraphs(seed):
+    """Random detector error models (mechanisms flipping 1-4 of 14-18 detectors and sometimes an observable; repeated
+    masks, mechanisms that open several detectors at once, detectors touched once) lowered with small tiles, so that
+    positions are reused, several checks open in one step and passes have many groups.  The butterfly tables executed by
+    the emulator against the recurrence oracle."""
+    from tensorqec.jl_b200 import _cabi
+    rng = np.random.RandomState(100 + seed)
+    nd, nm, no = 14 + seed % 5, 40 + 6 * seed, 1 + seed % 2
+    masks = []
+    for _ in range(nm):
+        k = rng.randint(1, 5)
+        m = sorted(rng.choice(nd, size=k, replace=False).tolist())
+        masks.append(m)
+    masks += masks[:5]                                           # repeated masks: dependent steps with one coordinate
+    p = rng.uniform(0.001, 0.3, size=len(masks))
+    obs = [sorted(set(rng.choice(len(masks), size=6, replace=False).tolist())) for _ in range(no)]
+    factors = [S.Factor((e,), np.array([1.0 - p[e], p[e]])) for e in range(len(masks))]
+    checks = [S.Check(tuple(e for e, m in enumerate(masks) if d in m), "syn", d) for d in range(nd)]
+    used = [d for d in range(nd) if checks[d].vars]
+    checks = [S.Check(checks[d].vars, "syn", i) for i, d in enumerate(used)]
+    nd = len(used)
+    checks += [S.Check(tuple(o), "obs", l) for l, o in enumerate(obs)]
+    ne = len(masks)
+    t_max = 6 + seed % 3
+    lw = _cabi.Lowered(_cabi.Problem(factors, checks, S.SUMPROD, ne, nd, no, flags=_cabi.COMPILE_FORCE_WIDE, wide_t_max=t_max))
+    off = lw.get(_cabi.LW_WD_BF_OFF)
+    assert (off >= 0).sum() >= len(off) - 1, "rank-1 passes should get a butterfly block"
+    H = np.zeros((nd, ne), dtype=np.int64)
+    for c in checks[:nd]:
+        H[c.index, list(c.vars)] = 1
+    e = (rng.rand(5, ne) < 0.15).astype(np.int64)
+    syn = ((e @ H.T) % 2).astype(np.uint8)
+    got = wide_emulator.run_lowered(lw, no, syn, butterfly=True)
+    order = [int(i) for i in lw.get(_cabi.LW_ORDER)]
+    ref = frontier.run(factors, checks, order, 1, syn, ne)
+    assert np.allclose(got, ref, rtol=1e-11, atol=0)
