@@ -135,6 +135,10 @@ typedef struct {
   double bf_mant;          /* product of the t0 normalised away = bf_mant * 2^bf_log2; applied to the output when   */
   int32_t bf_log2;         /* the butterfly passes are in use                                                     */
 } tqec_wide_desc;
+#ifndef TQEC_BF_SWZ_WIDE
+#define TQEC_BF_SWZ_WIDE 0  /* 1: the k_wide_bf tile swizzle folds index bits 8..10 as well as 5..7 into bits 1..3 (measured
+                               7 % slower at d = 5 x 5: benchmarks/ab_swz.sh) */
+#endif
 #define TQEC_BF_G 5            /* dimensions of a butterfly group: a thread holds 2^5 state entries in registers */
 #define TQEC_BF_GROUP_INTS 16  /* group record: n_free, dep0, n_dep, close0, n_closes, basis[5], zero mask, val0, -, order */
 

@@ -114,8 +114,8 @@ static void bf_add_basis(BfGroup &g, uint32_t bv, uint32_t v, uint32_t cu, int p
   g.red.push_back(v); g.expr.push_back(ev); g.pivot.push_back(piv); g.bvec.push_back(bv); g.runit.push_back(r);
 }
 
-// bank image of a position under the kernel's swizzle phys(x) = x ^ ((x >> 4) & 14): bank pair = phys & 15
-static int bf_bank_image(int q) { return q < 4 ? (1 << q) : (q >= 5 && q <= 7 ? (1 << (q - 4)) : 0); }
+// bank image of a position under the kernel's swizzle phys(x) = x ^ ((x >> 4) & 14) ^ ((x >> 7) & 14): bank pair = phys & 15
+static int bf_bank_image(int q) { return q < 4 ? (1 << q) : (q >= 5 && q <= 7 ? (1 << (q - 4)) : (TQEC_BF_SWZ_WIDE && q >= 8 && q <= 10 ? (1 << (q - 7)) : 0)); }
 
 #define BF_FAIL(N) do { if (std::getenv("TQEC_BF_DEBUG")) std::fprintf(stderr, "bf_encode_pass: steps %d..%d rejected (reason %d)\n", t0, t1, N); return false; } while (0)
 static bool bf_encode_pass(const std::vector<WRole> &roles, int t0, int t1, const std::vector<Factor> &factors,

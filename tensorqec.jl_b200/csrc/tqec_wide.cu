@@ -336,7 +336,8 @@ struct BfGroupS {
   int16_t n_free, dep0, n_dep, close0, n_closes, pad;
 };
 
-__host__ __device__ __forceinline__ uint32_t bf_phys(uint32_t x) { return x ^ ((x >> 4) & 14u); }
+// swizzle of the tile index: bits 5..7 and 8..10 are folded into bits 1..3 (bit 0 stays: entries travel in 16-byte pairs)
+__host__ __device__ __forceinline__ uint32_t bf_phys(uint32_t x) { return TQEC_BF_SWZ_WIDE ? (x ^ ((x >> 4) & 14u) ^ ((x >> 7) & 14u)) : (x ^ ((x >> 4) & 14u)); }
 __host__ __device__ constexpr int bf_ctz(int k) { return (k & 1) ? 0 : (k & 2) ? 1 : (k & 4) ? 2 : (k & 8) ? 3 : (k & 16) ? 4 : 5; }
 
 template <int C>
