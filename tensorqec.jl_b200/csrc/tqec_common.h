@@ -112,7 +112,7 @@ struct tqec_plan {
   int64_t launches;
   // in-place patch sweep (optional)
   tqec::SweepDev sw;
-  int has_sweep, sw_teams, sw_smem, sw_maxt;
+  int has_sweep, sw_teams, sw_smem, sw_maxt, sw_ext;   // sw_ext: the plan uses fresh-pin shapes (extended instantiation of k_sweep)
   // fully tabulated plan (n_checks <= 16): outputs of every syndrome, filled once by the plan's own kernels
   int has_table;
   uint64_t *d_tab_corr;

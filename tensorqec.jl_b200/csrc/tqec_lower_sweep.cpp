@@ -64,6 +64,7 @@ struct Raw {
   std::vector<std::pair<int, std::vector<int>>> free;      // (variable index j, chains)
   std::vector<std::pair<int, int>> closed;                 // (syndrome bit, chain)
   std::vector<int> chains;
+  std::vector<int> fresh, freed;                           // chains that come alive (fresh pins) / die in this step
 };
 
 struct Layer {
@@ -81,6 +82,7 @@ struct SuperStep {
   bool conflict = false, has_late = false;
   int late_sb = 0, late_bit = 0;
   int wbase = 0, bpp = 0, n_words = 0;
+  std::vector<std::vector<int>> fresh;                     // per layer: chains that come alive
 };
 
 static bool check_has(const Check &c, int v) { return std::find(c.vars.begin(), c.vars.end(), v) != c.vars.end(); }
@@ -113,10 +115,16 @@ static Classified classify(const Factor &f, const Role &R, const std::vector<Che
     int donor = -1;
     for (int c : rest)
       if (closing.count(c) && !donors.count(c)) { donor = c; break; }
-    if (donor < 0) return out;
-    donors.insert(donor);
     PinnedC p;
     p.j = (int)j; p.o = ov[0]; p.c = donor;
+    if (donor < 0) {
+      // FRESH pin: the opened check takes a dead slot; its own slot joins the flip mask of the pinned variable, so that
+      // output bit 1 reads the live (bit 0) half of the slot
+      p.extra = rest;
+      out.pinned.push_back(p);
+      continue;
+    }
+    donors.insert(donor);
     for (int c : rest)
       if (c != donor) p.extra.push_back(c);
     out.pinned.push_back(p);
@@ -156,7 +164,7 @@ static Desc descriptor(const std::vector<const Raw *> &group, const std::vector<
 // axis of that syndrome bit), no data moves.  Output in POSITION order: [head pattern][state index], index bit
 // chain_pos[k] = parity of check live_order[k].
 static void head_eval(const Schedule &sch, int h, const std::vector<Role> &roles, const std::vector<int> &head_bits,
-                      const std::vector<int> &live_order, const std::vector<int> &chain_pos, std::vector<double> &hs,
+                      const std::vector<int> &live_order, const std::vector<int> &chain_pos, int Wt, std::vector<double> &hs,
                       std::vector<uint64_t> &hc) {
   const bool maxplus = sch.semiring == TQEC_SEMIRING_MAXPLUS;
   const int ncw = std::max(1, (sch.n_vars + 63) / 64);
@@ -242,19 +250,24 @@ static void head_eval(const Schedule &sch, int h, const std::vector<Role> &roles
     state_bit[k] = found;
   }
   if ((size_t)1 << (nh + W) != St.size()) throw std::runtime_error("head_eval: size mismatch");
-  hs.assign(St.size(), 0.0);
-  if (maxplus) hc.assign(St.size() * ncw, 0); else hc.assign(((size_t)1 << nh) * ncw, 0);
+  // Wt >= W chains in all: the ones added by fresh pins are dead after the head, their set halves hold the semiring's zero
+  const size_t total = (size_t)1 << (nh + Wt);
+  hs.assign(total, 0.0);
+  if (maxplus) hc.assign(total * ncw, 0); else hc.assign(((size_t)1 << nh) * ncw, 0);
+  uint32_t extra_mask = 0;
+  for (int k = W; k < Wt; ++k) extra_mask |= 1u << chain_pos[k];
   for (size_t hp = 0; hp < ((size_t)1 << nh); ++hp) {
     size_t bsrc = 0;
     for (int j = 0; j < nh; ++j)
       if ((hp >> j) & 1) bsrc |= (size_t)1 << batch_order[j];
-    for (size_t idx = 0; idx < ((size_t)1 << W); ++idx) {
+    for (size_t idx = 0; idx < ((size_t)1 << Wt); ++idx) {
+      if (idx & extra_mask) { hs[(hp << Wt) | idx] = zero; continue; }
       size_t src = bsrc;
       for (int k = 0; k < W; ++k)
         if ((idx >> chain_pos[k]) & 1) src |= (size_t)1 << state_bit[k];
-      hs[(hp << W) | idx] = St[src];
+      hs[(hp << Wt) | idx] = St[src];
       if (maxplus)
-        for (int w = 0; w < ncw; ++w) hc[((hp << W) | idx) * ncw + w] = cfg[src * ncw + w];
+        for (int w = 0; w < ncw; ++w) hc[((hp << Wt) | idx) * ncw + w] = cfg[src * ncw + w];
     }
   }
 }
@@ -453,24 +466,39 @@ bool lower_sweep(const Schedule &sch, int max_head_bits, SweepPlan &plan) {
       if (!has(roles[t].closing, c)) nl.push_back(c);
     live.swap(nl);
   }
-  const int W = (int)live.size();
+  int W = (int)live.size();
   if (W > NB || W < 1) return false;
-  const int sg = NB - W;
-  if (sg > 5) return false;
+  const int W0 = W;                                            // chains alive after the head; fresh pins may add more
   std::map<int, int> chain_of;
   for (int k = 0; k < W; ++k) chain_of[live[k]] = k;
   const std::vector<int> live_order = live;
 
   std::vector<Raw> raw;
+  std::map<int, int> dead_since;                               // chain -> step after which it is free again
   for (int t = h; t < n; ++t) {
     const Role &R = roles[t];
     const Classified &C = cls[t];
     Raw g;
     g.step = t; g.fi = R.fi;
-    for (auto &p : C.pinned) g.pinned.push_back({p.j, chain_of.at(p.c)});
+    for (auto &p : C.pinned)
+      if (p.c < 0) {
+        // a chain that died in an earlier step (such two steps never share a super-step: see match), else a new one
+        int ch = -1;
+        for (auto &kv : dead_since)
+          if (kv.second + 1 <= t) { ch = kv.first; break; }       // (std::map iterates in ascending chain order)
+        if (ch >= 0) dead_since.erase(ch);
+        else {
+          ch = W++;
+          if (W > NB) return false;
+        }
+        chain_of[p.o] = ch;
+        g.fresh.push_back(ch);
+      }
+    for (auto &p : C.pinned) g.pinned.push_back({p.j, p.c >= 0 ? chain_of.at(p.c) : chain_of.at(p.o)});
     for (auto &p : C.pinned) {
       std::vector<int> k;
       for (int c : p.extra) k.push_back(chain_of.at(c));
+      if (p.c < 0) k.push_back(chain_of.at(p.o));
       g.pk.push_back(k);
     }
     for (auto &fr : C.free) {
@@ -485,11 +513,22 @@ bool lower_sweep(const Schedule &sch, int max_head_bits, SweepPlan &plan) {
     for (auto &fr : g.free) chs.insert(fr.second.begin(), fr.second.end());
     for (auto &c : g.closed) chs.insert(c.second);
     g.chains.assign(chs.begin(), chs.end());
-    for (auto &p : C.pinned) chain_of[p.o] = chain_of.at(p.c);
+    std::set<int> donors_used;
+    for (auto &p : C.pinned)
+      if (p.c >= 0) donors_used.insert(chain_of.at(p.c));
+    for (auto &p : C.pinned)
+      if (p.c >= 0) chain_of[p.o] = chain_of.at(p.c);
+    for (int c : R.closing)
+      if (!donors_used.count(chain_of.at(c))) {
+        dead_since[chain_of.at(c)] = t;
+        g.freed.push_back(chain_of.at(c));
+      }
     const size_t nch = g.chains.size();
     raw.push_back(g);
     if (nch > (size_t)MAX_PATCH || nch == 0) return false;
   }
+  const int sg = NB - W;
+  if (sg > 5 || sg < 0) return false;
   std::vector<int> final_live;
   for (auto &kv : chain_of)
     if (checks[kv.first].kind == 1) final_live.push_back(kv.first);
@@ -506,6 +545,10 @@ bool lower_sweep(const Schedule &sch, int max_head_bits, SweepPlan &plan) {
     for (auto *g : group) cs.insert(g->chains.begin(), g->chains.end());
     std::vector<int> chains(cs.begin(), cs.end());
     if ((int)chains.size() > MAX_PATCH) return m;
+    if (cnt == 2)
+      for (int a : group[0]->freed)
+        for (int b : group[1]->fresh)
+          if (a == b) return m;                                // a slot cannot die and reopen inside one super-step
     if (cnt == 2) {
       int both = 0;
       for (auto &p : group[0]->pinned)
@@ -583,6 +626,7 @@ bool lower_sweep(const Schedule &sch, int max_head_bits, SweepPlan &plan) {
           L.T[((size_t)pidx << NF) | kk] = st.table[a];
         }
       ss.layers.push_back(L);
+      ss.fresh.push_back(g.fresh);
     }
     if (cnt == 2) {
       int b = -1;
@@ -612,8 +656,8 @@ bool lower_sweep(const Schedule &sch, int max_head_bits, SweepPlan &plan) {
   for (auto &ss : ssteps) groups.push_back(ss.chains);
   auto ap = assign_positions(groups, W);
   const std::vector<int> &chain_pos = ap.first;
-  std::set<int> alive;
-  for (int k = 0; k < W; ++k) alive.insert(k);
+  std::set<int> alive;                                         // chains beyond W0 come alive when a fresh pin opens them
+  for (int k = 0; k < W0; ++k) alive.insert(k);
   int wbase = 0;
   for (auto &ss : ssteps) {
     ss.pos.clear();
@@ -654,7 +698,9 @@ bool lower_sweep(const Schedule &sch, int max_head_bits, SweepPlan &plan) {
     }
     ss.wbase = wbase;
     wbase += ss.n_words;
-    for (auto &l : ss.layers) {
+    for (size_t li = 0; li < ss.layers.size(); ++li) {
+      const Layer &l = ss.layers[li];
+      alive.insert(ss.fresh[li].begin(), ss.fresh[li].end());
       std::set<int> reused;
       for (auto &p : l.pinned) reused.insert(p.second);
       for (auto &c : l.closed)
@@ -692,7 +738,7 @@ bool lower_sweep(const Schedule &sch, int max_head_bits, SweepPlan &plan) {
   plan.W = W; plan.sg = sg; plan.head_steps = h; plan.n_ss = (int)ssteps.size(); plan.bp_words = wbase; plan.conflicts = ap.second;
   plan.head_bits = head_bits;
   plan.out_index = out_index;
-  head_eval(sch, h, roles, head_bits, live_order, chain_pos, plan.head_state, plan.head_cfg);
+  head_eval(sch, h, roles, head_bits, live_order, chain_pos, W, plan.head_state, plan.head_cfg);
   encode_sweep(plan, ssteps);
   return true;
 }

@@ -190,7 +190,9 @@ __device__ __forceinline__ void sweep_step(const int32_t *__restrict__ rec, cons
   }
 }
 
-template <int SEMI, int MAXT>
+// EXT = 1 additionally compiles the shapes with fresh pins (menu ids TQEC_SWEEP_MENU_BASE .. TQEC_SWEEP_MENU_MAXPLUS - 1: even-
+// distance and rectangular codes); plans that do not use them run the EXT = 0 instantiation, whose code is unchanged
+template <int SEMI, int MAXT, int EXT>
 __global__ void __launch_bounds__(MAXT, 1)
 k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, uint64_t *__restrict__ corr,
         double *__restrict__ out, int32_t *__restrict__ argmax_out, uint32_t *__restrict__ bp_all) {
@@ -304,7 +306,7 @@ k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, ui
         switch (rec[0]) {
 #define SW_CASE(ID, M, NL, NP0, P00, P01, NF0, F00, F01, K00, K01, NP1, P10, P11, NF1, F10, F11, K10, K11)               \
   case ID:                                                                                                             \
-    if (SEMI == TQEC_SEMIRING_SUMPROD || ID < TQEC_SWEEP_MENU_MAXPLUS)   /* keeps the max-plus kernel's code small */    \
+    if (ID < TQEC_SWEEP_MENU_BASE || (ID < TQEC_SWEEP_MENU_MAXPLUS ? EXT != 0 : SEMI == TQEC_SEMIRING_SUMPROD))  /* code size */ \
       sweep_step<SEMI, M, NL, NP0, P00, P01, NF0, F00, F01, K00, K01, NP1, P10, P11, NF1, F10, F11, K10, K11>(         \
           rec, sm_tv, st_abs, lt, srow, lrow, bpf, lane);                                                             \
     break;
@@ -418,8 +420,9 @@ k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, ui
 }
 
 template <int SEMI>
-static const void *sweep_kernel(int maxt) {
-  return maxt == 768 ? (const void *)k_sweep<SEMI, 768> : maxt == 640 ? (const void *)k_sweep<SEMI, 640> : (const void *)k_sweep<SEMI, 512>;
+static const void *sweep_kernel(int maxt, int ext) {
+  if (ext) return (const void *)k_sweep<SEMI, 512, 1>;          // (the register-budget variants exist for the base menu only)
+  return maxt == 768 ? (const void *)k_sweep<SEMI, 768, 0> : maxt == 640 ? (const void *)k_sweep<SEMI, 640, 0> : (const void *)k_sweep<SEMI, 512, 0>;
 }
 
 int launch_sweep(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d_corr, double *d_out, int32_t *d_argmax,
@@ -427,8 +430,8 @@ int launch_sweep(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d
   const int64_t groups = (B + plan->sw.grp - 1) / plan->sw.grp;
   const int64_t ctas = (groups + plan->sw_teams - 1) / plan->sw_teams;
   const int grid = (int)(ctas < plan->sm_count ? ctas : plan->sm_count);
-  const void *kern = plan->semiring == TQEC_SEMIRING_MAXPLUS ? sweep_kernel<TQEC_SEMIRING_MAXPLUS>(plan->sw_maxt)
-                                                             : sweep_kernel<TQEC_SEMIRING_SUMPROD>(plan->sw_maxt);
+  const void *kern = plan->semiring == TQEC_SEMIRING_MAXPLUS ? sweep_kernel<TQEC_SEMIRING_MAXPLUS>(plan->sw_maxt, plan->sw_ext)
+                                                             : sweep_kernel<TQEC_SEMIRING_SUMPROD>(plan->sw_maxt, plan->sw_ext);
   void *args[] = {(void *)&plan->sw, (void *)&d_synd, (void *)&B, (void *)&d_corr, (void *)&d_out, (void *)&d_argmax,
                   (void *)&plan->d_sw_bp};
   TQEC_CUDA(cudaLaunchKernel(kern, dim3(grid), dim3(32 * plan->sw_teams), args, (size_t)plan->sw_smem, stream));
@@ -514,9 +517,16 @@ int sweep_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &pr
   // register budget variant: 512 threads (128 registers), 640 (96) or 768 (80); TQEC_SWEEP_MAXT overrides the default
   int maxt = 512;
   if (const char *e = std::getenv("TQEC_SWEEP_MAXT")) { const int v = std::atoi(e); if (v == 768 || v == 640 || v == 512) maxt = v; }
-  const void *kern = d->semiring == TQEC_SEMIRING_MAXPLUS ? sweep_kernel<TQEC_SEMIRING_MAXPLUS>(maxt)
-                                                          : sweep_kernel<TQEC_SEMIRING_SUMPROD>(maxt);
+  int ext = 0;
+  for (int i = 0; i < s->n_ss; ++i) {
+    const int id = s->rec[(size_t)i * SW_REC_INTS];
+    if (id >= TQEC_SWEEP_MENU_BASE && id < TQEC_SWEEP_MENU_MAXPLUS) ext = 1;
+  }
+  if (ext) maxt = 512;
+  const void *kern = d->semiring == TQEC_SEMIRING_MAXPLUS ? sweep_kernel<TQEC_SEMIRING_MAXPLUS>(maxt, ext)
+                                                          : sweep_kernel<TQEC_SEMIRING_SUMPROD>(maxt, ext);
   p->sw_maxt = maxt;
+  p->sw_ext = ext;
   cudaFuncAttributes fa;
   TQEC_CUDA(cudaFuncGetAttributes(&fa, kern));
   int cap = fa.maxThreadsPerBlock / 32;

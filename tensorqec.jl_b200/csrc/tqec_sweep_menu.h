@@ -17,10 +17,21 @@
   X(9, 3, 2, 1, 0, -1, 1, 2, 0, 0, 0, 1, 1, -1, 1, 5, 0, 0, 0) \
   X(10, 3, 2, 1, 0, -1, 1, 6, 0, 0, 0, 1, 1, -1, 1, 1, 0, 0, 0) \
   X(11, 4, 2, 1, 0, -1, 1, 6, 0, 0, 0, 1, 1, -1, 1, 9, 0, 0, 0) \
-  X(12, 4, 1, 1, 0, -1, 1, 14, 0, 0, 0, 0, -1, -1, 0, 0, 0, 0, 0) \
-  X(13, 4, 1, 1, 0, -1, 1, 6, 0, 8, 0, 0, -1, -1, 0, 0, 0, 0, 0) \
-  X(14, 4, 2, 1, 0, -1, 1, 2, 0, 0, 0, 1, 1, -1, 1, 5, 0, 8, 0) \
-  X(15, 4, 2, 1, 0, -1, 1, 2, 0, 0, 0, 1, 2, -1, 1, 10, 0, 1, 0) \
-  X(16, 4, 2, 1, 0, -1, 1, 6, 0, 0, 0, 0, -1, -1, 2, 9, 6, 0, 0)
-#define TQEC_SWEEP_MENU_SIZE 17
-#define TQEC_SWEEP_MENU_MAXPLUS 12 /* shapes 0..11 are compiled into the max-plus kernel; 12.. are sum-product only */
+  /* 12..19: shapes with FRESH pins (K contains the pinned variable's own bit: the opened check takes a dead slot, output \
+     bit 1 reads the live half) and their neighbours -- even-distance and rectangular rotated surface codes */ \
+  X(12, 3, 1, 2, 0, 1, 0, 0, 0, 5, 2, 0, -1, -1, 0, 0, 0, 0, 0) \
+  X(13, 3, 1, 0, -1, -1, 2, 1, 6, 0, 0, 0, -1, -1, 0, 0, 0, 0, 0) \
+  X(14, 4, 2, 1, 0, -1, 1, 6, 0, 0, 0, 1, 3, -1, 1, 2, 0, 0, 0) \
+  X(15, 3, 2, 2, 0, 1, 0, 0, 0, 5, 2, 0, -1, -1, 2, 1, 2, 0, 0) \
+  X(16, 4, 2, 1, 0, -1, 1, 2, 0, 0, 0, 1, 2, -1, 1, 10, 0, 0, 0) \
+  X(17, 3, 2, 2, 0, 1, 0, 0, 0, 5, 2, 1, 0, -1, 1, 2, 0, 0, 0) \
+  X(18, 3, 2, 0, -1, -1, 2, 1, 2, 0, 0, 1, 1, -1, 1, 4, 0, 0, 0) \
+  X(19, 3, 2, 1, 0, -1, 1, 2, 0, 0, 0, 0, -1, -1, 2, 2, 5, 0, 0) \
+  X(20, 4, 1, 1, 0, -1, 1, 14, 0, 0, 0, 0, -1, -1, 0, 0, 0, 0, 0) \
+  X(21, 4, 1, 1, 0, -1, 1, 6, 0, 8, 0, 0, -1, -1, 0, 0, 0, 0, 0) \
+  X(22, 4, 2, 1, 0, -1, 1, 2, 0, 0, 0, 1, 1, -1, 1, 5, 0, 8, 0) \
+  X(23, 4, 2, 1, 0, -1, 1, 2, 0, 0, 0, 1, 2, -1, 1, 10, 0, 1, 0) \
+  X(24, 4, 2, 1, 0, -1, 1, 6, 0, 0, 0, 0, -1, -1, 2, 9, 6, 0, 0)
+#define TQEC_SWEEP_MENU_SIZE 25
+#define TQEC_SWEEP_MENU_MAXPLUS 20 /* shapes 0..19 are compiled into the max-plus kernel; 20.. are sum-product only */
+#define TQEC_SWEEP_MENU_BASE 12    /* shapes 12..19 only in the extended instantiation of k_sweep (plans with fresh pins) */

@@ -769,9 +769,23 @@ int wide_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &pro
                          (int64_t)r[11] + TQEC_BF_G + r[2] <= w->n_bf_vals,
                      "wide: bad butterfly group %d of pass %d", g, i);
         for (int j = 0; j < TQEC_BF_G; ++j) TQEC_REQUIRE(r[5 + j] > 0 && r[5 + j] < 4096, "wide: bad basis vector in pass %d", i);
+        uint32_t seen = 0;
+        for (int q = 0; q < r[0]; ++q) {
+          const uint32_t pq = ((uint32_t)r[13] >> (4 * q)) & 15u;
+          TQEC_REQUIRE(pq < 12 && !((seen >> pq) & 1u), "wide: bad coset enumeration order in pass %d", i);
+          seen |= 1u << pq;
+        }
         s_sum += r[2]; c_sum += r[4];
       }
       TQEC_REQUIRE(s_sum == ns && c_sum == nc, "wide: butterfly groups of pass %d do not cover its steps", i);
+      {
+        uint32_t seen = 0;
+        for (int q = 0; q < 12; ++q) {
+          const int pq = bfp[8 + q];
+          TQEC_REQUIRE(q < bfp[6] ? (pq >= 0 && pq < 12 && !((seen >> pq) & 1u)) : pq == -1, "wide: bad output positions in pass %d", i);
+          if (pq >= 0) seen |= 1u << pq;
+        }
+      }
       for (int q = 0; q < ns; ++q) TQEC_REQUIRE(crec[q - ns] > 0 && crec[q - ns] < (1 << TQEC_BF_G), "wide: bad dependent step in pass %d", i);
       for (int c = 0; c < nc; ++c)
         TQEC_REQUIRE(crec[2 * c] >= 0 && crec[2 * c] < 12 && crec[2 * c + 1] >= 0 && crec[2 * c + 1] < d->n_checks, "wide: bad close record in pass %d", i);

@@ -62,6 +62,17 @@ MENU: List[tuple] = [
     (3, (((0,), (2,)), ((1,), (5,)))),
     (3, (((0,), (6,)), ((1,), (1,)))),
     (4, (((0,), (6,)), ((1,), (9,)))),
+    # shapes with FRESH pins (a pinned variable whose flip mask contains its own bit: the opened check takes a dead slot)
+    # and the shapes around them: even-distance and rectangular rotated surface codes
+    (3, (((0, 1), (), (5, 2)),)),
+    (3, (((), (1, 6)),)),
+    (4, (((0,), (6,)), ((3,), (2,)))),
+    (3, (((0, 1), (), (5, 2)), ((), (1, 2)))),
+    (4, (((0,), (2,)), ((2,), (10,)))),
+    (3, (((0, 1), (), (5, 2)), ((0,), (2,)))),
+    (3, (((), (1, 2)), ((1,), (4,)))),
+    (3, (((0,), (2,)), ((), (2, 5)))),
+    # sum-product only
     (4, (((0,), (14,)),)),
     (4, (((0,), (6,), (8,)),)),
     (4, (((0,), (2,)), ((1,), (5,), (8,)))),
@@ -70,7 +81,7 @@ MENU: List[tuple] = [
 ]
 
 
-MENU_MAXPLUS = 12       # shapes 0..11 are compiled into the max-plus kernel; later ones are sum-product only
+MENU_MAXPLUS = 20       # shapes 0..19 are compiled into the max-plus kernel; later ones are sum-product only
 _DISCOVER = None
 
 
@@ -104,6 +115,7 @@ class SuperStep:
     looppos: List[int] = field(default_factory=list)    # active positions walked by the iteration loop
     conflict: bool = False
     late: Optional[Tuple[int, int]] = None     # (syndrome bit, patch bit): check opened by layer 0 and closed by layer 1
+    fresh: List[List[int]] = field(default_factory=list)      # per layer: chains that come alive (fresh pins)
     wbase: int = 0                             # first back-pointer word (per lane) of the step inside a pass
     bpp: int = 0                               # back-pointer bits per patch
     n_words: int = 0
@@ -182,7 +194,10 @@ def _classify(f, touched, opened, closing, checks):
         rest = [c for c in tv if c != ov[0]]
         cand = [c for c in rest if c in closing and c not in donors]
         if not cand:
-            return None
+            # FRESH pin: the opened check takes a dead slot (donor None); its own slot joins the flip mask of the pinned
+            # variable, so that output bit 1 reads the live (bit 0) half of the slot
+            pinned.append((j, ov[0], None, rest))
+            continue
         donors.add(cand[0])
         pinned.append((j, ov[0], cand[0], [c for c in rest if c != cand[0]]))
     if len(pinned) > 2 or len(free) > 2:
@@ -365,29 +380,53 @@ def lower_sweep(sch: S.Schedule, max_head_bits: int = MAX_HEAD_BITS) -> Optional
     W = len(live)
     if W > NB or W < 1:
         return None
-    sg = NB - W
-    if sg > 5:
-        return None
     chain_of = {c: k for k, c in enumerate(live)}
     live_order = list(live)
+    W0 = W                                                     # chains alive after the head; fresh pins may add more
 
     # layers in chain coordinates
     raw = []
+    dead_since: dict = {}                                      # chain -> step after which it is free again
+    fresh_at: List[List[int]] = []
     for t in range(h, n):
         fi, touched, opened, closing = roles[t]
         pinned, free = cls[t]
         f = factors[fi]
-        lp = [(j, chain_of[c]) for j, o, c, _ in pinned]
-        lk = [[chain_of[c] for c in extra] for _, _, _, extra in pinned]
+        fresh_chains = []
+        for j, o, c, _ in pinned:
+            if c is None:
+                # a chain that died in an earlier step (such two steps never share a super-step: see match), else a new one
+                cands = sorted(ch for ch, ts in dead_since.items() if ts + 1 <= t)
+                if cands:
+                    ch = cands[0]
+                    del dead_since[ch]
+                else:
+                    ch = W
+                    W += 1
+                    if W > NB:
+                        return None
+                chain_of[o] = ch
+                fresh_chains.append(ch)
+        lp = [(j, chain_of[c] if c is not None else chain_of[o]) for j, o, c, _ in pinned]
+        lk = [[chain_of[c] for c in extra] + ([chain_of[o]] if c0 is None else []) for _, o, c0, extra in pinned]
         lf = [(j, [chain_of[c] for c in tv]) for j, tv in free]
         lc = [(checks[c].index, chain_of[c]) for c in closing]
         chains = sorted({ch for _, ch in lp} | {ch for chs in lk for ch in chs} | {ch for _, chs in lf for ch in chs} |
                         {ch for _, ch in lc})
+        donors_used = {chain_of[c] for _, _, c, _ in pinned if c is not None}
         for j, o, c, _ in pinned:
-            chain_of[o] = chain_of[c]
-        raw.append(dict(step=t, fi=fi, pinned=lp, pk=lk, free=lf, closed=lc, chains=chains))
+            if c is not None:
+                chain_of[o] = chain_of[c]
+        for c in closing:
+            if chain_of[c] not in donors_used:
+                dead_since[chain_of[c]] = t
+        freed = [chain_of[c] for c in closing if chain_of[c] not in donors_used]
+        raw.append(dict(step=t, fi=fi, pinned=lp, pk=lk, free=lf, closed=lc, chains=chains, fresh=fresh_chains, freed=freed))
         if len(chains) > MAX_PATCH or len(chains) == 0:
             return None
+    sg = NB - W
+    if sg > 5 or sg < 0:
+        return None
     # an observable must still be alive at the end, everything else dead
     final_live = [c for c in chain_of if checks[c].kind == "obs"]
     menu_ix = {m: i for i, m in enumerate(MENU) if sch.semiring == S.SUMPROD or i < MENU_MAXPLUS}
@@ -408,6 +447,8 @@ def lower_sweep(sch: S.Schedule, max_head_bits: int = MAX_HEAD_BITS) -> Optional
         chains = sorted({ch for g in group for ch in g["chains"]})
         if len(chains) > MAX_PATCH:
             return None
+        if len(group) == 2 and set(group[0]["freed"]) & set(group[1]["fresh"]):
+            return None                                        # a slot cannot die and reopen inside one super-step
         if len(group) == 2:
             # a check opened by the first layer and closed by the second cannot be folded into the load address (its
             # slot still holds the first layer's closed check): its syndrome bit is applied late -- to the second
@@ -466,6 +507,7 @@ def lower_sweep(sch: S.Schedule, max_head_bits: int = MAX_HEAD_BITS) -> Optional
                     T[(pidx << NF) | kk] = st.table[a]
             layers.append(Layer(g["step"], g["fi"], tuple(f.vars), pinned, free, closed, T, pk))
         ss = SuperStep(layers, list(perm), mi)
+        ss.fresh = [list(g["fresh"]) for g in raw[k:k + cnt]]
         if cnt == 2:
             both = {pb for _, pb in layers[0].pinned} & {cb for _, cb in layers[1].closed}
             if both:
@@ -481,7 +523,7 @@ def lower_sweep(sch: S.Schedule, max_head_bits: int = MAX_HEAD_BITS) -> Optional
     # positions: chains -> 0..W-1, shot bits -> W..NB-1
     chain_pos, n_conf = _assign_positions([ss.chains for ss in ssteps], W)
     # liveness of chains per super-step (a chain is dead after the step that closes it without re-opening)
-    alive = set(range(W))
+    alive = set(range(W0))                                     # chains beyond W0 come alive when a fresh pin opens them
     wbase = 0
     for ss in ssteps:
         M = len(ss.chains)
@@ -508,8 +550,9 @@ def lower_sweep(sch: S.Schedule, max_head_bits: int = MAX_HEAD_BITS) -> Optional
             ss.n_words = (n_iter + ipw - 1) // ipw
         ss.wbase = wbase
         wbase += ss.n_words
-        # chains that die in this super-step
-        for l in ss.layers:
+        # chains that come alive (fresh pins) and chains that die in this super-step, layer by layer
+        for li, l in enumerate(ss.layers):
+            alive.update(ss.fresh[li])
             reused = {pb for _, pb in l.pinned}
             for _, cb in l.closed:
                 if cb not in reused:
@@ -528,6 +571,15 @@ def lower_sweep(sch: S.Schedule, max_head_bits: int = MAX_HEAD_BITS) -> Optional
         return None
 
     hs, hc = _head_eval(sch, h, roles, head_bits, live_order)
+    if W > W0:
+        # chains added by fresh pins are dead after the head: their set halves hold the semiring's zero
+        ext = np.full((hs.shape[0], 1 << W), -np.inf if sch.semiring == S.MAXPLUS else 0.0)
+        ext[:, : 1 << W0] = hs
+        hs = ext
+        if hc is not None:
+            extc = np.zeros((hc.shape[0], 1 << W, hc.shape[2]), dtype=np.uint64)
+            extc[:, : 1 << W0, :] = hc
+            hc = extc
     # head table in POSITION order: index bit chain_pos[k] = parity of chain k
     idx = np.arange(1 << W)
     src = np.zeros_like(idx)

@@ -93,6 +93,42 @@ def test_sweep_kernel_edge_cases(tq, d, monkeypatch):
     plan2.close()
 
 
+@pytest.mark.parametrize("dx,dz", [(6, 6), (8, 8), (5, 7)])
+def test_sweep_kernel_even_and_rectangular_codes(tq, dx, dz, monkeypatch):
+    """k_sweep on even-distance and rectangular rotated surface codes: their sweeps open checks into dead slots (fresh
+    pins: a pinned variable whose flip mask contains its own bit) and close checks without a successor.  Bit-identical to
+    the C port of the recurrence and to the general kernels on the same unfused schedule; default (p, p, p) noise and
+    per-qubit noise."""
+    from tensorqec.jl_b200 import _cabi
+    n = dx * dz
+    t = tq.CSSTannerGraph(tq.SurfaceCode(dx, dz))
+    rng = np.random.default_rng(dx * 10 + dz)
+    for em in (tq.iid_error(0.05, t),
+               tq.IndependentDepolarizingError(rng.uniform(0.01, 0.1, n), rng.uniform(0.01, 0.1, n), rng.uniform(0.01, 0.1, n))):
+        ct = tq.compile(tq.TNMAP(), t, em)
+        sch = ct.cd.schedule
+        assert ct.cd.plan.query(_cabi.Q_SWEEP) == 1 and getattr(sch, "sweep", None) is not None
+        ex, ez, sx, sz = _syndromes(t, em, 78, 600)
+        syn = np.concatenate([sx, sz], axis=1)
+        syn[0] = 0
+        syn[1] = 1
+        oracle_plan = cref.FrontierPlan(sch)
+        for B in (1, 33, 600):
+            corr, logp = ct.cd.plan.decode_map(tq.pack_bits(syn[:B]))
+            lp, cfg = oracle_plan.run(syn[:B])
+            assert np.array_equal(tq.unpack_bits(corr, 2 * n), cfg) and np.array_equal(logp, lp)
+        res = tq.decode(ct, tq.CSSSyndrome(sx, sz))
+        assert tq.syndrome_extraction(res.error_pattern, t) == tq.CSSSyndrome(sx, sz)
+        corr, logp = ct.cd.plan.decode_map(tq.pack_bits(syn))
+        monkeypatch.setenv("TQEC_NO_SWEEP", "1")
+        plan2 = _cabi.Plan(sch, 0)
+        monkeypatch.delenv("TQEC_NO_SWEEP")
+        assert plan2.query(_cabi.Q_SWEEP) == 0
+        corr2, logp2 = plan2.decode_map(tq.pack_bits(syn))
+        assert np.array_equal(corr, corr2) and np.array_equal(logp, logp2)
+        plan2.close()
+
+
 def test_sweep_kernel_long_head(tq):
     """The 12-bit tabulated head bench.py uses (17 of the 81 steps of d = 9 become a table look-up): same corrections and
     log-weights, bit for bit, as the C port of the full recurrence and as the default 10-bit head."""

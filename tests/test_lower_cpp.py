@@ -51,9 +51,9 @@ def _check_schedule(lw, py):
             (sw.W, sw.sg, len(sw.ssteps), sw.bp_words, sw.head_steps, sw.conflicts)
 
 
-@pytest.mark.parametrize("code", ["d3", "d5", "d7", "d9", "steane", "color488_5", "d4", "d6"])
+@pytest.mark.parametrize("code", ["d3", "d5", "d7", "d9", "steane", "color488_5", "d4", "d6", "d8", "d5x7"])
 def test_tnmap_tables_identical(code):
-    c = {"steane": tq.SteaneCode(), "color488_5": tq.Color488(5)}.get(code) or tq.SurfaceCode(int(code[1:]), int(code[1:]))
+    c = {"steane": tq.SteaneCode(), "color488_5": tq.Color488(5), "d5x7": tq.SurfaceCode(5, 7)}.get(code) or tq.SurfaceCode(int(code[1:]), int(code[1:]))
     factors, checks, nq, ns = _tnmap_graph(c)
     py = D._tnmap_lower(tq.TNMAP(), factors, checks, nq, ns, None)
     lw = _cabi.Lowered(_cabi.Problem(factors, checks, S.MAXPLUS, nq, ns, 0, head_bits=12))

@@ -46,6 +46,30 @@ def test_sweep_emulator_matches_recurrence_bit_exact(tq, d, B):
     assert np.array_equal((cfg @ H.T) % 2, syn)                  # every correction reproduces its syndrome
 
 
+@pytest.mark.parametrize("dx,dz,B", [(6, 6, 40), (8, 8, 16), (5, 7, 40)])
+def test_sweep_fresh_pins_even_and_rectangular_codes(tq, dx, dz, B):
+    """Even-distance and rectangular rotated surface codes: their sweeps contain steps that open a check without closing
+    one through the same variable (column turns).  Such a FRESH pin takes a dead slot -- a pinned variable whose flip
+    mask contains its own bit, so output bit 1 reads the live half -- and a check may close without a successor.  The
+    emulator stays bit-identical to the recurrence."""
+    from tensorqec.jl_b200 import schedule as S, sweep as SW
+    t = tq.CSSTannerGraph(tq.SurfaceCode(dx, dz))
+    em = tq.iid_error(0.05, t)
+    gdp, _ = tq.reduce2general(t, em)
+    factors = [S.Factor(tuple(int(v) for v in ix), S.flat_table(tt)) for ix, tt in zip(gdp.ptn.ixs, gdp.ptn.tensors)]
+    checks = [S.Check(tuple(c), "syn", s) for s, c in enumerate(gdp.tanner.s2q)]
+    su = S.lower(factors, checks, S.MAXPLUS, gdp.tanner.nq, gdp.tanner.ns, 0, fuse=False)
+    pl = SW.lower_sweep(su, 12)
+    assert pl is not None, "the plan should fit the in-place patch sweep"
+    if dx == dz:
+        assert any(any(l.pk and any((m >> pb) & 1 for (_, pb), m in zip(l.pinned, l.pk)) for l in ss.layers) for ss in pl.ssteps), "no fresh pin"
+    syn = _syndromes(t, em, 200 + dx, B)
+    syn[0] = 0
+    lp, cfg = sweep_emulator.run(pl, SW.MENU, syn)
+    lp0, cfg0 = frontier.run(su.factors, su.checks, su.order, 0, syn, su.n_vars)
+    assert np.array_equal(lp, lp0) and np.array_equal(cfg, cfg0)
+
+
 @pytest.mark.parametrize("bits", [6, 8, 12])
 def test_sweep_head_bits_do_not_change_results(tq, bits):
     """A longer tabulated head (TNMAP(head_bits=...)) removes steps from the per-shot path, not from the arithmetic: the
