@@ -211,7 +211,7 @@ class _LazySchedule:
                 import warnings
                 warnings.warn(f"{type(decoder).__name__}: this plan (frontier {lw['w_max']} bits) does not fit the in-place patch sweep "
                               f"(k_sweep) and decodes through the general frontier kernels, at roughly half the throughput; "
-                              f"odd-distance rotated surface codes in the library's own order do fit", RuntimeWarning, stacklevel=4)
+                              f"rotated surface codes (d = 5 .. 9, even and rectangular ones included) in the library's own order do fit", RuntimeWarning, stacklevel=4)
 
     @property
     def schedule(self):

@@ -18,6 +18,9 @@ The recurrence is the one of schedule.py (one factor absorbed per step, candidat
   * LATE FOLD.  A check opened by the first layer of a super-step and closed by the second cannot be folded into the
     load address (its slot still holds the first layer's closed check); its syndrome bit is applied to the second
     layer's table rows (a row-swapped copy of the table, chosen per shot) and to the store address instead.
+  * FRESH PINS.  A variable may also open a check without closing one (the column turn of an even-distance code): the
+    opened check then takes a DEAD slot (a chain whose check closed without a successor, or a new one) and the pinned
+    variable's flip mask contains its own bit, so that output bit 1 reads the live (bit 0) half of the slot.
   * PINNED / FREE VARIABLES.  A variable that opens a check is pinned to that check's output bit (the opened check
     inherits the slot of a check the same variable closes) and may flip further patch bits when it is 1; a variable
     that opens nothing is a candidate dimension (butterfly over its flip mask).  Observable checks of sum-product
