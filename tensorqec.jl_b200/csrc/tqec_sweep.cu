@@ -306,7 +306,8 @@ k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, ui
         switch (rec[0]) {
 #define SW_CASE(ID, M, NL, NP0, P00, P01, NF0, F00, F01, K00, K01, NP1, P10, P11, NF1, F10, F11, K10, K11)               \
   case ID:                                                                                                             \
-    if (ID < TQEC_SWEEP_MENU_BASE || (ID < TQEC_SWEEP_MENU_MAXPLUS ? EXT != 0 : SEMI == TQEC_SEMIRING_SUMPROD))  /* code size */ \
+    if (ID < TQEC_SWEEP_MENU_BASE || (ID < TQEC_SWEEP_MENU_MAXPLUS ? EXT != 0                                              \
+                                          : (SEMI == TQEC_SEMIRING_SUMPROD && (ID < TQEC_SWEEP_MENU_SP_BASE || EXT != 0))))  /* code size */ \
       sweep_step<SEMI, M, NL, NP0, P00, P01, NF0, F00, F01, K00, K01, NP1, P10, P11, NF1, F10, F11, K10, K11>(         \
           rec, sm_tv, st_abs, lt, srow, lrow, bpf, lane);                                                             \
     break;
@@ -520,7 +521,7 @@ int sweep_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &pr
   int ext = 0;
   for (int i = 0; i < s->n_ss; ++i) {
     const int id = s->rec[(size_t)i * SW_REC_INTS];
-    if (id >= TQEC_SWEEP_MENU_BASE && id < TQEC_SWEEP_MENU_MAXPLUS) ext = 1;
+    if ((id >= TQEC_SWEEP_MENU_BASE && id < TQEC_SWEEP_MENU_MAXPLUS) || id >= TQEC_SWEEP_MENU_SP_BASE) ext = 1;
   }
   if (ext) maxt = 512;
   const void *kern = d->semiring == TQEC_SEMIRING_MAXPLUS ? sweep_kernel<TQEC_SEMIRING_MAXPLUS>(maxt, ext)

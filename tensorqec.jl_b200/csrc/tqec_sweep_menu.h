@@ -31,7 +31,16 @@
   X(21, 4, 1, 1, 0, -1, 1, 6, 0, 8, 0, 0, -1, -1, 0, 0, 0, 0, 0) \
   X(22, 4, 2, 1, 0, -1, 1, 2, 0, 0, 0, 1, 1, -1, 1, 5, 0, 8, 0) \
   X(23, 4, 2, 1, 0, -1, 1, 2, 0, 0, 0, 1, 2, -1, 1, 10, 0, 1, 0) \
-  X(24, 4, 2, 1, 0, -1, 1, 6, 0, 0, 0, 0, -1, -1, 2, 9, 6, 0, 0)
-#define TQEC_SWEEP_MENU_SIZE 25
+  X(24, 4, 2, 1, 0, -1, 1, 6, 0, 0, 0, 0, -1, -1, 2, 9, 6, 0, 0) \
+  /* 25..31: sum-product only, extended instantiation: TNMMAP plans of even-distance and rectangular codes */ \
+  X(25, 4, 1, 0, -1, -1, 2, 3, 12, 0, 0, 0, -1, -1, 0, 0, 0, 0, 0) \
+  X(26, 3, 1, 2, 0, 1, 0, 0, 0, 1, 6, 0, -1, -1, 0, 0, 0, 0, 0) \
+  X(27, 4, 2, 2, 0, 1, 0, 0, 0, 1, 6, 1, 2, -1, 1, 9, 0, 0, 0) \
+  X(28, 4, 2, 2, 0, 1, 0, 0, 0, 1, 6, 0, -1, -1, 2, 9, 6, 0, 0) \
+  X(29, 3, 2, 1, 0, -1, 1, 6, 0, 0, 0, 1, 0, -1, 1, 6, 0, 0, 0) \
+  X(30, 4, 2, 1, 0, -1, 1, 6, 0, 0, 0, 0, -1, -1, 2, 6, 9, 0, 0) \
+  X(31, 3, 2, 1, 0, -1, 1, 6, 0, 0, 0, 0, -1, -1, 2, 6, 1, 0, 0)
+#define TQEC_SWEEP_MENU_SIZE 32
 #define TQEC_SWEEP_MENU_MAXPLUS 20 /* shapes 0..19 are compiled into the max-plus kernel; 20.. are sum-product only */
 #define TQEC_SWEEP_MENU_BASE 12    /* shapes 12..19 only in the extended instantiation of k_sweep (plans with fresh pins) */
+#define TQEC_SWEEP_MENU_SP_BASE 25 /* sum-product shapes 25.. only in the extended instantiation as well */

@@ -81,6 +81,14 @@ MENU: List[tuple] = [
     (4, (((0,), (2,)), ((1,), (5,), (8,)))),
     (4, (((0,), (2,)), ((2,), (10,), (1,)))),
     (4, (((0,), (6,)), ((), (9, 6)))),
+    # sum-product only, extended instantiation: TNMMAP plans of even-distance and rectangular codes
+    (4, (((), (3, 12)),)),
+    (3, (((0, 1), (), (1, 6)),)),
+    (4, (((0, 1), (), (1, 6)), ((2,), (9,)))),
+    (4, (((0, 1), (), (1, 6)), ((), (9, 6)))),
+    (3, (((0,), (6,)), ((0,), (6,)))),
+    (4, (((0,), (6,)), ((), (6, 9)))),
+    (3, (((0,), (6,)), ((), (6, 1)))),
 ]
 
 

@@ -360,6 +360,29 @@ def test_tnmmap_d9_through_the_sweep(tq):
     assert tq.syndrome_extraction(res.error_pattern, t) == tq.CSSSyndrome(sx, sz)
 
 
+@pytest.mark.parametrize("dx,dz", [(6, 6), (5, 7), (6, 8)])
+def test_tnmmap_even_and_rectangular_codes_through_the_sweep(tq, dx, dz):
+    """TNMMAP (CSS) of even-distance and rectangular codes on k_sweep<SUMPROD> (fresh pins, extended instantiation):
+    against the C port of the recurrence at the north-star tolerance."""
+    from tensorqec.jl_b200 import _cabi
+    t, em = _css_case(tq, tq.SurfaceCode(dx, dz))
+    ct = tq.compile(tq.TNMMAP(), t, em)
+    assert ct.plan.query(_cabi.Q_SWEEP) == 1
+    ex, ez, sx, sz = _syndromes(t, em, 100 + dx, 300)
+    res = tq.decode(ct, tq.CSSSyndrome(sx, sz))
+    sch = ct.schedule
+    ref = cref.FrontierPlan(sch).run(np.concatenate([sx, sz], axis=1))
+    got = res.marginal.reshape(300, -1, order="F")
+    assert np.allclose(got, ref, rtol=MAR_RTOL, atol=0)
+    # the decoded sector is the argmax wherever it is unique ((p, p, p) noise makes some sectors tie exactly, and an FMA
+    # rounds such a pair differently from the C port)
+    srt = np.sort(ref, axis=1)
+    clear = srt[:, -1] > srt[:, -2] * (1 + 1e-9)
+    assert clear.sum() > 200 and np.array_equal(res.sector[clear], np.argmax(ref, axis=1)[clear])
+    assert np.array_equal(res.sector, np.argmax(got, axis=1))
+    assert tq.syndrome_extraction(res.error_pattern, t) == tq.CSSSyndrome(sx, sz)
+
+
 def test_gf2_kernels_bit_exact(tq):
     rng = np.random.default_rng(0)
     for rows, cols in [(2, 5), (40, 81), (80, 162), (130, 300), (1, 1)]:

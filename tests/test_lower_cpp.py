@@ -89,9 +89,9 @@ def test_overlapping_priors_are_merged_identically():
         assert len(py.factors) == 4                               # {0,1,2} merged, {3}, {4,5}, unity factor for variable 6
 
 
-@pytest.mark.parametrize("d", [3, 5, 7, 9])
+@pytest.mark.parametrize("d", [3, 5, 7, 9, 6, (5, 7), (6, 8)])
 def test_tnmmap_css_tables_identical(d):
-    t = tq.CSSTannerGraph(tq.SurfaceCode(d, d))
+    t = tq.CSSTannerGraph(tq.SurfaceCode(*d) if isinstance(d, tuple) else tq.SurfaceCode(d, d))
     _, _, factors, checks, dims, _, _, _ = D._tnmmap_css_graph(tq.get_problem(t, tq.iid_error(0.05, t)))
     py = D._sumprod_lower(tq.TNMMAP(), factors, checks, dims, None)
     _check_schedule(_cabi.Lowered(_cabi.Problem(factors, checks, S.SUMPROD, *dims)), py)

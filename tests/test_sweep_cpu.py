@@ -114,6 +114,21 @@ def test_sweep_sum_product_tnmmap_bit_exact(tq, d, B):
     assert np.array_equal(mar, np.ldexp(ref, -sch.log2_scale))
 
 
+@pytest.mark.parametrize("dx,dz,B", [(6, 6, 24), (5, 7, 40), (6, 8, 12)])
+def test_sweep_sum_product_even_and_rectangular_codes(tq, dx, dz, B):
+    """TNMMAP (CSS) of even-distance / rectangular codes through the sweep (fresh pins + open observable slots)."""
+    from tensorqec.jl_b200 import sweep as SW
+    t = tq.CSSTannerGraph(tq.SurfaceCode(dx, dz))
+    em = tq.iid_error(0.05, t)
+    lx, lz, sch, R, L, FIX = tq.tnmmap_css_schedule(tq.TNMMAP(), tq.get_problem(t, em))
+    pl = getattr(sch, "sweep", None)
+    assert pl is not None and pl.semiring == 1 and len(pl.out_index) == 4
+    syn = _syndromes(t, em, 9 * dx + dz, B)
+    mar = sweep_emulator.run(pl, SW.MENU, syn)
+    ref = frontier.run(sch.factors, sch.checks, sch.order, 1, syn, sch.n_vars)
+    assert np.array_equal(mar, np.ldexp(ref, -sch.log2_scale))
+
+
 def test_sweep_plan_geometry(tq):
     from tensorqec.jl_b200 import sweep as SW
     t, em, su, pl = _plan(tq, 9)
