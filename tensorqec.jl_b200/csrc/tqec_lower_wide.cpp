@@ -120,9 +120,10 @@ static int bf_bank_image(int q) { return q < 4 ? (1 << q) : (q >= 5 && q <= 7 ? 
 #define BF_FAIL(N) do { if (std::getenv("TQEC_BF_DEBUG")) std::fprintf(stderr, "bf_encode_pass: steps %d..%d rejected (reason %d)\n", t0, t1, N); return false; } while (0)
 static bool bf_encode_pass(const std::vector<WRole> &roles, int t0, int t1, const std::vector<Factor> &factors,
                            const std::vector<Check> &checks, const std::vector<std::vector<double>> &tabs,
-                           const std::vector<int> &L_in, const std::vector<int> &L_out, int n_pos, int gmax,
+                           const std::vector<int> &L_in, const std::vector<int> &L_out, int n_pos, int gmax, int n_spec,
                            std::vector<int32_t> &ints, std::vector<double> &vals, double &mant, int &exp2) {
   if (n_pos > 12 || (int)L_in.size() > n_pos || (int)L_out.size() > n_pos || t1 - t0 > 240) BF_FAIL(1);
+  if (n_spec > 19) BF_FAIL(13);                                  // k_wide_bf tabulates the spectator deposit for 7 + 7 + 5 bits
   std::map<int, int> pos;
   uint32_t live = 0, ever = 0;
   for (size_t i = 0; i < L_in.size(); ++i) { pos[L_in[i]] = (int)i; live |= 1u << i; }
@@ -462,7 +463,7 @@ WidePlan lower_wide(const std::vector<Factor> &factors_in, const std::vector<Che
       double mant = P.bf_mant;
       int exp2 = P.bf_log2;
       const int n_pos = std::min(12, t_max);
-      if (bf_encode_pass(roles, t, best_t1, factors, checks, tabs, L_in, L_out, n_pos, TQEC_BF_G, P.bf_ints, P.bf_vals, mant, exp2)) {
+      if (bf_encode_pass(roles, t, best_t1, factors, checks, tabs, L_in, L_out, n_pos, TQEC_BF_G, n_spec, P.bf_ints, P.bf_vals, mant, exp2)) {
         P.bf_off.push_back((int32_t)keep_i);
         P.bf_mant = mant; P.bf_log2 = exp2;
       } else {

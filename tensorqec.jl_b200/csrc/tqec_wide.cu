@@ -759,7 +759,8 @@ int wide_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &pro
                        (int64_t)o + 20 + (int64_t)ng * TQEC_BF_GROUP_INTS + ns + 2 * (int64_t)nc <= w->n_bf_ints,
                    "wide: bad butterfly block for pass %d", i);
       const int32_t *h = w->pass_hdr + (size_t)i * TQEC_WIDE_PASS_INTS;
-      TQEC_REQUIRE(h[TQEC_WP_TIN] <= 12 && h[TQEC_WP_TOUT] <= 12 && bfp[5] == h[TQEC_WP_TIN] && bfp[6] == h[TQEC_WP_TOUT],
+      TQEC_REQUIRE(h[TQEC_WP_TIN] <= 12 && h[TQEC_WP_TOUT] <= 12 && bfp[5] == h[TQEC_WP_TIN] && bfp[6] == h[TQEC_WP_TOUT] &&
+                       h[TQEC_WP_WIN] - h[TQEC_WP_TIN] <= 19,
                    "wide: butterfly block of pass %d does not match its header", i);
       const int32_t *grec = bfp + 20, *crec = grec + ng * TQEC_BF_GROUP_INTS + ns;
       int s_sum = 0, c_sum = 0;
