@@ -119,6 +119,46 @@ __device__ __forceinline__ void sweep_layer(double (&R)[1 << M], const double *T
   sweep_layer_seq<SEMI, M, NP, P0, P1, NF, F0, F1, K0, K1, OFF>(R, T, bits, std::make_integer_sequence<int, (1 << M)>{});
 }
 
+// The LAST layer of a super-step writes its outputs straight to the state.  For the common max-plus form (one free
+// variable) the winner is not selected into a register first: the two candidates are stored under complementary
+// predicates (`@p st c1; @!p st c0`), which replaces two FSEL on the ALU pipe -- the busiest pipe of this kernel -- and
+// the separate store by two predicated stores (ptxas keeps predicated stores as they are; it turns every predicated
+// register write into a select).  Same values, same tie rule.
+template <int SEMI, int M, int NP, int P0, int P1, int NF, int F0, int F1, int K0, int K1, int OFF, int JO>
+__device__ __forceinline__ void sweep_out_store(const double (&R)[1 << M], const double *T, uint32_t &bits, uint32_t addr) {
+  constexpr int pidx = (NP > 0 ? ((JO >> (P0 < 0 ? 0 : P0)) & 1) : 0) | (NP > 1 ? (((JO >> (P1 < 0 ? 0 : P1)) & 1) << 1) : 0);
+  constexpr int J = JO ^ ((pidx & 1) ? K0 : 0) ^ ((pidx & 2) ? K1 : 0);
+  const double *Tp = T + (pidx << NF);
+  if (SEMI == TQEC_SEMIRING_MAXPLUS && NF == 1) {
+    constexpr uint32_t m = 1u << ((OFF + JO) & 31);
+    const double c0 = R[J] + Tp[0], c1 = R[J ^ F0] + Tp[1];
+#ifdef TQEC_DIAG_NOMEM
+    if (c0 == 1.2345 && addr == 77) asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(c1));
+    asm("{\n .reg .pred p;\n setp.gt.f64 p, %1, %2;\n @p or.b32 %0, %0, %3;\n}" : "+r"(bits) : "d"(c1), "d"(c0), "n"(m));
+#else
+    asm volatile("{\n .reg .pred p;\n setp.gt.f64 p, %1, %2;\n @p st.shared.f64 [%3], %1;\n @!p st.shared.f64 [%3], %2;\n @p or.b32 %0, %0, %4;\n}"
+                 : "+r"(bits) : "d"(c1), "d"(c0), "r"(addr), "n"(m));
+#endif
+  } else {
+    double O[1 << M];
+    sweep_out<SEMI, M, NP, P0, P1, NF, F0, F1, K0, K1, OFF, JO>(R, O, T, bits);
+    sw_sts(addr, O[JO]);
+  }
+}
+
+template <int SEMI, int M, int NP, int P0, int P1, int NF, int F0, int F1, int K0, int K1, int OFF, int... J>
+__device__ __forceinline__ void sweep_layer_store_seq(const double (&R)[1 << M], const double *T, uint32_t &bits, uint32_t outb,
+                                                      const uint32_t (&lo)[4], const uint32_t (&hi)[4],
+                                                      std::integer_sequence<int, J...>) {
+  (sweep_out_store<SEMI, M, NP, P0, P1, NF, F0, F1, K0, K1, OFF, J>(R, T, bits, sw_xor3(outb, lo[J & 3], hi[(J >> 2) & 3])), ...);
+}
+
+template <int SEMI, int M, int NP, int P0, int P1, int NF, int F0, int F1, int K0, int K1, int OFF>
+__device__ __forceinline__ void sweep_layer_store(const double (&R)[1 << M], const double *T, uint32_t &bits, uint32_t outb,
+                                                  const uint32_t (&lo)[4], const uint32_t (&hi)[4]) {
+  sweep_layer_store_seq<SEMI, M, NP, P0, P1, NF, F0, F1, K0, K1, OFF>(R, T, bits, outb, lo, hi, std::make_integer_sequence<int, (1 << M)>{});
+}
+
 template <int SEMI, int M, int NL, int NP0, int P00, int P01, int NF0, int F00, int F01, int K00, int K01, int NP1,
           int P10, int P11, int NF1, int F10, int F11, int K10, int K11>
 __device__ __forceinline__ void sweep_step(const int32_t *__restrict__ rec, const double *__restrict__ tvals,
@@ -167,11 +207,23 @@ __device__ __forceinline__ void sweep_step(const int32_t *__restrict__ rec, cons
     const uint32_t inb_n = base_n ^ (uint32_t)stab_row[sidx_n];
     uint32_t bits = 0;
 #ifndef TQEC_DIAG_NOLAYERS   // diagnosis only (wrong results): load / store skeleton without the arithmetic
+#ifdef TQEC_SWEEP_SELECT_THEN_STORE   // the round-1 form: every layer selects into registers, one store loop at the end
     sweep_layer<SEMI, M, NP0, P00, P01, NF0, F00, F01, K00, K01, 0>(R, T0, bits);
     if (NL > 1) sweep_layer<SEMI, M, NP1, P10, P11, NF1, F10, F11, K10, K11, N * NF0>(R, T1, bits);
-#endif
 #pragma unroll
     for (int j = 0; j < N; ++j) sw_sts(sw_xor3(outb, lo[j & 3], hi[(j >> 2) & 3]), R[j]);
+#else
+    if (NL > 1) {
+      sweep_layer<SEMI, M, NP0, P00, P01, NF0, F00, F01, K00, K01, 0>(R, T0, bits);
+      sweep_layer_store<SEMI, M, NP1, P10, P11, NF1, F10, F11, K10, K11, N * NF0>(R, T1, bits, outb, lo, hi);
+    } else {
+      sweep_layer_store<SEMI, M, NP0, P00, P01, NF0, F00, F01, K00, K01, 0>(R, T0, bits, outb, lo, hi);
+    }
+#endif
+#else
+#pragma unroll
+    for (int j = 0; j < N; ++j) sw_sts(sw_xor3(outb, lo[j & 3], hi[(j >> 2) & 3]), R[j]);
+#endif
     if (BPP) {
       if (IPW == 1) {
         bpt[(r0.w + it) * 32 + lane] = bits;
