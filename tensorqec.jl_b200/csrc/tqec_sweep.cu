@@ -23,6 +23,12 @@ namespace tqec {
 
 #define SW_REC_INTS 32
 #define SW_TB_INTS 64
+#ifndef TQEC_SWEEP_STORE_MASK
+#define TQEC_SWEEP_STORE_MASK 0x11   /* outputs (index mod 8) of a last layer that are stored as a predicated pair instead of selected: a
+                                        predicated-off store still takes a shared-memory wavefront slot, so the two forms are mixed to load
+                                        the ALU pipe and the LSU evenly (same-box A/B, benchmarks/ab_store.sh: 0x00 72.9, 0xff 73.1, 0x55 73.5,
+                                        0x33 74.0, 0x11 74.1 M syndromes/s at d = 9) */
+#endif
 
 __device__ __forceinline__ double sw_lds(uint32_t addr) {
   double v;
@@ -129,7 +135,7 @@ __device__ __forceinline__ void sweep_out_store(const double (&R)[1 << M], const
   constexpr int pidx = (NP > 0 ? ((JO >> (P0 < 0 ? 0 : P0)) & 1) : 0) | (NP > 1 ? (((JO >> (P1 < 0 ? 0 : P1)) & 1) << 1) : 0);
   constexpr int J = JO ^ ((pidx & 1) ? K0 : 0) ^ ((pidx & 2) ? K1 : 0);
   const double *Tp = T + (pidx << NF);
-  if (SEMI == TQEC_SEMIRING_MAXPLUS && NF == 1) {
+  if (SEMI == TQEC_SEMIRING_MAXPLUS && NF == 1 && (((TQEC_SWEEP_STORE_MASK) >> (JO & 7)) & 1)) {
     constexpr uint32_t m = 1u << ((OFF + JO) & 31);
     const double c0 = R[J] + Tp[0], c1 = R[J ^ F0] + Tp[1];
 #ifdef TQEC_DIAG_NOMEM
