@@ -383,6 +383,25 @@ def test_tnmmap_even_and_rectangular_codes_through_the_sweep(tq, dx, dz):
     assert tq.syndrome_extraction(res.error_pattern, t) == tq.CSSSyndrome(sx, sz)
 
 
+def test_byte_entry_points_multi_chunk_pipeline(tq):
+    """tqec_decode_map_bytes / tqec_decode_marginal_bytes on batches that span several chunks of the pinned staging
+    pipeline (2^19 shots per chunk, two slots, three streams): same results as the packed-word entry points."""
+    B = 1_300_000
+    t, em = _css_case(tq, tq.SurfaceCode(5, 5))
+    ex, ez, sx, sz = _syndromes(t, em, 5, 4096)
+    rep = (B + 4095) // 4096
+    bits = np.tile(np.concatenate([sx, sz], axis=1), (rep, 1))[:B].copy()
+    bits[-1] ^= 1                                                # the last shot differs from its tile-mates
+    ct = tq.compile(tq.TNMAP(), t, em)
+    corr_w, logp_w = ct.cd.plan.decode_map(tq.pack_bits(bits))
+    corr_b, logp_b = ct.cd.plan.decode_map_bits(bits, 50)
+    assert np.array_equal(tq.unpack_bits(corr_w, 50), corr_b) and np.array_equal(logp_w, logp_b)
+    cm = tq.compile(tq.TNMMAP(), t, em)
+    mar_w, arg_w = cm.plan.decode_marginal(tq.pack_bits(bits))
+    mar_b, arg_b = cm.plan.decode_marginal_bits(bits)
+    assert np.array_equal(mar_w, mar_b) and np.array_equal(arg_w, arg_b)
+
+
 def test_gf2_kernels_bit_exact(tq):
     rng = np.random.default_rng(0)
     for rows, cols in [(2, 5), (40, 81), (80, 162), (130, 300), (1, 1)]:
