@@ -484,18 +484,44 @@ static const void *sweep_kernel(int maxt, int ext) {
   return maxt == 768 ? (const void *)k_sweep<SEMI, 768, 0> : maxt == 640 ? (const void *)k_sweep<SEMI, 640, 0> : (const void *)k_sweep<SEMI, 512, 0>;
 }
 
-int launch_sweep(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d_corr, double *d_out, int32_t *d_argmax,
-                 cudaStream_t stream) {
-  const int64_t groups = (B + plan->sw.grp - 1) / plan->sw.grp;
+static int launch_sweep_part(tqec_plan *plan, const SweepDev &P, const uint64_t *d_synd, int64_t B, uint64_t *d_corr, double *d_out,
+                             int32_t *d_argmax, cudaStream_t stream) {
+  const int64_t groups = (B + P.grp - 1) / P.grp;
   const int64_t ctas = (groups + plan->sw_teams - 1) / plan->sw_teams;
   const int grid = (int)(ctas < plan->sm_count ? ctas : plan->sm_count);
   const void *kern = plan->semiring == TQEC_SEMIRING_MAXPLUS ? sweep_kernel<TQEC_SEMIRING_MAXPLUS>(plan->sw_maxt, plan->sw_ext)
                                                              : sweep_kernel<TQEC_SEMIRING_SUMPROD>(plan->sw_maxt, plan->sw_ext);
-  void *args[] = {(void *)&plan->sw, (void *)&d_synd, (void *)&B, (void *)&d_corr, (void *)&d_out, (void *)&d_argmax,
+  void *args[] = {(void *)&P, (void *)&d_synd, (void *)&B, (void *)&d_corr, (void *)&d_out, (void *)&d_argmax,
                   (void *)&plan->d_sw_bp};
   TQEC_CUDA(cudaLaunchKernel(kern, dim3(grid), dim3(32 * plan->sw_teams), args, (size_t)plan->sw_smem, stream));
   plan->launches += 1;
   return TQEC_OK;
+}
+
+// A launch runs whole rounds: every team takes one group of `grp` shots per round, so a batch that ends half-way through a
+// round pays for the full round (1.25e6 shots per GPU = 16.5 rounds of 148 x 16 x 32 shots: 3 % of the step at 8 GPUs).
+// The tail of a multi-round batch is therefore launched on its own with smaller groups (16 or 8 shots per team and
+// round: less efficient per shot -- idle lanes in the traceback -- but the round is as short as the tail).  Groups only
+// decide which team decodes which shots: results are unchanged.
+int launch_sweep(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d_corr, double *d_out, int32_t *d_argmax,
+                 cudaStream_t stream) {
+  const SweepDev &P = plan->sw;
+  const int64_t per_round = (int64_t)plan->sm_count * plan->sw_teams * P.grp;
+  const int64_t rounds = B / per_round, tail = B - rounds * per_round;
+  int g_tail = P.grp;
+  if (P.grp == 32 && rounds >= 4 && tail > 0 && std::getenv("TQEC_SWEEP_NO_TAIL_SPLIT") == nullptr) {
+    if (4 * tail <= per_round && (1 << P.sg) <= 8) g_tail = 8;
+    else if (2 * tail <= per_round && (1 << P.sg) <= 16) g_tail = 16;
+  }
+  if (g_tail == P.grp) return launch_sweep_part(plan, P, d_synd, B, d_corr, d_out, d_argmax, stream);
+  const int64_t main_shots = rounds * per_round;
+  const int64_t NO = plan->semiring == TQEC_SEMIRING_MAXPLUS ? 1 : ((int64_t)1 << P.n_obs);
+  int rc = launch_sweep_part(plan, P, d_synd, main_shots, d_corr, d_out, d_argmax, stream);
+  if (rc) return rc;
+  SweepDev T = P;
+  T.grp = g_tail;
+  return launch_sweep_part(plan, T, d_synd + main_shots * P.nsw, tail, d_corr ? d_corr + main_shots * P.ncw : nullptr,
+                           d_out ? d_out + main_shots * NO : nullptr, d_argmax ? d_argmax + main_shots : nullptr, stream);
 }
 
 template <typename T>

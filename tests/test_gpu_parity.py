@@ -129,6 +129,32 @@ def test_sweep_kernel_even_and_rectangular_codes(tq, dx, dz, monkeypatch):
         plan2.close()
 
 
+@pytest.mark.parametrize("extra", [5_000, 30_000])
+def test_sweep_tail_launch_does_not_change_results(tq, extra, monkeypatch):
+    """A batch that ends inside a round is decoded by two launches of k_sweep -- whole rounds with 32 shots per team and
+    round, the tail with 8 or 16 -- and gives the same corrections and log-weights, bit for bit, as a single launch."""
+    from tensorqec.jl_b200 import _cabi
+    t, em = _css_case(tq, tq.SurfaceCode(7, 7))
+    ct = tq.compile(tq.TNMAP(), t, em)
+    assert ct.cd.plan.query(_cabi.Q_SWEEP) == 1
+    per_round = 148 * 16 * 32
+    B = 4 * per_round + extra
+    ex, ez, sx, sz = _syndromes(t, em, 31, 8192)
+    bits = np.tile(np.concatenate([sx, sz], axis=1), ((B + 8191) // 8192, 1))[:B]
+    words = tq.pack_bits(bits)
+    l0 = ct.cd.plan.query(_cabi.Q_LAUNCHES)
+    corr, logp = ct.cd.plan.decode_map(words)
+    launches = ct.cd.plan.query(_cabi.Q_LAUNCHES) - l0
+    monkeypatch.setenv("TQEC_SWEEP_NO_TAIL_SPLIT", "1")
+    l1 = ct.cd.plan.query(_cabi.Q_LAUNCHES)
+    corr1, logp1 = ct.cd.plan.decode_map(words)
+    assert ct.cd.plan.query(_cabi.Q_LAUNCHES) - l1 == 1
+    assert launches == 2, "the tail should have been launched separately (148 SMs x 16 teams x 32 shots per round)"
+    assert np.array_equal(corr, corr1) and np.array_equal(logp, logp1)
+    lp, cfg = cref.FrontierPlan(ct.cd.schedule).run(bits[-2000:])
+    assert np.array_equal(tq.unpack_bits(corr[-2000:], 98), cfg) and np.array_equal(logp[-2000:], lp)
+
+
 def test_sweep_kernel_long_head(tq):
     """The 12-bit tabulated head bench.py uses (17 of the 81 steps of d = 9 become a table look-up): same corrections and
     log-weights, bit for bit, as the C port of the full recurrence and as the default 10-bit head."""
