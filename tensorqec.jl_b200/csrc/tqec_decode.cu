@@ -1254,6 +1254,13 @@ extern "C" int tqec_decode_marginal_dev(tqec_plan *p, const uint64_t *d_synd, in
   return launch_decode(p, d_synd, B, nullptr, d_mar, d_argmax, (cudaStream_t)stream);
 }
 
+// chunk size of the host pipelines: about `want` shots, rounded down to whole rounds of k_sweep when the plan runs on it
+static int64_t pipeline_chunk(const tqec_plan *p, int64_t want) {
+  if (!p->has_sweep) return want;
+  const int64_t per_round = (int64_t)p->sm_count * p->sw_teams * p->sw.grp;
+  return per_round > 0 && want > per_round ? (want / per_round) * per_round : want;
+}
+
 static int ensure_pipeline(tqec_plan *p) {
   if (p->s_in) return TQEC_OK;
   TQEC_CUDA(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
@@ -1280,7 +1287,7 @@ extern "C" int tqec_decode_map(tqec_plan *p, const uint64_t *synd, int64_t B, ui
   // Chunked three-stage pipeline: H2D of chunk c+1 and D2H of chunk c-1 overlap the decode of chunk c (three streams,
   // one event pair per chunk; the device buffers hold the whole batch, so chunks never alias).
   if ((rc = ensure_pipeline(p))) return rc;
-  const int64_t CH = (int64_t)1 << 21;
+  const int64_t CH = pipeline_chunk(p, (int64_t)1 << 21);
   const int nsw = p->dev.nsw, ncw = p->dev.ncw;
   const uint64_t *d_syn = (const uint64_t *)p->d_io[0];
   uint64_t *d_cor = (uint64_t *)p->d_io[1];
@@ -1316,7 +1323,7 @@ extern "C" int tqec_decode_marginal(tqec_plan *p, const uint64_t *synd, int64_t 
   if ((rc = ensure_cap(&p->d_io[2], &p->io_cap[2], ab))) return rc;
   // same chunked three-stage pipeline as tqec_decode_map
   if ((rc = ensure_pipeline(p))) return rc;
-  const int64_t CH = (int64_t)1 << 21;
+  const int64_t CH = pipeline_chunk(p, (int64_t)1 << 21);
   const int nsw = p->dev.nsw;
   const int64_t NO = (int64_t)1 << p->dev.n_obs;
   const uint64_t *d_syn = (const uint64_t *)p->d_io[0];
@@ -1408,7 +1415,7 @@ static int decode_bytes(tqec_plan *p, const uint8_t *synd_bits, int64_t B, uint8
   const bool mp = p->semiring == TQEC_SEMIRING_MAXPLUS;
   const int nc = p->dev.n_checks, nv = p->dev.n_vars, nsw = p->dev.nsw, ncw = p->dev.ncw;
   const int64_t NO = mp ? 1 : ((int64_t)1 << p->dev.n_obs);
-  const int64_t CH = (int64_t)1 << 19;
+  const int64_t CH = pipeline_chunk(p, (int64_t)1 << 19);
   const int64_t nb = B < CH ? B : CH;
   const size_t nc1 = (size_t)(nc ? nc : 1), nv1 = (size_t)(nv ? nv : 1);
   int rc;

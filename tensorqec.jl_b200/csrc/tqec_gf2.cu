@@ -416,6 +416,11 @@ extern "C" int tqec_mc_run(const tqec_mc_desc *mc, uint64_t seed, int64_t shot_o
   TQEC_REQUIRE(n_shots >= 0, "tqec_mc_run: negative shot count");
   TQEC_CUDA(cudaSetDevice(P->device));
   int64_t chunk = mc->chunk > 0 ? mc->chunk : (int64_t)1 << 20;
+  if (mc->chunk <= 0 && P->has_sweep) {
+    // whole rounds of k_sweep per chunk (148 SMs x teams x 32 shots): no half-empty last round in every chunk
+    const int64_t per_round = (int64_t)P->sm_count * P->sw_teams * P->sw.grp;
+    if (per_round > 0 && chunk > per_round) chunk = (chunk / per_round) * per_round;
+  }
   if (chunk > n_shots) chunk = n_shots > 0 ? n_shots : 1;
   const int ew = P->dev.ncw, sw = P->dev.nsw;
   cudaStream_t st = P->stream;
