@@ -398,7 +398,6 @@ def lower_sweep(sch: S.Schedule, max_head_bits: int = MAX_HEAD_BITS) -> Optional
     # layers in chain coordinates
     raw = []
     dead_since: dict = {}                                      # chain -> step after which it is free again
-    fresh_at: List[List[int]] = []
     for t in range(h, n):
         fi, touched, opened, closing = roles[t]
         pinned, free = cls[t]
