@@ -325,7 +325,8 @@ def run_ours(args):
             nb = min(B, 2_000_000)
             bits = tq.unpack_bits(syn_words[:nb], mc.H.rows)
             nsx = t.stgx.ns
-            syn_obj = tq.CSSSyndrome(bits[:, :nsx], bits[:, nsx:])
+            # the reference's CSSSyndrome holds sx and sz as two arrays of their own (src/decoding/interfaces.jl)
+            syn_obj = tq.CSSSyndrome(np.ascontiguousarray(bits[:, :nsx]), np.ascontiguousarray(bits[:, nsx:]))
             tq.decode(mc.compiled, syn_obj)
             t0 = time.perf_counter()
             res = tq.decode(mc.compiled, syn_obj)

@@ -276,6 +276,11 @@ int tqec_decode_marginal_log2(tqec_plan *plan, const uint64_t *synd, int64_t n_s
  * synd_bits = B * n_checks bytes, corr_bits = B * n_vars bytes.  The bytes cross PCIe as they are and are packed /
  * unpacked on the device next to the decode kernel (host-side packing of 1e7 shots costs more than decoding them). */
 int tqec_decode_map_bytes(tqec_plan *plan, const uint8_t *synd_bits, int64_t n_shots, uint8_t *corr_bits, double *logp_out);
+/* TNMAP with the syndrome kept as two arrays -- a CSS code's sx (n_a bits per shot) and sz (n_b bits per shot), the layout of
+ * the reference's CSSSyndrome (src/decoding/interfaces.jl): bit k of a shot is synd_a[shot][k] for k < n_a, else
+ * synd_b[shot][k - n_a]; n_a + n_b = n_checks.  Saves the host-side concatenation of the two arrays. */
+int tqec_decode_map_bytes2(tqec_plan *plan, const uint8_t *synd_a, int32_t n_a, const uint8_t *synd_b, int32_t n_b,
+                           int64_t n_shots, uint8_t *corr_bits, double *logp_out);
 int tqec_decode_marginal_bytes(tqec_plan *plan, const uint8_t *synd_bits, int64_t n_shots, double *mar_out,
                                int32_t *argmax_out);
 

@@ -27,7 +27,7 @@ EXPORTS = [
     "tqec_logical_flags", "tqec_coset_rep", "tqec_sample_errors", "tqec_mc_run", "tqec_fp64_peak",
     "tqec_lower", "tqec_lowered_destroy", "tqec_lowered_get", "tqec_plan_from_lowered", "tqec_plan_compile",
     "tqec_comm_unique_id", "tqec_comm_init", "tqec_comm_destroy", "tqec_comm_allreduce_counts",
-    "tqec_decode_map_bytes", "tqec_decode_marginal_bytes", "tqec_dmma_peak", "tqec_decode_marginal_log2",
+    "tqec_decode_map_bytes", "tqec_decode_map_bytes2", "tqec_decode_marginal_bytes", "tqec_dmma_peak", "tqec_decode_marginal_log2",
     "tqec_table_create", "tqec_table_destroy", "tqec_table_decode", "tqec_bp_create", "tqec_bp_destroy", "tqec_bp_decode",
 ]
 
@@ -125,6 +125,7 @@ def lib():
     L.tqec_plan_compile.argtypes = [C.POINTER(ProblemDesc), C.POINTER(vp)]
     L.tqec_decode_marginal_log2.argtypes = [vp, vp, i64, vp, vp, vp]
     L.tqec_decode_map_bytes.argtypes = [vp, vp, i64, vp, vp]
+    L.tqec_decode_map_bytes2.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, i64, vp, vp]
     L.tqec_decode_marginal_bytes.argtypes = [vp, vp, i64, vp, vp]
     L.tqec_table_create.argtypes = [i64, i32, i32, vp, vp, i32, C.POINTER(vp)]
     L.tqec_table_destroy.argtypes = [vp]
@@ -203,6 +204,9 @@ class Problem:
         self.desc = ProblemDesc(semiring, n_vars, n_checks, n_obs, len(factors), _ptr(k[0]), _ptr(k[1]), _ptr(k[2]),
                                 len(checks), _ptr(k[3]), _ptr(k[4]), _ptr(k[5]), _ptr(k[6]),
                                 _ptr(k[7]) if k[7] is not None else None, head_bits, table_bits, device, flags, wide_t_max)
+
+
+from .mod2 import empty_big as _empty_big  # noqa: E402
 
 
 class Lowered:
@@ -332,16 +336,25 @@ class Plan:
         """(B, n_checks) uint8 0/1 -> ((B, n_vars) uint8, logp): one byte per bit both ways, packed on the device."""
         s = _c(synd_bits, np.uint8)
         B = s.shape[0]
-        corr = np.empty((B, n_vars), dtype=np.uint8)
-        logp = np.empty(B, dtype=np.float64)
+        corr = _empty_big((B, n_vars), np.uint8)
+        logp = _empty_big(B, np.float64)
         check(lib().tqec_decode_map_bytes(self.h, _ptr(s), B, _ptr(corr), _ptr(logp)))
+        return corr, logp
+
+    def decode_map_bits2(self, sa: np.ndarray, sb: np.ndarray, n_vars: int):
+        """The same with the syndrome as two (B, n) uint8 arrays (a CSS code's sx and sz): no concatenation on the host."""
+        a, b = _c(sa, np.uint8), _c(sb, np.uint8)
+        B = a.shape[0]
+        corr = _empty_big((B, n_vars), np.uint8)
+        logp = _empty_big(B, np.float64)
+        check(lib().tqec_decode_map_bytes2(self.h, _ptr(a), a.shape[1], _ptr(b), b.shape[1], B, _ptr(corr), _ptr(logp)))
         return corr, logp
 
     def decode_marginal_bits(self, synd_bits: np.ndarray):
         s = _c(synd_bits, np.uint8)
         B = s.shape[0]
-        mar = np.empty((B, 1 << self.n_obs), dtype=np.float64)
-        arg = np.empty(B, dtype=np.int32)
+        mar = _empty_big((B, 1 << self.n_obs), np.float64)
+        arg = _empty_big(B, np.int32)
         check(lib().tqec_decode_marginal_bytes(self.h, _ptr(s), B, _ptr(mar), _ptr(arg)))
         return mar, arg
 

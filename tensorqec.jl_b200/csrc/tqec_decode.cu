@@ -1363,6 +1363,25 @@ __global__ void k_pack_bits(const uint8_t *__restrict__ bytes, int64_t B, int n_
     out[i] = v;
   }
 }
+// the same for syndromes kept as two arrays (a CSS code: sx with n_a bits and sz with n_b bits per shot): the chunk arrives as
+// the block of sx rows followed by the block of sz rows, bit k of a shot is read from the array it belongs to
+__global__ void k_pack_bits2(const uint8_t *__restrict__ bytes, int64_t B, int n_a, int n_b, int words, uint64_t *__restrict__ out) {
+  const int64_t n = B * words;
+  const uint8_t *A = bytes, *Bs = bytes + B * n_a;
+  const int n_bits = n_a + n_b;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t shot = i / words;
+    const int w = (int)(i - shot * words);
+    const int m = n_bits - 64 * w < 64 ? n_bits - 64 * w : 64;
+    uint64_t v = 0;
+    for (int k = 0; k < m; ++k) {
+      const int b = 64 * w + k;
+      const uint8_t x = b < n_a ? A[shot * n_a + b] : Bs[shot * n_b + (b - n_a)];
+      v |= (uint64_t)(x & 1u) << k;
+    }
+    out[i] = v;
+  }
+}
 __global__ void k_unpack_bits(const uint64_t *__restrict__ wordsv, int64_t B, int n_bits, int words, uint8_t *__restrict__ out) {
   const int64_t n = B * (int64_t)n_bits;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1410,7 +1429,8 @@ static int ensure_pinned(void **slot, size_t *cap, size_t bytes) {
 // slots: the caller's arrays are pageable, so every chunk goes through pinned staging buffers (host copy by par_memcpy,
 // then a true asynchronous transfer); H2D of chunk c + 1, the kernels of chunk c, D2H of chunk c - 1 and the host copies
 // overlap.
-static int decode_bytes(tqec_plan *p, const uint8_t *synd_bits, int64_t B, uint8_t *corr_bits, double *out, int32_t *argmax_out) {
+static int decode_bytes(tqec_plan *p, const uint8_t *synd_bits, int64_t B, uint8_t *corr_bits, double *out, int32_t *argmax_out,
+                        const uint8_t *synd_b = nullptr, int n_a = 0) {
   tqec::NvtxRange nvtx_range("tqec_decode_bytes");
   const bool mp = p->semiring == TQEC_SEMIRING_MAXPLUS;
   const int nc = p->dev.n_checks, nv = p->dev.n_vars, nsw = p->dev.nsw, ncw = p->dev.ncw;
@@ -1444,13 +1464,19 @@ static int decode_bytes(tqec_plan *p, const uint8_t *synd_bits, int64_t B, uint8
       uint8_t *d_x = (uint8_t *)p->d_io[3] + slot * sz3;
       uint8_t *h_in = (uint8_t *)p->h_pin[0] + slot * sz0;
       if (c >= 2) TQEC_CUDA(cudaEventSynchronize(p->ev_in[slot]));      // the staging buffer's previous transfer has left
-      par_memcpy(h_in, synd_bits + (size_t)o * nc, (size_t)n * nc);
+      if (synd_b) {                                            // two source arrays: block of sx rows, then block of sz rows
+        par_memcpy(h_in, synd_bits + (size_t)o * n_a, (size_t)n * n_a);
+        par_memcpy(h_in + (size_t)n * n_a, synd_b + (size_t)o * (nc - n_a), (size_t)n * (nc - n_a));
+      } else {
+        par_memcpy(h_in, synd_bits + (size_t)o * nc, (size_t)n * nc);
+      }
       if (c >= 2) TQEC_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_cmp[slot], 0));   // chunk c - 2 has consumed the device slot
       TQEC_CUDA(cudaMemcpyAsync(d_sb, h_in, (size_t)n * nc, cudaMemcpyHostToDevice, p->s_in));
       TQEC_CUDA(cudaEventRecord(p->ev_in[slot], p->s_in));
       TQEC_CUDA(cudaStreamWaitEvent(p->stream, p->ev_in[slot], 0));
       if (ev_out_used[slot]) TQEC_CUDA(cudaStreamWaitEvent(p->stream, p->ev_out[slot], 0));   // chunk c - 2's results have left
-      k_pack_bits<<<grid_for(n * nsw, p->sm_count), 256, 0, p->stream>>>(d_sb, n, nc, nsw, d_syn);
+      if (synd_b) k_pack_bits2<<<grid_for(n * nsw, p->sm_count), 256, 0, p->stream>>>(d_sb, n, n_a, nc - n_a, nsw, d_syn);
+      else k_pack_bits<<<grid_for(n * nsw, p->sm_count), 256, 0, p->stream>>>(d_sb, n, nc, nsw, d_syn);
       TQEC_CUDA(cudaGetLastError());
       if ((rc = launch_decode(p, d_syn, n, mp ? d_cor : nullptr, d_out, mp ? nullptr : (int32_t *)d_x, p->stream))) return rc;
       if (mp) {
@@ -1493,6 +1519,17 @@ extern "C" int tqec_decode_map_bytes(tqec_plan *p, const uint8_t *synd_bits, int
   if (B == 0) return TQEC_OK;
   TQEC_CUDA(cudaSetDevice(p->device));
   return decode_bytes(p, synd_bits, B, corr_bits, logp_out, nullptr);
+}
+
+extern "C" int tqec_decode_map_bytes2(tqec_plan *p, const uint8_t *synd_a, int32_t n_a, const uint8_t *synd_b, int32_t n_b, int64_t B,
+                                      uint8_t *corr_bits, double *logp_out) {
+  TQEC_REQUIRE(p && p->semiring == TQEC_SEMIRING_MAXPLUS, "tqec_decode_map_bytes2: plan is not a max-plus (TNMAP) plan");
+  TQEC_REQUIRE(n_a > 0 && n_b > 0 && n_a + n_b == p->dev.n_checks, "tqec_decode_map_bytes2: %d + %d syndrome bits, the plan has %d checks",
+               n_a, n_b, p->dev.n_checks);
+  TQEC_REQUIRE(B >= 0 && (B == 0 || (synd_a && synd_b && corr_bits)), "tqec_decode_map_bytes2: NULL buffer");
+  if (B == 0) return TQEC_OK;
+  TQEC_CUDA(cudaSetDevice(p->device));
+  return decode_bytes(p, synd_a, B, corr_bits, logp_out, nullptr, synd_b, n_a);
 }
 
 extern "C" int tqec_decode_marginal_bytes(tqec_plan *p, const uint8_t *synd_bits, int64_t B, double *mar_out, int32_t *argmax_out) {

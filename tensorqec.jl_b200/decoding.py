@@ -25,7 +25,7 @@ from .wide import lower_wide
 from .dem import DetectorErrorModel, dem2tanner
 from .error_model import (AbstractErrorModel, CSSErrorPattern, CSSSyndrome, IndependentDepolarizingError,
                           IndependentFlipError, SimpleSyndrome, iid_error)
-from .mod2 import as_bits, pack_bits, unpack_bits
+from .mod2 import ValidatedBits, as_bits, concat_bits, pack_bits, unpack_bits
 from .tanner import (AbstractTannerGraph, CSSTannerGraph, SimpleTannerGraph, gf2_right_inverse, gf2_sector_fixes,
                      logical_operator)
 
@@ -176,7 +176,7 @@ def reduce2general(tanner: CSSTannerGraph, pvec_or_tn):
 
 def extract_decoding(cgdp: CSSToGeneralDecodingProblem, error_pattern: np.ndarray) -> DecodingResult:
     n = cgdp.qubit_num
-    e = np.asarray(error_pattern)
+    e = np.asanyarray(error_pattern)                            # keeps the ValidatedBits mark of the library's own corrections
     return DecodingResult(True, CSSErrorPattern(e[..., :n], e[..., n:2 * n]))
 
 
@@ -307,13 +307,8 @@ def _compile_tnmap(decoder: TNMAP, problem: GeneralDecodingProblem) -> CompiledT
     return CompiledTNMAP(decoder, problem)
 
 
-class _ValidatedBits(np.ndarray):
-    """uint8 0/1 array that already went through as_bits (skips a second validation pass over a large batch)."""
-    _tqec_validated = True
-
-
 def _syndrome_bits(s, n) -> np.ndarray:
-    b = s if isinstance(s, _ValidatedBits) else as_bits(s)
+    b = s if isinstance(s, ValidatedBits) else as_bits(s)
     b = b[None, :] if b.ndim == 1 else b
     if b.shape[1] != n:
         raise ValueError(f"syndrome has {b.shape[1]} bits, the decoder expects {n}")
@@ -322,10 +317,11 @@ def _syndrome_bits(s, n) -> np.ndarray:
 
 def _decode_tnmap(ct: CompiledTNMAP, syndrome: SimpleSyndrome) -> DecodingResult:
     raw = syndrome.s
-    bits = raw if isinstance(raw, _ValidatedBits) else as_bits(raw).view(_ValidatedBits)   # validated once: 1e7 shots are 0.8 GB
+    bits = raw if isinstance(raw, ValidatedBits) else as_bits(raw).view(ValidatedBits)   # validated once: 1e7 shots are 0.8 GB
     single = bits.ndim == 1
     bits = _syndrome_bits(bits, ct.n_checks)
     cfg, logp = ct.plan.decode_map_bits(bits, ct.qubit_num)     # one byte per bit both ways; packed on the device
+    cfg = cfg.view(ValidatedBits)                                # the library's own 0/1 bytes: no validation pass downstream
     ok = np.isfinite(logp)
     if single:
         return DecodingResult(bool(ok[0]), cfg[0], logp=logp[0])
@@ -550,7 +546,14 @@ def decode(first, *args):
         if not isinstance(syn, CSSSyndrome):
             raise TypeError("a CSS-compiled decoder decodes a CSSSyndrome")
         sx, sz = as_bits(syn.sx), as_bits(syn.sz)
-        res = decode(ct.cd, SimpleSyndrome(np.concatenate([sx, sz], axis=-1).view(_ValidatedBits)))
+        if isinstance(ct.cd, CompiledTNMAP) and sx.ndim == 2 and sz.ndim == 2 and sx.shape[0] == sz.shape[0]:
+            # batched TNMAP: the library reads sx and sz where they lie (tqec_decode_map_bytes2), no concatenation here
+            if sx.shape[1] + sz.shape[1] != ct.cd.n_checks:
+                raise ValueError(f"syndrome has {sx.shape[1] + sz.shape[1]} bits, the decoder expects {ct.cd.n_checks}")
+            cfg, logp = ct.cd.plan.decode_map_bits2(sx, sz, ct.cd.qubit_num)
+            res = DecodingResult(np.isfinite(logp), cfg.view(ValidatedBits), logp=logp)
+        else:
+            res = decode(ct.cd, SimpleSyndrome(concat_bits(sx, sz).view(ValidatedBits)))
         out = extract_decoding(ct.reduction, res.error_pattern)
         out.success_tag, out.logp = res.success_tag, res.logp
         return out

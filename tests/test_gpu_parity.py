@@ -422,6 +422,8 @@ def test_byte_entry_points_multi_chunk_pipeline(tq):
     corr_w, logp_w = ct.cd.plan.decode_map(tq.pack_bits(bits))
     corr_b, logp_b = ct.cd.plan.decode_map_bits(bits, 50)
     assert np.array_equal(tq.unpack_bits(corr_w, 50), corr_b) and np.array_equal(logp_w, logp_b)
+    corr_2, logp_2 = ct.cd.plan.decode_map_bits2(bits[:, :12].copy(), bits[:, 12:].copy(), 50)   # sx | sz as two arrays
+    assert np.array_equal(corr_2, corr_b) and np.array_equal(logp_2, logp_b)
     cm = tq.compile(tq.TNMMAP(), t, em)
     mar_w, arg_w = cm.plan.decode_marginal(tq.pack_bits(bits))
     mar_b, arg_b = cm.plan.decode_marginal_bits(bits)
