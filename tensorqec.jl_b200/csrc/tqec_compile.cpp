@@ -82,7 +82,7 @@ static void lower_problem(const tqec_problem_desc *d, tqec_lowered &L) {
   const bool no_sweep = (d->flags & TQEC_COMPILE_NO_SWEEP) || std::getenv("TQEC_NO_SWEEP");
   const std::vector<int> *order = P.has_order ? &P.order : nullptr;
   if (P.semiring == TQEC_SEMIRING_MAXPLUS) {
-    const int head_bits = env_int("TQEC_HEAD_BITS", d->head_bits > 0 ? d->head_bits : 12);
+    const int head_bits = env_int("TQEC_HEAD_BITS", d->head_bits > 0 ? d->head_bits : 14);
     if (!no_sweep) {
       bool ok = false;
       Schedule su;

@@ -86,9 +86,76 @@ __global__ void k_sample_errors(int model, int n_sites, const double *__restrict
   err[gid] = out;
 }
 
+// Raw 53-bit draw of philox_uniform: u = bits * 2^-53 exactly, so `u < p` is the integer compare `bits < ceil(p * 2^53)`
+// (scaling a double by a power of two is exact): same decisions, no int -> FP64 conversion and no FP64 compare per site.
+__device__ __forceinline__ uint64_t philox_bits53(uint64_t seed, uint64_t shot, uint32_t site) {
+  uint32_t c0 = (uint32_t)shot, c1 = (uint32_t)(shot >> 32), c2 = site, c3 = 0u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c0, c1, c2, c3, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return (((uint64_t)c0 << 32) | c1) >> 11;
+}
+__device__ __forceinline__ uint64_t prob_threshold53(double p) {       // negative / NaN -> 0 (never), p >= 1 -> always
+  return p > 0.0 ? __double2ull_ru(fmin(p, 1.0) * 9007199254740992.0) : 0ull;
+}
+
+// Depolarizing model, one thread per SHOT: the draw of qubit q decides both its X bit (position q) and its Z bit (position
+// n_sites + q), so it is made once (k_sample_errors makes it once per output bit, i.e. twice); thresholds Y | X+Y | X+Y+Z
+// as 53-bit integers in shared memory; the thread assembles its shot's words (<= SAMPLE_MAXW) and writes them out.
+#define SAMPLE_MAXW 16
+__global__ void __launch_bounds__(128)
+k_sample_depol(int n_sites, const double *__restrict__ p, uint64_t seed, int64_t shot_offset, int64_t B,
+               uint64_t *__restrict__ err, int words) {
+  extern __shared__ uint64_t sh_thr[];                                  // [3][n_sites]
+  for (int q = threadIdx.x; q < n_sites; q += blockDim.x) {
+    const double px = p[q], py = p[n_sites + q], pz = p[2 * n_sites + q];
+    sh_thr[q] = prob_threshold53(py);                                   // Y first, then X, then Z (error_model.jl:101-115)
+    sh_thr[n_sites + q] = prob_threshold53(px + py);
+    sh_thr[2 * n_sites + q] = prob_threshold53(px + py + pz);
+  }
+  __syncthreads();
+  const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (s >= B) return;
+  const uint64_t shot = (uint64_t)(shot_offset + s);
+  uint64_t out[SAMPLE_MAXW];
+#pragma unroll
+  for (int w = 0; w < SAMPLE_MAXW; ++w) out[w] = 0ull;
+  for (int q0 = 0; q0 < n_sites; q0 += 64) {
+    uint64_t xw = 0ull, zw = 0ull;
+    const int nb = min(64, n_sites - q0);
+#pragma unroll 4
+    for (int b = 0; b < nb; ++b) {
+      const int q = q0 + b;
+      const uint64_t u = philox_bits53(seed, shot, (uint32_t)q);
+      const bool isY = u < sh_thr[q];
+      const bool isXY = u < sh_thr[n_sites + q];                        // X or Y (thresholds ascend unless a p is negative)
+      const bool isX = !isY && isXY;
+      const bool isZ = !isY && !isX && u < sh_thr[2 * n_sites + q];
+      xw |= (uint64_t)(isX || isY) << b;
+      zw |= (uint64_t)(isZ || isY) << b;
+    }
+    const int zp = n_sites + q0, zs = zp & 63;
+    out[q0 >> 6] |= xw;
+    out[zp >> 6] |= zw << zs;
+    if (zs && (zp >> 6) + 1 < words) out[(zp >> 6) + 1] |= zw >> (64 - zs);
+  }
+  for (int w = 0; w < words; ++w) err[s * words + w] = out[w];
+}
+
 int launch_sample(int model, int n_sites, const double *d_p, uint64_t seed, int64_t shot_offset, int64_t B,
                   uint64_t *d_err, int words, cudaStream_t stream) {
   if (B <= 0) return TQEC_OK;
+  if (model == TQEC_MODEL_DEPOL && words <= SAMPLE_MAXW && n_sites > 0 && (size_t)n_sites * 24 <= 40 * 1024) {
+    const int threads = 128;
+    k_sample_depol<<<(unsigned)((B + threads - 1) / threads), threads, (size_t)n_sites * 24, stream>>>(n_sites, d_p, seed, shot_offset,
+                                                                                                      B, d_err, words);
+    TQEC_CUDA(cudaGetLastError());
+    return TQEC_OK;
+  }
   const int64_t n = B * words;
   const int threads = 256;
   k_sample_errors<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>(model, n_sites, d_p, seed, shot_offset, B, d_err, words);

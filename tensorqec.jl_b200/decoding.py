@@ -110,7 +110,7 @@ class TNMAP(AbstractGeneralDecoder):
     device: int = 0
     table_bits: int = 16         # plans with at most this many syndrome bits are decoded once per syndrome at compile time
                                  # and served from that table (k_lookup); up to 26 (table of 2^bits entries)
-    head_bits: int = 12          # syndrome bits the tabulated head of the sweep lowering may depend on (sweep.py): more
+    head_bits: int = 14          # syndrome bits the tabulated head of the sweep lowering may depend on (sweep.py): more
                                  # bits = fewer steps per shot, a larger table (2^bits x 2^W entries) and a slower compile
 
     def __repr__(self):

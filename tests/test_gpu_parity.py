@@ -462,6 +462,21 @@ def test_sampler_bit_exact_and_offset_invariant(tq):
     assert one.shape == (100,)
 
 
+@pytest.mark.parametrize("n", [5, 64, 65, 128, 200])
+def test_sampler_per_qubit_rates_word_boundaries(tq, n):
+    """k_sample_depol (one thread per shot, one draw per qubit, integer thresholds) against the oracle's float compare:
+    per-qubit rates, z blocks that straddle word boundaries, p = 0 and px + py + pz = 1 sites."""
+    rng = np.random.default_rng(n)
+    px, py, pz = rng.uniform(0, 0.3, n), rng.uniform(0, 0.3, n), rng.uniform(0, 0.3, n)
+    px[0] = py[0] = pz[0] = 0.0
+    px[-1], py[-1], pz[-1] = 0.25, 0.25, 0.5
+    em = tq.IndependentDepolarizingError(px, py, pz)
+    ep = tq.random_error_pattern(em, seed=(7 << 33) + n, shots=3000, shot_offset=(1 << 32) - 100)
+    ox, oz = philox.sample_depolarizing(px, py, pz, (7 << 33) + n, (1 << 32) - 100, 3000)
+    assert np.array_equal(ep.xerror, ox) and np.array_equal(ep.zerror, oz)
+    assert not ep.xerror[:, 0].any() and not ep.zerror[:, 0].any() and (ep.xerror[:, -1] | ep.zerror[:, -1]).all()
+
+
 @pytest.mark.parametrize("d,shots", [(3, 20000), (5, 20000), (7, 6000)])
 def test_fused_pipeline_counts_bit_exact(tq, d, shots):
     t, em = _css_case(tq, tq.SurfaceCode(d, d))

@@ -55,9 +55,11 @@ def _check_schedule(lw, py):
 def test_tnmap_tables_identical(code):
     c = {"steane": tq.SteaneCode(), "color488_5": tq.Color488(5), "d5x7": tq.SurfaceCode(5, 7)}.get(code) or tq.SurfaceCode(int(code[1:]), int(code[1:]))
     factors, checks, nq, ns = _tnmap_graph(c)
-    py = D._tnmap_lower(tq.TNMAP(), factors, checks, nq, ns, None)
+    py = D._tnmap_lower(tq.TNMAP(head_bits=12), factors, checks, nq, ns, None)
     lw = _cabi.Lowered(_cabi.Problem(factors, checks, S.MAXPLUS, nq, ns, 0, head_bits=12))
     _check_schedule(lw, py)
+    if code == "d5":                                              # the shipped defaults agree too (head_bits = 0 -> the library's)
+        _check_schedule(_cabi.Lowered(_cabi.Problem(factors, checks, S.MAXPLUS, nq, ns, 0)), D._tnmap_lower(tq.TNMAP(), factors, checks, nq, ns, None))
     if code in ("d5", "d7", "d9"):
         assert lw.meta["kind"] == 1, "odd-distance surface codes decode through the in-place patch sweep"
 
@@ -71,7 +73,7 @@ def test_tnmap_generic_noise_custom_order_and_head_bits():
         py = D._tnmap_lower(tq.TNMAP(head_bits=head_bits), factors, checks, nq, ns, None)
         _check_schedule(_cabi.Lowered(_cabi.Problem(factors, checks, S.MAXPLUS, nq, ns, 0, head_bits=head_bits)), py)
     order = list(range(48, -1, -1))                               # a caller-supplied order: general kernels, fused
-    py = D._tnmap_lower(tq.TNMAP(), factors, checks, nq, ns, order)
+    py = D._tnmap_lower(tq.TNMAP(head_bits=12), factors, checks, nq, ns, order)
     _check_schedule(_cabi.Lowered(_cabi.Problem(factors, checks, S.MAXPLUS, nq, ns, 0, order=order, head_bits=12)), py)
 
 
