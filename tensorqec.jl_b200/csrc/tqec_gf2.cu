@@ -55,37 +55,6 @@ __device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_t shot, u
   return (double)bits * (1.0 / 9007199254740992.0);
 }
 
-// one thread per (shot, output word): sites are visited word by word so that every thread writes whole words
-__global__ void k_sample_errors(int model, int n_sites, const double *__restrict__ p, uint64_t seed, int64_t shot_offset,
-                                int64_t B, uint64_t *__restrict__ err, int words) {
-  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (gid >= B * words) return;
-  const int64_t s = gid / words;
-  const int w = (int)(gid - s * words);
-  const uint64_t shot = (uint64_t)(shot_offset + s);
-  uint64_t out = 0;
-  const int nbits = model == TQEC_MODEL_DEPOL ? 2 * n_sites : n_sites;
-  for (int b = 0; b < 64; ++b) {
-    const int bit = w * 64 + b;
-    if (bit >= nbits) break;
-    if (model == TQEC_MODEL_FLIP) {
-      const double u = philox_uniform(seed, shot, (uint32_t)bit);
-      if (u < p[bit]) out |= 1ull << b;
-    } else {
-      const int q = bit < n_sites ? bit : bit - n_sites;
-      const double u = philox_uniform(seed, shot, (uint32_t)q);
-      const double px = p[q], py = p[n_sites + q], pz = p[2 * n_sites + q];
-      // Y first, then X, then Z (error_model.jl:101-115)
-      const bool isY = u < py;
-      const bool isX = !isY && u < px + py;
-      const bool isZ = !isY && !isX && u < px + py + pz;
-      const bool on = bit < n_sites ? (isX || isY) : (isZ || isY);
-      if (on) out |= 1ull << b;
-    }
-  }
-  err[gid] = out;
-}
-
 // Raw 53-bit draw of philox_uniform: u = bits * 2^-53 exactly, so `u < p` is the integer compare `bits < ceil(p * 2^53)`
 // (scaling a double by a power of two is exact): same decisions, no int -> FP64 conversion and no FP64 compare per site.
 __device__ __forceinline__ uint64_t philox_bits53(uint64_t seed, uint64_t shot, uint32_t site) {
@@ -101,6 +70,36 @@ __device__ __forceinline__ uint64_t philox_bits53(uint64_t seed, uint64_t shot, 
 }
 __device__ __forceinline__ uint64_t prob_threshold53(double p) {       // negative / NaN -> 0 (never), p >= 1 -> always
   return p > 0.0 ? __double2ull_ru(fmin(p, 1.0) * 9007199254740992.0) : 0ull;
+}
+
+// one thread per (shot, output word): sites are visited word by word so that every thread writes whole words
+__global__ void k_sample_errors(int model, int n_sites, const double *__restrict__ p, uint64_t seed, int64_t shot_offset,
+                                int64_t B, uint64_t *__restrict__ err, int words) {
+  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (gid >= B * words) return;
+  const int64_t s = gid / words;
+  const int w = (int)(gid - s * words);
+  const uint64_t shot = (uint64_t)(shot_offset + s);
+  uint64_t out = 0;
+  const int nbits = model == TQEC_MODEL_DEPOL ? 2 * n_sites : n_sites;
+  for (int b = 0; b < 64; ++b) {
+    const int bit = w * 64 + b;
+    if (bit >= nbits) break;
+    if (model == TQEC_MODEL_FLIP) {                                  // u < p as an integer compare (see prob_threshold53)
+      if (philox_bits53(seed, shot, (uint32_t)bit) < prob_threshold53(__ldg(p + bit))) out |= 1ull << b;
+    } else {
+      const int q = bit < n_sites ? bit : bit - n_sites;
+      const double u = philox_uniform(seed, shot, (uint32_t)q);
+      const double px = p[q], py = p[n_sites + q], pz = p[2 * n_sites + q];
+      // Y first, then X, then Z (error_model.jl:101-115)
+      const bool isY = u < py;
+      const bool isX = !isY && u < px + py;
+      const bool isZ = !isY && !isX && u < px + py + pz;
+      const bool on = bit < n_sites ? (isX || isY) : (isZ || isY);
+      if (on) out |= 1ull << b;
+    }
+  }
+  err[gid] = out;
 }
 
 // Depolarizing model, one thread per SHOT: the draw of qubit q decides both its X bit (position q) and its Z bit (position
