@@ -215,8 +215,8 @@ typedef struct {
   const int32_t *row_kind;     /* 0: clamped by syndrome bit row_index; 1: open output axis row_index          */
   const int32_t *row_index;
   const int32_t *order;        /* NULL, or n_factors entries: absorption order of the prior factors            */
-  int32_t head_bits;           /* syndrome bits the tabulated head of the sweep may depend on (0 = default 14 for
-                                  max-plus, 10 for sum-product; at most 16)                                    */
+  int32_t head_bits;           /* syndrome bits the tabulated head of the sweep may depend on (0 = default 14;
+                                  at most 16)                                                                  */
   int32_t table_bits;          /* as in tqec_plan_desc                                                         */
   int32_t device;
   int32_t flags;               /* TQEC_COMPILE_*                                                               */

@@ -125,7 +125,7 @@ static void lower_problem(const tqec_problem_desc *d, tqec_lowered &L) {
     L.kind = 0;
     if (!no_sweep && L.sch.w_max >= 5 && L.sch.w_max <= 10) {
       bool ok = false;
-      try { ok = lower_sweep(L.sch, env_int("TQEC_HEAD_BITS_SP", d->head_bits > 0 ? d->head_bits : 10), L.sw); } catch (const std::runtime_error &) { ok = false; }
+      try { ok = lower_sweep(L.sch, env_int("TQEC_HEAD_BITS_SP", d->head_bits > 0 ? d->head_bits : 14), L.sw); } catch (const std::runtime_error &) { ok = false; }
       if (ok) L.kind = 1;
     }
     return;

@@ -133,6 +133,7 @@ class TNMMAP(AbstractGeneralDecoder):
     factorize: bool = True
     device: int = 0
     table_bits: int = 16         # as for TNMAP: problems with at most this many syndrome / detector bits are tabulated
+    head_bits: int = 14          # as for TNMAP (CSS plans on k_sweep<SUMPROD>: 2^bits x 2^W doubles, no configuration table)
     dynamic_rescale: bool = False  # per-shot dynamic rescaling (int32 exponent per shot) against FP64 underflow on extremely
                                  # unlikely syndromes; runs the plan on the global-memory executor (slower; tables are static-
                                  # ally scaled in any case, which covers every BASELINE config)
@@ -365,7 +366,7 @@ class CompiledTNMMAP(CompiledDecoder, _LazySchedule):
 def _sumprod_lower(decoder, factors, checks, dims, order):
     """Python lowering of a marginal network (the oracle of tqec_lower for sum-product plans)."""
     sch = _lower_sumprod(factors, checks, dims[0], dims[1], dims[2], order, dynamic=bool(getattr(decoder, "dynamic_rescale", False)))
-    _attach_sweep(sch)
+    _attach_sweep(sch, max_head_bits=int(os.environ.get("TQEC_HEAD_BITS_SP", getattr(decoder, "head_bits", 0) or 14)))
     sch.table_bits = decoder.table_bits
     return sch
 
