@@ -1256,6 +1256,7 @@ extern "C" int tqec_decode_marginal_dev(tqec_plan *p, const uint64_t *d_synd, in
 
 // chunk size of the host pipelines: about `want` shots, rounded down to whole rounds of k_sweep when the plan runs on it
 static int64_t pipeline_chunk(const tqec_plan *p, int64_t want) {
+  if (const char *e = std::getenv("TQEC_PIPE_CHUNK_LOG2")) { const int v = std::atoi(e); if (v >= 10 && v <= 24) want = (int64_t)1 << v; }
   if (!p->has_sweep) return want;
   const int64_t per_round = (int64_t)p->sm_count * p->sw_teams * p->sw.grp;
   return per_round > 0 && want > per_round ? (want / per_round) * per_round : want;
@@ -1287,7 +1288,7 @@ extern "C" int tqec_decode_map(tqec_plan *p, const uint64_t *synd, int64_t B, ui
   // Chunked three-stage pipeline: H2D of chunk c+1 and D2H of chunk c-1 overlap the decode of chunk c (three streams,
   // one event pair per chunk; the device buffers hold the whole batch, so chunks never alias).
   if ((rc = ensure_pipeline(p))) return rc;
-  const int64_t CH = pipeline_chunk(p, (int64_t)1 << 21);
+  const int64_t CH = pipeline_chunk(p, (int64_t)1 << 20);
   const int nsw = p->dev.nsw, ncw = p->dev.ncw;
   const uint64_t *d_syn = (const uint64_t *)p->d_io[0];
   uint64_t *d_cor = (uint64_t *)p->d_io[1];
@@ -1323,7 +1324,7 @@ extern "C" int tqec_decode_marginal(tqec_plan *p, const uint64_t *synd, int64_t 
   if ((rc = ensure_cap(&p->d_io[2], &p->io_cap[2], ab))) return rc;
   // same chunked three-stage pipeline as tqec_decode_map
   if ((rc = ensure_pipeline(p))) return rc;
-  const int64_t CH = pipeline_chunk(p, (int64_t)1 << 21);
+  const int64_t CH = pipeline_chunk(p, (int64_t)1 << 20);
   const int nsw = p->dev.nsw;
   const int64_t NO = (int64_t)1 << p->dev.n_obs;
   const uint64_t *d_syn = (const uint64_t *)p->d_io[0];

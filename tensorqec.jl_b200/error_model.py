@@ -16,7 +16,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _cabi
-from .mod2 import as_bits, pack_bits, unpack_bits
+from .mod2 import as_bits, pack_bits, unpack_bits, validated
 from .tanner import CSSTannerGraph, SimpleTannerGraph
 
 
@@ -84,7 +84,7 @@ class SimpleSyndrome:
     s: np.ndarray
 
     def __post_init__(self):
-        self.s = as_bits(self.s)
+        self.s = validated(self.s)                            # checked once here; decode() does not scan the batch again
 
     def __eq__(self, o):
         return isinstance(o, SimpleSyndrome) and np.array_equal(self.s, o.s)
@@ -96,7 +96,7 @@ class CSSSyndrome:
     sz: np.ndarray
 
     def __post_init__(self):
-        self.sx, self.sz = as_bits(self.sx), as_bits(self.sz)
+        self.sx, self.sz = validated(self.sx), validated(self.sz)
 
     def __eq__(self, o):
         return isinstance(o, CSSSyndrome) and np.array_equal(self.sx, o.sx) and np.array_equal(self.sz, o.sz)

@@ -77,6 +77,20 @@ class ValidatedBits(np.ndarray):
     as_bits returns it as it is instead of scanning a large batch again.  Views and slices keep the mark."""
     _tqec_validated = True
 
+    def __array_ufunc__(self, ufunc, method, *inputs, out=None, **kwargs):
+        # arithmetic on validated bits gives plain arrays (the result need not be 0/1); only views and slices keep the mark
+        plain = tuple(np.asarray(x) if isinstance(x, ValidatedBits) else x for x in inputs)
+        if out is not None:
+            kwargs["out"] = tuple(np.asarray(x) if isinstance(x, ValidatedBits) else x for x in out)
+        return getattr(ufunc, method)(*plain, **kwargs)
+
+
+def validated(v) -> np.ndarray:
+    """as_bits + the ValidatedBits mark: containers that checked their bits once (SimpleSyndrome, CSSSyndrome) hand them
+    to `decode` without a second pass over a batch-sized array."""
+    a = as_bits(v)
+    return a if isinstance(a, ValidatedBits) else a.view(ValidatedBits)
+
 
 _LIBC = None
 
