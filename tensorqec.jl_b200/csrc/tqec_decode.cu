@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <future>
 #include <thread>
 
 #include "tqec_common.h"
@@ -1288,7 +1289,7 @@ extern "C" int tqec_decode_map(tqec_plan *p, const uint64_t *synd, int64_t B, ui
   // Chunked three-stage pipeline: H2D of chunk c+1 and D2H of chunk c-1 overlap the decode of chunk c (three streams,
   // one event pair per chunk; the device buffers hold the whole batch, so chunks never alias).
   if ((rc = ensure_pipeline(p))) return rc;
-  const int64_t CH = pipeline_chunk(p, (int64_t)1 << 20);
+  const int64_t CH = pipeline_chunk(p, std::min<int64_t>((int64_t)1 << 20, std::max<int64_t>((int64_t)1 << 18, B / 4)));   // >= 4 chunks in flight when the batch allows
   const int nsw = p->dev.nsw, ncw = p->dev.ncw;
   const uint64_t *d_syn = (const uint64_t *)p->d_io[0];
   uint64_t *d_cor = (uint64_t *)p->d_io[1];
@@ -1324,7 +1325,7 @@ extern "C" int tqec_decode_marginal(tqec_plan *p, const uint64_t *synd, int64_t 
   if ((rc = ensure_cap(&p->d_io[2], &p->io_cap[2], ab))) return rc;
   // same chunked three-stage pipeline as tqec_decode_map
   if ((rc = ensure_pipeline(p))) return rc;
-  const int64_t CH = pipeline_chunk(p, (int64_t)1 << 20);
+  const int64_t CH = pipeline_chunk(p, std::min<int64_t>((int64_t)1 << 20, std::max<int64_t>((int64_t)1 << 18, B / 4)));   // >= 4 chunks in flight when the batch allows
   const int nsw = p->dev.nsw;
   const int64_t NO = (int64_t)1 << p->dev.n_obs;
   const uint64_t *d_syn = (const uint64_t *)p->d_io[0];
@@ -1403,7 +1404,8 @@ static void par_memcpy(void *dst, const void *src, size_t n) {
   const size_t MIN_PART = (size_t)4 << 20;
   unsigned hw = std::thread::hardware_concurrency();
   size_t parts = n / MIN_PART;
-  if (parts > 6) parts = 6;
+  static const size_t max_parts = [] { const char *e = std::getenv("TQEC_COPY_THREADS"); const int v = e ? std::atoi(e) : 0; return (size_t)(v >= 1 && v <= 64 ? v : 8); }();
+  if (parts > max_parts) parts = max_parts;
   if (hw && parts > hw) parts = hw;
   if (parts <= 1) { std::memcpy(dst, src, n); return; }
   std::vector<std::thread> th;
@@ -1455,6 +1457,8 @@ static int decode_bytes(tqec_plan *p, const uint8_t *synd_bits, int64_t B, uint8
   if ((rc = ensure_pinned(&p->h_pin[2], &p->h_pin_cap[2], 2 * sz3))) return rc;
   const int64_t n_chunks = (B + nb - 1) / nb;
   bool ev_out_used[2] = {false, false};
+  std::future<int> out_task;                                     // copy-out of chunk c - 1 (at most one in flight)
+  struct Joiner { std::future<int> &f; ~Joiner() { if (f.valid()) f.wait(); } } joiner{out_task};   // early returns wait for it
   for (int64_t c = 0; c <= n_chunks; ++c) {
     const int slot = (int)(c & 1);
     if (c < n_chunks) {
@@ -1486,6 +1490,8 @@ static int decode_bytes(tqec_plan *p, const uint8_t *synd_bits, int64_t B, uint8
       }
       TQEC_CUDA(cudaEventRecord(p->ev_cmp[slot], p->stream));
       TQEC_CUDA(cudaStreamWaitEvent(p->s_out, p->ev_cmp[slot], 0));
+      // chunk c - 2's results must have left the staging slot before chunk c's transfers are enqueued into it
+      if (out_task.valid() && out_task.get() != 0) { tqec::set_error("decode_bytes: waiting for a result transfer failed"); return TQEC_ERR_CUDA; }
       if (mp) {
         TQEC_CUDA(cudaMemcpyAsync((uint8_t *)p->h_pin[2] + slot * sz3, d_x, (size_t)n * nv, cudaMemcpyDeviceToHost, p->s_out));
         if (out) TQEC_CUDA(cudaMemcpyAsync((char *)p->h_pin[1] + slot * sz2, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost, p->s_out));
@@ -1497,19 +1503,27 @@ static int decode_bytes(tqec_plan *p, const uint8_t *synd_bits, int64_t B, uint8
       ev_out_used[slot] = true;
       p->launches += mp ? 2 : 1;
     }
-    if (c >= 1) {                                                // results of the previous chunk: pinned staging -> caller's arrays
+    if (c >= 1) {
+      // results of the previous chunk: pinned staging -> caller's arrays, on a helper thread so that the copy overlaps the
+      // next chunk's input copy on this one (joined before the staging slot's next transfer is enqueued, i.e. next pass)
       const int ps = (int)((c - 1) & 1);
       const int64_t o = (c - 1) * nb, n = B - o < nb ? B - o : nb;
-      TQEC_CUDA(cudaEventSynchronize(p->ev_out[ps]));
-      if (mp) {
-        par_memcpy(corr_bits + (size_t)o * nv, (uint8_t *)p->h_pin[2] + ps * sz3, (size_t)n * nv);
-        if (out) std::memcpy(out + o, (char *)p->h_pin[1] + ps * sz2, (size_t)n * 8);
-      } else {
-        par_memcpy(out + o * NO, (char *)p->h_pin[1] + ps * sz2, (size_t)n * NO * 8);
-        if (argmax_out) std::memcpy(argmax_out + o, (uint8_t *)p->h_pin[2] + ps * sz3, (size_t)n * 4);
-      }
+      const int dev = p->device;
+      if (out_task.valid() && out_task.get() != 0) { tqec::set_error("decode_bytes: waiting for a result transfer failed"); return TQEC_ERR_CUDA; }
+      out_task = std::async(std::launch::async, [=]() -> int {
+        if (cudaSetDevice(dev) != cudaSuccess || cudaEventSynchronize(p->ev_out[ps]) != cudaSuccess) return 1;
+        if (mp) {
+          par_memcpy(corr_bits + (size_t)o * nv, (uint8_t *)p->h_pin[2] + ps * sz3, (size_t)n * nv);
+          if (out) std::memcpy(out + o, (char *)p->h_pin[1] + ps * sz2, (size_t)n * 8);
+        } else {
+          par_memcpy(out + o * NO, (char *)p->h_pin[1] + ps * sz2, (size_t)n * NO * 8);
+          if (argmax_out) std::memcpy(argmax_out + o, (uint8_t *)p->h_pin[2] + ps * sz3, (size_t)n * 4);
+        }
+        return 0;
+      });
     }
   }
+  if (out_task.valid() && out_task.get() != 0) { tqec::set_error("decode_bytes: waiting for a result transfer failed"); return TQEC_ERR_CUDA; }
   TQEC_CUDA(cudaStreamSynchronize(p->stream));
   return TQEC_OK;
 }
