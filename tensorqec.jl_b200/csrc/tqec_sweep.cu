@@ -509,11 +509,16 @@ int launch_sweep(tqec_plan *plan, const uint64_t *d_synd, int64_t B, uint64_t *d
   const int64_t per_round = (int64_t)plan->sm_count * plan->sw_teams * P.grp;
   const int64_t rounds = B / per_round, tail = B - rounds * per_round;
   int g_tail = P.grp;
-  if (P.grp == 32 && rounds >= 4 && tail > 0 && std::getenv("TQEC_SWEEP_NO_TAIL_SPLIT") == nullptr) {
+  if (P.grp == 32 && tail > 0 && std::getenv("TQEC_SWEEP_NO_TAIL_SPLIT") == nullptr) {
     if (4 * tail <= per_round && (1 << P.sg) <= 8) g_tail = 8;
     else if (2 * tail <= per_round && (1 << P.sg) <= 16) g_tail = 16;
   }
   if (g_tail == P.grp) return launch_sweep_part(plan, P, d_synd, B, d_corr, d_out, d_argmax, stream);
+  if (rounds == 0) {                                             // less than a round in all (the last chunk of a pipeline, small
+    SweepDev T = P;                                              // batches): one launch with the smaller groups, every SM busy
+    T.grp = g_tail;
+    return launch_sweep_part(plan, T, d_synd, B, d_corr, d_out, d_argmax, stream);
+  }
   const int64_t main_shots = rounds * per_round;
   const int64_t NO = plan->semiring == TQEC_SEMIRING_MAXPLUS ? 1 : ((int64_t)1 << P.n_obs);
   int rc = launch_sweep_part(plan, P, d_synd, main_shots, d_corr, d_out, d_argmax, stream);

@@ -137,6 +137,7 @@ def test_sweep_tail_launch_does_not_change_results(tq, extra, monkeypatch):
     t, em = _css_case(tq, tq.SurfaceCode(7, 7))
     ct = tq.compile(tq.TNMAP(), t, em)
     assert ct.cd.plan.query(_cabi.Q_SWEEP) == 1
+    monkeypatch.setenv("TQEC_PIPE_CHUNK_LOG2", "24")           # one chunk: the host pipeline would cut the batch at whole rounds
     per_round = 148 * 16 * 32
     B = 4 * per_round + extra
     ex, ez, sx, sz = _syndromes(t, em, 31, 8192)
