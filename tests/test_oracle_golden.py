@@ -3,6 +3,7 @@ tests hold for this path.  CPU only."""
 import os
 
 import numpy as np
+import pytest
 
 from oracle import bruteforce, cref, dense, emulator, frontier, gf2, networks, philox
 
@@ -115,6 +116,26 @@ def test_mod2_and_bitmul(tq):
     w = tq.pack_bits(A)
     assert w.shape == (300, 16) and np.array_equal(tq.unpack_bits(w, 1000), A)
     assert int(w[0, 0]) & 1 == A[0, 0] and (int(w[0, 1]) >> 3) & 1 == A[0, 67]
+
+
+def test_syndrome_containers_validate_once(tq):
+    """SimpleSyndrome / CSSSyndrome check their bits when they are built and hand `decode` marked arrays (no second pass over a
+    batch); views keep the mark, anything computed from them is a plain array again and would be checked."""
+    from tensorqec.jl_b200.mod2 import ValidatedBits, as_bits
+    sx = np.array([[0, 1, 1], [1, 0, 0]], dtype=np.uint8)
+    s = tq.CSSSyndrome(sx, [[1, 0], [0, 1]])
+    assert isinstance(s.sx, ValidatedBits) and isinstance(s.sz, ValidatedBits) and np.shares_memory(s.sx, sx)
+    assert as_bits(s.sx) is s.sx and isinstance(s.sx[1:], ValidatedBits)
+    for derived in (s.sx + 1, s.sx ^ s.sx, np.concatenate([s.sx, s.sz], axis=1), np.asarray(s.sx)):
+        assert not isinstance(derived, ValidatedBits)
+    with pytest.raises(ValueError):
+        as_bits(s.sx + 1)
+    with pytest.raises(ValueError):
+        tq.SimpleSyndrome(np.array([0, 1, 2], dtype=np.uint8))
+    with pytest.raises(ValueError):
+        tq.CSSSyndrome(sx, [[0, 3]])
+    assert tq.SimpleSyndrome([0, 1, 1]) == tq.SimpleSyndrome(np.array([0, 1, 1])) and s == tq.CSSSyndrome(sx.copy(), s.sz)
+    assert int(s.sx.sum()) == 3 and bool((s.sx == sx).all())
 
 
 def test_color488_and_steane(tq):
