@@ -79,6 +79,7 @@ struct SweepDev {
   int32_t head_tma;                 // 1: head rows are stored pre-swizzled and fetched by cp.async.bulk (TMA)
   int32_t grp;                      // shots per deferred-traceback group (2^sg .. 32): the back-pointer ring of a team holds this many
   int32_t off_states, off_rec, off_lanetab, off_tvals, off_words, words_bytes;   // shared-memory layout (bytes)
+  int32_t off_tb;                   // >= 0: the traceback records have a shared-memory copy at this offset (max-plus plans)
 };
 
 // Device view of the global-memory lowering of a plan (tqec_wide.cu; tables described in tensorqec.jl_b200/wide.py).

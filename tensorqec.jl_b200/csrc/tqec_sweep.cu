@@ -51,6 +51,16 @@ __device__ __forceinline__ uint32_t sw_xor3(uint32_t a, uint32_t b, uint32_t c) 
   asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
 }
+__device__ __forceinline__ int32_t sw_lds32(uint32_t addr) {
+  int32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int4 sw_lds128(uint32_t addr) {
+  int4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 // ---- TMA (1-D bulk copy) of a tabulated head row into the team's state, completion on an mbarrier ----------------------------
 __device__ __forceinline__ void sw_mbar_init(uint32_t bar) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
@@ -248,6 +258,94 @@ __device__ __forceinline__ void sweep_step(const int32_t *__restrict__ rec, cons
   }
 }
 
+// Deferred traceback of one shot (lane q walks shot q of its group backwards through the super-steps): per step the patch
+// coordinates of the current entry, the packed back-pointers of its patch, the assignments they encode, the entry the winner came
+// from.  A chain of dependent look-ups, so the records are read from the CTA's shared-memory copy when there is one (TBSM).
+template <bool TBSM>
+__device__ __forceinline__ void sw_traceback(const SweepDev &P, uint32_t tb_abs, const uint32_t *bp, int lane, const uint64_t (&syn)[4],
+                                             int64_t myshot, int64_t B, uint64_t *__restrict__ corr) {
+#define TBW(k) (TBSM ? sw_lds32(taddr + 4u * (uint32_t)(k)) : __ldg(t + (k)))
+#define TBW4(k) (TBSM ? sw_lds128(taddr + 4u * (uint32_t)(k)) : __ldg(reinterpret_cast<const int4 *>(t + (k))))
+  const int SG = 1 << P.sg, NE = 1 << P.W;
+    const int f = lane >> P.sg, sub = lane & (SG - 1);
+    const uint32_t *bpq = bp + (size_t)f * P.bp_words * 32;
+    uint64_t cfg[4] = {0ull, 0ull, 0ull, 0ull};
+    uint32_t x = (uint32_t)P.out_index[0] | ((uint32_t)sub << P.W);
+    for (int i = P.n_ss - 1; i >= 0; --i) {
+      const int32_t *t = P.tb + (size_t)i * SW_TB_INTS;
+      const uint32_t taddr = tb_abs + (uint32_t)i * (SW_TB_INTS * 4);
+      const int4 t0 = TBW4(0);          // M, layers, loop bits, bpp
+      const int4 t1 = TBW4(4);      // wbase, ipw, closed, late (bit | patch bit << 16)
+      const int4 tp = TBW4(8);      // positions of patch bits
+      const int pos[4] = {tp.x, tp.y, tp.z, tp.w};
+      uint32_t j = 0, ln = 0, it = 0, pm = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (b < t0.x) { j |= ((x >> pos[b]) & 1u) << b; pm |= 1u << pos[b]; }
+#pragma unroll
+      for (int q = 0; q < 5; ++q) ln |= ((x >> TBW(12 + q)) & 1u) << q;
+      for (int q = 0; q < t0.z; ++q) it |= ((x >> TBW(17 + q)) & 1u) << q;
+      uint32_t lsyn = 0;
+      if (t1.w >= 0) {
+        const int sb = t1.w & 0xffff, w = sb >> 6;
+        const uint64_t sw = w == 0 ? syn[0] : (w == 1 ? syn[1] : (w == 2 ? syn[2] : syn[3]));
+        lsyn = (uint32_t)((sw >> (sb & 63)) & 1ull);
+        j ^= lsyn << (t1.w >> 16);
+      }
+      uint32_t pb = 0;
+      if (t0.w) {
+        const uint32_t wd = __ldcg(bpq + (size_t)(t1.x + it / t1.y) * 32 + ln);
+        pb = wd >> (t0.w * (it % t1.y));
+      }
+      for (int li = t0.y - 1; li >= 0; --li) {
+        const int lo = 30 + 14 * li;
+        const int np = TBW(lo), nf = TBW(lo + 1), bo = TBW(lo + 2), flipm = TBW(lo + 11);
+        const uint32_t k = nf ? ((pb >> (bo + j * nf)) & ((1u << nf) - 1u)) : 0u;
+        uint32_t pflip = 0;
+        for (int q = 0; q < np; ++q) {
+          const int pbit = TBW(lo + 3 + 2 * q), v = TBW(lo + 4 + 2 * q);
+          if ((j >> pbit) & 1u) pflip ^= (uint32_t)TBW(lo + 12 + q);
+          const uint64_t bitv = (uint64_t)(((j >> pbit) & 1u) ^ (lsyn & ((uint32_t)flipm >> q) & 1u)) << (v & 63);
+          const int w = v >> 6;
+          cfg[0] |= w == 0 ? bitv : 0ull; cfg[1] |= w == 1 ? bitv : 0ull;
+          cfg[2] |= w == 2 ? bitv : 0ull; cfg[3] |= w == 3 ? bitv : 0ull;
+        }
+        for (int q = 0; q < nf; ++q) {
+          const int fm = TBW(lo + 7 + 2 * q), v = TBW(lo + 8 + 2 * q);
+          const uint32_t kb = (k >> q) & 1u;
+          const uint64_t bitv = (uint64_t)kb << (v & 63);
+          const int w = v >> 6;
+          cfg[0] |= w == 0 ? bitv : 0ull; cfg[1] |= w == 1 ? bitv : 0ull;
+          cfg[2] |= w == 2 ? bitv : 0ull; cfg[3] |= w == 3 ? bitv : 0ull;
+          if (kb) j ^= (uint32_t)fm;
+        }
+        j ^= pflip;
+      }
+      x &= ~pm;
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (b < t0.x) x |= ((j >> b) & 1u) << pos[b];
+      for (int q = 0; q < t1.z; ++q) {
+        const int sb = TBW(22 + 2 * q), ps = TBW(23 + 2 * q), w = sb >> 6;
+        const uint64_t sw = w == 0 ? syn[0] : (w == 1 ? syn[1] : (w == 2 ? syn[2] : syn[3]));
+        x ^= (uint32_t)((sw >> (sb & 63)) & 1ull) << ps;
+      }
+    }
+    int hp = 0;
+    for (int jb = 0; jb < P.nh; ++jb) {
+      const int b = P.head_bits[jb], w = b >> 6;
+      const uint64_t sw = w == 0 ? syn[0] : (w == 1 ? syn[1] : (w == 2 ? syn[2] : syn[3]));
+      hp |= (int)((sw >> (b & 63)) & 1ull) << jb;
+    }
+    const uint64_t *hc = P.head_cfg + (((size_t)hp << P.W) + (x & (uint32_t)(NE - 1))) * P.ncw;
+    if (myshot < B)
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+        if (w < P.ncw) corr[myshot * P.ncw + w] = cfg[w] | __ldg(hc + w);
+#undef TBW
+#undef TBW4
+}
+
 // EXT = 1 additionally compiles the shapes with fresh pins (menu ids TQEC_SWEEP_MENU_BASE .. TQEC_SWEEP_MENU_MAXPLUS - 1: even-
 // distance and rectangular codes); plans that do not use them run the EXT = 0 instantiation, whose code is unchanged
 template <int SEMI, int MAXT, int EXT>
@@ -264,6 +362,11 @@ k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, ui
   for (int i = threadIdx.x; i < P.n_ss * SW_REC_INTS; i += blockDim.x) sm_rec[i] = P.rec[i];
   for (int i = threadIdx.x; i < P.n_ss * 32; i += blockDim.x) sm_lt[i] = P.lanetab[i];
   for (int i = threadIdx.x; i < P.n_tvals; i += blockDim.x) sm_tv[i] = P.tvals[i];
+  // traceback records: the walk is a chain of dependent look-ups per super-step, so they sit next to the other tables
+  int32_t *sm_tb = reinterpret_cast<int32_t *>(smem_raw + (P.off_tb >= 0 ? P.off_tb : 0));
+  const uint32_t tb_abs = (uint32_t)__cvta_generic_to_shared(sm_tb);
+  if (SEMI == TQEC_SEMIRING_MAXPLUS && P.off_tb >= 0)
+    for (int i = threadIdx.x; i < P.n_ss * SW_TB_INTS; i += blockDim.x) sm_tb[i] = P.tb[i];
   __syncthreads();
   unsigned char *words = smem_raw + P.off_words + (size_t)P.words_bytes * warp;
   uint64_t *sh_syn = reinterpret_cast<uint64_t *>(words);
@@ -399,80 +502,8 @@ k_sweep(const SweepDev P, const uint64_t *__restrict__ synd, const int64_t B, ui
 
     // deferred traceback: lane q walks shot q of the group
     if (SEMI == TQEC_SEMIRING_MAXPLUS && live && lane < G) {
-      const int f = lane >> P.sg, sub = lane & (SG - 1);
-      const uint32_t *bpq = bp + (size_t)f * P.bp_words * 32;
-      uint64_t cfg[4] = {0ull, 0ull, 0ull, 0ull};
-      uint32_t x = (uint32_t)P.out_index[0] | ((uint32_t)sub << P.W);
-      for (int i = P.n_ss - 1; i >= 0; --i) {
-        const int32_t *t = P.tb + (size_t)i * SW_TB_INTS;
-        const int4 t0 = __ldg(reinterpret_cast<const int4 *>(t));          // M, layers, loop bits, bpp
-        const int4 t1 = __ldg(reinterpret_cast<const int4 *>(t + 4));      // wbase, ipw, closed, late (bit | patch bit << 16)
-        const int4 tp = __ldg(reinterpret_cast<const int4 *>(t + 8));      // positions of patch bits
-        const int pos[4] = {tp.x, tp.y, tp.z, tp.w};
-        uint32_t j = 0, ln = 0, it = 0, pm = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-          if (b < t0.x) { j |= ((x >> pos[b]) & 1u) << b; pm |= 1u << pos[b]; }
-#pragma unroll
-        for (int q = 0; q < 5; ++q) ln |= ((x >> __ldg(t + 12 + q)) & 1u) << q;
-        for (int q = 0; q < t0.z; ++q) it |= ((x >> __ldg(t + 17 + q)) & 1u) << q;
-        uint32_t lsyn = 0;
-        if (t1.w >= 0) {
-          const int sb = t1.w & 0xffff, w = sb >> 6;
-          const uint64_t sw = w == 0 ? syn[0] : (w == 1 ? syn[1] : (w == 2 ? syn[2] : syn[3]));
-          lsyn = (uint32_t)((sw >> (sb & 63)) & 1ull);
-          j ^= lsyn << (t1.w >> 16);
-        }
-        uint32_t pb = 0;
-        if (t0.w) {
-          const uint32_t wd = __ldcg(bpq + (size_t)(t1.x + it / t1.y) * 32 + ln);
-          pb = wd >> (t0.w * (it % t1.y));
-        }
-        for (int li = t0.y - 1; li >= 0; --li) {
-          const int32_t *L = t + 30 + 14 * li;
-          const int np = __ldg(L), nf = __ldg(L + 1), bo = __ldg(L + 2), flipm = __ldg(L + 11);
-          const uint32_t k = nf ? ((pb >> (bo + j * nf)) & ((1u << nf) - 1u)) : 0u;
-          uint32_t pflip = 0;
-          for (int q = 0; q < np; ++q) {
-            const int pbit = __ldg(L + 3 + 2 * q), v = __ldg(L + 4 + 2 * q);
-            if ((j >> pbit) & 1u) pflip ^= (uint32_t)__ldg(L + 12 + q);
-            const uint64_t bitv = (uint64_t)(((j >> pbit) & 1u) ^ (lsyn & ((uint32_t)flipm >> q) & 1u)) << (v & 63);
-            const int w = v >> 6;
-            cfg[0] |= w == 0 ? bitv : 0ull; cfg[1] |= w == 1 ? bitv : 0ull;
-            cfg[2] |= w == 2 ? bitv : 0ull; cfg[3] |= w == 3 ? bitv : 0ull;
-          }
-          for (int q = 0; q < nf; ++q) {
-            const int fm = __ldg(L + 7 + 2 * q), v = __ldg(L + 8 + 2 * q);
-            const uint32_t kb = (k >> q) & 1u;
-            const uint64_t bitv = (uint64_t)kb << (v & 63);
-            const int w = v >> 6;
-            cfg[0] |= w == 0 ? bitv : 0ull; cfg[1] |= w == 1 ? bitv : 0ull;
-            cfg[2] |= w == 2 ? bitv : 0ull; cfg[3] |= w == 3 ? bitv : 0ull;
-            if (kb) j ^= (uint32_t)fm;
-          }
-          j ^= pflip;
-        }
-        x &= ~pm;
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-          if (b < t0.x) x |= ((j >> b) & 1u) << pos[b];
-        for (int q = 0; q < t1.z; ++q) {
-          const int sb = __ldg(t + 22 + 2 * q), ps = __ldg(t + 23 + 2 * q), w = sb >> 6;
-          const uint64_t sw = w == 0 ? syn[0] : (w == 1 ? syn[1] : (w == 2 ? syn[2] : syn[3]));
-          x ^= (uint32_t)((sw >> (sb & 63)) & 1ull) << ps;
-        }
-      }
-      int hp = 0;
-      for (int jb = 0; jb < P.nh; ++jb) {
-        const int b = P.head_bits[jb], w = b >> 6;
-        const uint64_t sw = w == 0 ? syn[0] : (w == 1 ? syn[1] : (w == 2 ? syn[2] : syn[3]));
-        hp |= (int)((sw >> (b & 63)) & 1ull) << jb;
-      }
-      const uint64_t *hc = P.head_cfg + (((size_t)hp << P.W) + (x & (uint32_t)(NE - 1))) * P.ncw;
-      if (myshot < B)
-#pragma unroll
-        for (int w = 0; w < 4; ++w)
-          if (w < P.ncw) corr[myshot * P.ncw + w] = cfg[w] | __ldg(hc + w);
+      if (P.off_tb >= 0) sw_traceback<true>(P, tb_abs, bp, lane, syn, myshot, B, corr);
+      else sw_traceback<false>(P, 0u, bp, lane, syn, myshot, B, corr);
     }
     __syncwarp();
   }
@@ -603,6 +634,7 @@ int sweep_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &pr
   const size_t gap = (8192 - (size_t)reserved % 8192) % 8192;
   const size_t rec_b = ((size_t)s->n_ss * SW_REC_INTS * 4 + 15) & ~(size_t)15, lt_b = (size_t)s->n_ss * 128;
   const size_t tv_b = ((size_t)s->n_tvals * 8 + 15) & ~(size_t)15;
+  const size_t tb_b = d->semiring == TQEC_SEMIRING_MAXPLUS && std::getenv("TQEC_SWEEP_TB_GLOBAL") == nullptr ? (size_t)s->n_ss * SW_TB_INTS * 4 : 0;
   const size_t words_b = ((((size_t)nsw << s->sg) * 8 + ((size_t)s->n_ss << s->sg) * 4 + 15) & ~(size_t)15) + 16;   // syndromes, early + late masks, mbarrier
   // register budget variant: 512 threads (128 registers), 640 (96) or 768 (80); TQEC_SWEEP_MAXT overrides the default
   int maxt = 512;
@@ -627,20 +659,21 @@ int sweep_create(tqec_plan *p, const tqec_plan_desc *d, const cudaDeviceProp &pr
   if (const char *e = std::getenv("TQEC_SWEEP_TEAMS")) { const int v = std::atoi(e); if (v >= 1 && v < cap) cap = v; }
   const size_t budget = (size_t)prop.sharedMemPerBlockOptin;
   int nw = 0;
-  size_t offs[4] = {0, 0, 0, 0}, total = 0;
+  size_t offs[5] = {0, 0, 0, 0, 0}, total = 0;
   for (int cand = cap; cand >= 1 && nw == 0; --cand) {
     size_t front = 0, tail = gap + (size_t)8192 * cand;
-    const size_t sizes[4] = {rec_b, lt_b, tv_b, words_b * cand};
-    size_t o[4];
-    for (int i = 0; i < 4; ++i) {
+    const size_t sizes[5] = {rec_b, lt_b, tv_b, words_b * cand, tb_b};
+    size_t o[5];
+    for (int i = 0; i < 5; ++i) {
       if (front + sizes[i] <= gap) { o[i] = front; front += sizes[i]; }
       else { o[i] = tail; tail += sizes[i]; }
     }
-    if (tail <= budget) { nw = cand; total = tail; for (int i = 0; i < 4; ++i) offs[i] = o[i]; }
+    if (tail <= budget) { nw = cand; total = tail; for (int i = 0; i < 5; ++i) offs[i] = o[i]; }
   }
   if (nw < 1) { sweep_destroy(p); std::memset(p->d_sw, 0, sizeof(p->d_sw)); return TQEC_OK; }   // does not fit: general kernels
   D.off_states = (int32_t)gap; D.off_rec = (int32_t)offs[0]; D.off_lanetab = (int32_t)offs[1]; D.off_tvals = (int32_t)offs[2];
   D.off_words = (int32_t)offs[3]; D.words_bytes = (int32_t)words_b;
+  D.off_tb = tb_b ? (int32_t)offs[4] : -1;
   p->sw_teams = nw; p->sw_smem = (int)total;
   TQEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
   const size_t bp_bytes = (size_t)p->sm_count * nw * (D.grp >> s->sg) * D.bp_words * 32 * sizeof(uint32_t);
