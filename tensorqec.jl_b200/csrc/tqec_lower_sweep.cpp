@@ -1,11 +1,15 @@
 // Host-side lowering, part 2: the in-place patch sweep executed by k_sweep (see tqec_lower.h).
 // Mirrors tensorqec.jl_b200/sweep.py decision for decision (that file carries the full description).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <set>
 #include <stdexcept>
+#include <thread>
 
 #include "tqec_lower.h"
 #include "tqec_sweep_menu.h"
@@ -159,6 +163,25 @@ static Desc descriptor(const std::vector<const Raw *> &group, const std::vector<
   return d;
 }
 
+// Split [0, n) over a few host threads when the range is large (head tables of 2^20+ entries); every index is computed
+// independently of the others, so the result does not depend on the split.
+template <typename F>
+static void parallel_ranges(size_t n, F &&fn) {
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t parts = n >> 16;
+  if (parts > 16) parts = 16;
+  if (hw && parts > hw) parts = hw;
+  if (parts <= 1) { fn((size_t)0, n); return; }
+  const size_t step = (n + parts - 1) / parts;
+  std::vector<std::thread> th;
+  for (size_t k = 1; k < parts; ++k) {
+    const size_t lo = k * step, hi = std::min(n, lo + step);
+    if (lo < hi) th.emplace_back([&fn, lo, hi] { fn(lo, hi); });
+  }
+  fn((size_t)0, std::min(n, step));
+  for (auto &t : th) t.join();
+}
+
 // Tabulate the first h steps for every value of the syndrome bits they close (sweep.py:_head_eval).  Internal layout:
 // one index bit per axis in creation order; closing a check only changes the role of its axis (state axis -> batch
 // axis of that syndrome bit), no data moves.  Output in POSITION order: [head pattern][state index], index bit
@@ -175,6 +198,8 @@ static void head_eval(const Schedule &sch, int h, const std::vector<Role> &roles
   std::vector<uint64_t> cfg;
   if (maxplus) cfg.assign(ncw, 0);
   const double zero = maxplus ? -INFINITY : 0.0;
+  std::vector<double> best;
+  std::vector<uint64_t> bcfg;
   for (int t = 0; t < h; ++t) {
     const Role &R = roles[t];
     const Factor &f = sch.factors[R.fi];
@@ -195,42 +220,50 @@ static void head_eval(const Schedule &sch, int h, const std::vector<Role> &roles
       throw std::runtime_error("head_eval: check is not open");
     };
     const size_t n = St.size();
-    std::vector<double> best(n);
-    std::vector<uint64_t> bcfg;
-    if (maxplus) bcfg.resize(n * ncw);
+    if (best.size() < n) best.resize(n);                          // the two buffers of a step are kept and swapped: no fresh
+    if (maxplus && bcfg.size() < n * ncw) bcfg.resize(n * ncw);   // 200 MB allocation (and its page faults) per step
     const int NA = 1 << f.vars.size();
+    std::vector<size_t> flips(NA, 0);
+    std::vector<uint64_t> amasks((size_t)NA * ncw, 0);
     for (int a = 0; a < NA; ++a) {
-      size_t flip = 0;
       for (int c : R.touched) {
         int p = 0;
         for (size_t j = 0; j < f.vars.size(); ++j)
           if (check_has(sch.checks[c], f.vars[j])) p ^= (a >> j) & 1;
-        if (p) flip |= (size_t)1 << bit_of_check(c);
+        if (p) flips[a] |= (size_t)1 << bit_of_check(c);
       }
-      std::vector<uint64_t> amask(ncw, 0);
       if (maxplus)
         for (size_t j = 0; j < f.vars.size(); ++j)
-          if ((a >> j) & 1) amask[f.vars[j] >> 6] |= (uint64_t)1 << (f.vars[j] & 63);
-      const double ta = T[a];
-      for (size_t i = 0; i < n; ++i) {
-        const size_t src = i ^ flip;
-        const double cand = maxplus ? St[src] + ta : St[src] * ta;
-        if (a == 0) {
-          best[i] = cand;
-          if (maxplus)
-            for (int w = 0; w < ncw; ++w) bcfg[i * ncw + w] = cfg[src * ncw + w] | amask[w];
-        } else if (maxplus) {
-          if (cand > best[i]) {            // strict: the smallest assignment wins exact ties
+          if ((a >> j) & 1) amasks[(size_t)a * ncw + (f.vars[j] >> 6)] |= (uint64_t)1 << (f.vars[j] & 63);
+    }
+    // per entry: candidates in ascending assignment order (the order of the additions and of the tie rule is per entry,
+    // so the entries can be split over threads)
+    parallel_ranges(n, [&](size_t i0, size_t i1) {
+      for (int a = 0; a < NA; ++a) {
+        const size_t flip = flips[a];
+        const uint64_t *amask = amasks.data() + (size_t)a * ncw;
+        const double ta = T[a];
+        for (size_t i = i0; i < i1; ++i) {
+          const size_t src = i ^ flip;
+          const double cand = maxplus ? St[src] + ta : St[src] * ta;
+          if (a == 0) {
             best[i] = cand;
-            for (int w = 0; w < ncw; ++w) bcfg[i * ncw + w] = cfg[src * ncw + w] | amask[w];
+            if (maxplus)
+              for (int w = 0; w < ncw; ++w) bcfg[i * ncw + w] = cfg[src * ncw + w] | amask[w];
+          } else if (maxplus) {
+            if (cand > best[i]) {            // strict: the smallest assignment wins exact ties
+              best[i] = cand;
+              for (int w = 0; w < ncw; ++w) bcfg[i * ncw + w] = cfg[src * ncw + w] | amask[w];
+            }
+          } else {
+            best[i] = best[i] + cand;
           }
-        } else {
-          best[i] = best[i] + cand;
         }
       }
-    }
+    });
+    best.resize(n);
     St.swap(best);
-    if (maxplus) cfg.swap(bcfg);
+    if (maxplus) { bcfg.resize(n * ncw); cfg.swap(bcfg); }
     for (int c : R.closing) {
       const int p = bit_of_check(c);
       axis_batch[p] = 1;
@@ -256,20 +289,20 @@ static void head_eval(const Schedule &sch, int h, const std::vector<Role> &roles
   if (maxplus) hc.assign(total * ncw, 0); else hc.assign(((size_t)1 << nh) * ncw, 0);
   uint32_t extra_mask = 0;
   for (int k = W; k < Wt; ++k) extra_mask |= 1u << chain_pos[k];
-  for (size_t hp = 0; hp < ((size_t)1 << nh); ++hp) {
-    size_t bsrc = 0;
-    for (int j = 0; j < nh; ++j)
-      if ((hp >> j) & 1) bsrc |= (size_t)1 << batch_order[j];
-    for (size_t idx = 0; idx < ((size_t)1 << Wt); ++idx) {
-      if (idx & extra_mask) { hs[(hp << Wt) | idx] = zero; continue; }
-      size_t src = bsrc;
+  parallel_ranges(total, [&](size_t e0, size_t e1) {
+    for (size_t e = e0; e < e1; ++e) {
+      const size_t hp = e >> Wt, idx = e & (((size_t)1 << Wt) - 1);
+      if (idx & extra_mask) { hs[e] = zero; continue; }
+      size_t src = 0;
+      for (int j = 0; j < nh; ++j)
+        if ((hp >> j) & 1) src |= (size_t)1 << batch_order[j];
       for (int k = 0; k < W; ++k)
         if ((idx >> chain_pos[k]) & 1) src |= (size_t)1 << state_bit[k];
-      hs[(hp << Wt) | idx] = St[src];
+      hs[e] = St[src];
       if (maxplus)
-        for (int w = 0; w < ncw; ++w) hc[((hp << Wt) | idx) * ncw + w] = cfg[src * ncw + w];
+        for (int w = 0; w < ncw; ++w) hc[e * ncw + w] = cfg[src * ncw + w];
     }
-  }
+  });
 }
 
 static std::pair<std::vector<int>, int> assign_positions(const std::vector<std::vector<int>> &groups, int W, uint64_t seed = 0) {
@@ -738,7 +771,11 @@ bool lower_sweep(const Schedule &sch, int max_head_bits, SweepPlan &plan) {
   plan.W = W; plan.sg = sg; plan.head_steps = h; plan.n_ss = (int)ssteps.size(); plan.bp_words = wbase; plan.conflicts = ap.second;
   plan.head_bits = head_bits;
   plan.out_index = out_index;
+  const auto tq_t0 = std::chrono::steady_clock::now();
   head_eval(sch, h, roles, head_bits, live_order, chain_pos, W, plan.head_state, plan.head_cfg);
+  if (std::getenv("TQEC_LOWER_TIMING"))
+    fprintf(stderr, "lower_sweep: head_eval %.3f s (%d head bits, %d steps)\n",
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - tq_t0).count(), (int)head_bits.size(), h);
   encode_sweep(plan, ssteps);
   return true;
 }
