@@ -16,6 +16,7 @@
 #include <cstring>
 
 #include <future>
+#include <system_error>
 #include <thread>
 
 #include "tqec_common.h"
@@ -1412,7 +1413,12 @@ static void par_memcpy(void *dst, const void *src, size_t n) {
   const size_t step = ((n / parts) + 63) & ~(size_t)63;
   for (size_t i = 1; i < parts; ++i) {
     const size_t o = i * step, m = o >= n ? 0 : (i + 1 == parts ? n - o : (o + step > n ? n - o : step));
-    if (m) th.emplace_back([=] { std::memcpy((char *)dst + o, (const char *)src + o, m); });
+    if (!m) continue;
+    try {
+      th.emplace_back([=] { std::memcpy((char *)dst + o, (const char *)src + o, m); });
+    } catch (const std::system_error &) {                        // no thread to be had: this part is copied here
+      std::memcpy((char *)dst + o, (const char *)src + o, m);
+    }
   }
   std::memcpy(dst, src, step < n ? step : n);
   for (auto &t : th) t.join();
@@ -1510,7 +1516,7 @@ static int decode_bytes(tqec_plan *p, const uint8_t *synd_bits, int64_t B, uint8
       const int64_t o = (c - 1) * nb, n = B - o < nb ? B - o : nb;
       const int dev = p->device;
       if (out_task.valid() && out_task.get() != 0) { tqec::set_error("decode_bytes: waiting for a result transfer failed"); return TQEC_ERR_CUDA; }
-      out_task = std::async(std::launch::async, [=]() -> int {
+      auto copy_out = [=]() -> int {
         if (cudaSetDevice(dev) != cudaSuccess || cudaEventSynchronize(p->ev_out[ps]) != cudaSuccess) return 1;
         if (mp) {
           par_memcpy(corr_bits + (size_t)o * nv, (uint8_t *)p->h_pin[2] + ps * sz3, (size_t)n * nv);
@@ -1520,7 +1526,12 @@ static int decode_bytes(tqec_plan *p, const uint8_t *synd_bits, int64_t B, uint8
           if (argmax_out) std::memcpy(argmax_out + o, (uint8_t *)p->h_pin[2] + ps * sz3, (size_t)n * 4);
         }
         return 0;
-      });
+      };
+      try {
+        out_task = std::async(std::launch::async, copy_out);
+      } catch (const std::system_error &) {                      // no thread to be had: copy on this one
+        if (copy_out() != 0) { tqec::set_error("decode_bytes: waiting for a result transfer failed"); return TQEC_ERR_CUDA; }
+      }
     }
   }
   if (out_task.valid() && out_task.get() != 0) { tqec::set_error("decode_bytes: waiting for a result transfer failed"); return TQEC_ERR_CUDA; }

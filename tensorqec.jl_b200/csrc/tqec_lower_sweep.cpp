@@ -9,6 +9,7 @@
 #include <map>
 #include <set>
 #include <stdexcept>
+#include <system_error>
 #include <thread>
 
 #include "tqec_lower.h"
@@ -176,7 +177,12 @@ static void parallel_ranges(size_t n, F &&fn) {
   std::vector<std::thread> th;
   for (size_t k = 1; k < parts; ++k) {
     const size_t lo = k * step, hi = std::min(n, lo + step);
-    if (lo < hi) th.emplace_back([&fn, lo, hi] { fn(lo, hi); });
+    if (lo >= hi) continue;
+    try {
+      th.emplace_back([&fn, lo, hi] { fn(lo, hi); });
+    } catch (const std::system_error &) {                        // no thread to be had: this range runs here
+      fn(lo, hi);
+    }
   }
   fn((size_t)0, std::min(n, step));
   for (auto &t : th) t.join();
