@@ -231,7 +231,7 @@ struct CompiledTNMMAPCUDA <: CompiledDecoder
     R::GF2; L::GF2; FIX::GF2
 end
 
-function compile(decoder::TNMMAP, problem::IndependentDepolarizingDecodingProblem; device::Integer = 0)
+function compile(decoder::TNMMAP, problem::IndependentDepolarizingDecodingProblem; device::Integer = 0, head_bits::Integer = 0)
     tanner = problem.tanner
     n = nq(tanner); nsx = ns(tanner.stgx); nsz = ns(tanner.stgz)
     lx, lz = logical_operator(tanner); k = size(lx, 1)
@@ -240,7 +240,7 @@ function compile(decoder::TNMMAP, problem::IndependentDepolarizingDecodingProble
     rows = vcat([(tanner.stgx.s2q[i] .+ n, :syn, i) for i in 1:nsx], [(tanner.stgz.s2q[i], :syn, nsx + i) for i in 1:nsz],
                 [(findall(x -> x.x, lx[i, :]) .+ n, :obs, i) for i in 1:k],      # iy order of tndecoder.jl:134
                 [(findall(x -> x.x, lz[i, :]), :obs, k + i) for i in 1:k])
-    plan = compile_plan(SUMPROD, 2n, nsx + nsz, 2k, factors, rows; device)
+    plan = compile_plan(SUMPROD, 2n, nsx + nsz, 2k, factors, rows; head_bits, device)   # head_bits = 0: the library's default (14)
     Hx = [a.x for a in tanner.stgx.H]; Hz = [a.x for a in tanner.stgz.H]
     R = falses(2n, nsx + nsz); R[1:n, nsx+1:end] = gf2_right_inverse(Hz); R[n+1:end, 1:nsx] = gf2_right_inverse(Hx)
     L = falses(2k, 2n); FIX = falses(2k, 2n)
