@@ -234,9 +234,9 @@ int tqec_lowered_destroy(tqec_lowered *lw);
 /* Tables of a lowering, for inspection and for tests (the Python lowering is kept as the oracle of the C++ one):
  * *data points into the handle (valid until it is destroyed), *count = number of elements. */
 enum {
-  TQEC_LW_META = 0,        /* int32[16]: kind (0 schedule, 1 schedule + sweep, 2 wide), n_steps, w_max, log2_scale,
+  TQEC_LW_META = 0,        /* int32[20]: kind (0 schedule, 1 schedule + sweep, 2 wide), n_steps, w_max, log2_scale,
                               sweep {W, sg, n_ss, n_head_bits, bp_words, head_steps, conflicts}, wide {n_pass, n_steps,
-                              w_cap, t_max}, table_bits                                                        */
+                              w_cap, t_max}, table_bits, n_obs, n_checks, n_vars, semiring                     */
   TQEC_LW_COST = 1,        /* double[2]: candidate evaluations per shot, HBM bytes per shot (wide)              */
   TQEC_LW_ORDER = 2,       /* int32: absorption order of the merged factors                                    */
   TQEC_LW_HDR = 3, TQEC_LW_INTS = 4, TQEC_LW_TABLES = 5 /* double */, TQEC_LW_OBS_SLOT = 6,
@@ -250,6 +250,13 @@ enum {
 };
 int tqec_lowered_get(const tqec_lowered *lw, int32_t what, const void **data, int64_t *count);
 int tqec_plan_from_lowered(const tqec_lowered *lw, int32_t device, tqec_plan **out);
+/* Plan serialisation: a lowered plan as one file (every table tqec_plan_from_lowered reads, behind a magic word and the
+ * library's table-format version), so that a host can lower once -- 0.7 s at d = 9 with the 14-bit head, 1.4 s for the
+ * d = 5 x 5 circuit-level DEM -- and create plans from the file afterwards (on any device / rank).  The reference has no
+ * counterpart (a CompiledTNMAP is rebuilt by compile(), src/decoding/tndecoder.jl:46-50).  A file of another table
+ * format, a truncated or a corrupt one is refused with TQEC_ERR_INVALID.                                           */
+int tqec_lowered_save(const tqec_lowered *lw, const char *path);
+int tqec_lowered_load(const char *path, tqec_lowered **out);
 /* = tqec_lower + tqec_plan_from_lowered + tqec_lowered_destroy */
 int tqec_plan_compile(const tqec_problem_desc *prob, tqec_plan **out);
 

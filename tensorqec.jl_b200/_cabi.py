@@ -26,6 +26,7 @@ EXPORTS = [
     "tqec_gf2_create", "tqec_gf2_destroy", "tqec_gf2_apply", "tqec_gf2_apply_dev",
     "tqec_logical_flags", "tqec_coset_rep", "tqec_sample_errors", "tqec_mc_run", "tqec_fp64_peak",
     "tqec_lower", "tqec_lowered_destroy", "tqec_lowered_get", "tqec_plan_from_lowered", "tqec_plan_compile",
+    "tqec_lowered_save", "tqec_lowered_load",
     "tqec_comm_unique_id", "tqec_comm_init", "tqec_comm_destroy", "tqec_comm_allreduce_counts",
     "tqec_decode_map_bytes", "tqec_decode_map_bytes2", "tqec_decode_marginal_bytes", "tqec_dmma_peak", "tqec_decode_marginal_log2",
     "tqec_table_create", "tqec_table_destroy", "tqec_table_decode", "tqec_bp_create", "tqec_bp_destroy", "tqec_bp_decode",
@@ -122,6 +123,8 @@ def lib():
     L.tqec_lowered_destroy.argtypes = [vp]
     L.tqec_lowered_get.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64)]
     L.tqec_plan_from_lowered.argtypes = [vp, i32, C.POINTER(vp)]
+    L.tqec_lowered_save.argtypes = [vp, C.c_char_p]
+    L.tqec_lowered_load.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.tqec_plan_compile.argtypes = [C.POINTER(ProblemDesc), C.POINTER(vp)]
     L.tqec_decode_marginal_log2.argtypes = [vp, vp, i64, vp, vp, vp]
     L.tqec_decode_map_bytes.argtypes = [vp, vp, i64, vp, vp]
@@ -217,6 +220,19 @@ class Lowered:
         check(lib().tqec_lower(C.byref(problem.desc), C.byref(h)))
         self.h = h
 
+    def save(self, path) -> None:
+        """Write the lowered plan to `path` (tqec_lowered_save): lower once, create plans from the file afterwards."""
+        check(lib().tqec_lowered_save(self.h, os.fsencode(path)))
+
+    @classmethod
+    def load(cls, path) -> "Lowered":
+        """A lowered plan from a file written by `save` (tqec_lowered_load); refused if the library's table format changed."""
+        self = cls.__new__(cls)
+        h = C.c_void_p()
+        check(lib().tqec_lowered_load(os.fsencode(path), C.byref(h)))
+        self.h = h
+        return self
+
     def get(self, what: int) -> np.ndarray:
         ptr, n = C.c_void_p(), C.c_int64(0)
         check(lib().tqec_lowered_get(self.h, what, C.byref(ptr), C.byref(n)))
@@ -267,6 +283,26 @@ class Plan:
         h = C.c_void_p()
         check(lib().tqec_plan_from_lowered(lw.h, d.device, C.byref(h)))
         lw.close()
+        self.h = h
+        return self
+
+    @classmethod
+    def from_lowered(cls, lw: "Lowered", device: int = 0):
+        """Plan from a lowered plan (e.g. `Lowered.load(path)`): no lowering, only the upload (tqec_plan_from_lowered)."""
+        require_device(device)
+        self = cls.__new__(cls)
+        self.sch = None
+        self.device = device
+        m = lw.meta
+        dims = lw.get(LW_META)
+        self.lowered = m
+        self.n_obs, n_checks, n_vars = int(dims[16]), int(dims[17]), int(dims[18])
+        self.nsw = max(1, (n_checks + 63) // 64)
+        self.ncw = max(1, (n_vars + 63) // 64)
+        self.order = [int(i) for i in lw.get(LW_ORDER)]
+        self.cost = [float(x) for x in lw.get(LW_COST)]
+        h = C.c_void_p()
+        check(lib().tqec_plan_from_lowered(lw.h, device, C.byref(h)))
         self.h = h
         return self
 

@@ -4,6 +4,7 @@
 //                         compiled shape; otherwise the fused schedule for the general kernels;
 //   sum-product (TNMMAP): schedule (+ sweep when it fits) up to 13 bits, global-memory passes beyond.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
@@ -137,7 +138,7 @@ static void lower_problem(const tqec_problem_desc *d, tqec_lowered &L) {
 }
 
 static void finish(tqec_lowered &L) {
-  L.meta.assign(16, 0);
+  L.meta.assign(20, 0);
   L.meta[0] = L.kind;
   if (L.kind == 2) {
     L.meta[1] = L.wd.n_steps; L.meta[2] = L.wd.w_peak; L.meta[3] = L.wd.log2_scale;
@@ -159,6 +160,7 @@ static void finish(tqec_lowered &L) {
     }
   }
   L.meta[15] = L.table_bits;
+  L.meta[16] = L.n_obs; L.meta[17] = L.n_checks; L.meta[18] = L.n_vars; L.meta[19] = L.semiring;
   if (L.obs32.empty()) L.obs32.push_back(0);
   if (L.head_bits32.empty()) L.head_bits32.push_back(0);
 }
@@ -257,6 +259,108 @@ extern "C" int tqec_plan_from_lowered(const tqec_lowered *L, int32_t device, tqe
     }
   }
   return tqec_plan_create(&d, out);
+}
+
+// ---- plan serialisation: a lowered plan as one file ----------------------------------------------------------------------------
+// Everything tqec_plan_from_lowered and tqec_lowered_get read, as tagged little-endian blobs behind a magic word and the
+// library's table-format version; a file written by another table format is refused, not reinterpreted.
+namespace {
+constexpr char LW_MAGIC[8] = {'T', 'Q', 'E', 'C', 'L', 'W', '0', '1'};
+constexpr int32_t LW_FORMAT = 3;   // bump whenever a table layout (records, headers, menu ids) changes
+
+struct Writer {
+  FILE *f;
+  bool ok = true;
+  void raw(const void *p, size_t n) { if (ok && n && std::fwrite(p, 1, n, f) != n) ok = false; }
+  template <typename T> void scalar(T v) { raw(&v, sizeof(T)); }
+  template <typename T> void vec(const std::vector<T> &v) { scalar<int64_t>((int64_t)v.size()); raw(v.data(), v.size() * sizeof(T)); }
+};
+struct Reader {
+  FILE *f;
+  bool ok = true;
+  void raw(void *p, size_t n) { if (ok && n && std::fread(p, 1, n, f) != n) ok = false; }
+  template <typename T> T scalar() { T v{}; raw(&v, sizeof(T)); return v; }
+  template <typename T> void vec(std::vector<T> &v) {
+    const int64_t n = scalar<int64_t>();
+    if (!ok || n < 0 || n > ((int64_t)1 << 34)) { ok = false; return; }
+    v.resize((size_t)n);
+    raw(v.data(), (size_t)n * sizeof(T));
+  }
+};
+}  // namespace
+
+extern "C" int tqec_lowered_save(const tqec_lowered *L, const char *path) {
+  TQEC_REQUIRE(L && path, "tqec_lowered_save: NULL argument");
+  FILE *f = std::fopen(path, "wb");
+  if (!f) { set_error("tqec_lowered_save: cannot open %s for writing", path); return TQEC_ERR_INVALID; }
+  Writer w{f};
+  w.raw(LW_MAGIC, 8);
+  w.scalar<int32_t>(LW_FORMAT);
+  for (int v : {L->kind, L->semiring, L->n_vars, L->n_checks, L->n_obs, L->table_bits, L->plan_flags}) w.scalar<int32_t>(v);
+  w.vec(L->meta); w.vec(L->order32); w.vec(L->obs32); w.vec(L->head_bits32); w.vec(L->out_index32); w.vec(L->cost); w.vec(L->bf_scale);
+  // schedule (kinds 0 and 1)
+  w.scalar<int32_t>((int32_t)L->sch.steps.size()); w.scalar<int32_t>(L->sch.w_max); w.scalar<int32_t>(L->sch.log2_scale);
+  w.vec(L->sch.hdr); w.vec(L->sch.ints); w.vec(L->sch.tables);
+  // sweep (kind 1)
+  for (int v : {L->sw.W, L->sw.sg, L->sw.head_steps, L->sw.n_ss, L->sw.bp_words, L->sw.conflicts}) w.scalar<int32_t>(v);
+  w.vec(L->sw.head_bits); w.vec(L->sw.head_state); w.vec(L->sw.head_cfg); w.vec(L->sw.out_index);
+  w.vec(L->sw.rec); w.vec(L->sw.tb); w.vec(L->sw.lanetab); w.vec(L->sw.tvals);
+  // global-memory passes (kind 2)
+  for (int v : {L->wd.w_cap, L->wd.w_peak, L->wd.t_max, L->wd.n_pass, L->wd.n_steps, L->wd.log2_scale, L->wd.bf_log2}) w.scalar<int32_t>(v);
+  w.scalar<double>(L->wd.bf_mant);
+  w.vec(L->wd.pass_hdr); w.vec(L->wd.step_hdr); w.vec(L->wd.ints); w.vec(L->wd.tables);
+  w.vec(L->wd.bf_off); w.vec(L->wd.bf_ints); w.vec(L->wd.bf_vals);
+  w.raw(LW_MAGIC, 8);                                            // trailer: a truncated file does not load
+  const bool closed = std::fclose(f) == 0;
+  if (!w.ok || !closed) { std::remove(path); set_error("tqec_lowered_save: write to %s failed", path); return TQEC_ERR_INVALID; }
+  return TQEC_OK;
+}
+
+extern "C" int tqec_lowered_load(const char *path, tqec_lowered **out) {
+  TQEC_REQUIRE(path && out, "tqec_lowered_load: NULL argument");
+  *out = nullptr;
+  FILE *f = std::fopen(path, "rb");
+  if (!f) { set_error("tqec_lowered_load: cannot open %s", path); return TQEC_ERR_INVALID; }
+  Reader r{f};
+  char magic[8] = {0};
+  r.raw(magic, 8);
+  const int32_t fmt = r.scalar<int32_t>();
+  if (!r.ok || std::memcmp(magic, LW_MAGIC, 8) != 0 || fmt != LW_FORMAT) {
+    std::fclose(f);
+    set_error("tqec_lowered_load: %s is not a lowered plan of this library (table format %d expected)", path, (int)LW_FORMAT);
+    return TQEC_ERR_INVALID;
+  }
+  tqec_lowered *L = new tqec_lowered();
+  for (int *v : {&L->kind, &L->semiring, &L->n_vars, &L->n_checks, &L->n_obs, &L->table_bits, &L->plan_flags}) *v = r.scalar<int32_t>();
+  r.vec(L->meta); r.vec(L->order32); r.vec(L->obs32); r.vec(L->head_bits32); r.vec(L->out_index32); r.vec(L->cost); r.vec(L->bf_scale);
+  const int32_t n_steps = r.scalar<int32_t>();
+  L->sch.w_max = r.scalar<int32_t>(); L->sch.log2_scale = r.scalar<int32_t>();
+  r.vec(L->sch.hdr); r.vec(L->sch.ints); r.vec(L->sch.tables);
+  for (int *v : {&L->sw.W, &L->sw.sg, &L->sw.head_steps, &L->sw.n_ss, &L->sw.bp_words, &L->sw.conflicts}) *v = r.scalar<int32_t>();
+  r.vec(L->sw.head_bits); r.vec(L->sw.head_state); r.vec(L->sw.head_cfg); r.vec(L->sw.out_index);
+  r.vec(L->sw.rec); r.vec(L->sw.tb); r.vec(L->sw.lanetab); r.vec(L->sw.tvals);
+  for (int *v : {&L->wd.w_cap, &L->wd.w_peak, &L->wd.t_max, &L->wd.n_pass, &L->wd.n_steps, &L->wd.log2_scale, &L->wd.bf_log2}) *v = r.scalar<int32_t>();
+  L->wd.bf_mant = r.scalar<double>();
+  r.vec(L->wd.pass_hdr); r.vec(L->wd.step_hdr); r.vec(L->wd.ints); r.vec(L->wd.tables);
+  r.vec(L->wd.bf_off); r.vec(L->wd.bf_ints); r.vec(L->wd.bf_vals);
+  char trailer[8] = {0};
+  r.raw(trailer, 8);
+  std::fclose(f);
+  const bool sane = r.ok && std::memcmp(trailer, LW_MAGIC, 8) == 0 && L->kind >= 0 && L->kind <= 2 && n_steps >= 0 && n_steps < (1 << 24) &&
+                    (L->semiring == TQEC_SEMIRING_MAXPLUS || L->semiring == TQEC_SEMIRING_SUMPROD) && L->n_vars >= 0 && L->n_checks >= 0 &&
+                    L->n_obs >= 0 && L->n_obs <= 16 && (int64_t)L->sch.hdr.size() >= (int64_t)n_steps * TQEC_HDR_INTS;
+  if (!sane) {
+    delete L;
+    set_error("tqec_lowered_load: %s is truncated or corrupt", path);
+    return TQEC_ERR_INVALID;
+  }
+  L->sch.steps.resize((size_t)n_steps);                          // only the count is read after the lowering
+  L->sch.semiring = L->sw.semiring = L->wd.semiring = L->semiring;
+  L->sch.n_vars = L->sw.n_vars = L->wd.n_vars = L->n_vars;
+  L->sch.n_checks = L->sw.n_checks = L->wd.n_checks = L->n_checks;
+  L->sch.n_obs = L->sw.n_obs = L->wd.n_obs = L->n_obs;
+  *out = L;
+  return TQEC_OK;
 }
 
 extern "C" int tqec_plan_compile(const tqec_problem_desc *prob, tqec_plan **out) {

@@ -711,6 +711,34 @@ def test_library_compile_equals_python_lowering(tq, d, monkeypatch):
     assert np.array_equal(logp, lp) and np.array_equal(tq.unpack_bits(corr, 2 * d * d), cfg)
 
 
+def test_plan_from_a_saved_lowering_decodes_identically(tq, tmp_path):
+    """tqec_lowered_save -> tqec_lowered_load -> tqec_plan_from_lowered: a plan created from the file decodes bit for bit like
+    the plan compiled in one go (TNMAP d = 7 on k_sweep, TNMMAP d = 5 marginals)."""
+    from tensorqec.jl_b200 import _cabi, decoding as D, schedule as S
+    t, em = _css_case(tq, tq.SurfaceCode(7, 7))
+    ex, ez, sx, sz = _syndromes(t, em, 5, 700)
+    gdp, _ = tq.reduce2general(t, em)
+    factors, checks = D._tnmap_graph(gdp)
+    prob = _cabi.Problem(factors, checks, S.MAXPLUS, gdp.tanner.nq, gdp.tanner.ns, 0)
+    direct = _cabi.Plan.compile(prob)
+    _cabi.Lowered(prob).save(tmp_path / "d7.tqlw")
+    loaded = _cabi.Plan.from_lowered(_cabi.Lowered.load(tmp_path / "d7.tqlw"))
+    assert loaded.query(_cabi.Q_SWEEP) == direct.query(_cabi.Q_SWEEP) == 1
+    words = tq.pack_bits(np.concatenate([sx, sz], axis=1))
+    c0, l0 = direct.decode_map(words)
+    c1, l1 = loaded.decode_map(words)
+    assert np.array_equal(c0, c1) and np.array_equal(l0, l1)
+    t5, em5 = _css_case(tq, tq.SurfaceCode(5, 5))
+    _, _, f5, ch5, dims, _, _, _ = D._tnmmap_css_graph(tq.get_problem(t5, em5))
+    prob5 = _cabi.Problem(f5, ch5, S.SUMPROD, dims[0], dims[1], dims[2], table_bits=-1)
+    _cabi.Lowered(prob5).save(tmp_path / "m5.tqlw")
+    a, b = _cabi.Plan.compile(prob5), _cabi.Plan.from_lowered(_cabi.Lowered.load(tmp_path / "m5.tqlw"))
+    _, _, sx5, sz5 = _syndromes(t5, em5, 6, 300)
+    w5 = tq.pack_bits(np.concatenate([sx5, sz5], axis=1))
+    ma, mb = a.decode_marginal(w5), b.decode_marginal(w5)
+    assert np.array_equal(ma[0], mb[0]) and np.array_equal(ma[1], mb[1])
+
+
 def test_library_communicator_single_rank(tq):
     """tqec_comm_* with one rank: the NCCL all-reduce inside the fused Monte-Carlo pipeline leaves the counters as they
     are, and the stand-alone all-reduce returns its input (the 2 / 4 / 8-rank case runs under torchrun in bench.py)."""

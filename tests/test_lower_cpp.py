@@ -170,3 +170,43 @@ def test_lowering_errors_are_reported():
         _cabi.Lowered(_cabi.Problem(f, [S.Check((0,), "syn", 0)], S.SUMPROD, 1, 1, 1))
     h = C.c_void_p()
     assert _cabi.lib().tqec_lower(None, C.byref(h)) == -1 and not h.value
+
+
+@pytest.mark.parametrize("case", ["tnmap_d7", "tnmmap_d5", "dem_wide", "steane"])
+def test_lowered_plan_round_trips_through_a_file(case, tmp_path):
+    """tqec_lowered_save / tqec_lowered_load: every table the plan is created from comes back identical (sweep plan with its
+    head tables, sum-product schedule, global-memory passes with butterfly blocks, a small general schedule); files that are
+    truncated, corrupt or not plans at all are refused."""
+    import os
+    from tensorqec.jl_b200._cabi import TqecError
+    if case == "tnmap_d7":
+        factors, checks, nq, ns = _tnmap_graph(tq.SurfaceCode(7, 7))
+        prob = _cabi.Problem(factors, checks, S.MAXPLUS, nq, ns, 0, head_bits=10)
+    elif case == "steane":
+        factors, checks, nq, ns = _tnmap_graph(tq.SteaneCode())
+        prob = _cabi.Problem(factors, checks, S.MAXPLUS, nq, ns, 0)
+    elif case == "tnmmap_d5":
+        t = tq.CSSTannerGraph(tq.SurfaceCode(5, 5))
+        _, _, factors, checks, dims, _, _, _ = D._tnmmap_css_graph(tq.get_problem(t, tq.iid_error(0.05, t)))
+        prob = _cabi.Problem(factors, checks, S.SUMPROD, dims[0], dims[1], dims[2])
+    else:
+        dem = tq.parse_dem_file(os.path.join(os.path.dirname(__file__), "golden", "surface_d3_r3_phenom.dem"))
+        factors, checks, dims = _dem_graph(dem)
+        prob = _cabi.Problem(factors, checks, S.SUMPROD, dims[0], dims[1], dims[2], flags=_cabi.COMPILE_FORCE_WIDE)
+    lw = _cabi.Lowered(prob)
+    path = tmp_path / "plan.tqlw"
+    lw.save(path)
+    back = _cabi.Lowered.load(path)
+    assert back.meta == lw.meta
+    for what, dt in [(w, _cabi._LW_DTYPE.get(w, np.int32)) for w in range(24)]:
+        a, b = lw.get(what), back.get(what)
+        assert a.dtype == b.dtype == np.dtype(dt) and _same(a, b), what
+    raw = path.read_bytes()
+    for name, blob in (("cut", raw[: len(raw) // 2]), ("tail", raw[:-3]), ("magic", b"NOTAPLAN" + raw[8:]),
+                       ("format", raw[:8] + (999).to_bytes(4, "little") + raw[12:]), ("empty", b"")):
+        bad = tmp_path / f"{name}.tqlw"
+        bad.write_bytes(blob)
+        with pytest.raises(TqecError):
+            _cabi.Lowered.load(bad)
+    with pytest.raises(TqecError):
+        _cabi.Lowered.load(tmp_path / "missing.tqlw")
