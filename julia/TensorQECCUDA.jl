@@ -76,6 +76,23 @@ function compile_plan(semiring, n_vars, n_checks, n_obs, factors, rows; order = 
     return p
 end
 
+"""
+    load_plan(path, n_vars, n_checks, n_obs; device = 0)
+
+Plan from a lowered plan that `tqec_lowered_save` wrote (a host lowers once with `tqec_lower`, stores the result and every
+rank or later session creates its plan from the file: no lowering, only the upload).
+"""
+function load_plan(path::AbstractString, n_vars, n_checks, n_obs; device = 0)
+    lref = Ref{Ptr{Cvoid}}(C_NULL); href = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:tqec_lowered_load, LIB), Cint, (Cstring, Ref{Ptr{Cvoid}}), path, lref))
+    rc = ccall((:tqec_plan_from_lowered, LIB), Cint, (Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}), lref[], device, href)
+    ccall((:tqec_lowered_destroy, LIB), Cint, (Ptr{Cvoid},), lref[])
+    check(rc)
+    p = Plan(href[], cld(max(n_checks, 1), 64), cld(max(n_vars, 1), 64), n_obs)
+    finalizer(x -> ccall((:tqec_plan_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), p)
+    return p
+end
+
 # ---- contraction tree -> absorption order ------------------------------------------------------------------------------
 # The reference lets OMEinsum choose a contraction tree (`optimize_code`, tndecoder.jl:48, 140-144, 213-217).  The
 # frontier schedule absorbs the prior tensors one at a time, so it takes the tree's LEAF ORDER: a depth-first walk
