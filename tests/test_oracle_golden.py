@@ -118,6 +118,24 @@ def test_mod2_and_bitmul(tq):
     assert int(w[0, 0]) & 1 == A[0, 0] and (int(w[0, 1]) >> 3) & 1 == A[0, 67]
 
 
+def test_integer_thresholds_decide_like_the_float_compare():
+    """The samplers compare the raw 53-bit draw with ceil(p * 2^53) instead of converting it to a double and comparing with p
+    (k_sample_depol / k_sample_errors, csrc/tqec_gf2.cu): the same decision for every draw, because u = bits * 2^-53 and
+    p * 2^53 are both exact.  Checked on random probabilities, on draws right at the threshold and on the corner values."""
+    import math
+    rng = np.random.default_rng(53)
+    ps = np.concatenate([rng.uniform(0, 1, 2000), rng.uniform(0, 1e-9, 200), [0.0, 1.0, 0.5, 2.0 ** -53, 1 - 2.0 ** -53, 0.05 / 3]])
+    for p in ps:
+        thr = min(math.ceil(min(p, 1.0) * 2.0 ** 53), 2 ** 53) if p > 0 else 0
+        near = [b for b in (thr - 2, thr - 1, thr, thr + 1, 0, 2 ** 53 - 1) if 0 <= b < 2 ** 53]
+        bits = np.array(near + list(rng.integers(0, 2 ** 53, 20)), dtype=np.uint64)
+        u = bits.astype(np.float64) * (1.0 / 9007199254740992.0)
+        assert np.array_equal(u < p, bits < np.uint64(thr)), p
+    # the sums of the depolarizing rule are rounded once, as doubles, before they become thresholds
+    px, py, pz = 0.1, 0.2, 0.3
+    assert math.ceil((px + py) * 2.0 ** 53) == math.ceil(float(np.float64(px) + np.float64(py)) * 2.0 ** 53)
+
+
 def test_syndrome_containers_validate_once(tq):
     """SimpleSyndrome / CSSSyndrome check their bits when they are built and hand `decode` marked arrays (no second pass over a
     batch); views keep the mark, anything computed from them is a plain array again and would be checked."""
